@@ -1,0 +1,253 @@
+/*
+ * tgx.h — C-ABI of the B200 batched trajectory-evaluation engine (libtgx.so).
+ *
+ * This is the drop-in boundary for ONE path of jrached/trajectory_generator_ros2: sampling the
+ * parametric trajectory classes Circle / Line / Figure8 (with their ramp-up / hold / ramp-down phases and
+ * the braking trajectory) into per-time-step setpoints.  Citations are file:line in the reference tree.
+ *
+ *   reference interface                                         replaced by
+ *   ----------------------------------------------------------  ---------------------------------------------
+ *   Trajectory::generateTraj          Trajectory.hpp:33-35       tgx_plan + tgx_eval      (tgx_generate_host)
+ *     Circle::generateTraj            Circle.cpp:30-94
+ *     Line::generateTraj              Line.cpp:31-89
+ *     Figure8::generateTraj           Figure8.cpp:30-94
+ *   create{Circle,Line,Figure8}Goal   Circle.cpp:96-130, Line.cpp:91-115, Figure8.cpp:96-128   (inside tgx_eval)
+ *   Trajectory::generateStopTraj      Trajectory.hpp:38-41       tgx_plan_stop + tgx_eval (tgx_stop_host)
+ *     Circle/Line/Figure8 overrides   Circle.cpp:132-169, Line.cpp:117-152, Figure8.cpp:130-167
+ *   Trajectory::trajectoryInsideBounds Trajectory.hpp:44-46      tgx_limits.box + TGX_ST_OUTSIDE_BOUNDS
+ *     Circle/Line/Figure8 overrides   Circle.cpp:171-179, Line.cpp:154-173, Figure8.cpp:169-177
+ *   index_msgs (phase announcements)  Circle.cpp:45,61-62,74,89  tgx_phases (keys + kinds; host formats text)
+ *   traj_goals_[pub_index_]           TrajectoryGenerator.cpp:557  sample k of the output planes
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Every function returns an int status (TGX_OK == 0) and
+ *     never throws, never calls exit(): the reference's exit(1) / RCLCPP_WARN paths become per-trajectory
+ *     status bits (tgx_status_bits).
+ *   - "d_" pointers are CUDA device pointers on the engine's device, "h_" pointers are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - Sample k of a trajectory is time k*dt (TrajectoryGenerator.cpp:557 walks the vector by index).
+ *   - An engine handle is bound to one GPU and is not thread-safe (the reference's objects are not either,
+ *     Trajectory.hpp:47).
+ *   - There is no CPU fallback: every entry point that computes samples runs CUDA kernels and fails with
+ *     TGX_ERR_CUDA if no device is usable.
+ */
+#ifndef TGX_H_
+#define TGX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGX_VERSION 100          /* 0.1.0 */
+#define TGX_MAX_VGOALS 8         /* inline capacity of v_goals per trajectory (default.yaml:42 uses 3) */
+#define TGX_NCHAN 14             /* numeric fields of one setpoint */
+#define TGX_MAX_PHASES (2 * TGX_MAX_VGOALS + 2)  /* index_msgs entries of one trajectory, upper bound */
+
+/* Trajectory class tag (TrajectoryGenerator.cpp:176-260 dispatches on the same three names). */
+enum tgx_type {
+    TGX_CIRCLE = 0,
+    TGX_LINE = 1,
+    TGX_FIGURE8 = 2
+};
+
+/* Channel order of the struct-of-arrays output: the numeric fields of snapstack_msgs2/Goal in the order
+ * create*Goal fills them (Circle.cpp:107-126). */
+enum tgx_channel {
+    TGX_PX = 0, TGX_PY, TGX_PZ,
+    TGX_VX, TGX_VY, TGX_VZ,
+    TGX_AX, TGX_AY, TGX_AZ,
+    TGX_JX, TGX_JY, TGX_JZ,
+    TGX_PSI, TGX_DPSI
+};
+
+/* Circle / Figure8 constructor arguments (Circle.hpp:30-31, Figure8.hpp:30-31). 13 doubles. */
+typedef struct tgx_orbit_params {
+    double r;                        /* radius, m */
+    double cx, cy;                   /* centre, m */
+    double t_traj;                   /* hold time per goal velocity, s */
+    double accel;                    /* ramp acceleration, m/s^2 */
+    double v_goals[TGX_MAX_VGOALS];  /* goal speeds, m/s; first n_vgoals are used */
+} tgx_orbit_params;
+
+/* Line constructor arguments (Line.hpp:30-31). 13 doubles. */
+typedef struct tgx_line_params {
+    double A[3];                     /* start point (z only enters |B-A| and the bounds test) */
+    double B[3];                     /* end point */
+    double a1;                       /* acceleration, m/s^2 (> 0) */
+    double a3;                       /* deceleration magnitude, m/s^2 (> 0) */
+    double v_goal;                   /* cruise speed = v_goals[0] (Line.cpp:43) */
+    double reserved[4];
+} tgx_line_params;
+
+/* One trajectory's parameters: exactly 128 bytes, the unit of the batch parameter array. */
+typedef struct tgx_params {
+    int32_t type;                    /* enum tgx_type */
+    int32_t n_vgoals;                /* orbit: 1..TGX_MAX_VGOALS; line: ignored */
+    double dt;                       /* Trajectory::dt_ = 1/pub_freq (TrajectoryGenerator.cpp:171-172) */
+    double alt;                      /* alt_: z of every sample */
+    union {
+        tgx_orbit_params orbit;      /* TGX_CIRCLE, TGX_FIGURE8 */
+        tgx_line_params line;        /* TGX_LINE */
+    } u;
+} tgx_params;
+
+/* Per-trajectory status bitmask. 0 = clean. */
+enum tgx_status_bits {
+    TGX_ST_VGOALS_NOT_INCREASING = 1u << 0, /* RCLCPP_WARN at Circle.cpp:57-59 / Figure8.cpp:57-59 (samples still produced) */
+    TGX_ST_FINAL_V_NONZERO       = 1u << 1, /* exit(1) at Circle.cpp:85-88 / Figure8.cpp:85-88 */
+    TGX_ST_LINE_END_NOT_B        = 1u << 2, /* exit(1) at Line.cpp:76-79 (end point > 0.05 m from B) */
+    TGX_ST_LINE_D2_NEGATIVE      = 1u << 3, /* Line.cpp:165-168: cruise segment length < 0 */
+    TGX_ST_OUTSIDE_BOUNDS        = 1u << 4, /* trajectoryInsideBounds() == false (only if a box was given) */
+    TGX_ST_BAD_PARAM             = 1u << 5, /* v<=0, accel<=0 (TrajectoryGenerator.cpp:184-195,268-277), dt<=0, r<=0,
+                                               n_vgoals out of range, unknown type, non-finite input: no samples */
+    TGX_ST_VMAX_EXCEEDED         = 1u << 6, /* max_k |v_k| > limits.v_max  (tgx_feasibility only) */
+    TGX_ST_AMAX_EXCEEDED         = 1u << 7, /* max_k |a_k| > limits.a_max  (tgx_feasibility only) */
+    TGX_ST_TOO_LONG              = 1u << 8, /* sample count would exceed the engine's max_samples guard (the reference
+                                               would loop for ever / exhaust memory): no samples */
+    TGX_ST_TRUNCATED             = 1u << 9  /* row capacity of the output layout < sample count: tail not written */
+};
+
+/* Status bits that mean "the reference would not have produced this trajectory". */
+#define TGX_ST_FATAL_MASK (TGX_ST_FINAL_V_NONZERO | TGX_ST_LINE_END_NOT_B | TGX_ST_BAD_PARAM | TGX_ST_TOO_LONG)
+
+/* Library return codes. */
+enum tgx_error {
+    TGX_OK = 0,
+    TGX_ERR_INVALID = 1,      /* NULL / negative / inconsistent argument */
+    TGX_ERR_CUDA = 2,         /* a CUDA runtime call failed; tgx_last_cuda_error() has the text */
+    TGX_ERR_ALIGNMENT = 3,    /* output layout not aligned for vector stores */
+    TGX_ERR_NO_PLAN = 4,      /* tgx_eval / tgx_feasibility before tgx_plan */
+    TGX_ERR_NOMEM = 5,        /* device or host allocation failed */
+    TGX_ERR_CAPACITY = 6      /* a caller-provided buffer is too small */
+};
+
+/* Room box + kinematic limits. Box follows trajectoryInsideBounds(xmin,xmax,ymin,ymax,zmin,zmax). */
+typedef struct tgx_limits {
+    double box[6];            /* xmin, xmax, ymin, ymax, zmin, zmax */
+    double v_max;             /* m/s   (used by tgx_feasibility) */
+    double a_max;             /* m/s^2 (used by tgx_feasibility) */
+    int32_t check_box;        /* 0: ignore box */
+    int32_t reserved;
+} tgx_limits;
+
+/* Where samples go: element (trajectory i, channel c, sample k) lives at
+ *     base[ (traj_offset ? traj_offset[i] : i*traj_stride) + c*chan_stride + k ]        (units: doubles)
+ * Plane-major:       chan_stride = n*row, traj_stride = row.
+ * Trajectory-major:  chan_stride = row,   traj_stride = 14*row.
+ * base must be 32-byte aligned and every stride/offset a multiple of 4 doubles (vector stores).
+ * Samples k >= capacity are not written (status TGX_ST_TRUNCATED). Padding k in [N_i, capacity) is never
+ * written either. */
+typedef struct tgx_layout {
+    double* d_base;
+    int64_t traj_stride;
+    int64_t chan_stride;
+    const int64_t* d_traj_offset;   /* optional device array [n]; overrides traj_stride */
+    int64_t capacity;               /* max samples per trajectory that fit */
+    uint32_t channel_mask;          /* bit c set = write channel c; 0 means all 14 */
+    uint32_t reserved;
+} tgx_layout;
+
+/* index_msgs of one trajectory: the reference stores announcement strings keyed by sample index
+ * (Circle.cpp:45,61-62,74,89).  The engine returns (key, kind, value) triples in emission order; a later
+ * entry with the same key overwrites an earlier one, as operator[] does in the reference. */
+enum tgx_phase_kind {
+    TGX_PH_ACCEL_TO = 0,     /* "<Shape> traj: accelerating to <value> m/s"                              */
+    TGX_PH_REACHED = 1,      /* "<Shape> traj: reached <value> m/s, keeping constant v for <value2> s"   */
+    TGX_PH_DECEL = 2,        /* "<Shape> traj: decelerating to 0 m/s"                                    */
+    TGX_PH_STOPPED = 3,      /* "<Shape> traj: stopped"                                                  */
+    TGX_PH_PRESSED_END = 4   /* "<Shape> traj: pressed END, decelerating to 0 m/s" (stop trajectories)   */
+};
+
+typedef struct tgx_phases {
+    int32_t n;
+    int32_t key[TGX_MAX_PHASES];
+    int32_t kind[TGX_MAX_PHASES];
+    double value[TGX_MAX_PHASES];    /* v_goal for ACCEL_TO / REACHED */
+    double value2[TGX_MAX_PHASES];   /* hold time for REACHED (t_traj, or Line's t2) */
+} tgx_phases;
+
+typedef struct tgx_engine tgx_engine;
+
+/* ---- life cycle ---------------------------------------------------------------------------------- */
+int tgx_version(void);
+const char* tgx_strerror(int code);
+const char* tgx_last_cuda_error(void);            /* text of the last CUDA failure on this thread */
+int tgx_create(tgx_engine** out, int device);     /* binds to `device`; TGX_ERR_CUDA if there is none */
+int tgx_destroy(tgx_engine* e);
+/* Guard against parameters for which the reference never terminates. Default 1<<24 samples. */
+int tgx_set_max_samples(tgx_engine* e, int64_t max_samples);
+/* Bytes of device scratch currently held by the engine (plan tables). */
+int64_t tgx_scratch_bytes(const tgx_engine* e);
+
+/* ---- counting pass: Trajectory::generateTraj's loop structure only -------------------------------- */
+/* Replays the reference's scalar recurrences (v <- min(v + a*dt, v_goal), cur += dt, ...) with
+ * non-contracted IEEE fp64 operations, one thread per trajectory, and writes the exact sample count and
+ * status of each.  No samples are produced. d_counts / d_status may be NULL. */
+int tgx_count(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits,
+              int32_t* d_counts, uint32_t* d_status, void* stream);
+
+/* ---- planning pass: counts + the segment / tile tables tgx_eval consumes --------------------------- */
+/* Must precede tgx_eval / tgx_feasibility. Keeps device scratch inside the engine (the "current plan").
+ * Synchronises `stream` once (to size the scratch). d_counts / d_status / d_phases may be NULL.
+ * *total_samples (host, may be NULL) receives sum_i N_i. */
+int tgx_plan(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits,
+             int32_t* d_counts, uint32_t* d_status, tgx_phases* d_phases, int64_t* total_samples,
+             void* stream);
+
+/* Braking plan (Trajectory::generateStopTraj): trajectory i brakes from the setpoint d_from[i*14 .. i*14+13]
+ * (channel order tgx_channel; the reference reads goals[pub_index], Circle.cpp:140-143, Line.cpp:124-127).
+ * The result is a new current plan whose samples are the braking trajectory (sample 0 = first braking
+ * step, as the reference replaces the vector and resets pub_index to 0, Circle.cpp:162-164). */
+int tgx_plan_stop(tgx_engine* e, const tgx_params* d_params, int64_t n, const double* d_from,
+                  int32_t* d_counts, uint32_t* d_status, tgx_phases* d_phases, int64_t* total_samples,
+                  void* stream);
+
+/* ---- evaluation: create*Goal for every (trajectory, k) of the current plan ------------------------- */
+/* One thread per pair of adjacent samples, fp64, SoA planes written with vector stores.
+ * If d_max_v / d_max_a are non-NULL the per-trajectory maxima of |v_k| and |a_k| (Euclidean norm of the
+ * written x,y,z components) are reduced in the same pass. */
+int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_max_a, void* stream);
+
+/* ---- feasibility only: no sample stores ------------------------------------------------------------ */
+/* Evaluates every sample of the current plan, reduces max |v|, max |a| per trajectory and sets
+ * d_flags[i] = 1 iff max_v <= v_max && max_a <= a_max && status has no bit set (incl. OUTSIDE_BOUNDS).
+ * d_status (may be NULL) is updated in place with VMAX/AMAX bits on top of the plan's status. */
+int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, double* d_max_v,
+                    double* d_max_a, uint32_t* d_status, void* stream);
+
+/* ---- host-buffer convenience calls (what the drop-in C++ classes use) ------------------------------ */
+/* Counts for host-resident parameters (H2D, tgx_count, D2H). */
+int tgx_count_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                   int32_t* h_counts, uint32_t* h_status);
+
+/* Full generateTraj for host-resident parameters into a host buffer with the layout
+ * h_out[(i*14 + c)*capacity + k] (trajectory-major rows of `capacity` doubles).  Runs in chunks of
+ * trajectories so that device staging stays bounded, overlapping D2H copies with evaluation.
+ * h_phases may be NULL. */
+int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                      double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
+                      tgx_phases* h_phases);
+
+/* Full generateStopTraj: h_from[i*14..] is the setpoint being braked from. Same output layout. */
+int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const double* h_from,
+                  double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
+                  tgx_phases* h_phases);
+
+/* ---- sharding helper (multi-GPU: one process per GPU, contiguous block partition, no collective) ---- */
+/* Rank `rank` of `world` owns trajectories [*lo, *hi) of a batch of n. */
+int tgx_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+
+/* ---- introspection used by bench.py ---------------------------------------------------------------- */
+/* Number of CUDA kernels this library has launched on this engine since creation. */
+int64_t tgx_launch_count(const tgx_engine* e);
+/* Tiles / segments of the current plan (0 if none). */
+int64_t tgx_plan_tiles(const tgx_engine* e);
+int64_t tgx_plan_segments(const tgx_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* TGX_H_ */

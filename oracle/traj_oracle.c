@@ -1,0 +1,527 @@
+/*
+ * traj_oracle.c — CPU ORACLE (test infrastructure, NOT product code; see traj_oracle.h).
+ *
+ * Plain-C restatement of the reference samplers.  Every function cites the reference file:line it
+ * follows.  Arithmetic is written in the reference's own operation order (C left-to-right evaluation,
+ * std::min / std::max argument order, pow() calls kept as pow()) so that, built with
+ * -O2 -ffp-contract=off against the same libm, it is bit-identical to the reference's output.
+ */
+#define _GNU_SOURCE
+#include "traj_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI_2
+#define M_PI_2 1.57079632679489661923
+#endif
+
+/* ---- sample sink ------------------------------------------------------------------------------------ */
+
+typedef struct {
+    double* out;          /* may be NULL */
+    int64_t chan_stride;
+    int64_t cap;
+    int64_t n;            /* samples pushed so far (== goals.size()) */
+    double last[TGX_NCHAN]; /* goals.back() */
+} sink_t;
+
+static void sink_push(sink_t* s, const double g[TGX_NCHAN]) {
+    if (s->out && s->n < s->cap) {
+        for (int c = 0; c < TGX_NCHAN; ++c) s->out[c * s->chan_stride + s->n] = g[c];
+    }
+    memcpy(s->last, g, sizeof(s->last));
+    s->n += 1;
+}
+
+static void phase_add(tgx_phases* ph, int64_t key, int kind, double value, double value2) {
+    if (!ph || ph->n >= TGX_MAX_PHASES) return;
+    ph->key[ph->n] = (int32_t)key;
+    ph->kind[ph->n] = kind;
+    ph->value[ph->n] = value;
+    ph->value2[ph->n] = value2;
+    ph->n += 1;
+}
+
+/* std::min(a, b) / std::max(a, b) exactly as libstdc++ defines them. */
+static double std_min(double a, double b) { return (b < a) ? b : a; }
+static double std_max(double a, double b) { return (a < b) ? b : a; }
+
+/* ---- create*Goal ------------------------------------------------------------------------------------ */
+
+/* Circle::createCircleGoal, Circle.cpp:96-130 (accel is accepted and unused, :113-114). */
+static void circle_goal(const tgx_params* p, double v, double theta, double g[TGX_NCHAN]) {
+    const tgx_orbit_params* o = &p->u.orbit;
+    double s = sin(theta);
+    double c = cos(theta);
+    double v2r = pow(v, 2) / o->r;
+    double v3r2 = pow(v, 3) / pow(o->r, 2);
+    double omega = v / o->r;
+    g[TGX_PX] = o->cx + o->r * c;
+    g[TGX_PY] = o->cy + o->r * s;
+    g[TGX_PZ] = p->alt;
+    g[TGX_VX] = -v * s;
+    g[TGX_VY] = v * c;
+    g[TGX_VZ] = 0;
+    g[TGX_AX] = -v2r * c;
+    g[TGX_AY] = -v2r * s;
+    g[TGX_AZ] = 0;
+    g[TGX_JX] = v3r2 * s;
+    g[TGX_JY] = -v3r2 * c;
+    g[TGX_JZ] = 0;
+    g[TGX_PSI] = theta + M_PI_2;
+    g[TGX_DPSI] = omega;
+}
+
+/* Figure8::createFigure8Goal, Figure8.cpp:96-128. */
+static void figure8_goal(const tgx_params* p, double v, double theta, double g[TGX_NCHAN]) {
+    const tgx_orbit_params* o = &p->u.orbit;
+    double s = sin(theta);
+    double c = cos(theta);
+    double sc = s * c;
+    double omega = v / o->r;
+    g[TGX_PX] = o->cx + o->r * s;
+    g[TGX_PY] = o->cy + o->r * s * c;
+    g[TGX_PZ] = p->alt;
+    g[TGX_VX] = o->r * omega * c;
+    g[TGX_VY] = o->r * omega * (c * c - s * s);
+    g[TGX_VZ] = 0;
+    g[TGX_AX] = -o->r * omega * omega * s;
+    g[TGX_AY] = -4 * o->r * omega * omega * sc;
+    g[TGX_AZ] = 0;
+    g[TGX_JX] = 0;
+    g[TGX_JY] = 0;
+    g[TGX_JZ] = 0;
+    g[TGX_PSI] = atan2(g[TGX_VY], g[TGX_VX]);
+    g[TGX_DPSI] = omega;
+}
+
+/* Line::createLineGoal, Line.cpp:91-115 (sin/cos re-evaluated per call on the same theta). */
+static void line_goal(const tgx_params* p, double last_x, double last_y, double v, double accel,
+                      double theta, double g[TGX_NCHAN]) {
+    double s = sin(theta);
+    double c = cos(theta);
+    g[TGX_PX] = last_x + v * c * p->dt;
+    g[TGX_PY] = last_y + v * s * p->dt;
+    g[TGX_PZ] = p->alt;
+    g[TGX_VX] = v * c;
+    g[TGX_VY] = v * s;
+    g[TGX_VZ] = 0;
+    g[TGX_AX] = accel * c;
+    g[TGX_AY] = accel * s;
+    g[TGX_AZ] = 0;
+    g[TGX_JX] = 0;
+    g[TGX_JY] = 0;
+    g[TGX_JZ] = 0;
+    g[TGX_PSI] = theta;
+    g[TGX_DPSI] = 0;
+}
+
+static void orbit_goal(const tgx_params* p, double v, double theta, double g[TGX_NCHAN]) {
+    if (p->type == TGX_FIGURE8) figure8_goal(p, v, theta, g);
+    else circle_goal(p, v, theta, g);
+}
+
+/* ---- parameter validation ----------------------------------------------------------------------------
+ * Mirrors the node-side checks that precede construction (TrajectoryGenerator.cpp:184-195 "All velocities
+ * must be > 0", "accel must be > 0"; :268-277 for Line) plus the conditions under which the reference's
+ * loops cannot terminate or divide by zero (dt <= 0, r <= 0, non-finite input). */
+static int finite_pos(double x) { return isfinite(x) && x > 0.0; }
+
+static int params_ok(const tgx_params* p) {
+    if (!finite_pos(p->dt) || !isfinite(p->alt)) return 0;
+    if (p->type == TGX_CIRCLE || p->type == TGX_FIGURE8) {
+        const tgx_orbit_params* o = &p->u.orbit;
+        if (p->n_vgoals < 1 || p->n_vgoals > TGX_MAX_VGOALS) return 0;
+        if (!finite_pos(o->r) || !finite_pos(o->accel)) return 0;
+        if (!isfinite(o->cx) || !isfinite(o->cy) || !isfinite(o->t_traj)) return 0;
+        for (int i = 0; i < p->n_vgoals; ++i)
+            if (!finite_pos(o->v_goals[i])) return 0;
+        return 1;
+    }
+    if (p->type == TGX_LINE) {
+        const tgx_line_params* l = &p->u.line;
+        for (int i = 0; i < 3; ++i)
+            if (!isfinite(l->A[i]) || !isfinite(l->B[i])) return 0;
+        return finite_pos(l->v_goal) && finite_pos(l->a1) && finite_pos(l->a3);
+    }
+    return 0;
+}
+
+/* ---- Line helpers ----------------------------------------------------------------------------------- */
+
+/* (B_ - A_).norm(): Eigen's 3-element reduction is x^2 + (y^2 + z^2), then sqrt (Line.cpp:157,176). */
+static double line_length(const tgx_line_params* l) {
+    double dx = l->B[0] - l->A[0];
+    double dy = l->B[1] - l->A[1];
+    double dz = l->B[2] - l->A[2];
+    return sqrt(dx * dx + (dy * dy + dz * dz));
+}
+
+/* Line::get_d2, Line.cpp:175-181. */
+double orc_line_d2(const tgx_params* p) {
+    const tgx_line_params* l = &p->u.line;
+    double d = line_length(l);
+    double vg = l->v_goal;
+    double d1 = 0.5 * vg * vg / l->a1;
+    double d3 = 0.5 * vg * vg / l->a3;
+    return d - d1 - d3;
+}
+
+/* ---- generateTraj ----------------------------------------------------------------------------------- */
+
+/* Circle::generateTraj, Circle.cpp:30-94 == Figure8::generateTraj, Figure8.cpp:30-94. */
+static int64_t orbit_generate(const tgx_params* p, sink_t* sk, uint32_t* status, tgx_phases* ph,
+                              int64_t max_samples) {
+    const tgx_orbit_params* o = &p->u.orbit;
+    double g[TGX_NCHAN];
+    double theta = 0;
+    double v = 0;
+    orbit_goal(p, v, theta, g);                       /* :41 */
+    sink_push(sk, g);
+    for (int i = 0; i < p->n_vgoals; ++i) {           /* :43 */
+        double v_goal = o->v_goals[i];
+        phase_add(ph, sk->n - 1, TGX_PH_ACCEL_TO, v_goal, 0.0);   /* :45 */
+        while (v < v_goal) {                          /* :47 */
+            double v_new = std_min(v + o->accel * p->dt, v_goal);
+            if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+            v = v_new;
+            double omega = v / o->r;
+            theta += omega * p->dt;
+            orbit_goal(p, v, theta, g);
+            sink_push(sk, g);
+        }
+        if (fabs(v - v_goal) > 0.001) *status |= TGX_ST_VGOALS_NOT_INCREASING;   /* :57-59 */
+        phase_add(ph, sk->n - 1, TGX_PH_REACHED, v_goal, o->t_traj);             /* :61-62 */
+        double current_t_traj = 0;
+        while (current_t_traj < o->t_traj) {          /* :63 */
+            if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+            double omega = v / o->r;
+            theta += omega * p->dt;
+            orbit_goal(p, v, theta, g);
+            sink_push(sk, g);
+            double t_new = current_t_traj + p->dt;
+            if (t_new == current_t_traj) { *status |= TGX_ST_TOO_LONG; return -1; }
+            current_t_traj = t_new;
+        }
+    }
+    phase_add(ph, sk->n - 1, TGX_PH_DECEL, 0.0, 0.0); /* :74 */
+    while (v > 0) {                                   /* :75 */
+        double v_new = std_max(v - o->accel * p->dt, 0.0);
+        if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        v = v_new;
+        double omega = v / o->r;
+        theta += omega * p->dt;
+        orbit_goal(p, v, theta, g);
+        sink_push(sk, g);
+    }
+    if (fabs(v) > 0.001) *status |= TGX_ST_FINAL_V_NONZERO;       /* :85-88 (exit(1) in the reference) */
+    phase_add(ph, sk->n - 1, TGX_PH_STOPPED, 0.0, 0.0);           /* :89 */
+    return sk->n;
+}
+
+/* Line::Line (theta_, Line.cpp:24) + Line::generateTraj, Line.cpp:31-89. */
+static int64_t line_generate(const tgx_params* p, sink_t* sk, uint32_t* status, tgx_phases* ph,
+                             int64_t max_samples) {
+    const tgx_line_params* l = &p->u.line;
+    double g[TGX_NCHAN];
+    double theta = atan2(l->B[1] - l->A[1], l->B[0] - l->A[0]);   /* :24 */
+    double v = 0;
+    line_goal(p, l->A[0], l->A[1], v, 0, theta, g);   /* :40 */
+    sink_push(sk, g);
+    double v_goal = l->v_goal;                        /* :43 */
+    phase_add(ph, sk->n - 1, TGX_PH_ACCEL_TO, v_goal, 0.0);
+    while (v < v_goal) {                              /* :46 */
+        double v_new = std_min(v + l->a1 * p->dt, v_goal);
+        if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        v = v_new;
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, l->a1, theta, g);
+        sink_push(sk, g);
+    }
+    double d2 = orc_line_d2(p);
+    if (d2 < 0) *status |= TGX_ST_LINE_D2_NEGATIVE;   /* the condition Line.cpp:165 reports */
+    double t2 = d2 / v_goal;                          /* :53 */
+    phase_add(ph, sk->n - 1, TGX_PH_REACHED, v_goal, t2);
+    double current_t_traj = 0;
+    while (current_t_traj < t2) {                     /* :57 */
+        if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, 0, theta, g);
+        sink_push(sk, g);
+        double t_new = current_t_traj + p->dt;
+        if (t_new == current_t_traj) { *status |= TGX_ST_TOO_LONG; return -1; }
+        current_t_traj = t_new;
+    }
+    phase_add(ph, sk->n - 1, TGX_PH_DECEL, 0.0, 0.0); /* :64 */
+    while (v > 0) {                                   /* :65 */
+        double v_new = std_max(v - l->a3 * p->dt, 0.0);
+        if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        v = v_new;
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, -l->a3, theta, g);
+        sink_push(sk, g);
+    }
+    double thresh = 0.05;                             /* :71-79 (exit(1) in the reference) */
+    if (fabs(l->B[0] - sk->last[TGX_PX]) > thresh || fabs(l->B[1] - sk->last[TGX_PY]) > thresh)
+        *status |= TGX_ST_LINE_END_NOT_B;
+    /* Force last goal pos to be equal to B, :81-82 */
+    sk->last[TGX_PX] = l->B[0];
+    sk->last[TGX_PY] = l->B[1];
+    if (sk->out && sk->n - 1 < sk->cap) {
+        sk->out[TGX_PX * sk->chan_stride + (sk->n - 1)] = l->B[0];
+        sk->out[TGX_PY * sk->chan_stride + (sk->n - 1)] = l->B[1];
+    }
+    phase_add(ph, sk->n - 1, TGX_PH_STOPPED, 0.0, 0.0);           /* :84 */
+    return sk->n;
+}
+
+int64_t orc_generate(const tgx_params* p, double* out, int64_t chan_stride, int64_t cap,
+                     uint32_t* status, tgx_phases* ph, int64_t max_samples) {
+    uint32_t st = 0;
+    int64_t n;
+    sink_t sk = {out, chan_stride, cap, 0, {0}};
+    if (ph) ph->n = 0;
+    if (!params_ok(p)) {
+        st |= TGX_ST_BAD_PARAM;
+        n = -1;
+    } else if (p->type == TGX_LINE) {
+        n = line_generate(p, &sk, &st, ph, max_samples);
+    } else {
+        n = orbit_generate(p, &sk, &st, ph, max_samples);
+    }
+    if (n < 0 && ph) ph->n = 0;
+    if (n > cap && out) st |= TGX_ST_TRUNCATED;
+    if (status) *status = st;
+    return n;
+}
+
+/* ---- generateStopTraj ------------------------------------------------------------------------------- */
+
+int64_t orc_stop(const tgx_params* p, const double* from, double* out, int64_t chan_stride, int64_t cap,
+                 uint32_t* status, tgx_phases* ph, int64_t max_samples) {
+    uint32_t st = 0;
+    sink_t sk = {out, chan_stride, cap, 0, {0}};
+    double g[TGX_NCHAN];
+    if (ph) ph->n = 0;
+    if (!params_ok(p)) {
+        if (status) *status = TGX_ST_BAD_PARAM;
+        return -1;
+    }
+    /* 2D current (goal) vel: Circle.cpp:140-141, Line.cpp:124-125, Figure8.cpp:138-139 */
+    double v = sqrt(pow(from[TGX_VX], 2) + pow(from[TGX_VY], 2));
+    if (p->type == TGX_LINE) {
+        /* Line::generateStopTraj, Line.cpp:117-152 */
+        const tgx_line_params* l = &p->u.line;
+        double theta = atan2(from[TGX_VY], from[TGX_VX]);         /* :126-127 */
+        phase_add(ph, 0, TGX_PH_PRESSED_END, 0.0, 0.0);           /* :132 */
+        v = std_max(v - l->a3 * p->dt, 0.0);                      /* :133 */
+        line_goal(p, from[TGX_PX], from[TGX_PY], v, -l->a3, theta, g);
+        sink_push(&sk, g);
+        while (v > 0) {                                           /* :136 */
+            double v_new = std_max(v - l->a3 * p->dt, 0.0);
+            if (v_new == v || sk.n >= max_samples) { st |= TGX_ST_TOO_LONG; break; }
+            v = v_new;
+            line_goal(p, sk.last[TGX_PX], sk.last[TGX_PY], v, -l->a3, theta, g);
+            sink_push(&sk, g);
+        }
+    } else {
+        /* Circle::generateStopTraj, Circle.cpp:132-169; Figure8::generateStopTraj, Figure8.cpp:130-167
+         * (Figure8 recovers theta with the circle's atan2(p - c), :140-141). */
+        const tgx_orbit_params* o = &p->u.orbit;
+        double theta = atan2(from[TGX_PY] - o->cy, from[TGX_PX] - o->cx);
+        phase_add(ph, 0, TGX_PH_PRESSED_END, 0.0, 0.0);           /* :148 */
+        while (v > 0) {                                           /* :150 */
+            double v_new = std_max(v - o->accel * p->dt, 0.0);
+            if (v_new == v || sk.n >= max_samples) { st |= TGX_ST_TOO_LONG; break; }
+            v = v_new;
+            double omega = v / o->r;
+            theta += omega * p->dt;
+            orbit_goal(p, v, theta, g);
+            sink_push(&sk, g);
+        }
+    }
+    if (st & TGX_ST_TOO_LONG) {
+        if (ph) ph->n = 0;
+        if (status) *status = st;
+        return -1;
+    }
+    /* index_msgs_tmp[goals_tmp.size() - 1]: size_t(0) - 1 converts to int key -1 when nothing was pushed. */
+    phase_add(ph, sk.n - 1, TGX_PH_STOPPED, 0.0, 0.0);
+    if (sk.n > cap && out) st |= TGX_ST_TRUNCATED;
+    if (status) *status = st;
+    return sk.n;
+}
+
+/* ---- trajectoryInsideBounds ------------------------------------------------------------------------- */
+
+/* Trajectory::isPointInsideBounds, Trajectory.hpp:50-57 (closed intervals). */
+static int point_inside(const double box[6], double x, double y, double z) {
+    if (x < box[0] || x > box[1]) return 0;
+    if (y < box[2] || y > box[3]) return 0;
+    if (z < box[4] || z > box[5]) return 0;
+    return 1;
+}
+
+int orc_inside_bounds(const tgx_params* p, const double box[6]) {
+    if (p->type == TGX_LINE) {
+        /* Line::trajectoryInsideBounds, Line.cpp:154-173 */
+        const tgx_line_params* l = &p->u.line;
+        if (orc_line_d2(p) < 0) return 0;
+        return point_inside(box, l->A[0], l->A[1], l->A[2]) && point_inside(box, l->B[0], l->B[1], l->B[2]);
+    }
+    /* Circle.cpp:171-179, Figure8.cpp:169-177 */
+    const tgx_orbit_params* o = &p->u.orbit;
+    return point_inside(box, o->cx - o->r, o->cy - o->r, p->alt) &&
+           point_inside(box, o->cx + o->r, o->cy + o->r, p->alt);
+}
+
+/* ---- batch drivers ---------------------------------------------------------------------------------- */
+
+typedef struct {
+    int mode;                 /* 0 generate, 1 feasibility, 2 timing */
+    const tgx_params* p;
+    int64_t lo, hi;
+    double* out;
+    int64_t traj_stride, chan_stride, cap;
+    int32_t* counts;
+    uint32_t* status;
+    const tgx_limits* limits;
+    uint8_t* flags;
+    double* max_v;
+    double* max_a;
+    int64_t max_samples;
+    int64_t total;
+    double checksum;
+} job_t;
+
+static void reduce_norms(const double* row, int64_t stride, int64_t n, double* mv, double* ma) {
+    double bv = 0.0, ba = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+        double vx = row[TGX_VX * stride + k], vy = row[TGX_VY * stride + k], vz = row[TGX_VZ * stride + k];
+        double ax = row[TGX_AX * stride + k], ay = row[TGX_AY * stride + k], az = row[TGX_AZ * stride + k];
+        double nv = sqrt(vx * vx + vy * vy + vz * vz);
+        double na = sqrt(ax * ax + ay * ay + az * az);
+        if (nv > bv) bv = nv;
+        if (na > ba) ba = na;
+    }
+    *mv = bv;
+    *ma = ba;
+}
+
+static void* job_run(void* arg) {
+    job_t* j = (job_t*)arg;
+    double* scratch = NULL;
+    int64_t scratch_cap = 0;
+    j->total = 0;
+    j->checksum = 0.0;
+    for (int64_t i = j->lo; i < j->hi; ++i) {
+        uint32_t st = 0;
+        int64_t n;
+        if (j->mode == 0) {
+            double* dst = j->out ? j->out + i * j->traj_stride : NULL;
+            n = orc_generate(&j->p[i], dst, j->chan_stride, j->cap, &st, NULL, j->max_samples);
+        } else {
+            /* count first so the scratch row is large enough, then generate into it */
+            n = orc_generate(&j->p[i], NULL, 0, 0, &st, NULL, j->max_samples);
+            if (n > 0) {
+                if (n > scratch_cap) {
+                    free(scratch);
+                    scratch_cap = n + 1024;
+                    scratch = (double*)malloc((size_t)scratch_cap * TGX_NCHAN * sizeof(double));
+                    if (!scratch) { scratch_cap = 0; n = -1; }
+                }
+                if (n > 0) {
+                    st = 0;
+                    n = orc_generate(&j->p[i], scratch, scratch_cap, scratch_cap, &st, NULL, j->max_samples);
+                }
+            }
+            if (j->mode == 1) {
+                double mv = 0.0, ma = 0.0;
+                if (n > 0) reduce_norms(scratch, scratch_cap, n, &mv, &ma);
+                if (j->limits && j->limits->check_box && !(st & TGX_ST_BAD_PARAM) &&
+                    !orc_inside_bounds(&j->p[i], j->limits->box))
+                    st |= TGX_ST_OUTSIDE_BOUNDS;
+                if (j->limits && mv > j->limits->v_max) st |= TGX_ST_VMAX_EXCEEDED;
+                if (j->limits && ma > j->limits->a_max) st |= TGX_ST_AMAX_EXCEEDED;
+                if (j->max_v) j->max_v[i] = mv;
+                if (j->max_a) j->max_a[i] = ma;
+                if (j->flags) j->flags[i] = (st == 0) ? 1 : 0;
+            } else if (n > 0) {
+                j->checksum += scratch[TGX_PX * scratch_cap + (n - 1)] + scratch[TGX_PSI * scratch_cap + n / 2];
+            }
+        }
+        if (j->counts) j->counts[i] = (int32_t)(n < 0 ? 0 : n);
+        if (j->status) j->status[i] = st;
+        if (n > 0) j->total += n;
+    }
+    free(scratch);
+    return NULL;
+}
+
+static int64_t run_jobs(job_t* proto, int64_t n, int nthreads, double* checksum) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 1024) nthreads = 1024;
+    if ((int64_t)nthreads > n) nthreads = (int)(n > 0 ? n : 1);
+    job_t* jobs = (job_t*)calloc((size_t)nthreads, sizeof(job_t));
+    pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+    if (!jobs || !th) { free(jobs); free(th); return -1; }
+    for (int t = 0; t < nthreads; ++t) {
+        jobs[t] = *proto;
+        jobs[t].lo = n * t / nthreads;
+        jobs[t].hi = n * (t + 1) / nthreads;
+    }
+    for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, job_run, &jobs[t]);
+    job_run(&jobs[0]);
+    for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    int64_t total = 0;
+    double cs = 0.0;
+    for (int t = 0; t < nthreads; ++t) { total += jobs[t].total; cs += jobs[t].checksum; }
+    if (checksum) *checksum = cs;
+    free(jobs);
+    free(th);
+    return total;
+}
+
+int orc_generate_batch(const tgx_params* p, int64_t n, double* out, int64_t traj_stride,
+                       int64_t chan_stride, int64_t cap, int32_t* counts, uint32_t* status,
+                       int64_t max_samples, int nthreads) {
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.mode = 0; j.p = p; j.out = out; j.traj_stride = traj_stride; j.chan_stride = chan_stride;
+    j.cap = cap; j.counts = counts; j.status = status; j.max_samples = max_samples;
+    return run_jobs(&j, n, nthreads, NULL) < 0 ? -1 : 0;
+}
+
+int orc_feasibility_batch(const tgx_params* p, int64_t n, const tgx_limits* limits, uint8_t* flags,
+                          double* max_v, double* max_a, int32_t* counts, uint32_t* status,
+                          int64_t max_samples, int nthreads) {
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.mode = 1; j.p = p; j.limits = limits; j.flags = flags; j.max_v = max_v; j.max_a = max_a;
+    j.counts = counts; j.status = status; j.max_samples = max_samples;
+    return run_jobs(&j, n, nthreads, NULL) < 0 ? -1 : 0;
+}
+
+int64_t orc_time_batch(const tgx_params* p, int64_t n, int64_t max_samples, int nthreads, double* checksum) {
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.mode = 2; j.p = p; j.max_samples = max_samples;
+    return run_jobs(&j, n, nthreads, checksum);
+}
+
+/* ---- checksum ---------------------------------------------------------------------------------------- */
+
+uint64_t orc_fnv1a64(const double* x, int64_t n, uint64_t seed) {
+    uint64_t h = seed;
+    for (int64_t i = 0; i < n; ++i) {
+        double d = x[i];
+        if (d == 0.0) d = 0.0;   /* canonicalise -0.0 */
+        uint64_t bits;
+        memcpy(&bits, &d, sizeof(bits));
+        for (int b = 0; b < 8; ++b) {
+            h ^= (bits >> (8 * b)) & 0xffu;
+            h *= 0x100000001b3ULL;
+        }
+    }
+    return h;
+}
