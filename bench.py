@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the trajectory-sampling hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" is one pass of the hot path over one batch of synthetic parameters that are already resident in HBM:
+tgx_plan (strict-IEEE replay -> counts + segment/tile tables) followed by tgx_eval (the store-bound sampling
+kernel).  Default workload: BASELINE.json configs[1], 1 Mi circles x ~1000 samples on each GPU (weak scaling).
+Rank 0 prints ONE JSON line.  `--impl reference` times the reference's own CPU implementation (oracle/_ref, the
+unmodified sources behind stub headers; falls back to the plain-C oracle port) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "traj samples/s (p,v,a,j,yaw)"
+UNIT = "samples/s"
+BYTES_PER_SAMPLE = 112          # 14 fp64 channels per sample
+FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_params(workload: str, n: int, lo: int, hi: int):
+    from trajectory_generator_ros2_b200 import workloads
+    if workload == "circles_cfg2":
+        return workloads.circles_cfg2(n, lo=lo, hi=hi)
+    if workload == "mixed_cfg3":
+        return workloads.mixed_cfg3(n, lo=lo, hi=hi)
+    if workload == "montecarlo_cfg4":
+        return workloads.montecarlo_cfg4(n, lo=lo, hi=hi)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+WORKLOAD_DESC = {
+    "circles_cfg2": "BASELINE configs[1]: {n} circles x ~1000 samples per GPU, random r/v/centre (rng 1234), dt 0.01",
+    "mixed_cfg3": "BASELINE configs[2]: {n} mixed circle/line/figure-eight with one or two ramp-ups per GPU (rng 1235)",
+    "montecarlo_cfg4": "BASELINE configs[3]: {n} wide-range circles per GPU, max-|v|/|a| feasibility only (rng 1236)",
+}
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            with open(self.tmp.name) as f:
+                for line in f:
+                    parts = [x.strip() for x in line.split(",")]
+                    if len(parts) < 7:
+                        continue
+                    try:
+                        sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for nm, val in zip(names, parts[3:7]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+        finally:
+            try:
+                os.unlink(self.tmp.name)
+            except OSError:
+                pass
+        if sm:
+            # samples under load = the upper half of the power readings (the timed region is short)
+            order = np.argsort(pw)
+            hot = order[len(order) // 2:]
+            out["sm_mhz"] = float(np.median(np.asarray(sm)[hot]))
+            out["sm_max_mhz"] = float(max(mx))
+            out["power_w_max"] = float(max(pw))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---- CPU legs ------------------------------------------------------------------------------------------------
+def cpu_time_sample(params, threads: int, prefer_reference: bool = True):
+    """Time the reference's CPU path on `params` -> (samples, seconds, kind)."""
+    from oracle_lib import Oracle, Reference
+    if prefer_reference and Reference.available():
+        ref = Reference()
+        t0 = time.perf_counter()
+        total, _ = ref.time_batch(params, threads)
+        return total, time.perf_counter() - t0, "reference"
+    orc = Oracle()
+    t0 = time.perf_counter()
+    total, _ = orc.time_batch(params, threads)
+    return total, time.perf_counter() - t0, "port"
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    n_sample = args.cpu_sample
+    params = make_params(args.workload, args.n_per_gpu, 0, n_sample)
+    kind = None
+    for _ in range(args.warmup):
+        cpu_time_sample(params[: max(1, n_sample // 8)], threads)
+    total_samples, total_s = 0, 0.0
+    for _ in range(args.steps):
+        s, dt, kind = cpu_time_sample(params, threads)
+        total_samples += s
+        total_s += dt
+    value = total_samples / total_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[args.workload].format(n=args.n_per_gpu),
+                   "step": f"generateTraj of the first {n_sample} trajectories of the workload into std::vector<Goal>, "
+                           f"{threads} host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"first {n_sample} trajectories ({total_samples // args.steps} samples) per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm ---------------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, read+write bytes)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback 6650 GB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(workload: str):
+    """dram bytes per eval launch from the committed ncu capture of the same command, if there is one."""
+    path = os.path.join(ROOT, "profiles", "eval_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return d.get(workload)
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from trajectory_generator_ros2_b200 import abi, workloads
+    from trajectory_generator_ros2_b200.engine import Engine, PinnedArray
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = Engine(local_rank)
+    if args.tile_shift or args.spt:
+        eng.set_tuning(args.tile_shift or 10, args.spt or 2)
+
+    n = args.n_per_gpu
+    lo, hi = rank * n, (rank + 1) * n                      # weak scaling: every GPU owns n trajectories
+    params = make_params(args.workload, world * n, lo, hi)
+    d_params = eng.upload_params(params)
+    feas_only = args.workload == "montecarlo_cfg4"
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS) if feas_only else None
+
+    # size the output from a first (untimed) count
+    counts, _ = eng.count(d_params)
+    max_count = int(counts.max().item())
+    total_samples = int(counts.sum(dtype=torch.int64).item())
+    row = max(1024, (max_count + 1023) // 1024 * 1024) if not feas_only else 0
+    chunks = 1
+    out = None
+    if not feas_only:
+        while True:
+            try:
+                rows = (n + chunks - 1) // chunks
+                shape = (abi.TGX_NCHAN, rows, row) if args.plane_major else (rows, abi.TGX_NCHAN, row)
+                out = torch.empty(shape, dtype=torch.float64, device=dev)
+                break
+            except torch.OutOfMemoryError:
+                chunks *= 2
+                if chunks > 64:
+                    raise
+    rows = (n + chunks - 1) // chunks
+    chunk_params = [d_params[c * rows: min(n, (c + 1) * rows)] for c in range(chunks)]
+
+    ev_pairs = []
+
+    def step(record: bool):
+        for c in range(chunks):
+            dp = chunk_params[c]
+            eng.plan(dp, limits=lim, want_outputs=False)
+            if record:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            if feas_only:
+                eng.feasibility(lim, int(dp.shape[0]), flags=flags[c], max_v=mv[c], max_a=ma[c], status=st[c])
+            else:
+                view = out[:, : dp.shape[0]] if args.plane_major else out[: dp.shape[0]]
+                if view.is_contiguous():
+                    eng.eval(view, plane_major=args.plane_major)
+                else:   # plane-major partial chunk: describe the full buffer
+                    lay = abi.Layout()
+                    lay.d_base, lay.traj_stride, lay.chan_stride, lay.capacity = out.data_ptr(), row, rows * row, row
+                    eng.eval_layout(lay)
+            if record:
+                b.record()
+                ev_pairs.append((a, b))
+
+    if feas_only:
+        flags = [torch.empty(int(p.shape[0]), dtype=torch.uint8, device=dev) for p in chunk_params]
+        mv = [torch.empty(int(p.shape[0]), dtype=torch.float64, device=dev) for p in chunk_params]
+        ma = [torch.empty(int(p.shape[0]), dtype=torch.float64, device=dev) for p in chunk_params]
+        st = [torch.empty(int(p.shape[0]), dtype=torch.int32, device=dev) for p in chunk_params]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        step(True)
+    t_stop.record()
+    barrier()
+    elapsed_ms = t_start.elapsed_time(t_stop)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    eval_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs])) * chunks   # per step
+    if world > 1:
+        t = torch.tensor([elapsed_ms, eval_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, eval_ms = float(t[0]), float(t[1])
+        tot = torch.tensor([total_samples], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        job_samples = int(tot[0])
+    else:
+        job_samples = total_samples
+    ms_per_step = elapsed_ms / args.steps
+    value = job_samples / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region) ----
+    e2e = None
+    if not feas_only and not args.no_e2e:
+        call_n = min(n, args.e2e_call)                       # trajectories per tgx_generate_host call
+        pin_out = PinnedArray((call_n, abi.TGX_NCHAN, row))
+        pin_params = PinnedArray((call_n,), dtype=abi.PARAMS_DTYPE)
+        h_counts_total = 0
+
+        def e2e_step():
+            tot = 0
+            for s in range(0, n, call_n):
+                m = min(call_n, n - s)
+                pin_params.array[:m] = params[s:s + m]
+                _, c, _, _ = eng.generate_host(pin_params.array[:m], row, out=pin_out.array[:m])
+                tot += int(c.sum())
+            return tot
+
+        del out
+        torch.cuda.empty_cache()
+        for _ in range(1):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            h_counts_total = e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t[0])
+        assert h_counts_total == total_samples
+        e2e = {"value": job_samples / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * (abi.TGX_NCHAN * row * 8 + 8)),
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
+               "call": f"tgx_generate_host, {call_n} trajectories per call into one reused pinned host buffer"}
+        pin_out.free()
+        pin_params.free()
+    elif feas_only and not args.no_e2e:
+        # feasibility: H2D of the parameter records, D2H of flags + maxima
+        h_flags = np.empty(n, dtype=np.uint8)
+        pin = torch.from_numpy(np.ascontiguousarray(params).view(np.uint8).reshape(n, 128)).pin_memory()
+
+        def e2e_step():
+            dp = pin.to(dev, non_blocking=True)
+            eng.plan(dp, limits=lim, want_outputs=False)
+            f, v_, a_, s_ = eng.feasibility(lim, n)
+            return f.cpu(), v_.cpu(), a_.cpu()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        e2e = {"value": job_samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 128),
+               "d2h_bytes_per_step": int(n * 17), "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
+               "call": "H2D params, tgx_plan + tgx_feasibility, D2H flags + max_v + max_a"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        eval_bytes = BYTES_PER_SAMPLE * total_samples if not feas_only else 17 * n
+        achieved = eval_bytes / (eval_ms * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = host_threads()
+            s, dt, kind = cpu_time_sample(params[: args.cpu_sample], threads)
+            cpu = {"value": s / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"first {args.cpu_sample} trajectories of the workload ({s} samples), "
+                             f"generateTraj into std::vector<Goal>, {dt:.2f} s wall"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD_DESC[args.workload].format(n=n),
+                "trajectories_per_gpu": n, "samples_per_gpu": total_samples, "row_stride": row,
+                "layout": "plane-major [14][n][row]" if args.plane_major else "trajectory-major [n][14][row]",
+                "chunks": chunks,
+                "step": "tgx_plan (count + scans + fill) + " + ("tgx_feasibility" if feas_only else "tgx_eval")
+                        + ", parameters resident in HBM",
+                "l2": "each step writes %.1f GB >> 126 MB L2, no flush needed" % (eval_bytes / 1e9)
+                      if not feas_only else "reduction only",
+                "parallelism": f"{world} independent shards, no data-path collective",
+                "eval_ms_per_step": eval_ms,
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                         "kernel": "tgx::eval_kernel", "bytes_per_launch": eval_bytes / chunks,
+                         "peak_source": peak_src + " — of measured" if "MEASURED" in peak_src else peak_src},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="circles_cfg2", choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--n-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--plane-major", action="store_true")
+    ap.add_argument("--tile-shift", type=int, default=0)
+    ap.add_argument("--spt", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="trajectories timed on the CPU legs")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-call", type=int, default=1 << 16)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,10 @@ int tgx_create(tgx_engine** out, int device);     /* binds to `device`; TGX_ERR_
 int tgx_destroy(tgx_engine* e);
 /* Guard against parameters for which the reference never terminates. Default 1<<24 samples. */
 int tgx_set_max_samples(tgx_engine* e, int64_t max_samples);
+/* Kernel shape used by tgx_eval / tgx_feasibility: one CTA evaluates a tile of (1 << tile_shift) consecutive
+ * samples of one trajectory (tile_shift in 9..11), each thread `spt` adjacent samples (2: 128-bit stores,
+ * 4: 256-bit stores).  Invalidates the current plan.  Default 10, 2. */
+int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt);
 /* Bytes of device scratch currently held by the engine (plan tables). */
 int64_t tgx_scratch_bytes(const tgx_engine* e);
 
@@ -235,12 +239,17 @@ int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const do
                   double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
                   tgx_phases* h_phases);
 
+/* Page-locked host memory, so that the D2H copies of the calls above run asynchronously at full PCIe rate. */
+void* tgx_alloc_host(int64_t bytes);
+void tgx_free_host(void* p);
+
 /* ---- sharding helper (multi-GPU: one process per GPU, contiguous block partition, no collective) ---- */
 /* Rank `rank` of `world` owns trajectories [*lo, *hi) of a batch of n. */
 int tgx_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
 
 /* ---- introspection used by bench.py ---------------------------------------------------------------- */
-/* Number of CUDA kernels this library has launched on this engine since creation. */
+/* Number of this library's own (hand-written) kernels launched on this engine since creation: plan_count,
+ * plan_fill, eval, feasibility_finalize.  The cub scans inside tgx_plan are not counted. */
 int64_t tgx_launch_count(const tgx_engine* e);
 /* Tiles / segments of the current plan (0 if none). */
 int64_t tgx_plan_tiles(const tgx_engine* e);

@@ -1,0 +1,411 @@
+"""GPU parity tests: the CUDA engine, called through the C-ABI (libtgx.so), against the CPU oracle.
+
+Counts, status bits and index_msgs must be exact; samples must be within the tolerances in parity.py.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from parity import assert_samples_close, merge_errors
+from trajectory_generator_ros2_b200 import abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_generate(engine, params, capacity=None, want_phases=True, plane_major=False):
+    """plan + eval on device tensors -> (out [n,14,cap] numpy, counts, status, phases)."""
+    import torch
+    d_params = engine.upload_params(params)
+    plan = engine.plan(d_params, want_phases=want_phases)
+    counts = plan.counts.cpu().numpy()
+    status = plan.status.cpu().numpy().view(np.uint32)
+    cap = capacity if capacity is not None else max(4, int((counts.max(initial=0) + 3) // 4 * 4))
+    n = len(params)
+    shape = (abi.TGX_NCHAN, n, cap) if plane_major else (n, abi.TGX_NCHAN, cap)
+    out = torch.full(shape, float("nan"), dtype=torch.float64, device=d_params.device)
+    engine.eval(out, plane_major=plane_major)
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    if plane_major:
+        o = np.ascontiguousarray(o.transpose(1, 0, 2))
+    ph = plan.phases.cpu().numpy().view(abi.PHASES_DTYPE).reshape(n) if want_phases else None
+    assert plan.total_samples == int(counts.sum())
+    return o, counts, status, ph
+
+
+def check_batch(engine, oracle, params, what, **kw):
+    out, counts, status, ph = gpu_generate(engine, params, **kw)
+    o_counts, o_status = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts, o_counts, err_msg=f"{what}: sample counts")
+    np.testing.assert_array_equal(status, o_status, err_msg=f"{what}: status bits")
+    worst = {}
+    for i in range(len(params)):
+        ref, st, oph = oracle.generate(params[i:i + 1])
+        n = counts[i]
+        assert ref.shape[1] == n
+        if n == 0:
+            continue
+        merge_errors(worst, assert_samples_close(out[i, :, :n], ref, f"{what}[{i}]"))
+        assert np.isnan(out[i, :, n:]).all(), f"{what}[{i}]: padding was written"
+        if ph is not None:
+            assert abi.phases_to_index_msgs(int(params["type"][i]), ph[i]) == \
+                abi.phases_to_index_msgs(int(params["type"][i]), oph), f"{what}[{i}]: index_msgs"
+    return worst
+
+
+# ---- known-answer cases (config/default.yaml) ------------------------------------------
+
+def test_default_circle(engine, oracle):
+    p = workloads.default_circle()
+    out, counts, status, ph = gpu_generate(engine, p)
+    assert counts[0] == 25001 and status[0] == 0
+    msgs = abi.phases_to_index_msgs(abi.TGX_CIRCLE, ph[0])
+    assert sorted(msgs) == [0, 250, 8250, 8500, 16500, 24500, 25000]
+    assert msgs[16500] == "Circle traj: reached 2.000000 m/s, keeping constant v for 80.000000 s"
+    ref, _, _ = oracle.generate(p)
+    e = assert_samples_close(out[0, :, :25001], ref, "default circle")
+    assert e["pos_abs"] < 2e-11, e   # tile-aligned exact bases keep the drift far below the 1e-9 m budget
+    # unwrapped yaw at the end of the run (Circle.cpp:125)
+    assert abs(out[0, abi.PSI, 25000] - 122.15903162087876) < 1e-9
+
+
+def test_default_figure8(engine, oracle):
+    p = workloads.default_figure8()
+    out, counts, status, ph = gpu_generate(engine, p)
+    assert counts[0] == 25001 and status[0] == 0
+    ref, _, oph = oracle.generate(p)
+    assert_samples_close(out[0, :, :25001], ref, "default figure8")
+    assert abi.phases_to_index_msgs(abi.TGX_FIGURE8, ph[0])[25000] == "Figure 8 traj: stopped"
+    assert (out[0, abi.JX:abi.JZ + 1, :25001] == 0).all()   # Figure8 jerk is identically zero (Figure8.cpp:117-119)
+
+
+def test_default_line(engine, oracle):
+    p = workloads.default_line()
+    out, counts, status, ph = gpu_generate(engine, p)
+    assert counts[0] == 685 and status[0] == 0
+    assert sorted(abi.phases_to_index_msgs(abi.TGX_LINE, ph[0])) == [0, 67, 584, 684]
+    ref, _, _ = oracle.generate(p)
+    assert_samples_close(out[0, :, :685], ref, "default line")
+    # last sample forced to B exactly (Line.cpp:81-82)
+    assert out[0, abi.PX, 684] == 0.0 and out[0, abi.PY, 684] == 3.0
+    # first sample: a = 0; ramp-up: a = +a1; cruise: 0; ramp-down: -a3
+    assert out[0, abi.AY, 0] == 0.0
+    np.testing.assert_allclose(out[0, abi.AY, [1, 67, 68, 584, 585, 684]], [1.5, 1.5, 0, 0, -1, -1], atol=1e-15)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------
+
+def test_count_traps(engine, oracle):
+    """Counts are decided by accumulated rounding, not by ceil() formulas (SURVEY.md §7.3 hard part 1)."""
+    cases = [(2.0, 0.3, 10.0), (3.0, 0.1, 1.0), (1.0, 0.3, 5.0), (1.0, 0.4, 80.0), (2.5, 0.5, 20.0)]
+    params = abi.concat([abi.circle_params(1.5, 2.0, 0.1, -0.2, [v], t, a, 0.01) for v, a, t in cases])
+    out, counts, status, _ = gpu_generate(engine, params)
+    o_counts, _ = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts, o_counts)
+    # the three traps from the survey: ramp 667 + hold 1001; ramp 3001 + hold 100; ramp 334 + hold 501
+    assert counts[0] == 1 + 667 + 1001 + 667
+    assert counts[1] == 1 + 3001 + 100 + 3001
+    assert counts[2] == 1 + 334 + 501 + 334
+    check_batch(engine, oracle, params, "count traps")
+
+
+def test_round_parameter_grid_counts(engine, oracle):
+    """Human-style round parameters: every (v, a, t) of a grid must give the oracle's exact count."""
+    vs = [0.5, 1.0, 1.5, 2.0, 3.0]
+    accs = [0.1, 0.2, 0.3, 0.4, 0.5, 0.7, 1.0]
+    ts = [0.0, 0.5, 1.0, 2.0, 5.0, 10.0, 20.0]
+    dts = [0.01, 0.02, 0.005]
+    recs = [abi.circle_params(1.0, 1.5, 0, 0, [v], t, a, dt, kind=k)
+            for v in vs for a in accs for t in ts for dt in dts for k in (abi.TGX_CIRCLE, abi.TGX_FIGURE8)]
+    params = abi.concat(recs)
+    d = engine.upload_params(params)
+    counts, status = engine.count(d)
+    o_counts, o_status = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts.cpu().numpy(), o_counts)
+    np.testing.assert_array_equal(status.cpu().numpy().view(np.uint32), o_status)
+    plan = engine.plan(d)
+    np.testing.assert_array_equal(plan.counts.cpu().numpy(), o_counts)
+
+
+def test_vgoals_edge_cases(engine, oracle):
+    params = abi.concat([
+        abi.circle_params(1.8, 3.4, 0, 0, [2.0, 1.0], 1.0, 0.4, 0.01),            # decreasing: warning, N = 1201
+        abi.circle_params(1.8, 3.4, 0, 0, [1.0, 2.0, 2.0], 2.0, 0.4, 0.01),       # repeated goal: zero-length ramp
+        abi.figure8_params(1.8, 2.0, 1, -1, [0.5, 1.0, 1.5, 2.0, 2.5], 1.5, 1.0, 0.01),
+        abi.circle_params(1.0, 1.0, 0, 0, [0.3] * 8, 0.25, 2.0, 0.01),            # 8 goals, many short phases
+        abi.circle_params(1.0, 1.0, 0, 0, [1.0], 0.0, 1.0, 0.01),                 # no hold at all
+        abi.circle_params(1.0, 1.0, 0, 0, [1.0], -3.0, 1.0, 0.01),                # negative hold time
+        abi.circle_params(1.0, 0.7, 0, 0, [0.004], 0.05, 1.0, 0.01),              # ramp of a single clamped step
+    ])
+    out, counts, status, ph = gpu_generate(engine, params)
+    assert counts[0] == 1201 and status[0] == abi.ST_VGOALS_NOT_INCREASING
+    check_batch(engine, oracle, params, "v_goals edge cases")
+
+
+def test_bad_params_are_rejected(engine, oracle):
+    good = abi.circle_params(1.8, 3.4, 0, 0, [1.0], 2.0, 0.4, 0.01)
+    bad = []
+    for field, val in (("accel", 0.0), ("accel", -1.0), ("r", 0.0), ("dt", 0.0), ("dt", float("nan")),
+                       ("t_traj", float("inf")), ("n_vgoals", 0), ("n_vgoals", 9), ("type", 7)):
+        q = good.copy()
+        q[field] = val
+        bad.append(q)
+    q = good.copy(); q["v_goals"][0, 0] = -1.0; bad.append(q)
+    ql = workloads.default_line().copy(); ql["a3"] = 0.0; bad.append(ql)
+    params = abi.concat([good] + bad + [workloads.default_line()])
+    out, counts, status, ph = gpu_generate(engine, params, capacity=1024)
+    o_counts, o_status = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts, o_counts)
+    np.testing.assert_array_equal(status, o_status)
+    assert counts[0] > 0 and counts[-1] == 685
+    assert (counts[1:-1] == 0).all() and (status[1:-1] == abi.ST_BAD_PARAM).all()
+    assert np.isnan(out[1:-1]).all()          # rejected trajectories write nothing
+    assert (ph["n"][1:-1] == 0).all()
+
+
+def test_too_long_guard(engine, oracle):
+    """Parameters for which the reference would loop (almost) for ever are cut by the max_samples guard."""
+    params = abi.concat([
+        abi.circle_params(1.0, 1.0, 0, 0, [1.0], 1.0, 1e-30, 0.01),       # v + a*dt never reaches v_goal
+        abi.circle_params(1.0, 1.0, 0, 0, [1.0], 1e9, 1.0, 0.01),        # 1e11 hold samples
+        abi.circle_params(1.0, 1.0, 0, 0, [1.0], 1.0, 1.0, 0.01),
+    ])
+    engine.set_max_samples(100000)
+    try:
+        d = engine.upload_params(params)
+        counts, status = engine.count(d)
+        o_counts, o_status = oracle.count_batch(params, max_samples=100000)
+        np.testing.assert_array_equal(counts.cpu().numpy(), o_counts)
+        np.testing.assert_array_equal(status.cpu().numpy().view(np.uint32), o_status)
+        assert o_status[0] == abi.ST_TOO_LONG and o_status[1] == abi.ST_TOO_LONG and o_status[2] == 0
+    finally:
+        engine.set_max_samples(abi.DEFAULT_MAX_SAMPLES)
+
+
+def test_line_edge_cases(engine, oracle):
+    params = abi.concat([
+        workloads.default_line(),
+        abi.line_params(1.8, [0, -3, 1.8], [0, -2.5, 1.8], [1.0], 1.5, 1.0, 0.01),     # d2 < 0: overshoots B
+        abi.line_params(1.0, [-4.25, -3.5, 1.0], [4.5, 4.25, 1.0], [3.0], 1.5, 1.0, 0.01),
+        abi.line_params(1.0, [1, 1, 1.0], [-2, 0.5, 1.0], [0.7], 0.9, 0.6, 0.01),      # heading in quadrant 3
+        abi.line_params(1.0, [0, 0, 0.5], [0, 2, 2.5], [0.5], 1.0, 1.0, 0.02),         # z differs: 3-D |B-A|
+    ])
+    out, counts, status, ph = gpu_generate(engine, params)
+    assert status[1] & abi.ST_LINE_D2_NEGATIVE
+    check_batch(engine, oracle, params, "line edge cases")
+
+
+# ---- random batches -----------------------------------------------------------------------------------------
+
+def test_random_circles_cfg2(engine, oracle):
+    params = workloads.circles_cfg2(3000)
+    worst = check_batch(engine, oracle, params, "cfg2 circles", capacity=1024, want_phases=False)
+    assert worst["pos_abs"] < 1e-11, worst
+
+
+def test_random_mixed_cfg3(engine, oracle):
+    params = workloads.mixed_cfg3(3000)
+    assert set(np.unique(params["type"])) == {0, 1, 2}
+    check_batch(engine, oracle, params, "cfg3 mixed", want_phases=True)
+
+
+def test_layouts_and_tunings_agree(engine, oracle):
+    """Every kernel shape and both plane orders must produce bit-identical planes."""
+    import torch
+    params = abi.concat([workloads.mixed_cfg3(300), workloads.default_circle()])
+    base, counts, status, _ = gpu_generate(engine, params, want_phases=False)
+    try:
+        for shift, spt in ((9, 2), (9, 4), (10, 4), (11, 2), (11, 4)):
+            engine.set_tuning(shift, spt)
+            for plane_major in (False, True):
+                out, c2, s2, _ = gpu_generate(engine, params, want_phases=False, plane_major=plane_major)
+                np.testing.assert_array_equal(c2, counts)
+                # tile size changes where segment bases sit, so values may differ in the last bits only
+                m = ~np.isnan(base)
+                assert (np.isnan(out) == np.isnan(base)).all()
+                np.testing.assert_allclose(out[m], base[m], rtol=0, atol=5e-12)
+    finally:
+        engine.set_tuning(10, 2)
+    ref, _, _ = oracle.generate(params[-1:])
+    assert_samples_close(base[-1, :, :25001], ref, "default circle in mixed batch")
+
+
+def test_capacity_truncation_and_channel_mask(engine):
+    import torch
+    params = workloads.circles_cfg2(64)
+    d = engine.upload_params(params)
+    plan = engine.plan(d)
+    full = torch.full((64, 14, 1024), float("nan"), dtype=torch.float64, device=d.device)
+    engine.eval(full)
+    cut = torch.full((64, 14, 1024), float("nan"), dtype=torch.float64, device=d.device)
+    engine.eval(cut, capacity=501)     # odd capacity: the last vector is a partial store
+    only = torch.full((64, 14, 1024), float("nan"), dtype=torch.float64, device=d.device)
+    engine.eval(only, channel_mask=(1 << abi.PX) | (1 << abi.PSI))
+    torch.cuda.synchronize()
+    full, cut, only = full.cpu().numpy(), cut.cpu().numpy(), only.cpu().numpy()
+    np.testing.assert_array_equal(cut[:, :, :501], full[:, :, :501])
+    assert np.isnan(cut[:, :, 501:]).all()
+    np.testing.assert_array_equal(only[:, [abi.PX, abi.PSI]], full[:, [abi.PX, abi.PSI]])
+    rest = [c for c in range(14) if c not in (abi.PX, abi.PSI)]
+    assert np.isnan(only[:, rest]).all()
+
+
+def test_alignment_is_checked(engine):
+    import torch
+    from trajectory_generator_ros2_b200.engine import TgxError
+    params = workloads.circles_cfg2(4)
+    d = engine.upload_params(params)
+    engine.plan(d)
+    out = torch.zeros((4, 14, 1022), dtype=torch.float64, device=d.device)
+    with pytest.raises(TgxError) as ei:
+        engine.eval(out)
+    assert ei.value.code == abi.TGX_ERR_ALIGNMENT
+
+
+# ---- braking trajectories ------------------------------------------------------------------------------------
+
+def test_stop_trajectories(engine, oracle):
+    import torch
+    cases = [(workloads.default_circle(), 12500, 500), (workloads.default_figure8(), 12500, 481),
+             (workloads.default_line(), 342, 100), (workloads.default_circle(), 100, None),
+             (workloads.default_line(), 30, None), (workloads.default_line(), 650, None),
+             (workloads.default_circle(), 0, 0), (workloads.default_line(), 0, 1)]
+    params = abi.concat([c[0] for c in cases])
+    froms = np.stack([oracle.generate(c[0])[0][:, c[1]] for c in cases])
+    d = engine.upload_params(params)
+    plan = engine.plan_stop(d, torch.from_numpy(froms).to(d.device), want_phases=True)
+    counts = plan.counts.cpu().numpy()
+    ph = plan.phases.cpu().numpy().view(abi.PHASES_DTYPE).reshape(len(cases))
+    cap = int((counts.max() + 3) // 4 * 4)
+    out = torch.full((len(cases), 14, cap), float("nan"), dtype=torch.float64, device=d.device)
+    engine.eval(out)
+    out = out.cpu().numpy()
+    for i, (p, k, expect) in enumerate(cases):
+        ref, st, oph = oracle.stop(p, froms[i])
+        assert counts[i] == ref.shape[1], (i, counts[i], ref.shape)
+        if expect is not None:
+            assert counts[i] == expect
+        if counts[i]:
+            assert_samples_close(out[i, :, :counts[i]], ref, f"stop[{i}]")
+        t = int(p["type"][0])
+        assert abi.phases_to_index_msgs(t, ph[i], stop_traj=True) == abi.phases_to_index_msgs(t, oph, stop_traj=True)
+
+
+# ---- feasibility -------------------------------------------------------------------------------------------
+
+def test_feasibility_matches_oracle(engine, oracle):
+    params = abi.concat([workloads.montecarlo_cfg4(2000), workloads.mixed_cfg3(500)])
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    d = engine.upload_params(params)
+    plan = engine.plan(d, limits=lim)
+    flags, mv, ma, status = engine.feasibility(lim, len(params))
+    flags, mv, ma = flags.cpu().numpy(), mv.cpu().numpy(), ma.cpu().numpy()
+    status = status.cpu().numpy().view(np.uint32)
+    o_flags, o_mv, o_ma, o_counts, o_status = oracle.feasibility_batch(params, lim)
+    np.testing.assert_array_equal(plan.counts.cpu().numpy(), o_counts)
+    np.testing.assert_allclose(mv, o_mv, rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(ma, o_ma, rtol=1e-8, atol=1e-14)
+    # a verdict may only differ where a maximum sits within tolerance of its limit
+    near = (np.abs(o_mv - lim.v_max) <= 1e-8 * lim.v_max) | (np.abs(o_ma - lim.a_max) <= 1e-8 * lim.a_max)
+    np.testing.assert_array_equal(flags[~near], o_flags[~near])
+    np.testing.assert_array_equal(status[~near], o_status[~near])
+    assert 0 < flags.sum() < len(flags)        # the sweep has both feasible and infeasible members
+    assert (status & abi.ST_OUTSIDE_BOUNDS).any()
+    # the fused store+reduce path gives the same maxima
+    import torch
+    cap = int((o_counts.max() + 3) // 4 * 4)
+    out = torch.empty((len(params), 14, cap), dtype=torch.float64, device=d.device)
+    mv2 = torch.empty(len(params), dtype=torch.float64, device=d.device)
+    ma2 = torch.empty(len(params), dtype=torch.float64, device=d.device)
+    engine.eval(out, max_v=mv2, max_a=ma2)
+    np.testing.assert_array_equal(mv2.cpu().numpy(), mv)
+    np.testing.assert_array_equal(ma2.cpu().numpy(), ma)
+
+
+# ---- host-buffer C-ABI calls ------------------------------------------------------------------------------
+
+def test_generate_host_matches_device_path(engine, oracle):
+    params = abi.concat([workloads.mixed_cfg3(500), workloads.default_line()])
+    base, counts, status, ph = gpu_generate(engine, params, capacity=2048)
+    out, c2, s2, ph2 = engine.generate_host(params, 2048, want_phases=True)
+    np.testing.assert_array_equal(c2, counts)
+    np.testing.assert_array_equal(s2, status)
+    for i in range(len(params)):
+        np.testing.assert_array_equal(out[i, :, :counts[i]], base[i, :, :counts[i]])
+    assert (ph2["n"] == ph["n"]).all()
+    for i in range(len(params)):     # entries past n are unspecified
+        m = ph["n"][i]
+        assert (ph2["key"][i, :m] == ph["key"][i, :m]).all() and (ph2["kind"][i, :m] == ph["kind"][i, :m]).all()
+        assert (ph2["value"][i, :m] == ph["value"][i, :m]).all() and (ph2["value2"][i, :m] == ph["value2"][i, :m]).all()
+    hc, hs = engine.count_host(params)
+    np.testing.assert_array_equal(hc, counts)
+    # truncation is reported on the host path
+    out3, c3, s3, _ = engine.generate_host(params[:8], 512)
+    assert ((s3 & abi.ST_TRUNCATED) != 0).tolist() == (c3 > 512).tolist()
+
+
+def test_generate_host_chunking(engine, oracle):
+    """More rows than one 1 GiB staging chunk holds: exercises the double-buffered chunk loop."""
+    params = workloads.circles_cfg2(24000)          # 24000 * 14 * 1024 * 8 B = 2.75 GB -> 3 chunks
+    out, counts, status, _ = engine.generate_host(params, 1024)
+    o_counts, o_status = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts, o_counts)
+    for i in (0, 9361, 9362, 18723, 18724, 23999):
+        ref, _, _ = oracle.generate(params[i:i + 1])
+        assert_samples_close(out[i, :, :counts[i]], ref, f"chunked[{i}]")
+
+
+def test_stop_host(engine, oracle):
+    p = workloads.default_circle()
+    ref, _, _ = oracle.generate(p)
+    out, counts, status, ph = engine.stop_host(p, ref[:, 12500], 512, want_phases=True)
+    sref, _, sph = oracle.stop(p, ref[:, 12500])
+    assert counts[0] == 500 == sref.shape[1]
+    assert_samples_close(out[0, :, :500], sref, "stop_host")
+    assert abi.phases_to_index_msgs(0, ph[0], True) == {0: "Circle traj: pressed END, decelerating to 0 m/s",
+                                                        499: "Circle traj: stopped"}
+
+
+# ---- size-independent properties at BASELINE scale -------------------------------------------------------
+
+def test_properties_at_scale(engine, oracle):
+    """262144 cfg-2 circles (2.6e8 samples): counts vs the oracle for ALL trajectories, values for a 1 % subset,
+    and closed-form invariants for every sample (|p - c| = r, |v| = v_k, p.z = alt)."""
+    import torch
+    n = 1 << 18
+    params = workloads.circles_cfg2(n)
+    d = engine.upload_params(params)
+    plan = engine.plan(d)
+    counts = plan.counts.cpu().numpy()
+    o_counts, o_status = oracle.count_batch(params, nthreads=32)
+    np.testing.assert_array_equal(counts, o_counts)
+    assert counts.min() >= 1000 and counts.max() <= 1001
+    out = torch.empty((n, 14, 1024), dtype=torch.float64, device=d.device)
+    engine.eval(out)
+    k = torch.arange(1024, device=d.device)[None, :]
+    valid = k < plan.counts[:, None]
+    r = torch.from_numpy(params["r"].copy()).to(d.device)[:, None]
+    cx = torch.from_numpy(params["cx"].copy()).to(d.device)[:, None]
+    cy = torch.from_numpy(params["cy"].copy()).to(d.device)[:, None]
+    alt = torch.from_numpy(params["alt"].copy()).to(d.device)[:, None]
+    vg = torch.from_numpy(params["v_goals"][:, 0].copy()).to(d.device)[:, None]
+    rad = torch.hypot(out[:, abi.PX] - cx, out[:, abi.PY] - cy)
+    assert float(((rad - r).abs() * valid).max()) < 1e-12
+    assert bool(((out[:, abi.PZ] == alt) | ~valid).all())
+    speed = torch.hypot(out[:, abi.VX], out[:, abi.VY])
+    assert float(((speed - out[:, abi.DPSI] * r).abs() * valid).max()) < 1e-12     # |v| = omega * r
+    assert float((speed * valid).max()) <= float(vg.max()) * (1 + 1e-15)
+    last = (plan.counts.long() - 1)[:, None]
+    assert float(torch.gather(speed, 1, last).abs().max()) == 0.0                  # every trajectory ends at rest
+    # yaw never goes backwards, up to the rounding-level seam between a ramp chunk's closed form and the exactly
+    # replayed sample that ends it (<= kRampChunk half-ulps of theta, ~1e-12 rad here)
+    dpsi = out[:, abi.PSI, 1:] - out[:, abi.PSI, :-1]
+    assert float((dpsi * valid[:, 1:]).min()) >= -2e-12
+    sub = np.arange(0, n, 100)
+    host = out[torch.from_numpy(sub).to(d.device)].cpu().numpy()
+    worst = {}
+    for j, i in enumerate(sub):
+        ref, _, _ = oracle.generate(params[i:i + 1])
+        merge_errors(worst, assert_samples_close(host[j, :, :counts[i]], ref, f"scale[{i}]"))
+    print("worst errors at scale:", worst)

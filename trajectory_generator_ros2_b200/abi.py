@@ -123,6 +123,21 @@ PHASES_DTYPE = np.dtype({
 })
 
 
+def concat(parts) -> np.ndarray:
+    """Concatenate tgx_params arrays byte-wise.
+
+    np.concatenate on this dtype silently re-packs the overlapping (union) fields into a 200-byte record; going
+    through raw bytes keeps the 128-byte C layout.
+    """
+    parts = [np.ascontiguousarray(x) for x in parts]
+    for x in parts:
+        assert x.dtype == PARAMS_DTYPE, x.dtype
+    if not parts:
+        return np.zeros(0, dtype=PARAMS_DTYPE)
+    raw = np.concatenate([x.view(np.uint8).reshape(-1, 128) for x in parts], axis=0)
+    return np.ascontiguousarray(raw).view(PARAMS_DTYPE).reshape(-1)
+
+
 def make_limits(box=None, v_max=float("inf"), a_max=float("inf")) -> Limits:
     lim = Limits()
     if box is not None:

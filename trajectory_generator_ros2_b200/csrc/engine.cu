@@ -1,0 +1,579 @@
+// engine.cu — host side of libtgx: the C-ABI declared in include/tgx.h.
+//
+// Owns the plan tables (TrajRec / Seg / Tile) in device memory, sequences the planning passes
+// (count -> exclusive scans -> fill) and the evaluation kernel on the caller's stream, and provides the
+// host-buffer convenience calls the drop-in C++ classes use (chunked, double-buffered H2D / eval / D2H).
+// There is no CPU implementation of any sampler in this library: if CUDA is unavailable every entry point
+// that would compute returns TGX_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <iterator>
+#include <new>
+#include <string>
+
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "tgx_internal.cuh"
+
+namespace tgx {
+
+cudaError_t launch_plan_count(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
+                              int64_t max_samples, int tile_shift, int32_t* counts, uint32_t* status,
+                              int32_t* nseg, int32_t* ntile, cudaStream_t stream);
+cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
+                             int64_t max_samples, int tile_shift, const int32_t* plan_counts,
+                             const int64_t* seg_off, const int64_t* tile_off, TrajRec* recs, Seg* segs, Tile* tiles,
+                             int32_t* counts, uint32_t* status, tgx_phases* phases, cudaStream_t stream);
+cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles, int tile_shift,
+                        int spt, const OutView& out, bool store, double* max_v, double* max_a,
+                        cudaStream_t stream);
+cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, const double* max_v,
+                                        const double* max_a, double v_max, double a_max, uint8_t* flags,
+                                        uint32_t* status_out, cudaStream_t stream);
+
+}  // namespace tgx
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+
+int cuda_fail(cudaError_t e, const char* what) {
+    g_last_cuda_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return TGX_ERR_CUDA;
+}
+
+#define TGX_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// A growable device buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want) {
+        if (want <= bytes) return TGX_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        const size_t grown = want + want / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, grown);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                g_last_cuda_error = "cudaMalloc(" + std::to_string(want) + " bytes) failed";
+                return TGX_ERR_NOMEM;
+            }
+            bytes = want;
+            return TGX_OK;
+        }
+        bytes = grown;
+        return TGX_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want) {
+        if (want <= bytes) return TGX_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            g_last_cuda_error = "cudaHostAlloc(" + std::to_string(want) + " bytes) failed";
+            return TGX_ERR_NOMEM;
+        }
+        bytes = want;
+        return TGX_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+// int32 -> int64 widening input iterator for the cub scans (sums of counts can exceed 2^31).
+struct WideIter {
+    using iterator_category = std::random_access_iterator_tag;
+    using value_type = int64_t;
+    using difference_type = int64_t;
+    using pointer = const int64_t*;
+    using reference = int64_t;
+    const int32_t* p;
+    __host__ __device__ int64_t operator*() const { return (int64_t)*p; }
+    __host__ __device__ int64_t operator[](difference_type i) const { return (int64_t)p[i]; }
+    __host__ __device__ WideIter operator+(difference_type i) const { return WideIter{p + i}; }
+    __host__ __device__ WideIter operator-(difference_type i) const { return WideIter{p - i}; }
+    __host__ __device__ difference_type operator-(const WideIter& o) const { return p - o.p; }
+    __host__ __device__ WideIter& operator+=(difference_type i) { p += i; return *this; }
+    __host__ __device__ WideIter& operator++() { ++p; return *this; }
+    __host__ __device__ WideIter operator++(int) { WideIter t = *this; ++p; return t; }
+    __host__ __device__ bool operator==(const WideIter& o) const { return p == o.p; }
+    __host__ __device__ bool operator!=(const WideIter& o) const { return p != o.p; }
+};
+
+}  // namespace
+
+struct tgx_engine {
+    int device = 0;
+    int64_t max_samples = (int64_t)1 << 24;
+    int tile_shift = 10;   // 1024 samples per tile
+    int spt = 2;           // samples per thread: 2 -> 128-bit stores, 4 -> 256-bit stores
+    int64_t launches = 0;
+
+    // per-trajectory scratch (capacity in trajectories)
+    DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals;
+    // tables
+    DevBuf segs, tiles;
+    PinBuf h_totals;
+
+    // current plan
+    bool has_plan = false;
+    int64_t plan_n = 0, plan_tiles = 0, plan_segs = 0, plan_samples = 0;
+
+    // host-buffer path
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    cudaEvent_t hev[2] = {nullptr, nullptr};       // slot's D2H copies done -> its staging buffers are reusable
+    cudaEvent_t hev_eval = nullptr;                // last evaluation done -> the shared plan tables are reusable
+    DevBuf h_params[2], h_out[2], h_cnt[2], h_st[2], h_ph[2], h_from[2];
+};
+
+namespace {
+
+int ensure_traj_scratch(tgx_engine* e, int64_t n) {
+    int rc;
+    const size_t n1 = (size_t)n + 1;
+    if ((rc = e->cnt.reserve(n1 * sizeof(int32_t)))) return rc;
+    if ((rc = e->nseg.reserve(n1 * sizeof(int32_t)))) return rc;
+    if ((rc = e->ntile.reserve(n1 * sizeof(int32_t)))) return rc;
+    if ((rc = e->status.reserve(n1 * sizeof(uint32_t)))) return rc;
+    if ((rc = e->seg_off.reserve(n1 * sizeof(int64_t)))) return rc;
+    if ((rc = e->tile_off.reserve(n1 * sizeof(int64_t)))) return rc;
+    if ((rc = e->recs.reserve(n1 * sizeof(tgx::TrajRec)))) return rc;
+    if ((rc = e->totals.reserve(4 * sizeof(int64_t)))) return rc;
+    if ((rc = e->h_totals.reserve(4 * sizeof(int64_t)))) return rc;
+    return TGX_OK;
+}
+
+// counts -> plan tables.  `stop_from` selects the braking plan.
+int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_from, int64_t n,
+                const tgx_limits* limits, int32_t* d_counts, uint32_t* d_status, tgx_phases* d_phases,
+                int64_t* total_samples, cudaStream_t stream) {
+    if (!e || n < 0 || (n > 0 && !d_params)) return TGX_ERR_INVALID;
+    if (n > 0x7fffffffLL) return TGX_ERR_INVALID;
+    TGX_CUDA(cudaSetDevice(e->device));
+    e->has_plan = false;
+    e->plan_n = e->plan_tiles = e->plan_segs = e->plan_samples = 0;
+    if (total_samples) *total_samples = 0;
+    if (n == 0) {
+        e->has_plan = true;
+        return TGX_OK;
+    }
+    int rc = ensure_traj_scratch(e, n);
+    if (rc) return rc;
+
+    int32_t* cnt = e->cnt.as<int32_t>();
+    int32_t* nseg = e->nseg.as<int32_t>();
+    int32_t* ntile = e->ntile.as<int32_t>();
+    uint32_t* st = e->status.as<uint32_t>();
+    int64_t* seg_off = e->seg_off.as<int64_t>();
+    int64_t* tile_off = e->tile_off.as<int64_t>();
+    int64_t* totals = e->totals.as<int64_t>();
+
+    // pass 1: counts
+    TGX_CUDA(tgx::launch_plan_count(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, cnt, st, nseg,
+                                    ntile, stream));
+    e->launches += 1;
+    // trailing zero so that an exclusive scan over n+1 items leaves the grand total in element n
+    TGX_CUDA(cudaMemsetAsync(nseg + n, 0, sizeof(int32_t), stream));
+    TGX_CUDA(cudaMemsetAsync(ntile + n, 0, sizeof(int32_t), stream));
+
+    // pass 2: exclusive scans (segment and tile offsets) and the sample total
+    WideIter seg_in{nseg}, tile_in{ntile}, cnt_in{cnt};
+    size_t need = 0, t1 = 0, t2 = 0;
+    TGX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t1, seg_in, seg_off, (int)(n + 1), stream));
+    TGX_CUDA(cub::DeviceReduce::Sum(nullptr, t2, cnt_in, totals, (int)n, stream));
+    need = std::max(t1, t2);
+    if ((rc = e->cub_tmp.reserve(need))) return rc;
+    size_t tmp_bytes = e->cub_tmp.bytes;
+    TGX_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp_bytes, seg_in, seg_off, (int)(n + 1), stream));
+    tmp_bytes = e->cub_tmp.bytes;
+    TGX_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp_bytes, tile_in, tile_off, (int)(n + 1), stream));
+    tmp_bytes = e->cub_tmp.bytes;
+    TGX_CUDA(cub::DeviceReduce::Sum(e->cub_tmp.p, tmp_bytes, cnt_in, totals, (int)n, stream));
+    // (the cub scan / reduce launches are library plumbing and are not counted in tgx_launch_count)
+
+    int64_t* h = static_cast<int64_t*>(e->h_totals.p);
+    TGX_CUDA(cudaMemcpyAsync(h + 0, totals, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    TGX_CUDA(cudaMemcpyAsync(h + 1, seg_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    TGX_CUDA(cudaMemcpyAsync(h + 2, tile_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    TGX_CUDA(cudaStreamSynchronize(stream));
+    const int64_t tot_samples = h[0], tot_segs = h[1], tot_tiles = h[2];
+    if (tot_segs > 0x7fffffffLL || tot_tiles > 0x7fffffffLL) return TGX_ERR_CAPACITY;
+
+    if ((rc = e->segs.reserve((size_t)std::max<int64_t>(tot_segs, 1) * sizeof(tgx::Seg)))) return rc;
+    if ((rc = e->tiles.reserve((size_t)std::max<int64_t>(tot_tiles, 1) * sizeof(tgx::Tile)))) return rc;
+
+    // pass 3: fill
+    TGX_CUDA(tgx::launch_plan_fill(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, cnt, seg_off,
+                                   tile_off, e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(),
+                                   e->tiles.as<tgx::Tile>(), d_counts, d_status, d_phases, stream));
+    e->launches += 1;
+
+    e->has_plan = true;
+    e->plan_n = n;
+    e->plan_tiles = tot_tiles;
+    e->plan_segs = tot_segs;
+    e->plan_samples = tot_samples;
+    if (total_samples) *total_samples = tot_samples;
+    return TGX_OK;
+}
+
+int check_layout(const tgx_layout* out, int spt) {
+    if (!out || !out->d_base || out->capacity < 0) return TGX_ERR_INVALID;
+    const int64_t a = 4;   // doubles; keeps both store widths legal and rows sector-aligned
+    (void)spt;
+    if ((reinterpret_cast<uintptr_t>(out->d_base) & 31u) != 0) return TGX_ERR_ALIGNMENT;
+    if (out->chan_stride % a != 0) return TGX_ERR_ALIGNMENT;
+    if (!out->d_traj_offset && out->traj_stride % a != 0) return TGX_ERR_ALIGNMENT;
+    return TGX_OK;
+}
+
+tgx::OutView make_view(const tgx_layout* out) {
+    tgx::OutView v;
+    v.base = out->d_base;
+    v.traj_stride = out->traj_stride;
+    v.chan_stride = out->chan_stride;
+    v.traj_offset = out->d_traj_offset;
+    v.capacity = out->capacity;
+    v.channel_mask = out->channel_mask ? out->channel_mask : 0x3fffu;
+    return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tgx_version(void) { return TGX_VERSION; }
+
+const char* tgx_strerror(int code) {
+    switch (code) {
+        case TGX_OK: return "ok";
+        case TGX_ERR_INVALID: return "invalid argument";
+        case TGX_ERR_CUDA: return "CUDA runtime error (see tgx_last_cuda_error)";
+        case TGX_ERR_ALIGNMENT: return "output layout is not aligned for vector stores (32-byte base, strides multiple of 4 doubles)";
+        case TGX_ERR_NO_PLAN: return "no current plan: call tgx_plan first";
+        case TGX_ERR_NOMEM: return "out of memory";
+        case TGX_ERR_CAPACITY: return "capacity exceeded";
+        default: return "unknown error";
+    }
+}
+
+const char* tgx_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+int tgx_create(tgx_engine** out, int device) {
+    if (!out) return TGX_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaGetDeviceCount");
+    if (ndev <= 0 || device < 0 || device >= ndev) {
+        g_last_cuda_error = "no CUDA device " + std::to_string(device) + " (device count " + std::to_string(ndev) + ")";
+        return TGX_ERR_CUDA;
+    }
+    TGX_CUDA(cudaSetDevice(device));
+    tgx_engine* e = new (std::nothrow) tgx_engine();
+    if (!e) return TGX_ERR_NOMEM;
+    e->device = device;
+    *out = e;
+    return TGX_OK;
+}
+
+int tgx_destroy(tgx_engine* e) {
+    if (!e) return TGX_OK;
+    cudaSetDevice(e->device);
+    DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
+                      &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        e->h_params[i].release();
+        e->h_out[i].release();
+        e->h_cnt[i].release();
+        e->h_st[i].release();
+        e->h_ph[i].release();
+        e->h_from[i].release();
+        if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
+        if (e->hev[i]) cudaEventDestroy(e->hev[i]);
+    }
+    if (e->hev_eval) cudaEventDestroy(e->hev_eval);
+    e->h_totals.release();
+    delete e;
+    return TGX_OK;
+}
+
+int tgx_set_max_samples(tgx_engine* e, int64_t max_samples) {
+    if (!e || max_samples < 1 || max_samples > 0x7ffffff0LL) return TGX_ERR_INVALID;
+    e->max_samples = max_samples;
+    return TGX_OK;
+}
+
+// Tuning knob used by bench.py sweeps: tile = 1 << tile_shift samples per CTA, spt samples per thread.
+int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt) {
+    if (!e) return TGX_ERR_INVALID;
+    if (spt != 2 && spt != 4) return TGX_ERR_INVALID;
+    if (tile_shift < 9 || tile_shift > 11) return TGX_ERR_INVALID;
+    const int threads = (1 << tile_shift) / spt;
+    if (threads < 128 || threads > 1024) return TGX_ERR_INVALID;
+    e->tile_shift = tile_shift;
+    e->spt = spt;
+    e->has_plan = false;   // tile size is baked into a plan
+    return TGX_OK;
+}
+
+int64_t tgx_scratch_bytes(const tgx_engine* e) {
+    if (!e) return 0;
+    const DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
+                            &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles};
+    int64_t s = 0;
+    for (const DevBuf* b : bufs) s += (int64_t)b->bytes;
+    return s;
+}
+
+int64_t tgx_launch_count(const tgx_engine* e) { return e ? e->launches : 0; }
+int64_t tgx_plan_tiles(const tgx_engine* e) { return e && e->has_plan ? e->plan_tiles : 0; }
+int64_t tgx_plan_segments(const tgx_engine* e) { return e && e->has_plan ? e->plan_segs : 0; }
+
+int tgx_count(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits, int32_t* d_counts,
+              uint32_t* d_status, void* stream) {
+    if (!e || n < 0 || (n > 0 && !d_params)) return TGX_ERR_INVALID;
+    if (n == 0) return TGX_OK;
+    TGX_CUDA(cudaSetDevice(e->device));
+    TGX_CUDA(tgx::launch_plan_count(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, d_counts, d_status,
+                                    nullptr, nullptr, static_cast<cudaStream_t>(stream)));
+    e->launches += 1;
+    return TGX_OK;
+}
+
+int tgx_plan(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits, int32_t* d_counts,
+             uint32_t* d_status, tgx_phases* d_phases, int64_t* total_samples, void* stream) {
+    return plan_common(e, d_params, nullptr, n, limits, d_counts, d_status, d_phases, total_samples,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int tgx_plan_stop(tgx_engine* e, const tgx_params* d_params, int64_t n, const double* d_from, int32_t* d_counts,
+                  uint32_t* d_status, tgx_phases* d_phases, int64_t* total_samples, void* stream) {
+    if (n > 0 && !d_from) return TGX_ERR_INVALID;
+    return plan_common(e, d_params, d_from, n, nullptr, d_counts, d_status, d_phases, total_samples,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_max_a, void* stream) {
+    if (!e) return TGX_ERR_INVALID;
+    if (!e->has_plan) return TGX_ERR_NO_PLAN;
+    int rc = check_layout(out, e->spt);
+    if (rc) return rc;
+    TGX_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (e->plan_n == 0) return TGX_OK;
+    if (d_max_v) TGX_CUDA(cudaMemsetAsync(d_max_v, 0, (size_t)e->plan_n * sizeof(double), s));
+    if (d_max_a) TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)e->plan_n * sizeof(double), s));
+    if (e->plan_tiles == 0) return TGX_OK;
+    TGX_CUDA(tgx::launch_eval(e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(), e->tiles.as<tgx::Tile>(),
+                              e->plan_tiles, e->tile_shift, e->spt, make_view(out), true, d_max_v, d_max_a, s));
+    e->launches += 1;
+    return TGX_OK;
+}
+
+int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, double* d_max_v, double* d_max_a,
+                    uint32_t* d_status, void* stream) {
+    if (!e || !limits) return TGX_ERR_INVALID;
+    if (!e->has_plan) return TGX_ERR_NO_PLAN;
+    TGX_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t n = e->plan_n;
+    if (n == 0) return TGX_OK;
+    int rc;
+    if (!d_max_v) {
+        if ((rc = e->maxv.reserve((size_t)n * sizeof(double)))) return rc;
+        d_max_v = e->maxv.as<double>();
+    }
+    if (!d_max_a) {
+        if ((rc = e->maxa.reserve((size_t)n * sizeof(double)))) return rc;
+        d_max_a = e->maxa.as<double>();
+    }
+    TGX_CUDA(cudaMemsetAsync(d_max_v, 0, (size_t)n * sizeof(double), s));
+    TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)n * sizeof(double), s));
+    if (e->plan_tiles > 0) {
+        tgx::OutView none{};
+        TGX_CUDA(tgx::launch_eval(e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(), e->tiles.as<tgx::Tile>(),
+                                  e->plan_tiles, e->tile_shift, e->spt, none, false, d_max_v, d_max_a, s));
+        e->launches += 1;
+    }
+    TGX_CUDA(tgx::launch_feasibility_finalize(n, e->status.as<uint32_t>(), d_max_v, d_max_a, limits->v_max,
+                                              limits->a_max, d_flags, d_status, s));
+    e->launches += 1;
+    return TGX_OK;
+}
+
+int tgx_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi) {
+    if (n < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return TGX_ERR_INVALID;
+    // floor(rank*n/world) without overflow for n < 2^62 / world
+    *lo = (int64_t)(((__int128)n * rank) / world);
+    *hi = (int64_t)(((__int128)n * (rank + 1)) / world);
+    return TGX_OK;
+}
+
+// ---- pinned host memory for callers that want asynchronous D2H (bench.py's e2e leg, the C++ drop-in) ----
+void* tgx_alloc_host(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void tgx_free_host(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- host-buffer calls --------------------------------------------------------------------------------------
+
+static int host_streams(tgx_engine* e) {
+    for (int i = 0; i < 2; ++i) {
+        if (!e->hs[i]) TGX_CUDA(cudaStreamCreateWithFlags(&e->hs[i], cudaStreamNonBlocking));
+        if (!e->hev[i]) TGX_CUDA(cudaEventCreateWithFlags(&e->hev[i], cudaEventDisableTiming));
+    }
+    if (!e->hev_eval) TGX_CUDA(cudaEventCreateWithFlags(&e->hev_eval, cudaEventDisableTiming));
+    return TGX_OK;
+}
+
+int tgx_count_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                   int32_t* h_counts, uint32_t* h_status) {
+    if (!e || n < 0 || (n > 0 && !h_params)) return TGX_ERR_INVALID;
+    if (n == 0) return TGX_OK;
+    TGX_CUDA(cudaSetDevice(e->device));
+    int rc = host_streams(e);
+    if (rc) return rc;
+    cudaStream_t s = e->hs[0];
+    if ((rc = e->h_params[0].reserve((size_t)n * sizeof(tgx_params)))) return rc;
+    if ((rc = e->h_cnt[0].reserve((size_t)n * sizeof(int32_t)))) return rc;
+    if ((rc = e->h_st[0].reserve((size_t)n * sizeof(uint32_t)))) return rc;
+    TGX_CUDA(cudaMemcpyAsync(e->h_params[0].p, h_params, (size_t)n * sizeof(tgx_params), cudaMemcpyHostToDevice, s));
+    rc = tgx_count(e, e->h_params[0].as<tgx_params>(), n, limits, e->h_cnt[0].as<int32_t>(),
+                   e->h_st[0].as<uint32_t>(), s);
+    if (rc) return rc;
+    if (h_counts) TGX_CUDA(cudaMemcpyAsync(h_counts, e->h_cnt[0].p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (h_status) TGX_CUDA(cudaMemcpyAsync(h_status, e->h_st[0].p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    TGX_CUDA(cudaStreamSynchronize(s));
+    return TGX_OK;
+}
+
+// Shared body of tgx_generate_host / tgx_stop_host.
+static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_from, int64_t n,
+                    const tgx_limits* limits, double* h_out, int64_t capacity, int32_t* h_counts,
+                    uint32_t* h_status, tgx_phases* h_phases) {
+    if (!e || n < 0 || (n > 0 && (!h_params || !h_out)) || capacity < 0) return TGX_ERR_INVALID;
+    if (capacity % 4 != 0) return TGX_ERR_ALIGNMENT;
+    if (n == 0) return TGX_OK;
+    TGX_CUDA(cudaSetDevice(e->device));
+    int rc = host_streams(e);
+    if (rc) return rc;
+
+    // chunk so that one device staging buffer stays <= ~1 GiB (two are in flight)
+    const int64_t row_bytes = (int64_t)TGX_NCHAN * capacity * (int64_t)sizeof(double);
+    int64_t chunk = row_bytes > 0 ? std::max<int64_t>(1, ((int64_t)1 << 30) / row_bytes) : n;
+    chunk = std::min(chunk, n);
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+
+    for (int b = 0; b < 2 && b < nchunks; ++b) {
+        if ((rc = e->h_params[b].reserve((size_t)chunk * sizeof(tgx_params)))) return rc;
+        if ((rc = e->h_out[b].reserve((size_t)std::max<int64_t>(chunk * row_bytes, 32)))) return rc;
+        if ((rc = e->h_cnt[b].reserve((size_t)chunk * sizeof(int32_t)))) return rc;
+        if ((rc = e->h_st[b].reserve((size_t)chunk * sizeof(uint32_t)))) return rc;
+        if (h_phases && (rc = e->h_ph[b].reserve((size_t)chunk * sizeof(tgx_phases)))) return rc;
+        if (h_from && (rc = e->h_from[b].reserve((size_t)chunk * TGX_NCHAN * sizeof(double)))) return rc;
+    }
+
+    for (int64_t ci = 0; ci < nchunks; ++ci) {
+        const int b = (int)(ci & 1);
+        cudaStream_t s = e->hs[b];
+        const int64_t lo = ci * chunk, m = std::min(chunk, n - lo);
+        // the staging buffers of slot b are free once the copies issued two chunks ago have completed
+        if (ci >= 2) TGX_CUDA(cudaEventSynchronize(e->hev[b]));
+        // the plan tables are shared by both slots: do not re-plan before the previous chunk's evaluation is done
+        // (its D2H copy, the slow part, still overlaps with this chunk's planning and evaluation)
+        if (ci >= 1) TGX_CUDA(cudaStreamWaitEvent(s, e->hev_eval, 0));
+        TGX_CUDA(cudaMemcpyAsync(e->h_params[b].p, h_params + lo, (size_t)m * sizeof(tgx_params),
+                                 cudaMemcpyHostToDevice, s));
+        if (h_from)
+            TGX_CUDA(cudaMemcpyAsync(e->h_from[b].p, h_from + lo * TGX_NCHAN, (size_t)m * TGX_NCHAN * sizeof(double),
+                                     cudaMemcpyHostToDevice, s));
+        tgx_phases* d_ph = h_phases ? e->h_ph[b].as<tgx_phases>() : nullptr;
+        // planning synchronises stream s once; the other slot's D2H copies keep running meanwhile
+        if (h_from)
+            rc = tgx_plan_stop(e, e->h_params[b].as<tgx_params>(), m, e->h_from[b].as<double>(),
+                               e->h_cnt[b].as<int32_t>(), e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
+        else
+            rc = tgx_plan(e, e->h_params[b].as<tgx_params>(), m, limits, e->h_cnt[b].as<int32_t>(),
+                          e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
+        if (rc) return rc;
+        if (capacity > 0) {
+            tgx_layout lay{};
+            lay.d_base = e->h_out[b].as<double>();
+            lay.traj_stride = TGX_NCHAN * capacity;
+            lay.chan_stride = capacity;
+            lay.capacity = capacity;
+            rc = tgx_eval(e, &lay, nullptr, nullptr, s);
+            if (rc) return rc;
+            TGX_CUDA(cudaEventRecord(e->hev_eval, s));
+            TGX_CUDA(cudaMemcpyAsync(h_out + lo * TGX_NCHAN * capacity, e->h_out[b].p, (size_t)(m * row_bytes),
+                                     cudaMemcpyDeviceToHost, s));
+        }
+        if (h_counts)
+            TGX_CUDA(cudaMemcpyAsync(h_counts + lo, e->h_cnt[b].p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (h_status)
+            TGX_CUDA(cudaMemcpyAsync(h_status + lo, e->h_st[b].p, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (h_phases)
+            TGX_CUDA(cudaMemcpyAsync(h_phases + lo, e->h_ph[b].p, (size_t)m * sizeof(tgx_phases), cudaMemcpyDeviceToHost, s));
+        TGX_CUDA(cudaEventRecord(e->hev[b], s));
+    }
+    TGX_CUDA(cudaStreamSynchronize(e->hs[0]));
+    TGX_CUDA(cudaStreamSynchronize(e->hs[1]));
+    // TRUNCATED is a property of the caller's capacity, known only here
+    if (h_status && h_counts)
+        for (int64_t i = 0; i < n; ++i)
+            if ((int64_t)h_counts[i] > capacity) h_status[i] |= TGX_ST_TRUNCATED;
+    return TGX_OK;
+}
+
+int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits, double* h_out,
+                      int64_t capacity, int32_t* h_counts, uint32_t* h_status, tgx_phases* h_phases) {
+    return host_run(e, h_params, nullptr, n, limits, h_out, capacity, h_counts, h_status, h_phases);
+}
+
+int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const double* h_from, double* h_out,
+                  int64_t capacity, int32_t* h_counts, uint32_t* h_status, tgx_phases* h_phases) {
+    if (n > 0 && !h_from) return TGX_ERR_INVALID;
+    return host_run(e, h_params, h_from, n, nullptr, h_out, capacity, h_counts, h_status, h_phases);
+}
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+// eval.cu — the evaluation kernel of libtgx: create{Circle,Line,Figure8}Goal for every (trajectory, k).
+//
+// One CTA per Tile (tile_size consecutive samples of one trajectory), one thread per SPT adjacent samples.
+// The CTA stages its trajectory's TrajRec (64 B) and the tile's Seg records (64 B each) in shared memory,
+// every thread finds the segment its samples fall in, evaluates the closed form of the reference's
+// recurrences inside that segment
+//       v_k     = vb + j*dv                                   (j = k - kb; the clamped last step is exact)
+//       S_k     = sum_{m=1..j} v_m = j*vb + dv*j(j+1)/2
+//       theta_k = theta_b + S_k * (dt/r)          (Circle.cpp:50-51, Figure8.cpp:50-51: theta += (v/r)*dt)
+//       p_k     = p_b + S_k * (cos|sin theta) * dt            (Line.cpp:97-98: p = last + v*c*dt)
+// and then the reference's per-sample formulas (Circle.cpp:96-130, Line.cpp:91-115, Figure8.cpp:96-128) in
+// fp64.  The 14 channels go to struct-of-arrays planes with 128-bit (SPT=2) or 256-bit (SPT=4) streaming
+// vector stores: a warp writes 512 B / 1 KiB of contiguous, sector-aligned bytes per channel per instruction.
+// The kernel is store-bound: 112 B written per sample, ~0.3 B read.
+//
+// With REDUCE the per-trajectory maxima of |v_k|^2 and |a_k|^2 are reduced with warp shuffles, one shared-memory
+// hop per CTA and one atomicMax per tile (feasibility check, BASELINE.json configs 4-5).
+#include <cuda_runtime.h>
+
+#include "tgx_internal.cuh"
+
+namespace tgx {
+
+namespace {
+
+constexpr double kPiOver2 = 1.57079632679489661923;
+
+template <int SPT>
+struct VecStore;
+
+template <>
+struct VecStore<2> {
+    static __device__ __forceinline__ void st(double* p, const double (&x)[2]) {
+        asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x[0]), "d"(x[1]) : "memory");
+    }
+};
+
+template <>
+struct VecStore<4> {
+    static __device__ __forceinline__ void st(double* p, const double (&x)[4]) {
+        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
+                     "d"(x[3])
+                     : "memory");
+    }
+};
+
+// Store SPT adjacent samples of one channel; nvalid < SPT only on a trajectory's last, partial vector.
+template <int SPT>
+__device__ __forceinline__ void store_channel(double* p, const double (&x)[SPT], int nvalid) {
+    if (nvalid >= SPT) {
+        VecStore<SPT>::st(p, x);
+    } else {
+#pragma unroll
+        for (int u = 0; u < SPT; ++u)
+            if (u < nvalid) __stcs(p + u, x[u]);
+    }
+}
+
+// Position of sample k inside segment sg: j = k - kb, the (double) step count fj the closed forms use, and v.
+// On the step where the reference's std::min / std::max clamp fired (flag set, j == n) v is exactly the clamp
+// value and the closed forms are evaluated at j-1 plus one clamped step.
+struct SegPos {
+    int j;
+    bool last;     // j == n
+    bool clamp;    // last && clamp flag
+    double fj;     // clamp ? j-1 : j
+    double tri;    // fj*(fj+1)/2, exact
+    double v;
+};
+
+__device__ __forceinline__ SegPos seg_pos(const Seg& sg, int k) {
+    SegPos q;
+    q.j = k - sg.kb;
+    q.last = (q.j == sg.n);
+    q.clamp = q.last && (sg.flags & kSegClampLast);
+    q.fj = (double)(q.clamp ? q.j - 1 : q.j);
+    q.tri = 0.5 * (q.fj * (q.fj + 1.0));   // j(j+1) < 2^53: exact
+    q.v = q.clamp ? sg.vclamp : fma(q.fj, sg.dv, sg.vb);
+    return q;
+}
+
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double x) {
+    // For non-negative doubles the IEEE bit pattern is monotone in the value.
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(x));
+}
+
+}  // namespace
+
+template <int THREADS, int SPT, bool STORE, bool REDUCE>
+__global__ void __launch_bounds__(THREADS)
+eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, const Tile* __restrict__ tiles,
+            OutView out, double* __restrict__ max_v, double* __restrict__ max_a) {
+    __shared__ __align__(16) TrajRec s_rec;
+    __shared__ __align__(16) Seg s_seg[kMaxSegPerTile];
+    __shared__ int s_kend[kMaxSegPerTile];          // last sample of each segment
+    __shared__ double s_red[2][THREADS / 32];
+
+    // ---- stage the tile's constants in shared memory (16-byte chunks, one per thread) -------------------
+    const int4 tw = __ldg(reinterpret_cast<const int4*>(tiles) + blockIdx.x);   // {traj, k_lo, seg_begin, nseg}
+    const int traj = tw.x, k_lo = tw.y, seg_begin = tw.z;
+    const int nseg = tw.w < kMaxSegPerTile ? tw.w : kMaxSegPerTile;
+    {
+        const int4* src = reinterpret_cast<const int4*>(segs + seg_begin);
+        for (int t = threadIdx.x; t < 4 + 4 * nseg; t += THREADS) {
+            if (t < 4) {
+                reinterpret_cast<int4*>(&s_rec)[t] = __ldg(reinterpret_cast<const int4*>(recs + traj) + t);
+            } else {
+                const int4 w = __ldg(src + (t - 4));
+                reinterpret_cast<int4*>(s_seg)[t - 4] = w;
+                if (((t - 4) & 3) == 0) s_kend[(t - 4) >> 2] = w.x + w.y;   // kb + n
+            }
+        }
+    }
+    __syncthreads();
+
+    const int type = s_rec.type & kRecTypeMask;
+    const int n = s_rec.n;
+    const int k0 = k_lo + SPT * (int)threadIdx.x;
+    int limit = n;
+    if (STORE && out.capacity < (int64_t)limit) limit = (int)out.capacity;
+    const int nvalid = (REDUCE ? n : limit) - k0;   // samples this thread evaluates (may be <= 0)
+
+    double best_v2 = 0.0, best_a2 = 0.0;
+
+    if (nvalid > 0) {
+        // ---- segment of each sample: count the segments that end before it (independent broadcast reads) ----
+        int si[SPT];
+        {
+            int c = 0;
+            for (int i = 0; i + 1 < nseg; ++i) c += (k0 > s_kend[i]) ? 1 : 0;
+            si[0] = c;
+#pragma unroll
+            for (int u = 1; u < SPT; ++u) {
+                while (c + 1 < nseg && k0 + u > s_kend[c]) ++c;     // a thread may straddle a boundary
+                si[u] = c;
+            }
+        }
+
+        double* row = nullptr;
+        int nst = 0;
+        if (STORE) {
+            const int64_t toff = out.traj_offset ? __ldg(out.traj_offset + traj) : (int64_t)traj * out.traj_stride;
+            row = out.base + toff + k0;
+            nst = limit - k0;   // <= 0: nothing to store for this thread
+        }
+        const uint32_t mask = out.channel_mask;
+        const int64_t cs = out.chan_stride;
+#define TGX_STORE(CH, ARR)                                                                     \
+    do {                                                                                       \
+        if (STORE && nst > 0 && (mask & (1u << (CH)))) store_channel<SPT>(row + (CH) * cs, ARR, nst); \
+    } while (0)
+
+        double o[SPT];
+        if (type == TGX_LINE) {
+            // ---- Line::createLineGoal, Line.cpp:91-115 ------------------------------------------------
+            const double c = s_rec.f[0], s = s_rec.f[1], theta = s_rec.f[2], alt = s_rec.f[3], dt = s_rec.f[4];
+            const double cdt = c * dt, sdt = s * dt;
+            const bool force_b = (s_rec.type & kRecForceB) != 0;
+            double v[SPT], acc[SPT], py[SPT];
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) {
+                const Seg& sg = s_seg[si[u]];
+                const SegPos q = seg_pos(sg, k0 + u);
+                v[u] = q.v;
+                acc[u] = (q.j == 0) ? 0.0 : sg.acc;   // sample 0 is createLineGoal(A.x, A.y, 0, accel = 0, theta) (:40)
+                // S = sum of v over the segment's steps so far; p = p_base + S * (c|s) * dt   (:97-98)
+                const double S = fma(sg.dv, q.tri, q.fj * sg.vb) + (q.clamp ? sg.vclamp : 0.0);
+                const bool fb = force_b && (k0 + u == n - 1);                  // last goal forced to B (:81-82)
+                o[u] = fb ? s_rec.f[5] : fma(S, cdt, sg.s0);
+                py[u] = fb ? s_rec.f[6] : fma(S, sdt, sg.s1);
+            }
+            TGX_STORE(TGX_PX, o);
+            TGX_STORE(TGX_PY, py);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = alt;
+            TGX_STORE(TGX_PZ, o);
+            double vx[SPT], vy[SPT], ax[SPT], ay[SPT];
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) {
+                vx[u] = v[u] * c;
+                vy[u] = v[u] * s;
+                ax[u] = acc[u] * c;
+                ay[u] = acc[u] * s;
+            }
+            TGX_STORE(TGX_VX, vx);
+            TGX_STORE(TGX_VY, vy);
+            TGX_STORE(TGX_AX, ax);
+            TGX_STORE(TGX_AY, ay);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = 0.0;
+            TGX_STORE(TGX_VZ, o);
+            TGX_STORE(TGX_AZ, o);
+            TGX_STORE(TGX_JX, o);
+            TGX_STORE(TGX_JY, o);
+            TGX_STORE(TGX_JZ, o);
+            TGX_STORE(TGX_DPSI, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = theta;
+            TGX_STORE(TGX_PSI, o);
+            if (REDUCE) {
+#pragma unroll
+                for (int u = 0; u < SPT; ++u)
+                    if (u < nvalid) {
+                        best_v2 = fmax(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
+                        best_a2 = fmax(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
+                    }
+            }
+        } else {
+            const double r = s_rec.f[0], cx = s_rec.f[1], cy = s_rec.f[2], alt = s_rec.f[3];
+            const double dtr = s_rec.f[4], rinv = s_rec.f[5];
+            double v[SPT], th[SPT], sn[SPT], cn[SPT], om[SPT];
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) {
+                const Seg& sg = s_seg[si[u]];
+                const SegPos q = seg_pos(sg, k0 + u);
+                v[u] = q.v;
+                // theta_b + sum_{m<=j} (v_m / r) * dt  =  theta_b + j*w1 + j(j+1)/2 * (dv*dt/r); a hold (dv = 0) is the
+                // reference's exact arithmetic progression; a segment's last sample carries the replayed theta.
+                th[u] = q.last ? sg.acc : fma(q.tri, sg.dv * dtr, fma(q.fj, sg.s1, sg.s0));
+                sincos(th[u], &sn[u], &cn[u]);
+                om[u] = v[u] * rinv;                 // omega = v / r
+            }
+            if (type == TGX_CIRCLE) {
+                // ---- Circle::createCircleGoal, Circle.cpp:96-130 ---------------------------------------
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = fma(r, cn[u], cx);
+                TGX_STORE(TGX_PX, o);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = fma(r, sn[u], cy);
+                TGX_STORE(TGX_PY, o);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = alt;
+                TGX_STORE(TGX_PZ, o);
+                double vx[SPT], vy[SPT], ax[SPT], ay[SPT];
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) {
+                    const double v2r = v[u] * om[u];          // v^2 / r
+                    vx[u] = -v[u] * sn[u];
+                    vy[u] = v[u] * cn[u];
+                    ax[u] = -v2r * cn[u];                      // tangential term omitted as in :113-114
+                    ay[u] = -v2r * sn[u];
+                }
+                TGX_STORE(TGX_VX, vx);
+                TGX_STORE(TGX_VY, vy);
+                TGX_STORE(TGX_AX, ax);
+                TGX_STORE(TGX_AY, ay);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = (v[u] * om[u]) * om[u] * sn[u];     // v^3/r^2 * s
+                TGX_STORE(TGX_JX, o);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = -((v[u] * om[u]) * om[u]) * cn[u];
+                TGX_STORE(TGX_JY, o);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = th[u] + kPiOver2;                   // unwrapped (:125)
+                TGX_STORE(TGX_PSI, o);
+                TGX_STORE(TGX_DPSI, om);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = 0.0;
+                TGX_STORE(TGX_VZ, o);
+                TGX_STORE(TGX_AZ, o);
+                TGX_STORE(TGX_JZ, o);
+                if (REDUCE) {
+#pragma unroll
+                    for (int u = 0; u < SPT; ++u)
+                        if (u < nvalid) {
+                            best_v2 = fmax(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
+                            best_a2 = fmax(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
+                        }
+                }
+            } else {
+                // ---- Figure8::createFigure8Goal, Figure8.cpp:96-128 ------------------------------------
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = fma(r, sn[u], cx);
+                TGX_STORE(TGX_PX, o);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = fma(r * sn[u], cn[u], cy);
+                TGX_STORE(TGX_PY, o);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = alt;
+                TGX_STORE(TGX_PZ, o);
+                double vx[SPT], vy[SPT], ax[SPT], ay[SPT];
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) {
+                    const double rw = r * om[u];               // r_*omega (not v: :111)
+                    vx[u] = rw * cn[u];
+                    vy[u] = rw * (cn[u] * cn[u] - sn[u] * sn[u]);
+                    ax[u] = -rw * om[u] * sn[u];
+                    ay[u] = (-4.0 * r) * om[u] * om[u] * (sn[u] * cn[u]);
+                }
+                TGX_STORE(TGX_VX, vx);
+                TGX_STORE(TGX_VY, vy);
+                TGX_STORE(TGX_AX, ax);
+                TGX_STORE(TGX_AY, ay);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = atan2(vy[u], vx[u]);               // face the velocity (:123)
+                TGX_STORE(TGX_PSI, o);
+                TGX_STORE(TGX_DPSI, om);
+#pragma unroll
+                for (int u = 0; u < SPT; ++u) o[u] = 0.0;
+                TGX_STORE(TGX_VZ, o);
+                TGX_STORE(TGX_AZ, o);
+                TGX_STORE(TGX_JX, o);
+                TGX_STORE(TGX_JY, o);
+                TGX_STORE(TGX_JZ, o);
+                if (REDUCE) {
+#pragma unroll
+                    for (int u = 0; u < SPT; ++u)
+                        if (u < nvalid) {
+                            best_v2 = fmax(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
+                            best_a2 = fmax(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
+                        }
+                }
+            }
+        }
+#undef TGX_STORE
+    }
+
+    if (REDUCE) {
+        // ---- per-trajectory max |v|, max |a|: warp shuffles -> shared -> one atomicMax per tile ------------
+        best_v2 = warp_max(best_v2);
+        best_a2 = warp_max(best_a2);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) {
+            s_red[0][warp] = best_v2;
+            s_red[1][warp] = best_a2;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double a = lane < THREADS / 32 ? s_red[0][lane] : 0.0;
+            double b = lane < THREADS / 32 ? s_red[1][lane] : 0.0;
+            a = warp_max(a);
+            b = warp_max(b);
+            if (lane == 0) {
+                if (max_v) atomic_max_nonneg(max_v + traj, sqrt(a));
+                if (max_a) atomic_max_nonneg(max_a + traj, sqrt(b));
+            }
+        }
+    }
+}
+
+// Feasibility verdict per trajectory (BASELINE.json config 4): flag = max_v <= v_max && max_a <= a_max &&
+// no status bit set (the plan's status already carries OUTSIDE_BOUNDS when a box was given).
+__global__ void __launch_bounds__(256)
+feasibility_finalize_kernel(int64_t n, const uint32_t* __restrict__ plan_status, const double* __restrict__ max_v,
+                            const double* __restrict__ max_a, double v_max, double a_max,
+                            uint8_t* __restrict__ flags, uint32_t* __restrict__ status_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t st = plan_status[i];
+    if (max_v[i] > v_max) st |= TGX_ST_VMAX_EXCEEDED;
+    if (max_a[i] > a_max) st |= TGX_ST_AMAX_EXCEEDED;
+    if (flags) flags[i] = st == 0 ? 1 : 0;
+    if (status_out) status_out[i] = st;
+}
+
+// ---- host-side launchers -----------------------------------------------------------------------------------
+
+template <int THREADS, int SPT>
+static cudaError_t launch_eval_t(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles,
+                                 const OutView& out, bool store, double* max_v, double* max_a,
+                                 cudaStream_t stream) {
+    const bool reduce = max_v || max_a;
+    const unsigned grid = (unsigned)ntiles;
+    if (store && reduce)
+        eval_kernel<THREADS, SPT, true, true><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+    else if (store)
+        eval_kernel<THREADS, SPT, true, false><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+    else
+        eval_kernel<THREADS, SPT, false, true><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+    return cudaGetLastError();
+}
+
+// tile_shift in {9, 10, 11}; spt in {2, 4}: threads per CTA = (1 << tile_shift) / spt.
+cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles, int tile_shift,
+                        int spt, const OutView& out, bool store, double* max_v, double* max_a,
+                        cudaStream_t stream) {
+    if (ntiles <= 0) return cudaSuccess;
+    if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const int threads = (1 << tile_shift) / spt;
+#define TGX_CASE(T, S) \
+    if (threads == (T) && spt == (S)) return launch_eval_t<T, S>(recs, segs, tiles, ntiles, out, store, max_v, max_a, stream)
+    TGX_CASE(128, 4);
+    TGX_CASE(256, 2);
+    TGX_CASE(256, 4);
+    TGX_CASE(512, 2);
+    TGX_CASE(512, 4);
+    TGX_CASE(1024, 2);
+#undef TGX_CASE
+    return cudaErrorInvalidConfiguration;
+}
+
+cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, const double* max_v,
+                                        const double* max_a, double v_max, double a_max, uint8_t* flags,
+                                        uint32_t* status_out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t blocks = (n + 255) / 256;
+    feasibility_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, plan_status, max_v, max_a, v_max, a_max,
+                                                                     flags, status_out);
+    return cudaGetLastError();
+}
+
+}  // namespace tgx

@@ -1,0 +1,86 @@
+// tgx_internal.cuh — device-side records shared by the planning and evaluation kernels of libtgx.
+//
+// Data layout in HBM:
+//
+//   tgx_params[n]   caller's parameter records, 128 B each (one cache line per trajectory)
+//   TrajRec[n]      per-trajectory constants the evaluation kernel needs, 64 B each
+//   Seg[n_seg]      "linear-v segments": maximal runs of samples inside ONE phase of ONE tile over which
+//                   v_k is an arithmetic progression.  Each carries the exact (bit-for-bit replayed) state
+//                   of the reference's recurrence at its base sample, so the closed form inside a segment
+//                   never drifts by more than tile_size roundings from the reference's running sums.
+//   Tile[n_tile]    work list: one entry per (trajectory, block of tile_size consecutive samples)
+//
+// The planning kernels (plan.cu) build TrajRec/Seg/Tile by replaying the reference's scalar recurrences
+// (Circle.cpp:47-82, Line.cpp:46-68, Figure8.cpp:47-82) one thread per trajectory; the evaluation kernel
+// (eval.cu) consumes one Tile per CTA.
+#pragma once
+
+#include <cstdint>
+
+#include "../../include/tgx.h"
+
+namespace tgx {
+
+// type field of TrajRec: low byte = tgx_type, bit 8 = "force the last sample's position to B" (Line.cpp:81-82;
+// not set for braking trajectories, Line.cpp:117-152).
+constexpr int32_t kRecTypeMask = 0xff;
+constexpr int32_t kRecForceB = 1 << 8;
+
+struct __align__(16) TrajRec {
+    int32_t type;
+    int32_t n;        // sample count (0: rejected / empty)
+    double f[7];
+    // orbit (Circle, Figure8): f0 = r, f1 = cx, f2 = cy, f3 = alt, f4 = dt / r, f5 = 1 / r
+    // line:                    f0 = cos(theta), f1 = sin(theta), f2 = theta, f3 = alt, f4 = dt, f5 = Bx, f6 = By
+};
+static_assert(sizeof(TrajRec) == 64, "TrajRec must be 64 bytes");
+
+constexpr int32_t kSegClampLast = 1;   // sample kb+n has v == vclamp exactly (the std::min / std::max clamp fired)
+
+struct __align__(16) Seg {
+    int32_t kb;       // base sample index; the segment covers samples kb+1 .. kb+n (j = k - kb in 1..n);
+                      // the first segment of a generateTraj plan has kb = 0 and also serves sample 0 (j = 0)
+    int32_t n;
+    int32_t flags;
+    int32_t pad;
+    double vb;        // speed at the base sample (exact replay)
+    double dv;        // signed speed increment per step: +accel*dt, 0, or -accel*dt (the rounded product)
+    double vclamp;    // v_goal (ramp-up) or 0 (ramp-down)
+    double s0;        // orbit: theta at the base sample;  line: x at the base sample   (exact replay)
+    double s1;        // orbit: theta increment per step at the base speed (a hold's exact progression step, or
+                      //        (vb/r)*dt for a ramp);  line: y at the base sample
+    double acc;       // orbit: theta at the segment's LAST sample kb+n (exact replay);
+                      // line: the `accel` argument createLineGoal receives on this phase (+a1, 0, -a3)
+};
+static_assert(sizeof(Seg) == 64, "Seg must be 64 bytes");
+
+struct __align__(16) Tile {
+    int32_t traj;       // trajectory index
+    int32_t k_lo;       // first sample of the tile (multiple of tile_size)
+    int32_t seg_begin;  // index of the tile's first segment in Seg[]
+    int32_t nseg;       // number of segments that intersect the tile (all lie inside it)
+};
+static_assert(sizeof(Tile) == 16, "Tile must be 16 bytes");
+
+// A ramp is cut into chunks of at most kRampChunk steps, each starting from the exactly replayed state, which
+// bounds the closed form's rounding drift against the reference's running sums to kRampChunk half-ulps.
+constexpr int kRampChunk = 256;
+
+// Shared-memory segment table of the evaluation kernel.  Mandatory segments in one tile: every phase of a
+// trajectory (2*K ramps/holds + ramp-down = 17) could start inside the same tile, plus ramp chunks (tile/256 <= 8).
+// Optional segments (exact-progression breaks inside holds, plan.cu) are only emitted while the tile holds fewer than
+// kMaxOptionalSegPerTile segments, so the total never exceeds kMaxSegPerTile.
+constexpr int kMaxSegPerTile = 64;
+constexpr int kMaxOptionalSegPerTile = 36;
+
+// Device-side view of tgx_layout.
+struct OutView {
+    double* base;
+    int64_t traj_stride;
+    int64_t chan_stride;
+    const int64_t* traj_offset;
+    int64_t capacity;
+    uint32_t channel_mask;
+};
+
+}  // namespace tgx

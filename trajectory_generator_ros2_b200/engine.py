@@ -1,0 +1,314 @@
+"""ctypes binding of libtgx.so (include/tgx.h) plus a small torch-based convenience layer.
+
+torch is used only as plumbing: device memory (tensors), the current CUDA stream and, in ``sharding.py``,
+``torch.distributed``.  All sampling runs in the hand-written CUDA kernels behind the C-ABI; there is no Python
+or CPU implementation of any sampler in this package, and importing this module fails loudly when the built
+library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtgx.so")
+
+
+class TgxError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{what}: tgx error {code}" + (f" ({detail})" if detail else ""))
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or `make -C trajectory_generator_ros2_b200/csrc`. There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.tgx_version.restype = C.c_int
+    lib.tgx_strerror.restype = C.c_char_p
+    lib.tgx_strerror.argtypes = [C.c_int]
+    lib.tgx_last_cuda_error.restype = C.c_char_p
+    lib.tgx_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.tgx_destroy.argtypes = [vp]
+    lib.tgx_set_max_samples.argtypes = [vp, i64]
+    lib.tgx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
+    lib.tgx_scratch_bytes.restype = i64
+    lib.tgx_scratch_bytes.argtypes = [vp]
+    lib.tgx_launch_count.restype = i64
+    lib.tgx_launch_count.argtypes = [vp]
+    lib.tgx_plan_tiles.restype = i64
+    lib.tgx_plan_tiles.argtypes = [vp]
+    lib.tgx_plan_segments.restype = i64
+    lib.tgx_plan_segments.argtypes = [vp]
+    lib.tgx_count.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.tgx_plan.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64), vp]
+    lib.tgx_plan_stop.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64), vp]
+    lib.tgx_eval.argtypes = [vp, C.POINTER(abi.Layout), vp, vp, vp]
+    lib.tgx_feasibility.argtypes = [vp, C.POINTER(abi.Limits), vp, vp, vp, vp, vp]
+    lib.tgx_count_host.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.tgx_generate_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp]
+    lib.tgx_stop_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp]
+    lib.tgx_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    lib.tgx_alloc_host.restype = vp
+    lib.tgx_alloc_host.argtypes = [i64]
+    lib.tgx_free_host.argtypes = [vp]
+    return lib
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block partition of a batch (tgx_shard_range)."""
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    rc = lib().tgx_shard_range(n, rank, world, C.byref(lo), C.byref(hi))
+    if rc:
+        raise TgxError(rc, "tgx_shard_range", lib().tgx_strerror(rc).decode())
+    return int(lo.value), int(hi.value)
+
+
+def _limits_ptr(limits: Optional[abi.Limits]):
+    return C.cast(C.pointer(limits), C.c_void_p) if limits is not None else None
+
+
+@dataclass
+class Plan:
+    """What tgx_plan returned for a batch (tensors live on the engine's device)."""
+    n: int
+    counts: "object"          # torch.int32 [n]
+    status: "object"          # torch.int32 [n] (bit pattern of the uint32 status)
+    total_samples: int
+    phases: "object" = None   # torch.uint8 [n, sizeof(tgx_phases)] or None
+    tiles: int = 0
+    segments: int = 0
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory obtained from tgx_alloc_host."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().tgx_alloc_host(max(self.nbytes, 1))
+        if not self.ptr:
+            raise MemoryError(f"tgx_alloc_host({self.nbytes}) failed")
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().tgx_free_host(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One tgx_engine bound to one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._lib = lib()
+        self._h = C.c_void_p()
+        rc = self._lib.tgx_create(C.byref(self._h), device)
+        if rc:
+            raise TgxError(rc, "tgx_create", self._detail(rc))
+        self.device = device
+
+    # ------------------------------------------------------------------------------------------------
+    def _detail(self, rc: int) -> str:
+        s = self._lib.tgx_strerror(rc).decode()
+        if rc == abi.TGX_ERR_CUDA:
+            s += ": " + self._lib.tgx_last_cuda_error().decode()
+        return s
+
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise TgxError(rc, what, self._detail(rc))
+
+    def close(self):
+        if self._h:
+            self._lib.tgx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream() -> int:
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+
+    def _torch_device(self):
+        import torch
+        return torch.device("cuda", self.device)
+
+    # ------------------------------------------------------------------------------------------------
+    def set_max_samples(self, n: int):
+        self._check(self._lib.tgx_set_max_samples(self._h, n), "tgx_set_max_samples")
+
+    def set_tuning(self, tile_shift: int, spt: int):
+        self._check(self._lib.tgx_set_tuning(self._h, tile_shift, spt), "tgx_set_tuning")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.tgx_launch_count(self._h))
+
+    @property
+    def scratch_bytes(self) -> int:
+        return int(self._lib.tgx_scratch_bytes(self._h))
+
+    # ------------------------------------------------------------------------------------------------
+    def upload_params(self, params: np.ndarray):
+        """Host tgx_params array -> uint8 [n, 128] tensor on the engine's device."""
+        import torch
+        assert params.dtype == abi.PARAMS_DTYPE
+        raw = torch.from_numpy(np.ascontiguousarray(params).view(np.uint8).reshape(len(params), 128))
+        return raw.to(self._torch_device(), non_blocking=False)
+
+    def count(self, d_params, limits: Optional[abi.Limits] = None):
+        """tgx_count on a device-resident parameter tensor -> (counts int32 [n], status int32 [n])."""
+        import torch
+        n = int(d_params.shape[0])
+        counts = torch.empty(n, dtype=torch.int32, device=d_params.device)
+        status = torch.empty(n, dtype=torch.int32, device=d_params.device)
+        self._check(self._lib.tgx_count(self._h, d_params.data_ptr(), n, _limits_ptr(limits), counts.data_ptr(),
+                                        status.data_ptr(), self._stream()), "tgx_count")
+        return counts, status
+
+    def plan(self, d_params, limits: Optional[abi.Limits] = None, want_phases: bool = False,
+             want_outputs: bool = True) -> Plan:
+        """tgx_plan on a device-resident parameter tensor."""
+        import torch
+        n = int(d_params.shape[0])
+        counts = status = phases = None
+        if want_outputs:
+            counts = torch.empty(n, dtype=torch.int32, device=d_params.device)
+            status = torch.empty(n, dtype=torch.int32, device=d_params.device)
+        if want_phases:
+            phases = torch.empty((n, C.sizeof(abi.Phases)), dtype=torch.uint8, device=d_params.device)
+        total = C.c_int64(0)
+        self._check(self._lib.tgx_plan(self._h, d_params.data_ptr(), n, _limits_ptr(limits),
+                                       counts.data_ptr() if counts is not None else None,
+                                       status.data_ptr() if status is not None else None,
+                                       phases.data_ptr() if phases is not None else None,
+                                       C.byref(total), self._stream()), "tgx_plan")
+        return Plan(n, counts, status, int(total.value), phases, int(self._lib.tgx_plan_tiles(self._h)),
+                    int(self._lib.tgx_plan_segments(self._h)))
+
+    def plan_stop(self, d_params, d_from, want_phases: bool = False) -> Plan:
+        """tgx_plan_stop: d_from is a float64 [n, 14] tensor with the setpoints being braked from."""
+        import torch
+        n = int(d_params.shape[0])
+        assert d_from.dtype == torch.float64 and d_from.is_contiguous() and tuple(d_from.shape) == (n, abi.TGX_NCHAN)
+        counts = torch.empty(n, dtype=torch.int32, device=d_params.device)
+        status = torch.empty(n, dtype=torch.int32, device=d_params.device)
+        phases = torch.empty((n, C.sizeof(abi.Phases)), dtype=torch.uint8, device=d_params.device) if want_phases else None
+        total = C.c_int64(0)
+        self._check(self._lib.tgx_plan_stop(self._h, d_params.data_ptr(), n, d_from.data_ptr(), counts.data_ptr(),
+                                            status.data_ptr(), phases.data_ptr() if phases is not None else None,
+                                            C.byref(total), self._stream()), "tgx_plan_stop")
+        return Plan(n, counts, status, int(total.value), phases, int(self._lib.tgx_plan_tiles(self._h)),
+                    int(self._lib.tgx_plan_segments(self._h)))
+
+    def eval(self, out, capacity: Optional[int] = None, plane_major: bool = False, max_v=None, max_a=None,
+             channel_mask: int = 0, traj_offset=None):
+        """tgx_eval into a float64 tensor.
+
+        out: [n, 14, row] (trajectory-major, default) or [14, n, row] (plane_major=True).
+        """
+        import torch
+        assert out.dtype == torch.float64 and out.is_contiguous()
+        lay = abi.Layout()
+        lay.d_base = out.data_ptr()
+        if plane_major:
+            nch, n, row = out.shape
+            lay.traj_stride, lay.chan_stride = row, n * row
+        else:
+            n, nch, row = out.shape
+            lay.traj_stride, lay.chan_stride = nch * row, row
+        assert nch == abi.TGX_NCHAN
+        lay.capacity = row if capacity is None else capacity
+        lay.channel_mask = channel_mask
+        lay.d_traj_offset = traj_offset.data_ptr() if traj_offset is not None else None
+        self._check(self._lib.tgx_eval(self._h, C.byref(lay), max_v.data_ptr() if max_v is not None else None,
+                                       max_a.data_ptr() if max_a is not None else None, self._stream()), "tgx_eval")
+
+    def eval_layout(self, lay: abi.Layout, max_v=None, max_a=None):
+        self._check(self._lib.tgx_eval(self._h, C.byref(lay), max_v.data_ptr() if max_v is not None else None,
+                                       max_a.data_ptr() if max_a is not None else None, self._stream()), "tgx_eval")
+
+    def feasibility(self, limits: abi.Limits, n: int, flags=None, max_v=None, max_a=None, status=None):
+        """tgx_feasibility on the current plan -> (flags uint8 [n], max_v, max_a, status int32)."""
+        import torch
+        dev = self._torch_device()
+        flags = torch.empty(n, dtype=torch.uint8, device=dev) if flags is None else flags
+        max_v = torch.empty(n, dtype=torch.float64, device=dev) if max_v is None else max_v
+        max_a = torch.empty(n, dtype=torch.float64, device=dev) if max_a is None else max_a
+        status = torch.empty(n, dtype=torch.int32, device=dev) if status is None else status
+        self._check(self._lib.tgx_feasibility(self._h, C.byref(limits), flags.data_ptr(), max_v.data_ptr(),
+                                              max_a.data_ptr(), status.data_ptr(), self._stream()), "tgx_feasibility")
+        return flags, max_v, max_a, status
+
+    # ---- host-buffer calls -------------------------------------------------------------------------
+    def count_host(self, params: np.ndarray, limits: Optional[abi.Limits] = None):
+        params = np.ascontiguousarray(params)
+        n = len(params)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.tgx_count_host(self._h, params.ctypes.data, n, _limits_ptr(limits), counts.ctypes.data,
+                                             status.ctypes.data), "tgx_count_host")
+        return counts, status
+
+    def generate_host(self, params: np.ndarray, capacity: int, limits: Optional[abi.Limits] = None,
+                      out: Optional[np.ndarray] = None, want_phases: bool = False):
+        """tgx_generate_host -> (out [n, 14, capacity], counts, status, phases or None)."""
+        params = np.ascontiguousarray(params)
+        n = len(params)
+        if out is None:
+            out = np.full((n, abi.TGX_NCHAN, capacity), np.nan)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (n, abi.TGX_NCHAN, capacity)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.uint32)
+        phases = np.zeros(n, dtype=abi.PHASES_DTYPE) if want_phases else None
+        self._check(self._lib.tgx_generate_host(self._h, params.ctypes.data, n, _limits_ptr(limits), out.ctypes.data,
+                                                capacity, counts.ctypes.data, status.ctypes.data,
+                                                phases.ctypes.data if phases is not None else None),
+                    "tgx_generate_host")
+        return out, counts, status, phases
+
+    def stop_host(self, params: np.ndarray, from14: np.ndarray, capacity: int, want_phases: bool = False):
+        """tgx_stop_host -> (out [n, 14, capacity], counts, status, phases or None)."""
+        params = np.ascontiguousarray(params)
+        n = len(params)
+        from14 = np.ascontiguousarray(from14, dtype=np.float64).reshape(n, abi.TGX_NCHAN)
+        out = np.full((n, abi.TGX_NCHAN, capacity), np.nan)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.uint32)
+        phases = np.zeros(n, dtype=abi.PHASES_DTYPE) if want_phases else None
+        self._check(self._lib.tgx_stop_host(self._h, params.ctypes.data, n, from14.ctypes.data, out.ctypes.data,
+                                            capacity, counts.ctypes.data, status.ctypes.data,
+                                            phases.ctypes.data if phases is not None else None), "tgx_stop_host")
+        return out, counts, status, phases

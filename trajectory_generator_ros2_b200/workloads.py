@@ -1,0 +1,143 @@
+"""Synthetic parameter batches for the BASELINE.json configurations.
+
+Every generator draws trajectory i from a counter-based stream keyed by (seed, i // BLOCK), so any contiguous shard
+[lo, hi) of a batch can be produced on its own rank and is identical to the same slice of the full batch: the
+multi-GPU runs need no host->host or device->device parameter exchange.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import abi
+
+BLOCK = 1 << 16
+DT = 0.01   # pub_freq 100 Hz (default.yaml:6, TrajectoryGenerator.cpp:171-172)
+
+
+def _blocks(lo: int, hi: int):
+    b = lo // BLOCK
+    while b * BLOCK < hi:
+        s, e = max(lo, b * BLOCK), min(hi, (b + 1) * BLOCK)
+        yield b, s - b * BLOCK, e - b * BLOCK
+        b += 1
+
+
+def _draw(seed: int, lo: int, hi: int, fill):
+    """Run `fill(rng, m) -> params[m]` per BLOCK and cut the requested slice out."""
+    parts = []
+    for b, s, e in _blocks(lo, hi):
+        rng = np.random.default_rng([seed, b])
+        parts.append(fill(rng, BLOCK)[s:e])
+    if not parts:
+        return np.zeros(0, dtype=abi.PARAMS_DTYPE)
+    return abi.concat(parts)
+
+
+def _fill_circles_cfg2(rng, m, kind=abi.TGX_CIRCLE):
+    p = np.zeros(m, dtype=abi.PARAMS_DTYPE)
+    p["type"] = kind
+    p["n_vgoals"] = 1
+    p["dt"] = DT
+    p["r"] = rng.uniform(0.5, 5.0, m)
+    p["cx"] = rng.uniform(-2.0, 2.0, m)
+    p["cy"] = rng.uniform(-2.0, 2.0, m)
+    p["alt"] = rng.uniform(1.0, 2.5, m)
+    v = rng.uniform(0.5, 3.0, m)
+    a = rng.uniform(0.7, 2.0, m)
+    p["v_goals"][:, 0] = v
+    p["accel"] = a
+    p["t_traj"] = 9.98 - 2.0 * v / a
+    return p
+
+
+def default_circle() -> np.ndarray:
+    """BASELINE.json configs[0]: the single circle of config/default.yaml (:5-6, :38-44), traj_type Circle."""
+    return abi.circle_params(alt=1.8, r=3.4, cx=0.0, cy=0.0, v_goals=[1.0, 2.0, 2.0], t_traj=80.0, accel=0.4, dt=DT)
+
+
+def default_figure8() -> np.ndarray:
+    return abi.figure8_params(alt=1.8, r=3.4, cx=0.0, cy=0.0, v_goals=[1.0, 2.0, 2.0], t_traj=80.0, accel=0.4, dt=DT)
+
+
+def default_line() -> np.ndarray:
+    """config/default.yaml:46-53 (Line built with z = alt for both ends, TrajectoryGenerator.cpp:283-285)."""
+    return abi.line_params(alt=1.8, A=[0.0, -3.0, 1.8], B=[0.0, 3.0, 1.8], v_goals=[1.0], a1=1.5, a3=1.0, dt=DT)
+
+
+def circles_cfg2(n: int, seed: int = 1234, lo: int = 0, hi: int | None = None) -> np.ndarray:
+    """BASELINE.json configs[1]: random circles with ~1000 samples each (N_i in {1000, 1001}), all three phases
+    present, every row fits a 1024-sample stride."""
+    hi = n if hi is None else hi
+    return _draw(seed, lo, hi, _fill_circles_cfg2)
+
+
+def _fill_mixed_cfg3(rng, m):
+    p = np.zeros(m, dtype=abi.PARAMS_DTYPE)
+    kind = rng.choice([abi.TGX_CIRCLE, abi.TGX_LINE, abi.TGX_FIGURE8], size=m, p=[0.4, 0.3, 0.3])
+    orb = _fill_circles_cfg2(rng, m)
+    # half of the orbits get two increasing goal speeds (two ramp-ups, two holds)
+    two = rng.random(m) < 0.5
+    v1 = orb["v_goals"][:, 0].copy()
+    v0 = v1 * rng.uniform(0.3, 0.8, m)
+    a = orb["accel"]
+    orb["n_vgoals"] = np.where(two, 2, 1)
+    orb["v_goals"][:, 0] = np.where(two, v0, v1)
+    orb["v_goals"][:, 1] = np.where(two, v1, 0.0)
+    orb["t_traj"] = np.where(two, (9.98 - 2.0 * v1 / a) / 2.0, orb["t_traj"])
+    p[:] = orb
+    p["type"] = kind
+    # lines: A, B ~ U[-4,4]^2, redrawn until the cruise segment is at least 20 % of |B - A|
+    is_line = kind == abi.TGX_LINE
+    idx = np.nonzero(is_line)[0]
+    ln = np.zeros(len(idx), dtype=abi.PARAMS_DTYPE)
+    ln["type"] = abi.TGX_LINE
+    ln["n_vgoals"] = 1
+    ln["dt"] = DT
+    ln["alt"] = p["alt"][idx]
+    v = rng.uniform(0.5, 2.0, len(idx))
+    a1 = rng.uniform(0.8, 2.0, len(idx))
+    a3 = rng.uniform(0.5, 1.5, len(idx))
+    A = rng.uniform(-4.0, 4.0, (len(idx), 2))
+    B = rng.uniform(-4.0, 4.0, (len(idx), 2))
+    for _ in range(64):
+        d = np.hypot(*(B - A).T)
+        d2 = d - 0.5 * v * v / a1 - 0.5 * v * v / a3
+        bad = d2 < 0.2 * d
+        if not bad.any():
+            break
+        nb = int(bad.sum())
+        A[bad] = rng.uniform(-4.0, 4.0, (nb, 2))
+        B[bad] = rng.uniform(-4.0, 4.0, (nb, 2))
+        v[bad] = rng.uniform(0.5, 2.0, nb)
+    ln["A"][:, :2], ln["B"][:, :2] = A, B
+    ln["A"][:, 2] = ln["alt"]
+    ln["B"][:, 2] = ln["alt"]
+    ln["v_goal"], ln["a1"], ln["a3"] = v, a1, a3
+    p[idx] = ln
+    return p
+
+
+def mixed_cfg3(n: int, seed: int = 1235, lo: int = 0, hi: int | None = None) -> np.ndarray:
+    """BASELINE.json configs[2]: circle 0.4 / line 0.3 / figure-eight 0.3 with one or two ramp-ups."""
+    hi = n if hi is None else hi
+    return _draw(seed, lo, hi, _fill_mixed_cfg3)
+
+
+def _fill_montecarlo_cfg4(rng, m):
+    p = _fill_circles_cfg2(rng, m)
+    p["r"] = rng.uniform(0.2, 5.0, m)
+    v = rng.uniform(0.2, 8.0, m)
+    a = p["accel"]
+    p["v_goals"][:, 0] = v
+    # keep ~1000 samples per trajectory: the hold shrinks as the ramps grow, but never below 0.5 s
+    p["t_traj"] = np.maximum(9.98 - 2.0 * v / a, 0.5)
+    return p
+
+
+def montecarlo_cfg4(n: int, seed: int = 1236, lo: int = 0, hi: int | None = None) -> np.ndarray:
+    """BASELINE.json configs[3]/[4]: wide-range circles for the max-|v| / max-|a| feasibility sweep."""
+    hi = n if hi is None else hi
+    return _draw(seed, lo, hi, _fill_montecarlo_cfg4)
+
+
+MONTECARLO_LIMITS = dict(box=(-5.0, 5.0, -5.0, 5.0, -5.0, 5.0), v_max=5.0, a_max=6.0)
