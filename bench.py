@@ -58,58 +58,73 @@ WORKLOAD_DESC = {
 
 # ---- clocks ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; only samples inside [mark_start, mark_stop] count."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=self.tmp, stderr=subprocess.DEVNULL)
+            time.sleep(1.0)     # let the sampler come up before the timed region starts
         except Exception:
             self.proc = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.tmp.flush()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         try:
             with open(self.tmp.name) as f:
                 for line in f:
                     parts = [x.strip() for x in line.split(",")]
-                    if len(parts) < 7:
+                    if len(parts) < 8:
                         continue
                     try:
-                        sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                        ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]))
                     except ValueError:
                         continue
-                    for nm, val in zip(names, parts[3:7]):
-                        if val.lower().startswith("active"):
-                            reasons.add(nm)
         finally:
             try:
                 os.unlink(self.tmp.name)
             except OSError:
                 pass
-        if sm:
-            # samples under load = the upper half of the power readings (the timed region is short)
-            order = np.argsort(pw)
-            hot = order[len(order) // 2:]
-            out["sm_mhz"] = float(np.median(np.asarray(sm)[hot]))
-            out["sm_max_mhz"] = float(max(mx))
-            out["power_w_max"] = float(max(pw))
-            out["samples"] = len(sm)
+        if not rows:
+            return out
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
+        used = inside if inside else rows
+        reasons = set()
+        for r in used:
+            for nm, val in zip(names, r[4]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        out["sm_mhz"] = float(np.median([r[1] for r in used]))
+        out["sm_max_mhz"] = float(max(r[2] for r in used))
+        out["power_w_max"] = float(max(r[3] for r in used))
+        out["samples"] = len(used)
+        out["window"] = "timed region" if inside else "whole run (no sample fell inside the timed region)"
         out["reasons"] = sorted(reasons)
         return out
 
@@ -203,7 +218,7 @@ def run_ours(args):
 
     eng = Engine(local_rank)
     if args.tile_shift or args.spt:
-        eng.set_tuning(args.tile_shift or 10, args.spt or 2)
+        eng.set_tuning(args.tile_shift or 10, args.spt or 4)
 
     n = args.n_per_gpu
     lo, hi = rank * n, (rank + 1) * n                      # weak scaling: every GPU owns n trajectories
@@ -269,8 +284,10 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step(False)
-    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.mark_start()
     launches0 = eng.launch_count
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -278,6 +295,8 @@ def run_ours(args):
         step(True)
     t_stop.record()
     barrier()
+    if sampler:
+        sampler.mark_stop()
     elapsed_ms = t_start.elapsed_time(t_stop)
     launches = eng.launch_count - launches0
     clocks = sampler.stop() if sampler else None
@@ -396,7 +415,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="circles_cfg2", choices=sorted(WORKLOAD_DESC))

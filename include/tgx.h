@@ -180,8 +180,17 @@ int tgx_destroy(tgx_engine* e);
 int tgx_set_max_samples(tgx_engine* e, int64_t max_samples);
 /* Kernel shape used by tgx_eval / tgx_feasibility: one CTA evaluates a tile of (1 << tile_shift) consecutive
  * samples of one trajectory (tile_shift in 9..11), each thread `spt` adjacent samples (2: 128-bit stores,
- * 4: 256-bit stores).  Invalidates the current plan.  Default 10, 2. */
+ * 4: 256-bit stores).  Invalidates the current plan.  Default 10, 4. */
 int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt);
+/* Planning mode.  Sample counts, phase boundaries, status bits and every speed v_k are bit-identical to the
+ * reference in both modes.
+ *   exact_ramps = 0 (default): ramps are advanced in exact arithmetic-progression jumps of v and the angle / position
+ *       state in closed form per jump; the state at segment bases then differs from the reference's running sums by
+ *       those sums' own accumulated rounding (<= ~1e-12 rad, ~1e-12 m).  O(#binades) work per trajectory.
+ *   exact_ramps = 1: every ramp step is replayed with the reference's operation sequence; the (v, theta | x, y) state
+ *       at every segment base, and theta on every hold sample, is bit-identical to the reference.  O(N) work.
+ * Braking plans (tgx_plan_stop) always use the exact replay.  Invalidates the current plan. */
+int tgx_set_plan_mode(tgx_engine* e, int exact_ramps);
 /* Bytes of device scratch currently held by the engine (plan tables). */
 int64_t tgx_scratch_bytes(const tgx_engine* e);
 
@@ -254,6 +263,10 @@ int64_t tgx_launch_count(const tgx_engine* e);
 /* Tiles / segments of the current plan (0 if none). */
 int64_t tgx_plan_tiles(const tgx_engine* e);
 int64_t tgx_plan_segments(const tgx_engine* e);
+
+/* Debug aid: checks the planner's hoisted-reciprocal division against IEEE division on n*per_thread pseudo-random
+ * operand pairs on the GPU; *mismatches must come back 0. */
+int tgx_selftest_division(tgx_engine* e, int64_t n, uint64_t seed, int per_thread, uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

@@ -36,3 +36,11 @@ def engine():
     e = Engine(0)
     yield e
     e.close()
+
+
+@pytest.fixture(params=["fast", "exact"])
+def mode_engine(request, engine):
+    """The engine in each planning mode (tgx_set_plan_mode): fast exact-v jumps (default) and step-by-step replay."""
+    engine.set_plan_mode(request.param == "exact")
+    yield engine
+    engine.set_plan_mode(False)

@@ -56,7 +56,8 @@ def check_batch(engine, oracle, params, what, **kw):
 
 # ---- known-answer cases (config/default.yaml) ------------------------------------------
 
-def test_default_circle(engine, oracle):
+def test_default_circle(mode_engine, oracle):
+    engine = mode_engine
     p = workloads.default_circle()
     out, counts, status, ph = gpu_generate(engine, p)
     assert counts[0] == 25001 and status[0] == 0
@@ -65,12 +66,13 @@ def test_default_circle(engine, oracle):
     assert msgs[16500] == "Circle traj: reached 2.000000 m/s, keeping constant v for 80.000000 s"
     ref, _, _ = oracle.generate(p)
     e = assert_samples_close(out[0, :, :25001], ref, "default circle")
-    assert e["pos_abs"] < 2e-11, e   # tile-aligned exact bases keep the drift far below the 1e-9 m budget
+    assert e["pos_abs"] < 2e-11, e   # exact hold progressions keep the drift far below the 1e-9 m budget
     # unwrapped yaw at the end of the run (Circle.cpp:125)
     assert abs(out[0, abi.PSI, 25000] - 122.15903162087876) < 1e-9
 
 
-def test_default_figure8(engine, oracle):
+def test_default_figure8(mode_engine, oracle):
+    engine = mode_engine
     p = workloads.default_figure8()
     out, counts, status, ph = gpu_generate(engine, p)
     assert counts[0] == 25001 and status[0] == 0
@@ -80,7 +82,8 @@ def test_default_figure8(engine, oracle):
     assert (out[0, abi.JX:abi.JZ + 1, :25001] == 0).all()   # Figure8 jerk is identically zero (Figure8.cpp:117-119)
 
 
-def test_default_line(engine, oracle):
+def test_default_line(mode_engine, oracle):
+    engine = mode_engine
     p = workloads.default_line()
     out, counts, status, ph = gpu_generate(engine, p)
     assert counts[0] == 685 and status[0] == 0
@@ -94,9 +97,35 @@ def test_default_line(engine, oracle):
     np.testing.assert_allclose(out[0, abi.AY, [1, 67, 68, 584, 585, 684]], [1.5, 1.5, 0, 0, -1, -1], atol=1e-15)
 
 
+def test_hold_theta_is_bit_exact(engine, oracle):
+    """Inside a hold the reference's theta is an exact arithmetic progression per binade; the plan cuts segments at
+    the binade crossings, so Circle yaw (theta + pi/2, Circle.cpp:125) must equal the oracle's bit for bit there,
+    and every segment's last sample is the exactly replayed state."""
+    p = workloads.default_circle()
+    engine.set_plan_mode(True)
+    try:
+        out, counts, status, ph = gpu_generate(engine, p)
+    finally:
+        engine.set_plan_mode(False)
+    ref, _, _ = oracle.generate(p)
+    psi, rpsi = out[0, abi.PSI, :25001], ref[abi.PSI]
+    for lo, hi in ((251, 8250), (8501, 16500), (16501, 24500)):     # the three 80 s holds
+        assert (psi[lo:hi + 1] == rpsi[lo:hi + 1]).all(), (lo, hi)
+    assert psi[250] == rpsi[250] and psi[8500] == rpsi[8500] and psi[25000] == rpsi[25000]   # ramp ends
+    # ramps: closed form between exactly replayed chunk bases, <= kRampChunk half-ulps of drift
+    assert np.abs(psi - rpsi).max() < 2e-12
+
+
+def test_planner_division_selftest(engine):
+    """The ramps divide v by the loop-invariant r with a hoisted reciprocal; it must equal IEEE division."""
+    assert engine.selftest_division(1 << 22, seed=12345, per_thread=64) == 0
+    assert engine.selftest_division(1 << 20, seed=777, per_thread=256) == 0
+
+
 # ---- edge cases ------------------------------------------------------------------------------------------
 
-def test_count_traps(engine, oracle):
+def test_count_traps(mode_engine, oracle):
+    engine = mode_engine
     """Counts are decided by accumulated rounding, not by ceil() formulas (SURVEY.md §7.3 hard part 1)."""
     cases = [(2.0, 0.3, 10.0), (3.0, 0.1, 1.0), (1.0, 0.3, 5.0), (1.0, 0.4, 80.0), (2.5, 0.5, 20.0)]
     params = abi.concat([abi.circle_params(1.5, 2.0, 0.1, -0.2, [v], t, a, 0.01) for v, a, t in cases])
@@ -110,7 +139,8 @@ def test_count_traps(engine, oracle):
     check_batch(engine, oracle, params, "count traps")
 
 
-def test_round_parameter_grid_counts(engine, oracle):
+def test_round_parameter_grid_counts(mode_engine, oracle):
+    engine = mode_engine
     """Human-style round parameters: every (v, a, t) of a grid must give the oracle's exact count."""
     vs = [0.5, 1.0, 1.5, 2.0, 3.0]
     accs = [0.1, 0.2, 0.3, 0.4, 0.5, 0.7, 1.0]
@@ -128,7 +158,8 @@ def test_round_parameter_grid_counts(engine, oracle):
     np.testing.assert_array_equal(plan.counts.cpu().numpy(), o_counts)
 
 
-def test_vgoals_edge_cases(engine, oracle):
+def test_vgoals_edge_cases(mode_engine, oracle):
+    engine = mode_engine
     params = abi.concat([
         abi.circle_params(1.8, 3.4, 0, 0, [2.0, 1.0], 1.0, 0.4, 0.01),            # decreasing: warning, N = 1201
         abi.circle_params(1.8, 3.4, 0, 0, [1.0, 2.0, 2.0], 2.0, 0.4, 0.01),       # repeated goal: zero-length ramp
@@ -143,7 +174,8 @@ def test_vgoals_edge_cases(engine, oracle):
     check_batch(engine, oracle, params, "v_goals edge cases")
 
 
-def test_bad_params_are_rejected(engine, oracle):
+def test_bad_params_are_rejected(mode_engine, oracle):
+    engine = mode_engine
     good = abi.circle_params(1.8, 3.4, 0, 0, [1.0], 2.0, 0.4, 0.01)
     bad = []
     for field, val in (("accel", 0.0), ("accel", -1.0), ("r", 0.0), ("dt", 0.0), ("dt", float("nan")),
@@ -164,7 +196,8 @@ def test_bad_params_are_rejected(engine, oracle):
     assert (ph["n"][1:-1] == 0).all()
 
 
-def test_too_long_guard(engine, oracle):
+def test_too_long_guard(mode_engine, oracle):
+    engine = mode_engine
     """Parameters for which the reference would loop (almost) for ever are cut by the max_samples guard."""
     params = abi.concat([
         abi.circle_params(1.0, 1.0, 0, 0, [1.0], 1.0, 1e-30, 0.01),       # v + a*dt never reaches v_goal
@@ -183,7 +216,8 @@ def test_too_long_guard(engine, oracle):
         engine.set_max_samples(abi.DEFAULT_MAX_SAMPLES)
 
 
-def test_line_edge_cases(engine, oracle):
+def test_line_edge_cases(mode_engine, oracle):
+    engine = mode_engine
     params = abi.concat([
         workloads.default_line(),
         abi.line_params(1.8, [0, -3, 1.8], [0, -2.5, 1.8], [1.0], 1.5, 1.0, 0.01),     # d2 < 0: overshoots B
@@ -198,13 +232,15 @@ def test_line_edge_cases(engine, oracle):
 
 # ---- random batches -----------------------------------------------------------------------------------------
 
-def test_random_circles_cfg2(engine, oracle):
+def test_random_circles_cfg2(mode_engine, oracle):
+    engine = mode_engine
     params = workloads.circles_cfg2(3000)
     worst = check_batch(engine, oracle, params, "cfg2 circles", capacity=1024, want_phases=False)
     assert worst["pos_abs"] < 1e-11, worst
 
 
-def test_random_mixed_cfg3(engine, oracle):
+def test_random_mixed_cfg3(mode_engine, oracle):
+    engine = mode_engine
     params = workloads.mixed_cfg3(3000)
     assert set(np.unique(params["type"])) == {0, 1, 2}
     check_batch(engine, oracle, params, "cfg3 mixed", want_phases=True)
@@ -216,7 +252,7 @@ def test_layouts_and_tunings_agree(engine, oracle):
     params = abi.concat([workloads.mixed_cfg3(300), workloads.default_circle()])
     base, counts, status, _ = gpu_generate(engine, params, want_phases=False)
     try:
-        for shift, spt in ((9, 2), (9, 4), (10, 4), (11, 2), (11, 4)):
+        for shift, spt in ((9, 2), (9, 4), (10, 2), (11, 2), (11, 4)):
             engine.set_tuning(shift, spt)
             for plane_major in (False, True):
                 out, c2, s2, _ = gpu_generate(engine, params, want_phases=False, plane_major=plane_major)
@@ -226,7 +262,7 @@ def test_layouts_and_tunings_agree(engine, oracle):
                 assert (np.isnan(out) == np.isnan(base)).all()
                 np.testing.assert_allclose(out[m], base[m], rtol=0, atol=5e-12)
     finally:
-        engine.set_tuning(10, 2)
+        engine.set_tuning(10, 4)
     ref, _, _ = oracle.generate(params[-1:])
     assert_samples_close(base[-1, :, :25001], ref, "default circle in mixed batch")
 

@@ -23,10 +23,10 @@
 namespace tgx {
 
 cudaError_t launch_plan_count(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
-                              int64_t max_samples, int tile_shift, int32_t* counts, uint32_t* status,
-                              int32_t* nseg, int32_t* ntile, cudaStream_t stream);
+                              int64_t max_samples, int tile_shift, bool exact_ramps, int32_t* counts,
+                              uint32_t* status, int32_t* nseg, int32_t* ntile, cudaStream_t stream);
 cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
-                             int64_t max_samples, int tile_shift, const int32_t* plan_counts,
+                             int64_t max_samples, int tile_shift, bool exact_ramps, const int32_t* plan_counts,
                              const int64_t* seg_off, const int64_t* tile_off, TrajRec* recs, Seg* segs, Tile* tiles,
                              int32_t* counts, uint32_t* status, tgx_phases* phases, cudaStream_t stream);
 cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles, int tile_shift,
@@ -35,6 +35,9 @@ cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles,
 cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, const double* max_v,
                                         const double* max_a, double v_max, double a_max, uint8_t* flags,
                                         uint32_t* status_out, cudaStream_t stream);
+
+cudaError_t launch_selftest_division(int64_t n, uint64_t seed, int per_thread, unsigned long long* mismatches,
+                                     cudaStream_t stream);
 
 }  // namespace tgx
 
@@ -136,7 +139,8 @@ struct tgx_engine {
     int device = 0;
     int64_t max_samples = (int64_t)1 << 24;
     int tile_shift = 10;   // 1024 samples per tile
-    int spt = 2;           // samples per thread: 2 -> 128-bit stores, 4 -> 256-bit stores
+    bool exact_ramps = false;   // plan mode: replay ramps step by step (bit-identical state) or in exact-v jumps
+    int spt = 4;           // samples per thread: 2 -> 128-bit stores, 4 -> 256-bit stores (measured best on B200)
     int64_t launches = 0;
 
     // per-trajectory scratch (capacity in trajectories)
@@ -199,8 +203,8 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     int64_t* totals = e->totals.as<int64_t>();
 
     // pass 1: counts
-    TGX_CUDA(tgx::launch_plan_count(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, cnt, st, nseg,
-                                    ntile, stream));
+    TGX_CUDA(tgx::launch_plan_count(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
+                                    cnt, st, nseg, ntile, stream));
     e->launches += 1;
     // trailing zero so that an exclusive scan over n+1 items leaves the grand total in element n
     TGX_CUDA(cudaMemsetAsync(nseg + n, 0, sizeof(int32_t), stream));
@@ -233,7 +237,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     if ((rc = e->tiles.reserve((size_t)std::max<int64_t>(tot_tiles, 1) * sizeof(tgx::Tile)))) return rc;
 
     // pass 3: fill
-    TGX_CUDA(tgx::launch_plan_fill(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, cnt, seg_off,
+    TGX_CUDA(tgx::launch_plan_fill(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, e->exact_ramps, cnt, seg_off,
                                    tile_off, e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(),
                                    e->tiles.as<tgx::Tile>(), d_counts, d_status, d_phases, stream));
     e->launches += 1;
@@ -348,6 +352,13 @@ int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt) {
     return TGX_OK;
 }
 
+int tgx_set_plan_mode(tgx_engine* e, int exact_ramps) {
+    if (!e) return TGX_ERR_INVALID;
+    e->exact_ramps = exact_ramps != 0;
+    e->has_plan = false;
+    return TGX_OK;
+}
+
 int64_t tgx_scratch_bytes(const tgx_engine* e) {
     if (!e) return 0;
     const DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
@@ -366,8 +377,8 @@ int tgx_count(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_li
     if (!e || n < 0 || (n > 0 && !d_params)) return TGX_ERR_INVALID;
     if (n == 0) return TGX_OK;
     TGX_CUDA(cudaSetDevice(e->device));
-    TGX_CUDA(tgx::launch_plan_count(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, d_counts, d_status,
-                                    nullptr, nullptr, static_cast<cudaStream_t>(stream)));
+    TGX_CUDA(tgx::launch_plan_count(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, false, d_counts,
+                                    d_status, nullptr, nullptr, static_cast<cudaStream_t>(stream)));
     e->launches += 1;
     return TGX_OK;
 }
@@ -438,6 +449,22 @@ int tgx_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t
     // floor(rank*n/world) without overflow for n < 2^62 / world
     *lo = (int64_t)(((__int128)n * rank) / world);
     *hi = (int64_t)(((__int128)n * (rank + 1)) / world);
+    return TGX_OK;
+}
+
+// Debug aid: compares the planner's hoisted-reciprocal division with __ddiv_rn on n*per_thread pseudo-random
+// operand pairs and returns the number of mismatches (must be 0).
+int tgx_selftest_division(tgx_engine* e, int64_t n, uint64_t seed, int per_thread, uint64_t* mismatches) {
+    if (!e || !mismatches || n < 0 || per_thread < 1) return TGX_ERR_INVALID;
+    TGX_CUDA(cudaSetDevice(e->device));
+    int rc = e->totals.reserve(4 * sizeof(int64_t));
+    if (rc) return rc;
+    unsigned long long* d = e->totals.as<unsigned long long>();
+    TGX_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
+    TGX_CUDA(tgx::launch_selftest_division(n, seed, per_thread, d, nullptr));
+    unsigned long long h = 0;
+    TGX_CUDA(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    *mismatches = (uint64_t)h;
     return TGX_OK;
 }
 

@@ -129,75 +129,214 @@ struct Emitter {
     }
 };
 
+// ---- skip-ahead for x <- fl(x + a) with a constant addend -------------------------------------------------
+// While x stays inside one binade [2^E, 2^(E+1)] (same sign), every exact sum x + a is rounded to the same grid
+// of spacing u = 2^(E-52), so unless a is an odd multiple of u/2 (a tie, where round-half-even alternates) each step
+// adds exactly the same inc = fl(x + a) - x and the reference's running sum is an exact arithmetic progression.
+// Given one real step x0 -> x1 this returns how many FURTHER steps are guaranteed to add exactly x1 - x0
+// (0 when the step crossed a binade, hit a tie, or the values are zero / subnormal-ish).
+__device__ __forceinline__ long long regular_run(double x0, double x1, double a) {
+    const long long i0 = __double_as_longlong(x0), i1 = __double_as_longlong(x1);
+    if (((i0 ^ i1) >> 52) != 0) return 0;                 // sign or exponent changed: an irregular (crossing) step
+    const int e = (int)((i1 >> 52) & 0x7ff);
+    if (e < 64 || e == 0x7ff) return 0;                   // zero, subnormal, tiny or non-finite: step one by one
+    const double inc = dsub(x1, x0);                      // exact
+    if (inc == 0.0) return 1LL << 40;                     // |a| < u/2: x does not move while it stays in this binade
+    const double lo = __longlong_as_double(i1 & 0x7ff0000000000000LL);   // 2^E
+    const double r = fabs(a) / dmul(lo, 0x1p-53);         // |a| in units of u/2 (exact scaling)
+    if (r < 0x1p53 && r == rint(r) && (((long long)r) & 1LL)) return 0;  // tie: increments alternate
+    const double ax = fabs(x1), ai = fabs(inc);
+    const bool growing = (inc > 0.0) == (x1 > 0.0);
+    const double room = growing ? dsub(dmul(2.0, lo), ax) : dsub(ax, lo);   // exact distance to the binade edge
+    const double q = floor(ddiv(room, ai));
+    long long J = q > 1e15 ? (1LL << 40) : (long long)q;
+    // exact check: after J further steps the value must still lie in [2^E, 2^(E+1)]
+    while (J > 0) {
+        const double y = fabs(fma((double)J, inc, x1));
+        if (growing ? (y <= dmul(2.0, lo)) : (y >= lo)) break;
+        --J;
+    }
+    return J;
+}
+
 // One velocity ramp of the reference (up: std::min clamp at v_goal; down: std::max clamp at 0), shared by all
-// three classes.  STEP advances the class-specific state (theta, or x/y) for the new v.
-// Returns false when the reference would never terminate / the sample guard is hit.
-template <bool UP, class Step>
+// three classes.  Returns false when the reference would never terminate / the sample guard is hit.
+//
+// XR (exact ramps): every step is replayed; STEP advances the class state (theta, or x/y) with the reference's own
+// operation sequence, so the state at every segment base is bit-identical to the reference's.
+//
+// !XR (fast ramps): v <- fl(v + a*dt) is itself an exact arithmetic progression inside a binade of v, so the ramp
+// is advanced in exact jumps (the step COUNT and every v_k stay bit-identical to the reference), and the class
+// state is advanced in closed form over each jump, s += c * sum(v): it then differs from the reference's running
+// sum by that sum's own accumulated rounding, at most a few hundred half-ulps of theta (~1e-13 rad).
+template <bool UP, bool XR, bool TRACK0, bool TRACK1, class Step>
 __device__ __forceinline__ bool ramp(double& v, double target, double adt, double dtr, int& k,
                                      int64_t max_samples, int tmask, Emitter& E, double acc, double& s0,
-                                     double& s1, Step step) {
+                                     double& s1, double c0, double c1, Step step) {
     bool open = false;
+    const double clampv = UP ? target : 0.0;
     while (UP ? (v < target) : (v > 0.0)) {
         const double vn = UP ? std_min(dadd(v, adt), target) : std_max(dsub(v, adt), 0.0);
         if (vn == v || (int64_t)k + 1 >= max_samples) return false;
         if (!open) {
             // orbit: Seg.s1 = theta increment per step at the base speed, (vb/r)*dt up to rounding
-            E.open(k, v, UP ? adt : -adt, UP ? target : 0.0, s0, E.orbit ? dmul(v, dtr) : s1, acc);
+            E.open(k, v, UP ? adt : -adt, clampv, s0, E.orbit ? dmul(v, dtr) : s1, acc);
             open = true;
         }
-        v = vn;
-        step(v);
-        ++k;
-        // k is the last sample of its tile (segments never straddle tiles), or the ramp chunk is full (bounds
-        // the rounding drift of the closed form against the reference's running sums)
-        if (((k + 1) & tmask) == 0 || k - E.cur.kb >= kRampChunk) {
-            E.close(k, v == (UP ? target : 0.0), s0);
-            open = false;
+        if (XR) {
+            v = vn;
+            step(v);
+            ++k;
+            // k is the last sample of its tile (segments never straddle tiles), or the ramp chunk is full (bounds
+            // the rounding drift of the closed form against the reference's running sums)
+            if (((k + 1) & tmask) == 0 || k - E.cur.kb >= kRampChunk) {
+                E.close(k, v == clampv, s0);
+                open = false;
+            }
+        } else {
+            const double inc = dsub(vn, v);                      // exact
+            long long J = (vn == clampv) ? 0 : regular_run(v, vn, UP ? adt : -adt);
+            J = min(J, (long long)(((k + 1) | tmask) - (k + 1)));  // stay inside the tile of sample k+1
+            J = min(J, max_samples - 2 - (long long)k);            // the guard fires on the next real step
+            if (J > 0) {
+                // none of the jumped steps may reach the clamp: vn + J*inc strictly between 0 and target
+                const double room = UP ? dsub(target, vn) : vn;
+                const double q = ceil(ddiv(room, fabs(inc))) - 1.0;
+                const long long Jc = q < 1.0 ? 0 : (q > 1e15 ? (1LL << 40) : (long long)q);
+                J = min(J, Jc);
+                while (J > 0) {
+                    const double y = fma((double)J, inc, vn);
+                    if (UP ? (y < target) : (y > 0.0)) break;
+                    --J;
+                }
+            }
+            if (J < 0) J = 0;
+            const double fJ = (double)J;
+            if (TRACK0 || TRACK1) {
+                // sum of v over the real step and the J jumped ones: (J+1)*vn + inc*J(J+1)/2
+                const double S = fma(inc, 0.5 * (fJ * (fJ + 1.0)), (fJ + 1.0) * vn);
+                if (TRACK0) s0 = fma(c0, S, s0);
+                if (TRACK1) s1 = fma(c1, S, s1);
+            }
+            v = fma(fJ, inc, vn);                                // exact
+            k += 1 + (int)J;
+            if (((k + 1) & tmask) == 0) {
+                E.close(k, v == clampv, s0);
+                open = false;
+            }
         }
     }
-    if (open) E.close(k, v == (UP ? target : 0.0), s0);
+    if (open) E.close(k, v == clampv, s0);
     return true;
 }
 
-// The constant-speed phase: `while (current_t_traj_ < t) { ...; current_t_traj_ += dt_; }`.
+// The constant-speed phase: `while (current_t_traj_ < t) { ...; current_t_traj_ += dt_; }`
+// (Circle.cpp:63-71, Line.cpp:57-62, Figure8.cpp:63-71).  a0 / a1 are the constants the reference adds to
+// s0 / s1 on every step of the phase (orbit: s0 = theta, a0 = (v/r)*dt; line: s0 = x, s1 = y, a = (v*c)*dt, (v*s)*dt).
 //
-// EXACT (orbits): with v constant the reference adds the same w = (v/r)*dt to theta every step.  While theta
-// stays inside one binade every sum theta + w rounds by the same amount, so the reference's theta is an EXACT
-// arithmetic progression with step d = fl(theta + w) - theta.  The segment is cut whenever d changes (a binade
-// crossing; the crossing step itself becomes the segment's exactly stored last sample), so the evaluation
-// kernel's theta_b + j*d reproduces the reference's running sum bit for bit.
-template <bool EXACT, class Step>
+// The loop is NOT replayed step by step: after each real step the three running sums (current_t_traj_, s0, s1) are
+// advanced in one exact jump over the steps for which regular_run() proves their increments constant, bounded
+// by the tile end, the sample guard and the step on which current_t_traj_ reaches t_hold.  A phase of n steps costs
+// O(number of binade crossings + number of tiles) iterations and still yields the reference's bit-exact state.
+//
+// EXACT (orbits): the segment is cut whenever theta's effective increment d changes (a binade crossing; the
+// crossing step itself becomes the segment's exactly stored last sample), so the evaluation kernel's
+// theta_b + j*d reproduces the reference's running sum bit for bit.
+template <bool TRACK0, bool TRACK1, bool EXACT>
 __device__ __forceinline__ bool hold(double v, double t_hold, double dt, int& k, int64_t max_samples, int tmask,
-                                     Emitter& E, double& s0, double& s1, Step step) {
+                                     Emitter& E, double& s0, double& s1, double a0, double a1) {
     bool open = false;
     double cur = 0.0;
     double seg_d = 0.0;
     while (cur < t_hold) {
         if ((int64_t)k + 1 >= max_samples) return false;
-        const double s0_old = s0, s1_old = s1;
-        step(v);
-        const double d = EXACT ? dsub(s0, s0_old) : 0.0;
+        // ---- one real step ----------------------------------------------------------------------------
+        const double s0n = TRACK0 ? dadd(s0, a0) : s0;
+        const double s1n = TRACK1 ? dadd(s1, a1) : s1;
+        const double cn = dadd(cur, dt);
+        if (cn == cur) return false;
+        const double d0 = TRACK0 ? dsub(s0n, s0) : 0.0;      // exact effective increments
+        const double d1 = TRACK1 ? dsub(s1n, s1) : 0.0;
+        const double dc = dsub(cn, cur);
         if (!open) {
-            E.open(k, v, 0.0, v, s0_old, EXACT ? d : s1_old, 0.0);
-            seg_d = d;
+            E.open(k, v, 0.0, v, s0, EXACT ? d0 : s1, 0.0);
+            seg_d = d0;
             open = true;
         }
+        long long J = regular_run(cur, cn, dt);
+        if (TRACK0) J = min(J, regular_run(s0, s0n, a0));
+        if (TRACK1) J = min(J, regular_run(s1, s1n, a1));
+        s0 = s0n;
+        s1 = s1n;
+        cur = cn;
         ++k;
-        const double tn = dadd(cur, dt);
-        if (tn == cur) return false;
-        cur = tn;
-        if (((k + 1) & tmask) == 0 || (EXACT && d != seg_d && E.can_break())) {
+        if (((k + 1) & tmask) == 0 || (EXACT && d0 != seg_d && E.can_break())) {
             E.close(k, false, s0);
             open = false;
+            continue;
+        }
+        // ---- exact jump over the regular run ----------------------------------------------------------
+        J = min(J, (long long)((k | tmask) - k));            // stay inside the tile
+        J = min(J, max_samples - 1 - (long long)k);          // the guard fires on the next real step
+        if (J > 0 && cur < t_hold) {
+            if (fma((double)J, dc, cur) >= t_hold) {
+                // the phase ends inside the run: take exactly the m steps after which current_t_traj_ >= t_hold
+                double g = ceil(ddiv(dsub(t_hold, cur), dc));
+                long long m = g < 1.0 ? 1 : (g > (double)J ? J : (long long)g);
+                while (m > 1 && fma((double)(m - 1), dc, cur) >= t_hold) --m;
+                while (m < J && fma((double)m, dc, cur) < t_hold) ++m;
+                J = m;
+            }
+            const double fJ = (double)J;
+            if (TRACK0) s0 = fma(fJ, d0, s0);                // exact: every partial sum is representable
+            if (TRACK1) s1 = fma(fJ, d1, s1);
+            cur = fma(fJ, dc, cur);
+            k += (int)J;
+            if (((k + 1) & tmask) == 0) {
+                E.close(k, false, s0);
+                open = false;
+            }
         }
     }
     if (open) E.close(k, false, s0);
     return true;
 }
 
+// Division by a loop-invariant divisor, correctly rounded (== __ddiv_rn) with the reciprocal hoisted out of the
+// ramp loops: y = RN(1/b); q0 = RN(a*y); two residual corrections q <- RN(q + RN(a - b*q)*y) (Markstein's
+// sequence: the first correction makes q faithful, the second correctly rounded, provided b's significand is not
+// all ones).  Outside a comfortable exponent range, or for that one significand, it falls back to __ddiv_rn.
+struct InvDiv {
+    double b, y;
+    bool fast;
+};
+
+__device__ __forceinline__ InvDiv make_invdiv(double b) {
+    InvDiv d;
+    d.b = b;
+    d.y = __drcp_rn(b);
+    const long long bits = __double_as_longlong(b);
+    const bool all_ones = (bits & 0x000fffffffffffffLL) == 0x000fffffffffffffLL;
+    const double ab = fabs(b);
+    d.fast = !all_ones && ab > 0x1p-200 && ab < 0x1p200;
+    return d;
+}
+
+__device__ __forceinline__ double div_inv(double a, const InvDiv& d) {
+    const double aa = fabs(a);
+    if (d.fast && aa > 0x1p-200 && aa < 0x1p200) {
+        double q = dmul(a, d.y);
+        double r = fma(-q, d.b, a);
+        q = fma(r, d.y, q);
+        r = fma(-q, d.b, a);
+        return fma(r, d.y, q);
+    }
+    return ddiv(a, d.b);
+}
+
 // Circle::generateTraj (Circle.cpp:30-94) == Figure8::generateTraj (Figure8.cpp:30-94).
-// STATE = false skips the theta recurrence (counts and status do not depend on it).
-template <bool STATE>
+// STATE = false skips the theta recurrence (counts and status do not depend on it); XR selects exact ramps.
+template <bool STATE, bool XR>
 __device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E, uint32_t& st) {
     const tgx_orbit_params& o = p.u.orbit;
     const double r = o.r, dt = p.dt;
@@ -206,32 +345,29 @@ __device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E
     const int tmask = (1 << E.tile_shift) - 1;
     double v = 0.0, th = 0.0, unused = 0.0;
     int k = 0;   // index of the last sample produced so far; sample 0 (v = 0, theta = 0) exists (:41)
-    double v_cached = -1.0, w_cached = 0.0;
-    auto step = [&](double vnew) {                           // omega = v/r_; theta += omega*dt_  (:50-51, :65-67)
-        if (STATE) {
-            if (vnew != v_cached) {                          // same v gives the same omega*dt: skip the division
-                v_cached = vnew;
-                w_cached = dmul(ddiv(vnew, r), dt);
-            }
-            th = dadd(th, w_cached);
-        }
+    const InvDiv rdiv = make_invdiv(r);
+    auto step = [&](double vnew) {                           // omega = v/r_; theta += omega*dt_  (:50-51, :79)
+        if (STATE) th = dadd(th, dmul(div_inv(vnew, rdiv), dt));
     };
     for (int g = 0; g < p.n_vgoals; ++g) {                   // :43
         const double vg = o.v_goals[g];
         E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                // :45
-        if (!ramp<true>(v, vg, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, step)) {   // :47-54
+        if (!ramp<true, XR, STATE, false>(v, vg, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, dtr, 0.0,
+                                          step)) {                                              // :47-54
             st |= TGX_ST_TOO_LONG;
             return -1;
         }
         if (fabs(dsub(v, vg)) > 0.001) st |= TGX_ST_VGOALS_NOT_INCREASING;                // :57-59
         E.phase(k, TGX_PH_REACHED, vg, o.t_traj);            // :61-62
-        if (!hold<STATE>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, step)) {   // :63-71
+        const double w = STATE ? dmul(div_inv(v, rdiv), dt) : 0.0;    // omega*dt_, the same on every step (:65-67)
+        if (!hold<STATE, false, STATE>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0)) {   // :63-71
             st |= TGX_ST_TOO_LONG;
             return -1;
         }
     }
     E.phase(k, TGX_PH_DECEL, 0.0, 0.0);                      // :74
-    if (!ramp<false>(v, 0.0, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, step)) {   // :75-82
+    if (!ramp<false, XR, STATE, false>(v, 0.0, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, dtr, 0.0,
+                                       step)) {                                                 // :75-82
         st |= TGX_ST_TOO_LONG;
         return -1;
     }
@@ -253,6 +389,7 @@ __device__ double line_d2(const tgx_line_params& l) {
 }
 
 // Line::Line (theta_, Line.cpp:24) + Line::generateTraj (Line.cpp:31-89).
+template <bool XR>
 __device__ int replay_line(const tgx_params& p, int64_t max_samples, Emitter& E, uint32_t& st, double& theta,
                            double& c, double& s) {
     const tgx_line_params& l = p.u.line;
@@ -272,7 +409,9 @@ __device__ int replay_line(const tgx_params& p, int64_t max_samples, Emitter& E,
     };
     const double vg = l.v_goal;                                  // :43
     E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                        // :44
-    if (!ramp<true>(v, vg, dmul(l.a1, dt), 0.0, k, max_samples, tmask, E, l.a1, x, y, step)) {   // :46-50
+    const double cdt = dmul(cc, dt), sdt = dmul(ss, dt);
+    if (!ramp<true, XR, true, true>(v, vg, dmul(l.a1, dt), 0.0, k, max_samples, tmask, E, l.a1, x, y, cdt, sdt,
+                                    step)) {                                                   // :46-50
         st |= TGX_ST_TOO_LONG;
         return -1;
     }
@@ -280,12 +419,14 @@ __device__ int replay_line(const tgx_params& p, int64_t max_samples, Emitter& E,
     if (d2 < 0.0) st |= TGX_ST_LINE_D2_NEGATIVE;                 // the condition Line.cpp:165 reports
     const double t2 = ddiv(d2, vg);                              // :53
     E.phase(k, TGX_PH_REACHED, vg, t2);                          // :55-56
-    if (!hold<false>(v, t2, dt, k, max_samples, tmask, E, x, y, step)) {                     // :57-62
+    if (!hold<true, true, false>(v, t2, dt, k, max_samples, tmask, E, x, y, dmul(dmul(v, cc), dt),
+                                 dmul(dmul(v, ss), dt))) {                                   // :57-62
         st |= TGX_ST_TOO_LONG;
         return -1;
     }
     E.phase(k, TGX_PH_DECEL, 0.0, 0.0);                          // :64
-    if (!ramp<false>(v, 0.0, dmul(l.a3, dt), 0.0, k, max_samples, tmask, E, -l.a3, x, y, step)) {   // :65-68
+    if (!ramp<false, XR, true, true>(v, 0.0, dmul(l.a3, dt), 0.0, k, max_samples, tmask, E, -l.a3, x, y, cdt, sdt,
+                                     step)) {                                                  // :65-68
         st |= TGX_ST_TOO_LONG;
         return -1;
     }
@@ -323,7 +464,7 @@ struct PlanOut {
 
 // generateTraj plan of one trajectory.  FILL = false: count only; STATE = false: skip the theta replay (then the
 // segment count is not meaningful: exact-progression breaks depend on theta).
-template <bool FILL, bool STATE>
+template <bool FILL, bool STATE, bool XR>
 __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_limits* lim, Emitter& E,
                             TrajRec* rec) {
     PlanOut r{0, 0u, 0, 0};
@@ -332,8 +473,8 @@ __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_
     } else {
         int n;
         double theta = 0.0, c = 1.0, s = 0.0;
-        if (p.type == TGX_LINE) n = replay_line(p, max_samples, E, r.status, theta, c, s);
-        else n = replay_orbit<STATE>(p, max_samples, E, r.status);
+        if (p.type == TGX_LINE) n = replay_line<XR>(p, max_samples, E, r.status, theta, c, s);
+        else n = replay_orbit<STATE, XR>(p, max_samples, E, r.status);
         E.finish();
         if (lim && lim->check_box && !inside_bounds(p, lim->box)) r.status |= TGX_ST_OUTSIDE_BOUNDS;
         if (n > 0) {
@@ -424,8 +565,10 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
             double th = atan2(dsub(from[TGX_PY], o.cy), dsub(from[TGX_PX], o.cx));
             double unused = 0.0;
             const double adt = dmul(o.accel, dt);
-            auto step = [&](double vnew) { th = dadd(th, dmul(ddiv(vnew, o.r), dt)); };
-            ok = ramp<false>(v, 0.0, adt, ddiv(dt, o.r), k, max_samples, tmask, E, 0.0, th, unused, step);   // :150-157
+            const InvDiv rdiv = make_invdiv(o.r);
+            auto step = [&](double vnew) { th = dadd(th, dmul(div_inv(vnew, rdiv), dt)); };
+            ok = ramp<false, true, true, false>(v, 0.0, adt, ddiv(dt, o.r), k, max_samples, tmask, E, 0.0, th, unused,
+                                                0.0, 0.0, step);                               // :150-157
             t.type = p.type;
             t.f[0] = o.r; t.f[1] = o.cx; t.f[2] = o.cy; t.f[3] = p.alt;
             t.f[4] = ddiv(dt, o.r); t.f[5] = ddiv(1.0, o.r);
@@ -464,7 +607,7 @@ __device__ __forceinline__ tgx_params load_params(const tgx_params* params, int6
 
 // Counting pass: N_i, status_i and, with SEGS, the number of segments / tiles the fill pass will emit (which
 // requires the full state replay, because exact-progression breaks depend on theta).
-template <bool SEGS>
+template <bool SEGS, bool XR>
 __global__ void __launch_bounds__(128)
 plan_count_kernel(const tgx_params* __restrict__ params, const double* __restrict__ stop_from, int64_t n,
                   tgx_limits lim, int has_lim, int64_t max_samples, int tile_shift,
@@ -481,7 +624,7 @@ plan_count_kernel(const tgx_params* __restrict__ params, const double* __restric
         for (int c = 0; c < TGX_NCHAN; ++c) from[c] = stop_from[i * TGX_NCHAN + c];
         r = stop_one<false>(p, from, max_samples, E, nullptr);
     } else {
-        r = plan_one<false, SEGS>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr);
+        r = plan_one<false, SEGS, XR>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr);
     }
     if (counts) counts[i] = r.n;
     if (status) status[i] = r.status;
@@ -490,6 +633,7 @@ plan_count_kernel(const tgx_params* __restrict__ params, const double* __restric
 }
 
 // Fill pass: same replay, now writing the tables at the offsets the scans produced.
+template <bool XR>
 __global__ void __launch_bounds__(128)
 plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict__ stop_from, int64_t n,
                  tgx_limits lim, int has_lim, int64_t max_samples, int tile_shift,
@@ -512,35 +656,68 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
         r = stop_one<true>(p, from, max_samples, E, recs + i);
         if (phases && r.status) phases[i].n = 0;
     } else {
-        r = plan_one<true, true>(p, max_samples, has_lim ? &lim : nullptr, E, recs + i);
+        r = plan_one<true, true, XR>(p, max_samples, has_lim ? &lim : nullptr, E, recs + i);
     }
     if (counts) counts[i] = r.n;
     if (status) status[i] = r.status;
 }
 
+// Self-test of div_inv against __ddiv_rn on pseudo-random operands (splitmix64 streams): counts mismatches.
+__global__ void __launch_bounds__(256)
+selftest_division_kernel(int64_t n, uint64_t seed, int per_thread, unsigned long long* __restrict__ mismatches) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t z = seed + 0x9e3779b97f4a7c15ULL * (uint64_t)(i + 1);
+    auto next = [&]() {
+        z += 0x9e3779b97f4a7c15ULL;
+        uint64_t x = z;
+        x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+        return x ^ (x >> 31);
+    };
+    // divisor: random significand, exponent in [-8, 8]; every 16th thread gets a hard significand
+    uint64_t mb = next() & 0x000fffffffffffffULL;
+    if ((i & 15) == 0) mb = 0x000fffffffffffffULL - (next() & 3);       // all ones and its neighbours
+    if ((i & 15) == 1) mb = next() & 7;                                  // just above a power of two
+    const int eb = (int)(next() % 17) - 8;
+    const double b = __longlong_as_double((long long)(((uint64_t)(1023 + eb) << 52) | mb));
+    const InvDiv d = make_invdiv(b);
+    unsigned long long bad = 0;
+    for (int t = 0; t < per_thread; ++t) {
+        const uint64_t ma = next() & 0x000fffffffffffffULL;
+        const int ea = (int)(next() % 41) - 30;
+        const double a = __longlong_as_double((long long)(((uint64_t)(1023 + ea) << 52) | ma));
+        if (div_inv(a, d) != ddiv(a, b)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ---- host-side launchers (called from engine.cu) -------------------------------------------------------
 
 cudaError_t launch_plan_count(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
-                              int64_t max_samples, int tile_shift, int32_t* counts, uint32_t* status,
-                              int32_t* nseg, int32_t* ntile, cudaStream_t stream) {
+                              int64_t max_samples, int tile_shift, bool exact_ramps, int32_t* counts,
+                              uint32_t* status, int32_t* nseg, int32_t* ntile, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     tgx_limits l{};
     if (lim) l = *lim;
     const int threads = 128;
     const int64_t blocks = (n + threads - 1) / threads;
-    if (nseg || ntile)
-        plan_count_kernel<true><<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0,
-                                                                         max_samples, tile_shift, counts, status,
-                                                                         nseg, ntile);
-    else
-        plan_count_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0,
-                                                                          max_samples, tile_shift, counts, status,
-                                                                          nseg, ntile);
+#define TGX_LAUNCH_COUNT(SEGS, XR)                                                                          \
+    plan_count_kernel<SEGS, XR><<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0, \
+                                                                         max_samples, tile_shift, counts, status, \
+                                                                         nseg, ntile)
+    if (nseg || ntile) {
+        if (exact_ramps) TGX_LAUNCH_COUNT(true, true);
+        else TGX_LAUNCH_COUNT(true, false);
+    } else {
+        TGX_LAUNCH_COUNT(false, false);   // counts and status only: the fast replay is exact for both
+    }
+#undef TGX_LAUNCH_COUNT
     return cudaGetLastError();
 }
 
 cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
-                             int64_t max_samples, int tile_shift, const int32_t* plan_counts,
+                             int64_t max_samples, int tile_shift, bool exact_ramps, const int32_t* plan_counts,
                              const int64_t* seg_off, const int64_t* tile_off, TrajRec* recs, Seg* segs, Tile* tiles,
                              int32_t* counts, uint32_t* status, tgx_phases* phases, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
@@ -548,9 +725,23 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
     if (lim) l = *lim;
     const int threads = 128;
     const int64_t blocks = (n + threads - 1) / threads;
-    plan_fill_kernel<<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0, max_samples,
-                                                              tile_shift, plan_counts, seg_off, tile_off, recs, segs,
-                                                              tiles, counts, status, phases);
+    if (exact_ramps)
+        plan_fill_kernel<true><<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0,
+                                                                        max_samples, tile_shift, plan_counts, seg_off,
+                                                                        tile_off, recs, segs, tiles, counts, status,
+                                                                        phases);
+    else
+        plan_fill_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0,
+                                                                         max_samples, tile_shift, plan_counts, seg_off,
+                                                                         tile_off, recs, segs, tiles, counts, status,
+                                                                         phases);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_selftest_division(int64_t n, uint64_t seed, int per_thread, unsigned long long* mismatches,
+                                     cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    selftest_division_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, seed, per_thread, mismatches);
     return cudaGetLastError();
 }
 

@@ -41,6 +41,7 @@ def _load() -> C.CDLL:
     lib.tgx_destroy.argtypes = [vp]
     lib.tgx_set_max_samples.argtypes = [vp, i64]
     lib.tgx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
+    lib.tgx_set_plan_mode.argtypes = [vp, C.c_int]
     lib.tgx_scratch_bytes.restype = i64
     lib.tgx_scratch_bytes.argtypes = [vp]
     lib.tgx_launch_count.restype = i64
@@ -58,6 +59,7 @@ def _load() -> C.CDLL:
     lib.tgx_generate_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp]
     lib.tgx_stop_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp]
     lib.tgx_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    lib.tgx_selftest_division.argtypes = [vp, i64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     lib.tgx_alloc_host.restype = vp
     lib.tgx_alloc_host.argtypes = [i64]
     lib.tgx_free_host.argtypes = [vp]
@@ -172,6 +174,9 @@ class Engine:
     def set_tuning(self, tile_shift: int, spt: int):
         self._check(self._lib.tgx_set_tuning(self._h, tile_shift, spt), "tgx_set_tuning")
 
+    def set_plan_mode(self, exact_ramps: bool):
+        self._check(self._lib.tgx_set_plan_mode(self._h, 1 if exact_ramps else 0), "tgx_set_plan_mode")
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.tgx_launch_count(self._h))
@@ -271,6 +276,12 @@ class Engine:
         self._check(self._lib.tgx_feasibility(self._h, C.byref(limits), flags.data_ptr(), max_v.data_ptr(),
                                               max_a.data_ptr(), status.data_ptr(), self._stream()), "tgx_feasibility")
         return flags, max_v, max_a, status
+
+    def selftest_division(self, n: int, seed: int = 1, per_thread: int = 64) -> int:
+        bad = C.c_uint64(0)
+        self._check(self._lib.tgx_selftest_division(self._h, n, seed, per_thread, C.byref(bad)),
+                    "tgx_selftest_division")
+        return int(bad.value)
 
     # ---- host-buffer calls -------------------------------------------------------------------------
     def count_host(self, params: np.ndarray, limits: Optional[abi.Limits] = None):
