@@ -98,7 +98,8 @@ enum tgx_status_bits {
     TGX_ST_VGOALS_NOT_INCREASING = 1u << 0, /* RCLCPP_WARN at Circle.cpp:57-59 / Figure8.cpp:57-59 (samples still produced) */
     TGX_ST_FINAL_V_NONZERO       = 1u << 1, /* exit(1) at Circle.cpp:85-88 / Figure8.cpp:85-88 */
     TGX_ST_LINE_END_NOT_B        = 1u << 2, /* exit(1) at Line.cpp:76-79 (end point > 0.05 m from B) */
-    TGX_ST_LINE_D2_NEGATIVE      = 1u << 3, /* Line.cpp:165-168: cruise segment length < 0 */
+    TGX_ST_LINE_D2_NEGATIVE      = 1u << 3, /* Line.cpp:165-168: cruise segment length < 0; reported, like the reference does,
+                                               by the bounds check only (set together with OUTSIDE_BOUNDS) */
     TGX_ST_OUTSIDE_BOUNDS        = 1u << 4, /* trajectoryInsideBounds() == false (only if a box was given) */
     TGX_ST_BAD_PARAM             = 1u << 5, /* v<=0, accel<=0 (TrajectoryGenerator.cpp:184-195,268-277), dt<=0, r<=0,
                                                n_vgoals out of range, unknown type, non-finite input: no samples */

@@ -169,12 +169,18 @@ int64_t ref_stop(const tgx_params* p, const double* from, double* out, int64_t c
     return (int64_t)goals.size();
 }
 
-int ref_inside_bounds(const tgx_params* p, const double box[6]) {
+// Returns 1 / 0; *n_errors (may be NULL) receives how many RCLCPP_ERROR lines the call logged (Line.cpp:166 logs
+// "Line trajectory not feasible" when d2 < 0).
+static int inside_bounds_impl(const tgx_params* p, const double box[6], long* n_errors) {
     LogScope scope;
     tgx_stub::log_state().throw_on_error = false;   // Line.cpp:166 logs an error and returns false
     auto traj = make_traj(*p);
-    return traj->trajectoryInsideBounds(box[0], box[1], box[2], box[3], box[4], box[5]) ? 1 : 0;
+    const bool ok = traj->trajectoryInsideBounds(box[0], box[1], box[2], box[3], box[4], box[5]);
+    if (n_errors) *n_errors = tgx_stub::log_state().n_error;
+    return ok ? 1 : 0;
 }
+
+int ref_inside_bounds(const tgx_params* p, const double box[6]) { return inside_bounds_impl(p, box, nullptr); }
 
 // Multi-threaded batch generation with SoA repack (for parity checks at moderate scale).
 int ref_generate_batch(const tgx_params* p, int64_t n, double* out, int64_t traj_stride, int64_t chan_stride,
@@ -216,8 +222,13 @@ int ref_feasibility_batch(const tgx_params* p, int64_t n, const tgx_limits* limi
                 if (nv > mv) mv = nv;
                 if (na > ma) ma = na;
             }
-            if (limits && limits->check_box && !(st & TGX_ST_BAD_PARAM) && !ref_inside_bounds(&p[i], limits->box))
-                st |= TGX_ST_OUTSIDE_BOUNDS;
+            if (limits && limits->check_box && !(st & TGX_ST_BAD_PARAM)) {
+                long n_err = 0;
+                if (!inside_bounds_impl(&p[i], limits->box, &n_err)) {
+                    st |= TGX_ST_OUTSIDE_BOUNDS;
+                    if (n_err > 0) st |= TGX_ST_LINE_D2_NEGATIVE;   // the only error trajectoryInsideBounds logs
+                }
+            }
             if (limits && mv > limits->v_max) st |= TGX_ST_VMAX_EXCEEDED;
             if (limits && ma > limits->a_max) st |= TGX_ST_AMAX_EXCEEDED;
             if (max_v) max_v[i] = mv;

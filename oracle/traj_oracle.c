@@ -240,9 +240,7 @@ static int64_t line_generate(const tgx_params* p, sink_t* sk, uint32_t* status, 
         line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, l->a1, theta, g);
         sink_push(sk, g);
     }
-    double d2 = orc_line_d2(p);
-    if (d2 < 0) *status |= TGX_ST_LINE_D2_NEGATIVE;   /* the condition Line.cpp:165 reports */
-    double t2 = d2 / v_goal;                          /* :53 */
+    double t2 = orc_line_d2(p) / v_goal;              /* :53 (a negative d2 simply skips the cruise loop) */
     phase_add(ph, sk->n - 1, TGX_PH_REACHED, v_goal, t2);
     double current_t_traj = 0;
     while (current_t_traj < t2) {                     /* :57 */
@@ -439,8 +437,11 @@ static void* job_run(void* arg) {
                 double mv = 0.0, ma = 0.0;
                 if (n > 0) reduce_norms(scratch, scratch_cap, n, &mv, &ma);
                 if (j->limits && j->limits->check_box && !(st & TGX_ST_BAD_PARAM) &&
-                    !orc_inside_bounds(&j->p[i], j->limits->box))
+                    !orc_inside_bounds(&j->p[i], j->limits->box)) {
                     st |= TGX_ST_OUTSIDE_BOUNDS;
+                    /* Line::trajectoryInsideBounds reports "not feasible" when d2 < 0 (Line.cpp:165-168) */
+                    if (j->p[i].type == TGX_LINE && orc_line_d2(&j->p[i]) < 0) st |= TGX_ST_LINE_D2_NEGATIVE;
+                }
                 if (j->limits && mv > j->limits->v_max) st |= TGX_ST_VMAX_EXCEEDED;
                 if (j->limits && ma > j->limits->a_max) st |= TGX_ST_AMAX_EXCEEDED;
                 if (j->max_v) j->max_v[i] = mv;

@@ -226,8 +226,14 @@ def test_line_edge_cases(mode_engine, oracle):
         abi.line_params(1.0, [0, 0, 0.5], [0, 2, 2.5], [0.5], 1.0, 1.0, 0.02),         # z differs: 3-D |B-A|
     ])
     out, counts, status, ph = gpu_generate(engine, params)
-    assert status[1] & abi.ST_LINE_D2_NEGATIVE
+    assert status[1] == abi.ST_LINE_END_NOT_B      # d2 < 0: the line overshoots B by 0.33 m (exit(1) in the reference)
     check_batch(engine, oracle, params, "line edge cases")
+    # the bounds check is where the reference reports d2 < 0 (Line.cpp:165-168)
+    lim = abi.make_limits(box=(-5, 5, -5, 5, -5, 5))
+    c, st = engine.count(engine.upload_params(params), limits=lim)
+    st = st.cpu().numpy().view(np.uint32)
+    assert st[1] == abi.ST_LINE_END_NOT_B | abi.ST_OUTSIDE_BOUNDS | abi.ST_LINE_D2_NEGATIVE
+    assert st[0] == 0 and st[4] == 0
 
 
 # ---- random batches -----------------------------------------------------------------------------------------

@@ -1,0 +1,63 @@
+"""CPU: the plain-C oracle against the UNMODIFIED reference compiled behind stub headers (oracle/_ref), bit for bit,
+on random parameters.  Skipped where oracle/_ref is not built (no /root/reference at build time)."""
+import numpy as np
+import pytest
+
+from trajectory_generator_ros2_b200 import abi, workloads
+
+
+@pytest.mark.parametrize("name,n", [("circles_cfg2", 400), ("mixed_cfg3", 900), ("montecarlo_cfg4", 300)])
+def test_batches_bit_exact(oracle, reference, name, n):
+    params = getattr(workloads, name)(n)
+    o_out, o_counts, o_status = oracle.generate_batch(params, 2400)
+    r_out, r_counts, r_status = reference.generate_batch(params, 2400)
+    np.testing.assert_array_equal(o_counts, r_counts)
+    np.testing.assert_array_equal(o_status, r_status)
+    assert (o_counts <= 2400).all()
+    ob, rb = (o_out + 0.0).view(np.uint64), (r_out + 0.0).view(np.uint64)
+    assert (ob == rb).all()
+
+
+def test_index_msgs_and_stop_bit_exact(oracle, reference):
+    params = workloads.mixed_cfg3(120)
+    rng = np.random.default_rng(7)
+    for i in range(len(params)):
+        p = params[i:i + 1]
+        o, ost, oph = oracle.generate(p)
+        r, rst, rmsgs = reference.generate(p)
+        assert ost == rst and o.shape == r.shape
+        if ost & abi.ST_FATAL_MASK:
+            continue
+        t = int(p["type"][0])
+        assert abi.phases_to_index_msgs(t, oph) == rmsgs
+        k = int(rng.integers(0, o.shape[1]))
+        so, sost, soph = oracle.stop(p, o[:, k])
+        sr, srst, srmsgs = reference.stop(p, r[:, k])
+        assert so.shape == sr.shape
+        assert ((so + 0.0).view(np.uint64) == (sr + 0.0).view(np.uint64)).all()
+        assert abi.phases_to_index_msgs(t, soph, stop_traj=True) == srmsgs
+
+
+def test_bounds_and_feasibility_match(oracle, reference):
+    params = abi.concat([workloads.montecarlo_cfg4(500), workloads.mixed_cfg3(300)])
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    for i in range(0, len(params), 7):
+        assert oracle.inside_bounds(params[i:i + 1], lim.box[:]) == reference.inside_bounds(params[i:i + 1], lim.box[:])
+    of = oracle.feasibility_batch(params, lim)
+    rf = reference.feasibility_batch(params, lim)
+    for a, b in zip(of, rf):
+        np.testing.assert_array_equal(a, b)
+    assert 0 < of[0].sum() < len(params)
+
+
+def test_optimisation_level_does_not_change_the_reference(tmp_path, oracle):
+    """The reference's CMake sets no optimisation flag; -O0 and -O2 builds of the oracle agree bit for bit."""
+    import os
+    import subprocess
+    from oracle_lib import ORACLE_DIR, Oracle
+    so = tmp_path / "liboracle_O0.so"
+    subprocess.run(["gcc", "-std=c11", "-O0", "-ffp-contract=off", "-fPIC", "-pthread", "-shared", "-o", str(so),
+                    os.path.join(ORACLE_DIR, "traj_oracle.c"), "-lm"], check=True)
+    o0 = Oracle(str(so))
+    for p in (workloads.default_circle(), workloads.default_figure8(), workloads.default_line()):
+        assert o0.fnv(o0.generate(p)[0]) == oracle.fnv(oracle.generate(p)[0])

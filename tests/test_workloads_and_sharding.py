@@ -1,0 +1,82 @@
+"""CPU: synthetic workloads (BASELINE.json configs) and the multi-GPU host logic on the gloo backend."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from trajectory_generator_ros2_b200 import abi, workloads
+
+
+def test_cfg2_recipe_counts(oracle):
+    p = workloads.circles_cfg2(20000)
+    counts, status = oracle.count_batch(p)
+    assert counts.min() >= 1000 and counts.max() <= 1001 and (status == 0).all()
+    assert (p["t_traj"] >= 1.4).all()
+
+
+def test_workloads_are_shard_invariant():
+    for fn in (workloads.circles_cfg2, workloads.mixed_cfg3, workloads.montecarlo_cfg4):
+        full = fn(200000)
+        part = fn(200000, lo=65000, hi=140001)
+        assert full[65000:140001].tobytes() == part.tobytes()
+        assert fn(10, lo=3, hi=3).shape == (0,)
+
+
+def test_cfg3_mix_and_line_feasibility(oracle):
+    p = workloads.mixed_cfg3(30000)
+    frac = np.bincount(p["type"], minlength=3) / len(p)
+    assert abs(frac[0] - 0.4) < 0.02 and abs(frac[1] - 0.3) < 0.02 and abs(frac[2] - 0.3) < 0.02
+    lines = p[p["type"] == abi.TGX_LINE][:500]
+    for i in range(0, len(lines), 25):
+        assert oracle.line_d2(lines[i:i + 1]) > 0
+    counts, status = oracle.count_batch(p[:3000])
+    assert (status == 0).all() and counts.min() > 50 and counts.max() < 2400
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n, ret):
+    import torch
+    import torch.distributed as dist
+    from oracle_lib import Oracle
+    from trajectory_generator_ros2_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = sharding.shard_bounds(n, rank, world)
+        params = workloads.montecarlo_cfg4(n, lo=lo, hi=hi)           # every rank draws only its own shard
+        lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+        flags = Oracle().feasibility_batch(params, lim, nthreads=2)[0]   # stand-in for the per-rank GPU result
+        full = sharding.gather_flags(torch.from_numpy(flags), n)
+        total = sharding.count_feasible(torch.from_numpy(flags))
+        ret[rank] = (full.numpy().copy(), total, (lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1001), (3, 500)])
+def test_gloo_shard_and_gather(oracle, world, n):
+    """world-size 2/3 on CPU: contiguous shards + the optional all-gather of feasibility flags reproduce the
+    single-process result (the flags themselves come from the oracle here; the GPU path is tested with -m gpu)."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    expect = oracle.feasibility_batch(workloads.montecarlo_cfg4(n), lim)[0]
+    spans = []
+    for r in range(world):
+        full, total, span = ret[r]
+        np.testing.assert_array_equal(full, expect)
+        assert total == int(expect.sum())
+        spans.append(span)
+    assert spans[0][0] == 0 and spans[-1][1] == n

@@ -415,9 +415,7 @@ __device__ int replay_line(const tgx_params& p, int64_t max_samples, Emitter& E,
         st |= TGX_ST_TOO_LONG;
         return -1;
     }
-    const double d2 = line_d2(l);
-    if (d2 < 0.0) st |= TGX_ST_LINE_D2_NEGATIVE;                 // the condition Line.cpp:165 reports
-    const double t2 = ddiv(d2, vg);                              // :53
+    const double t2 = ddiv(line_d2(l), vg);                      // :53 (a negative d2 simply skips the cruise loop)
     E.phase(k, TGX_PH_REACHED, vg, t2);                          // :55-56
     if (!hold<true, true, false>(v, t2, dt, k, max_samples, tmask, E, x, y, dmul(dmul(v, cc), dt),
                                  dmul(dmul(v, ss), dt))) {                                   // :57-62
@@ -476,7 +474,11 @@ __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_
         if (p.type == TGX_LINE) n = replay_line<XR>(p, max_samples, E, r.status, theta, c, s);
         else n = replay_orbit<STATE, XR>(p, max_samples, E, r.status);
         E.finish();
-        if (lim && lim->check_box && !inside_bounds(p, lim->box)) r.status |= TGX_ST_OUTSIDE_BOUNDS;
+        if (lim && lim->check_box && !inside_bounds(p, lim->box)) {
+            r.status |= TGX_ST_OUTSIDE_BOUNDS;
+            // Line::trajectoryInsideBounds reports "not feasible" when d2 < 0 (Line.cpp:165-168)
+            if (p.type == TGX_LINE && line_d2(p.u.line) < 0.0) r.status |= TGX_ST_LINE_D2_NEGATIVE;
+        }
         if (n > 0) {
             r.n = n;
             r.nseg = E.nseg;
