@@ -218,6 +218,14 @@ int tgx_plan_stop(tgx_engine* e, const tgx_params* d_params, int64_t n, const do
                   int32_t* d_counts, uint32_t* d_status, tgx_phases* d_phases, int64_t* total_samples,
                   void* stream);
 
+/* Per-time evaluation from an explicit state: the public helpers createCircleGoal(v, accel, theta) (Circle.hpp:39),
+ * createFigure8Goal (Figure8.hpp:39) and createLineGoal(last_x, last_y, v, accel, theta) (Line.hpp:38).
+ * d_state[4*i ..] = {v, accel, s0, s1}: orbit s0 = theta; line s0 = last_x, s1 = last_y and the explicit heading
+ * theta is taken from d_params[i].u.line.reserved[0].  The result is a current plan with exactly one sample per
+ * trajectory; tgx_eval then writes it at k = 0. */
+int tgx_plan_samples(tgx_engine* e, const tgx_params* d_params, int64_t n, const double* d_state,
+                     int32_t* d_counts, uint32_t* d_status, void* stream);
+
 /* ---- evaluation: create*Goal for every (trajectory, k) of the current plan ------------------------- */
 /* One thread per pair of adjacent samples, fp64, SoA planes written with vector stores.
  * If d_max_v / d_max_a are non-NULL the per-trajectory maxima of |v_k| and |a_k| (Euclidean norm of the
@@ -248,6 +256,10 @@ int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, cons
 int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const double* h_from,
                   double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
                   tgx_phases* h_phases);
+
+/* One create*Goal call for host-resident arguments (see tgx_plan_samples); h_out14 receives the 14 channels. */
+int tgx_sample_host(tgx_engine* e, const tgx_params* h_params, double v, double accel, double s0, double s1,
+                    double* h_out14);
 
 /* Page-locked host memory, so that the D2H copies of the calls above run asynchronously at full PCIe rate. */
 void* tgx_alloc_host(int64_t bytes);

@@ -1,0 +1,33 @@
+"""The C++ drop-in classes (trajectory_generator_ros2_b200/host) against the reference's own classes, both driven
+through trajectory_generator::Trajectory in one binary (tests/cpp/dropin_parity.cpp, built by __graft_entry__.build()
+where /root/reference exists; the binary travels to the GPU box)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "bin", "dropin_parity")
+
+
+@pytest.mark.gpu
+def test_dropin_classes_match_reference_classes():
+    if not os.path.exists(BIN):
+        pytest.skip("tests/cpp/bin/dropin_parity not built (needs /root/reference at build time)")
+    r = subprocess.run([BIN], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "DROPIN PARITY OK" in r.stdout
+
+
+def test_dropin_compiles_under_the_reference_names():
+    """Source-level drop-in: the host classes compile as trajectory_generator::{Circle,Line,Figure8} against the
+    reference's unmodified Trajectory.hpp (only checkable where the reference tree is present)."""
+    if not os.path.exists("/root/reference/include/trajectory_generator_ros2/trajectories/Trajectory.hpp"):
+        pytest.skip("/root/reference not present")
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "--no-print-directory", "-B",
+                        "check-dropin-namespace"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

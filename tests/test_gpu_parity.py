@@ -233,7 +233,8 @@ def test_line_edge_cases(mode_engine, oracle):
     c, st = engine.count(engine.upload_params(params), limits=lim)
     st = st.cpu().numpy().view(np.uint32)
     assert st[1] == abi.ST_LINE_END_NOT_B | abi.ST_OUTSIDE_BOUNDS | abi.ST_LINE_D2_NEGATIVE
-    assert st[0] == 0 and st[4] == 0
+    assert st[0] == 0 and st[2] == 0 and st[3] == 0
+    assert st[4] == abi.ST_LINE_END_NOT_B      # 3-D |B-A| with a 2-D motion: the cruise overshoots B in the plane
 
 
 # ---- random batches -----------------------------------------------------------------------------------------

@@ -38,6 +38,8 @@ cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, 
 
 cudaError_t launch_selftest_division(int64_t n, uint64_t seed, int per_thread, unsigned long long* mismatches,
                                      cudaStream_t stream);
+cudaError_t launch_plan_samples(const tgx_params* params, const double* state, int64_t n, TrajRec* recs, Seg* segs,
+                                Tile* tiles, int32_t* counts, uint32_t* status, cudaStream_t stream);
 
 }  // namespace tgx
 
@@ -396,6 +398,31 @@ int tgx_plan_stop(tgx_engine* e, const tgx_params* d_params, int64_t n, const do
                        static_cast<cudaStream_t>(stream));
 }
 
+int tgx_plan_samples(tgx_engine* e, const tgx_params* d_params, int64_t n, const double* d_state, int32_t* d_counts,
+                     uint32_t* d_status, void* stream) {
+    if (!e || n < 0 || (n > 0 && (!d_params || !d_state))) return TGX_ERR_INVALID;
+    if (n > 0x7fffffffLL) return TGX_ERR_INVALID;
+    TGX_CUDA(cudaSetDevice(e->device));
+    e->has_plan = false;
+    int rc = ensure_traj_scratch(e, n);
+    if (rc) return rc;
+    if ((rc = e->segs.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(tgx::Seg)))) return rc;
+    if ((rc = e->tiles.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(tgx::Tile)))) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // the engine's own status copy feeds tgx_feasibility; keep it consistent
+    TGX_CUDA(tgx::launch_plan_samples(d_params, d_state, n, e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(),
+                                      e->tiles.as<tgx::Tile>(), e->cnt.as<int32_t>(), e->status.as<uint32_t>(), s));
+    e->launches += 1;
+    if (d_counts) TGX_CUDA(cudaMemcpyAsync(d_counts, e->cnt.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (d_status) TGX_CUDA(cudaMemcpyAsync(d_status, e->status.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    e->has_plan = true;
+    e->plan_n = n;
+    e->plan_tiles = n;
+    e->plan_segs = n;
+    e->plan_samples = n;
+    return TGX_OK;
+}
+
 int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_max_a, void* stream) {
     if (!e) return TGX_ERR_INVALID;
     if (!e->has_plan) return TGX_ERR_NO_PLAN;
@@ -589,6 +616,35 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
     if (h_status && h_counts)
         for (int64_t i = 0; i < n; ++i)
             if ((int64_t)h_counts[i] > capacity) h_status[i] |= TGX_ST_TRUNCATED;
+    return TGX_OK;
+}
+
+int tgx_sample_host(tgx_engine* e, const tgx_params* h_params, double v, double accel, double s0, double s1,
+                    double* h_out14) {
+    if (!e || !h_params || !h_out14) return TGX_ERR_INVALID;
+    TGX_CUDA(cudaSetDevice(e->device));
+    int rc = host_streams(e);
+    if (rc) return rc;
+    cudaStream_t s = e->hs[0];
+    if ((rc = e->h_params[0].reserve(sizeof(tgx_params)))) return rc;
+    if ((rc = e->h_from[0].reserve(4 * sizeof(double)))) return rc;
+    if ((rc = e->h_out[0].reserve((size_t)TGX_NCHAN * 4 * sizeof(double)))) return rc;
+    const double state[4] = {v, accel, s0, s1};
+    TGX_CUDA(cudaMemcpyAsync(e->h_params[0].p, h_params, sizeof(tgx_params), cudaMemcpyHostToDevice, s));
+    TGX_CUDA(cudaMemcpyAsync(e->h_from[0].p, state, sizeof(state), cudaMemcpyHostToDevice, s));
+    rc = tgx_plan_samples(e, e->h_params[0].as<tgx_params>(), 1, e->h_from[0].as<double>(), nullptr, nullptr, s);
+    if (rc) return rc;
+    tgx_layout lay{};
+    lay.d_base = e->h_out[0].as<double>();
+    lay.traj_stride = TGX_NCHAN * 4;
+    lay.chan_stride = 4;
+    lay.capacity = 4;
+    rc = tgx_eval(e, &lay, nullptr, nullptr, s);
+    if (rc) return rc;
+    double tmp[TGX_NCHAN * 4];
+    TGX_CUDA(cudaMemcpyAsync(tmp, e->h_out[0].p, sizeof(tmp), cudaMemcpyDeviceToHost, s));
+    TGX_CUDA(cudaStreamSynchronize(s));
+    for (int c = 0; c < TGX_NCHAN; ++c) h_out14[c] = tmp[c * 4];
     return TGX_OK;
 }
 

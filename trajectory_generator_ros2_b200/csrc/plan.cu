@@ -664,6 +664,48 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
     if (status) status[i] = r.status;
 }
 
+// "Per-time evaluation": a one-sample plan per trajectory from an explicit state, i.e. the public helpers
+// createCircleGoal(v, accel, theta) (Circle.cpp:96), createFigure8Goal (Figure8.cpp:96) and
+// createLineGoal(last_x, last_y, v, accel, theta) (Line.cpp:91).  state[i] = {v, accel, s0, s1}: orbit s0 = theta;
+// line s0 = last_x, s1 = last_y and the explicit heading theta is read from params[i].u.line.reserved[0].
+__global__ void __launch_bounds__(128)
+plan_samples_kernel(const tgx_params* __restrict__ params, const double* __restrict__ state, int64_t n,
+                    TrajRec* __restrict__ recs, Seg* __restrict__ segs, Tile* __restrict__ tiles,
+                    int32_t* __restrict__ counts, uint32_t* __restrict__ status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const tgx_params p = load_params(params, i);
+    const double v = state[4 * i + 0], accel = state[4 * i + 1], s0 = state[4 * i + 2], s1 = state[4 * i + 3];
+    TrajRec t;
+    Seg g;
+    g.kb = -1; g.n = 1; g.flags = 0; g.pad = 0;
+    g.vb = v; g.dv = 0.0; g.vclamp = v;
+    t.n = 1;
+    for (int q = 0; q < 7; ++q) t.f[q] = 0.0;
+    const bool ok = params_ok(p);
+    if (p.type == TGX_LINE) {
+        const double theta = p.u.line.reserved[0];
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        t.type = TGX_LINE;
+        t.f[0] = cs; t.f[1] = sn; t.f[2] = theta; t.f[3] = p.alt; t.f[4] = p.dt;
+        g.s0 = s0; g.s1 = s1; g.acc = accel;
+    } else {
+        t.type = p.type & kRecTypeMask;
+        t.f[0] = p.u.orbit.r; t.f[1] = p.u.orbit.cx; t.f[2] = p.u.orbit.cy; t.f[3] = p.alt;
+        t.f[4] = ddiv(p.dt, p.u.orbit.r); t.f[5] = ddiv(1.0, p.u.orbit.r);
+        g.s0 = s0; g.s1 = 0.0; g.acc = s0;    // the segment's (only) sample carries theta exactly
+    }
+    if (!ok) t.n = 0;
+    recs[i] = t;
+    segs[i] = g;
+    Tile tl;
+    tl.traj = (int32_t)i; tl.k_lo = 0; tl.seg_begin = (int32_t)i; tl.nseg = ok ? 1 : 0;
+    tiles[i] = tl;
+    if (counts) counts[i] = ok ? 1 : 0;
+    if (status) status[i] = ok ? 0u : (uint32_t)TGX_ST_BAD_PARAM;
+}
+
 // Self-test of div_inv against __ddiv_rn on pseudo-random operands (splitmix64 streams): counts mismatches.
 __global__ void __launch_bounds__(256)
 selftest_division_kernel(int64_t n, uint64_t seed, int per_thread, unsigned long long* __restrict__ mismatches) {
@@ -737,6 +779,14 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
                                                                          max_samples, tile_shift, plan_counts, seg_off,
                                                                          tile_off, recs, segs, tiles, counts, status,
                                                                          phases);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_plan_samples(const tgx_params* params, const double* state, int64_t n, TrajRec* recs, Seg* segs,
+                                Tile* tiles, int32_t* counts, uint32_t* status, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    plan_samples_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(params, state, n, recs, segs, tiles, counts,
+                                                                         status);
     return cudaGetLastError();
 }
 

@@ -59,6 +59,8 @@ def _load() -> C.CDLL:
     lib.tgx_generate_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp]
     lib.tgx_stop_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp]
     lib.tgx_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    lib.tgx_plan_samples.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.tgx_sample_host.argtypes = [vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp]
     lib.tgx_selftest_division.argtypes = [vp, i64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     lib.tgx_alloc_host.restype = vp
     lib.tgx_alloc_host.argtypes = [i64]
@@ -309,6 +311,14 @@ class Engine:
                                                 phases.ctypes.data if phases is not None else None),
                     "tgx_generate_host")
         return out, counts, status, phases
+
+    def sample_host(self, params: np.ndarray, v: float, accel: float, s0: float, s1: float = 0.0) -> np.ndarray:
+        """tgx_sample_host: one create*Goal evaluation -> the 14 channels."""
+        params = np.ascontiguousarray(params)
+        out = np.zeros(abi.TGX_NCHAN)
+        self._check(self._lib.tgx_sample_host(self._h, params.ctypes.data, v, accel, s0, s1, out.ctypes.data),
+                    "tgx_sample_host")
+        return out
 
     def stop_host(self, params: np.ndarray, from14: np.ndarray, capacity: int, want_phases: bool = False):
         """tgx_stop_host -> (out [n, 14, capacity], counts, status, phases or None)."""

@@ -1,0 +1,274 @@
+// tgx_trajectories.cpp — see tgx_trajectories.hpp.  Host glue only: every sample comes from libtgx (CUDA).
+#include "tgx_trajectories.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+namespace TGX_DROPIN_NAMESPACE {
+
+namespace {
+
+using snapstack_msgs2::msg::Goal;
+
+[[noreturn]] void die(const rclcpp::Logger& logger, const char* what, int rc) {
+    RCLCPP_ERROR(logger, "tgx: %s failed: %s (%s)", what, tgx_strerror(rc), tgx_last_cuda_error());
+    std::exit(1);   // generateTraj "can exit the program" (Trajectory.hpp:32); there is no CPU fallback
+}
+
+// std::to_string(double) is "%f" (Circle.cpp:45, 61-62).
+std::string f6(double x) { return std::to_string(x); }
+
+std::string phaseText(const std::string& shape, int type, int kind, double value, double value2, bool stop_traj) {
+    switch (kind) {
+        case TGX_PH_ACCEL_TO: return shape + " traj: accelerating to " + f6(value) + " m/s";
+        case TGX_PH_REACHED:
+            return shape + " traj: reached " + f6(value) + " m/s, keeping constant v for " + f6(value2) + " s";
+        case TGX_PH_DECEL: return shape + " traj: decelerating to 0 m/s";
+        case TGX_PH_STOPPED:
+            // Figure8::generateTraj announces "Figure 8 traj: stopped" (Figure8.cpp:89); its braking path and the
+            // other classes use the plain shape name.
+            if (type == TGX_FIGURE8 && !stop_traj) return "Figure 8 traj: stopped";
+            return shape + " traj: stopped";
+        case TGX_PH_PRESSED_END: return shape + " traj: pressed END, decelerating to 0 m/s";
+        default: return shape + " traj: ?";
+    }
+}
+
+Goal goalFromPlanes(const double* row, int64_t cap, int64_t k) {
+    Goal g;
+    g.header.frame_id = "world";                 // Circle.cpp:106
+    g.p.x = row[TGX_PX * cap + k];  g.p.y = row[TGX_PY * cap + k];  g.p.z = row[TGX_PZ * cap + k];
+    g.v.x = row[TGX_VX * cap + k];  g.v.y = row[TGX_VY * cap + k];  g.v.z = row[TGX_VZ * cap + k];
+    g.a.x = row[TGX_AX * cap + k];  g.a.y = row[TGX_AY * cap + k];  g.a.z = row[TGX_AZ * cap + k];
+    g.j.x = row[TGX_JX * cap + k];  g.j.y = row[TGX_JY * cap + k];  g.j.z = row[TGX_JZ * cap + k];
+    g.psi = row[TGX_PSI * cap + k];
+    g.dpsi = row[TGX_DPSI * cap + k];
+    g.power = true;                              // Circle.cpp:127
+    return g;
+}
+
+void goalToArray(const Goal& g, double a[TGX_NCHAN]) {
+    a[TGX_PX] = g.p.x; a[TGX_PY] = g.p.y; a[TGX_PZ] = g.p.z;
+    a[TGX_VX] = g.v.x; a[TGX_VY] = g.v.y; a[TGX_VZ] = g.v.z;
+    a[TGX_AX] = g.a.x; a[TGX_AY] = g.a.y; a[TGX_AZ] = g.a.z;
+    a[TGX_JX] = g.j.x; a[TGX_JY] = g.j.y; a[TGX_JZ] = g.j.z;
+    a[TGX_PSI] = g.psi; a[TGX_DPSI] = g.dpsi;
+}
+
+// Page-locked staging buffer, reused across calls.
+struct Staging {
+    double* p = nullptr;
+    int64_t doubles = 0;
+    double* reserve(int64_t want) {
+        if (want <= doubles) return p;
+        if (p) tgx_free_host(p);
+        p = static_cast<double*>(tgx_alloc_host(want * (int64_t)sizeof(double)));
+        doubles = p ? want : 0;
+        return p;
+    }
+};
+
+Staging& staging() {
+    static Staging s;
+    return s;
+}
+
+tgx_params orbitParams(int type, double alt, double r, double cx, double cy, const std::vector<double>& v_goals,
+                       double t_traj, double accel, double dt) {
+    if (v_goals.size() > TGX_MAX_VGOALS)
+        throw std::invalid_argument("tgx: at most " + std::to_string(TGX_MAX_VGOALS) + " v_goals are supported");
+    tgx_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.type = type;
+    p.n_vgoals = (int32_t)v_goals.size();
+    p.dt = dt;
+    p.alt = alt;
+    p.u.orbit.r = r;
+    p.u.orbit.cx = cx;
+    p.u.orbit.cy = cy;
+    p.u.orbit.t_traj = t_traj;
+    p.u.orbit.accel = accel;
+    for (size_t i = 0; i < v_goals.size(); ++i) p.u.orbit.v_goals[i] = v_goals[i];
+    return p;
+}
+
+}  // namespace
+
+tgx_engine* sharedEngine() {
+    static tgx_engine* engine = nullptr;
+    if (!engine) {
+        int device = 0;
+        if (const char* env = std::getenv("TGX_DEVICE")) device = std::atoi(env);
+        const int rc = tgx_create(&engine, device);
+        if (rc != TGX_OK) {
+            std::fprintf(stderr, "tgx: cannot create the GPU engine on device %d: %s (%s)\n", device,
+                         tgx_strerror(rc), tgx_last_cuda_error());
+            std::exit(1);
+        }
+    }
+    return engine;
+}
+
+GpuTrajectory::GpuTrajectory(const tgx_params& params, const char* shape, const char* logger_name)
+    : ::trajectory_generator::Trajectory(params.dt), params_(params), shape_(shape),
+      logger_(rclcpp::get_logger(logger_name)) {}
+
+GpuTrajectory::~GpuTrajectory() {}
+
+void GpuTrajectory::generateTraj(std::vector<Goal>& goals, std::unordered_map<int, std::string>& index_msgs,
+                                 const rclcpp::Clock::SharedPtr& clock) {
+    rclcpp::Time tstart = clock->now();
+    tgx_engine* e = sharedEngine();
+
+    // pass 1: the exact sample count (replays the reference's loops on the GPU)
+    int32_t n = 0;
+    uint32_t status = 0;
+    int rc = tgx_count_host(e, &params_, 1, nullptr, &n, &status);
+    if (rc != TGX_OK) die(logger_, "tgx_count_host", rc);
+    last_status_ = status;
+    if (status & (TGX_ST_BAD_PARAM | TGX_ST_TOO_LONG)) {
+        RCLCPP_ERROR(logger_, "Error: %s trajectory parameters rejected (status 0x%x)", shape_.c_str(), status);
+        std::exit(1);
+    }
+
+    // pass 2: all samples into a page-locked SoA row, then repack to the reference's AoS messages
+    const int64_t cap = ((int64_t)n + 3) / 4 * 4;
+    double* row = staging().reserve((int64_t)TGX_NCHAN * cap);
+    if (!row) die(logger_, "tgx_alloc_host", TGX_ERR_NOMEM);
+    tgx_phases phases;
+    rc = tgx_generate_host(e, &params_, 1, nullptr, row, cap, &n, &status, &phases);
+    if (rc != TGX_OK) die(logger_, "tgx_generate_host", rc);
+    last_status_ = status;
+
+    const size_t base = goals.size();            // generateTraj APPENDS (Circle.cpp:41: push_back, keys size()-1)
+    goals.reserve(base + (size_t)n);
+    for (int64_t k = 0; k < n; ++k) goals.push_back(goalFromPlanes(row, cap, k));
+    for (int i = 0; i < phases.n; ++i)
+        index_msgs[(int)base + phases.key[i]] =
+            phaseText(shape_, params_.type, phases.kind[i], phases.value[i], phases.value2[i], false);
+
+    if (status & TGX_ST_VGOALS_NOT_INCREASING)   // Circle.cpp:57-59, Figure8.cpp:57-59
+        RCLCPP_WARN(logger_, "Vels are not in increasing order, ignoring vels from the first to decrease...");
+    if (status & TGX_ST_FINAL_V_NONZERO) {       // Circle.cpp:85-88
+        RCLCPP_ERROR(logger_, "Error: final velocity is not zero");
+        std::exit(1);
+    }
+    if (status & TGX_ST_LINE_END_NOT_B) {        // Line.cpp:76-79
+        RCLCPP_ERROR(logger_, "Error: final point is not B");
+        std::exit(1);
+    }
+    RCLCPP_INFO(logger_, "Time to calculate the traj (s): %f", (clock->now() - tstart).seconds());
+    RCLCPP_INFO(logger_, "Goal vector size = %lu", goals.size());
+}
+
+void GpuTrajectory::generateStopTraj(std::vector<Goal>& goals, std::unordered_map<int, std::string>& index_msgs,
+                                     int& pub_index, const rclcpp::Clock::SharedPtr& clock) {
+    rclcpp::Time tstart = clock->now();
+    tgx_engine* e = sharedEngine();
+
+    double from[TGX_NCHAN];
+    goalToArray(goals[pub_index], from);         // the setpoint being braked from (Circle.cpp:140-143)
+
+    // a braking ramp never has more samples than v / (a*dt) + 2; size the row from a count-only call
+    int32_t n = 0;
+    uint32_t status = 0;
+    double dummy[4 * TGX_NCHAN];
+    int rc = tgx_stop_host(e, &params_, 1, from, dummy, 0, &n, &status, nullptr);
+    if (rc != TGX_OK) die(logger_, "tgx_stop_host", rc);
+    const int64_t cap = ((int64_t)n + 3) / 4 * 4;
+    double* row = staging().reserve((int64_t)TGX_NCHAN * (cap > 0 ? cap : 4));
+    if (!row) die(logger_, "tgx_alloc_host", TGX_ERR_NOMEM);
+    tgx_phases phases;
+    rc = tgx_stop_host(e, &params_, 1, from, row, cap, &n, &status, &phases);
+    if (rc != TGX_OK) die(logger_, "tgx_stop_host", rc);
+    last_status_ = status & ~(uint32_t)TGX_ST_TRUNCATED;
+
+    std::vector<Goal> goals_tmp;
+    std::unordered_map<int, std::string> index_msgs_tmp;
+    goals_tmp.reserve((size_t)n);
+    for (int64_t k = 0; k < n; ++k) goals_tmp.push_back(goalFromPlanes(row, cap, k));
+    for (int i = 0; i < phases.n; ++i)
+        index_msgs_tmp[phases.key[i]] =
+            phaseText(shape_, params_.type, phases.kind[i], phases.value[i], phases.value2[i], true);
+
+    goals = std::move(goals_tmp);                // Circle.cpp:162-164: replace, reset the publication index
+    index_msgs = std::move(index_msgs_tmp);
+    pub_index = 0;
+
+    RCLCPP_INFO(logger_, "Time to calculate the braking traj (s): %f", (clock->now() - tstart).seconds());
+    RCLCPP_INFO(logger_, "Goal vector size = %lu", goals.size());
+}
+
+bool GpuTrajectory::trajectoryInsideBounds(double xmin, double xmax, double ymin, double ymax, double zmin,
+                                           double zmax) {
+    tgx_limits lim;
+    std::memset(&lim, 0, sizeof(lim));
+    lim.box[0] = xmin; lim.box[1] = xmax; lim.box[2] = ymin; lim.box[3] = ymax; lim.box[4] = zmin; lim.box[5] = zmax;
+    lim.check_box = 1;
+    int32_t n = 0;
+    uint32_t status = 0;
+    const int rc = tgx_count_host(sharedEngine(), &params_, 1, &lim, &n, &status);
+    if (rc != TGX_OK) die(logger_, "tgx_count_host", rc);
+    if (status & TGX_ST_LINE_D2_NEGATIVE)        // Line.cpp:165-168
+        RCLCPP_ERROR(logger_, "Line trajectory not feasible. Please increase accel, decrease v, or increase line length.");
+    return (status & (TGX_ST_OUTSIDE_BOUNDS | TGX_ST_BAD_PARAM)) == 0;
+}
+
+Goal GpuTrajectory::sampleGoal(double v, double accel, double s0, double s1) const {
+    double out[TGX_NCHAN];
+    const int rc = tgx_sample_host(sharedEngine(), &params_, v, accel, s0, s1, out);
+    if (rc != TGX_OK) die(logger_, "tgx_sample_host", rc);
+    return goalFromPlanes(out, 1, 0);
+}
+
+Circle::Circle(double alt, double r, double cx, double cy, std::vector<double> v_goals, double t_traj,
+               double accel, double dt)
+    : GpuTrajectory(orbitParams(TGX_CIRCLE, alt, r, cx, cy, v_goals, t_traj, accel, dt), "Circle", "circle_logger") {}
+
+Goal Circle::createCircleGoal(double v, double accel, double theta) const { return sampleGoal(v, accel, theta, 0.0); }
+
+Figure8::Figure8(double alt, double r, double cx, double cy, std::vector<double> v_goals, double t_traj,
+                 double accel, double dt)
+    : GpuTrajectory(orbitParams(TGX_FIGURE8, alt, r, cx, cy, v_goals, t_traj, accel, dt), "Figure8",
+                    "figure8_logger") {}
+
+Goal Figure8::createFigure8Goal(double v, double accel, double theta) const {
+    return sampleGoal(v, accel, theta, 0.0);
+}
+
+namespace {
+tgx_params lineParams(double alt, const Eigen::Vector3d& A, const Eigen::Vector3d& B,
+                      const std::vector<double>& v_goals, double a1, double a3, double dt) {
+    if (v_goals.empty()) throw std::invalid_argument("tgx: Line needs v_goals[0]");
+    tgx_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.type = TGX_LINE;
+    p.n_vgoals = 1;
+    p.dt = dt;
+    p.alt = alt;
+    p.u.line.A[0] = A.x(); p.u.line.A[1] = A.y(); p.u.line.A[2] = A.z();
+    p.u.line.B[0] = B.x(); p.u.line.B[1] = B.y(); p.u.line.B[2] = B.z();
+    p.u.line.a1 = a1;
+    p.u.line.a3 = a3;
+    p.u.line.v_goal = v_goals[0];                // "for now just 1 element" (Line.hpp:57, Line.cpp:43)
+    return p;
+}
+}  // namespace
+
+Line::Line(double alt, Eigen::Vector3d A, Eigen::Vector3d B, std::vector<double> v_goals, double a1, double a3,
+           double dt)
+    : GpuTrajectory(lineParams(alt, A, B, v_goals, a1, a3, dt), "Line", "line_logger") {}
+
+Goal Line::createLineGoal(double last_x, double last_y, double v, double accel, double theta) const {
+    // the line's own heading lives in the plan; an explicit theta is passed through the state slot of the call
+    double out[TGX_NCHAN];
+    tgx_params p = params_;
+    p.u.line.reserved[0] = theta;                // tgx_sample_host reads the explicit heading here for lines
+    const int rc = tgx_sample_host(sharedEngine(), &p, v, accel, last_x, last_y, out);
+    if (rc != TGX_OK) die(logger_, "tgx_sample_host", rc);
+    return goalFromPlanes(out, 1, 0);
+}
+
+}  // namespace TGX_DROPIN_NAMESPACE
