@@ -452,3 +452,40 @@ def test_properties_at_scale(engine, oracle):
         ref, _, _ = oracle.generate(params[i:i + 1])
         merge_errors(worst, assert_samples_close(host[j, :, :counts[i]], ref, f"scale[{i}]"))
     print("worst errors at scale:", worst)
+
+
+# ---- the Python mirror of the reference's class interface ------------------------------------------------
+
+def test_python_trajectory_classes(engine, oracle):
+    from trajectory_generator_ros2_b200 import trajectories as T
+    circ = T.Circle(1.8, 3.4, 0.0, 0.0, [1.0, 2.0, 2.0], 80.0, 0.4, 0.01, engine=engine)
+    goals, msgs = [T.Goal()], {}                         # non-empty on entry: generateTraj appends
+    circ.generateTraj(goals, msgs)
+    assert len(goals) == 25002 and sorted(msgs) == [1, 251, 8251, 8501, 16501, 24501, 25001]
+    ref, _, _ = oracle.generate(workloads.default_circle())
+    got = np.stack([g.channels() for g in goals[1:]], axis=1)
+    assert_samples_close(got, ref, "python Circle")
+    assert goals[5].frame_id == "world" and goals[5].power is True
+    assert circ.trajectoryInsideBounds(-5, 5, -5, 5, -5, 5) and not circ.trajectoryInsideBounds(-3, 3, -3, 3, 0, 3)
+    pub = circ.generateStopTraj(goals, msgs, 12501)
+    assert pub == 0 and len(goals) == 500 and msgs == {0: "Circle traj: pressed END, decelerating to 0 m/s",
+                                                        499: "Circle traj: stopped"}
+    g = circ.createCircleGoal(1.7, 0.4, 2.5)
+    assert abs(g.p.x - (3.4 * np.cos(2.5))) < 1e-12 and abs(g.psi - (2.5 + np.pi / 2)) < 1e-15
+
+    line = T.Line(1.8, [0, -3, 1.8], [0, 3, 1.8], [1.0], 1.5, 1.0, 0.01, engine=engine)
+    goals, msgs = [], {}
+    line.generateTraj(goals, msgs)
+    assert len(goals) == 685 and goals[-1].p.y == 3.0 and sorted(msgs) == [0, 67, 584, 684]
+    g = line.createLineGoal(0.3, -1.0, 0.8, 1.5, 0.7)
+    assert abs(g.p.x - (0.3 + 0.8 * np.cos(0.7) * 0.01)) < 1e-15 and abs(g.a.y - 1.5 * np.sin(0.7)) < 1e-15
+
+    short = T.Line(1.8, [0, -3, 1.8], [0, -2.5, 1.8], [1.0], 1.5, 1.0, 0.01, engine=engine)
+    assert not short.trajectoryInsideBounds(-5, 5, -5, 5, -5, 5)
+    with pytest.raises(T.TrajectoryError):
+        short.generateTraj([], {})                       # the reference exits here: "final point is not B"
+
+    fig = T.Figure8(1.8, 3.4, 0.0, 0.0, [1.0, 2.0, 2.0], 80.0, 0.4, 0.01, engine=engine)
+    goals, msgs = [], {}
+    fig.generateTraj(goals, msgs)
+    assert len(goals) == 25001 and msgs[25000] == "Figure 8 traj: stopped"
