@@ -192,6 +192,12 @@ int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt);
  *       at every segment base, and theta on every hold sample, is bit-identical to the reference.  O(N) work.
  * Braking plans (tgx_plan_stop) always use the exact replay.  Invalidates the current plan. */
 int tgx_set_plan_mode(tgx_engine* e, int exact_ramps);
+/* Single-replay planning (default on): once a plan has measured the largest per-trajectory segment / tile counts of
+ * a batch, later plans give every trajectory a fixed slice of the tables and need no counting pass and no scans; a
+ * batch that does not fit falls back to the two-replay exact-offset path automatically.  allow = 0 disables it. */
+int tgx_set_slab_planning(tgx_engine* e, int allow);
+/* How many plans so far took the single-replay / the two-replay path (either pointer may be NULL). */
+int tgx_plan_path_counts(const tgx_engine* e, int64_t* slab_plans, int64_t* exact_plans);
 /* Bytes of device scratch currently held by the engine (plan tables). */
 int64_t tgx_scratch_bytes(const tgx_engine* e);
 
@@ -271,7 +277,7 @@ int tgx_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t
 
 /* ---- introspection used by bench.py ---------------------------------------------------------------- */
 /* Number of this library's own (hand-written) kernels launched on this engine since creation: plan_count,
- * plan_fill, eval, feasibility_finalize.  The cub scans inside tgx_plan are not counted. */
+ * build_cur_table, plan_fill, eval, feasibility_finalize.  The cub scans inside tgx_plan are not counted. */
 int64_t tgx_launch_count(const tgx_engine* e);
 /* Tiles / segments of the current plan (0 if none). */
 int64_t tgx_plan_tiles(const tgx_engine* e);

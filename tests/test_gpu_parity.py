@@ -489,3 +489,55 @@ def test_python_trajectory_classes(engine, oracle):
     goals, msgs = [], {}
     fig.generateTraj(goals, msgs)
     assert len(goals) == 25001 and msgs[25000] == "Figure 8 traj: stopped"
+
+
+# ---- single-replay (slab) planning -------------------------------------------------------------------------
+
+def test_slab_planning_matches_exact_offsets_and_falls_back(engine, oracle):
+    """The second plan of a similar batch takes the single-replay path (fixed per-trajectory slices); its samples
+    must be bit-identical to the two-replay path, and a batch that does not fit its slices must fall back."""
+    import torch
+    params = workloads.circles_cfg2(5000)
+    engine.set_slab_planning(False)
+    base, counts, status, _ = gpu_generate(engine, params, capacity=1024, want_phases=False)
+    engine.set_slab_planning(True)
+    s0, e0 = engine.plan_path_counts()
+    first, c1, st1, _ = gpu_generate(engine, params, capacity=1024, want_phases=False)     # learns the slice sizes
+    s1, e1 = engine.plan_path_counts()
+    assert (s1 - s0, e1 - e0) == (0, 1)
+    second, c2, st2, ph2 = gpu_generate(engine, workloads.circles_cfg2(5000), capacity=1024, want_phases=True)
+    s2, e2 = engine.plan_path_counts()
+    assert (s2 - s1, e2 - e1) == (1, 0), "second plan of the same batch shape should be single-replay"
+    np.testing.assert_array_equal(c2, counts)
+    np.testing.assert_array_equal(st2, status)
+    m = ~np.isnan(base)
+    assert (np.isnan(second) == np.isnan(base)).all() and (np.isnan(first) == np.isnan(base)).all()
+    np.testing.assert_array_equal(second[m], base[m])
+    np.testing.assert_array_equal(first[m], base[m])
+    # phases come out of the single-replay path too
+    _, _, oph = oracle.generate(params[17:18])
+    assert abi.phases_to_index_msgs(0, ph2[17]) == abi.phases_to_index_msgs(0, oph)
+    # a batch with a 25-tile trajectory and bad parameters does not fit 1-tile slices: automatic fallback
+    bad = workloads.default_circle().copy()
+    bad["accel"] = -1.0
+    mixed = abi.concat([workloads.circles_cfg2(300), workloads.default_circle(), bad, workloads.mixed_cfg3(200)])
+    out, c3, st3, _ = gpu_generate(engine, mixed, want_phases=False)
+    s3, e3 = engine.plan_path_counts()
+    assert e3 - e2 == 1, "overflowing slices must redo the plan with exact offsets"
+    o_counts, o_status = oracle.count_batch(mixed)
+    np.testing.assert_array_equal(c3, o_counts)
+    np.testing.assert_array_equal(st3, o_status)
+    ref, _, _ = oracle.generate(mixed[300:301])
+    assert_samples_close(out[300, :, :25001], ref, "default circle after slab fallback")
+    # ragged batch learned: the next plan of it stays on the exact-offset path (too many empty slots otherwise)
+    gpu_generate(engine, mixed, want_phases=False)
+    s4, e4 = engine.plan_path_counts()
+    assert (s4 - s3, e4 - e3) == (0, 1)
+
+
+def test_hold_table_handles_mixed_dt(engine, oracle):
+    """The hold-length table is built for the first trajectory's dt; others must fall back to their own walk."""
+    recs = [abi.circle_params(1.0, 1.5, 0, 0, [1.0], t, 0.5, dt)
+            for dt in (0.01, 0.02, 0.005, 0.01, 1.0 / 3.0, 0.01) for t in (0.0, 0.7, 10.0, 33.3)]
+    params = abi.concat(recs)
+    check_batch(engine, oracle, params, "mixed dt")

@@ -54,7 +54,15 @@ def main():
     ms = timed(lambda: eng.count(d_params))
     print(f"tgx_count                   : {ms:8.3f} ms")
     ms = timed(lambda: eng.plan(d_params, want_outputs=False))
-    print(f"tgx_plan                    : {ms:8.3f} ms   tiles {eng._lib.tgx_plan_tiles(eng._h)} segs {eng._lib.tgx_plan_segments(eng._h)}")
+    print(f"tgx_plan                    : {ms:8.3f} ms   tiles {eng._lib.tgx_plan_tiles(eng._h)} segs {eng._lib.tgx_plan_segments(eng._h)} (single-replay, two-replay plans so far: {eng.plan_path_counts()})")
+    eng.set_slab_planning(False)
+    ms = timed(lambda: eng.plan(d_params, want_outputs=False))
+    print(f"tgx_plan (two-replay path)  : {ms:8.3f} ms")
+    eng.set_slab_planning(True)
+    eng.set_plan_mode(True)
+    ms = timed(lambda: eng.plan(d_params, want_outputs=False))
+    print(f"tgx_plan (exact ramps)      : {ms:8.3f} ms   paths {eng.plan_path_counts()}")
+    eng.set_plan_mode(False)
     # ---- eval shapes --------------------------------------------------------------------------------------------
     for shift, spt in ((9, 2), (9, 4), (10, 2), (10, 4), (11, 2), (11, 4)):
         eng.set_tuning(shift, spt)

@@ -22,13 +22,18 @@
 
 namespace tgx {
 
+cudaError_t launch_build_cur_table(const tgx_params* params, int64_t max_samples, void* table, cudaStream_t stream);
+size_t cur_table_bytes();
 cudaError_t launch_plan_count(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
-                              int64_t max_samples, int tile_shift, bool exact_ramps, int32_t* counts,
-                              uint32_t* status, int32_t* nseg, int32_t* ntile, cudaStream_t stream);
+                              int64_t max_samples, int tile_shift, bool exact_ramps, const void* cur_table,
+                              int32_t* counts, uint32_t* status, int32_t* nseg, int32_t* ntile,
+                              cudaStream_t stream);
 cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
-                             int64_t max_samples, int tile_shift, bool exact_ramps, const int32_t* plan_counts,
-                             const int64_t* seg_off, const int64_t* tile_off, TrajRec* recs, Seg* segs, Tile* tiles,
-                             int32_t* counts, uint32_t* status, tgx_phases* phases, cudaStream_t stream);
+                             int64_t max_samples, int tile_shift, bool exact_ramps, const void* cur_table,
+                             const int32_t* plan_counts, const int64_t* seg_off, const int64_t* tile_off,
+                             int seg_slab, int tile_slab, TrajRec* recs, Seg* segs, Tile* tiles, int32_t* counts,
+                             uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
+                             PlanStats* stats, cudaStream_t stream);
 cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles, int tile_shift,
                         int spt, const OutView& out, bool store, double* max_v, double* max_a,
                         cudaStream_t stream);
@@ -145,8 +150,14 @@ struct tgx_engine {
     int spt = 4;           // samples per thread: 2 -> 128-bit stores, 4 -> 256-bit stores (measured best on B200)
     int64_t launches = 0;
 
+    // slab-mode planning (single replay): slice sizes learned from the previous exact-offset plan
+    bool allow_slabs = true;
+    bool slabs_ready = false;
+    int seg_slab = 0, tile_slab = 0;
+    int64_t slab_plans = 0, exact_plans = 0;
+
     // per-trajectory scratch (capacity in trajectories)
-    DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals;
+    DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals, cur_table, stats;
     // tables
     DevBuf segs, tiles;
     PinBuf h_totals;
@@ -175,7 +186,9 @@ int ensure_traj_scratch(tgx_engine* e, int64_t n) {
     if ((rc = e->tile_off.reserve(n1 * sizeof(int64_t)))) return rc;
     if ((rc = e->recs.reserve(n1 * sizeof(tgx::TrajRec)))) return rc;
     if ((rc = e->totals.reserve(4 * sizeof(int64_t)))) return rc;
-    if ((rc = e->h_totals.reserve(4 * sizeof(int64_t)))) return rc;
+    if ((rc = e->h_totals.reserve(16 * sizeof(int64_t)))) return rc;
+    if ((rc = e->cur_table.reserve(tgx::cur_table_bytes()))) return rc;
+    if ((rc = e->stats.reserve(sizeof(tgx::PlanStats)))) return rc;
     return TGX_OK;
 }
 
@@ -203,46 +216,108 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     int64_t* seg_off = e->seg_off.as<int64_t>();
     int64_t* tile_off = e->tile_off.as<int64_t>();
     int64_t* totals = e->totals.as<int64_t>();
+    tgx::PlanStats* d_stats = e->stats.as<tgx::PlanStats>();
+    tgx::PlanStats* h_stats = reinterpret_cast<tgx::PlanStats*>(static_cast<int64_t*>(e->h_totals.p) + 4);
 
-    // pass 1: counts
-    TGX_CUDA(tgx::launch_plan_count(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
-                                    cnt, st, nseg, ntile, stream));
-    e->launches += 1;
-    // trailing zero so that an exclusive scan over n+1 items leaves the grand total in element n
-    TGX_CUDA(cudaMemsetAsync(nseg + n, 0, sizeof(int32_t), stream));
-    TGX_CUDA(cudaMemsetAsync(ntile + n, 0, sizeof(int32_t), stream));
+    // the hold-length table of this batch's dt (one thread, a few microseconds)
+    const void* tab = nullptr;
+    if (!d_stop_from) {
+        TGX_CUDA(tgx::launch_build_cur_table(d_params, e->max_samples, e->cur_table.p, stream));
+        e->launches += 1;
+        tab = e->cur_table.p;
+    }
 
-    // pass 2: exclusive scans (segment and tile offsets) and the sample total
-    WideIter seg_in{nseg}, tile_in{ntile}, cnt_in{cnt};
-    size_t need = 0, t1 = 0, t2 = 0;
-    TGX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t1, seg_in, seg_off, (int)(n + 1), stream));
-    TGX_CUDA(cub::DeviceReduce::Sum(nullptr, t2, cnt_in, totals, (int)n, stream));
-    need = std::max(t1, t2);
-    if ((rc = e->cub_tmp.reserve(need))) return rc;
-    size_t tmp_bytes = e->cub_tmp.bytes;
-    TGX_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp_bytes, seg_in, seg_off, (int)(n + 1), stream));
-    tmp_bytes = e->cub_tmp.bytes;
-    TGX_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp_bytes, tile_in, tile_off, (int)(n + 1), stream));
-    tmp_bytes = e->cub_tmp.bytes;
-    TGX_CUDA(cub::DeviceReduce::Sum(e->cub_tmp.p, tmp_bytes, cnt_in, totals, (int)n, stream));
-    // (the cub scan / reduce launches are library plumbing and are not counted in tgx_launch_count)
+    int64_t tot_samples = 0, tot_segs = 0, tot_tiles = 0;
+    bool done = false;
 
-    int64_t* h = static_cast<int64_t*>(e->h_totals.p);
-    TGX_CUDA(cudaMemcpyAsync(h + 0, totals, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    TGX_CUDA(cudaMemcpyAsync(h + 1, seg_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    TGX_CUDA(cudaMemcpyAsync(h + 2, tile_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    TGX_CUDA(cudaStreamSynchronize(stream));
-    const int64_t tot_samples = h[0], tot_segs = h[1], tot_tiles = h[2];
-    if (tot_segs > 0x7fffffffLL || tot_tiles > 0x7fffffffLL) return TGX_ERR_CAPACITY;
+    // ---- slab mode: ONE replay, no scans; falls through to the exact-offset path if a slice overflows ----------
+    if (e->allow_slabs && e->slabs_ready && !d_stop_from) {
+        const int64_t need_segs = n * (int64_t)e->seg_slab, need_tiles = n * (int64_t)e->tile_slab;
+        if (need_segs <= 0x7fffffffLL && need_tiles <= 0x7fffffffLL) {
+            if ((rc = e->segs.reserve((size_t)need_segs * sizeof(tgx::Seg)))) return rc;
+            if ((rc = e->tiles.reserve((size_t)need_tiles * sizeof(tgx::Tile)))) return rc;
+            TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+            TGX_CUDA(tgx::launch_plan_fill(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
+                                           tab, nullptr, nullptr, nullptr, e->seg_slab, e->tile_slab,
+                                           e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(),
+                                           e->tiles.as<tgx::Tile>(), d_counts, d_status, cnt, st, d_phases, d_stats,
+                                           stream));
+            e->launches += 1;
+            TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
+            TGX_CUDA(cudaStreamSynchronize(stream));
+            if (!h_stats->overflow) {
+                tot_samples = (int64_t)h_stats->total_samples;
+                tot_segs = need_segs;
+                tot_tiles = need_tiles;
+                done = true;
+                e->slab_plans += 1;
+                // a batch with many fewer tiles than slots would launch mostly empty CTAs: go back to exact offsets
+                if ((int64_t)h_stats->total_tiles * 2 < need_tiles) e->slabs_ready = false;
+            } else {
+                e->slabs_ready = false;   // re-learn the slice sizes below
+            }
+        }
+    }
 
-    if ((rc = e->segs.reserve((size_t)std::max<int64_t>(tot_segs, 1) * sizeof(tgx::Seg)))) return rc;
-    if ((rc = e->tiles.reserve((size_t)std::max<int64_t>(tot_tiles, 1) * sizeof(tgx::Tile)))) return rc;
+    if (!done) {
+        // ---- exact-offset mode, pass 1: counts ------------------------------------------------------------------
+        TGX_CUDA(tgx::launch_plan_count(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift,
+                                        e->exact_ramps, tab, cnt, st, nseg, ntile, stream));
+        e->launches += 1;
+        // trailing zero so that an exclusive scan over n+1 items leaves the grand total in element n
+        TGX_CUDA(cudaMemsetAsync(nseg + n, 0, sizeof(int32_t), stream));
+        TGX_CUDA(cudaMemsetAsync(ntile + n, 0, sizeof(int32_t), stream));
 
-    // pass 3: fill
-    TGX_CUDA(tgx::launch_plan_fill(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, e->exact_ramps, cnt, seg_off,
-                                   tile_off, e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(),
-                                   e->tiles.as<tgx::Tile>(), d_counts, d_status, d_phases, stream));
-    e->launches += 1;
+        // pass 2: exclusive scans (segment and tile offsets) and the sample total
+        WideIter seg_in{nseg}, tile_in{ntile}, cnt_in{cnt};
+        size_t need = 0, t1 = 0, t2 = 0;
+        TGX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t1, seg_in, seg_off, (int)(n + 1), stream));
+        TGX_CUDA(cub::DeviceReduce::Sum(nullptr, t2, cnt_in, totals, (int)n, stream));
+        need = std::max(t1, t2);
+        if ((rc = e->cub_tmp.reserve(need))) return rc;
+        size_t tmp_bytes = e->cub_tmp.bytes;
+        TGX_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp_bytes, seg_in, seg_off, (int)(n + 1), stream));
+        tmp_bytes = e->cub_tmp.bytes;
+        TGX_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp_bytes, tile_in, tile_off, (int)(n + 1), stream));
+        tmp_bytes = e->cub_tmp.bytes;
+        TGX_CUDA(cub::DeviceReduce::Sum(e->cub_tmp.p, tmp_bytes, cnt_in, totals, (int)n, stream));
+        // (the cub scan / reduce launches are library plumbing and are not counted in tgx_launch_count)
+
+        int64_t* h = static_cast<int64_t*>(e->h_totals.p);
+        TGX_CUDA(cudaMemcpyAsync(h + 0, totals, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        TGX_CUDA(cudaMemcpyAsync(h + 1, seg_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        TGX_CUDA(cudaMemcpyAsync(h + 2, tile_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        TGX_CUDA(cudaStreamSynchronize(stream));
+        tot_samples = h[0];
+        tot_segs = h[1];
+        tot_tiles = h[2];
+        if (tot_segs > 0x7fffffffLL || tot_tiles > 0x7fffffffLL) return TGX_ERR_CAPACITY;
+
+        if ((rc = e->segs.reserve((size_t)std::max<int64_t>(tot_segs, 1) * sizeof(tgx::Seg)))) return rc;
+        if ((rc = e->tiles.reserve((size_t)std::max<int64_t>(tot_tiles, 1) * sizeof(tgx::Tile)))) return rc;
+
+        // pass 3: fill (also measures the per-trajectory maxima that size the slabs of the next plan)
+        TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+        TGX_CUDA(tgx::launch_plan_fill(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
+                                       tab, cnt, seg_off, tile_off, 0, 0, e->recs.as<tgx::TrajRec>(),
+                                       e->segs.as<tgx::Seg>(), e->tiles.as<tgx::Tile>(), d_counts, d_status, nullptr,
+                                       nullptr, d_phases, d_stats, stream));
+        e->launches += 1;
+        e->exact_plans += 1;
+        if (e->allow_slabs && !d_stop_from) {
+            TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
+            TGX_CUDA(cudaStreamSynchronize(stream));
+            // slices: the largest trajectory of this batch plus headroom; worth it only for batches without many
+            // short rows (every slot becomes a CTA) and with a moderate table footprint
+            const int seg_slab = (h_stats->max_nseg + 4 + 3) / 4 * 4;
+            const int tile_slab = std::max(h_stats->max_ntile, 1);
+            const bool dense = n * (int64_t)tile_slab <= tot_tiles + tot_tiles / 4 + 1;
+            const bool small = n * (int64_t)seg_slab * (int64_t)sizeof(tgx::Seg) <= ((int64_t)8 << 30);
+            e->slabs_ready = dense && small && tot_tiles > 0;
+            e->seg_slab = seg_slab;
+            e->tile_slab = tile_slab;
+        }
+    }
 
     e->has_plan = true;
     e->plan_n = n;
@@ -317,7 +392,7 @@ int tgx_destroy(tgx_engine* e) {
     if (!e) return TGX_OK;
     cudaSetDevice(e->device);
     DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
-                      &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles};
+                      &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         e->h_params[i].release();
@@ -351,6 +426,7 @@ int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt) {
     e->tile_shift = tile_shift;
     e->spt = spt;
     e->has_plan = false;   // tile size is baked into a plan
+    e->slabs_ready = false;
     return TGX_OK;
 }
 
@@ -358,13 +434,32 @@ int tgx_set_plan_mode(tgx_engine* e, int exact_ramps) {
     if (!e) return TGX_ERR_INVALID;
     e->exact_ramps = exact_ramps != 0;
     e->has_plan = false;
+    e->slabs_ready = false;   // segment counts differ between the modes (ramp chunks)
+    return TGX_OK;
+}
+
+// Single-replay planning with per-trajectory slices sized from the previous plan (default on).  allow = 0 forces the
+// two-replay exact-offset path for every plan.
+int tgx_set_slab_planning(tgx_engine* e, int allow) {
+    if (!e) return TGX_ERR_INVALID;
+    e->allow_slabs = allow != 0;
+    e->slabs_ready = false;
+    e->has_plan = false;
+    return TGX_OK;
+}
+
+// How many plans so far took the single-replay / the two-replay path.
+int tgx_plan_path_counts(const tgx_engine* e, int64_t* slab_plans, int64_t* exact_plans) {
+    if (!e) return TGX_ERR_INVALID;
+    if (slab_plans) *slab_plans = e->slab_plans;
+    if (exact_plans) *exact_plans = e->exact_plans;
     return TGX_OK;
 }
 
 int64_t tgx_scratch_bytes(const tgx_engine* e) {
     if (!e) return 0;
     const DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
-                            &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles};
+                            &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats};
     int64_t s = 0;
     for (const DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;
@@ -379,9 +474,13 @@ int tgx_count(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_li
     if (!e || n < 0 || (n > 0 && !d_params)) return TGX_ERR_INVALID;
     if (n == 0) return TGX_OK;
     TGX_CUDA(cudaSetDevice(e->device));
-    TGX_CUDA(tgx::launch_plan_count(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, false, d_counts,
-                                    d_status, nullptr, nullptr, static_cast<cudaStream_t>(stream)));
-    e->launches += 1;
+    int rc = e->cur_table.reserve(tgx::cur_table_bytes());
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TGX_CUDA(tgx::launch_build_cur_table(d_params, e->max_samples, e->cur_table.p, s));
+    TGX_CUDA(tgx::launch_plan_count(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, false,
+                                    e->cur_table.p, d_counts, d_status, nullptr, nullptr, s));
+    e->launches += 2;
     return TGX_OK;
 }
 

@@ -103,6 +103,7 @@ eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, cons
 
     // ---- stage the tile's constants in shared memory (16-byte chunks, one per thread) -------------------
     const int4 tw = __ldg(reinterpret_cast<const int4*>(tiles) + blockIdx.x);   // {traj, k_lo, seg_begin, nseg}
+    if (tw.w <= 0) return;   // an empty slot of a slab-mode plan (whole CTA, before any barrier)
     const int traj = tw.x, k_lo = tw.y, seg_begin = tw.z;
     const int nseg = tw.w < kMaxSegPerTile ? tw.w : kMaxSegPerTile;
     {

@@ -61,6 +61,8 @@ struct Emitter {
     int32_t seg_base;     // absolute index of segs[0]
     tgx_phases* ph;       // may be nullptr
     bool orbit;           // Circle / Figure8: Seg.s1 = theta increment per step, Seg.acc = exact theta of the last sample
+    int seg_cap;          // slab mode: capacity of this trajectory's slice (writes beyond it are dropped and the
+    int tile_cap;         //            plan is redone with exact offsets); otherwise INT_MAX
 
     int nseg = 0;
     int ntile = 0;
@@ -80,7 +82,7 @@ struct Emitter {
     }
     __device__ void flush_tile() {
         if (cur_tile < 0) return;
-        if (tiles) {
+        if (tiles && ntile < tile_cap) {
             Tile t;
             t.traj = traj;
             t.k_lo = cur_tile << tile_shift;
@@ -111,7 +113,7 @@ struct Emitter {
     }
     // `last_state`: orbit only, the exactly replayed theta at sample k_last.
     __device__ void close(int k_last, bool clamp_last, double last_state) {
-        if (segs) {
+        if (segs && nseg < seg_cap) {
             cur.n = k_last - cur.kb;
             cur.flags = clamp_last ? kSegClampLast : 0;
             if (orbit) cur.acc = last_state;
@@ -230,68 +232,157 @@ __device__ __forceinline__ bool ramp(double& v, double target, double adt, doubl
     return true;
 }
 
+// ---- the hold counter: current_t_traj_ += dt_ -----------------------------------------------------------------
+// `double cur = 0; while (cur < t_hold) { ...; cur += dt; }` (Circle.cpp:62-71): the number of iterations is the
+// smallest m with c_m >= t_hold where c_0 = 0, c_m = fl(c_{m-1} + dt).  That sequence depends on dt alone, and by
+// the binade argument above it is piecewise an exact arithmetic progression: (m0, c0, inc, cnt) says "after m0
+// steps cur == c0, and each of the next cnt steps adds exactly inc".  A batch almost always shares one dt
+// (1/pub_freq, TrajectoryGenerator.cpp:171-172), so the runs are tabulated once per plan by a one-thread kernel and
+// every trajectory looks its hold length up; a trajectory with a different dt walks the runs itself.
+constexpr int kCurTableMax = 192;
+
+struct CurTable {
+    double dt;
+    int32_t n;            // entries
+    int32_t stagnates;    // after the last entry cur stops changing (dt < ulp/2): longer holds never terminate
+    long long m_end;      // steps covered by the table
+    long long m0[kCurTableMax];
+    long long cnt[kCurTableMax];
+    double c0[kCurTableMax];
+    double inc[kCurTableMax];
+};
+
+// One run of the counter starting from (m, cur): returns false on stagnation.
+__device__ __forceinline__ bool cur_run(double cur, double dt, double& inc, long long& cnt) {
+    const double cn = dadd(cur, dt);
+    if (cn == cur) return false;
+    inc = dsub(cn, cur);
+    cnt = 1 + regular_run(cur, cn, dt);
+    return true;
+}
+
+// Smallest j in [1, cnt] with c0 + j*inc >= t, given that c0 < t and c0 + cnt*inc >= t (all partial sums exact).
+__device__ __forceinline__ long long steps_to_reach(double c0, double inc, long long cnt, double t) {
+    const double g = ceil(ddiv(dsub(t, c0), inc));
+    long long j = g < 1.0 ? 1 : (g > (double)cnt ? cnt : (long long)g);
+    while (j > 1 && fma((double)(j - 1), inc, c0) >= t) --j;
+    while (j < cnt && fma((double)j, inc, c0) < t) ++j;
+    return j;
+}
+
+__global__ void build_cur_table_kernel(const tgx_params* __restrict__ params, int64_t max_samples,
+                                       CurTable* __restrict__ tab) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const double dt = params[0].dt;
+    tab->dt = dt;
+    tab->stagnates = 0;
+    int n = 0;
+    long long m = 0;
+    double cur = 0.0;
+    if (isfinite(dt) && dt > 0.0) {
+        while (n < kCurTableMax && m < max_samples) {
+            double inc;
+            long long cnt;
+            if (!cur_run(cur, dt, inc, cnt)) {
+                tab->stagnates = 1;
+                break;
+            }
+            tab->m0[n] = m;
+            tab->c0[n] = cur;
+            tab->inc[n] = inc;
+            tab->cnt[n] = cnt;
+            ++n;
+            cur = fma((double)cnt, inc, cur);     // exact
+            m += cnt;
+        }
+    }
+    tab->n = n;
+    tab->m_end = m;
+}
+
+// Number of hold iterations for t_hold, or -1 if the reference would not terminate within `limit` more samples.
+__device__ long long hold_steps(double t_hold, double dt, long long limit, const CurTable* __restrict__ tab) {
+    if (!(0.0 < t_hold)) return 0;
+    if (tab && tab->dt == dt && tab->n > 0) {
+        // largest entry whose start value is below t_hold (c0 is increasing, c0[0] = 0 < t_hold)
+        int lo = 0, hi = tab->n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tab->c0[mid] < t_hold) lo = mid; else hi = mid - 1;
+        }
+        const double c0 = tab->c0[lo], inc = tab->inc[lo];
+        const long long cnt = tab->cnt[lo];
+        if (fma((double)cnt, inc, c0) >= t_hold) {
+            const long long m = tab->m0[lo] + steps_to_reach(c0, inc, cnt, t_hold);
+            return m <= limit ? m : -1;
+        }
+        // beyond the table: never terminates (stagnation), exceeds the guard, or the table was cut short
+        if (tab->stagnates || tab->m_end > limit) return -1;
+    }
+    long long m = 0;
+    double cur = 0.0;
+    while (cur < t_hold) {
+        double inc;
+        long long cnt;
+        if (m > limit || !cur_run(cur, dt, inc, cnt)) return -1;
+        if (fma((double)cnt, inc, cur) >= t_hold) cnt = steps_to_reach(cur, inc, cnt, t_hold);
+        cur = fma((double)cnt, inc, cur);
+        m += cnt;
+    }
+    return m <= limit ? m : -1;
+}
+
 // The constant-speed phase: `while (current_t_traj_ < t) { ...; current_t_traj_ += dt_; }`
 // (Circle.cpp:63-71, Line.cpp:57-62, Figure8.cpp:63-71).  a0 / a1 are the constants the reference adds to
 // s0 / s1 on every step of the phase (orbit: s0 = theta, a0 = (v/r)*dt; line: s0 = x, s1 = y, a = (v*c)*dt, (v*s)*dt).
 //
-// The loop is NOT replayed step by step: after each real step the three running sums (current_t_traj_, s0, s1) are
-// advanced in one exact jump over the steps for which regular_run() proves their increments constant, bounded
-// by the tile end, the sample guard and the step on which current_t_traj_ reaches t_hold.  A phase of n steps costs
-// O(number of binade crossings + number of tiles) iterations and still yields the reference's bit-exact state.
+// The phase is NOT replayed step by step: its length comes from hold_steps(), and the running sums s0 / s1 are
+// advanced in exact jumps over the steps for which regular_run() proves their increments constant, bounded by the
+// tile end.  A phase of n steps costs O(number of binade crossings + number of tiles) iterations and still yields
+// the reference's bit-exact state.
 //
 // EXACT (orbits): the segment is cut whenever theta's effective increment d changes (a binade crossing; the
 // crossing step itself becomes the segment's exactly stored last sample), so the evaluation kernel's
 // theta_b + j*d reproduces the reference's running sum bit for bit.
 template <bool TRACK0, bool TRACK1, bool EXACT>
 __device__ __forceinline__ bool hold(double v, double t_hold, double dt, int& k, int64_t max_samples, int tmask,
-                                     Emitter& E, double& s0, double& s1, double a0, double a1) {
+                                     Emitter& E, double& s0, double& s1, double a0, double a1,
+                                     const CurTable* __restrict__ tab) {
+    long long rem = hold_steps(t_hold, dt, (long long)max_samples - 1 - (long long)k, tab);
+    if (rem < 0) return false;
     bool open = false;
-    double cur = 0.0;
     double seg_d = 0.0;
-    while (cur < t_hold) {
-        if ((int64_t)k + 1 >= max_samples) return false;
+    while (rem > 0) {
         // ---- one real step ----------------------------------------------------------------------------
         const double s0n = TRACK0 ? dadd(s0, a0) : s0;
         const double s1n = TRACK1 ? dadd(s1, a1) : s1;
-        const double cn = dadd(cur, dt);
-        if (cn == cur) return false;
         const double d0 = TRACK0 ? dsub(s0n, s0) : 0.0;      // exact effective increments
         const double d1 = TRACK1 ? dsub(s1n, s1) : 0.0;
-        const double dc = dsub(cn, cur);
         if (!open) {
             E.open(k, v, 0.0, v, s0, EXACT ? d0 : s1, 0.0);
             seg_d = d0;
             open = true;
         }
-        long long J = regular_run(cur, cn, dt);
+        long long J = rem - 1;
         if (TRACK0) J = min(J, regular_run(s0, s0n, a0));
         if (TRACK1) J = min(J, regular_run(s1, s1n, a1));
         s0 = s0n;
         s1 = s1n;
-        cur = cn;
         ++k;
+        --rem;
         if (((k + 1) & tmask) == 0 || (EXACT && d0 != seg_d && E.can_break())) {
             E.close(k, false, s0);
             open = false;
             continue;
         }
-        // ---- exact jump over the regular run ----------------------------------------------------------
-        J = min(J, (long long)((k | tmask) - k));            // stay inside the tile
-        J = min(J, max_samples - 1 - (long long)k);          // the guard fires on the next real step
-        if (J > 0 && cur < t_hold) {
-            if (fma((double)J, dc, cur) >= t_hold) {
-                // the phase ends inside the run: take exactly the m steps after which current_t_traj_ >= t_hold
-                double g = ceil(ddiv(dsub(t_hold, cur), dc));
-                long long m = g < 1.0 ? 1 : (g > (double)J ? J : (long long)g);
-                while (m > 1 && fma((double)(m - 1), dc, cur) >= t_hold) --m;
-                while (m < J && fma((double)m, dc, cur) < t_hold) ++m;
-                J = m;
-            }
+        // ---- exact jump over the regular run, inside the tile ------------------------------------------
+        J = min(J, (long long)((k | tmask) - k));
+        if (J > 0) {
             const double fJ = (double)J;
             if (TRACK0) s0 = fma(fJ, d0, s0);                // exact: every partial sum is representable
             if (TRACK1) s1 = fma(fJ, d1, s1);
-            cur = fma(fJ, dc, cur);
             k += (int)J;
+            rem -= J;
             if (((k + 1) & tmask) == 0) {
                 E.close(k, false, s0);
                 open = false;
@@ -337,7 +428,8 @@ __device__ __forceinline__ double div_inv(double a, const InvDiv& d) {
 // Circle::generateTraj (Circle.cpp:30-94) == Figure8::generateTraj (Figure8.cpp:30-94).
 // STATE = false skips the theta recurrence (counts and status do not depend on it); XR selects exact ramps.
 template <bool STATE, bool XR>
-__device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E, uint32_t& st) {
+__device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E, uint32_t& st,
+                            const CurTable* __restrict__ tab) {
     const tgx_orbit_params& o = p.u.orbit;
     const double r = o.r, dt = p.dt;
     const double adt = dmul(o.accel, dt);
@@ -360,7 +452,7 @@ __device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E
         if (fabs(dsub(v, vg)) > 0.001) st |= TGX_ST_VGOALS_NOT_INCREASING;                // :57-59
         E.phase(k, TGX_PH_REACHED, vg, o.t_traj);            // :61-62
         const double w = STATE ? dmul(div_inv(v, rdiv), dt) : 0.0;    // omega*dt_, the same on every step (:65-67)
-        if (!hold<STATE, false, STATE>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0)) {   // :63-71
+        if (!hold<STATE, false, STATE>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0, tab)) {   // :63-71
             st |= TGX_ST_TOO_LONG;
             return -1;
         }
@@ -391,7 +483,7 @@ __device__ double line_d2(const tgx_line_params& l) {
 // Line::Line (theta_, Line.cpp:24) + Line::generateTraj (Line.cpp:31-89).
 template <bool XR>
 __device__ int replay_line(const tgx_params& p, int64_t max_samples, Emitter& E, uint32_t& st, double& theta,
-                           double& c, double& s) {
+                           double& c, double& s, const CurTable* __restrict__ tab) {
     const tgx_line_params& l = p.u.line;
     const double dt = p.dt;
     const int tmask = (1 << E.tile_shift) - 1;
@@ -418,7 +510,7 @@ __device__ int replay_line(const tgx_params& p, int64_t max_samples, Emitter& E,
     const double t2 = ddiv(line_d2(l), vg);                      // :53 (a negative d2 simply skips the cruise loop)
     E.phase(k, TGX_PH_REACHED, vg, t2);                          // :55-56
     if (!hold<true, true, false>(v, t2, dt, k, max_samples, tmask, E, x, y, dmul(dmul(v, cc), dt),
-                                 dmul(dmul(v, ss), dt))) {                                   // :57-62
+                                 dmul(dmul(v, ss), dt), tab)) {                              // :57-62
         st |= TGX_ST_TOO_LONG;
         return -1;
     }
@@ -464,15 +556,15 @@ struct PlanOut {
 // segment count is not meaningful: exact-progression breaks depend on theta).
 template <bool FILL, bool STATE, bool XR>
 __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_limits* lim, Emitter& E,
-                            TrajRec* rec) {
+                            TrajRec* rec, const CurTable* __restrict__ tab) {
     PlanOut r{0, 0u, 0, 0};
     if (!params_ok(p)) {
         r.status = TGX_ST_BAD_PARAM;
     } else {
         int n;
         double theta = 0.0, c = 1.0, s = 0.0;
-        if (p.type == TGX_LINE) n = replay_line<XR>(p, max_samples, E, r.status, theta, c, s);
-        else n = replay_orbit<STATE, XR>(p, max_samples, E, r.status);
+        if (p.type == TGX_LINE) n = replay_line<XR>(p, max_samples, E, r.status, theta, c, s, tab);
+        else n = replay_orbit<STATE, XR>(p, max_samples, E, r.status, tab);
         E.finish();
         if (lim && lim->check_box && !inside_bounds(p, lim->box)) {
             r.status |= TGX_ST_OUTSIDE_BOUNDS;
@@ -607,18 +699,37 @@ __device__ __forceinline__ tgx_params load_params(const tgx_params* params, int6
 
 // ---- kernels ------------------------------------------------------------------------------------------
 
+// Per-plan statistics the fill pass accumulates (one atomic per warp).
+__device__ __forceinline__ void accumulate_stats(PlanStats* stats, int n, int nseg, int ntile, bool overflow) {
+    if (!stats) return;
+    const unsigned mask = __activemask();
+    const unsigned tot = __reduce_add_sync(mask, (unsigned)n);
+    const int mseg = __reduce_max_sync(mask, nseg);
+    const int mtile = __reduce_max_sync(mask, ntile);
+    const unsigned tiles = __reduce_add_sync(mask, (unsigned)ntile);
+    const unsigned ovf = __reduce_or_sync(mask, overflow ? 1u : 0u);
+    if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) {
+        atomicAdd(&stats->total_samples, (unsigned long long)tot);
+        atomicAdd(&stats->total_tiles, (unsigned long long)tiles);
+        atomicMax(&stats->max_nseg, mseg);
+        atomicMax(&stats->max_ntile, mtile);
+        if (ovf) atomicOr(&stats->overflow, 1);
+    }
+}
+
 // Counting pass: N_i, status_i and, with SEGS, the number of segments / tiles the fill pass will emit (which
 // requires the full state replay, because exact-progression breaks depend on theta).
 template <bool SEGS, bool XR>
 __global__ void __launch_bounds__(128)
 plan_count_kernel(const tgx_params* __restrict__ params, const double* __restrict__ stop_from, int64_t n,
                   tgx_limits lim, int has_lim, int64_t max_samples, int tile_shift,
+                  const CurTable* __restrict__ tab,
                   int32_t* __restrict__ counts, uint32_t* __restrict__ status, int32_t* __restrict__ nseg,
                   int32_t* __restrict__ ntile) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const tgx_params p = load_params(params, i);
-    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, nullptr, p.type != TGX_LINE};
+    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, nullptr, p.type != TGX_LINE, 0x7fffffff, 0x7fffffff};
     PlanOut r;
     if (stop_from) {
         double from[TGX_NCHAN];
@@ -626,7 +737,7 @@ plan_count_kernel(const tgx_params* __restrict__ params, const double* __restric
         for (int c = 0; c < TGX_NCHAN; ++c) from[c] = stop_from[i * TGX_NCHAN + c];
         r = stop_one<false>(p, from, max_samples, E, nullptr);
     } else {
-        r = plan_one<false, SEGS, XR>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr);
+        r = plan_one<false, SEGS, XR>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
     }
     if (counts) counts[i] = r.n;
     if (status) status[i] = r.status;
@@ -634,22 +745,33 @@ plan_count_kernel(const tgx_params* __restrict__ params, const double* __restric
     if (ntile) ntile[i] = r.ntile;
 }
 
-// Fill pass: same replay, now writing the tables at the offsets the scans produced.
+// Fill pass: the replay that writes the tables.
+//   exact-offset mode (seg_slab == 0): trajectory i owns Seg[seg_off[i] ..] and Tile[tile_off[i] ..], sized by the
+//       counting pass and the scans (two replays per plan);
+//   slab mode (seg_slab > 0): trajectory i owns the fixed slices Seg[i*seg_slab ..], Tile[i*tile_slab ..] — no
+//       counting pass, no scans.  A trajectory that needs more than its slice sets stats->overflow (its extra
+//       records are dropped) and the host redoes the plan in exact-offset mode.  Unused tile slots are written as
+//       empty tiles (nseg = 0), which the evaluation kernel skips.
 template <bool XR>
 __global__ void __launch_bounds__(128)
 plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict__ stop_from, int64_t n,
                  tgx_limits lim, int has_lim, int64_t max_samples, int tile_shift,
-                 const int32_t* __restrict__ plan_counts,
-                 const int64_t* __restrict__ seg_off, const int64_t* __restrict__ tile_off,
-                 TrajRec* __restrict__ recs, Seg* __restrict__ segs, Tile* __restrict__ tiles,
-                 int32_t* __restrict__ counts, uint32_t* __restrict__ status, tgx_phases* __restrict__ phases) {
+                 const CurTable* __restrict__ tab, const int32_t* __restrict__ plan_counts,
+                 const int64_t* __restrict__ seg_off, const int64_t* __restrict__ tile_off, int seg_slab,
+                 int tile_slab, TrajRec* __restrict__ recs, Seg* __restrict__ segs, Tile* __restrict__ tiles,
+                 int32_t* __restrict__ counts, uint32_t* __restrict__ status, int32_t* __restrict__ counts2,
+                 uint32_t* __restrict__ status2, tgx_phases* __restrict__ phases, PlanStats* __restrict__ stats) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const tgx_params p = load_params(params, i);
-    // A trajectory the counting pass rejected owns no slice of Seg[] / Tile[]: replay it without writing tables.
-    const bool keep = plan_counts[i] > 0;
-    Emitter E{tile_shift, (int32_t)i, keep ? segs + seg_off[i] : nullptr, keep ? tiles + tile_off[i] : nullptr,
-              (int32_t)seg_off[i], phases ? phases + i : nullptr, p.type != TGX_LINE};
+    const bool slab = seg_slab > 0;
+    // exact-offset mode: a trajectory the counting pass rejected owns no slice: replay it without writing tables
+    const bool keep = slab || plan_counts[i] > 0;
+    const int64_t so = slab ? i * (int64_t)seg_slab : seg_off[i];
+    const int64_t to = slab ? i * (int64_t)tile_slab : tile_off[i];
+    Emitter E{tile_shift, (int32_t)i, keep ? segs + so : nullptr, keep ? tiles + to : nullptr, (int32_t)so,
+              phases ? phases + i : nullptr, p.type != TGX_LINE, slab ? seg_slab : 0x7fffffff,
+              slab ? tile_slab : 0x7fffffff};
     PlanOut r;
     if (stop_from) {
         double from[TGX_NCHAN];
@@ -658,10 +780,24 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
         r = stop_one<true>(p, from, max_samples, E, recs + i);
         if (phases && r.status) phases[i].n = 0;
     } else {
-        r = plan_one<true, true, XR>(p, max_samples, has_lim ? &lim : nullptr, E, recs + i);
+        r = plan_one<true, true, XR>(p, max_samples, has_lim ? &lim : nullptr, E, recs + i, tab);
+    }
+    bool overflow = false;
+    if (slab) {
+        overflow = r.nseg > seg_slab || r.ntile > tile_slab;
+        // E counted what the replay emitted even if the trajectory was rejected afterwards (r.ntile == 0 then)
+        const int used = (r.n > 0 && !overflow) ? r.ntile : 0;
+        for (int t = used; t < tile_slab; ++t) {
+            Tile e;
+            e.traj = (int32_t)i; e.k_lo = 0; e.seg_begin = (int32_t)so; e.nseg = 0;
+            tiles[to + t] = e;
+        }
     }
     if (counts) counts[i] = r.n;
     if (status) status[i] = r.status;
+    if (counts2) counts2[i] = r.n;
+    if (status2) status2[i] = r.status;
+    accumulate_stats(stats, r.n, r.nseg, r.ntile, overflow);
 }
 
 // "Per-time evaluation": a one-sample plan per trajectory from an explicit state, i.e. the public helpers
@@ -738,18 +874,27 @@ selftest_division_kernel(int64_t n, uint64_t seed, int per_thread, unsigned long
 
 // ---- host-side launchers (called from engine.cu) -------------------------------------------------------
 
+cudaError_t launch_build_cur_table(const tgx_params* params, int64_t max_samples, void* table, cudaStream_t stream) {
+    build_cur_table_kernel<<<1, 32, 0, stream>>>(params, max_samples, static_cast<CurTable*>(table));
+    return cudaGetLastError();
+}
+
+size_t cur_table_bytes() { return sizeof(CurTable); }
+
 cudaError_t launch_plan_count(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
-                              int64_t max_samples, int tile_shift, bool exact_ramps, int32_t* counts,
-                              uint32_t* status, int32_t* nseg, int32_t* ntile, cudaStream_t stream) {
+                              int64_t max_samples, int tile_shift, bool exact_ramps, const void* cur_table,
+                              int32_t* counts, uint32_t* status, int32_t* nseg, int32_t* ntile,
+                              cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     tgx_limits l{};
     if (lim) l = *lim;
     const int threads = 128;
     const int64_t blocks = (n + threads - 1) / threads;
+    const CurTable* tab = static_cast<const CurTable*>(cur_table);
 #define TGX_LAUNCH_COUNT(SEGS, XR)                                                                          \
     plan_count_kernel<SEGS, XR><<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0, \
-                                                                         max_samples, tile_shift, counts, status, \
-                                                                         nseg, ntile)
+                                                                         max_samples, tile_shift, tab, counts,  \
+                                                                         status, nseg, ntile)
     if (nseg || ntile) {
         if (exact_ramps) TGX_LAUNCH_COUNT(true, true);
         else TGX_LAUNCH_COUNT(true, false);
@@ -761,24 +906,24 @@ cudaError_t launch_plan_count(const tgx_params* params, const double* stop_from,
 }
 
 cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, int64_t n, const tgx_limits* lim,
-                             int64_t max_samples, int tile_shift, bool exact_ramps, const int32_t* plan_counts,
-                             const int64_t* seg_off, const int64_t* tile_off, TrajRec* recs, Seg* segs, Tile* tiles,
-                             int32_t* counts, uint32_t* status, tgx_phases* phases, cudaStream_t stream) {
+                             int64_t max_samples, int tile_shift, bool exact_ramps, const void* cur_table,
+                             const int32_t* plan_counts, const int64_t* seg_off, const int64_t* tile_off,
+                             int seg_slab, int tile_slab, TrajRec* recs, Seg* segs, Tile* tiles, int32_t* counts,
+                             uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
+                             PlanStats* stats, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     tgx_limits l{};
     if (lim) l = *lim;
     const int threads = 128;
     const int64_t blocks = (n + threads - 1) / threads;
-    if (exact_ramps)
-        plan_fill_kernel<true><<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0,
-                                                                        max_samples, tile_shift, plan_counts, seg_off,
-                                                                        tile_off, recs, segs, tiles, counts, status,
-                                                                        phases);
-    else
-        plan_fill_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(params, stop_from, n, l, lim ? 1 : 0,
-                                                                         max_samples, tile_shift, plan_counts, seg_off,
-                                                                         tile_off, recs, segs, tiles, counts, status,
-                                                                         phases);
+    const CurTable* tab = static_cast<const CurTable*>(cur_table);
+#define TGX_LAUNCH_FILL(XR)                                                                                       \
+    plan_fill_kernel<XR><<<(unsigned)blocks, threads, 0, stream>>>(                                               \
+        params, stop_from, n, l, lim ? 1 : 0, max_samples, tile_shift, tab, plan_counts, seg_off, tile_off,       \
+        seg_slab, tile_slab, recs, segs, tiles, counts, status, counts2, status2, phases, stats)
+    if (exact_ramps) TGX_LAUNCH_FILL(true);
+    else TGX_LAUNCH_FILL(false);
+#undef TGX_LAUNCH_FILL
     return cudaGetLastError();
 }
 

@@ -73,6 +73,16 @@ constexpr int kRampChunk = 256;
 constexpr int kMaxSegPerTile = 64;
 constexpr int kMaxOptionalSegPerTile = 36;
 
+// Statistics of one plan, accumulated by the fill pass and read back by the host (one small D2H per plan).
+struct PlanStats {
+    unsigned long long total_samples;   // sum of N_i
+    unsigned long long total_tiles;     // sum of ceil(N_i / tile)
+    int max_nseg;                       // largest segment count of a trajectory
+    int max_ntile;                      // largest tile count of a trajectory
+    int overflow;                       // slab mode: some trajectory did not fit its slice
+    int pad;
+};
+
 // Device-side view of tgx_layout.
 struct OutView {
     double* base;

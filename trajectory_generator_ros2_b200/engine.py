@@ -42,6 +42,8 @@ def _load() -> C.CDLL:
     lib.tgx_set_max_samples.argtypes = [vp, i64]
     lib.tgx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     lib.tgx_set_plan_mode.argtypes = [vp, C.c_int]
+    lib.tgx_set_slab_planning.argtypes = [vp, C.c_int]
+    lib.tgx_plan_path_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.tgx_scratch_bytes.restype = i64
     lib.tgx_scratch_bytes.argtypes = [vp]
     lib.tgx_launch_count.restype = i64
@@ -178,6 +180,15 @@ class Engine:
 
     def set_plan_mode(self, exact_ramps: bool):
         self._check(self._lib.tgx_set_plan_mode(self._h, 1 if exact_ramps else 0), "tgx_set_plan_mode")
+
+    def set_slab_planning(self, allow: bool):
+        self._check(self._lib.tgx_set_slab_planning(self._h, 1 if allow else 0), "tgx_set_slab_planning")
+
+    def plan_path_counts(self):
+        """(single-replay plans, two-replay plans) so far."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.tgx_plan_path_counts(self._h, C.byref(a), C.byref(b)), "tgx_plan_path_counts")
+        return int(a.value), int(b.value)
 
     @property
     def launch_count(self) -> int:
