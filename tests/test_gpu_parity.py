@@ -259,8 +259,9 @@ def test_layouts_and_tunings_agree(engine, oracle):
     params = abi.concat([workloads.mixed_cfg3(300), workloads.default_circle()])
     base, counts, status, _ = gpu_generate(engine, params, want_phases=False)
     try:
-        for shift, spt in ((9, 2), (9, 4), (10, 2), (11, 2), (11, 4)):
+        for shift, spt, variant in ((9, 2, 0), (9, 4, 1), (9, 2, 2), (10, 4, 1), (10, 4, 2), (9, 4, 0)):
             engine.set_tuning(shift, spt)
+            engine.set_eval_variant(variant)
             for plane_major in (False, True):
                 out, c2, s2, _ = gpu_generate(engine, params, want_phases=False, plane_major=plane_major)
                 np.testing.assert_array_equal(c2, counts)
@@ -270,6 +271,7 @@ def test_layouts_and_tunings_agree(engine, oracle):
                 np.testing.assert_allclose(out[m], base[m], rtol=0, atol=5e-12)
     finally:
         engine.set_tuning(10, 4)
+        engine.set_eval_variant(0)
     ref, _, _ = oracle.generate(params[-1:])
     assert_samples_close(base[-1, :, :25001], ref, "default circle in mixed batch")
 

@@ -64,15 +64,14 @@ def main():
     print(f"tgx_plan (exact ramps)      : {ms:8.3f} ms   paths {eng.plan_path_counts()}")
     eng.set_plan_mode(False)
     # ---- eval shapes --------------------------------------------------------------------------------------------
-    for shift, spt in ((9, 2), (9, 4), (10, 2), (10, 4), (11, 2), (11, 4)):
+    for shift, spt in ((9, 2), (9, 4), (10, 4)):
         eng.set_tuning(shift, spt)
         eng.plan(d_params, want_outputs=False)
-        for plane_major in (False, True):
-            view = out.view(14, n, row) if plane_major else out
-            ms = timed(lambda: eng.eval(view, plane_major=plane_major))
-            print(f"eval tile={1 << shift:5d} spt={spt} threads={(1 << shift) // spt:4d} "
-                  f"{'plane-major' if plane_major else 'traj-major '}: {ms:8.3f} ms  {112 * total / ms / 1e6:8.1f} GB/s  "
-                  f"{total / ms / 1e6:7.2f} Gsamples/s")
+        for variant in (0, 1, 2):
+            eng.set_eval_variant(variant)
+            ms = timed(lambda: eng.eval(out))
+            print(f"eval tile={1 << shift:5d} spt={spt} threads={(1 << shift) // spt:4d} variant={variant}: {ms:8.3f} ms  "
+                  f"{112 * total / ms / 1e6:8.1f} GB/s  {total / ms / 1e6:7.2f} Gsamples/s")
     eng.close()
 
 

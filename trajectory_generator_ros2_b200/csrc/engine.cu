@@ -35,7 +35,7 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
                              PlanStats* stats, cudaStream_t stream);
 cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles, int tile_shift,
-                        int spt, const OutView& out, bool store, double* max_v, double* max_a,
+                        int spt, int variant, const OutView& out, bool store, double* max_v, double* max_a,
                         cudaStream_t stream);
 cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, const double* max_v,
                                         const double* max_a, double v_max, double a_max, uint8_t* flags,
@@ -147,6 +147,7 @@ struct tgx_engine {
     int64_t max_samples = (int64_t)1 << 24;
     int tile_shift = 10;   // 1024 samples per tile
     bool exact_ramps = false;   // plan mode: replay ramps step by step (bit-identical state) or in exact-v jumps
+    int variant = 0;       // staging variant of the evaluation kernel (see eval.cu: launch_eval)
     int spt = 4;           // samples per thread: 2 -> 128-bit stores, 4 -> 256-bit stores (measured best on B200)
     int64_t launches = 0;
 
@@ -420,9 +421,9 @@ int tgx_set_max_samples(tgx_engine* e, int64_t max_samples) {
 int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt) {
     if (!e) return TGX_ERR_INVALID;
     if (spt != 2 && spt != 4) return TGX_ERR_INVALID;
-    if (tile_shift < 9 || tile_shift > 11) return TGX_ERR_INVALID;
+    if (tile_shift < 9 || tile_shift > 10) return TGX_ERR_INVALID;
     const int threads = (1 << tile_shift) / spt;
-    if (threads < 128 || threads > 1024) return TGX_ERR_INVALID;
+    if (threads != 128 && threads != 256) return TGX_ERR_INVALID;
     e->tile_shift = tile_shift;
     e->spt = spt;
     e->has_plan = false;   // tile size is baked into a plan
@@ -453,6 +454,14 @@ int tgx_plan_path_counts(const tgx_engine* e, int64_t* slab_plans, int64_t* exac
     if (!e) return TGX_ERR_INVALID;
     if (slab_plans) *slab_plans = e->slab_plans;
     if (exact_plans) *exact_plans = e->exact_plans;
+    return TGX_OK;
+}
+
+// Staging variant of the evaluation kernel: 0 one copy of the tile's constants per CTA behind __syncthreads,
+// 1 one copy per warp behind __syncwarp, 2 as 1 with a register cap that admits one more CTA per SM.
+int tgx_set_eval_variant(tgx_engine* e, int variant) {
+    if (!e || variant < 0 || variant > 2) return TGX_ERR_INVALID;
+    e->variant = variant;
     return TGX_OK;
 }
 
@@ -534,7 +543,8 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
     if (d_max_a) TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)e->plan_n * sizeof(double), s));
     if (e->plan_tiles == 0) return TGX_OK;
     TGX_CUDA(tgx::launch_eval(e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(), e->tiles.as<tgx::Tile>(),
-                              e->plan_tiles, e->tile_shift, e->spt, make_view(out), true, d_max_v, d_max_a, s));
+                              e->plan_tiles, e->tile_shift, e->spt, e->variant, make_view(out), true, d_max_v, d_max_a,
+                              s));
     e->launches += 1;
     return TGX_OK;
 }
@@ -561,7 +571,7 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
     if (e->plan_tiles > 0) {
         tgx::OutView none{};
         TGX_CUDA(tgx::launch_eval(e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(), e->tiles.as<tgx::Tile>(),
-                                  e->plan_tiles, e->tile_shift, e->spt, none, false, d_max_v, d_max_a, s));
+                                  e->plan_tiles, e->tile_shift, e->spt, e->variant, none, false, d_max_v, d_max_a, s));
         e->launches += 1;
     }
     TGX_CUDA(tgx::launch_feasibility_finalize(n, e->status.as<uint32_t>(), d_max_v, d_max_a, limits->v_max,

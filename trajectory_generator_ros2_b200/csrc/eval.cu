@@ -25,30 +25,46 @@ namespace {
 
 constexpr double kPiOver2 = 1.57079632679489661923;
 
-template <int SPT>
+// POLICY: 0 = .cs (streaming, evict-first), 1 = default write-back, 2 = L1::no_allocate + L2::evict_first
+template <int SPT, int POLICY>
 struct VecStore;
 
-template <>
-struct VecStore<2> {
+template <int POLICY>
+struct VecStore<2, POLICY> {
     static __device__ __forceinline__ void st(double* p, const double (&x)[2]) {
-        asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x[0]), "d"(x[1]) : "memory");
+        if (POLICY == 0)
+            asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x[0]), "d"(x[1]) : "memory");
+        else if (POLICY == 1)
+            asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x[0]), "d"(x[1]) : "memory");
+        else
+            asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x[0]), "d"(x[1]) : "memory");
     }
 };
 
-template <>
-struct VecStore<4> {
+template <int POLICY>
+struct VecStore<4, POLICY> {
     static __device__ __forceinline__ void st(double* p, const double (&x)[4]) {
-        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
-                     "d"(x[3])
-                     : "memory");
+        if (POLICY == 0)
+            asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
+                         "d"(x[3]) : "memory");
+        else if (POLICY == 1)
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
+                         "d"(x[3]) : "memory");
+        else
+            asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p),
+                         "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
     }
 };
+
+#ifndef TGX_STORE_POLICY
+#define TGX_STORE_POLICY 0
+#endif
 
 // Store SPT adjacent samples of one channel; nvalid < SPT only on a trajectory's last, partial vector.
 template <int SPT>
 __device__ __forceinline__ void store_channel(double* p, const double (&x)[SPT], int nvalid) {
     if (nvalid >= SPT) {
-        VecStore<SPT>::st(p, x);
+        VecStore<SPT, TGX_STORE_POLICY>::st(p, x);
     } else {
 #pragma unroll
         for (int u = 0; u < SPT; ++u)
@@ -92,14 +108,22 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double x) {
 
 }  // namespace
 
-template <int THREADS, int SPT, bool STORE, bool REDUCE>
-__global__ void __launch_bounds__(THREADS)
+// WARP_STAGE: every warp stages the tile's constants in its own shared-memory slice and synchronises only with
+// __syncwarp(), so no warp ever waits at a CTA barrier for the slowest one (the constants are L2-resident after the
+// first warp's miss); otherwise one copy per CTA behind __syncthreads().  MINB: minimum CTAs per SM (register cap).
+template <int THREADS, int SPT, bool STORE, bool REDUCE, bool WARP_STAGE, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, const Tile* __restrict__ tiles,
             OutView out, double* __restrict__ max_v, double* __restrict__ max_a) {
-    __shared__ __align__(16) TrajRec s_rec;
-    __shared__ __align__(16) Seg s_seg[kMaxSegPerTile];
-    __shared__ int s_kend[kMaxSegPerTile];          // last sample of each segment
+    constexpr int kSlices = WARP_STAGE ? THREADS / 32 : 1;
+    __shared__ __align__(16) TrajRec s_rec_all[kSlices];
+    __shared__ __align__(16) Seg s_seg_all[kSlices][kMaxSegPerTile];
+    __shared__ int s_kend_all[kSlices][kMaxSegPerTile];          // last sample of each segment
     __shared__ double s_red[2][THREADS / 32];
+    const int slice = WARP_STAGE ? (int)(threadIdx.x >> 5) : 0;
+    TrajRec& s_rec = s_rec_all[slice];
+    Seg* const s_seg = s_seg_all[slice];
+    int* const s_kend = s_kend_all[slice];
 
     // ---- stage the tile's constants in shared memory (16-byte chunks, one per thread) -------------------
     const int4 tw = __ldg(reinterpret_cast<const int4*>(tiles) + blockIdx.x);   // {traj, k_lo, seg_begin, nseg}
@@ -108,7 +132,8 @@ eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, cons
     const int nseg = tw.w < kMaxSegPerTile ? tw.w : kMaxSegPerTile;
     {
         const int4* src = reinterpret_cast<const int4*>(segs + seg_begin);
-        for (int t = threadIdx.x; t < 4 + 4 * nseg; t += THREADS) {
+        for (int t = WARP_STAGE ? (int)(threadIdx.x & 31) : (int)threadIdx.x; t < 4 + 4 * nseg;
+             t += WARP_STAGE ? 32 : THREADS) {
             if (t < 4) {
                 reinterpret_cast<int4*>(&s_rec)[t] = __ldg(reinterpret_cast<const int4*>(recs + traj) + t);
             } else {
@@ -118,7 +143,8 @@ eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, cons
             }
         }
     }
-    __syncthreads();
+    if (WARP_STAGE) __syncwarp();
+    else __syncthreads();
 
     const int type = s_rec.type & kRecTypeMask;
     const int n = s_rec.n;
@@ -224,7 +250,11 @@ eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, cons
                 // theta_b + sum_{m<=j} (v_m / r) * dt  =  theta_b + j*w1 + j(j+1)/2 * (dv*dt/r); a hold (dv = 0) is the
                 // reference's exact arithmetic progression; a segment's last sample carries the replayed theta.
                 th[u] = q.last ? sg.acc : fma(q.tri, sg.dv * dtr, fma(q.fj, sg.s1, sg.s0));
+#ifdef TGX_EXPERIMENT_NOTRIG
+                sn[u] = th[u] * 0.5; cn[u] = th[u] * 0.25;   // bandwidth experiment only: no trigonometry
+#else
                 sincos(th[u], &sn[u], &cn[u]);
+#endif
                 om[u] = v[u] * rinv;                 // omega = v / r
             }
             if (type == TGX_CIRCLE) {
@@ -323,23 +353,31 @@ eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, cons
     }
 
     if (REDUCE) {
-        // ---- per-trajectory max |v|, max |a|: warp shuffles -> shared -> one atomicMax per tile ------------
+        // ---- per-trajectory max |v|, max |a|: warp shuffles, then one atomicMax per warp (WARP_STAGE) or one
+        //      shared-memory hop and one atomicMax per tile ----------------------------------------------------
         best_v2 = warp_max(best_v2);
         best_a2 = warp_max(best_a2);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) {
-            s_red[0][warp] = best_v2;
-            s_red[1][warp] = best_a2;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double a = lane < THREADS / 32 ? s_red[0][lane] : 0.0;
-            double b = lane < THREADS / 32 ? s_red[1][lane] : 0.0;
-            a = warp_max(a);
-            b = warp_max(b);
+        if (WARP_STAGE) {
+            if (lane == 0 && nvalid > 0) {
+                if (max_v) atomic_max_nonneg(max_v + traj, sqrt(best_v2));
+                if (max_a) atomic_max_nonneg(max_a + traj, sqrt(best_a2));
+            }
+        } else {
             if (lane == 0) {
-                if (max_v) atomic_max_nonneg(max_v + traj, sqrt(a));
-                if (max_a) atomic_max_nonneg(max_a + traj, sqrt(b));
+                s_red[0][warp] = best_v2;
+                s_red[1][warp] = best_a2;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double a = lane < THREADS / 32 ? s_red[0][lane] : 0.0;
+                double b = lane < THREADS / 32 ? s_red[1][lane] : 0.0;
+                a = warp_max(a);
+                b = warp_max(b);
+                if (lane == 0) {
+                    if (max_v) atomic_max_nonneg(max_v + traj, sqrt(a));
+                    if (max_a) atomic_max_nonneg(max_a + traj, sqrt(b));
+                }
             }
         }
     }
@@ -362,36 +400,41 @@ feasibility_finalize_kernel(int64_t n, const uint32_t* __restrict__ plan_status,
 
 // ---- host-side launchers -----------------------------------------------------------------------------------
 
-template <int THREADS, int SPT>
+template <int THREADS, int SPT, bool WARP_STAGE, int MINB>
 static cudaError_t launch_eval_t(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles,
                                  const OutView& out, bool store, double* max_v, double* max_a,
                                  cudaStream_t stream) {
     const bool reduce = max_v || max_a;
     const unsigned grid = (unsigned)ntiles;
     if (store && reduce)
-        eval_kernel<THREADS, SPT, true, true><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, true, true, WARP_STAGE, MINB><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
     else if (store)
-        eval_kernel<THREADS, SPT, true, false><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, true, false, WARP_STAGE, MINB><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
     else
-        eval_kernel<THREADS, SPT, false, true><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, false, true, WARP_STAGE, MINB><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
     return cudaGetLastError();
 }
 
-// tile_shift in {9, 10, 11}; spt in {2, 4}: threads per CTA = (1 << tile_shift) / spt.
+// tile = 1 << tile_shift samples per CTA, spt samples per thread: threads per CTA = tile / spt in {128, 256}.
+// variant 0: CTA-wide staging; 1: per-warp staging; 2: per-warp staging with a register cap for one more CTA per SM.
 cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles, int tile_shift,
-                        int spt, const OutView& out, bool store, double* max_v, double* max_a,
+                        int spt, int variant, const OutView& out, bool store, double* max_v, double* max_a,
                         cudaStream_t stream) {
     if (ntiles <= 0) return cudaSuccess;
     if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int threads = (1 << tile_shift) / spt;
-#define TGX_CASE(T, S) \
-    if (threads == (T) && spt == (S)) return launch_eval_t<T, S>(recs, segs, tiles, ntiles, out, store, max_v, max_a, stream)
-    TGX_CASE(128, 4);
-    TGX_CASE(256, 2);
-    TGX_CASE(256, 4);
-    TGX_CASE(512, 2);
-    TGX_CASE(512, 4);
-    TGX_CASE(1024, 2);
+#define TGX_CASE(T, S, V, W, M) \
+    if (threads == (T) && spt == (S) && variant == (V)) \
+        return launch_eval_t<T, S, W, M>(recs, segs, tiles, ntiles, out, store, max_v, max_a, stream)
+    TGX_CASE(128, 4, 0, false, 6);
+    TGX_CASE(128, 4, 1, true, 6);
+    TGX_CASE(128, 4, 2, true, 8);
+    TGX_CASE(256, 2, 0, false, 3);
+    TGX_CASE(256, 2, 1, true, 3);
+    TGX_CASE(256, 2, 2, true, 4);
+    TGX_CASE(256, 4, 0, false, 3);
+    TGX_CASE(256, 4, 1, true, 3);
+    TGX_CASE(256, 4, 2, true, 4);
 #undef TGX_CASE
     return cudaErrorInvalidConfiguration;
 }
