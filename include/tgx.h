@@ -184,9 +184,6 @@ int tgx_set_max_samples(tgx_engine* e, int64_t max_samples);
  * 4: 256-bit stores); (1 << tile_shift) / spt must be 128 or 256 threads.  Invalidates the current plan.
  * Default 10, 4. */
 int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt);
-/* How a CTA stages its tile's constants in shared memory: 0 once per CTA (__syncthreads), 1 once per warp
- * (__syncwarp only), 2 as 1 plus a register cap for one more CTA per SM.  Results are identical. */
-int tgx_set_eval_variant(tgx_engine* e, int variant);
 /* Planning mode.  Sample counts, phase boundaries, status bits and every speed v_k are bit-identical to the
  * reference in both modes.
  *   exact_ramps = 0 (default): ramps are advanced in exact arithmetic-progression jumps of v and the angle / position

@@ -259,19 +259,18 @@ def test_layouts_and_tunings_agree(engine, oracle):
     params = abi.concat([workloads.mixed_cfg3(300), workloads.default_circle()])
     base, counts, status, _ = gpu_generate(engine, params, want_phases=False)
     try:
-        for shift, spt, variant in ((9, 2, 0), (9, 4, 1), (9, 2, 2), (10, 4, 1), (10, 4, 2), (9, 4, 0)):
+        for shift, spt in ((9, 2), (9, 4), (10, 4)):
             engine.set_tuning(shift, spt)
-            engine.set_eval_variant(variant)
             for plane_major in (False, True):
                 out, c2, s2, _ = gpu_generate(engine, params, want_phases=False, plane_major=plane_major)
                 np.testing.assert_array_equal(c2, counts)
-                # tile size changes where segment bases sit, so values may differ in the last bits only
+                # tile size changes where the exactly replayed segment bases sit, so values may differ by the closed
+                # form's drift inside a tile (<= 1024 half-ulps of theta), far below the 1e-9 m parity budget
                 m = ~np.isnan(base)
                 assert (np.isnan(out) == np.isnan(base)).all()
-                np.testing.assert_allclose(out[m], base[m], rtol=0, atol=5e-12)
+                np.testing.assert_allclose(out[m], base[m], rtol=0, atol=1e-10)
     finally:
         engine.set_tuning(10, 4)
-        engine.set_eval_variant(0)
     ref, _, _ = oracle.generate(params[-1:])
     assert_samples_close(base[-1, :, :25001], ref, "default circle in mixed batch")
 

@@ -67,10 +67,12 @@ def main():
     for shift, spt in ((9, 2), (9, 4), (10, 4)):
         eng.set_tuning(shift, spt)
         eng.plan(d_params, want_outputs=False)
-        for variant in (0, 1, 2):
-            eng.set_eval_variant(variant)
+        for slabs in (False, True):
+            eng.set_slab_planning(slabs)
+            eng.plan(d_params, want_outputs=False)
+            eng.plan(d_params, want_outputs=False)
             ms = timed(lambda: eng.eval(out))
-            print(f"eval tile={1 << shift:5d} spt={spt} threads={(1 << shift) // spt:4d} variant={variant}: {ms:8.3f} ms  "
+            print(f"eval tile={1 << shift:5d} spt={spt} threads={(1 << shift) // spt:4d} {'slab plan         ' if slabs else 'exact-offset plan  '}: {ms:8.3f} ms  "
                   f"{112 * total / ms / 1e6:8.1f} GB/s  {total / ms / 1e6:7.2f} Gsamples/s")
     eng.close()
 

@@ -34,9 +34,8 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
                              int seg_slab, int tile_slab, TrajRec* recs, Seg* segs, Tile* tiles, int32_t* counts,
                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
                              PlanStats* stats, cudaStream_t stream);
-cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles, int tile_shift,
-                        int spt, int variant, const OutView& out, bool store, double* max_v, double* max_a,
-                        cudaStream_t stream);
+cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int spt, const OutView& out, bool store,
+                        double* max_v, double* max_a, cudaStream_t stream);
 cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, const double* max_v,
                                         const double* max_a, double v_max, double a_max, uint8_t* flags,
                                         uint32_t* status_out, cudaStream_t stream);
@@ -147,20 +146,21 @@ struct tgx_engine {
     int64_t max_samples = (int64_t)1 << 24;
     int tile_shift = 10;   // 1024 samples per tile
     bool exact_ramps = false;   // plan mode: replay ramps step by step (bit-identical state) or in exact-v jumps
-    int variant = 0;       // staging variant of the evaluation kernel (see eval.cu: launch_eval)
     int spt = 4;           // samples per thread: 2 -> 128-bit stores, 4 -> 256-bit stores (measured best on B200)
     int64_t launches = 0;
 
     // slab-mode planning (single replay): slice sizes learned from the previous exact-offset plan
     bool allow_slabs = true;
     bool slabs_ready = false;
-    int seg_slab = 0, tile_slab = 0;
+    int seg_slab = 0, tile_slab = 0;             // slice sizes the NEXT slab plan will use
+    int seg_slab_plan = 0, tile_slab_plan = 0;   // slice sizes of the CURRENT plan (if plan_packed)
     int64_t slab_plans = 0, exact_plans = 0;
 
     // per-trajectory scratch (capacity in trajectories)
     DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals, cur_table, stats;
-    // tables
-    DevBuf segs, tiles;
+    // tables (exact-offset plans) and packets (slab plans)
+    DevBuf segs, tiles, packets;
+    bool plan_packed = false;
     PinBuf h_totals;
 
     // current plan
@@ -175,6 +175,18 @@ struct tgx_engine {
 };
 
 namespace {
+
+tgx::TableView table_view(const tgx_engine* e) {
+    tgx::TableView tv{};
+    tv.recs = e->recs.as<tgx::TrajRec>();
+    tv.segs = e->segs.as<tgx::Seg>();
+    tv.tiles = e->tiles.as<tgx::Tile>();
+    if (e->plan_packed) {
+        tv.seg_slab = e->seg_slab_plan;
+        tv.tile_slab = e->tile_slab_plan;
+    }
+    return tv;
+}
 
 int ensure_traj_scratch(tgx_engine* e, int64_t n) {
     int rc;
@@ -251,6 +263,9 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                 tot_segs = need_segs;
                 tot_tiles = need_tiles;
                 done = true;
+                e->plan_packed = true;
+                e->seg_slab_plan = e->seg_slab;
+                e->tile_slab_plan = e->tile_slab;
                 e->slab_plans += 1;
                 // a batch with many fewer tiles than slots would launch mostly empty CTAs: go back to exact offsets
                 if ((int64_t)h_stats->total_tiles * 2 < need_tiles) e->slabs_ready = false;
@@ -261,6 +276,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     }
 
     if (!done) {
+        e->plan_packed = false;
         // ---- exact-offset mode, pass 1: counts ------------------------------------------------------------------
         TGX_CUDA(tgx::launch_plan_count(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift,
                                         e->exact_ramps, tab, cnt, st, nseg, ntile, stream));
@@ -393,7 +409,7 @@ int tgx_destroy(tgx_engine* e) {
     if (!e) return TGX_OK;
     cudaSetDevice(e->device);
     DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
-                      &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats};
+                      &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats, &e->packets};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         e->h_params[i].release();
@@ -457,18 +473,11 @@ int tgx_plan_path_counts(const tgx_engine* e, int64_t* slab_plans, int64_t* exac
     return TGX_OK;
 }
 
-// Staging variant of the evaluation kernel: 0 one copy of the tile's constants per CTA behind __syncthreads,
-// 1 one copy per warp behind __syncwarp, 2 as 1 with a register cap that admits one more CTA per SM.
-int tgx_set_eval_variant(tgx_engine* e, int variant) {
-    if (!e || variant < 0 || variant > 2) return TGX_ERR_INVALID;
-    e->variant = variant;
-    return TGX_OK;
-}
-
 int64_t tgx_scratch_bytes(const tgx_engine* e) {
     if (!e) return 0;
     const DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
-                            &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats};
+                            &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats,
+                            &e->packets};
     int64_t s = 0;
     for (const DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;
@@ -524,6 +533,7 @@ int tgx_plan_samples(tgx_engine* e, const tgx_params* d_params, int64_t n, const
     if (d_counts) TGX_CUDA(cudaMemcpyAsync(d_counts, e->cnt.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     if (d_status) TGX_CUDA(cudaMemcpyAsync(d_status, e->status.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     e->has_plan = true;
+    e->plan_packed = false;
     e->plan_n = n;
     e->plan_tiles = n;
     e->plan_segs = n;
@@ -542,9 +552,8 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
     if (d_max_v) TGX_CUDA(cudaMemsetAsync(d_max_v, 0, (size_t)e->plan_n * sizeof(double), s));
     if (d_max_a) TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)e->plan_n * sizeof(double), s));
     if (e->plan_tiles == 0) return TGX_OK;
-    TGX_CUDA(tgx::launch_eval(e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(), e->tiles.as<tgx::Tile>(),
-                              e->plan_tiles, e->tile_shift, e->spt, e->variant, make_view(out), true, d_max_v, d_max_a,
-                              s));
+    TGX_CUDA(tgx::launch_eval(table_view(e), e->plan_tiles, e->tile_shift, e->spt, make_view(out), true, d_max_v,
+                              d_max_a, s));
     e->launches += 1;
     return TGX_OK;
 }
@@ -570,8 +579,8 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
     TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)n * sizeof(double), s));
     if (e->plan_tiles > 0) {
         tgx::OutView none{};
-        TGX_CUDA(tgx::launch_eval(e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(), e->tiles.as<tgx::Tile>(),
-                                  e->plan_tiles, e->tile_shift, e->spt, e->variant, none, false, d_max_v, d_max_a, s));
+        TGX_CUDA(tgx::launch_eval(table_view(e), e->plan_tiles, e->tile_shift, e->spt, none, false, d_max_v, d_max_a,
+                                  s));
         e->launches += 1;
     }
     TGX_CUDA(tgx::launch_feasibility_finalize(n, e->status.as<uint32_t>(), d_max_v, d_max_a, limits->v_max,

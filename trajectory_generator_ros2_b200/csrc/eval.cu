@@ -108,43 +108,70 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double x) {
 
 }  // namespace
 
-// WARP_STAGE: every warp stages the tile's constants in its own shared-memory slice and synchronises only with
-// __syncwarp(), so no warp ever waits at a CTA barrier for the slowest one (the constants are L2-resident after the
-// first warp's miss); otherwise one copy per CTA behind __syncthreads().  MINB: minimum CTAs per SM (register cap).
-template <int THREADS, int SPT, bool STORE, bool REDUCE, bool WARP_STAGE, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, const Tile* __restrict__ tiles,
-            OutView out, double* __restrict__ max_v, double* __restrict__ max_a) {
-    constexpr int kSlices = WARP_STAGE ? THREADS / 32 : 1;
-    __shared__ __align__(16) TrajRec s_rec_all[kSlices];
-    __shared__ __align__(16) Seg s_seg_all[kSlices][kMaxSegPerTile];
-    __shared__ int s_kend_all[kSlices][kMaxSegPerTile];          // last sample of each segment
+// SLAB: the plan is a slab plan (fixed per-trajectory slices, see TableView).
+template <int THREADS, int SPT, bool STORE, bool REDUCE, bool SLAB>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 6)
+eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a) {
+    __shared__ __align__(16) TrajRec s_rec;
+    __shared__ __align__(16) Seg s_seg[kMaxSegPerTile];
+    __shared__ int s_kend[kMaxSegPerTile];          // last sample of each segment
+    __shared__ int4 s_tile;
     __shared__ double s_red[2][THREADS / 32];
-    const int slice = WARP_STAGE ? (int)(threadIdx.x >> 5) : 0;
-    TrajRec& s_rec = s_rec_all[slice];
-    Seg* const s_seg = s_seg_all[slice];
-    int* const s_kend = s_kend_all[slice];
 
     // ---- stage the tile's constants in shared memory (16-byte chunks, one per thread) -------------------
-    const int4 tw = __ldg(reinterpret_cast<const int4*>(tiles) + blockIdx.x);   // {traj, k_lo, seg_begin, nseg}
-    if (tw.w <= 0) return;   // an empty slot of a slab-mode plan (whole CTA, before any barrier)
-    const int traj = tw.x, k_lo = tw.y, seg_begin = tw.z;
-    const int nseg = tw.w < kMaxSegPerTile ? tw.w : kMaxSegPerTile;
-    {
-        const int4* src = reinterpret_cast<const int4*>(segs + seg_begin);
-        for (int t = WARP_STAGE ? (int)(threadIdx.x & 31) : (int)threadIdx.x; t < 4 + 4 * nseg;
-             t += WARP_STAGE ? 32 : THREADS) {
+    int traj, k_lo, nseg;
+    if (SLAB) {
+        traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
+        const int t = (int)blockIdx.x - traj * tv.tile_slab;
+        const int4* pseg = reinterpret_cast<const int4*>(tv.segs + (size_t)traj * (size_t)tv.seg_slab);
+        // round 1 (independent loads): record, this tile's directory entry and, for the first tile of a trajectory
+        // (whose segments start the slice), the first kSlabSpecSegs segments
+        {
+            const int c = threadIdx.x;
+            if (c < 4) {
+                reinterpret_cast<int4*>(&s_rec)[c] = __ldg(reinterpret_cast<const int4*>(tv.recs + traj) + c);
+            } else if (c == 4) {
+                s_tile = __ldg(reinterpret_cast<const int4*>(tv.tiles) + blockIdx.x);
+            } else if (t == 0 && c < 5 + 4 * kSlabSpecSegs) {
+                const int q = c - 5;
+                const int4 w = __ldg(pseg + q);
+                reinterpret_cast<int4*>(s_seg)[q] = w;
+                if ((q & 3) == 0) s_kend[q >> 2] = w.x + w.y;   // kb + n
+            }
+        }
+        __syncthreads();
+        const int4 tw = s_tile;
+        if (tw.w <= 0) return;   // an empty slot (whole CTA)
+        k_lo = tw.y;
+        nseg = tw.w < kMaxSegPerTile ? tw.w : kMaxSegPerTile;
+        const int have = (t == 0) ? kSlabSpecSegs : 0;
+        if (nseg > have) {       // CTA-uniform: a later tile of a long trajectory, or more segments than speculated
+            const int4* src = pseg + 4 * (tw.z - traj * tv.seg_slab);
+            for (int q = 4 * have + (int)threadIdx.x; q < 4 * nseg; q += THREADS) {
+                const int4 w = __ldg(src + q);
+                reinterpret_cast<int4*>(s_seg)[q] = w;
+                if ((q & 3) == 0) s_kend[q >> 2] = w.x + w.y;
+            }
+            __syncthreads();
+        }
+    } else {
+        const int4 tw = __ldg(reinterpret_cast<const int4*>(tv.tiles) + blockIdx.x);   // {traj, k_lo, seg_begin, nseg}
+        if (tw.w <= 0) return;
+        traj = tw.x;
+        k_lo = tw.y;
+        nseg = tw.w < kMaxSegPerTile ? tw.w : kMaxSegPerTile;
+        const int4* src = reinterpret_cast<const int4*>(tv.segs + tw.z);
+        for (int t = threadIdx.x; t < 4 + 4 * nseg; t += THREADS) {
             if (t < 4) {
-                reinterpret_cast<int4*>(&s_rec)[t] = __ldg(reinterpret_cast<const int4*>(recs + traj) + t);
+                reinterpret_cast<int4*>(&s_rec)[t] = __ldg(reinterpret_cast<const int4*>(tv.recs + traj) + t);
             } else {
                 const int4 w = __ldg(src + (t - 4));
                 reinterpret_cast<int4*>(s_seg)[t - 4] = w;
                 if (((t - 4) & 3) == 0) s_kend[(t - 4) >> 2] = w.x + w.y;   // kb + n
             }
         }
+        __syncthreads();
     }
-    if (WARP_STAGE) __syncwarp();
-    else __syncthreads();
 
     const int type = s_rec.type & kRecTypeMask;
     const int n = s_rec.n;
@@ -353,31 +380,23 @@ eval_kernel(const TrajRec* __restrict__ recs, const Seg* __restrict__ segs, cons
     }
 
     if (REDUCE) {
-        // ---- per-trajectory max |v|, max |a|: warp shuffles, then one atomicMax per warp (WARP_STAGE) or one
-        //      shared-memory hop and one atomicMax per tile ----------------------------------------------------
+        // ---- per-trajectory max |v|, max |a|: warp shuffles -> shared -> one atomicMax per tile ------------
         best_v2 = warp_max(best_v2);
         best_a2 = warp_max(best_a2);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (WARP_STAGE) {
-            if (lane == 0 && nvalid > 0) {
-                if (max_v) atomic_max_nonneg(max_v + traj, sqrt(best_v2));
-                if (max_a) atomic_max_nonneg(max_a + traj, sqrt(best_a2));
-            }
-        } else {
+        if (lane == 0) {
+            s_red[0][warp] = best_v2;
+            s_red[1][warp] = best_a2;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double a = lane < THREADS / 32 ? s_red[0][lane] : 0.0;
+            double b = lane < THREADS / 32 ? s_red[1][lane] : 0.0;
+            a = warp_max(a);
+            b = warp_max(b);
             if (lane == 0) {
-                s_red[0][warp] = best_v2;
-                s_red[1][warp] = best_a2;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                double a = lane < THREADS / 32 ? s_red[0][lane] : 0.0;
-                double b = lane < THREADS / 32 ? s_red[1][lane] : 0.0;
-                a = warp_max(a);
-                b = warp_max(b);
-                if (lane == 0) {
-                    if (max_v) atomic_max_nonneg(max_v + traj, sqrt(a));
-                    if (max_a) atomic_max_nonneg(max_a + traj, sqrt(b));
-                }
+                if (max_v) atomic_max_nonneg(max_v + traj, sqrt(a));
+                if (max_a) atomic_max_nonneg(max_a + traj, sqrt(b));
             }
         }
     }
@@ -400,41 +419,34 @@ feasibility_finalize_kernel(int64_t n, const uint32_t* __restrict__ plan_status,
 
 // ---- host-side launchers -----------------------------------------------------------------------------------
 
-template <int THREADS, int SPT, bool WARP_STAGE, int MINB>
-static cudaError_t launch_eval_t(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles,
-                                 const OutView& out, bool store, double* max_v, double* max_a,
-                                 cudaStream_t stream) {
+template <int THREADS, int SPT, bool SLAB>
+static cudaError_t launch_eval_t(const TableView& tv, int64_t ntiles, const OutView& out, bool store, double* max_v,
+                                 double* max_a, cudaStream_t stream) {
     const bool reduce = max_v || max_a;
     const unsigned grid = (unsigned)ntiles;
     if (store && reduce)
-        eval_kernel<THREADS, SPT, true, true, WARP_STAGE, MINB><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, true, true, SLAB><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     else if (store)
-        eval_kernel<THREADS, SPT, true, false, WARP_STAGE, MINB><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, true, false, SLAB><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     else
-        eval_kernel<THREADS, SPT, false, true, WARP_STAGE, MINB><<<grid, THREADS, 0, stream>>>(recs, segs, tiles, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, false, true, SLAB><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     return cudaGetLastError();
 }
 
 // tile = 1 << tile_shift samples per CTA, spt samples per thread: threads per CTA = tile / spt in {128, 256}.
-// variant 0: CTA-wide staging; 1: per-warp staging; 2: per-warp staging with a register cap for one more CTA per SM.
-cudaError_t launch_eval(const TrajRec* recs, const Seg* segs, const Tile* tiles, int64_t ntiles, int tile_shift,
-                        int spt, int variant, const OutView& out, bool store, double* max_v, double* max_a,
-                        cudaStream_t stream) {
+cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int spt, const OutView& out, bool store,
+                        double* max_v, double* max_a, cudaStream_t stream) {
     if (ntiles <= 0) return cudaSuccess;
     if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int threads = (1 << tile_shift) / spt;
-#define TGX_CASE(T, S, V, W, M) \
-    if (threads == (T) && spt == (S) && variant == (V)) \
-        return launch_eval_t<T, S, W, M>(recs, segs, tiles, ntiles, out, store, max_v, max_a, stream)
-    TGX_CASE(128, 4, 0, false, 6);
-    TGX_CASE(128, 4, 1, true, 6);
-    TGX_CASE(128, 4, 2, true, 8);
-    TGX_CASE(256, 2, 0, false, 3);
-    TGX_CASE(256, 2, 1, true, 3);
-    TGX_CASE(256, 2, 2, true, 4);
-    TGX_CASE(256, 4, 0, false, 3);
-    TGX_CASE(256, 4, 1, true, 3);
-    TGX_CASE(256, 4, 2, true, 4);
+    const bool packed = tv.tile_slab > 0;
+#define TGX_CASE(T, S)                                                                                     \
+    if (threads == (T) && spt == (S))                                                                      \
+        return packed ? launch_eval_t<T, S, true>(tv, ntiles, out, store, max_v, max_a, stream)            \
+                      : launch_eval_t<T, S, false>(tv, ntiles, out, store, max_v, max_a, stream)
+    TGX_CASE(128, 4);
+    TGX_CASE(256, 2);
+    TGX_CASE(256, 4);
 #undef TGX_CASE
     return cudaErrorInvalidConfiguration;
 }

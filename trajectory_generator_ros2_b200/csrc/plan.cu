@@ -359,7 +359,9 @@ __device__ __forceinline__ bool hold(double v, double t_hold, double dt, int& k,
         const double d0 = TRACK0 ? dsub(s0n, s0) : 0.0;      // exact effective increments
         const double d1 = TRACK1 ? dsub(s1n, s1) : 0.0;
         if (!open) {
-            E.open(k, v, 0.0, v, s0, EXACT ? d0 : s1, 0.0);
+            // Seg.s1: orbit = theta increment per step (the exact progression step when EXACT, else the nominal
+            // (v/r)*dt); line = y at the base sample
+            E.open(k, v, 0.0, v, s0, EXACT ? d0 : (E.orbit ? a0 : s1), 0.0);
             seg_d = d0;
             open = true;
         }
@@ -452,7 +454,7 @@ __device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E
         if (fabs(dsub(v, vg)) > 0.001) st |= TGX_ST_VGOALS_NOT_INCREASING;                // :57-59
         E.phase(k, TGX_PH_REACHED, vg, o.t_traj);            // :61-62
         const double w = STATE ? dmul(div_inv(v, rdiv), dt) : 0.0;    // omega*dt_, the same on every step (:65-67)
-        if (!hold<STATE, false, STATE>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0, tab)) {   // :63-71
+        if (!hold<STATE, false, STATE && XR>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0, tab)) {   // :63-71
             st |= TGX_ST_TOO_LONG;
             return -1;
         }
@@ -769,7 +771,9 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
     const bool keep = slab || plan_counts[i] > 0;
     const int64_t so = slab ? i * (int64_t)seg_slab : seg_off[i];
     const int64_t to = slab ? i * (int64_t)tile_slab : tile_off[i];
-    Emitter E{tile_shift, (int32_t)i, keep ? segs + so : nullptr, keep ? tiles + to : nullptr, (int32_t)so,
+    TrajRec* rec_out = recs + i;
+    Tile* tile_out = tiles + to;
+    Emitter E{tile_shift, (int32_t)i, keep ? segs + so : nullptr, keep ? tile_out : nullptr, (int32_t)so,
               phases ? phases + i : nullptr, p.type != TGX_LINE, slab ? seg_slab : 0x7fffffff,
               slab ? tile_slab : 0x7fffffff};
     PlanOut r;
@@ -777,10 +781,10 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
         double from[TGX_NCHAN];
 #pragma unroll
         for (int c = 0; c < TGX_NCHAN; ++c) from[c] = stop_from[i * TGX_NCHAN + c];
-        r = stop_one<true>(p, from, max_samples, E, recs + i);
+        r = stop_one<true>(p, from, max_samples, E, rec_out);
         if (phases && r.status) phases[i].n = 0;
     } else {
-        r = plan_one<true, true, XR>(p, max_samples, has_lim ? &lim : nullptr, E, recs + i, tab);
+        r = plan_one<true, true, XR>(p, max_samples, has_lim ? &lim : nullptr, E, rec_out, tab);
     }
     bool overflow = false;
     if (slab) {
@@ -790,7 +794,7 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
         for (int t = used; t < tile_slab; ++t) {
             Tile e;
             e.traj = (int32_t)i; e.k_lo = 0; e.seg_begin = (int32_t)so; e.nseg = 0;
-            tiles[to + t] = e;
+            tile_out[t] = e;
         }
     }
     if (counts) counts[i] = r.n;

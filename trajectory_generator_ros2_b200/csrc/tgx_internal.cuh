@@ -73,6 +73,25 @@ constexpr int kRampChunk = 256;
 constexpr int kMaxSegPerTile = 64;
 constexpr int kMaxOptionalSegPerTile = 36;
 
+// Where the evaluation kernel finds its plan: three dense arrays TrajRec[n], Tile[n_tile], Seg[n_seg].
+//   exact-offset plans (tile_slab == 0): a CTA reads its Tile, then the record and the segments it points to (two
+//       dependent rounds of loads);
+//   slab plans (tile_slab > 0): trajectory i owns Tile[i*tile_slab ..] and Seg[i*seg_slab ..], so everything is found
+//       from blockIdx alone (traj = blockIdx / tile_slab) and the first tile of a trajectory is staged in ONE round of
+//       independent 16-byte loads (record + tile entry + the first kSlabSpecSegs segments, speculatively).
+// Keeping these reads few and dense matters more than their size suggests: every DRAM read that lands in the middle
+// of the kernel's write stream costs a write->read->write bus turnaround (tools/wbw: 1 % of read traffic costs 8 %
+// of the write bandwidth; with cache-resident tables the same kernel writes 7.27 TB/s instead of 6.5 TB/s).
+struct TableView {
+    const TrajRec* recs;
+    const Seg* segs;
+    const Tile* tiles;
+    int seg_slab;
+    int tile_slab;                  // > 0: slab plan
+};
+
+constexpr int kSlabSpecSegs = 4;   // segments fetched speculatively with the record in a slab plan
+
 // Statistics of one plan, accumulated by the fill pass and read back by the host (one small D2H per plan).
 struct PlanStats {
     unsigned long long total_samples;   // sum of N_i

@@ -41,7 +41,6 @@ def _load() -> C.CDLL:
     lib.tgx_destroy.argtypes = [vp]
     lib.tgx_set_max_samples.argtypes = [vp, i64]
     lib.tgx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
-    lib.tgx_set_eval_variant.argtypes = [vp, C.c_int]
     lib.tgx_set_plan_mode.argtypes = [vp, C.c_int]
     lib.tgx_set_slab_planning.argtypes = [vp, C.c_int]
     lib.tgx_plan_path_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
@@ -178,9 +177,6 @@ class Engine:
 
     def set_tuning(self, tile_shift: int, spt: int):
         self._check(self._lib.tgx_set_tuning(self._h, tile_shift, spt), "tgx_set_tuning")
-
-    def set_eval_variant(self, variant: int):
-        self._check(self._lib.tgx_set_eval_variant(self._h, variant), "tgx_set_eval_variant")
 
     def set_plan_mode(self, exact_ramps: bool):
         self._check(self._lib.tgx_set_plan_mode(self._h, 1 if exact_ramps else 0), "tgx_set_plan_mode")
