@@ -393,8 +393,10 @@ def run_ours(args):
                 "trajectories_per_gpu": n, "samples_per_gpu": total_samples, "row_stride": row,
                 "layout": "plane-major [14][n][row]" if args.plane_major else "trajectory-major [n][14][row]",
                 "chunks": chunks,
-                "step": "tgx_plan (count + scans + fill) + " + ("tgx_feasibility" if feas_only else "tgx_eval")
-                        + ", parameters resident in HBM",
+                "step": "tgx_plan (hold-length table + one strict-IEEE replay per trajectory into fixed slices; the "
+                        "first plan of an engine measures the slice sizes with a count + scan + fill pass) + "
+                        + ("tgx_feasibility" if feas_only else "tgx_eval") + ", parameters resident in HBM",
+                "plan_paths": dict(zip(("single_replay", "two_replay"), eng.plan_path_counts())),
                 "l2": "each step writes %.1f GB >> 126 MB L2, no flush needed" % (eval_bytes / 1e9)
                       if not feas_only else "reduction only",
                 "parallelism": f"{world} independent shards, no data-path collective",
