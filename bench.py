@@ -316,6 +316,7 @@ def run_ours(args):
     # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region) ----
     e2e = None
     if not feas_only and not args.no_e2e:
+        eng.set_host_fill(not args.e2e_all_planes)
         call_n = min(n, args.e2e_call)                       # trajectories per tgx_generate_host call
         pin_out = PinnedArray((call_n, abi.TGX_NCHAN, row))
         pin_params = PinnedArray((call_n,), dtype=abi.PARAMS_DTYPE)
@@ -345,8 +346,12 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t[0])
         assert h_counts_total == total_samples
+        planes = 14 if args.e2e_all_planes else 10
         e2e = {"value": job_samples / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * (abi.TGX_NCHAN * row * 8 + 8)),
+               "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * (planes * row * 8 + 8)),
+               "wire_format": ("all 14 planes over PCIe" if args.e2e_all_planes else
+                               "10 varying planes over PCIe; the 4 constant planes (p.z = alt, v.z = a.z = j.z = 0) "
+                               "are written into the host buffer by host threads"),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
                "call": f"tgx_generate_host, {call_n} trajectories per call into one reused pinned host buffer"}
         pin_out.free()
@@ -428,6 +433,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="trajectories timed on the CPU legs")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-call", type=int, default=1 << 16)
+    ap.add_argument("--e2e-all-planes", action="store_true", help="ship all 14 planes over PCIe in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

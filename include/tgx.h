@@ -264,6 +264,13 @@ int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const do
                   double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
                   tgx_phases* h_phases);
 
+/* Wire format of the host-buffer calls.  The z-components of every setpoint are literal constants in the reference
+ * (p.z = alt_, v.z = a.z = j.z = 0: Circle.cpp:109-121, Line.cpp:99-108, Figure8.cpp:110-119).  With
+ * fill_constants_on_host = 1 (default) the device evaluates and ships only the 10 varying planes over PCIe and host
+ * threads write the 4 constant rows of each trajectory; with 0 all 14 planes are evaluated and shipped.  The host
+ * buffer holds the same values either way. */
+int tgx_set_host_fill(tgx_engine* e, int fill_constants_on_host);
+
 /* One create*Goal call for host-resident arguments (see tgx_plan_samples); h_out14 receives the 14 channels. */
 int tgx_sample_host(tgx_engine* e, const tgx_params* h_params, double v, double accel, double s0, double s1,
                     double* h_out14);

@@ -389,6 +389,21 @@ def test_generate_host_matches_device_path(engine, oracle):
     assert ((s3 & abi.ST_TRUNCATED) != 0).tolist() == (c3 > 512).tolist()
 
 
+def test_host_wire_formats_agree(engine):
+    """Shipping 10 planes and filling the 4 constant ones on the host gives the same buffer as shipping all 14."""
+    params = abi.concat([workloads.mixed_cfg3(700), workloads.default_circle()])
+    a, ca, sa, _ = engine.generate_host(params, 25004)
+    engine.set_host_fill(False)
+    try:
+        b, cb, sb, _ = engine.generate_host(params, 25004)
+    finally:
+        engine.set_host_fill(True)
+    np.testing.assert_array_equal(ca, cb)
+    for i in range(len(params)):
+        np.testing.assert_array_equal(a[i, :, :ca[i]], b[i, :, :ca[i]])
+        assert (a[i, abi.PZ, :ca[i]] == params["alt"][i]).all() and (a[i, abi.JZ, :ca[i]] == 0).all()
+
+
 def test_generate_host_chunking(engine, oracle):
     """More rows than one 1 GiB staging chunk holds: exercises the double-buffered chunk loop."""
     params = workloads.circles_cfg2(24000)          # 24000 * 14 * 1024 * 8 B = 2.75 GB -> 3 chunks

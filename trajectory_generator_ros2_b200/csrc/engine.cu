@@ -14,6 +14,8 @@
 #include <iterator>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
@@ -145,6 +147,7 @@ struct tgx_engine {
     int device = 0;
     int64_t max_samples = (int64_t)1 << 24;
     int tile_shift = 10;   // 1024 samples per tile
+    bool host_fill_constants = true;   // host-buffer calls: ship 10 planes over PCIe, memset the 4 constant ones
     bool exact_ramps = false;   // plan mode: replay ramps step by step (bit-identical state) or in exact-v jumps
     int spt = 4;           // samples per thread: 2 -> 128-bit stores, 4 -> 256-bit stores (measured best on B200)
     int64_t launches = 0;
@@ -455,6 +458,14 @@ int tgx_set_plan_mode(tgx_engine* e, int exact_ramps) {
     return TGX_OK;
 }
 
+// Host-buffer calls: 1 (default) = evaluate and ship only the 10 varying planes and write the 4 constant planes
+// (p.z = alt, v.z = a.z = j.z = 0) with host threads; 0 = evaluate and ship all 14 planes.
+int tgx_set_host_fill(tgx_engine* e, int fill_constants_on_host) {
+    if (!e) return TGX_ERR_INVALID;
+    e->host_fill_constants = fill_constants_on_host != 0;
+    return TGX_OK;
+}
+
 // Single-replay planning with per-trajectory slices sized from the previous plan (default on).  allow = 0 forces the
 // two-replay exact-offset path for every plan.
 int tgx_set_slab_planning(tgx_engine* e, int allow) {
@@ -659,6 +670,9 @@ int tgx_count_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const t
     return TGX_OK;
 }
 
+// Channels that vary along a trajectory (everything but p.z, v.z, a.z, j.z).
+constexpr uint32_t kVaryingChannels = 0x3fffu & ~((1u << TGX_PZ) | (1u << TGX_VZ) | (1u << TGX_AZ) | (1u << TGX_JZ));
+
 // Shared body of tgx_generate_host / tgx_stop_host.
 static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_from, int64_t n,
                     const tgx_limits* limits, double* h_out, int64_t capacity, int32_t* h_counts,
@@ -684,6 +698,34 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         if (h_phases && (rc = e->h_ph[b].reserve((size_t)chunk * sizeof(tgx_phases)))) return rc;
         if (h_from && (rc = e->h_from[b].reserve((size_t)chunk * TGX_NCHAN * sizeof(double)))) return rc;
     }
+
+    // The z-components are literal constants in the reference (p.z = alt_, v.z = a.z = j.z = 0: Circle.cpp:109-121,
+    // Line.cpp:99-108, Figure8.cpp:110-119).  They are not worth 29 % of the PCIe traffic: the device evaluates and
+    // ships the 10 varying planes, and host threads write the 4 constant rows of every trajectory meanwhile.
+    const bool fill = e->host_fill_constants && capacity > 0;
+    std::vector<std::thread> fillers;
+    if (fill) {
+        unsigned hw = std::thread::hardware_concurrency();
+        const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(hw ? hw / 2 : 1, 8u), n));
+        for (int t = 0; t < nthreads; ++t) {
+            const int64_t a = n * t / nthreads, z = n * (t + 1) / nthreads;
+            fillers.emplace_back([=] {
+                for (int64_t i = a; i < z; ++i) {
+                    double* row = h_out + i * TGX_NCHAN * capacity;
+                    const double alt = h_params[i].alt;
+                    double* pz = row + (int64_t)TGX_PZ * capacity;
+                    for (int64_t k = 0; k < capacity; ++k) pz[k] = alt;
+                    std::memset(row + (int64_t)TGX_VZ * capacity, 0, (size_t)capacity * sizeof(double));
+                    std::memset(row + (int64_t)TGX_AZ * capacity, 0, (size_t)capacity * sizeof(double));
+                    std::memset(row + (int64_t)TGX_JZ * capacity, 0, (size_t)capacity * sizeof(double));
+                }
+            });
+        }
+    }
+    struct Joiner {
+        std::vector<std::thread>& t;
+        ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
+    } joiner{fillers};
 
     for (int64_t ci = 0; ci < nchunks; ++ci) {
         const int b = (int)(ci & 1);
@@ -714,11 +756,24 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
             lay.traj_stride = TGX_NCHAN * capacity;
             lay.chan_stride = capacity;
             lay.capacity = capacity;
+            lay.channel_mask = fill ? kVaryingChannels : 0;
             rc = tgx_eval(e, &lay, nullptr, nullptr, s);
             if (rc) return rc;
             TGX_CUDA(cudaEventRecord(e->hev_eval, s));
-            TGX_CUDA(cudaMemcpyAsync(h_out + lo * TGX_NCHAN * capacity, e->h_out[b].p, (size_t)(m * row_bytes),
-                                     cudaMemcpyDeviceToHost, s));
+            if (fill) {
+                // the varying planes come in adjacent pairs (px,py | vx,vy | ax,ay | jx,jy | psi,dpsi): five 2-D copies,
+                // each moving 2 rows of every trajectory of the chunk
+                const size_t pitch = (size_t)row_bytes, width = (size_t)(2 * capacity) * sizeof(double);
+                for (int q = 0; q < 5; ++q) {
+                    const size_t off = (size_t)(3 * q) * (size_t)capacity;
+                    TGX_CUDA(cudaMemcpy2DAsync(h_out + lo * TGX_NCHAN * capacity + off, pitch,
+                                               e->h_out[b].as<double>() + off, pitch, width, (size_t)m,
+                                               cudaMemcpyDeviceToHost, s));
+                }
+            } else {
+                TGX_CUDA(cudaMemcpyAsync(h_out + lo * TGX_NCHAN * capacity, e->h_out[b].p, (size_t)(m * row_bytes),
+                                         cudaMemcpyDeviceToHost, s));
+            }
         }
         if (h_counts)
             TGX_CUDA(cudaMemcpyAsync(h_counts + lo, e->h_cnt[b].p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -730,6 +785,7 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
     }
     TGX_CUDA(cudaStreamSynchronize(e->hs[0]));
     TGX_CUDA(cudaStreamSynchronize(e->hs[1]));
+    for (auto& x : fillers) x.join();
     // TRUNCATED is a property of the caller's capacity, known only here
     if (h_status && h_counts)
         for (int64_t i = 0; i < n; ++i)

@@ -42,6 +42,7 @@ def _load() -> C.CDLL:
     lib.tgx_set_max_samples.argtypes = [vp, i64]
     lib.tgx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     lib.tgx_set_plan_mode.argtypes = [vp, C.c_int]
+    lib.tgx_set_host_fill.argtypes = [vp, C.c_int]
     lib.tgx_set_slab_planning.argtypes = [vp, C.c_int]
     lib.tgx_plan_path_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.tgx_scratch_bytes.restype = i64
@@ -180,6 +181,9 @@ class Engine:
 
     def set_plan_mode(self, exact_ramps: bool):
         self._check(self._lib.tgx_set_plan_mode(self._h, 1 if exact_ramps else 0), "tgx_set_plan_mode")
+
+    def set_host_fill(self, fill_constants_on_host: bool):
+        self._check(self._lib.tgx_set_host_fill(self._h, 1 if fill_constants_on_host else 0), "tgx_set_host_fill")
 
     def set_slab_planning(self, allow: bool):
         self._check(self._lib.tgx_set_slab_planning(self._h, 1 if allow else 0), "tgx_set_slab_planning")
