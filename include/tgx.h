@@ -49,7 +49,8 @@ extern "C" {
 enum tgx_type {
     TGX_CIRCLE = 0,
     TGX_LINE = 1,
-    TGX_FIGURE8 = 2
+    TGX_FIGURE8 = 2,
+    TGX_BOOMERANG = 3     /* Line out and back (Boomerang.cpp:31-141); takes tgx_line_params */
 };
 
 /* Channel order of the struct-of-arrays output: the numeric fields of snapstack_msgs2/Goal in the order
@@ -89,7 +90,7 @@ typedef struct tgx_params {
     double alt;                      /* alt_: z of every sample */
     union {
         tgx_orbit_params orbit;      /* TGX_CIRCLE, TGX_FIGURE8 */
-        tgx_line_params line;        /* TGX_LINE */
+        tgx_line_params line;        /* TGX_LINE, TGX_BOOMERANG */
     } u;
 } tgx_params;
 
@@ -97,7 +98,8 @@ typedef struct tgx_params {
 enum tgx_status_bits {
     TGX_ST_VGOALS_NOT_INCREASING = 1u << 0, /* RCLCPP_WARN at Circle.cpp:57-59 / Figure8.cpp:57-59 (samples still produced) */
     TGX_ST_FINAL_V_NONZERO       = 1u << 1, /* exit(1) at Circle.cpp:85-88 / Figure8.cpp:85-88 */
-    TGX_ST_LINE_END_NOT_B        = 1u << 2, /* exit(1) at Line.cpp:76-79 (end point > 0.05 m from B) */
+    TGX_ST_LINE_END_NOT_B        = 1u << 2, /* exit(1) at Line.cpp:76-79 (end point > 0.05 m from B); for a Boomerang also the
+                                               return leg's "final point is not A" (Boomerang.cpp:126-129) */
     TGX_ST_LINE_D2_NEGATIVE      = 1u << 3, /* Line.cpp:165-168: cruise segment length < 0; reported, like the reference does,
                                                by the bounds check only (set together with OUTSIDE_BOUNDS) */
     TGX_ST_OUTSIDE_BOUNDS        = 1u << 4, /* trajectoryInsideBounds() == false (only if a box was given) */

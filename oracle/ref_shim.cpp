@@ -19,6 +19,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "trajectory_generator_ros2/trajectories/Boomerang.hpp"
 #include "trajectory_generator_ros2/trajectories/Circle.hpp"
 #include "trajectory_generator_ros2/trajectories/Figure8.hpp"
 #include "trajectory_generator_ros2/trajectories/Line.hpp"
@@ -45,7 +46,7 @@ bool params_ok(const tgx_params& p) {
             if (!finite_pos(o.v_goals[i])) return false;
         return true;
     }
-    if (p.type == TGX_LINE) {
+    if (p.type == TGX_LINE || p.type == TGX_BOOMERANG) {
         const tgx_line_params& l = p.u.line;
         for (int i = 0; i < 3; ++i)
             if (!std::isfinite(l.A[i]) || !std::isfinite(l.B[i])) return false;
@@ -55,6 +56,12 @@ bool params_ok(const tgx_params& p) {
 }
 
 std::unique_ptr<tg::Trajectory> make_traj(const tgx_params& p) {
+    if (p.type == TGX_BOOMERANG) {
+        const tgx_line_params& l = p.u.line;
+        std::vector<double> vg{l.v_goal};
+        return std::make_unique<tg::Boomerang>(p.alt, Eigen::Vector3d(l.A[0], l.A[1], l.A[2]),
+                                               Eigen::Vector3d(l.B[0], l.B[1], l.B[2]), vg, l.a1, l.a3, p.dt);
+    }
     if (p.type == TGX_LINE) {
         const tgx_line_params& l = p.u.line;
         std::vector<double> vg{l.v_goal};
@@ -128,7 +135,7 @@ int64_t generate_one(const tgx_params& p, std::vector<Goal>& goals, std::unorder
         traj->generateTraj(goals, msgs, clock);
     } catch (const tgx_stub::ErrorLogged&) {
         // the reference would now call exit(1) (Circle.cpp:87, Line.cpp:78, Figure8.cpp:87)
-        st |= (p.type == TGX_LINE) ? TGX_ST_LINE_END_NOT_B : TGX_ST_FINAL_V_NONZERO;
+        st |= (p.type == TGX_LINE || p.type == TGX_BOOMERANG) ? TGX_ST_LINE_END_NOT_B : TGX_ST_FINAL_V_NONZERO;
     }
     if (tgx_stub::log_state().n_warn > 0) st |= TGX_ST_VGOALS_NOT_INCREASING;
     if (status) *status = st;

@@ -141,7 +141,7 @@ static int params_ok(const tgx_params* p) {
             if (!finite_pos(o->v_goals[i])) return 0;
         return 1;
     }
-    if (p->type == TGX_LINE) {
+    if (p->type == TGX_LINE || p->type == TGX_BOOMERANG) {
         const tgx_line_params* l = &p->u.line;
         for (int i = 0; i < 3; ++i)
             if (!isfinite(l->A[i]) || !isfinite(l->B[i])) return 0;
@@ -273,6 +273,97 @@ static int64_t line_generate(const tgx_params* p, sink_t* sk, uint32_t* status, 
     return sk->n;
 }
 
+/* Boomerang::generateTraj, Boomerang.cpp:31-141: Line's A -> B leg (without its "stopped" announcement), then the
+ * same profile back with negative speeds, ending forced at A. */
+static int64_t boomerang_generate(const tgx_params* p, sink_t* sk, uint32_t* status, tgx_phases* ph,
+                                  int64_t max_samples) {
+    const tgx_line_params* l = &p->u.line;
+    double g[TGX_NCHAN];
+    double theta = atan2(l->B[1] - l->A[1], l->B[0] - l->A[0]);   /* :24 */
+    double v = 0;
+    line_goal(p, l->A[0], l->A[1], v, 0, theta, g);               /* :40 */
+    sink_push(sk, g);
+    double v_goal = l->v_goal;
+    phase_add(ph, sk->n - 1, TGX_PH_ACCEL_TO, v_goal, 0.0);       /* :44 */
+    while (v < v_goal) {                                          /* :46 */
+        double v_new = std_min(v + l->a1 * p->dt, v_goal);
+        if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        v = v_new;
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, l->a1, theta, g);
+        sink_push(sk, g);
+    }
+    double t2 = orc_line_d2(p) / v_goal;                          /* :53 */
+    phase_add(ph, sk->n - 1, TGX_PH_REACHED, v_goal, t2);
+    double current_t_traj = 0;
+    while (current_t_traj < t2) {                                 /* :58 */
+        if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, 0, theta, g);
+        sink_push(sk, g);
+        double t_new = current_t_traj + p->dt;
+        if (t_new == current_t_traj) { *status |= TGX_ST_TOO_LONG; return -1; }
+        current_t_traj = t_new;
+    }
+    phase_add(ph, sk->n - 1, TGX_PH_DECEL, 0.0, 0.0);             /* :64 */
+    while (v > 0) {                                               /* :65 */
+        double v_new = std_max(v - l->a3 * p->dt, 0.0);
+        if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        v = v_new;
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, -l->a3, theta, g);
+        sink_push(sk, g);
+    }
+    double thresh = 0.05;                                         /* :71-79 */
+    if (fabs(l->B[0] - sk->last[TGX_PX]) > thresh || fabs(l->B[1] - sk->last[TGX_PY]) > thresh)
+        *status |= TGX_ST_LINE_END_NOT_B;
+    sk->last[TGX_PX] = l->B[0];                                   /* :81-82 */
+    sk->last[TGX_PY] = l->B[1];
+    if (sk->out && sk->n - 1 < sk->cap) {
+        sk->out[TGX_PX * sk->chan_stride + (sk->n - 1)] = l->B[0];
+        sk->out[TGX_PY * sk->chan_stride + (sk->n - 1)] = l->B[1];
+    }
+    /* ---- return leg, :85-134 ---- */
+    v = 0;
+    if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+    line_goal(p, l->B[0], l->B[1], -v, 0, theta, g);              /* :90 */
+    sink_push(sk, g);
+    phase_add(ph, sk->n - 1, TGX_PH_ACCEL_TO, v_goal, 0.0);       /* :94 */
+    while (fabs(v) < fabs(v_goal)) {                              /* :97 */
+        double v_new = std_max(v - l->a1 * p->dt, -v_goal);
+        if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        v = v_new;
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, -l->a1, theta, g);
+        sink_push(sk, g);
+    }
+    t2 = orc_line_d2(p) / v_goal;                                 /* :105 */
+    phase_add(ph, sk->n - 1, TGX_PH_REACHED, v_goal, t2);
+    current_t_traj = 0;
+    while (current_t_traj < t2) {                                 /* :110 */
+        if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, 0, theta, g);
+        sink_push(sk, g);
+        double t_new = current_t_traj + p->dt;
+        if (t_new == current_t_traj) { *status |= TGX_ST_TOO_LONG; return -1; }
+        current_t_traj = t_new;
+    }
+    phase_add(ph, sk->n - 1, TGX_PH_DECEL, 0.0, 0.0);             /* :116 */
+    while (v < 0) {                                               /* :117 */
+        double v_new = std_min(v + l->a3 * p->dt, 0.0);
+        if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        v = v_new;
+        line_goal(p, sk->last[TGX_PX], sk->last[TGX_PY], v, l->a3, theta, g);
+        sink_push(sk, g);
+    }
+    if (fabs(l->A[0] - sk->last[TGX_PX]) > thresh || fabs(l->A[1] - sk->last[TGX_PY]) > thresh)   /* :126-129 */
+        *status |= TGX_ST_LINE_END_NOT_B;
+    sk->last[TGX_PX] = l->A[0];                                   /* :131-132 */
+    sk->last[TGX_PY] = l->A[1];
+    if (sk->out && sk->n - 1 < sk->cap) {
+        sk->out[TGX_PX * sk->chan_stride + (sk->n - 1)] = l->A[0];
+        sk->out[TGX_PY * sk->chan_stride + (sk->n - 1)] = l->A[1];
+    }
+    phase_add(ph, sk->n - 1, TGX_PH_STOPPED, 0.0, 0.0);           /* :134 */
+    return sk->n;
+}
+
 int64_t orc_generate(const tgx_params* p, double* out, int64_t chan_stride, int64_t cap,
                      uint32_t* status, tgx_phases* ph, int64_t max_samples) {
     uint32_t st = 0;
@@ -284,6 +375,8 @@ int64_t orc_generate(const tgx_params* p, double* out, int64_t chan_stride, int6
         n = -1;
     } else if (p->type == TGX_LINE) {
         n = line_generate(p, &sk, &st, ph, max_samples);
+    } else if (p->type == TGX_BOOMERANG) {
+        n = boomerang_generate(p, &sk, &st, ph, max_samples);
     } else {
         n = orbit_generate(p, &sk, &st, ph, max_samples);
     }
@@ -307,8 +400,8 @@ int64_t orc_stop(const tgx_params* p, const double* from, double* out, int64_t c
     }
     /* 2D current (goal) vel: Circle.cpp:140-141, Line.cpp:124-125, Figure8.cpp:138-139 */
     double v = sqrt(pow(from[TGX_VX], 2) + pow(from[TGX_VY], 2));
-    if (p->type == TGX_LINE) {
-        /* Line::generateStopTraj, Line.cpp:117-152 */
+    if (p->type == TGX_LINE || p->type == TGX_BOOMERANG) {
+        /* Line::generateStopTraj, Line.cpp:117-152 (Boomerang.cpp:169-203 is a verbatim copy) */
         const tgx_line_params* l = &p->u.line;
         double theta = atan2(from[TGX_VY], from[TGX_VX]);         /* :126-127 */
         phase_add(ph, 0, TGX_PH_PRESSED_END, 0.0, 0.0);           /* :132 */
@@ -361,8 +454,8 @@ static int point_inside(const double box[6], double x, double y, double z) {
 }
 
 int orc_inside_bounds(const tgx_params* p, const double box[6]) {
-    if (p->type == TGX_LINE) {
-        /* Line::trajectoryInsideBounds, Line.cpp:154-173 */
+    if (p->type == TGX_LINE || p->type == TGX_BOOMERANG) {
+        /* Line::trajectoryInsideBounds, Line.cpp:154-173 (Boomerang.cpp:205-224 is a verbatim copy) */
         const tgx_line_params* l = &p->u.line;
         if (orc_line_d2(p) < 0) return 0;
         return point_inside(box, l->A[0], l->A[1], l->A[2]) && point_inside(box, l->B[0], l->B[1], l->B[2]);
@@ -440,7 +533,8 @@ static void* job_run(void* arg) {
                     !orc_inside_bounds(&j->p[i], j->limits->box)) {
                     st |= TGX_ST_OUTSIDE_BOUNDS;
                     /* Line::trajectoryInsideBounds reports "not feasible" when d2 < 0 (Line.cpp:165-168) */
-                    if (j->p[i].type == TGX_LINE && orc_line_d2(&j->p[i]) < 0) st |= TGX_ST_LINE_D2_NEGATIVE;
+                    if ((j->p[i].type == TGX_LINE || j->p[i].type == TGX_BOOMERANG) && orc_line_d2(&j->p[i]) < 0)
+                        st |= TGX_ST_LINE_D2_NEGATIVE;
                 }
                 if (j->limits && mv > j->limits->v_max) st |= TGX_ST_VMAX_EXCEEDED;
                 if (j->limits && ma > j->limits->a_max) st |= TGX_ST_AMAX_EXCEEDED;

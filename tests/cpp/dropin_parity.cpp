@@ -13,6 +13,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "trajectory_generator_ros2/trajectories/Boomerang.hpp"
 #include "trajectory_generator_ros2/trajectories/Circle.hpp"
 #include "trajectory_generator_ros2/trajectories/Figure8.hpp"
 #include "trajectory_generator_ros2/trajectories/Line.hpp"
@@ -142,6 +143,16 @@ int main() {
         runPair("default Line", r, g, 342);
         const Goal a = r.createLineGoal(0.3, -1.0, 0.8, 1.5, 0.7), b = g.createLineGoal(0.3, -1.0, 0.8, 1.5, 0.7);
         compareGoals("createLineGoal", {b}, {a});
+    }
+    {   // Line out and back
+        const Eigen::Vector3d A(0.0, -3.0, 1.8), B(0.0, 3.0, 1.8);
+        ref::Boomerang r(1.8, A, B, {1.0}, 1.5, 1.0, dt);
+        gpu::Boomerang g(1.8, A, B, {1.0}, 1.5, 1.0, dt);
+        runPair("default Boomerang", r, g, 1000);
+        const Eigen::Vector3d C(-4.25, -3.5, 1.0), D(4.5, 4.25, 1.0);
+        ref::Boomerang r2(1.0, C, D, {3.0}, 1.5, 1.0, dt);
+        gpu::Boomerang g2(1.0, C, D, {3.0}, 1.5, 1.0, dt);
+        runPair("diagonal Boomerang", r2, g2, 500);
     }
     {   // a Line that does not fit its bounds check (d2 < 0) must report false on both sides
         const Eigen::Vector3d A(0.0, -3.0, 1.8), B(0.0, -2.5, 1.8);

@@ -45,6 +45,10 @@ def cases():
     out.append(("line_diagonal_fast", abi.line_params(1.0, [-4.25, -3.5, 1.0], [4.5, 4.25, 1.0], [3.0], 1.5, 1.0, 0.01), 300))
     out.append(("line_quadrant3", abi.line_params(1.0, [1, 1, 1.0], [-2, 0.5, 1.0], [0.7], 0.9, 0.6, 0.01), 200))
     out.append(("line_z_differs", abi.line_params(1.0, [0, 0, 0.5], [0, 2, 2.5], [0.5], 1.0, 1.0, 0.02), 100))
+    out.append(("default_boomerang", abi.boomerang_params(1.8, [0, -3, 1.8], [0, 3, 1.8], [1.0], 1.5, 1.0, 0.01), 1000))
+    out.append(("boomerang_diagonal_fast", abi.boomerang_params(1.0, [-4.25, -3.5, 1.0], [4.5, 4.25, 1.0], [3.0], 1.5, 1.0, 0.01), 900))
+    out.append(("boomerang_quadrant3", abi.boomerang_params(1.0, [1, 1, 1.0], [-2, 0.5, 1.0], [0.7], 0.9, 0.6, 0.01), 700))
+    out.append(("boomerang_d2_negative", abi.boomerang_params(1.8, [0, -3, 1.8], [0, -2.5, 1.8], [1.0], 1.5, 1.0, 0.01), 50))
     c2 = workloads.circles_cfg2(8)
     for i in range(8):
         out.append((f"cfg2_circle_{i}", c2[i:i + 1].copy(), 500))

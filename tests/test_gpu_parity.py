@@ -237,6 +237,39 @@ def test_line_edge_cases(mode_engine, oracle):
     assert st[4] == abi.ST_LINE_END_NOT_B      # 3-D |B-A| with a 2-D motion: the cruise overshoots B in the plane
 
 
+def test_boomerang(mode_engine, oracle):
+    """Line out and back with negative return speeds (Boomerang.cpp:31-141)."""
+    engine = mode_engine
+    rng = np.random.default_rng(5)
+    recs = [abi.boomerang_params(1.8, [0, -3, 1.8], [0, 3, 1.8], [1.0], 1.5, 1.0, 0.01),
+            abi.boomerang_params(1.0, [-4.25, -3.5, 1.0], [4.5, 4.25, 1.0], [3.0], 1.5, 1.0, 0.01),
+            abi.boomerang_params(1.0, [1, 1, 1.0], [-2, 0.5, 1.0], [0.7], 0.9, 0.6, 0.01),
+            abi.boomerang_params(1.8, [0, -3, 1.8], [0, -2.5, 1.8], [1.0], 1.5, 1.0, 0.01)]    # d2 < 0: overshoots
+    for _ in range(60):
+        A, B = rng.uniform(-4, 4, 2), rng.uniform(-4, 4, 2)
+        recs.append(abi.boomerang_params(1.5, [A[0], A[1], 1.5], [B[0], B[1], 1.5], [rng.uniform(0.5, 2.0)],
+                                         rng.uniform(0.8, 2.0), rng.uniform(0.5, 1.5), 0.01))
+    params = abi.concat(recs)
+    out, counts, status, ph = gpu_generate(engine, params)
+    assert counts[0] == 1370 and status[0] == 0
+    assert sorted(abi.phases_to_index_msgs(abi.TGX_BOOMERANG, ph[0])) == [0, 67, 584, 685, 752, 1269, 1369]
+    # leg 1 ends forced at B, the return leg starts at B and ends forced at A
+    assert out[0, abi.PY, 684] == 3.0 and out[0, abi.PY, 685] == 3.0 and out[0, abi.PY, 1369] == -3.0
+    assert out[0, abi.VY, 1000] < 0 and out[0, abi.AY, 700] == -1.5 and out[0, abi.AY, 1300] == 1.0
+    assert status[3] == abi.ST_LINE_END_NOT_B
+    check_batch(engine, oracle, params, "boomerang")
+    # braking and the bounds check are Line's (Boomerang.cpp:169-224)
+    import torch
+    d = engine.upload_params(params[:3])
+    froms = np.stack([oracle.generate(params[i:i + 1])[0][:, 1000] for i in range(3)])
+    plan = engine.plan_stop(d, torch.from_numpy(froms).to(d.device))
+    for i in range(3):
+        assert int(plan.counts[i]) == oracle.stop(params[i:i + 1], froms[i])[0].shape[1]
+    c, st = engine.count(engine.upload_params(params[:4]), limits=abi.make_limits(box=(-5, 5, -5, 5, -5, 5)))
+    assert st.cpu().numpy().view(np.uint32).tolist() == [0, 0, 0, abi.ST_LINE_END_NOT_B | abi.ST_OUTSIDE_BOUNDS |
+                                                         abi.ST_LINE_D2_NEGATIVE]
+
+
 # ---- random batches -----------------------------------------------------------------------------------------
 
 def test_random_circles_cfg2(mode_engine, oracle):

@@ -13,8 +13,9 @@ GOLDEN = golden_util.load()
 def test_oracle_matches_reference_golden(oracle, case):
     p = case["params"]
     s, st, ph = oracle.generate(p)
-    assert s.shape[1] == case["n"]
     assert st == case["status"]
+    if not st & abi.ST_FATAL_MASK:
+        assert s.shape[1] == case["n"]
     if st & abi.ST_FATAL_MASK:
         # the reference calls exit(1) at this point (Line.cpp:76-79): what it had produced up to then is moot; the
         # engine and the oracle define the outcome as "all N samples, last one forced to B, status bit set"

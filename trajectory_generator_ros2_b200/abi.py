@@ -16,8 +16,9 @@ TGX_NCHAN = 14
 TGX_MAX_PHASES = 2 * TGX_MAX_VGOALS + 2
 
 # enum tgx_type
-TGX_CIRCLE, TGX_LINE, TGX_FIGURE8 = 0, 1, 2
-TYPE_NAMES = {TGX_CIRCLE: "Circle", TGX_LINE: "Line", TGX_FIGURE8: "Figure8"}
+TGX_CIRCLE, TGX_LINE, TGX_FIGURE8, TGX_BOOMERANG = 0, 1, 2, 3
+# prefix of the index_msgs texts; Boomerang.cpp announces itself as "Line traj: ..." (Boomerang.cpp:44,55,64,94,134)
+TYPE_NAMES = {TGX_CIRCLE: "Circle", TGX_LINE: "Line", TGX_FIGURE8: "Figure8", TGX_BOOMERANG: "Line"}
 
 # enum tgx_channel
 CHANNELS = ("px", "py", "pz", "vx", "vy", "vz", "ax", "ay", "az", "jx", "jy", "jz", "psi", "dpsi")
@@ -175,6 +176,13 @@ def line_params(alt, A, B, v_goals, a1, a3, dt) -> np.ndarray:
     p["B"][0, :] = B
     p["a1"], p["a3"] = a1, a3
     p["v_goal"] = list(v_goals)[0]
+    return p
+
+
+def boomerang_params(alt, A, B, v_goals, a1, a3, dt) -> np.ndarray:
+    """One Boomerang record from the reference constructor arguments (Boomerang.hpp:30-31)."""
+    p = line_params(alt, A, B, v_goals, a1, a3, dt)
+    p["type"] = TGX_BOOMERANG
     return p
 
 

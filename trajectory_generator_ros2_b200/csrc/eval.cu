@@ -215,7 +215,6 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
             // ---- Line::createLineGoal, Line.cpp:91-115 ------------------------------------------------
             const double c = s_rec.f[0], s = s_rec.f[1], theta = s_rec.f[2], alt = s_rec.f[3], dt = s_rec.f[4];
             const double cdt = c * dt, sdt = s * dt;
-            const bool force_b = (s_rec.type & kRecForceB) != 0;
             double v[SPT], acc[SPT], py[SPT];
 #pragma unroll
             for (int u = 0; u < SPT; ++u) {
@@ -225,9 +224,9 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
                 acc[u] = (q.j == 0) ? 0.0 : sg.acc;   // sample 0 is createLineGoal(A.x, A.y, 0, accel = 0, theta) (:40)
                 // S = sum of v over the segment's steps so far; p = p_base + S * (c|s) * dt   (:97-98)
                 const double S = fma(sg.dv, q.tri, q.fj * sg.vb) + (q.clamp ? sg.vclamp : 0.0);
-                const bool fb = force_b && (k0 + u == n - 1);                  // last goal forced to B (:81-82)
-                o[u] = fb ? s_rec.f[5] : fma(S, cdt, sg.s0);
-                py[u] = fb ? s_rec.f[6] : fma(S, sdt, sg.s1);
+                const bool fb = (sg.flags & kSegForcePos) != 0;                // a leg's last goal, forced to B / A
+                o[u] = fb ? sg.s0 : fma(S, cdt, sg.s0);
+                py[u] = fb ? sg.s1 : fma(S, sdt, sg.s1);
             }
             TGX_STORE(TGX_PX, o);
             TGX_STORE(TGX_PY, py);

@@ -43,7 +43,7 @@ __device__ bool params_ok(const tgx_params& p) {
             if (!finite_pos(o.v_goals[i])) return false;
         return true;
     }
-    if (p.type == TGX_LINE) {
+    if (p.type == TGX_LINE || p.type == TGX_BOOMERANG) {
         const tgx_line_params& l = p.u.line;
         for (int i = 0; i < 3; ++i)
             if (!isfinite(l.A[i]) || !isfinite(l.B[i])) return false;
@@ -51,6 +51,8 @@ __device__ bool params_ok(const tgx_params& p) {
     }
     return false;
 }
+
+__device__ __forceinline__ bool is_line_like(int type) { return type == TGX_LINE || type == TGX_BOOMERANG; }
 
 // Collects what a replay produces.  In counting mode (segs == nullptr) it only counts.
 struct Emitter {
@@ -112,10 +114,10 @@ struct Emitter {
         cur.acc = acc;
     }
     // `last_state`: orbit only, the exactly replayed theta at sample k_last.
-    __device__ void close(int k_last, bool clamp_last, double last_state) {
+    __device__ void close(int k_last, bool clamp_last, double last_state, int extra_flags = 0) {
         if (segs && nseg < seg_cap) {
             cur.n = k_last - cur.kb;
-            cur.flags = clamp_last ? kSegClampLast : 0;
+            cur.flags = (clamp_last ? kSegClampLast : 0) | extra_flags;
             if (orbit) cur.acc = last_state;
             segs[nseg] = cur;
         }
@@ -171,23 +173,48 @@ __device__ __forceinline__ long long regular_run(double x0, double x1, double a)
 // is advanced in exact jumps (the step COUNT and every v_k stay bit-identical to the reference), and the class
 // state is advanced in closed form over each jump, s += c * sum(v): it then differs from the reference's running
 // sum by that sum's own accumulated rounding, at most a few hundred half-ulps of theta (~1e-13 rad).
+//
+// v is the speed MAGNITUDE; sgn = -1 replays a Boomerang's return leg, whose speeds are the exact negatives
+// (v = max(v - a*dt, -v_goal), Boomerang.cpp:97-101: round-to-nearest is symmetric).  The segment records, STEP and
+// the coefficients c0 / c1 carry the sign.  force_xy (lines): the step on which the clamp fires ends a leg; the
+// reference then overwrites that sample's position (Line.cpp:81-82), so it becomes a one-sample segment of its own
+// holding the forced position.
 template <bool UP, bool XR, bool TRACK0, bool TRACK1, class Step>
 __device__ __forceinline__ bool ramp(double& v, double target, double adt, double dtr, int& k,
                                      int64_t max_samples, int tmask, Emitter& E, double acc, double& s0,
-                                     double& s1, double c0, double c1, Step step) {
+                                     double& s1, double c0, double c1, Step step, double sgn = 1.0,
+                                     const double* force_xy = nullptr) {
     bool open = false;
     const double clampv = UP ? target : 0.0;
     while (UP ? (v < target) : (v > 0.0)) {
         const double vn = UP ? std_min(dadd(v, adt), target) : std_max(dsub(v, adt), 0.0);
         if (vn == v || (int64_t)k + 1 >= max_samples) return false;
+        if (force_xy && vn == clampv) {
+            // the leg's last step: its own segment, position forced
+            if (open) {
+                E.close(k, false, s0);
+                open = false;
+            }
+            E.open(k, sgn * vn, 0.0, sgn * vn, force_xy[0], force_xy[1], acc);
+            v = vn;
+            if (XR) {
+                step(sgn * v);
+            } else {
+                if (TRACK0) s0 = fma(c0, v, s0);
+                if (TRACK1) s1 = fma(c1, v, s1);
+            }
+            ++k;
+            E.close(k, false, s0, kSegForcePos);
+            break;
+        }
         if (!open) {
             // orbit: Seg.s1 = theta increment per step at the base speed, (vb/r)*dt up to rounding
-            E.open(k, v, UP ? adt : -adt, clampv, s0, E.orbit ? dmul(v, dtr) : s1, acc);
+            E.open(k, sgn * v, sgn * (UP ? adt : -adt), sgn * clampv, s0, E.orbit ? dmul(v, dtr) : s1, acc);
             open = true;
         }
         if (XR) {
             v = vn;
-            step(v);
+            step(sgn * v);
             ++k;
             // k is the last sample of its tile (segments never straddle tiles), or the ramp chunk is full (bounds
             // the rounding drift of the closed form against the reference's running sums)
@@ -482,48 +509,67 @@ __device__ double line_d2(const tgx_line_params& l) {
     return dsub(dsub(d, d1), d3);
 }
 
-// Line::Line (theta_, Line.cpp:24) + Line::generateTraj (Line.cpp:31-89).
+// Line::Line (theta_, Line.cpp:24) + Line::generateTraj (Line.cpp:31-89); with `boomerang` the same profile is flown
+// back from B to A with negative speeds (Boomerang::generateTraj, Boomerang.cpp:31-141).
 template <bool XR>
 __device__ int replay_line(const tgx_params& p, int64_t max_samples, Emitter& E, uint32_t& st, double& theta,
-                           double& c, double& s, const CurTable* __restrict__ tab) {
+                           double& c, double& s, const CurTable* __restrict__ tab, bool boomerang) {
     const tgx_line_params& l = p.u.line;
     const double dt = p.dt;
     const int tmask = (1 << E.tile_shift) - 1;
     theta = atan2(dsub(l.B[1], l.A[1]), dsub(l.B[0], l.A[0]));   // :24
     sincos(theta, &s, &c);                                       // :93-94 (same value on every call)
     const double cc = c, ss = s;
-    double v = 0.0;
-    // sample 0: createLineGoal(A.x, A.y, 0, 0, theta)  (:40, :97-98)
-    double x = dadd(l.A[0], dmul(dmul(v, cc), dt));
-    double y = dadd(l.A[1], dmul(dmul(v, ss), dt));
-    int k = 0;
+    const double cdt = dmul(cc, dt), sdt = dmul(ss, dt);
+    const double vg = l.v_goal;                                  // :43
+    const double t2 = ddiv(line_d2(l), vg);                      // :53 (a negative d2 simply skips the cruise loop)
+    double x = 0.0, y = 0.0;
     auto step = [&](double vnew) {                               // p = goals.back().p + v*c*dt  (:49, :97-98)
         x = dadd(x, dmul(dmul(vnew, cc), dt));
         y = dadd(y, dmul(dmul(vnew, ss), dt));
     };
-    const double vg = l.v_goal;                                  // :43
-    E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                        // :44
-    const double cdt = dmul(cc, dt), sdt = dmul(ss, dt);
-    if (!ramp<true, XR, true, true>(v, vg, dmul(l.a1, dt), 0.0, k, max_samples, tmask, E, l.a1, x, y, cdt, sdt,
-                                    step)) {                                                   // :46-50
-        st |= TGX_ST_TOO_LONG;
-        return -1;
+    int k = 0;
+    for (int leg = 0; leg < (boomerang ? 2 : 1); ++leg) {
+        const double sgn = leg == 0 ? 1.0 : -1.0;
+        const double* from = leg == 0 ? l.A : l.B;
+        const double* to = leg == 0 ? l.B : l.A;
+        double v = 0.0;
+        // the leg's first sample: createLineGoal(from.x, from.y, +-0, 0, theta)  (:40, Boomerang.cpp:90)
+        x = dadd(from[0], dmul(dmul(sgn * v, cc), dt));
+        y = dadd(from[1], dmul(dmul(sgn * v, ss), dt));
+        if (leg == 1) {
+            // sample 0 of the plan is served by the first ramp segment (j = 0); the return leg's first sample needs
+            // a segment of its own, one step of speed -0 from B
+            if ((int64_t)k + 1 >= max_samples) {
+                st |= TGX_ST_TOO_LONG;
+                return -1;
+            }
+            E.open(k, sgn * v, 0.0, sgn * v, from[0], from[1], 0.0);
+            ++k;
+            E.close(k, false, 0.0);
+        }
+        E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                    // :44
+        if (!ramp<true, XR, true, true>(v, vg, dmul(l.a1, dt), 0.0, k, max_samples, tmask, E, sgn * l.a1, x, y,
+                                        sgn * cdt, sgn * sdt, step, sgn)) {                    // :46-50
+            st |= TGX_ST_TOO_LONG;
+            return -1;
+        }
+        E.phase(k, TGX_PH_REACHED, vg, t2);                      // :55-56
+        if (!hold<true, true, false>(sgn * v, t2, dt, k, max_samples, tmask, E, x, y, dmul(dmul(sgn * v, cc), dt),
+                                     dmul(dmul(sgn * v, ss), dt), tab)) {                    // :57-62
+            st |= TGX_ST_TOO_LONG;
+            return -1;
+        }
+        E.phase(k, TGX_PH_DECEL, 0.0, 0.0);                      // :64
+        if (!ramp<false, XR, true, true>(v, 0.0, dmul(l.a3, dt), 0.0, k, max_samples, tmask, E, -sgn * l.a3, x, y,
+                                         sgn * cdt, sgn * sdt, step, sgn, to)) {               // :65-68, forced :81-82
+            st |= TGX_ST_TOO_LONG;
+            return -1;
+        }
+        // :71-79 / Boomerang.cpp:126-129 (exit(1) in the reference), checked on the replayed, not the forced, position
+        if (fabs(dsub(to[0], x)) > 0.05 || fabs(dsub(to[1], y)) > 0.05) st |= TGX_ST_LINE_END_NOT_B;
     }
-    const double t2 = ddiv(line_d2(l), vg);                      // :53 (a negative d2 simply skips the cruise loop)
-    E.phase(k, TGX_PH_REACHED, vg, t2);                          // :55-56
-    if (!hold<true, true, false>(v, t2, dt, k, max_samples, tmask, E, x, y, dmul(dmul(v, cc), dt),
-                                 dmul(dmul(v, ss), dt), tab)) {                              // :57-62
-        st |= TGX_ST_TOO_LONG;
-        return -1;
-    }
-    E.phase(k, TGX_PH_DECEL, 0.0, 0.0);                          // :64
-    if (!ramp<false, XR, true, true>(v, 0.0, dmul(l.a3, dt), 0.0, k, max_samples, tmask, E, -l.a3, x, y, cdt, sdt,
-                                     step)) {                                                  // :65-68
-        st |= TGX_ST_TOO_LONG;
-        return -1;
-    }
-    if (fabs(dsub(l.B[0], x)) > 0.05 || fabs(dsub(l.B[1], y)) > 0.05) st |= TGX_ST_LINE_END_NOT_B;   // :71-79
-    E.phase(k, TGX_PH_STOPPED, 0.0, 0.0);                        // :84
+    E.phase(k, TGX_PH_STOPPED, 0.0, 0.0);                        // :84, Boomerang.cpp:134
     return k + 1;
 }
 
@@ -537,7 +583,7 @@ __device__ bool point_inside(const double* box, double x, double y, double z) {
 
 // trajectoryInsideBounds: Circle.cpp:171-179, Figure8.cpp:169-177, Line.cpp:154-173.
 __device__ bool inside_bounds(const tgx_params& p, const double* box) {
-    if (p.type == TGX_LINE) {
+    if (is_line_like(p.type)) {
         const tgx_line_params& l = p.u.line;
         if (line_d2(l) < 0.0) return false;
         return point_inside(box, l.A[0], l.A[1], l.A[2]) && point_inside(box, l.B[0], l.B[1], l.B[2]);
@@ -565,13 +611,15 @@ __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_
     } else {
         int n;
         double theta = 0.0, c = 1.0, s = 0.0;
-        if (p.type == TGX_LINE) n = replay_line<XR>(p, max_samples, E, r.status, theta, c, s, tab);
-        else n = replay_orbit<STATE, XR>(p, max_samples, E, r.status, tab);
+        if (is_line_like(p.type))
+            n = replay_line<XR>(p, max_samples, E, r.status, theta, c, s, tab, p.type == TGX_BOOMERANG);
+        else
+            n = replay_orbit<STATE, XR>(p, max_samples, E, r.status, tab);
         E.finish();
         if (lim && lim->check_box && !inside_bounds(p, lim->box)) {
             r.status |= TGX_ST_OUTSIDE_BOUNDS;
             // Line::trajectoryInsideBounds reports "not feasible" when d2 < 0 (Line.cpp:165-168)
-            if (p.type == TGX_LINE && line_d2(p.u.line) < 0.0) r.status |= TGX_ST_LINE_D2_NEGATIVE;
+            if (is_line_like(p.type) && line_d2(p.u.line) < 0.0) r.status |= TGX_ST_LINE_D2_NEGATIVE;
         }
         if (n > 0) {
             r.n = n;
@@ -581,10 +629,10 @@ __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_
         if (FILL && rec) {
             TrajRec t;
             t.n = r.n;
-            if (p.type == TGX_LINE) {
-                t.type = TGX_LINE | kRecForceB;
+            if (is_line_like(p.type)) {
+                t.type = TGX_LINE;
                 t.f[0] = c; t.f[1] = s; t.f[2] = theta; t.f[3] = p.alt; t.f[4] = p.dt;
-                t.f[5] = p.u.line.B[0]; t.f[6] = p.u.line.B[1];
+                t.f[5] = 0.0; t.f[6] = 0.0;
             } else {
                 const tgx_orbit_params& o = p.u.orbit;
                 t.type = p.type;
@@ -625,9 +673,9 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
         int k = -1;
         bool ok = true;
         E.phase(0, TGX_PH_PRESSED_END, 0.0, 0.0);                 // Circle.cpp:148, Line.cpp:132
-        if (p.type == TGX_LINE) {
+        if (is_line_like(p.type)) {
             const tgx_line_params& l = p.u.line;
-            const double theta = atan2(from[TGX_VY], from[TGX_VX]);   // Line.cpp:126-127
+            const double theta = atan2(from[TGX_VY], from[TGX_VX]);   // Line.cpp:126-127, Boomerang.cpp:178-179
             double s, c;
             sincos(theta, &s, &c);
             double x = from[TGX_PX], y = from[TGX_PY];
@@ -731,7 +779,7 @@ plan_count_kernel(const tgx_params* __restrict__ params, const double* __restric
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const tgx_params p = load_params(params, i);
-    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, nullptr, p.type != TGX_LINE, 0x7fffffff, 0x7fffffff};
+    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, nullptr, !is_line_like(p.type), 0x7fffffff, 0x7fffffff};
     PlanOut r;
     if (stop_from) {
         double from[TGX_NCHAN];
@@ -774,7 +822,7 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
     TrajRec* rec_out = recs + i;
     Tile* tile_out = tiles + to;
     Emitter E{tile_shift, (int32_t)i, keep ? segs + so : nullptr, keep ? tile_out : nullptr, (int32_t)so,
-              phases ? phases + i : nullptr, p.type != TGX_LINE, slab ? seg_slab : 0x7fffffff,
+              phases ? phases + i : nullptr, !is_line_like(p.type), slab ? seg_slab : 0x7fffffff,
               slab ? tile_slab : 0x7fffffff};
     PlanOut r;
     if (stop_from) {
@@ -823,7 +871,7 @@ plan_samples_kernel(const tgx_params* __restrict__ params, const double* __restr
     t.n = 1;
     for (int q = 0; q < 7; ++q) t.f[q] = 0.0;
     const bool ok = params_ok(p);
-    if (p.type == TGX_LINE) {
+    if (is_line_like(p.type)) {
         const double theta = p.u.line.reserved[0];
         double sn, cs;
         sincos(theta, &sn, &cs);

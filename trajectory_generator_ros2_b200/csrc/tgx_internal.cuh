@@ -21,21 +21,23 @@
 
 namespace tgx {
 
-// type field of TrajRec: low byte = tgx_type, bit 8 = "force the last sample's position to B" (Line.cpp:81-82;
-// not set for braking trajectories, Line.cpp:117-152).
+// type field of TrajRec: low byte = the evaluation formula (TGX_CIRCLE, TGX_LINE, TGX_FIGURE8; a Boomerang is planned
+// as a TGX_LINE whose return leg has negative speeds).
 constexpr int32_t kRecTypeMask = 0xff;
-constexpr int32_t kRecForceB = 1 << 8;
 
 struct __align__(16) TrajRec {
     int32_t type;
     int32_t n;        // sample count (0: rejected / empty)
     double f[7];
     // orbit (Circle, Figure8): f0 = r, f1 = cx, f2 = cy, f3 = alt, f4 = dt / r, f5 = 1 / r
-    // line:                    f0 = cos(theta), f1 = sin(theta), f2 = theta, f3 = alt, f4 = dt, f5 = Bx, f6 = By
+    // line:                    f0 = cos(theta), f1 = sin(theta), f2 = theta, f3 = alt, f4 = dt
 };
 static_assert(sizeof(TrajRec) == 64, "TrajRec must be 64 bytes");
 
 constexpr int32_t kSegClampLast = 1;   // sample kb+n has v == vclamp exactly (the std::min / std::max clamp fired)
+constexpr int32_t kSegForcePos = 2;    // line: a one-sample segment whose position is (s0, s1) itself: the reference
+                                       // overwrites a leg's last position with B / A (Line.cpp:81-82,
+                                       // Boomerang.cpp:81-82,131-132)
 
 struct __align__(16) Seg {
     int32_t kb;       // base sample index; the segment covers samples kb+1 .. kb+n (j = k - kb in 1..n);

@@ -155,7 +155,7 @@ void GpuTrajectory::generateTraj(std::vector<Goal>& goals, std::unordered_map<in
         RCLCPP_ERROR(logger_, "Error: final velocity is not zero");
         std::exit(1);
     }
-    if (status & TGX_ST_LINE_END_NOT_B) {        // Line.cpp:76-79
+    if (status & TGX_ST_LINE_END_NOT_B) {        // Line.cpp:76-79 (Boomerang.cpp:76-79, 126-129: "... is not A")
         RCLCPP_ERROR(logger_, "Error: final point is not B");
         std::exit(1);
     }
@@ -239,12 +239,12 @@ Goal Figure8::createFigure8Goal(double v, double accel, double theta) const {
 }
 
 namespace {
-tgx_params lineParams(double alt, const Eigen::Vector3d& A, const Eigen::Vector3d& B,
+tgx_params lineParams(int type, double alt, const Eigen::Vector3d& A, const Eigen::Vector3d& B,
                       const std::vector<double>& v_goals, double a1, double a3, double dt) {
     if (v_goals.empty()) throw std::invalid_argument("tgx: Line needs v_goals[0]");
     tgx_params p;
     std::memset(&p, 0, sizeof(p));
-    p.type = TGX_LINE;
+    p.type = type;
     p.n_vgoals = 1;
     p.dt = dt;
     p.alt = alt;
@@ -259,16 +259,32 @@ tgx_params lineParams(double alt, const Eigen::Vector3d& A, const Eigen::Vector3
 
 Line::Line(double alt, Eigen::Vector3d A, Eigen::Vector3d B, std::vector<double> v_goals, double a1, double a3,
            double dt)
-    : GpuTrajectory(lineParams(alt, A, B, v_goals, a1, a3, dt), "Line", "line_logger") {}
+    : GpuTrajectory(lineParams(TGX_LINE, alt, A, B, v_goals, a1, a3, dt), "Line", "line_logger") {}
 
-Goal Line::createLineGoal(double last_x, double last_y, double v, double accel, double theta) const {
+namespace {
+Goal lineGoal(const tgx_params& params, const rclcpp::Logger& logger, double last_x, double last_y, double v,
+              double accel, double theta) {
     // the line's own heading lives in the plan; an explicit theta is passed through the state slot of the call
     double out[TGX_NCHAN];
-    tgx_params p = params_;
+    tgx_params p = params;
     p.u.line.reserved[0] = theta;                // tgx_sample_host reads the explicit heading here for lines
     const int rc = tgx_sample_host(sharedEngine(), &p, v, accel, last_x, last_y, out);
-    if (rc != TGX_OK) die(logger_, "tgx_sample_host", rc);
+    if (rc != TGX_OK) die(logger, "tgx_sample_host", rc);
     return goalFromPlanes(out, 1, 0);
+}
+}  // namespace
+
+Goal Line::createLineGoal(double last_x, double last_y, double v, double accel, double theta) const {
+    return lineGoal(params_, logger_, last_x, last_y, v, accel, theta);
+}
+
+// Boomerang.cpp announces itself with Line's texts and logger ("Line traj: ...", "line_logger", Boomerang.hpp:63).
+Boomerang::Boomerang(double alt, Eigen::Vector3d A, Eigen::Vector3d B, std::vector<double> v_goals, double a1,
+                     double a3, double dt)
+    : GpuTrajectory(lineParams(TGX_BOOMERANG, alt, A, B, v_goals, a1, a3, dt), "Line", "line_logger") {}
+
+Goal Boomerang::createLineGoal(double last_x, double last_y, double v, double accel, double theta) const {
+    return lineGoal(params_, logger_, last_x, last_y, v, accel, theta);
 }
 
 }  // namespace TGX_DROPIN_NAMESPACE

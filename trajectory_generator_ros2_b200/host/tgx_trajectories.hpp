@@ -1,4 +1,4 @@
-// tgx_trajectories.hpp — C++ host side of the drop-in: GPU-backed Circle / Line / Figure8.
+// tgx_trajectories.hpp — C++ host side of the drop-in: GPU-backed Circle / Line / Figure8 / Boomerang.
 //
 // These classes keep the reference's interface — the constructor argument lists of Circle.hpp:30-31,
 // Line.hpp:30-31 and Figure8.hpp:30-31 and the three overrides of the abstract Trajectory interface
@@ -78,6 +78,15 @@ class Line : public GpuTrajectory {
 public:
     Line(double alt, Eigen::Vector3d A, Eigen::Vector3d B,
          std::vector<double> v_goals, double a1, double a3, double dt);
+    snapstack_msgs2::msg::Goal createLineGoal(double last_x, double last_y,
+                                              double v, double accel, double theta) const;
+};
+
+// Line out and back (Boomerang.hpp:30-31); announces itself as "Line traj: ..." like the reference does.
+class Boomerang : public GpuTrajectory {
+public:
+    Boomerang(double alt, Eigen::Vector3d A, Eigen::Vector3d B,
+              std::vector<double> v_goals, double a1, double a3, double dt);
     snapstack_msgs2::msg::Goal createLineGoal(double last_x, double last_y,
                                               double v, double accel, double theta) const;
 };

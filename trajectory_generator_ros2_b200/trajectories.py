@@ -161,3 +161,11 @@ class Line(Trajectory):
         raw = p.view(np.float64).reshape(-1, 16)
         raw[0, 12] = theta                                    # tgx_line_params.reserved[0]: the explicit heading
         return Goal.from_channels(self.engine.sample_host(p, v, accel, last_x, last_y))
+
+
+class Boomerang(Line):
+    """Line out and back (Boomerang.hpp:30-31); its announcements read "Line traj: ..." like the reference's."""
+    shape = "Line"
+
+    def __init__(self, alt, A, B, v_goals, a1, a3, dt, engine: Optional[Engine] = None):
+        Trajectory.__init__(self, abi.boomerang_params(alt, A, B, v_goals, a1, a3, dt), engine)
