@@ -378,6 +378,23 @@ def run_ours(args):
                "d2h_bytes_per_step": int(n * 17), "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
                "call": "H2D params, tgx_plan + tgx_feasibility, D2H flags + max_v + max_a"}
 
+    gather_ms = None
+    if feas_only and world > 1:
+        # BASELINE configs[4]: the only exchange of the path, an all-gather of the 1-byte feasibility flags (NCCL)
+        from trajectory_generator_ros2_b200 import sharding
+        local = torch.cat(flags)
+        for _ in range(2):
+            sharding.gather_flags(local, world * n)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        full = sharding.gather_flags(local, world * n)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = float(t[0])
+        assert full.numel() == world * n
     if rank == 0:
         peak, peak_src = measured_peak()
         eval_bytes = BYTES_PER_SAMPLE * total_samples if not feas_only else 17 * n
@@ -413,6 +430,11 @@ def run_ours(args):
                          "peak_source": peak_src + " — of measured" if "MEASURED" in peak_src else peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        if feas_only:
+            line["config"]["feasible_fraction"] = float(torch.cat(flags).float().mean())
+            line["config"]["flags_allgather_ms"] = gather_ms
+            line["roofline"]["note"] = ("reduction-only path: writes 17 B per trajectory, FP64-pipe- and issue-bound, "
+                                        "the HBM fraction is stated for information only")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
