@@ -199,6 +199,13 @@ int tgx_set_plan_mode(tgx_engine* e, int exact_ramps);
  * a batch, later plans give every trajectory a fixed slice of the tables and need no counting pass and no scans; a
  * batch that does not fit falls back to the two-replay exact-offset path automatically.  allow = 0 disables it. */
 int tgx_set_slab_planning(tgx_engine* e, int allow);
+/* Phase planning (default on): a batch of Circle / Figure8 trajectories of at most 4096 samples each is planned by a
+ * counting replay only (80 bytes per trajectory: where each phase starts) and the evaluation kernel derives its
+ * segments from the caller's parameter array in closed form, which removes most table reads from the store-bound
+ * kernel.  d_params must then stay valid and unchanged until the last tgx_eval / tgx_feasibility of that plan.
+ * Engaged automatically after a plan has seen such a batch; anything else falls back to segment tables. */
+int tgx_set_phase_planning(tgx_engine* e, int allow);
+int64_t tgx_phase_plan_count(const tgx_engine* e);
 /* How many plans so far took the single-replay / the two-replay path (either pointer may be NULL). */
 int tgx_plan_path_counts(const tgx_engine* e, int64_t* slab_plans, int64_t* exact_plans);
 /* Bytes of device scratch currently held by the engine (plan tables). */

@@ -547,6 +547,7 @@ def test_slab_planning_matches_exact_offsets_and_falls_back(engine, oracle):
     must be bit-identical to the two-replay path, and a batch that does not fit its slices must fall back."""
     import torch
     params = workloads.circles_cfg2(5000)
+    engine.set_phase_planning(False)      # this test is about the segment-table paths
     engine.set_slab_planning(False)
     base, counts, status, _ = gpu_generate(engine, params, capacity=1024, want_phases=False)
     engine.set_slab_planning(True)
@@ -582,6 +583,73 @@ def test_slab_planning_matches_exact_offsets_and_falls_back(engine, oracle):
     gpu_generate(engine, mixed, want_phases=False)
     s4, e4 = engine.plan_path_counts()
     assert (s4 - s3, e4 - e3) == (0, 1)
+    engine.set_phase_planning(True)
+
+
+def test_phase_planning(engine, oracle):
+    """Batches of short orbits are planned by a counting replay only and evaluated from the parameter records."""
+    engine.set_phase_planning(True)
+    rng = np.random.default_rng(11)
+    recs = [workloads.circles_cfg2(3000)]
+    # Figure8s, several goal speeds (K up to 8), repeated / decreasing goals, zero-length holds, two-tile trajectories
+    recs.append(workloads.circles_cfg2(500, seed=77))
+    recs[-1]["type"] = abi.TGX_FIGURE8
+    for K in (2, 3, 5, 8):
+        for _ in range(6):
+            v = np.sort(rng.uniform(0.3, 2.5, K))
+            if rng.random() < 0.3:
+                v = v[::-1].copy()                       # decreasing: warnings, skipped ramps
+            kind = abi.TGX_CIRCLE if rng.random() < 0.5 else abi.TGX_FIGURE8
+            recs.append(abi.circle_params(1.5, rng.uniform(0.5, 4), 0.3, -0.2, list(v), rng.uniform(0.0, 0.25),
+                                          rng.uniform(1.0, 2.0), 0.01, kind=kind))       # N <= 1024: one tile each
+    params = abi.concat(recs)
+    p0 = engine.phase_plan_count
+    first, c1, st1, _ = gpu_generate(engine, params, want_phases=False)          # learns (segment tables)
+    p1 = engine.phase_plan_count
+    out, counts, status, ph = gpu_generate(engine, params, want_phases=True)     # phase plan
+    p2 = engine.phase_plan_count
+    assert p2 - p1 == 1, "second plan of an all-orbit batch of short trajectories should be a phase plan"
+    o_counts, o_status = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts, o_counts)
+    np.testing.assert_array_equal(status, o_status)
+    m = ~np.isnan(first)
+    assert (np.isnan(out) == np.isnan(first)).all()
+    np.testing.assert_allclose(out[m], first[m], rtol=0, atol=1e-10)             # same samples as the table path
+    worst = {}
+    for i in list(range(0, 3000, 97)) + list(range(3000, len(params))):
+        ref, _, oph = oracle.generate(params[i:i + 1])
+        merge_errors(worst, assert_samples_close(out[i, :, :counts[i]], ref, f"phase[{i}]"))
+        t = int(params["type"][i])
+        assert abi.phases_to_index_msgs(t, ph[i]) == abi.phases_to_index_msgs(t, oph)
+    assert worst["pos_abs"] < 1e-10, worst
+    # feasibility runs on a phase plan too
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    d = engine.upload_params(params)
+    engine.plan(d, limits=lim)
+    assert engine.phase_plan_count - p2 == 1
+    flags, mv, ma, st = engine.feasibility(lim, len(params))
+    o_flags, o_mv, o_ma, _, o_st = oracle.feasibility_batch(params, lim)
+    np.testing.assert_allclose(mv.cpu().numpy(), o_mv, rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(ma.cpu().numpy(), o_ma, rtol=1e-8, atol=1e-14)
+    # trajectories of two and three tiles: every tile is its own CTA of the phase plan
+    long_ones = abi.concat([abi.circle_params(1.0, rng.uniform(1, 3), 0, 0, [rng.uniform(0.8, 1.5)],
+                                              rng.uniform(15.0, 25.0), 0.5, 0.01) for _ in range(40)])
+    gpu_generate(engine, long_ones, want_phases=False)
+    p3 = engine.phase_plan_count
+    out3, c3, st3, _ = gpu_generate(engine, long_ones, want_phases=False)
+    assert engine.phase_plan_count - p3 == 1 and c3.min() > 1024 and c3.max() > 2048
+    for i in range(0, 40, 7):
+        ref, _, _ = oracle.generate(long_ones[i:i + 1])
+        assert_samples_close(out3[i, :, :c3[i]], ref, f"phase long[{i}]")
+    p2 = engine.phase_plan_count
+    # a batch with a line, or with a long trajectory, falls back to segment tables on its own
+    mixed = abi.concat([params[:50], workloads.default_line(), workloads.default_circle()])
+    out2, c2, st2, _ = gpu_generate(engine, mixed, want_phases=False)
+    assert engine.phase_plan_count == p2, "a batch with a line and a 25-tile circle must not take the phase path"
+    o_counts, o_status = oracle.count_batch(mixed)
+    np.testing.assert_array_equal(c2, o_counts)
+    ref, _, _ = oracle.generate(mixed[50:51])
+    assert_samples_close(out2[50, :, :685], ref, "line after phase fallback")
 
 
 def test_hold_table_handles_mixed_dt(engine, oracle):

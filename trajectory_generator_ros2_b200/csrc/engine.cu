@@ -36,6 +36,10 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
                              int seg_slab, int tile_slab, TrajRec* recs, Seg* segs, Tile* tiles, int32_t* counts,
                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
                              PlanStats* stats, cudaStream_t stream);
+cudaError_t launch_plan_phase(const tgx_params* params, int64_t n, const tgx_limits* lim, int64_t max_samples,
+                              int tile_shift, int max_n, const void* cur_table, PhaseRec* phase, int32_t* counts,
+                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
+                              PlanStats* stats, cudaStream_t stream);
 cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int spt, const OutView& out, bool store,
                         double* max_v, double* max_a, cudaStream_t stream);
 cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, const double* max_v,
@@ -161,9 +165,15 @@ struct tgx_engine {
 
     // per-trajectory scratch (capacity in trajectories)
     DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals, cur_table, stats;
-    // tables (exact-offset plans) and packets (slab plans)
-    DevBuf segs, tiles, packets;
-    bool plan_packed = false;
+    // tables
+    DevBuf segs, tiles, packets, phase;
+    bool plan_packed = false;                    // current plan is a slab plan
+    bool plan_phase = false;                     // current plan is a phase plan
+    const tgx_params* plan_params = nullptr;     // phase plans read the caller's parameter array during evaluation
+    bool allow_phase = true;
+    bool phase_ready = false;
+    int phase_tile_slab = 0;
+    int64_t phase_plans = 0;
     PinBuf h_totals;
 
     // current plan
@@ -184,7 +194,11 @@ tgx::TableView table_view(const tgx_engine* e) {
     tv.recs = e->recs.as<tgx::TrajRec>();
     tv.segs = e->segs.as<tgx::Seg>();
     tv.tiles = e->tiles.as<tgx::Tile>();
-    if (e->plan_packed) {
+    if (e->plan_phase) {
+        tv.params = e->plan_params;
+        tv.phase = e->phase.as<tgx::PhaseRec>();
+        tv.tile_slab = e->tile_slab_plan;
+    } else if (e->plan_packed) {
         tv.seg_slab = e->seg_slab_plan;
         tv.tile_slab = e->tile_slab_plan;
     }
@@ -245,9 +259,41 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
 
     int64_t tot_samples = 0, tot_segs = 0, tot_tiles = 0;
     bool done = false;
+    e->plan_phase = false;
+    e->plan_params = nullptr;
+
+    // ---- phase mode: batches of short orbits.  One counting replay (no angle state, no tables): the evaluation
+    //      kernel derives its segments from the caller's parameter array, which must stay valid until tgx_eval ----
+    if (e->allow_phase && e->phase_ready && !e->exact_ramps && !d_stop_from) {
+        const int64_t need_tiles = n * (int64_t)e->phase_tile_slab;
+        if (need_tiles <= 0x7fffffffLL) {
+            if ((rc = e->phase.reserve((size_t)n * sizeof(tgx::PhaseRec)))) return rc;
+            const int max_n = std::min<int64_t>((int64_t)e->phase_tile_slab << e->tile_shift, tgx::kPhaseMaxSamples);
+            TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+            TGX_CUDA(tgx::launch_plan_phase(d_params, n, limits, e->max_samples, e->tile_shift, max_n, tab,
+                                            e->phase.as<tgx::PhaseRec>(), d_counts, d_status, cnt, st, d_phases,
+                                            d_stats, stream));
+            e->launches += 1;
+            TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
+            TGX_CUDA(cudaStreamSynchronize(stream));
+            if (!h_stats->overflow) {
+                tot_samples = (int64_t)h_stats->total_samples;
+                tot_segs = 0;
+                tot_tiles = need_tiles;
+                done = true;
+                e->plan_phase = true;
+                e->plan_packed = false;
+                e->plan_params = d_params;
+                e->tile_slab_plan = e->phase_tile_slab;
+                e->phase_plans += 1;
+            } else {
+                e->phase_ready = false;   // lines, long or rejected-by-size trajectories: plan with segment tables
+            }
+        }
+    }
 
     // ---- slab mode: ONE replay, no scans; falls through to the exact-offset path if a slice overflows ----------
-    if (e->allow_slabs && e->slabs_ready && !d_stop_from) {
+    if (!done && e->allow_slabs && e->slabs_ready && !d_stop_from) {
         const int64_t need_segs = n * (int64_t)e->seg_slab, need_tiles = n * (int64_t)e->tile_slab;
         if (need_segs <= 0x7fffffffLL && need_tiles <= 0x7fffffffLL) {
             if ((rc = e->segs.reserve((size_t)need_segs * sizeof(tgx::Seg)))) return rc;
@@ -272,6 +318,12 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                 e->slab_plans += 1;
                 // a batch with many fewer tiles than slots would launch mostly empty CTAs: go back to exact offsets
                 if ((int64_t)h_stats->total_tiles * 2 < need_tiles) e->slabs_ready = false;
+                // an all-orbit batch of short trajectories can drop the tables altogether next time
+                const int slots = (h_stats->max_n + (1 << e->tile_shift) - 1) >> e->tile_shift;
+                e->phase_ready = e->allow_phase && !e->exact_ramps && !h_stats->has_line && h_stats->max_n > 0 &&
+                                 h_stats->max_n <= tgx::kPhaseMaxSamples &&
+                                 n * (int64_t)slots <= (int64_t)h_stats->total_tiles + (int64_t)h_stats->total_tiles / 4 + 1;
+                e->phase_tile_slab = std::max(slots, 1);
             } else {
                 e->slabs_ready = false;   // re-learn the slice sizes below
             }
@@ -336,6 +388,9 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
             e->slabs_ready = dense && small && tot_tiles > 0;
             e->seg_slab = seg_slab;
             e->tile_slab = tile_slab;
+            e->phase_ready = e->allow_phase && !e->exact_ramps && dense && !h_stats->has_line && h_stats->max_n > 0 &&
+                             h_stats->max_n <= tgx::kPhaseMaxSamples;
+            e->phase_tile_slab = tile_slab;
         }
     }
 
@@ -412,7 +467,8 @@ int tgx_destroy(tgx_engine* e) {
     if (!e) return TGX_OK;
     cudaSetDevice(e->device);
     DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
-                      &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats, &e->packets};
+                      &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats, &e->packets,
+                      &e->phase};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         e->h_params[i].release();
@@ -447,6 +503,7 @@ int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt) {
     e->spt = spt;
     e->has_plan = false;   // tile size is baked into a plan
     e->slabs_ready = false;
+    e->phase_ready = false;
     return TGX_OK;
 }
 
@@ -455,6 +512,7 @@ int tgx_set_plan_mode(tgx_engine* e, int exact_ramps) {
     e->exact_ramps = exact_ramps != 0;
     e->has_plan = false;
     e->slabs_ready = false;   // segment counts differ between the modes (ramp chunks)
+    e->phase_ready = false;
     return TGX_OK;
 }
 
@@ -475,6 +533,19 @@ int tgx_set_slab_planning(tgx_engine* e, int allow) {
     e->has_plan = false;
     return TGX_OK;
 }
+
+// Phase planning (default on): batches of Circle / Figure8 trajectories of at most 4096 samples are planned by a
+// counting replay only and evaluated from the caller's parameter array (which must then stay valid and unchanged
+// until the last tgx_eval / tgx_feasibility of that plan).  allow = 0 always plans with segment tables.
+int tgx_set_phase_planning(tgx_engine* e, int allow) {
+    if (!e) return TGX_ERR_INVALID;
+    e->allow_phase = allow != 0;
+    e->phase_ready = false;
+    e->has_plan = false;
+    return TGX_OK;
+}
+
+int64_t tgx_phase_plan_count(const tgx_engine* e) { return e ? e->phase_plans : 0; }
 
 // How many plans so far took the single-replay / the two-replay path.
 int tgx_plan_path_counts(const tgx_engine* e, int64_t* slab_plans, int64_t* exact_plans) {
@@ -545,6 +616,7 @@ int tgx_plan_samples(tgx_engine* e, const tgx_params* d_params, int64_t n, const
     if (d_status) TGX_CUDA(cudaMemcpyAsync(d_status, e->status.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     e->has_plan = true;
     e->plan_packed = false;
+    e->plan_phase = false;
     e->plan_n = n;
     e->plan_tiles = n;
     e->plan_segs = n;

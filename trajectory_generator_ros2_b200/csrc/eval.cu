@@ -108,10 +108,50 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double x) {
 
 }  // namespace
 
-// SLAB: the plan is a slab plan (fixed per-trajectory slices, see TableView).
-template <int THREADS, int SPT, bool STORE, bool REDUCE, bool SLAB>
+// Phase plans: build the segment of phase p of an orbit (Circle / Figure8) in closed form from the parameter record
+// and the phase start indices.  Mirrors plan.cu's fast replay: a ramp of n steps adds a*dt per step and clamps on
+// its last step (Circle.cpp:47-54, 75-82); a hold keeps v (:63-71); theta advances by (v/r)*dt per step.
+__device__ void build_phase_segment(const tgx_params& par, const PhaseRec& phr, int p, Seg& sg, int& kend) {
+    const tgx_orbit_params& o = par.u.orbit;
+    const int K = par.n_vgoals;
+    const double adt = __dmul_rn(o.accel, par.dt);          // the rounded product the reference adds every step
+    const double dtr = phr.dtr;
+    double v = 0.0, th = 0.0;
+    for (int q = 0; q <= p; ++q) {
+        const int n = phr.key(q + 1) - phr.key(q);
+        const bool hold = (q & 1) && q < 2 * K;
+        const bool up = !(q & 1) && q < 2 * K;
+        const double target = up ? o.v_goals[q >> 1] : 0.0;
+        const double dv = hold ? 0.0 : (up ? adt : -adt);
+        // state after the phase: n-1 unclamped steps plus the clamped one (ramps), or n equal steps (holds)
+        const double m = hold ? (double)n : (double)(n > 0 ? n - 1 : 0);
+        const double w1 = v * dtr;
+        const double th_m = fma(0.5 * (m * (m + 1.0)), dv * dtr, fma(m, w1, th));
+        const double v_end = (hold || n == 0) ? v : target;
+        const double th_end = (hold || n == 0) ? th_m : fma(target, dtr, th_m);
+        if (q == p) {
+            sg.kb = phr.key(q);
+            sg.n = n;
+            sg.flags = (!hold && n > 0) ? kSegClampLast : 0;
+            sg.pad = 0;
+            sg.vb = v;
+            sg.dv = dv;
+            sg.vclamp = hold ? v : target;
+            sg.s0 = th;
+            sg.s1 = w1;
+            sg.acc = th_end;       // theta of the phase's last sample
+            kend = phr.key(q + 1);
+        }
+        v = v_end;
+        th = th_end;
+    }
+}
+
+// MODE 0: exact-offset plan, 1: slab plan (fixed per-trajectory slices), 2: phase plan (see TableView).
+template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 6)
 eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a) {
+    constexpr bool SLAB = MODE == 1;
     __shared__ __align__(16) TrajRec s_rec;
     __shared__ __align__(16) Seg s_seg[kMaxSegPerTile];
     __shared__ int s_kend[kMaxSegPerTile];          // last sample of each segment
@@ -120,7 +160,53 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 
     // ---- stage the tile's constants in shared memory (16-byte chunks, one per thread) -------------------
     int traj, k_lo, nseg;
-    if (SLAB) {
+    if (MODE == 2) {
+        __shared__ __align__(16) tgx_params s_par;
+        __shared__ __align__(16) PhaseRec s_phr;
+        traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
+        k_lo = ((int)blockIdx.x - traj * tv.tile_slab) * (THREADS * SPT);
+#ifdef TGX_EXPERIMENT_SAMEPACKET
+        const int4* ppar = reinterpret_cast<const int4*>(tv.params);      // bandwidth experiment: no DRAM reads
+        const int4* pphr = reinterpret_cast<const int4*>(tv.phase);
+#else
+        const int4* ppar = reinterpret_cast<const int4*>(tv.params + traj);
+        const int4* pphr = reinterpret_cast<const int4*>(tv.phase + traj);
+#endif
+        // round 1: the first 80 bytes of the parameters (everything up to v_goals[1]) and the first 48 bytes of the
+        // phase record (the phase starts for K <= 2, dt/r, 1/r)
+        {
+            const int c = threadIdx.x;
+            if (c < 5) reinterpret_cast<int4*>(&s_par)[c] = __ldg(ppar + c);
+            else if (c < 8) reinterpret_cast<int4*>(&s_phr)[c - 5] = __ldg(pphr + (c - 5));
+        }
+        __syncthreads();
+        const int nent = s_phr.n;
+        if (nent <= 0) return;                     // rejected trajectory (whole CTA)
+        if (nent > 6) {                            // K > 2: fetch the rest (CTA-uniform)
+            const int c = threadIdx.x;
+            if (c < 3) reinterpret_cast<int4*>(&s_par)[5 + c] = __ldg(ppar + 5 + c);
+            else if (c < 6) reinterpret_cast<int4*>(&s_phr)[3 + (c - 3)] = __ldg(pphr + 3 + (c - 3));
+            __syncthreads();
+        }
+        const int n_total = s_phr.key(nent - 1) + 1;
+        if (k_lo >= n_total) return;               // slot beyond the trajectory's last tile (whole CTA)
+        nseg = nent - 1;
+        if ((int)threadIdx.x < nseg) {
+            Seg sg;
+            int kend;
+            build_phase_segment(s_par, s_phr, threadIdx.x, sg, kend);
+            s_seg[threadIdx.x] = sg;
+            s_kend[threadIdx.x] = kend;
+        } else if ((int)threadIdx.x == nseg) {
+            TrajRec r;
+            r.type = s_par.type & kRecTypeMask;
+            r.n = n_total;
+            r.f[0] = s_par.u.orbit.r; r.f[1] = s_par.u.orbit.cx; r.f[2] = s_par.u.orbit.cy; r.f[3] = s_par.alt;
+            r.f[4] = s_phr.dtr; r.f[5] = s_phr.rinv; r.f[6] = 0.0;
+            s_rec = r;
+        }
+        __syncthreads();
+    } else if (SLAB) {
         traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
         const int t = (int)blockIdx.x - traj * tv.tile_slab;
         const int4* pseg = reinterpret_cast<const int4*>(tv.segs + (size_t)traj * (size_t)tv.seg_slab);
@@ -418,17 +504,17 @@ feasibility_finalize_kernel(int64_t n, const uint32_t* __restrict__ plan_status,
 
 // ---- host-side launchers -----------------------------------------------------------------------------------
 
-template <int THREADS, int SPT, bool SLAB>
+template <int THREADS, int SPT, int MODE>
 static cudaError_t launch_eval_t(const TableView& tv, int64_t ntiles, const OutView& out, bool store, double* max_v,
                                  double* max_a, cudaStream_t stream) {
     const bool reduce = max_v || max_a;
     const unsigned grid = (unsigned)ntiles;
     if (store && reduce)
-        eval_kernel<THREADS, SPT, true, true, SLAB><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, true, true, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     else if (store)
-        eval_kernel<THREADS, SPT, true, false, SLAB><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, true, false, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     else
-        eval_kernel<THREADS, SPT, false, true, SLAB><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
+        eval_kernel<THREADS, SPT, false, true, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     return cudaGetLastError();
 }
 
@@ -438,11 +524,12 @@ cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int
     if (ntiles <= 0) return cudaSuccess;
     if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int threads = (1 << tile_shift) / spt;
-    const bool packed = tv.tile_slab > 0;
+    const int mode = tv.phase ? 2 : (tv.tile_slab > 0 ? 1 : 0);
 #define TGX_CASE(T, S)                                                                                     \
     if (threads == (T) && spt == (S))                                                                      \
-        return packed ? launch_eval_t<T, S, true>(tv, ntiles, out, store, max_v, max_a, stream)            \
-                      : launch_eval_t<T, S, false>(tv, ntiles, out, store, max_v, max_a, stream)
+        return mode == 2   ? launch_eval_t<T, S, 2>(tv, ntiles, out, store, max_v, max_a, stream)          \
+               : mode == 1 ? launch_eval_t<T, S, 1>(tv, ntiles, out, store, max_v, max_a, stream)          \
+                           : launch_eval_t<T, S, 0>(tv, ntiles, out, store, max_v, max_a, stream)
     TGX_CASE(128, 4);
     TGX_CASE(256, 2);
     TGX_CASE(256, 4);

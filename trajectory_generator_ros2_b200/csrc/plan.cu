@@ -65,6 +65,7 @@ struct Emitter {
     bool orbit;           // Circle / Figure8: Seg.s1 = theta increment per step, Seg.acc = exact theta of the last sample
     int seg_cap;          // slab mode: capacity of this trajectory's slice (writes beyond it are dropped and the
     int tile_cap;         //            plan is redone with exact offsets); otherwise INT_MAX
+    int32_t* keys = nullptr;   // phase plans: where each phase starts (PhaseRec::key)
 
     int nseg = 0;
     int ntile = 0;
@@ -74,6 +75,7 @@ struct Emitter {
     Seg cur;              // the open segment, kept in registers until closed
 
     __device__ void phase(int key, int kind, double value, double value2) {
+        if (keys && nph < 19) keys[nph] = key;
         if (ph && nph < TGX_MAX_PHASES) {
             ph->key[nph] = key;
             ph->kind[nph] = kind;
@@ -750,20 +752,25 @@ __device__ __forceinline__ tgx_params load_params(const tgx_params* params, int6
 // ---- kernels ------------------------------------------------------------------------------------------
 
 // Per-plan statistics the fill pass accumulates (one atomic per warp).
-__device__ __forceinline__ void accumulate_stats(PlanStats* stats, int n, int nseg, int ntile, bool overflow) {
+__device__ __forceinline__ void accumulate_stats(PlanStats* stats, int n, int nseg, int ntile, bool overflow,
+                                                 bool line_like) {
     if (!stats) return;
     const unsigned mask = __activemask();
     const unsigned tot = __reduce_add_sync(mask, (unsigned)n);
     const int mseg = __reduce_max_sync(mask, nseg);
     const int mtile = __reduce_max_sync(mask, ntile);
+    const int mn = __reduce_max_sync(mask, n);
     const unsigned tiles = __reduce_add_sync(mask, (unsigned)ntile);
     const unsigned ovf = __reduce_or_sync(mask, overflow ? 1u : 0u);
+    const unsigned lin = __reduce_or_sync(mask, line_like ? 1u : 0u);
     if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) {
         atomicAdd(&stats->total_samples, (unsigned long long)tot);
         atomicAdd(&stats->total_tiles, (unsigned long long)tiles);
         atomicMax(&stats->max_nseg, mseg);
         atomicMax(&stats->max_ntile, mtile);
+        atomicMax(&stats->max_n, mn);
         if (ovf) atomicOr(&stats->overflow, 1);
+        if (lin) atomicOr(&stats->has_line, 1);
     }
 }
 
@@ -849,7 +856,55 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
     if (status) status[i] = r.status;
     if (counts2) counts2[i] = r.n;
     if (status2) status2[i] = r.status;
-    accumulate_stats(stats, r.n, r.nseg, r.ntile, overflow);
+    accumulate_stats(stats, r.n, r.nseg, r.ntile, overflow, is_line_like(p.type));
+}
+
+// Phase plan: counts only.  Replays the speed ramps and hold counters (no angle state: none is stored) and records
+// where each phase starts; the evaluation kernel derives everything else from the parameter record.  Only orbits
+// of at most max_n samples qualify; anything else sets stats->overflow and the host plans with segment tables.
+__global__ void __launch_bounds__(128)
+plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits lim, int has_lim,
+                  int64_t max_samples, int tile_shift, int max_n, const CurTable* __restrict__ tab,
+                  PhaseRec* __restrict__ phase, int32_t* __restrict__ counts, uint32_t* __restrict__ status,
+                  int32_t* __restrict__ counts2, uint32_t* __restrict__ status2, tgx_phases* __restrict__ phases,
+                  PlanStats* __restrict__ stats) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const tgx_params p = load_params(params, i);
+    PhaseRec rec;
+    int32_t keys[19];
+    rec.n = 0;
+#pragma unroll
+    for (int q = 0; q < 19; ++q) keys[q] = 0;
+    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, phases ? phases + i : nullptr, true, 0x7fffffff,
+              0x7fffffff, keys};
+    const bool line_like = is_line_like(p.type);
+    PlanOut r{0, 0u, 0, 0};
+    bool overflow = line_like;
+    if (!line_like) {
+        r = plan_one<false, false, false>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
+        if (r.n > max_n) overflow = true;
+        if (r.n > 0) rec.n = E.nph < 19 ? E.nph : 19;
+    }
+    if (phases && r.n == 0) phases[i].n = 0;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) rec.key_lo[q] = keys[q];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) rec.key_hi[q] = keys[7 + q];
+    rec.dtr = line_like ? 0.0 : ddiv(p.dt, p.u.orbit.r);
+    rec.rinv = line_like ? 0.0 : ddiv(1.0, p.u.orbit.r);
+    // 96-byte record: six 16-byte stores
+    {
+        const int4* src = reinterpret_cast<const int4*>(&rec);
+        int4* dst = reinterpret_cast<int4*>(phase + i);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) dst[q] = src[q];
+    }
+    if (counts) counts[i] = r.n;
+    if (status) status[i] = r.status;
+    if (counts2) counts2[i] = r.n;
+    if (status2) status2[i] = r.status;
+    accumulate_stats(stats, r.n, 0, 0, overflow, line_like);
 }
 
 // "Per-time evaluation": a one-sample plan per trajectory from an explicit state, i.e. the public helpers
@@ -976,6 +1031,19 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
     if (exact_ramps) TGX_LAUNCH_FILL(true);
     else TGX_LAUNCH_FILL(false);
 #undef TGX_LAUNCH_FILL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_plan_phase(const tgx_params* params, int64_t n, const tgx_limits* lim, int64_t max_samples,
+                              int tile_shift, int max_n, const void* cur_table, PhaseRec* phase, int32_t* counts,
+                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
+                              PlanStats* stats, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    tgx_limits l{};
+    if (lim) l = *lim;
+    plan_phase_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(
+        params, n, l, lim ? 1 : 0, max_samples, tile_shift, max_n, static_cast<const CurTable*>(cur_table), phase,
+        counts, status, counts2, status2, phases, stats);
     return cudaGetLastError();
 }
 

@@ -84,13 +84,32 @@ constexpr int kMaxOptionalSegPerTile = 36;
 // Keeping these reads few and dense matters more than their size suggests: every DRAM read that lands in the middle
 // of the kernel's write stream costs a write->read->write bus turnaround (tools/wbw: 1 % of read traffic costs 8 %
 // of the write bandwidth; with cache-resident tables the same kernel writes 7.27 TB/s instead of 6.5 TB/s).
+//   phase plans (phase != nullptr): batches of short orbits.  The planner writes only the sample index at which each
+//       phase starts (PhaseRec, 96 B, dense) and the CTA derives its segments from the caller's 128-byte parameter
+//       record in closed form; tile t of trajectory i is CTA i*tile_slab + t.  Reads per tile: 80 + 48 bytes.
+struct __align__(16) PhaseRec {
+    int32_t n;            // number of phase starts = 2*K + 2 (0: rejected trajectory)
+    int32_t key_lo[7];    // key(p) = sample index at which phase p starts, key(n-1) = N - 1 (the index_msgs keys), p < 7
+    double dtr;           // dt / r and 1 / r, divided once here instead of once per CTA
+    double rinv;
+    int32_t key_hi[12];   // key(p) for p = 7 .. 18 (only read when K > 2)
+    __host__ __device__ int key(int p) const { return p < 7 ? key_lo[p] : key_hi[p - 7]; }
+};
+static_assert(sizeof(PhaseRec) == 96, "PhaseRec must be 96 bytes");
+
 struct TableView {
     const TrajRec* recs;
     const Seg* segs;
     const Tile* tiles;
     int seg_slab;
-    int tile_slab;                  // > 0: slab plan
+    int tile_slab;                  // > 0: slab or phase plan
+    const tgx_params* params;       // phase plan
+    const PhaseRec* phase;          // phase plan
 };
+
+// Longest trajectory a phase plan accepts: its closed forms run from the phase start, so the rounding drift against
+// the reference's running sums grows with the phase length; 4096 steps keep it below ~1e-11 rad.
+constexpr int kPhaseMaxSamples = 4096;
 
 constexpr int kSlabSpecSegs = 4;   // segments fetched speculatively with the record in a slab plan
 
@@ -100,7 +119,9 @@ struct PlanStats {
     unsigned long long total_tiles;     // sum of ceil(N_i / tile)
     int max_nseg;                       // largest segment count of a trajectory
     int max_ntile;                      // largest tile count of a trajectory
-    int overflow;                       // slab mode: some trajectory did not fit its slice
+    int overflow;                       // slab / phase mode: some trajectory did not fit
+    int max_n;                          // largest sample count of a trajectory
+    int has_line;                       // some trajectory is a Line / Boomerang
     int pad;
 };
 

@@ -43,6 +43,9 @@ def _load() -> C.CDLL:
     lib.tgx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     lib.tgx_set_plan_mode.argtypes = [vp, C.c_int]
     lib.tgx_set_host_fill.argtypes = [vp, C.c_int]
+    lib.tgx_set_phase_planning.argtypes = [vp, C.c_int]
+    lib.tgx_phase_plan_count.restype = i64
+    lib.tgx_phase_plan_count.argtypes = [vp]
     lib.tgx_set_slab_planning.argtypes = [vp, C.c_int]
     lib.tgx_plan_path_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.tgx_scratch_bytes.restype = i64
@@ -184,6 +187,13 @@ class Engine:
 
     def set_host_fill(self, fill_constants_on_host: bool):
         self._check(self._lib.tgx_set_host_fill(self._h, 1 if fill_constants_on_host else 0), "tgx_set_host_fill")
+
+    def set_phase_planning(self, allow: bool):
+        self._check(self._lib.tgx_set_phase_planning(self._h, 1 if allow else 0), "tgx_set_phase_planning")
+
+    @property
+    def phase_plan_count(self) -> int:
+        return int(self._lib.tgx_phase_plan_count(self._h))
 
     def set_slab_planning(self, allow: bool):
         self._check(self._lib.tgx_set_slab_planning(self._h, 1 if allow else 0), "tgx_set_slab_planning")
