@@ -292,6 +292,15 @@ int main(int argc, char** argv) {
             printf("P6s P6 with one shared record (no DRAM rd): %7.3f ms  %7.1f GB/s (valid bytes)\n", ms, gbv / ms * 1e3);
             cudaFree(tiles0);
         }
+        for (int mod : {256, 4096, 65536}) {   // records reused cyclically: L2-resident (not L1-resident) tables
+            int4* tm; CK(cudaMalloc(&tm, (size_t)nslab * 16));
+            int4* hm = (int4*)malloc((size_t)nslab * 16);
+            for (int i = 0; i < nslab; ++i) hm[i] = make_int4((int)(((long long)i * 2654435761LL) % mod), 0, 0, 8);
+            CK(cudaMemcpy(tm, hm, (size_t)nslab * 16, cudaMemcpyHostToDevice));
+            ms = timeit([&] { slab256_prologue<NCH, ROW><<<nslab, 256>>>(out, tm, recs, valid); });
+            printf("P6c P6 reading from a %5d-record table (%.1f MB, L2-resident): %7.3f ms  %7.1f GB/s\n", mod, mod * 1152 / 1e6, ms, gbv / ms * 1e3);
+            cudaFree(tm); free(hm);
+        }
         ms = timeit([&] { slab256_prologue_warp<NCH, ROW><<<nslab, 256>>>(out, tiles, recs, valid); });
         printf("V2  prologue per warp, no CTA barrier     : %7.3f ms  %7.1f GB/s (valid bytes)\n", ms, gbv / ms * 1e3);
         ms = timeit([&] { slab256_prefetch<NCH, ROW, 2><<<nslab / 2, 256>>>(out, tiles, recs, valid); });
