@@ -224,6 +224,39 @@ __global__ void slab256_twosmall(double* out, const int4* __restrict__ tiles, co
     for (int c = 0; c < NCH; ++c) st4(slab + (size_t)c * ROW, r0.x + r1.y + c, 2.5, 3.5, 4.5);
 }
 
+// V7: the per-tile record fetched by the TMA unit (1-D bulk async copy + mbarrier) instead of LSU loads
+template <int NCH, int ROW>
+__global__ void slab256_tma(double* out, const double4* __restrict__ recs, int valid) {
+    __shared__ __align__(128) double4 s_rec[36];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+    const unsigned dst_a = (unsigned)__cvta_generic_to_shared(s_rec);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(1152) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                     "l"(recs + (size_t)blockIdx.x * 36), "r"(1152), "r"(bar_a)
+                     : "memory");
+    }
+    // all threads wait for phase 0
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+        }
+    }
+    double* slab = out + (size_t)blockIdx.x * NCH * ROW + threadIdx.x * 4;
+    if ((int)threadIdx.x * 4 + 3 >= valid) return;
+    const double a = s_rec[threadIdx.x & 31].x;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) st4(slab + (size_t)c * ROW, a + c, 2.5, 3.5, 4.5);
+}
+
 template <class F>
 double timeit(F launch, int reps = 5) {
     for (int i = 0; i < 2; ++i) launch();
@@ -301,6 +334,8 @@ int main(int argc, char** argv) {
             printf("P6c P6 reading from a %5d-record table (%.1f MB, L2-resident): %7.3f ms  %7.1f GB/s\n", mod, mod * 1152 / 1e6, ms, gbv / ms * 1e3);
             cudaFree(tm); free(hm);
         }
+        ms = timeit([&] { slab256_tma<NCH, ROW><<<nslab, 256>>>(out, recs, valid); });
+        printf("V7  record fetched by TMA bulk copy + mbarrier (own record per tile): %7.3f ms  %7.1f GB/s\n", ms, gbv / ms * 1e3);
         ms = timeit([&] { slab256_prologue_warp<NCH, ROW><<<nslab, 256>>>(out, tiles, recs, valid); });
         printf("V2  prologue per warp, no CTA barrier     : %7.3f ms  %7.1f GB/s (valid bytes)\n", ms, gbv / ms * 1e3);
         ms = timeit([&] { slab256_prefetch<NCH, ROW, 2><<<nslab / 2, 256>>>(out, tiles, recs, valid); });
