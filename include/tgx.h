@@ -50,8 +50,18 @@ enum tgx_type {
     TGX_CIRCLE = 0,
     TGX_LINE = 1,
     TGX_FIGURE8 = 2,
-    TGX_BOOMERANG = 3     /* Line out and back (Boomerang.cpp:31-141); takes tgx_line_params */
+    TGX_BOOMERANG = 3,    /* Line out and back (Boomerang.cpp:31-141); takes tgx_line_params */
+    /* Constant-speed polyline family; all take tgx_polyline_params and are planned by
+     * tgx_plan_polyline.  default.yaml:9 ships traj_type: T. */
+    TGX_SQUARE = 4,        /* Square.cpp:21-87 */
+    TGX_RECTANGLE = 5,     /* Rectangle.cpp:20-88 */
+    TGX_RECIPROCATING = 6, /* Reciprocating.cpp:24-60 */
+    TGX_BOUNCE = 7,        /* Bounce.cpp:19-52 */
+    TGX_M = 8,             /* M.cpp:13-67 */
+    TGX_I = 9,             /* I.cpp:19-75 */
+    TGX_T = 10             /* T.cpp:19-73 */
 };
+#define TGX_IS_POLYLINE(type) ((type) >= TGX_SQUARE && (type) <= TGX_T)
 
 /* Channel order of the struct-of-arrays output: the numeric fields of snapstack_msgs2/Goal in the order
  * create*Goal fills them (Circle.cpp:107-126). */
@@ -82,15 +92,43 @@ typedef struct tgx_line_params {
     double reserved[4];
 } tgx_line_params;
 
+/* Constructor arguments of the constant-speed polyline family (Square.hpp:31-32, Rectangle.hpp, Reciprocating.hpp,
+ * Bounce.hpp, M.hpp, I.hpp, T.hpp). 13 doubles.
+ *
+ * cos_o / sin_o: the reference rotates its waypoints with std::cos / std::sin of `orientation` (Square.cpp:37-38,
+ * M.cpp:29-30, ...), and the per-side step counts ceil(distance / (v*dt)) depend on the last bit of those two
+ * numbers.  libm's results are not reproducible across math libraries, so they are INPUTS here: a caller that wants
+ * indexing bit-identical to a reference built against its own libm passes that libm's values and sets
+ * TGX_POLY_TRIG_GIVEN in tgx_params.n_vgoals (tgx_polyline_finalize_host does exactly that; the host-buffer calls and
+ * the drop-in classes use it).  Without the flag the planner uses the device's cos / sin (<= 2 ulp from libm's). */
+typedef struct tgx_polyline_params {
+    double t_traj;                   /* total time, s */
+    double v_goal;                   /* v_goals_.empty() ? 1.0 : v_goals_[0] (Square.cpp:48, M.cpp:39, ...) */
+    double decel;                    /* braking deceleration: accel_ (Square.cpp:129, Rectangle.cpp:126), a3_
+                                        (Reciprocating.cpp:98); ignored by M / I / T (literal 1.0, M.cpp:101) and Bounce */
+    double orientation;              /* rad; unused by Reciprocating */
+    double cos_o, sin_o;             /* see above */
+    double g[7];                     /* geometry, by type:
+                                        SQUARE         side_length, cx, cy
+                                        RECTANGLE      side_a, side_b, cx, cy
+                                        RECIPROCATING  Ax, Ay, Az, Bx, By, Bz
+                                        BOUNCE         cx, cy, Az, Bz
+                                        M, I, T        cx, cy, length, width
+                                        g[5], g[6]: z and heading arguments of tgx_plan_samples (create*Goal helpers) */
+} tgx_polyline_params;
+
+#define TGX_POLY_TRIG_GIVEN 1        /* tgx_params.n_vgoals bit 0 for polyline types: cos_o / sin_o are valid */
+
 /* One trajectory's parameters: exactly 128 bytes, the unit of the batch parameter array. */
 typedef struct tgx_params {
     int32_t type;                    /* enum tgx_type */
-    int32_t n_vgoals;                /* orbit: 1..TGX_MAX_VGOALS; line: ignored */
+    int32_t n_vgoals;                /* orbit: 1..TGX_MAX_VGOALS; line: ignored; polyline: flag bits (TGX_POLY_*) */
     double dt;                       /* Trajectory::dt_ = 1/pub_freq (TrajectoryGenerator.cpp:171-172) */
     double alt;                      /* alt_: z of every sample */
     union {
         tgx_orbit_params orbit;      /* TGX_CIRCLE, TGX_FIGURE8 */
         tgx_line_params line;        /* TGX_LINE, TGX_BOOMERANG */
+        tgx_polyline_params poly;    /* TGX_SQUARE .. TGX_T */
     } u;
 } tgx_params;
 
@@ -109,11 +147,15 @@ enum tgx_status_bits {
     TGX_ST_AMAX_EXCEEDED         = 1u << 7, /* max_k |a_k| > limits.a_max  (tgx_feasibility only) */
     TGX_ST_TOO_LONG              = 1u << 8, /* sample count would exceed the engine's max_samples guard (the reference
                                                would loop for ever / exhaust memory): no samples */
-    TGX_ST_TRUNCATED             = 1u << 9  /* row capacity of the output layout < sample count: tail not written */
+    TGX_ST_TRUNCATED             = 1u << 9, /* row capacity of the output layout < sample count: tail not written */
+    TGX_ST_WRONG_PLANNER         = 1u << 10 /* a polyline-family trajectory handed to tgx_plan, or a Circle / Line / Figure8 /
+                                               Boomerang handed to tgx_plan_polyline: no samples (the host-buffer calls route
+                                               every trajectory to its planner themselves) */
 };
 
 /* Status bits that mean "the reference would not have produced this trajectory". */
-#define TGX_ST_FATAL_MASK (TGX_ST_FINAL_V_NONZERO | TGX_ST_LINE_END_NOT_B | TGX_ST_BAD_PARAM | TGX_ST_TOO_LONG)
+#define TGX_ST_FATAL_MASK \
+    (TGX_ST_FINAL_V_NONZERO | TGX_ST_LINE_END_NOT_B | TGX_ST_BAD_PARAM | TGX_ST_TOO_LONG | TGX_ST_WRONG_PLANNER)
 
 /* Library return codes. */
 enum tgx_error {
@@ -171,6 +213,27 @@ typedef struct tgx_phases {
     double value2[TGX_MAX_PHASES];   /* hold time for REACHED (t_traj, or Line's t2) */
 } tgx_phases;
 
+/* index_msgs of a polyline-family trajectory.  The reference announces EVERY sample ("Square traj: moving along side
+ * 2", Square.cpp:79; "M traj: segment 1 rev", M.cpp:57; "Reciprocating: forward", Reciprocating.cpp:47), so instead of
+ * one entry per sample the engine returns the structure those strings are a function of: the samples follow a
+ * periodic pattern of `n_legs` legs, leg l contributing count[l] consecutive samples per period,
+ *     sample k  ->  m = k - first_special,  leg = the l with  sum(count[0..l-1]) <= m mod period < sum(count[0..l]).
+ * Leg numbering: SQUARE / RECTANGLE side 0..3; RECIPROCATING 0 forward, 1 yaw flip at B, 2 reverse, 3 yaw flip at A;
+ * BOUNCE 0 "ascending", 1 "descending" (the reference labels by lap parity, Bounce.cpp:41); M legs 0..3 "segment l fwd",
+ * 4..7 "segment l-4 rev"; I 0..4 fwd, 5..9 rev; T 0..2 fwd, 3..5 rev.  The last sample's entry is then overwritten by
+ * "<Shape> traj: completed" (Square.cpp:88, Bounce.cpp:50, M.cpp:65; not for RECIPROCATING). */
+#define TGX_POLY_MAX_LEGS 10
+typedef struct tgx_polyline_legs {
+    int32_t n;                          /* sample count (0: rejected or empty) */
+    int32_t n_legs;
+    int32_t first_special;              /* 1: sample 0 precedes the pattern ("starting at corner 0", Square.cpp:60-61) */
+    int32_t last_special;               /* 1: the last sample is the yaw-flip goal the reference appends after a leg
+                                           that t_traj cut short (Reciprocating.cpp:50-57) */
+    int32_t period;                     /* sum of count[] */
+    int32_t count[TGX_POLY_MAX_LEGS];
+    int32_t reserved;
+} tgx_polyline_legs;
+
 typedef struct tgx_engine tgx_engine;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */
@@ -225,6 +288,21 @@ int tgx_count(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_li
 int tgx_plan(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits,
              int32_t* d_counts, uint32_t* d_status, tgx_phases* d_phases, int64_t* total_samples,
              void* stream);
+
+/* Planning pass of the constant-speed polyline family (Square / Rectangle / Reciprocating / Bounce / M / I / T
+ * ::generateTraj: Square.cpp:21-92, Rectangle.cpp:20-93, Reciprocating.cpp:24-60, Bounce.cpp:19-52, M.cpp:13-67,
+ * I.cpp:19-75, T.cpp:19-73).  One thread per trajectory builds the waypoints and per-leg step counts
+ * ceil(distance / (v*dt)) with non-contracted IEEE operations and looks the number of `t += dt` iterations up in the
+ * same table the hold phases use; the result is a current plan that tgx_eval / tgx_feasibility evaluate with the
+ * polyline kernel (frac = i / steps, p = start + frac * (end - start): positions are bit-identical to the reference).
+ * d_counts / d_status / d_legs / total_samples may be NULL.  Synchronises `stream` once. */
+int tgx_plan_polyline(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits,
+                      int32_t* d_counts, uint32_t* d_status, tgx_polyline_legs* d_legs, int64_t* total_samples,
+                      void* stream);
+
+/* Fills u.poly.cos_o / sin_o of every polyline-family record with the HOST libm's cos / sin of `orientation` and sets
+ * TGX_POLY_TRIG_GIVEN (see tgx_polyline_params); records of other types are left untouched. */
+int tgx_polyline_finalize_host(tgx_params* h_params, int64_t n);
 
 /* Braking plan (Trajectory::generateStopTraj): trajectory i brakes from the setpoint d_from[i*14 .. i*14+13]
  * (channel order tgx_channel; the reference reads goals[pub_index], Circle.cpp:140-143, Line.cpp:124-127).

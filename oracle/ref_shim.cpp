@@ -1,7 +1,7 @@
 // ref_shim.cpp — C-ABI driver around the UNMODIFIED reference trajectory classes (test infrastructure).
 //
 // Built ONLY by oracle/Makefile into oracle/_ref/libtrajref.so together with the reference's own
-// src/trajectories/{Circle,Line,Figure8}.cpp, compiled from where they lie under /root/reference behind the
+// src/trajectories/{Circle,Line,Figure8,Boomerang,Square,Rectangle,Reciprocating,Bounce,M,I,T}.cpp, compiled from where they lie under /root/reference behind the
 // stub headers in compat/ros2_stubs.  No reference source is copied into this repository; this file is the
 // repo's own glue: it constructs trajectory_generator::{Circle,Line,Figure8} with the constructor arguments
 // held in a tgx_params record, calls generateTraj / generateStopTraj / trajectoryInsideBounds and repacks the
@@ -20,9 +20,16 @@
 #include <vector>
 
 #include "trajectory_generator_ros2/trajectories/Boomerang.hpp"
+#include "trajectory_generator_ros2/trajectories/Bounce.hpp"
 #include "trajectory_generator_ros2/trajectories/Circle.hpp"
 #include "trajectory_generator_ros2/trajectories/Figure8.hpp"
+#include "trajectory_generator_ros2/trajectories/I.hpp"
 #include "trajectory_generator_ros2/trajectories/Line.hpp"
+#include "trajectory_generator_ros2/trajectories/M.hpp"
+#include "trajectory_generator_ros2/trajectories/Reciprocating.hpp"
+#include "trajectory_generator_ros2/trajectories/Rectangle.hpp"
+#include "trajectory_generator_ros2/trajectories/Square.hpp"
+#include "trajectory_generator_ros2/trajectories/T.hpp"
 
 #include "../include/tgx.h"
 
@@ -52,10 +59,49 @@ bool params_ok(const tgx_params& p) {
             if (!std::isfinite(l.A[i]) || !std::isfinite(l.B[i])) return false;
         return finite_pos(l.v_goal) && finite_pos(l.a1) && finite_pos(l.a3);
     }
+    if (TGX_IS_POLYLINE(p.type)) {
+        const tgx_polyline_params& q = p.u.poly;
+        if (!finite_pos(q.v_goal) || !std::isfinite(q.t_traj) || !std::isfinite(q.orientation)) return false;
+        for (int i = 0; i < 5; ++i)
+            if (!std::isfinite(q.g[i])) return false;
+        switch (p.type) {
+            case TGX_SQUARE: return finite_pos(q.g[0]) && finite_pos(q.decel);
+            case TGX_RECTANGLE: return finite_pos(q.g[0]) && finite_pos(q.g[1]) && finite_pos(q.decel);
+            case TGX_RECIPROCATING:
+                return std::isfinite(q.g[5]) && finite_pos(q.decel) && (q.g[0] != q.g[3] || q.g[1] != q.g[4]);
+            case TGX_BOUNCE: return q.g[2] != q.g[3];
+            default: return finite_pos(q.g[2]) && finite_pos(q.g[3]);
+        }
+    }
     return false;
 }
 
 std::unique_ptr<tg::Trajectory> make_traj(const tgx_params& p) {
+    if (TGX_IS_POLYLINE(p.type)) {
+        const tgx_polyline_params& q = p.u.poly;
+        std::vector<double> vg{q.v_goal};
+        switch (p.type) {
+            case TGX_SQUARE:
+                return std::make_unique<tg::Square>(p.alt, q.g[0], q.g[1], q.g[2], q.orientation, vg, q.t_traj, q.decel,
+                                                    p.dt);
+            case TGX_RECTANGLE:
+                return std::make_unique<tg::Rectangle>(p.alt, q.g[0], q.g[1], q.g[2], q.g[3], q.orientation, vg,
+                                                       q.t_traj, q.decel, p.dt);
+            case TGX_RECIPROCATING:
+                // a1 is stored and never used by the class (Reciprocating.hpp)
+                return std::make_unique<tg::Reciprocating>(p.alt, Eigen::Vector3d(q.g[0], q.g[1], q.g[2]),
+                                                           Eigen::Vector3d(q.g[3], q.g[4], q.g[5]), vg, q.decel,
+                                                           q.decel, q.t_traj, p.dt);
+            case TGX_BOUNCE:
+                return std::make_unique<tg::Bounce>(q.g[0], q.g[1], q.g[2], q.g[3], vg, q.t_traj, q.orientation, p.dt);
+            case TGX_M:
+                return std::make_unique<tg::M>(q.g[0], q.g[1], q.g[2], q.g[3], p.alt, vg, q.t_traj, q.orientation, p.dt);
+            case TGX_I:
+                return std::make_unique<tg::I>(q.g[0], q.g[1], q.g[2], q.g[3], p.alt, vg, q.t_traj, q.orientation, p.dt);
+            default:
+                return std::make_unique<tg::T>(q.g[0], q.g[1], q.g[2], q.g[3], p.alt, vg, q.t_traj, q.orientation, p.dt);
+        }
+    }
     if (p.type == TGX_BOOMERANG) {
         const tgx_line_params& l = p.u.line;
         std::vector<double> vg{l.v_goal};

@@ -11,11 +11,15 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #ifndef M_PI_2
 #define M_PI_2 1.57079632679489661923
+#endif
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
 #endif
 
 /* ---- sample sink ------------------------------------------------------------------------------------ */
@@ -146,6 +150,22 @@ static int params_ok(const tgx_params* p) {
         for (int i = 0; i < 3; ++i)
             if (!isfinite(l->A[i]) || !isfinite(l->B[i])) return 0;
         return finite_pos(l->v_goal) && finite_pos(l->a1) && finite_pos(l->a3);
+    }
+    if (TGX_IS_POLYLINE(p->type)) {
+        /* v > 0: "All velocities must be > 0" (TrajectoryGenerator.cpp:227-232, 306-311, ...); accel > 0 (:241-244,
+         * :251-254, :275-278).  A leg of length 0 would make the reference divide 0/0 (frac = i / steps with steps == 0). */
+        const tgx_polyline_params* q = &p->u.poly;
+        if (!finite_pos(q->v_goal) || !isfinite(q->t_traj) || !isfinite(q->orientation)) return 0;
+        for (int i = 0; i < 5; ++i)
+            if (!isfinite(q->g[i])) return 0;
+        switch (p->type) {
+            case TGX_SQUARE: return finite_pos(q->g[0]) && finite_pos(q->decel);
+            case TGX_RECTANGLE: return finite_pos(q->g[0]) && finite_pos(q->g[1]) && finite_pos(q->decel);
+            case TGX_RECIPROCATING:
+                return isfinite(q->g[5]) && finite_pos(q->decel) && (q->g[0] != q->g[3] || q->g[1] != q->g[4]);
+            case TGX_BOUNCE: return q->g[2] != q->g[3];
+            default: return finite_pos(q->g[2]) && finite_pos(q->g[3]);   /* M, I, T: length, width */
+        }
     }
     return 0;
 }
@@ -364,6 +384,405 @@ static int64_t boomerang_generate(const tgx_params* p, sink_t* sk, uint32_t* sta
     return sk->n;
 }
 
+
+/* ---- constant-speed polyline family ---------------------------------------------------
+ * Square / Rectangle / Reciprocating / Bounce / M / I / T.  `leg_of` (may be NULL) receives, per sample, the leg of
+ * the periodic pattern it belongs to in tgx_polyline_legs numbering (-1 for Square / Rectangle's sample 0), which is
+ * what the reference's per-sample index_msgs strings are a function of. */
+
+typedef struct {
+    int16_t* leg_of;
+    int64_t leg_cap;
+} legsink_t;
+
+static void leg_push(legsink_t* ls, int64_t k, int leg) {
+    if (ls && ls->leg_of && k < ls->leg_cap) ls->leg_of[k] = (int16_t)leg;
+}
+
+/* createSquareGoal (Square.cpp:94-110) == createRectangleGoal (Rectangle.cpp:95-111) == createReciprocatingGoal
+ * (Reciprocating.cpp:62-79) == createMGoal (M.cpp:69-86) == createIGoal (I.cpp:77-94) == createTGoal (T.cpp:75-92).
+ * goal.j is never assigned and keeps the message default 0. */
+static void planar_goal(const tgx_params* p, double x, double y, double v, double accel, double heading,
+                        double g[TGX_NCHAN]) {
+    g[TGX_PX] = x;
+    g[TGX_PY] = y;
+    g[TGX_PZ] = p->alt;
+    g[TGX_VX] = v * cos(heading);
+    g[TGX_VY] = v * sin(heading);
+    g[TGX_VZ] = 0;
+    g[TGX_AX] = accel * cos(heading);
+    g[TGX_AY] = accel * sin(heading);
+    g[TGX_AZ] = 0;
+    g[TGX_JX] = 0;
+    g[TGX_JY] = 0;
+    g[TGX_JZ] = 0;
+    g[TGX_PSI] = heading;
+    g[TGX_DPSI] = 0;
+}
+
+/* Bounce::createBounceGoal, Bounce.cpp:54-72. */
+static void bounce_goal(double x, double y, double z, double vz, double heading, double g[TGX_NCHAN]) {
+    memset(g, 0, TGX_NCHAN * sizeof(double));
+    g[TGX_PX] = x;
+    g[TGX_PY] = y;
+    g[TGX_PZ] = z;
+    g[TGX_VZ] = vz;
+    g[TGX_PSI] = heading;
+}
+
+/* double -> int conversion of a std::ceil result; out-of-range values (undefined behaviour in the reference) are
+ * reported as "too long". */
+static int ceil_to_int(double x, int* ok) {
+    double c = ceil(x);
+    if (!(c >= -2147483648.0 && c <= 1073741824.0)) { *ok = 0; return 0; }
+    return (int)c;
+}
+
+/* Square::generateTraj (Square.cpp:21-92) and Rectangle::generateTraj (Rectangle.cpp:20-93). */
+static int64_t square_generate(const tgx_params* p, sink_t* sk, legsink_t* ls, uint32_t* status, int64_t max_samples) {
+    const tgx_polyline_params* q = &p->u.poly;
+    const int rect = p->type == TGX_RECTANGLE;
+    double g[TGX_NCHAN];
+    double half_a = q->g[0] / 2.0;
+    double half_b = rect ? q->g[1] / 2.0 : half_a;
+    double cx = rect ? q->g[2] : q->g[1], cy = rect ? q->g[3] : q->g[2];
+    double cxs[4] = {-half_a, half_a, half_a, -half_a};       /* :30-33 counter-clockwise from top-left */
+    double cys[4] = {half_b, half_b, -half_b, -half_b};
+    double c = cos(q->orientation);                           /* :37-38 */
+    double s = sin(q->orientation);
+    for (int i = 0; i < 4; ++i) {                             /* :39-44 */
+        double x_new = c * cxs[i] - s * cys[i];
+        double y_new = s * cxs[i] + c * cys[i];
+        cxs[i] = x_new + cx;
+        cys[i] = y_new + cy;
+    }
+    double v_goal = q->v_goal;                                /* :48 */
+    double total_perimeter = rect ? 2 * (q->g[0] + q->g[1]) : 4 * q->g[0];   /* :49, Rectangle.cpp:49 */
+    double time_per_lap = total_perimeter / v_goal;
+    int ok = 1;
+    int num_laps = ceil_to_int(q->t_traj / time_per_lap, &ok);   /* :51 */
+    if (!ok) { *status |= TGX_ST_TOO_LONG; return -1; }
+    double dt = p->dt;
+    int current_corner = 0;
+    double heading0 = q->orientation + M_PI;                  /* :57 */
+    double t = 0.0;
+    planar_goal(p, cxs[0], cys[0], v_goal, 0, heading0, g);   /* :60 */
+    leg_push(ls, sk->n, -1);
+    sink_push(sk, g);
+    for (int lap = 0; lap < num_laps; ++lap) {                /* :64 */
+        for (int side = 0; side < 4; ++side) {
+            int next_corner = (current_corner + 1) % 4;
+            double sx = cxs[current_corner], sy = cys[current_corner];
+            double ex = cxs[next_corner], ey = cys[next_corner];
+            double ddx = ex - sx, ddy = ey - sy;
+            double side_length = sqrt(ddx * ddx + ddy * ddy);   /* (end - start).norm(), :69 */
+            double side_time = side_length / v_goal;
+            int steps = ceil_to_int(side_time / dt, &ok);       /* :71 */
+            if (!ok) { *status |= TGX_ST_TOO_LONG; return -1; }
+            for (int step = 1; step <= steps && t < q->t_traj; ++step) {   /* :73 */
+                if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+                double frac = (double)step / steps;
+                double x_new = sx + frac * (ex - sx);
+                double y_new = sy + frac * (ey - sy);
+                double heading = atan2(ey - sy, ex - sx);
+                planar_goal(p, x_new, y_new, v_goal, 0, heading, g);
+                leg_push(ls, sk->n, side);
+                sink_push(sk, g);
+                double t_new = t + dt;
+                if (t_new == t) { *status |= TGX_ST_TOO_LONG; return -1; }
+                t = t_new;
+                if (t >= q->t_traj) break;
+            }
+            current_corner = next_corner;
+        }
+        if (!(t < q->t_traj)) break;   /* later laps emit nothing */
+    }
+    return sk->n;
+}
+
+/* Reciprocating::Reciprocating + generateTraj, Reciprocating.cpp:13-60. */
+static int64_t recip_generate(const tgx_params* p, sink_t* sk, legsink_t* ls, uint32_t* status, int64_t max_samples) {
+    const tgx_polyline_params* q = &p->u.poly;
+    double g[TGX_NCHAN];
+    double Ax = q->g[0], Ay = q->g[1], Bx = q->g[3], By = q->g[4];
+    double theta_fwd = atan2(By - Ay, Bx - Ax);               /* :17-18 */
+    double theta_rev = atan2(Ay - By, Ax - Bx);
+    double v_goal = q->v_goal, dt = p->dt, t = 0.0;
+    int forward = 1;
+    double sx = Ax, sy = Ay, ex = Bx, ey = By;
+    double heading = theta_fwd;
+    while (t < q->t_traj) {                                   /* :36 */
+        double ddx = ex - sx, ddy = ey - sy;
+        double distance = sqrt(ddx * ddx + ddy * ddy);        /* (end - start).head<2>().norm(), :38 */
+        int ok = 1;
+        int steps = ceil_to_int(distance / (v_goal * dt), &ok);   /* :39 */
+        if (!ok || steps < 1) { *status |= TGX_ST_TOO_LONG; return -1; }
+        for (int i = 0; i <= steps && t < q->t_traj; ++i) {   /* :40 */
+            if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+            double frac = (double)i / steps;
+            double x = sx + frac * (ex - sx);
+            double y = sy + frac * (ey - sy);
+            planar_goal(p, x, y, v_goal, 0, heading, g);
+            leg_push(ls, sk->n, forward ? 0 : 2);
+            sink_push(sk, g);
+            double t_new = t + dt;
+            if (t_new == t) { *status |= TGX_ST_TOO_LONG; return -1; }
+            t = t_new;
+        }
+        forward = !forward;                                   /* :50-52 */
+        { double tx = sx, ty = sy; sx = ex; sy = ey; ex = tx; ey = ty; }
+        heading = forward ? theta_fwd : theta_rev;
+        if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        planar_goal(p, sx, sy, 0, 0, heading, g);             /* :54-56 yaw flip at the endpoint, unconditional */
+        leg_push(ls, sk->n, forward ? 3 : 1);
+        sink_push(sk, g);
+        t += dt;
+    }
+    return sk->n;
+}
+
+/* Bounce::generateTraj, Bounce.cpp:19-52. */
+static int64_t bounce_generate(const tgx_params* p, sink_t* sk, legsink_t* ls, uint32_t* status, int64_t max_samples) {
+    const tgx_polyline_params* q = &p->u.poly;
+    double g[TGX_NCHAN];
+    double v_goal = q->v_goal, dt = p->dt, t = 0.0;
+    int going_up = 1;
+    double z_start = q->g[2], z_end = q->g[3];
+    double heading = q->orientation;                          /* :32 */
+    while (t < q->t_traj) {                                   /* :34 */
+        double distance = fabs(z_end - z_start);
+        int ok = 1;
+        int steps = ceil_to_int(distance / (v_goal * dt), &ok);   /* :36 */
+        if (!ok || steps < 1) { *status |= TGX_ST_TOO_LONG; return -1; }
+        for (int i = 0; i <= steps && t < q->t_traj; ++i) {   /* :37 */
+            if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+            double frac = (double)i / steps;
+            double z = z_start + frac * (z_end - z_start);
+            double vz = (z_end > z_start) ? v_goal : -v_goal;
+            bounce_goal(q->g[0], q->g[1], z, vz, heading, g);
+            leg_push(ls, sk->n, going_up ? 0 : 1);
+            sink_push(sk, g);
+            double t_new = t + dt;
+            if (t_new == t) { *status |= TGX_ST_TOO_LONG; return -1; }
+            t = t_new;
+        }
+        going_up = !going_up;                                 /* :46-47 */
+        { double tz = z_start; z_start = z_end; z_end = tz; }
+    }
+    return sk->n;
+}
+
+/* M::generateTraj (M.cpp:13-67), I::generateTraj (I.cpp:19-75), T::generateTraj (T.cpp:19-73). */
+static int64_t letter_generate(const tgx_params* p, sink_t* sk, legsink_t* ls, uint32_t* status, int64_t max_samples) {
+    const tgx_polyline_params* q = &p->u.poly;
+    double g[TGX_NCHAN];
+    double cx = q->g[0], cy = q->g[1], length = q->g[2], width = q->g[3];
+    double bx[6], by[6], px[6], py[6];
+    int np;
+    if (p->type == TGX_M) {                                   /* M.cpp:20-26 */
+        np = 5;
+        bx[0] = -width / 2; by[0] = -length / 2;
+        bx[1] = -width / 2; by[1] = length / 2;
+        bx[2] = 0.0;        by[2] = -length / 2;
+        bx[3] = width / 2;  by[3] = length / 2;
+        bx[4] = width / 2;  by[4] = -length / 2;
+    } else if (p->type == TGX_I) {                            /* I.cpp:28-35 */
+        np = 6;
+        bx[0] = -width / 2; by[0] = length / 2;
+        bx[1] = width / 2;  by[1] = length / 2;
+        bx[2] = 0.0;        by[2] = length / 2;
+        bx[3] = 0.0;        by[3] = -length / 2;
+        bx[4] = -width / 2; by[4] = -length / 2;
+        bx[5] = width / 2;  by[5] = -length / 2;
+    } else {                                                  /* T.cpp:28-33 */
+        np = 4;
+        bx[0] = -width / 2; by[0] = length / 2;
+        bx[1] = width / 2;  by[1] = length / 2;
+        bx[2] = 0.0;        by[2] = length / 2;
+        bx[3] = 0.0;        by[3] = -length / 2;
+    }
+    double c = cos(q->orientation);                           /* M.cpp:29-30 */
+    double s = sin(q->orientation);
+    for (int i = 0; i < np; ++i) {                            /* M.cpp:32-37, I.cpp:40-45, T.cpp:38-43 */
+        px[i] = c * bx[i] - s * by[i] + cx;
+        py[i] = s * bx[i] + c * by[i] + cy;
+    }
+    double v_goal = q->v_goal, dt = p->dt, t = 0.0;
+    int forward = 1;
+    while (t < q->t_traj) {                                   /* M.cpp:44 */
+        for (int seg = 0; seg < np - 1 && t < q->t_traj; ++seg) {   /* :46 */
+            int a = forward ? seg : np - 1 - seg;             /* reversed copy of the point list, :45 */
+            int b = forward ? seg + 1 : np - 2 - seg;
+            double sx = px[a], sy = py[a], ex = px[b], ey = py[b];
+            double heading = atan2(ey - sy, ex - sx);         /* :49 */
+            double ddx = ex - sx, ddy = ey - sy;
+            double distance = sqrt(ddx * ddx + ddy * ddy);    /* :50 */
+            int ok = 1;
+            int steps = ceil_to_int(distance / (v_goal * dt), &ok);   /* :51 */
+            if (!ok || steps < 1) { *status |= TGX_ST_TOO_LONG; return -1; }
+            for (int i = 0; i <= steps && t < q->t_traj; ++i) {   /* :52 */
+                if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+                double frac = (double)i / steps;
+                double x = sx + frac * (ex - sx);
+                double y = sy + frac * (ey - sy);
+                planar_goal(p, x, y, v_goal, 0, heading, g);
+                leg_push(ls, sk->n, forward ? seg : (np - 1) + seg);
+                sink_push(sk, g);
+                double t_new = t + dt;
+                if (t_new == t) { *status |= TGX_ST_TOO_LONG; return -1; }
+                t = t_new;
+            }
+        }
+        forward = !forward;                                   /* :61 */
+    }
+    return sk->n;
+}
+
+static int64_t poly_generate(const tgx_params* p, sink_t* sk, legsink_t* ls, uint32_t* status, int64_t max_samples) {
+    switch (p->type) {
+        case TGX_SQUARE:
+        case TGX_RECTANGLE: return square_generate(p, sk, ls, status, max_samples);
+        case TGX_RECIPROCATING: return recip_generate(p, sk, ls, status, max_samples);
+        case TGX_BOUNCE: return bounce_generate(p, sk, ls, status, max_samples);
+        default: return letter_generate(p, sk, ls, status, max_samples);
+    }
+}
+
+int64_t orc_polyline_generate(const tgx_params* p, double* out, int64_t chan_stride, int64_t cap, uint32_t* status,
+                              int16_t* leg_of, int64_t max_samples) {
+    uint32_t st = 0;
+    int64_t n;
+    sink_t sk = {out, chan_stride, cap, 0, {0}};
+    legsink_t ls = {leg_of, cap};
+    if (!TGX_IS_POLYLINE(p->type) || !params_ok(p)) {
+        st |= TGX_ST_BAD_PARAM;
+        n = -1;
+    } else {
+        n = poly_generate(p, &sk, &ls, &st, max_samples);
+    }
+    if (n > cap && out) st |= TGX_ST_TRUNCATED;
+    if (status) *status = st;
+    return n;
+}
+
+/* The reference's index_msgs text for sample k of a polyline trajectory with n samples, given its leg
+ * (Square.cpp:61,79,88; Rectangle.cpp:61,79,88; Reciprocating.cpp:47,57; Bounce.cpp:42,50; M.cpp:57,65; I.cpp:65,73;
+ * T.cpp:63,71).  Returns the length written. */
+int orc_polyline_msg(int type, int leg, int64_t k, int64_t n, char* buf, int cap) {
+    static const char* const letter[] = {"M", "I", "T"};
+    const int last = (k == n - 1);
+    switch (type) {
+        case TGX_SQUARE:
+        case TGX_RECTANGLE: {
+            const char* name = type == TGX_SQUARE ? "Square" : "Rectangle";
+            if (last) return snprintf(buf, (size_t)cap, "%s traj: completed", name);
+            if (leg < 0) return snprintf(buf, (size_t)cap, "%s traj: starting at corner 0", name);
+            return snprintf(buf, (size_t)cap, "%s traj: moving along side %d", name, leg);
+        }
+        case TGX_RECIPROCATING:
+            if (leg == 1 || leg == 3) return snprintf(buf, (size_t)cap, "Reciprocating: yaw flip at endpoint");
+            return snprintf(buf, (size_t)cap, leg == 0 ? "Reciprocating: forward" : "Reciprocating: reverse");
+        case TGX_BOUNCE:
+            if (last) return snprintf(buf, (size_t)cap, "Bounce: completed");
+            return snprintf(buf, (size_t)cap, leg == 0 ? "Bounce: ascending" : "Bounce: descending");
+        default: {
+            const char* name = letter[type - TGX_M];
+            const int nseg = type == TGX_M ? 4 : (type == TGX_I ? 5 : 3);
+            if (last) return snprintf(buf, (size_t)cap, "%s traj: completed", name);
+            return snprintf(buf, (size_t)cap, "%s traj: segment %d %s", name, leg % nseg, leg < nseg ? "fwd" : "rev");
+        }
+    }
+}
+
+/* Braking trajectories of the family.  Square.cpp:112-137, Rectangle.cpp:113-137, Reciprocating.cpp:81-107,
+ * M.cpp:88-113, I.cpp:96-121, T.cpp:94-119: v = |v_xy|, heading = atan2(vy, vx), position frozen at the setpoint,
+ * `while (v > 0) v = max(v - decel*dt, 0)`.  Bounce.cpp:74-103: vz *= 0.8 until |vz| <= 0.01. */
+static int64_t poly_stop(const tgx_params* p, const double* from, sink_t* sk, uint32_t* status, int64_t max_samples) {
+    const tgx_polyline_params* q = &p->u.poly;
+    double g[TGX_NCHAN];
+    if (p->type == TGX_BOUNCE) {
+        double vz = from[TGX_VZ];                             /* Bounce.cpp:81-83 */
+        double z = from[TGX_PZ];
+        double heading = from[TGX_PSI];
+        while (fabs(vz) > 0.01) {                             /* :91 */
+            if (sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+            vz *= 0.8;
+            if (fabs(vz) < 0.01) vz = 0.0;
+            bounce_goal(q->g[0], q->g[1], z, vz, heading, g);
+            sink_push(sk, g);
+        }
+        return sk->n;
+    }
+    double v = sqrt(pow(from[TGX_VX], 2) + pow(from[TGX_VY], 2));   /* Square.cpp:118 */
+    double heading = atan2(from[TGX_VY], from[TGX_VX]);             /* :119 */
+    double decel = (p->type == TGX_M || p->type == TGX_I || p->type == TGX_T) ? 1.0 : q->decel;   /* M.cpp:101 */
+    while (v > 0) {                                                 /* :125 */
+        double v_new = std_max(v - decel * p->dt, 0.0);
+        if (v_new == v || sk->n >= max_samples) { *status |= TGX_ST_TOO_LONG; return -1; }
+        v = v_new;
+        planar_goal(p, from[TGX_PX], from[TGX_PY], v, -decel, heading, g);
+        sink_push(sk, g);
+    }
+    return sk->n;
+}
+
+/* trajectoryInsideBounds of the family: Square.cpp:139-157, Rectangle.cpp:139-159, Reciprocating.cpp:109-122,
+ * Bounce.cpp:105-120, M.cpp:115-145, I.cpp:123-153, T.cpp:121-149. */
+static int point_inside(const double box[6], double x, double y, double z);
+
+static int poly_inside_bounds(const tgx_params* p, const double box[6]) {
+    const tgx_polyline_params* q = &p->u.poly;
+    if (p->type == TGX_RECIPROCATING)
+        return point_inside(box, q->g[0], q->g[1], q->g[2]) && point_inside(box, q->g[3], q->g[4], q->g[5]);
+    if (p->type == TGX_BOUNCE)
+        return point_inside(box, q->g[0], q->g[1], q->g[2]) && point_inside(box, q->g[0], q->g[1], q->g[3]);
+    double c = cos(q->orientation);
+    double s = sin(q->orientation);
+    if (p->type == TGX_SQUARE || p->type == TGX_RECTANGLE) {
+        const int rect = p->type == TGX_RECTANGLE;
+        double ha = q->g[0] / 2.0, hb = rect ? q->g[1] / 2.0 : ha;
+        double cx = rect ? q->g[2] : q->g[1], cy = rect ? q->g[3] : q->g[2];
+        double xs[4] = {cx + c * -ha - s * hb, cx + c * ha - s * hb, cx + c * ha - s * -hb, cx + c * -ha - s * -hb};
+        double ys[4] = {cy + s * -ha + c * hb, cy + s * ha + c * hb, cy + s * ha + c * -hb, cy + s * -ha + c * -hb};
+        for (int i = 0; i < 4; ++i)
+            if (!point_inside(box, xs[i], ys[i], p->alt)) return 0;
+        return 1;
+    }
+    double cx = q->g[0], cy = q->g[1], length = q->g[2], width = q->g[3];
+    double xs[6], ys[6];
+    int np;
+    if (p->type == TGX_M) {                                   /* M.cpp:120-126 */
+        np = 5;
+        xs[0] = cx - width / 2; ys[0] = cy - length / 2;
+        xs[1] = cx - width / 2; ys[1] = cy + length / 2;
+        xs[2] = cx;             ys[2] = cy - length / 2;
+        xs[3] = cx + width / 2; ys[3] = cy + length / 2;
+        xs[4] = cx + width / 2; ys[4] = cy - length / 2;
+    } else if (p->type == TGX_I) {                            /* I.cpp:128-135 */
+        np = 6;
+        xs[0] = cx - width / 2; ys[0] = cy + length / 2;
+        xs[1] = cx + width / 2; ys[1] = cy + length / 2;
+        xs[2] = cx;             ys[2] = cy + length / 2;
+        xs[3] = cx;             ys[3] = cy - length / 2;
+        xs[4] = cx - width / 2; ys[4] = cy - length / 2;
+        xs[5] = cx + width / 2; ys[5] = cy - length / 2;
+    } else {                                                  /* T.cpp:126-131 */
+        np = 4;
+        xs[0] = cx - width / 2; ys[0] = cy + length / 2;
+        xs[1] = cx + width / 2; ys[1] = cy + length / 2;
+        xs[2] = cx;             ys[2] = cy + length / 2;
+        xs[3] = cx;             ys[3] = cy - length / 2;
+    }
+    for (int i = 0; i < np; ++i) {                            /* M.cpp:131-143 */
+        double x_shift = xs[i] - cx;
+        double y_shift = ys[i] - cy;
+        double x_rot = c * x_shift - s * y_shift + cx;
+        double y_rot = s * x_shift + c * y_shift + cy;
+        if (!point_inside(box, x_rot, y_rot, p->alt)) return 0;
+    }
+    return 1;
+}
+
 int64_t orc_generate(const tgx_params* p, double* out, int64_t chan_stride, int64_t cap,
                      uint32_t* status, tgx_phases* ph, int64_t max_samples) {
     uint32_t st = 0;
@@ -373,6 +792,8 @@ int64_t orc_generate(const tgx_params* p, double* out, int64_t chan_stride, int6
     if (!params_ok(p)) {
         st |= TGX_ST_BAD_PARAM;
         n = -1;
+    } else if (TGX_IS_POLYLINE(p->type)) {
+        n = poly_generate(p, &sk, NULL, &st, max_samples);   /* index_msgs: orc_polyline_generate's leg_of */
     } else if (p->type == TGX_LINE) {
         n = line_generate(p, &sk, &st, ph, max_samples);
     } else if (p->type == TGX_BOOMERANG) {
@@ -397,6 +818,18 @@ int64_t orc_stop(const tgx_params* p, const double* from, double* out, int64_t c
     if (!params_ok(p)) {
         if (status) *status = TGX_ST_BAD_PARAM;
         return -1;
+    }
+    if (TGX_IS_POLYLINE(p->type)) {
+        phase_add(ph, 0, TGX_PH_PRESSED_END, 0.0, 0.0);           /* Square.cpp:123 */
+        if (poly_stop(p, from, &sk, &st, max_samples) < 0) {
+            if (ph) ph->n = 0;
+            if (status) *status = st;
+            return -1;
+        }
+        phase_add(ph, sk.n - 1, TGX_PH_STOPPED, 0.0, 0.0);        /* :129 */
+        if (sk.n > cap && out) st |= TGX_ST_TRUNCATED;
+        if (status) *status = st;
+        return sk.n;
     }
     /* 2D current (goal) vel: Circle.cpp:140-141, Line.cpp:124-125, Figure8.cpp:138-139 */
     double v = sqrt(pow(from[TGX_VX], 2) + pow(from[TGX_VY], 2));
@@ -454,6 +887,7 @@ static int point_inside(const double box[6], double x, double y, double z) {
 }
 
 int orc_inside_bounds(const tgx_params* p, const double box[6]) {
+    if (TGX_IS_POLYLINE(p->type)) return poly_inside_bounds(p, box);
     if (p->type == TGX_LINE || p->type == TGX_BOOMERANG) {
         /* Line::trajectoryInsideBounds, Line.cpp:154-173 (Boomerang.cpp:205-224 is a verbatim copy) */
         const tgx_line_params* l = &p->u.line;

@@ -2,7 +2,7 @@
  * traj_oracle.h — CPU ORACLE (test infrastructure, NOT product code).
  *
  * A plain-C restatement of the reference's trajectory samplers (jrached/trajectory_generator_ros2,
- * src/trajectories/{Circle,Line,Figure8}.cpp).  It exists only to CHECK the CUDA engine: nothing in the
+ * src/trajectories/{Circle,Line,Figure8,Boomerang,Square,Rectangle,Reciprocating,Bounce,M,I,T}.cpp).  It exists only to CHECK the CUDA engine: nothing in the
  * product path (trajectory_generator_ros2_b200/, include/) may link, import or call it.  Allowed users:
  * tests/, __graft_entry__.smoke(), and bench.py's cpu_baseline / --impl reference legs.
  *
@@ -35,6 +35,16 @@ extern "C" {
  * receives the index_msgs entries in emission order. */
 int64_t orc_generate(const tgx_params* p, double* out, int64_t chan_stride, int64_t cap,
                      uint32_t* status, tgx_phases* ph, int64_t max_samples);
+
+/* generateTraj of the constant-speed polyline family (Square.cpp:21-92, Rectangle.cpp:20-93, Reciprocating.cpp:24-60,
+ * Bounce.cpp:19-52, M.cpp:13-67, I.cpp:19-75, T.cpp:19-73), same output convention as orc_generate (which also accepts
+ * these types).  leg_of (may be NULL, `cap` entries) receives the leg of every sample in tgx_polyline_legs numbering
+ * (-1 for the Square / Rectangle start sample): the reference's per-sample index_msgs strings are a function of it. */
+int64_t orc_polyline_generate(const tgx_params* p, double* out, int64_t chan_stride, int64_t cap, uint32_t* status,
+                              int16_t* leg_of, int64_t max_samples);
+
+/* The reference's index_msgs text of sample k (of n) of a polyline trajectory whose leg is `leg`. */
+int orc_polyline_msg(int type, int leg, int64_t k, int64_t n, char* buf, int cap);
 
 /* Trajectory::generateStopTraj (Circle.cpp:132-169, Line.cpp:117-152, Figure8.cpp:130-167): brake from the
  * setpoint from[14] (tgx_channel order).  Same output convention.  Returns the number of braking samples. */

@@ -58,6 +58,11 @@ class Oracle:
                                             C.POINTER(C.c_int32), C.POINTER(C.c_uint32), _c_i64, C.c_int]
         L.orc_time_batch.restype = _c_i64
         L.orc_time_batch.argtypes = [C.c_void_p, _c_i64, _c_i64, C.c_int, _c_dp]
+        L.orc_polyline_generate.restype = _c_i64
+        L.orc_polyline_generate.argtypes = [C.c_void_p, _c_dp, _c_i64, _c_i64, C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_int16), _c_i64]
+        L.orc_polyline_msg.restype = C.c_int
+        L.orc_polyline_msg.argtypes = [C.c_int, C.c_int, _c_i64, _c_i64, C.c_char_p, C.c_int]
         L.orc_fnv1a64.restype = C.c_uint64
         L.orc_fnv1a64.argtypes = [_c_dp, _c_i64, C.c_uint64]
 
@@ -78,6 +83,25 @@ class Oracle:
         n2 = self.lib.orc_generate(p.ctypes.data, _ptr(out), n, n, C.byref(st2), ph.ctypes.data, max_samples)
         assert n2 == n
         return out, int(st2.value), ph[0]
+
+    def polyline_generate(self, p: np.ndarray, max_samples: int = abi.DEFAULT_MAX_SAMPLES):
+        """Polyline family -> (samples[14, N], status, leg_of[N] int16, index_msgs dict)."""
+        st = C.c_uint32(0)
+        n = self.lib.orc_polyline_generate(p.ctypes.data, None, 0, 0, C.byref(st), None, max_samples)
+        if n <= 0:
+            return np.zeros((abi.TGX_NCHAN, 0)), int(st.value), np.zeros(0, dtype=np.int16), {}
+        out = np.full((abi.TGX_NCHAN, n), np.nan)
+        legs = np.zeros(n, dtype=np.int16)
+        n2 = self.lib.orc_polyline_generate(p.ctypes.data, _ptr(out), n, n, C.byref(st), _ptr(legs, C.c_int16),
+                                            max_samples)
+        assert n2 == n
+        buf = C.create_string_buffer(128)
+        msgs = {}
+        t = int(p["type"][0])
+        for k in range(n):
+            self.lib.orc_polyline_msg(t, int(legs[k]), k, n, buf, 128)
+            msgs[k] = buf.value.decode()
+        return out, int(st.value), legs, msgs
 
     def stop(self, p: np.ndarray, from14: np.ndarray, max_samples: int = abi.DEFAULT_MAX_SAMPLES):
         from14 = np.ascontiguousarray(from14, dtype=np.float64)
@@ -148,7 +172,7 @@ class Oracle:
 class Reference:
     """Thin wrapper over oracle/_ref/libtrajref.so (the unmodified reference)."""
 
-    MSG_CAP = 1 << 16
+    MSG_CAP = 1 << 22   # the polyline family announces every sample
 
     def __init__(self, path: str = REF_SO):
         self.lib = C.CDLL(path)

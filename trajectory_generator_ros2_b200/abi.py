@@ -17,8 +17,18 @@ TGX_MAX_PHASES = 2 * TGX_MAX_VGOALS + 2
 
 # enum tgx_type
 TGX_CIRCLE, TGX_LINE, TGX_FIGURE8, TGX_BOOMERANG = 0, 1, 2, 3
+TGX_SQUARE, TGX_RECTANGLE, TGX_RECIPROCATING, TGX_BOUNCE, TGX_M, TGX_I, TGX_T = 4, 5, 6, 7, 8, 9, 10
+POLYLINE_TYPES = (TGX_SQUARE, TGX_RECTANGLE, TGX_RECIPROCATING, TGX_BOUNCE, TGX_M, TGX_I, TGX_T)
+TGX_POLY_TRIG_GIVEN = 1
+TGX_POLY_MAX_LEGS = 10
 # prefix of the index_msgs texts; Boomerang.cpp announces itself as "Line traj: ..." (Boomerang.cpp:44,55,64,94,134)
-TYPE_NAMES = {TGX_CIRCLE: "Circle", TGX_LINE: "Line", TGX_FIGURE8: "Figure8", TGX_BOOMERANG: "Line"}
+TYPE_NAMES = {TGX_CIRCLE: "Circle", TGX_LINE: "Line", TGX_FIGURE8: "Figure8", TGX_BOOMERANG: "Line",
+              TGX_SQUARE: "Square", TGX_RECTANGLE: "Rectangle", TGX_RECIPROCATING: "Reciprocating",
+              TGX_BOUNCE: "Bounce", TGX_M: "M", TGX_I: "I", TGX_T: "T"}
+
+
+def is_polyline(type_id: int) -> bool:
+    return TGX_SQUARE <= int(type_id) <= TGX_T
 
 # enum tgx_channel
 CHANNELS = ("px", "py", "pz", "vx", "vy", "vz", "ax", "ay", "az", "jx", "jy", "jz", "psi", "dpsi")
@@ -35,7 +45,8 @@ ST_VMAX_EXCEEDED = 1 << 6
 ST_AMAX_EXCEEDED = 1 << 7
 ST_TOO_LONG = 1 << 8
 ST_TRUNCATED = 1 << 9
-ST_FATAL_MASK = ST_FINAL_V_NONZERO | ST_LINE_END_NOT_B | ST_BAD_PARAM | ST_TOO_LONG
+ST_WRONG_PLANNER = 1 << 10
+ST_FATAL_MASK = ST_FINAL_V_NONZERO | ST_LINE_END_NOT_B | ST_BAD_PARAM | ST_TOO_LONG | ST_WRONG_PLANNER
 STATUS_NAMES = {
     ST_VGOALS_NOT_INCREASING: "VGOALS_NOT_INCREASING",
     ST_FINAL_V_NONZERO: "FINAL_V_NONZERO",
@@ -47,6 +58,7 @@ STATUS_NAMES = {
     ST_AMAX_EXCEEDED: "AMAX_EXCEEDED",
     ST_TOO_LONG: "TOO_LONG",
     ST_TRUNCATED: "TRUNCATED",
+    ST_WRONG_PLANNER: "WRONG_PLANNER",
 }
 
 # enum tgx_error
@@ -68,8 +80,13 @@ class LineParams(C.Structure):
                 ("v_goal", C.c_double), ("reserved", C.c_double * 4)]
 
 
+class PolylineParams(C.Structure):
+    _fields_ = [("t_traj", C.c_double), ("v_goal", C.c_double), ("decel", C.c_double), ("orientation", C.c_double),
+                ("cos_o", C.c_double), ("sin_o", C.c_double), ("g", C.c_double * 7)]
+
+
 class _ParamsUnion(C.Union):
-    _fields_ = [("orbit", OrbitParams), ("line", LineParams)]
+    _fields_ = [("orbit", OrbitParams), ("line", LineParams), ("poly", PolylineParams)]
 
 
 class Params(C.Structure):
@@ -97,6 +114,13 @@ class Phases(C.Structure):
                 ("value", C.c_double * TGX_MAX_PHASES), ("value2", C.c_double * TGX_MAX_PHASES)]
 
 
+class PolylineLegs(C.Structure):
+    """struct tgx_polyline_legs."""
+    _fields_ = [("n", C.c_int32), ("n_legs", C.c_int32), ("first_special", C.c_int32), ("last_special", C.c_int32),
+                ("period", C.c_int32), ("count", C.c_int32 * TGX_POLY_MAX_LEGS), ("reserved", C.c_int32)]
+
+
+assert C.sizeof(PolylineLegs) == 64, C.sizeof(PolylineLegs)
 assert C.sizeof(Params) == 128, C.sizeof(Params)
 assert C.sizeof(Limits) == 72, C.sizeof(Limits)
 assert C.sizeof(Layout) == 48, C.sizeof(Layout)
@@ -105,14 +129,24 @@ assert C.sizeof(Layout) == 48, C.sizeof(Layout)
 PARAMS_DTYPE = np.dtype({
     "names": ["type", "n_vgoals", "dt", "alt",
               "r", "cx", "cy", "t_traj", "accel", "v_goals",
-              "A", "B", "a1", "a3", "v_goal"],
+              "A", "B", "a1", "a3", "v_goal", "line_heading",
+              "poly_t_traj", "poly_v_goal", "poly_decel", "orientation", "cos_o", "sin_o", "g"],
     "formats": ["<i4", "<i4", "<f8", "<f8",
                 "<f8", "<f8", "<f8", "<f8", "<f8", ("<f8", (TGX_MAX_VGOALS,)),
-                ("<f8", (3,)), ("<f8", (3,)), "<f8", "<f8", "<f8"],
+                ("<f8", (3,)), ("<f8", (3,)), "<f8", "<f8", "<f8", "<f8",
+                "<f8", "<f8", "<f8", "<f8", "<f8", "<f8", ("<f8", (7,))],
     "offsets": [0, 4, 8, 16,
                 24, 32, 40, 48, 56, 64,
-                24, 48, 72, 80, 88],
+                24, 48, 72, 80, 88, 96,
+                24, 32, 40, 48, 56, 64, 72],
     "itemsize": 128,
+})
+
+LEGS_DTYPE = np.dtype({
+    "names": ["n", "n_legs", "first_special", "last_special", "period", "count"],
+    "formats": ["<i4", "<i4", "<i4", "<i4", "<i4", ("<i4", (TGX_POLY_MAX_LEGS,))],
+    "offsets": [0, 4, 8, 12, 16, 20],
+    "itemsize": 64,
 })
 
 PHASES_DTYPE = np.dtype({
@@ -184,6 +218,108 @@ def boomerang_params(alt, A, B, v_goals, a1, a3, dt) -> np.ndarray:
     p = line_params(alt, A, B, v_goals, a1, a3, dt)
     p["type"] = TGX_BOOMERANG
     return p
+
+
+def polyline_params(kind, dt, alt, t_traj, v_goals, decel, orientation, geometry) -> np.ndarray:
+    """One polyline-family record.  cos_o / sin_o are left to tgx_polyline_finalize_host (Engine.finalize_polyline)."""
+    p = np.zeros(1, dtype=PARAMS_DTYPE)
+    v_goals = list(v_goals)
+    p["type"] = kind
+    p["dt"], p["alt"] = dt, alt
+    p["poly_t_traj"] = t_traj
+    p["poly_v_goal"] = v_goals[0] if v_goals else 1.0          # v_goals_.empty() ? 1.0 : v_goals_[0] (Square.cpp:48)
+    p["poly_decel"] = decel
+    p["orientation"] = orientation
+    p["g"][0, :len(geometry)] = geometry
+    return p
+
+
+def square_params(alt, side_length, cx, cy, orientation, v_goals, t_traj, accel, dt) -> np.ndarray:
+    """Square.hpp:31-32."""
+    return polyline_params(TGX_SQUARE, dt, alt, t_traj, v_goals, accel, orientation, [side_length, cx, cy])
+
+
+def rectangle_params(alt, side_a, side_b, cx, cy, orientation, v_goals, t_traj, accel, dt) -> np.ndarray:
+    """Rectangle.hpp."""
+    return polyline_params(TGX_RECTANGLE, dt, alt, t_traj, v_goals, accel, orientation, [side_a, side_b, cx, cy])
+
+
+def reciprocating_params(alt, A, B, v_goals, a1, a3, t_traj, dt) -> np.ndarray:
+    """Reciprocating.hpp (a1 is stored by the class and never used)."""
+    return polyline_params(TGX_RECIPROCATING, dt, alt, t_traj, v_goals, a3, 0.0, list(A) + list(B))
+
+
+def bounce_params(cx, cy, Az, Bz, v_goals, t_traj, orientation, dt) -> np.ndarray:
+    """Bounce.hpp (no alt: z runs between Az and Bz)."""
+    return polyline_params(TGX_BOUNCE, dt, 0.0, t_traj, v_goals, 0.0, orientation, [cx, cy, Az, Bz])
+
+
+def letter_params(kind, cx, cy, length, width, alt, v_goals, t_traj, orientation, dt) -> np.ndarray:
+    """M.hpp / I.hpp / T.hpp."""
+    return polyline_params(kind, dt, alt, t_traj, v_goals, 1.0, orientation, [cx, cy, length, width])
+
+
+def polyline_leg_of(legs, k: int) -> int:
+    """Leg (tgx_polyline_legs numbering) of sample k; -1 for the Square / Rectangle start sample."""
+    n = int(legs["n"])
+    first = int(legs["first_special"])
+    if first and k == 0:
+        return -1
+    counts = [int(c) for c in legs["count"][:int(legs["n_legs"])]]
+    if int(legs["last_special"]) and k == n - 1:
+        # the yaw flip appended after the leg that t_traj cut short (Reciprocating.cpp:50-57)
+        return polyline_leg_of(legs, k - 1) + 1
+    m = (k - first) % int(legs["period"])
+    for leg, c in enumerate(counts):
+        if m < c:
+            return leg
+        m -= c
+    raise AssertionError("inconsistent tgx_polyline_legs record")
+
+
+def polyline_msg(type_id: int, leg: int, k: int, n: int) -> str:
+    """The reference's index_msgs text of sample k of n (Square.cpp:61,79,88; Reciprocating.cpp:47,57; Bounce.cpp:42,50;
+    M.cpp:57,65; I.cpp:65,73; T.cpp:63,71)."""
+    name = TYPE_NAMES[type_id]
+    last = k == n - 1
+    if type_id in (TGX_SQUARE, TGX_RECTANGLE):
+        if last:
+            return f"{name} traj: completed"
+        return f"{name} traj: starting at corner 0" if leg < 0 else f"{name} traj: moving along side {leg}"
+    if type_id == TGX_RECIPROCATING:
+        return ("Reciprocating: forward", "Reciprocating: yaw flip at endpoint", "Reciprocating: reverse",
+                "Reciprocating: yaw flip at endpoint")[leg]
+    if type_id == TGX_BOUNCE:
+        if last:
+            return "Bounce: completed"
+        return "Bounce: ascending" if leg == 0 else "Bounce: descending"
+    nseg = {TGX_M: 4, TGX_I: 5, TGX_T: 3}[type_id]
+    if last:
+        return f"{name} traj: completed"
+    return f"{name} traj: segment {leg % nseg} {'fwd' if leg < nseg else 'rev'}"
+
+
+def polyline_index_msgs(type_id: int, legs) -> dict:
+    """tgx_polyline_legs record -> {sample index: message} for every sample, like the reference's map."""
+    n = int(legs["n"])
+    first = int(legs["first_special"])
+    counts = [int(c) for c in legs["count"][:int(legs["n_legs"])]]
+    out = {}
+    k = 0
+    if first and n > 0:
+        out[0] = polyline_msg(type_id, -1, 0, n)
+        k = 1
+    leg = 0
+    while k < n:
+        for _ in range(counts[leg]):
+            if k >= n:
+                break
+            out[k] = polyline_msg(type_id, leg, k, n)
+            k += 1
+        leg = (leg + 1) % len(counts)
+    if int(legs["last_special"]) and n > 0:
+        out[n - 1] = polyline_msg(type_id, polyline_leg_of(legs, n - 1), n - 1, n)
+    return out
 
 
 def format_phase(type_id: int, kind: int, value: float, value2: float, stop_traj: bool = False) -> str:
