@@ -346,6 +346,14 @@ int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, cons
                       double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
                       tgx_phases* h_phases);
 
+/* tgx_generate_host that additionally returns, for polyline-family trajectories, the leg structure their per-sample
+ * index_msgs are a function of (h_legs[i].n == 0 for the other families).  A batch may mix families: every chunk is
+ * routed to tgx_plan and / or tgx_plan_polyline as its trajectories require, and polyline records without
+ * TGX_POLY_TRIG_GIVEN get the host libm's cos / sin (see tgx_polyline_params). */
+int tgx_generate_host_legs(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                           double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
+                           tgx_phases* h_phases, tgx_polyline_legs* h_legs);
+
 /* Full generateStopTraj: h_from[i*14..] is the setpoint being braked from. Same output layout. */
 int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const double* h_from,
                   double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,

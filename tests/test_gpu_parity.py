@@ -179,7 +179,7 @@ def test_bad_params_are_rejected(mode_engine, oracle):
     good = abi.circle_params(1.8, 3.4, 0, 0, [1.0], 2.0, 0.4, 0.01)
     bad = []
     for field, val in (("accel", 0.0), ("accel", -1.0), ("r", 0.0), ("dt", 0.0), ("dt", float("nan")),
-                       ("t_traj", float("inf")), ("n_vgoals", 0), ("n_vgoals", 9), ("type", 7)):
+                       ("t_traj", float("inf")), ("n_vgoals", 0), ("n_vgoals", 9), ("type", 99)):
         q = good.copy()
         q[field] = val
         bad.append(q)

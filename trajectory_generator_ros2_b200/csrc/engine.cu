@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -50,6 +51,16 @@ cudaError_t launch_selftest_division(int64_t n, uint64_t seed, int per_thread, u
                                      cudaStream_t stream);
 cudaError_t launch_plan_samples(const tgx_params* params, const double* state, int64_t n, TrajRec* recs, Seg* segs,
                                 Tile* tiles, int32_t* counts, uint32_t* status, cudaStream_t stream);
+
+cudaError_t launch_plan_poly(const tgx_params* params, int64_t n, const tgx_limits* lim, int64_t max_samples,
+                             int tile_shift, const void* cur_table, void* recs, int32_t* counts, uint32_t* status,
+                             int32_t* counts2, uint32_t* status2, tgx_polyline_legs* legs, int32_t* ntile,
+                             PlanStats* stats, bool skip_foreign, cudaStream_t stream);
+size_t poly_rec_bytes();
+cudaError_t launch_poly_tiles(int64_t n, const int32_t* ntile, const int64_t* tile_off, int tile_shift, Tile* tiles,
+                              cudaStream_t stream);
+cudaError_t launch_eval_poly(const PolyView& pv, int64_t ntiles, int tile_shift, int spt, const OutView& out,
+                             bool store, double* max_v, double* max_a, cudaStream_t stream);
 
 }  // namespace tgx
 
@@ -176,6 +187,13 @@ struct tgx_engine {
     int64_t phase_plans = 0;
     PinBuf h_totals;
 
+    // polyline-family plans (tgx_plan_polyline): leg records, and the work list of a ragged batch
+    DevBuf poly_recs, poly_tiles, h_legs[2];
+    bool plan_poly = false;                      // current plan is a polyline plan
+    bool poly_listed = false;                    // ... addressed through poly_tiles rather than blockIdx / tile_slab
+    int poly_tile_slab = 0;
+    int64_t poly_plans = 0;
+
     // current plan
     bool has_plan = false;
     int64_t plan_n = 0, plan_tiles = 0, plan_segs = 0, plan_samples = 0;
@@ -230,6 +248,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     if (n > 0x7fffffffLL) return TGX_ERR_INVALID;
     TGX_CUDA(cudaSetDevice(e->device));
     e->has_plan = false;
+    e->plan_poly = false;
     e->plan_n = e->plan_tiles = e->plan_segs = e->plan_samples = 0;
     if (total_samples) *total_samples = 0;
     if (n == 0) {
@@ -403,6 +422,89 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     return TGX_OK;
 }
 
+// Polyline-family planning: one replay-free pass (leg records, counts, tile counts), then either slab addressing
+// (dense batches: tile t of trajectory i is CTA i*slab + t) or a scanned work list (ragged batches).
+int plan_polyline_common(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits,
+                         int32_t* d_counts, uint32_t* d_status, tgx_polyline_legs* d_legs, int64_t* total_samples,
+                         bool skip_foreign, cudaStream_t stream) {
+    if (!e || n < 0 || (n > 0 && !d_params)) return TGX_ERR_INVALID;
+    if (n > 0x7fffffffLL) return TGX_ERR_INVALID;
+    TGX_CUDA(cudaSetDevice(e->device));
+    e->has_plan = false;
+    e->plan_n = e->plan_tiles = e->plan_segs = e->plan_samples = 0;
+    if (total_samples) *total_samples = 0;
+    e->plan_poly = true;
+    e->plan_packed = e->plan_phase = false;
+    if (n == 0) {
+        e->has_plan = true;
+        return TGX_OK;
+    }
+    int rc = ensure_traj_scratch(e, n);
+    if (rc) return rc;
+    if ((rc = e->poly_recs.reserve((size_t)n * tgx::poly_rec_bytes()))) return rc;
+    int32_t* cnt = e->cnt.as<int32_t>();
+    int32_t* ntile = e->ntile.as<int32_t>();
+    uint32_t* st = e->status.as<uint32_t>();
+    tgx::PlanStats* d_stats = e->stats.as<tgx::PlanStats>();
+    tgx::PlanStats* h_stats = reinterpret_cast<tgx::PlanStats*>(static_cast<int64_t*>(e->h_totals.p) + 4);
+
+    TGX_CUDA(tgx::launch_build_cur_table(d_params, e->max_samples, e->cur_table.p, stream));
+    TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+    TGX_CUDA(tgx::launch_plan_poly(d_params, n, limits, e->max_samples, e->tile_shift, e->cur_table.p, e->poly_recs.p,
+                                   d_counts, d_status, cnt, st, d_legs, ntile, d_stats, skip_foreign, stream));
+    e->launches += 2;
+    TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
+    TGX_CUDA(cudaStreamSynchronize(stream));
+    const int64_t tot_tiles = (int64_t)h_stats->total_tiles;
+    const int64_t slab_tiles = n * (int64_t)h_stats->max_ntile;
+    int64_t plan_tiles;
+    if (slab_tiles <= tot_tiles + tot_tiles / 4 + 1 && slab_tiles <= 0x7fffffffLL) {
+        e->poly_listed = false;
+        e->poly_tile_slab = std::max(h_stats->max_ntile, 1);
+        plan_tiles = tot_tiles > 0 ? slab_tiles : 0;
+    } else {
+        if (tot_tiles > 0x7fffffffLL) return TGX_ERR_CAPACITY;
+        int64_t* tile_off = e->tile_off.as<int64_t>();
+        TGX_CUDA(cudaMemsetAsync(ntile + n, 0, sizeof(int32_t), stream));
+        WideIter tile_in{ntile};
+        size_t need = 0;
+        TGX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, tile_in, tile_off, (int)(n + 1), stream));
+        if ((rc = e->cub_tmp.reserve(need))) return rc;
+        size_t tmp_bytes = e->cub_tmp.bytes;
+        TGX_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp_bytes, tile_in, tile_off, (int)(n + 1), stream));
+        if ((rc = e->poly_tiles.reserve((size_t)std::max<int64_t>(tot_tiles, 1) * sizeof(tgx::Tile)))) return rc;
+        TGX_CUDA(tgx::launch_poly_tiles(n, ntile, tile_off, e->tile_shift, e->poly_tiles.as<tgx::Tile>(), stream));
+        e->launches += 1;
+        e->poly_listed = true;
+        e->poly_tile_slab = 0;
+        plan_tiles = tot_tiles;
+    }
+    e->poly_plans += 1;
+    e->has_plan = true;
+    e->plan_n = n;
+    e->plan_tiles = plan_tiles;
+    e->plan_segs = 0;
+    e->plan_samples = (int64_t)h_stats->total_samples;
+    if (total_samples) *total_samples = e->plan_samples;
+    return TGX_OK;
+}
+
+tgx::PolyView poly_view(const tgx_engine* e) {
+    tgx::PolyView pv{};
+    pv.recs = e->poly_recs.as<int4>();
+    pv.tiles = e->poly_listed ? e->poly_tiles.as<tgx::Tile>() : nullptr;
+    pv.tile_slab = e->poly_tile_slab;
+    return pv;
+}
+
+// Evaluation of the current plan, whichever family planned it.
+cudaError_t launch_current(const tgx_engine* e, const tgx::OutView& out, bool store, double* max_v, double* max_a,
+                           cudaStream_t s) {
+    if (e->plan_poly)
+        return tgx::launch_eval_poly(poly_view(e), e->plan_tiles, e->tile_shift, e->spt, out, store, max_v, max_a, s);
+    return tgx::launch_eval(table_view(e), e->plan_tiles, e->tile_shift, e->spt, out, store, max_v, max_a, s);
+}
+
 int check_layout(const tgx_layout* out, int spt) {
     if (!out || !out->d_base || out->capacity < 0) return TGX_ERR_INVALID;
     const int64_t a = 4;   // doubles; keeps both store widths legal and rows sector-aligned
@@ -468,9 +570,10 @@ int tgx_destroy(tgx_engine* e) {
     cudaSetDevice(e->device);
     DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
                       &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats, &e->packets,
-                      &e->phase};
+                      &e->phase, &e->poly_recs, &e->poly_tiles};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
+        e->h_legs[i].release();
         e->h_params[i].release();
         e->h_out[i].release();
         e->h_cnt[i].release();
@@ -580,7 +683,10 @@ int tgx_count(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_li
     TGX_CUDA(tgx::launch_build_cur_table(d_params, e->max_samples, e->cur_table.p, s));
     TGX_CUDA(tgx::launch_plan_count(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, false,
                                     e->cur_table.p, d_counts, d_status, nullptr, nullptr, s));
-    e->launches += 2;
+    // polyline-family trajectories (which the pass above marked WRONG_PLANNER) are counted by their own planner
+    TGX_CUDA(tgx::launch_plan_poly(d_params, n, limits, e->max_samples, e->tile_shift, e->cur_table.p, nullptr,
+                                   d_counts, d_status, nullptr, nullptr, nullptr, nullptr, nullptr, true, s));
+    e->launches += 3;
     return TGX_OK;
 }
 
@@ -588,6 +694,27 @@ int tgx_plan(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_lim
              uint32_t* d_status, tgx_phases* d_phases, int64_t* total_samples, void* stream) {
     return plan_common(e, d_params, nullptr, n, limits, d_counts, d_status, d_phases, total_samples,
                        static_cast<cudaStream_t>(stream));
+}
+
+int tgx_plan_polyline(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits,
+                      int32_t* d_counts, uint32_t* d_status, tgx_polyline_legs* d_legs, int64_t* total_samples,
+                      void* stream) {
+    return plan_polyline_common(e, d_params, n, limits, d_counts, d_status, d_legs, total_samples, false,
+                                static_cast<cudaStream_t>(stream));
+}
+
+// cos / sin of `orientation` from the HOST libm, the one a reference build on this machine links (tgx.h:
+// tgx_polyline_params).  Parameter preparation only: two libm calls per trajectory, no sampling.
+int tgx_polyline_finalize_host(tgx_params* h_params, int64_t n) {
+    if (n < 0 || (n > 0 && !h_params)) return TGX_ERR_INVALID;
+    for (int64_t i = 0; i < n; ++i) {
+        tgx_params& p = h_params[i];
+        if (!TGX_IS_POLYLINE(p.type)) continue;
+        p.u.poly.cos_o = std::cos(p.u.poly.orientation);
+        p.u.poly.sin_o = std::sin(p.u.poly.orientation);
+        p.n_vgoals |= TGX_POLY_TRIG_GIVEN;
+    }
+    return TGX_OK;
 }
 
 int tgx_plan_stop(tgx_engine* e, const tgx_params* d_params, int64_t n, const double* d_from, int32_t* d_counts,
@@ -617,6 +744,7 @@ int tgx_plan_samples(tgx_engine* e, const tgx_params* d_params, int64_t n, const
     e->has_plan = true;
     e->plan_packed = false;
     e->plan_phase = false;
+    e->plan_poly = false;
     e->plan_n = n;
     e->plan_tiles = n;
     e->plan_segs = n;
@@ -635,8 +763,7 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
     if (d_max_v) TGX_CUDA(cudaMemsetAsync(d_max_v, 0, (size_t)e->plan_n * sizeof(double), s));
     if (d_max_a) TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)e->plan_n * sizeof(double), s));
     if (e->plan_tiles == 0) return TGX_OK;
-    TGX_CUDA(tgx::launch_eval(table_view(e), e->plan_tiles, e->tile_shift, e->spt, make_view(out), true, d_max_v,
-                              d_max_a, s));
+    TGX_CUDA(launch_current(e, make_view(out), true, d_max_v, d_max_a, s));
     e->launches += 1;
     return TGX_OK;
 }
@@ -662,8 +789,7 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
     TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)n * sizeof(double), s));
     if (e->plan_tiles > 0) {
         tgx::OutView none{};
-        TGX_CUDA(tgx::launch_eval(table_view(e), e->plan_tiles, e->tile_shift, e->spt, none, false, d_max_v, d_max_a,
-                                  s));
+        TGX_CUDA(launch_current(e, none, false, d_max_v, d_max_a, s));
         e->launches += 1;
     }
     TGX_CUDA(tgx::launch_feasibility_finalize(n, e->status.as<uint32_t>(), d_max_v, d_max_a, limits->v_max,
@@ -721,6 +847,39 @@ static int host_streams(tgx_engine* e) {
     return TGX_OK;
 }
 
+// What a block of host-resident parameter records contains.
+struct KindMix {
+    bool classic = false, poly = false, bounce = false;
+};
+
+// Polyline-family records whose cos_o / sin_o the caller did not provide get the host libm's values (tgx.h:
+// tgx_polyline_params) in a private copy; returns the array to upload (the caller's own when nothing had to change).
+static const tgx_params* stage_params(const tgx_params* h_params, int64_t n, std::vector<tgx_params>& staged,
+                                      KindMix* mix) {
+    bool need_copy = false;
+    KindMix m;
+    for (int64_t i = 0; i < n; ++i) {
+        const tgx_params& p = h_params[i];
+        if (TGX_IS_POLYLINE(p.type)) {
+            m.poly = true;
+            if (p.type == TGX_BOUNCE) m.bounce = true;
+            if (!(p.n_vgoals & TGX_POLY_TRIG_GIVEN)) need_copy = true;
+        } else {
+            m.classic = true;
+        }
+    }
+    if (mix) *mix = m;
+    if (!need_copy) return h_params;
+    staged.assign(h_params, h_params + n);
+    for (tgx_params& p : staged) {
+        if (!TGX_IS_POLYLINE(p.type) || (p.n_vgoals & TGX_POLY_TRIG_GIVEN)) continue;
+        p.u.poly.cos_o = std::cos(p.u.poly.orientation);
+        p.u.poly.sin_o = std::sin(p.u.poly.orientation);
+        p.n_vgoals |= TGX_POLY_TRIG_GIVEN;
+    }
+    return staged.data();
+}
+
 int tgx_count_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
                    int32_t* h_counts, uint32_t* h_status) {
     if (!e || n < 0 || (n > 0 && !h_params)) return TGX_ERR_INVALID;
@@ -732,7 +891,9 @@ int tgx_count_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const t
     if ((rc = e->h_params[0].reserve((size_t)n * sizeof(tgx_params)))) return rc;
     if ((rc = e->h_cnt[0].reserve((size_t)n * sizeof(int32_t)))) return rc;
     if ((rc = e->h_st[0].reserve((size_t)n * sizeof(uint32_t)))) return rc;
-    TGX_CUDA(cudaMemcpyAsync(e->h_params[0].p, h_params, (size_t)n * sizeof(tgx_params), cudaMemcpyHostToDevice, s));
+    std::vector<tgx_params> staged;
+    const tgx_params* src = stage_params(h_params, n, staged, nullptr);
+    TGX_CUDA(cudaMemcpyAsync(e->h_params[0].p, src, (size_t)n * sizeof(tgx_params), cudaMemcpyHostToDevice, s));
     rc = tgx_count(e, e->h_params[0].as<tgx_params>(), n, limits, e->h_cnt[0].as<int32_t>(),
                    e->h_st[0].as<uint32_t>(), s);
     if (rc) return rc;
@@ -748,7 +909,7 @@ constexpr uint32_t kVaryingChannels = 0x3fffu & ~((1u << TGX_PZ) | (1u << TGX_VZ
 // Shared body of tgx_generate_host / tgx_stop_host.
 static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_from, int64_t n,
                     const tgx_limits* limits, double* h_out, int64_t capacity, int32_t* h_counts,
-                    uint32_t* h_status, tgx_phases* h_phases) {
+                    uint32_t* h_status, tgx_phases* h_phases, tgx_polyline_legs* h_legs) {
     if (!e || n < 0 || (n > 0 && (!h_params || !h_out)) || capacity < 0) return TGX_ERR_INVALID;
     if (capacity % 4 != 0) return TGX_ERR_ALIGNMENT;
     if (n == 0) return TGX_OK;
@@ -769,12 +930,17 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         if ((rc = e->h_st[b].reserve((size_t)chunk * sizeof(uint32_t)))) return rc;
         if (h_phases && (rc = e->h_ph[b].reserve((size_t)chunk * sizeof(tgx_phases)))) return rc;
         if (h_from && (rc = e->h_from[b].reserve((size_t)chunk * TGX_NCHAN * sizeof(double)))) return rc;
+        if (h_legs && (rc = e->h_legs[b].reserve((size_t)chunk * sizeof(tgx_polyline_legs)))) return rc;
     }
+    // Bounce moves along z (Bounce.cpp:39-41): its z-channels are not constants
+    KindMix whole;
+    for (int64_t i = 0; i < n && !whole.bounce; ++i)
+        if (h_params[i].type == TGX_BOUNCE) whole.bounce = true;
 
     // The z-components are literal constants in the reference (p.z = alt_, v.z = a.z = j.z = 0: Circle.cpp:109-121,
     // Line.cpp:99-108, Figure8.cpp:110-119).  They are not worth 29 % of the PCIe traffic: the device evaluates and
     // ships the 10 varying planes, and host threads write the 4 constant rows of every trajectory meanwhile.
-    const bool fill = e->host_fill_constants && capacity > 0;
+    const bool fill = e->host_fill_constants && capacity > 0 && !whole.bounce;
     std::vector<std::thread> fillers;
     if (fill) {
         unsigned hw = std::thread::hardware_concurrency();
@@ -808,29 +974,45 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         // the plan tables are shared by both slots: do not re-plan before the previous chunk's evaluation is done
         // (its D2H copy, the slow part, still overlaps with this chunk's planning and evaluation)
         if (ci >= 1) TGX_CUDA(cudaStreamWaitEvent(s, e->hev_eval, 0));
-        TGX_CUDA(cudaMemcpyAsync(e->h_params[b].p, h_params + lo, (size_t)m * sizeof(tgx_params),
-                                 cudaMemcpyHostToDevice, s));
+        KindMix mix;
+        std::vector<tgx_params> staged;
+        const tgx_params* src = stage_params(h_params + lo, m, staged, &mix);
+        TGX_CUDA(cudaMemcpyAsync(e->h_params[b].p, src, (size_t)m * sizeof(tgx_params), cudaMemcpyHostToDevice, s));
         if (h_from)
             TGX_CUDA(cudaMemcpyAsync(e->h_from[b].p, h_from + lo * TGX_NCHAN, (size_t)m * TGX_NCHAN * sizeof(double),
                                      cudaMemcpyHostToDevice, s));
         tgx_phases* d_ph = h_phases ? e->h_ph[b].as<tgx_phases>() : nullptr;
-        // planning synchronises stream s once; the other slot's D2H copies keep running meanwhile
-        if (h_from)
-            rc = tgx_plan_stop(e, e->h_params[b].as<tgx_params>(), m, e->h_from[b].as<double>(),
-                               e->h_cnt[b].as<int32_t>(), e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
-        else
-            rc = tgx_plan(e, e->h_params[b].as<tgx_params>(), m, limits, e->h_cnt[b].as<int32_t>(),
-                          e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
-        if (rc) return rc;
-        if (capacity > 0) {
-            tgx_layout lay{};
-            lay.d_base = e->h_out[b].as<double>();
-            lay.traj_stride = TGX_NCHAN * capacity;
-            lay.chan_stride = capacity;
-            lay.capacity = capacity;
-            lay.channel_mask = fill ? kVaryingChannels : 0;
-            rc = tgx_eval(e, &lay, nullptr, nullptr, s);
+        tgx_polyline_legs* d_legs = h_legs ? e->h_legs[b].as<tgx_polyline_legs>() : nullptr;
+        if (d_legs) TGX_CUDA(cudaMemsetAsync(d_legs, 0, (size_t)m * sizeof(tgx_polyline_legs), s));
+        tgx_layout lay{};
+        lay.d_base = e->h_out[b].as<double>();
+        lay.traj_stride = TGX_NCHAN * capacity;
+        lay.chan_stride = capacity;
+        lay.capacity = capacity;
+        lay.channel_mask = fill ? kVaryingChannels : 0;
+        // planning synchronises stream s once; the other slot's D2H copies keep running meanwhile.  Braking plans take
+        // every family in one pass; generateTraj plans route each family to its own planner (a mixed chunk is planned
+        // and evaluated twice, each pass writing only its own trajectories' rows).
+        const bool pass_classic = h_from || mix.classic;
+        const bool pass_poly = !h_from && mix.poly;
+        if (pass_classic) {
+            if (h_from)
+                rc = tgx_plan_stop(e, e->h_params[b].as<tgx_params>(), m, e->h_from[b].as<double>(),
+                                   e->h_cnt[b].as<int32_t>(), e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
+            else
+                rc = tgx_plan(e, e->h_params[b].as<tgx_params>(), m, limits, e->h_cnt[b].as<int32_t>(),
+                              e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
             if (rc) return rc;
+            if (capacity > 0 && (rc = tgx_eval(e, &lay, nullptr, nullptr, s))) return rc;
+        }
+        if (pass_poly) {
+            if (d_ph && !pass_classic) TGX_CUDA(cudaMemsetAsync(d_ph, 0, (size_t)m * sizeof(tgx_phases), s));
+            rc = plan_polyline_common(e, e->h_params[b].as<tgx_params>(), m, limits, e->h_cnt[b].as<int32_t>(),
+                                      e->h_st[b].as<uint32_t>(), d_legs, nullptr, pass_classic, s);
+            if (rc) return rc;
+            if (capacity > 0 && (rc = tgx_eval(e, &lay, nullptr, nullptr, s))) return rc;
+        }
+        if (capacity > 0) {
             TGX_CUDA(cudaEventRecord(e->hev_eval, s));
             if (fill) {
                 // the varying planes come in adjacent pairs (px,py | vx,vy | ax,ay | jx,jy | psi,dpsi): five 2-D copies,
@@ -853,6 +1035,9 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
             TGX_CUDA(cudaMemcpyAsync(h_status + lo, e->h_st[b].p, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (h_phases)
             TGX_CUDA(cudaMemcpyAsync(h_phases + lo, e->h_ph[b].p, (size_t)m * sizeof(tgx_phases), cudaMemcpyDeviceToHost, s));
+        if (h_legs)
+            TGX_CUDA(cudaMemcpyAsync(h_legs + lo, e->h_legs[b].p, (size_t)m * sizeof(tgx_polyline_legs),
+                                     cudaMemcpyDeviceToHost, s));
         TGX_CUDA(cudaEventRecord(e->hev[b], s));
     }
     TGX_CUDA(cudaStreamSynchronize(e->hs[0]));
@@ -896,13 +1081,19 @@ int tgx_sample_host(tgx_engine* e, const tgx_params* h_params, double v, double 
 
 int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits, double* h_out,
                       int64_t capacity, int32_t* h_counts, uint32_t* h_status, tgx_phases* h_phases) {
-    return host_run(e, h_params, nullptr, n, limits, h_out, capacity, h_counts, h_status, h_phases);
+    return host_run(e, h_params, nullptr, n, limits, h_out, capacity, h_counts, h_status, h_phases, nullptr);
+}
+
+int tgx_generate_host_legs(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                           double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
+                           tgx_phases* h_phases, tgx_polyline_legs* h_legs) {
+    return host_run(e, h_params, nullptr, n, limits, h_out, capacity, h_counts, h_status, h_phases, h_legs);
 }
 
 int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const double* h_from, double* h_out,
                   int64_t capacity, int32_t* h_counts, uint32_t* h_status, tgx_phases* h_phases) {
     if (n > 0 && !h_from) return TGX_ERR_INVALID;
-    return host_run(e, h_params, h_from, n, nullptr, h_out, capacity, h_counts, h_status, h_phases);
+    return host_run(e, h_params, h_from, n, nullptr, h_out, capacity, h_counts, h_status, h_phases, nullptr);
 }
 
 }  // extern "C"

@@ -18,59 +18,13 @@
 #include <cuda_runtime.h>
 
 #include "tgx_internal.cuh"
+#include "store.cuh"
 
 namespace tgx {
 
 namespace {
 
 constexpr double kPiOver2 = 1.57079632679489661923;
-
-// POLICY: 0 = .cs (streaming, evict-first), 1 = default write-back, 2 = L1::no_allocate + L2::evict_first
-template <int SPT, int POLICY>
-struct VecStore;
-
-template <int POLICY>
-struct VecStore<2, POLICY> {
-    static __device__ __forceinline__ void st(double* p, const double (&x)[2]) {
-        if (POLICY == 0)
-            asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x[0]), "d"(x[1]) : "memory");
-        else if (POLICY == 1)
-            asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x[0]), "d"(x[1]) : "memory");
-        else
-            asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x[0]), "d"(x[1]) : "memory");
-    }
-};
-
-template <int POLICY>
-struct VecStore<4, POLICY> {
-    static __device__ __forceinline__ void st(double* p, const double (&x)[4]) {
-        if (POLICY == 0)
-            asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
-                         "d"(x[3]) : "memory");
-        else if (POLICY == 1)
-            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
-                         "d"(x[3]) : "memory");
-        else
-            asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p),
-                         "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
-    }
-};
-
-#ifndef TGX_STORE_POLICY
-#define TGX_STORE_POLICY 0
-#endif
-
-// Store SPT adjacent samples of one channel; nvalid < SPT only on a trajectory's last, partial vector.
-template <int SPT>
-__device__ __forceinline__ void store_channel(double* p, const double (&x)[SPT], int nvalid) {
-    if (nvalid >= SPT) {
-        VecStore<SPT, TGX_STORE_POLICY>::st(p, x);
-    } else {
-#pragma unroll
-        for (int u = 0; u < SPT; ++u)
-            if (u < nvalid) __stcs(p + u, x[u]);
-    }
-}
 
 // Position of sample k inside segment sg: j = k - kb, the (double) step count fj the closed forms use, and v.
 // On the step where the reference's std::min / std::max clamp fired (flag set, j == n) v is exactly the clamp
@@ -93,17 +47,6 @@ __device__ __forceinline__ SegPos seg_pos(const Seg& sg, int k) {
     q.tri = 0.5 * (q.fj * (q.fj + 1.0));   // j(j+1) < 2^53: exact
     q.v = q.clamp ? sg.vclamp : fma(q.fj, sg.dv, sg.vb);
     return q;
-}
-
-__device__ __forceinline__ double warp_max(double x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
-}
-
-__device__ __forceinline__ void atomic_max_nonneg(double* addr, double x) {
-    // For non-negative doubles the IEEE bit pattern is monotone in the value.
-    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(x));
 }
 
 }  // namespace
@@ -297,7 +240,61 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     } while (0)
 
         double o[SPT];
-        if (type == TGX_LINE) {
+        if (type == kRecStatic) {
+            // ---- braking goals of the polyline family: createSquareGoal(last.p.x, last.p.y, v, -accel, heading) and
+            //      its copies (Square.cpp:126-127, M.cpp:103-104), createBounceGoal(cx, cy, z, vz, heading)
+            //      (Bounce.cpp:94): frozen position, velocity / acceleration along a fixed direction --------------
+            const double dx = s_rec.f[4], dy = s_rec.f[5], dz = s_rec.f[6];
+            double v[SPT], acc[SPT];
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) {
+                const Seg& sg = s_seg[si[u]];
+                v[u] = seg_pos(sg, k0 + u).v;
+                acc[u] = sg.acc;
+            }
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = s_rec.f[0];
+            TGX_STORE(TGX_PX, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = s_rec.f[1];
+            TGX_STORE(TGX_PY, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = s_rec.f[2];
+            TGX_STORE(TGX_PZ, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = v[u] * dx;
+            TGX_STORE(TGX_VX, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = v[u] * dy;
+            TGX_STORE(TGX_VY, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = v[u] * dz;
+            TGX_STORE(TGX_VZ, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = acc[u] * dx;
+            TGX_STORE(TGX_AX, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = acc[u] * dy;
+            TGX_STORE(TGX_AY, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = 0.0;
+            TGX_STORE(TGX_AZ, o);
+            TGX_STORE(TGX_JX, o);
+            TGX_STORE(TGX_JY, o);
+            TGX_STORE(TGX_JZ, o);
+            TGX_STORE(TGX_DPSI, o);
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) o[u] = s_rec.f[3];
+            TGX_STORE(TGX_PSI, o);
+            if (REDUCE) {
+#pragma unroll
+                for (int u = 0; u < SPT; ++u)
+                    if (u < nvalid) {
+                        best_v2 = fmax(best_v2, v[u] * v[u]);                       // the direction is a unit vector
+                        best_a2 = fmax(best_a2, acc[u] * acc[u] * (dx * dx + dy * dy));
+                    }
+            }
+        } else if (type == TGX_LINE) {
             // ---- Line::createLineGoal, Line.cpp:91-115 ------------------------------------------------
             const double c = s_rec.f[0], s = s_rec.f[1], theta = s_rec.f[2], alt = s_rec.f[3], dt = s_rec.f[4];
             const double cdt = c * dt, sdt = s * dt;

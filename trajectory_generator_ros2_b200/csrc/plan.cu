@@ -14,21 +14,11 @@
 // Output of a plan: TrajRec / Seg / Tile tables (tgx_internal.cuh) that eval.cu consumes, plus the caller-visible
 // counts, status bits and index_msgs (tgx_phases).
 #include "tgx_internal.cuh"
+#include "replay_common.cuh"
 
 namespace tgx {
 
 namespace {
-
-__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
-
-// libstdc++ std::min(a, b) / std::max(a, b)
-__device__ __forceinline__ double std_min(double a, double b) { return (b < a) ? b : a; }
-__device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }
-
-__device__ __forceinline__ bool finite_pos(double x) { return isfinite(x) && x > 0.0; }
 
 // Same acceptance rule as the node-side validation (TrajectoryGenerator.cpp:184-195, 268-277) plus the
 // conditions under which the reference's loops cannot terminate (dt <= 0, r <= 0, non-finite input).
@@ -53,6 +43,7 @@ __device__ bool params_ok(const tgx_params& p) {
 }
 
 __device__ __forceinline__ bool is_line_like(int type) { return type == TGX_LINE || type == TGX_BOOMERANG; }
+__device__ __forceinline__ bool is_orbit(int type) { return type == TGX_CIRCLE || type == TGX_FIGURE8; }
 
 // Collects what a replay produces.  In counting mode (segs == nullptr) it only counts.
 struct Emitter {
@@ -134,36 +125,6 @@ struct Emitter {
         if (ph) ph->n = nph < TGX_MAX_PHASES ? nph : TGX_MAX_PHASES;
     }
 };
-
-// ---- skip-ahead for x <- fl(x + a) with a constant addend -------------------------------------------------
-// While x stays inside one binade [2^E, 2^(E+1)] (same sign), every exact sum x + a is rounded to the same grid
-// of spacing u = 2^(E-52), so unless a is an odd multiple of u/2 (a tie, where round-half-even alternates) each step
-// adds exactly the same inc = fl(x + a) - x and the reference's running sum is an exact arithmetic progression.
-// Given one real step x0 -> x1 this returns how many FURTHER steps are guaranteed to add exactly x1 - x0
-// (0 when the step crossed a binade, hit a tie, or the values are zero / subnormal-ish).
-__device__ __forceinline__ long long regular_run(double x0, double x1, double a) {
-    const long long i0 = __double_as_longlong(x0), i1 = __double_as_longlong(x1);
-    if (((i0 ^ i1) >> 52) != 0) return 0;                 // sign or exponent changed: an irregular (crossing) step
-    const int e = (int)((i1 >> 52) & 0x7ff);
-    if (e < 64 || e == 0x7ff) return 0;                   // zero, subnormal, tiny or non-finite: step one by one
-    const double inc = dsub(x1, x0);                      // exact
-    if (inc == 0.0) return 1LL << 40;                     // |a| < u/2: x does not move while it stays in this binade
-    const double lo = __longlong_as_double(i1 & 0x7ff0000000000000LL);   // 2^E
-    const double r = fabs(a) / dmul(lo, 0x1p-53);         // |a| in units of u/2 (exact scaling)
-    if (r < 0x1p53 && r == rint(r) && (((long long)r) & 1LL)) return 0;  // tie: increments alternate
-    const double ax = fabs(x1), ai = fabs(inc);
-    const bool growing = (inc > 0.0) == (x1 > 0.0);
-    const double room = growing ? dsub(dmul(2.0, lo), ax) : dsub(ax, lo);   // exact distance to the binade edge
-    const double q = floor(ddiv(room, ai));
-    long long J = q > 1e15 ? (1LL << 40) : (long long)q;
-    // exact check: after J further steps the value must still lie in [2^E, 2^(E+1)]
-    while (J > 0) {
-        const double y = fabs(fma((double)J, inc, x1));
-        if (growing ? (y <= dmul(2.0, lo)) : (y >= lo)) break;
-        --J;
-    }
-    return J;
-}
 
 // One velocity ramp of the reference (up: std::min clamp at v_goal; down: std::max clamp at 0), shared by all
 // three classes.  Returns false when the reference would never terminate / the sample guard is hit.
@@ -261,44 +222,6 @@ __device__ __forceinline__ bool ramp(double& v, double target, double adt, doubl
     return true;
 }
 
-// ---- the hold counter: current_t_traj_ += dt_ -----------------------------------------------------------------
-// `double cur = 0; while (cur < t_hold) { ...; cur += dt; }` (Circle.cpp:62-71): the number of iterations is the
-// smallest m with c_m >= t_hold where c_0 = 0, c_m = fl(c_{m-1} + dt).  That sequence depends on dt alone, and by
-// the binade argument above it is piecewise an exact arithmetic progression: (m0, c0, inc, cnt) says "after m0
-// steps cur == c0, and each of the next cnt steps adds exactly inc".  A batch almost always shares one dt
-// (1/pub_freq, TrajectoryGenerator.cpp:171-172), so the runs are tabulated once per plan by a one-thread kernel and
-// every trajectory looks its hold length up; a trajectory with a different dt walks the runs itself.
-constexpr int kCurTableMax = 192;
-
-struct CurTable {
-    double dt;
-    int32_t n;            // entries
-    int32_t stagnates;    // after the last entry cur stops changing (dt < ulp/2): longer holds never terminate
-    long long m_end;      // steps covered by the table
-    long long m0[kCurTableMax];
-    long long cnt[kCurTableMax];
-    double c0[kCurTableMax];
-    double inc[kCurTableMax];
-};
-
-// One run of the counter starting from (m, cur): returns false on stagnation.
-__device__ __forceinline__ bool cur_run(double cur, double dt, double& inc, long long& cnt) {
-    const double cn = dadd(cur, dt);
-    if (cn == cur) return false;
-    inc = dsub(cn, cur);
-    cnt = 1 + regular_run(cur, cn, dt);
-    return true;
-}
-
-// Smallest j in [1, cnt] with c0 + j*inc >= t, given that c0 < t and c0 + cnt*inc >= t (all partial sums exact).
-__device__ __forceinline__ long long steps_to_reach(double c0, double inc, long long cnt, double t) {
-    const double g = ceil(ddiv(dsub(t, c0), inc));
-    long long j = g < 1.0 ? 1 : (g > (double)cnt ? cnt : (long long)g);
-    while (j > 1 && fma((double)(j - 1), inc, c0) >= t) --j;
-    while (j < cnt && fma((double)j, inc, c0) < t) ++j;
-    return j;
-}
-
 __global__ void build_cur_table_kernel(const tgx_params* __restrict__ params, int64_t max_samples,
                                        CurTable* __restrict__ tab) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -327,38 +250,6 @@ __global__ void build_cur_table_kernel(const tgx_params* __restrict__ params, in
     }
     tab->n = n;
     tab->m_end = m;
-}
-
-// Number of hold iterations for t_hold, or -1 if the reference would not terminate within `limit` more samples.
-__device__ long long hold_steps(double t_hold, double dt, long long limit, const CurTable* __restrict__ tab) {
-    if (!(0.0 < t_hold)) return 0;
-    if (tab && tab->dt == dt && tab->n > 0) {
-        // largest entry whose start value is below t_hold (c0 is increasing, c0[0] = 0 < t_hold)
-        int lo = 0, hi = tab->n - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tab->c0[mid] < t_hold) lo = mid; else hi = mid - 1;
-        }
-        const double c0 = tab->c0[lo], inc = tab->inc[lo];
-        const long long cnt = tab->cnt[lo];
-        if (fma((double)cnt, inc, c0) >= t_hold) {
-            const long long m = tab->m0[lo] + steps_to_reach(c0, inc, cnt, t_hold);
-            return m <= limit ? m : -1;
-        }
-        // beyond the table: never terminates (stagnation), exceeds the guard, or the table was cut short
-        if (tab->stagnates || tab->m_end > limit) return -1;
-    }
-    long long m = 0;
-    double cur = 0.0;
-    while (cur < t_hold) {
-        double inc;
-        long long cnt;
-        if (m > limit || !cur_run(cur, dt, inc, cnt)) return -1;
-        if (fma((double)cnt, inc, cur) >= t_hold) cnt = steps_to_reach(cur, inc, cnt, t_hold);
-        cur = fma((double)cnt, inc, cur);
-        m += cnt;
-    }
-    return m <= limit ? m : -1;
 }
 
 // The constant-speed phase: `while (current_t_traj_ < t) { ...; current_t_traj_ += dt_; }`
@@ -608,7 +499,9 @@ template <bool FILL, bool STATE, bool XR>
 __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_limits* lim, Emitter& E,
                             TrajRec* rec, const CurTable* __restrict__ tab) {
     PlanOut r{0, 0u, 0, 0};
-    if (!params_ok(p)) {
+    if (TGX_IS_POLYLINE(p.type)) {
+        r.status = TGX_ST_WRONG_PLANNER;   // planned by tgx_plan_polyline (polyline.cu)
+    } else if (!params_ok(p)) {
         r.status = TGX_ST_BAD_PARAM;
     } else {
         int n;
@@ -665,6 +558,66 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
     t.type = p.type & kRecTypeMask;
     t.n = 0;
     for (int i = 0; i < 7; ++i) t.f[i] = 0.0;
+    if (TGX_IS_POLYLINE(p.type)) {
+        // Braking trajectories of the constant-speed polyline family: the position stays at the setpoint being braked
+        // from, the speed ramps down along a fixed heading (kRecStatic records, see tgx_internal.cuh).
+        if (!poly_params_ok(p)) {
+            r.status = TGX_ST_BAD_PARAM;
+        } else {
+            const int tmask = (1 << E.tile_shift) - 1;
+            int k = -1;
+            bool ok = true;
+            t.type = kRecStatic;
+            E.phase(0, TGX_PH_PRESSED_END, 0.0, 0.0);                 // Square.cpp:123, Bounce.cpp:86
+            if (p.type == TGX_BOUNCE) {
+                // Bounce::generateStopTraj, Bounce.cpp:74-103: vz *= 0.8 until |vz| <= 0.01 (then exactly 0); one
+                // one-sample segment per step, all inside the first tile
+                double vz = from[TGX_VZ];
+                t.f[0] = p.u.poly.g[0]; t.f[1] = p.u.poly.g[1]; t.f[2] = from[TGX_PZ];   // :82, :94
+                t.f[3] = from[TGX_PSI];                                                   // :83
+                t.f[4] = 0.0; t.f[5] = 0.0; t.f[6] = 1.0;
+                if (!isfinite(vz)) ok = false;
+                while (ok && fabs(vz) > 0.01) {                       // :91
+                    if (k + 1 >= kMaxOptionalSegPerTile) { ok = false; break; }
+                    vz = dmul(vz, 0.8);                               // :92
+                    if (fabs(vz) < 0.01) vz = 0.0;                    // :93
+                    E.open(k, vz, 0.0, vz, 0.0, 0.0, 0.0);
+                    ++k;
+                    E.close(k, false, 0.0);
+                }
+            } else {
+                // Square.cpp:112-137 == Rectangle.cpp:113-137 == Reciprocating.cpp:81-107 (a3_) == M.cpp:88-113 ==
+                // I.cpp:96-121 == T.cpp:94-119 (literal decel 1.0)
+                double v = __dsqrt_rn(dadd(dmul(from[TGX_VX], from[TGX_VX]), dmul(from[TGX_VY], from[TGX_VY])));
+                const double heading = atan2(from[TGX_VY], from[TGX_VX]);
+                const double decel = (p.type == TGX_M || p.type == TGX_I || p.type == TGX_T) ? 1.0 : p.u.poly.decel;
+                double sn, cs;
+                sincos(heading, &sn, &cs);
+                t.f[0] = from[TGX_PX]; t.f[1] = from[TGX_PY]; t.f[2] = p.alt;
+                t.f[3] = heading;
+                t.f[4] = cs; t.f[5] = sn; t.f[6] = 0.0;
+                double u0 = 0.0, u1 = 0.0;
+                auto step = [](double) {};
+                ok = isfinite(v) && ramp<false, true, false, false>(v, 0.0, dmul(decel, p.dt), 0.0, k, max_samples,
+                                                                    tmask, E, -decel, u0, u1, 0.0, 0.0, step);
+            }
+            if (!ok) {
+                r.status |= TGX_ST_TOO_LONG;
+                E.nph = 0;
+            } else {
+                E.phase(k, TGX_PH_STOPPED, 0.0, 0.0);                 // key = size-1 (-1 when nothing was produced)
+                r.n = k + 1;
+            }
+            E.finish();
+            if (r.n > 0) {
+                r.nseg = E.nseg;
+                r.ntile = E.ntile;
+            }
+        }
+        t.n = r.n;
+        if (FILL && rec) *rec = t;
+        return r;
+    }
     if (!params_ok(p)) {
         r.status = TGX_ST_BAD_PARAM;
     } else {
@@ -786,7 +739,7 @@ plan_count_kernel(const tgx_params* __restrict__ params, const double* __restric
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const tgx_params p = load_params(params, i);
-    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, nullptr, !is_line_like(p.type), 0x7fffffff, 0x7fffffff};
+    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, nullptr, is_orbit(p.type), 0x7fffffff, 0x7fffffff};
     PlanOut r;
     if (stop_from) {
         double from[TGX_NCHAN];
@@ -829,7 +782,7 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
     TrajRec* rec_out = recs + i;
     Tile* tile_out = tiles + to;
     Emitter E{tile_shift, (int32_t)i, keep ? segs + so : nullptr, keep ? tile_out : nullptr, (int32_t)so,
-              phases ? phases + i : nullptr, !is_line_like(p.type), slab ? seg_slab : 0x7fffffff,
+              phases ? phases + i : nullptr, is_orbit(p.type), slab ? seg_slab : 0x7fffffff,
               slab ? tile_slab : 0x7fffffff};
     PlanOut r;
     if (stop_from) {
@@ -925,8 +878,26 @@ plan_samples_kernel(const tgx_params* __restrict__ params, const double* __restr
     g.vb = v; g.dv = 0.0; g.vclamp = v;
     t.n = 1;
     for (int q = 0; q < 7; ++q) t.f[q] = 0.0;
-    const bool ok = params_ok(p);
-    if (is_line_like(p.type)) {
+    const bool ok = TGX_IS_POLYLINE(p.type) ? poly_params_ok(p) : params_ok(p);
+    if (TGX_IS_POLYLINE(p.type)) {
+        // createSquareGoal(x, y, v, accel, heading) and its copies (Square.cpp:94-110); createBounceGoal(x, y, z, vz,
+        // heading) (Bounce.cpp:54-72).  state = {v | vz, accel, x, y}; z = g[5] (Bounce), heading = g[6].
+        const double heading = p.u.poly.g[6];
+        double sn, cs;
+        sincos(heading, &sn, &cs);
+        t.type = kRecStatic;
+        t.f[0] = s0; t.f[1] = s1; t.f[3] = heading;
+        if (p.type == TGX_BOUNCE) {
+            t.f[2] = p.u.poly.g[5];
+            t.f[4] = 0.0; t.f[5] = 0.0; t.f[6] = 1.0;
+            g.acc = 0.0;
+        } else {
+            t.f[2] = p.alt;
+            t.f[4] = cs; t.f[5] = sn; t.f[6] = 0.0;
+            g.acc = accel;
+        }
+        g.s0 = 0.0; g.s1 = 0.0;
+    } else if (is_line_like(p.type)) {
         const double theta = p.u.line.reserved[0];
         double sn, cs;
         sincos(theta, &sn, &cs);

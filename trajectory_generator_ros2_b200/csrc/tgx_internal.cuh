@@ -125,6 +125,54 @@ struct PlanStats {
     int pad;
 };
 
+// ---- constant-speed polyline family (Square / Rectangle / Reciprocating / Bounce / M / I / T) -------------------
+// The samples of such a trajectory follow a periodic pattern of legs: leg l contributes the samples
+// i = i0 .. steps of `frac = i / steps; p = start + frac * (end - start)` (Square.cpp:73-77, M.cpp:52-55), and the
+// number of samples is the number of `t += dt` iterations (the same counter as a hold phase).  The planner
+// (polyline.cu) writes one PolyHead + up to 10 PolyLeg + 2 special one-sample records per trajectory, kPolyRecs * 64
+// bytes at a fixed stride; the evaluation CTA stages them in one round of independent 16-byte loads.
+struct __align__(16) PolyLeg {
+    double sx, sy;        // start of the leg (Bounce: sx = z_start)
+    double dx, dy;        // end - start, the difference the reference recomputes for every sample
+    double heading;       // goal.psi
+    double vx, vy;        // v*cos(heading), v*sin(heading)  (Bounce: vx = vz)
+    int32_t steps;        // frac = (double)i / steps
+    int32_t i0;           // first i of the leg: 1 for Square / Rectangle sides, 0 otherwise
+};
+static_assert(sizeof(PolyLeg) == 64, "PolyLeg must be 64 bytes");
+
+struct __align__(16) PolyHead {
+    int32_t type;
+    int32_t n;              // sample count (0: rejected / empty)
+    int32_t n_legs;
+    int32_t first_special;  // 1: sample 0 is the record in slot kPolySlotFirst
+    int32_t last_special;   // 1: sample n-1 is the record in slot kPolySlotLast
+    int32_t period;         // sum over legs of (steps + 1 - i0)
+    int32_t pad[2];
+    double c0, c1;          // planar types: c0 = alt;  Bounce: c0 = cx, c1 = cy
+    double pad2[2];
+};
+static_assert(sizeof(PolyHead) == 64, "PolyHead must be 64 bytes");
+
+constexpr int kPolySlotLeg0 = 1;
+constexpr int kPolySlotFirst = 1 + TGX_POLY_MAX_LEGS;
+constexpr int kPolySlotLast = 2 + TGX_POLY_MAX_LEGS;
+constexpr int kPolyRecs = 3 + TGX_POLY_MAX_LEGS;     // 13 records of 64 bytes = 832 bytes per trajectory
+
+// Where the polyline evaluation kernel finds its work: tile t of trajectory i is CTA i*tile_slab + t (dense batches)
+// or the Tile list entry blockIdx.x (ragged batches; only Tile.traj and Tile.k_lo are used).
+struct PolyView {
+    const int4* recs;       // kPolyRecs * 4 int4 per trajectory
+    const Tile* tiles;      // nullptr: slab addressing
+    int tile_slab;
+};
+
+// TrajRec.type of a braking plan of the polyline family (Square.cpp:112-137 and its copies; Bounce.cpp:74-103): the
+// position is frozen at the setpoint being braked from, the velocity and acceleration point along a fixed direction.
+//   f0, f1, f2 = position;  f3 = psi;  f4, f5, f6 = unit direction (cos heading, sin heading, 0) or (0, 0, 1)
+//   Seg: v_k as for any ramp-down; Seg.acc = the signed acceleration magnitude along the direction (-decel, or 0)
+constexpr int32_t kRecStatic = 16;
+
 // Device-side view of tgx_layout.
 struct OutView {
     double* base;

@@ -59,6 +59,9 @@ def _load() -> C.CDLL:
     lib.tgx_count.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.tgx_plan.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64), vp]
     lib.tgx_plan_stop.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64), vp]
+    lib.tgx_plan_polyline.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64), vp]
+    lib.tgx_polyline_finalize_host.argtypes = [vp, i64]
+    lib.tgx_generate_host_legs.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp]
     lib.tgx_eval.argtypes = [vp, C.POINTER(abi.Layout), vp, vp, vp]
     lib.tgx_feasibility.argtypes = [vp, C.POINTER(abi.Limits), vp, vp, vp, vp, vp]
     lib.tgx_count_host.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -107,6 +110,7 @@ class Plan:
     phases: "object" = None   # torch.uint8 [n, sizeof(tgx_phases)] or None
     tiles: int = 0
     segments: int = 0
+    legs: "object" = None     # torch.uint8 [n, sizeof(tgx_polyline_legs)] or None (polyline plans)
 
 
 class PinnedArray:
@@ -250,6 +254,34 @@ class Engine:
         return Plan(n, counts, status, int(total.value), phases, int(self._lib.tgx_plan_tiles(self._h)),
                     int(self._lib.tgx_plan_segments(self._h)))
 
+    def plan_polyline(self, d_params, limits: Optional[abi.Limits] = None, want_legs: bool = False,
+                      want_outputs: bool = True) -> Plan:
+        """tgx_plan_polyline on a device-resident parameter tensor (Square / Rectangle / Reciprocating / Bounce / M / I / T)."""
+        import torch
+        n = int(d_params.shape[0])
+        counts = status = legs = None
+        if want_outputs:
+            counts = torch.empty(n, dtype=torch.int32, device=d_params.device)
+            status = torch.empty(n, dtype=torch.int32, device=d_params.device)
+        if want_legs:
+            legs = torch.empty((n, C.sizeof(abi.PolylineLegs)), dtype=torch.uint8, device=d_params.device)
+        total = C.c_int64(0)
+        self._check(self._lib.tgx_plan_polyline(self._h, d_params.data_ptr(), n, _limits_ptr(limits),
+                                                counts.data_ptr() if counts is not None else None,
+                                                status.data_ptr() if status is not None else None,
+                                                legs.data_ptr() if legs is not None else None,
+                                                C.byref(total), self._stream()), "tgx_plan_polyline")
+        return Plan(n, counts, status, int(total.value), None, int(self._lib.tgx_plan_tiles(self._h)), 0, legs)
+
+    @staticmethod
+    def finalize_polyline(params: np.ndarray) -> np.ndarray:
+        """tgx_polyline_finalize_host in place: cos_o / sin_o of polyline records from the host libm."""
+        assert params.dtype == abi.PARAMS_DTYPE and params.flags.c_contiguous
+        rc = lib().tgx_polyline_finalize_host(params.ctypes.data, len(params))
+        if rc:
+            raise TgxError(rc, "tgx_polyline_finalize_host", lib().tgx_strerror(rc).decode())
+        return params
+
     def plan_stop(self, d_params, d_from, want_phases: bool = False) -> Plan:
         """tgx_plan_stop: d_from is a float64 [n, 14] tensor with the setpoints being braked from."""
         import torch
@@ -319,6 +351,23 @@ class Engine:
         self._check(self._lib.tgx_count_host(self._h, params.ctypes.data, n, _limits_ptr(limits), counts.ctypes.data,
                                              status.ctypes.data), "tgx_count_host")
         return counts, status
+
+    def generate_host_legs(self, params: np.ndarray, capacity: int, limits: Optional[abi.Limits] = None,
+                           out: Optional[np.ndarray] = None):
+        """tgx_generate_host_legs -> (out [n, 14, capacity], counts, status, phases, legs)."""
+        params = np.ascontiguousarray(params)
+        n = len(params)
+        if out is None:
+            out = np.full((n, abi.TGX_NCHAN, capacity), np.nan)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (n, abi.TGX_NCHAN, capacity)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.uint32)
+        phases = np.zeros(n, dtype=abi.PHASES_DTYPE)
+        legs = np.zeros(n, dtype=abi.LEGS_DTYPE)
+        self._check(self._lib.tgx_generate_host_legs(self._h, params.ctypes.data, n, _limits_ptr(limits),
+                                                     out.ctypes.data, capacity, counts.ctypes.data, status.ctypes.data,
+                                                     phases.ctypes.data, legs.ctypes.data), "tgx_generate_host_legs")
+        return out, counts, status, phases, legs
 
     def generate_host(self, params: np.ndarray, capacity: int, limits: Optional[abi.Limits] = None,
                       out: Optional[np.ndarray] = None, want_phases: bool = False):

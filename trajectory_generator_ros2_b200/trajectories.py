@@ -88,14 +88,21 @@ class Trajectory:
         st = int(status[0])
         if st & (abi.ST_BAD_PARAM | abi.ST_TOO_LONG):
             raise TrajectoryError(f"{self.shape} trajectory parameters rejected (status {st:#x})")
-        cap = (int(counts[0]) + 3) // 4 * 4
-        out, counts, status, phases = self.engine.generate_host(self.params, cap, want_phases=True)
+        cap = max(4, (int(counts[0]) + 3) // 4 * 4)
+        out, counts, status, phases, legs = self.engine.generate_host_legs(self.params, cap)
         n, st = int(counts[0]), int(status[0])
         self.last_status = st
         base = len(goals)                                    # appends; keys are offset by the current size
         rows = out[0, :, :n].T
         goals.extend(Goal.from_channels(r) for r in rows)
-        for k, msg in abi.phases_to_index_msgs(int(self.params["type"][0]), phases[0]).items():
+        type_id = int(self.params["type"][0])
+        if abi.is_polyline(type_id):
+            msgs = abi.polyline_index_msgs(type_id, legs[0])
+            if n == 0 and type_id != abi.TGX_RECIPROCATING:
+                msgs = {-1: abi.polyline_msg(type_id, 0, -1, 0)}   # index_msgs[goals.size() - 1] on an empty vector
+        else:
+            msgs = abi.phases_to_index_msgs(type_id, phases[0])
+        for k, msg in msgs.items():
             index_msgs[base + k] = msg
         if st & abi.ST_VGOALS_NOT_INCREASING:
             self.warnings.append("Vels are not in increasing order, ignoring vels from the first to decrease...")
@@ -169,3 +176,90 @@ class Boomerang(Line):
 
     def __init__(self, alt, A, B, v_goals, a1, a3, dt, engine: Optional[Engine] = None):
         Trajectory.__init__(self, abi.boomerang_params(alt, A, B, v_goals, a1, a3, dt), engine)
+
+
+class _Polyline(Trajectory):
+    """Constant-speed polyline family: the public create<Shape>Goal(x, y, v, accel, heading) helper."""
+
+    def _create_goal(self, x, y, v, accel, heading) -> Goal:
+        p = self.params.copy()
+        p["g"][0, 6] = heading                                # tgx_polyline_params.g[6]: the explicit heading
+        return Goal.from_channels(self.engine.sample_host(p, v, accel, x, y))
+
+
+class Square(_Polyline):
+    shape = "Square"
+
+    def __init__(self, alt, side_length, cx, cy, orientation, v_goals, t_traj, accel, dt, engine: Optional[Engine] = None):
+        super().__init__(abi.square_params(alt, side_length, cx, cy, orientation, v_goals, t_traj, accel, dt), engine)
+
+    def createSquareGoal(self, x, y, v, accel, heading) -> Goal:
+        return self._create_goal(x, y, v, accel, heading)
+
+
+class Rectangle(_Polyline):
+    shape = "Rectangle"
+
+    def __init__(self, alt, side_a, side_b, cx, cy, orientation, v_goals, t_traj, accel, dt,
+                 engine: Optional[Engine] = None):
+        super().__init__(abi.rectangle_params(alt, side_a, side_b, cx, cy, orientation, v_goals, t_traj, accel, dt),
+                         engine)
+
+    def createRectangleGoal(self, x, y, v, accel, heading) -> Goal:
+        return self._create_goal(x, y, v, accel, heading)
+
+
+class Reciprocating(_Polyline):
+    shape = "Reciprocating"
+
+    def __init__(self, alt, A, B, v_goals, a1, a3, t_traj, dt, engine: Optional[Engine] = None):
+        super().__init__(abi.reciprocating_params(alt, A, B, v_goals, a1, a3, t_traj, dt), engine)
+
+    def createReciprocatingGoal(self, x, y, v, accel, heading) -> Goal:
+        return self._create_goal(x, y, v, accel, heading)
+
+
+class Bounce(_Polyline):
+    shape = "Bounce"
+
+    def __init__(self, cx, cy, Az, Bz, v_goals, t_traj, orientation, dt, engine: Optional[Engine] = None):
+        super().__init__(abi.bounce_params(cx, cy, Az, Bz, v_goals, t_traj, orientation, dt), engine)
+
+    def createBounceGoal(self, x, y, z, vz, heading) -> Goal:
+        p = self.params.copy()
+        p["g"][0, 5] = z
+        p["g"][0, 6] = heading
+        return Goal.from_channels(self.engine.sample_host(p, vz, 0.0, x, y))
+
+
+class M(_Polyline):
+    shape = "M"
+
+    def __init__(self, cx, cy, length, width, alt, v_goals, t_traj, orientation, dt, engine: Optional[Engine] = None):
+        super().__init__(abi.letter_params(abi.TGX_M, cx, cy, length, width, alt, v_goals, t_traj, orientation, dt),
+                         engine)
+
+    def createMGoal(self, x, y, v, accel, heading) -> Goal:
+        return self._create_goal(x, y, v, accel, heading)
+
+
+class I(_Polyline):
+    shape = "I"
+
+    def __init__(self, cx, cy, length, width, alt, v_goals, t_traj, orientation, dt, engine: Optional[Engine] = None):
+        super().__init__(abi.letter_params(abi.TGX_I, cx, cy, length, width, alt, v_goals, t_traj, orientation, dt),
+                         engine)
+
+    def createIGoal(self, x, y, v, accel, heading) -> Goal:
+        return self._create_goal(x, y, v, accel, heading)
+
+
+class T(_Polyline):
+    shape = "T"
+
+    def __init__(self, cx, cy, length, width, alt, v_goals, t_traj, orientation, dt, engine: Optional[Engine] = None):
+        super().__init__(abi.letter_params(abi.TGX_T, cx, cy, length, width, alt, v_goals, t_traj, orientation, dt),
+                         engine)
+
+    def createTGoal(self, x, y, v, accel, heading) -> Goal:
+        return self._create_goal(x, y, v, accel, heading)

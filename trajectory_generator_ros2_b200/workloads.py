@@ -141,3 +141,83 @@ def montecarlo_cfg4(n: int, seed: int = 1236, lo: int = 0, hi: int | None = None
 
 
 MONTECARLO_LIMITS = dict(box=(-5.0, 5.0, -5.0, 5.0, -5.0, 5.0), v_max=5.0, a_max=6.0)
+
+
+# ---- constant-speed polyline family -------------------------------------------------------------
+
+def default_polyline(kind: int) -> np.ndarray:
+    """The polyline-family trajectories of config/default.yaml (:9-36, :40-44, :46-49): traj_type T ships as the default;
+    v_goals [1.0, 2.0, 2.0] (only [0] is used), t_traj 80, orientation 0, centre (0, 0), alt 1.8."""
+    alt, vg, T, ori = 1.8, [1.0, 2.0, 2.0], 80.0, 0.0
+    if kind == abi.TGX_SQUARE:
+        return abi.square_params(alt, 2.0, 0.0, 0.0, ori, vg, T, 0.4, DT)
+    if kind == abi.TGX_RECTANGLE:
+        return abi.rectangle_params(alt, 2.0, 4.0, 0.0, 0.0, ori, vg, T, 0.4, DT)
+    if kind == abi.TGX_RECIPROCATING:
+        return abi.reciprocating_params(alt, [0.0, -3.0, alt], [0.0, 3.0, alt], [1.0], 1.5, 1.0, T, DT)
+    if kind == abi.TGX_BOUNCE:
+        return abi.bounce_params(0.0, 0.0, 4.0, 1.0, vg, T, ori, DT)
+    return abi.letter_params(kind, 0.0, 0.0, 3.0, 4.0, alt, vg, T, ori, DT)
+
+
+def _fill_polyline(rng, m, t_lo=8.0, t_hi=12.0):
+    """Random polyline-family trajectories of ~1000 samples (t_traj ~ U[8, 12] s at dt = 0.01), all seven shapes."""
+    p = np.zeros(m, dtype=abi.PARAMS_DTYPE)
+    kind = rng.choice(np.array(abi.POLYLINE_TYPES), size=m)
+    p["type"] = kind
+    p["dt"] = DT
+    p["alt"] = rng.uniform(1.0, 2.5, m)
+    p["poly_t_traj"] = rng.uniform(t_lo, t_hi, m)
+    p["poly_v_goal"] = rng.uniform(0.3, 3.0, m)
+    p["poly_decel"] = rng.uniform(0.3, 2.0, m)
+    p["orientation"] = np.where(rng.random(m) < 0.25, 0.0, rng.uniform(-np.pi, np.pi, m))
+    cx, cy = rng.uniform(-2.0, 2.0, m), rng.uniform(-2.0, 2.0, m)
+    d0, d1 = rng.uniform(0.5, 4.0, m), rng.uniform(0.5, 4.0, m)
+    g = np.zeros((m, 7))
+    sq = kind == abi.TGX_SQUARE
+    g[sq, 0], g[sq, 1], g[sq, 2] = d0[sq], cx[sq], cy[sq]
+    rc = kind == abi.TGX_RECTANGLE
+    g[rc, 0], g[rc, 1], g[rc, 2], g[rc, 3] = d0[rc], d1[rc], cx[rc], cy[rc]
+    rp = kind == abi.TGX_RECIPROCATING
+    A = rng.uniform(-4.0, 4.0, (m, 2))
+    B = A + rng.uniform(0.5, 4.0, (m, 1)) * np.stack([np.cos(p["orientation"]), np.sin(p["orientation"])], axis=1)
+    g[rp, 0], g[rp, 1], g[rp, 2] = A[rp, 0], A[rp, 1], p["alt"][rp]
+    g[rp, 3], g[rp, 4], g[rp, 5] = B[rp, 0], B[rp, 1], p["alt"][rp]
+    bo = kind == abi.TGX_BOUNCE
+    az = rng.uniform(0.5, 2.0, m)
+    g[bo, 0], g[bo, 1], g[bo, 2], g[bo, 3] = cx[bo], cy[bo], az[bo], az[bo] + d0[bo]
+    flip = bo & (rng.random(m) < 0.5)                 # default.yaml starts at the top (Az 4.0, Bz 1.0)
+    g[flip, 2], g[flip, 3] = g[flip, 3], g[flip, 2].copy()
+    lt = (kind == abi.TGX_M) | (kind == abi.TGX_I) | (kind == abi.TGX_T)
+    g[lt, 0], g[lt, 1], g[lt, 2], g[lt, 3] = cx[lt], cy[lt], d0[lt], d1[lt]
+    p["g"] = g
+    return p
+
+
+def polyline_mix(n: int, seed: int = 1238, lo: int = 0, hi: int | None = None) -> np.ndarray:
+    """Row f2 workload: the seven constant-speed shapes, ~1000 samples each.  cos_o / sin_o are left unset: the
+    host-buffer calls (or Engine.finalize_polyline) fill them from the host libm."""
+    hi = n if hi is None else hi
+    return _draw(seed, lo, hi, _fill_polyline)
+
+
+def _fill_letters_T(rng, m):
+    """The shipped default shape (traj_type: T, default.yaml:9) with random size / speed / pose, ~1000 samples."""
+    p = np.zeros(m, dtype=abi.PARAMS_DTYPE)
+    p["type"] = abi.TGX_T
+    p["dt"] = DT
+    p["alt"] = rng.uniform(1.0, 2.5, m)
+    p["poly_t_traj"] = rng.uniform(9.9, 10.1, m)
+    p["poly_v_goal"] = rng.uniform(0.3, 3.0, m)
+    p["poly_decel"] = 1.0
+    p["orientation"] = rng.uniform(-np.pi, np.pi, m)
+    g = np.zeros((m, 7))
+    g[:, 0], g[:, 1] = rng.uniform(-2.0, 2.0, m), rng.uniform(-2.0, 2.0, m)
+    g[:, 2], g[:, 3] = rng.uniform(0.5, 4.0, m), rng.uniform(0.5, 4.0, m)
+    p["g"] = g
+    return p
+
+
+def letters_T(n: int, seed: int = 1239, lo: int = 0, hi: int | None = None) -> np.ndarray:
+    hi = n if hi is None else hi
+    return _draw(seed, lo, hi, _fill_letters_T)
