@@ -46,13 +46,25 @@ def make_params(workload: str, n: int, lo: int, hi: int):
         return workloads.mixed_cfg3(n, lo=lo, hi=hi)
     if workload == "montecarlo_cfg4":
         return workloads.montecarlo_cfg4(n, lo=lo, hi=hi)
+    if workload in POLYLINE_WORKLOADS:
+        from trajectory_generator_ros2_b200.engine import Engine
+        gen = workloads.polyline_mix if workload == "polyline_mix" else workloads.letters_T
+        # cos / sin of the orientation from the host libm, as the reference computes them (tgx_polyline_finalize_host)
+        return Engine.finalize_polyline(np.ascontiguousarray(gen(n, lo=lo, hi=hi)).copy())
     raise SystemExit(f"unknown workload {workload}")
+
+
+POLYLINE_WORKLOADS = ("polyline_mix", "letters_T")
 
 
 WORKLOAD_DESC = {
     "circles_cfg2": "BASELINE configs[1]: {n} circles x ~1000 samples per GPU, random r/v/centre (rng 1234), dt 0.01",
     "mixed_cfg3": "BASELINE configs[2]: {n} mixed circle/line/figure-eight with one or two ramp-ups per GPU (rng 1235)",
     "montecarlo_cfg4": "BASELINE configs[3]: {n} wide-range circles per GPU, max-|v|/|a| feasibility only (rng 1236)",
+    "polyline_mix": "SURVEY 8(f2): {n} constant-speed polylines per GPU (Square/Rectangle/Reciprocating/Bounce/M/I/T, "
+                    "~1000 samples each, rng 1238)",
+    "letters_T": "SURVEY 8(f2): {n} T trajectories per GPU (the shape default.yaml ships), random size/speed/pose, "
+                 "~1000 samples each (rng 1239)",
 }
 
 
@@ -225,6 +237,7 @@ def run_ours(args):
     params = make_params(args.workload, world * n, lo, hi)
     d_params = eng.upload_params(params)
     feas_only = args.workload == "montecarlo_cfg4"
+    poly = args.workload in POLYLINE_WORKLOADS
     lim = abi.make_limits(**workloads.MONTECARLO_LIMITS) if feas_only else None
 
     # size the output from a first (untimed) count
@@ -253,7 +266,10 @@ def run_ours(args):
     def step(record: bool):
         for c in range(chunks):
             dp = chunk_params[c]
-            eng.plan(dp, limits=lim, want_outputs=False)
+            if poly:
+                eng.plan_polyline(dp, want_outputs=False)
+            else:
+                eng.plan(dp, limits=lim, want_outputs=False)
             if record:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -346,10 +362,11 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t[0])
         assert h_counts_total == total_samples
-        planes = 14 if args.e2e_all_planes else 10
+        has_bounce = bool((params["type"] == abi.TGX_BOUNCE).any())     # Bounce moves along z: nothing is constant
+        planes = 14 if (args.e2e_all_planes or has_bounce) else 10
         e2e = {"value": job_samples / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * (planes * row * 8 + 8)),
-               "wire_format": ("all 14 planes over PCIe" if args.e2e_all_planes else
+               "wire_format": ("all 14 planes over PCIe" if planes == 14 else
                                "10 varying planes over PCIe; the 4 constant planes (p.z = alt, v.z = a.z = j.z = 0) "
                                "are written into the host buffer by host threads"),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
@@ -415,7 +432,9 @@ def run_ours(args):
                 "trajectories_per_gpu": n, "samples_per_gpu": total_samples, "row_stride": row,
                 "layout": "plane-major [14][n][row]" if args.plane_major else "trajectory-major [n][14][row]",
                 "chunks": chunks,
-                "step": "tgx_plan (hold-length table + one strict-IEEE replay per trajectory into fixed slices; the "
+                "step": ("tgx_plan_polyline (hold-length table + waypoints / per-leg step counts in strict IEEE "
+                         "arithmetic, one thread per trajectory) + tgx_eval, parameters resident in HBM") if poly else
+                        "tgx_plan (hold-length table + one strict-IEEE replay per trajectory into fixed slices; the "
                         "first plan of an engine measures the slice sizes with a count + scan + fill pass) + "
                         + ("tgx_feasibility" if feas_only else "tgx_eval") + ", parameters resident in HBM",
                 "plan_paths": dict(zip(("single_replay", "two_replay"), eng.plan_path_counts())),
@@ -426,7 +445,7 @@ def run_ours(args):
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
-                         "kernel": "tgx::eval_kernel", "bytes_per_launch": eval_bytes / chunks,
+                         "kernel": "tgx::eval_poly_kernel" if poly else "tgx::eval_kernel", "bytes_per_launch": eval_bytes / chunks,
                          "peak_source": peak_src + " — of measured" if "MEASURED" in peak_src else peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }

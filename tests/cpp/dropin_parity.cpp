@@ -14,9 +14,16 @@
 #include <vector>
 
 #include "trajectory_generator_ros2/trajectories/Boomerang.hpp"
+#include "trajectory_generator_ros2/trajectories/Bounce.hpp"
 #include "trajectory_generator_ros2/trajectories/Circle.hpp"
 #include "trajectory_generator_ros2/trajectories/Figure8.hpp"
+#include "trajectory_generator_ros2/trajectories/I.hpp"
 #include "trajectory_generator_ros2/trajectories/Line.hpp"
+#include "trajectory_generator_ros2/trajectories/M.hpp"
+#include "trajectory_generator_ros2/trajectories/Reciprocating.hpp"
+#include "trajectory_generator_ros2/trajectories/Rectangle.hpp"
+#include "trajectory_generator_ros2/trajectories/Square.hpp"
+#include "trajectory_generator_ros2/trajectories/T.hpp"
 
 #include "tgx_trajectories.hpp"
 
@@ -160,6 +167,57 @@ int main() {
         gpu::Line g(1.8, A, B, {1.0}, 1.5, 1.0, dt);
         CHECK(!r.trajectoryInsideBounds(-5, 5, -5, 5, -5, 5) && !g.trajectoryInsideBounds(-5, 5, -5, 5, -5, 5),
               "short line: both sides must reject");
+    }
+    {   // the constant-speed polyline family, config/default.yaml values (traj_type: T ships as
+        // the default, default.yaml:9) and a rotated / off-centre variant of each
+        const std::vector<double> vg{1.0, 2.0, 2.0};
+        for (int variant = 0; variant < 2; ++variant) {
+            const double ori = variant ? 0.5 : 0.0, cx = variant ? 0.4 : 0.0, cy = variant ? -0.3 : 0.0;
+            const double T = variant ? 23.7 : 80.0, alt = 1.8;
+            const std::string tag = variant ? "rotated " : "default ";
+            {
+                ref::Square r(alt, 2.0, cx, cy, ori, vg, T, 0.4, dt);
+                gpu::Square g(alt, 2.0, cx, cy, ori, vg, T, 0.4, dt);
+                runPair((tag + "Square").c_str(), r, g, 1234);
+                compareGoals("createSquareGoal", {g.createSquareGoal(1.0, 2.0, 1.5, -0.4, 0.7)},
+                             {r.createSquareGoal(1.0, 2.0, 1.5, -0.4, 0.7)});
+            }
+            {
+                ref::Rectangle r(alt, 2.0, 4.0, cx, cy, ori, vg, T, 0.4, dt);
+                gpu::Rectangle g(alt, 2.0, 4.0, cx, cy, ori, vg, T, 0.4, dt);
+                runPair((tag + "Rectangle").c_str(), r, g, 777);
+            }
+            {
+                const Eigen::Vector3d A(cx, -3.0, alt), B(cy, 3.0, alt);
+                ref::Reciprocating r(alt, A, B, {1.0}, 1.5, 1.0, T, dt);
+                gpu::Reciprocating g(alt, A, B, {1.0}, 1.5, 1.0, T, dt);
+                runPair((tag + "Reciprocating").c_str(), r, g, 300);
+            }
+            {
+                ref::Bounce r(cx, cy, 4.0, 1.0, vg, T, ori, dt);
+                gpu::Bounce g(cx, cy, 4.0, 1.0, vg, T, ori, dt);
+                runPair((tag + "Bounce").c_str(), r, g, 450);
+                compareGoals("createBounceGoal", {g.createBounceGoal(0.1, 0.2, 2.5, -1.0, 0.3)},
+                             {r.createBounceGoal(0.1, 0.2, 2.5, -1.0, 0.3)});
+            }
+            {
+                ref::M r(cx, cy, 3.0, 4.0, alt, vg, T, ori, dt);
+                gpu::M g(cx, cy, 3.0, 4.0, alt, vg, T, ori, dt);
+                runPair((tag + "M").c_str(), r, g, 2000);
+            }
+            {
+                ref::I r(cx, cy, 3.0, 4.0, alt, vg, T, ori, dt);
+                gpu::I g(cx, cy, 3.0, 4.0, alt, vg, T, ori, dt);
+                runPair((tag + "I").c_str(), r, g, 2100);
+            }
+            {
+                ref::T r(cx, cy, 3.0, 4.0, alt, vg, T, ori, dt);
+                gpu::T g(cx, cy, 3.0, 4.0, alt, vg, T, ori, dt);
+                runPair((tag + "T").c_str(), r, g, 999);
+                compareGoals("createTGoal", {g.createTGoal(-1.0, 0.5, 2.0, 0.0, -2.1)},
+                             {r.createTGoal(-1.0, 0.5, 2.0, 0.0, -2.1)});
+            }
+        }
     }
     // random parameters
     std::mt19937_64 rng(20261018);

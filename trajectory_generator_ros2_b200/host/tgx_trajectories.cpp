@@ -1,6 +1,7 @@
 // tgx_trajectories.cpp — see tgx_trajectories.hpp.  Host glue only: every sample comes from libtgx (CUDA).
 #include "tgx_trajectories.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,6 +34,56 @@ std::string phaseText(const std::string& shape, int type, int kind, double value
             return shape + " traj: stopped";
         case TGX_PH_PRESSED_END: return shape + " traj: pressed END, decelerating to 0 m/s";
         default: return shape + " traj: ?";
+    }
+}
+
+// index_msgs text of sample k (of n) of a polyline-family trajectory whose leg is `leg` (tgx_polyline_legs numbering):
+// Square.cpp:61,79,88; Rectangle.cpp:61,79,88; Reciprocating.cpp:47,57; Bounce.cpp:42,50; M.cpp:57,65; I.cpp:65,73;
+// T.cpp:63,71.
+std::string polylineText(const std::string& shape, int type, int leg, int64_t k, int64_t n) {
+    const bool last = k == n - 1;
+    switch (type) {
+        case TGX_SQUARE:
+        case TGX_RECTANGLE:
+            if (last) return shape + " traj: completed";
+            if (leg < 0) return shape + " traj: starting at corner 0";
+            return shape + " traj: moving along side " + std::to_string(leg);
+        case TGX_RECIPROCATING:
+            if (leg == 1 || leg == 3) return "Reciprocating: yaw flip at endpoint";
+            return leg == 0 ? "Reciprocating: forward" : "Reciprocating: reverse";
+        case TGX_BOUNCE:
+            if (last) return "Bounce: completed";
+            return leg == 0 ? "Bounce: ascending" : "Bounce: descending";
+        default: {
+            const int nseg = type == TGX_M ? 4 : (type == TGX_I ? 5 : 3);
+            if (last) return shape + " traj: completed";
+            return shape + " traj: segment " + std::to_string(leg % nseg) + (leg < nseg ? " fwd" : " rev");
+        }
+    }
+}
+
+// The reference announces every sample of a polyline trajectory; rebuild its map from the leg structure.
+void polylineMessages(const std::string& shape, int type, const tgx_polyline_legs& L, int base,
+                      std::unordered_map<int, std::string>& index_msgs) {
+    const int64_t n = L.n;
+    if (n <= 0) {
+        // index_msgs[goals.size() - 1] = "... completed" on an empty vector (Bounce.cpp:50, M.cpp:65): key size()-1
+        if (type != TGX_RECIPROCATING) index_msgs[base - 1] = polylineText(shape, type, 0, -1, 0);
+        return;
+    }
+    int64_t k = 0;
+    if (L.first_special) index_msgs[base + (int)k++] = polylineText(shape, type, -1, 0, n);
+    int leg = 0;
+    while (k < n && L.n_legs > 0) {
+        for (int c = 0; c < L.count[leg] && k < n; ++c, ++k)
+            index_msgs[base + (int)k] = polylineText(shape, type, leg, k, n);
+        leg = (leg + 1) % L.n_legs;
+    }
+    // the yaw-flip goal appended after a leg that t_traj cut short (Reciprocating.cpp:50-57) replaces the last entry
+    if (L.last_special) {
+        int m = (int)((n - 2 - L.first_special) % L.period), l = 0;
+        while (l + 1 < L.n_legs && m >= L.count[l]) m -= L.count[l++];
+        index_msgs[base + (int)(n - 1)] = polylineText(shape, type, l + 1, n - 1, n);
     }
 }
 
@@ -134,20 +185,25 @@ void GpuTrajectory::generateTraj(std::vector<Goal>& goals, std::unordered_map<in
     }
 
     // pass 2: all samples into a page-locked SoA row, then repack to the reference's AoS messages
-    const int64_t cap = ((int64_t)n + 3) / 4 * 4;
+    const int64_t cap = std::max<int64_t>(4, ((int64_t)n + 3) / 4 * 4);
     double* row = staging().reserve((int64_t)TGX_NCHAN * cap);
     if (!row) die(logger_, "tgx_alloc_host", TGX_ERR_NOMEM);
     tgx_phases phases;
-    rc = tgx_generate_host(e, &params_, 1, nullptr, row, cap, &n, &status, &phases);
-    if (rc != TGX_OK) die(logger_, "tgx_generate_host", rc);
+    tgx_polyline_legs legs;
+    rc = tgx_generate_host_legs(e, &params_, 1, nullptr, row, cap, &n, &status, &phases, &legs);
+    if (rc != TGX_OK) die(logger_, "tgx_generate_host_legs", rc);
     last_status_ = status;
 
     const size_t base = goals.size();            // generateTraj APPENDS (Circle.cpp:41: push_back, keys size()-1)
     goals.reserve(base + (size_t)n);
     for (int64_t k = 0; k < n; ++k) goals.push_back(goalFromPlanes(row, cap, k));
-    for (int i = 0; i < phases.n; ++i)
-        index_msgs[(int)base + phases.key[i]] =
-            phaseText(shape_, params_.type, phases.kind[i], phases.value[i], phases.value2[i], false);
+    if (TGX_IS_POLYLINE(params_.type)) {
+        polylineMessages(shape_, params_.type, legs, (int)base, index_msgs);
+    } else {
+        for (int i = 0; i < phases.n; ++i)
+            index_msgs[(int)base + phases.key[i]] =
+                phaseText(shape_, params_.type, phases.kind[i], phases.value[i], phases.value2[i], false);
+    }
 
     if (status & TGX_ST_VGOALS_NOT_INCREASING)   // Circle.cpp:57-59, Figure8.cpp:57-59
         RCLCPP_WARN(logger_, "Vels are not in increasing order, ignoring vels from the first to decrease...");
@@ -285,6 +341,98 @@ Boomerang::Boomerang(double alt, Eigen::Vector3d A, Eigen::Vector3d B, std::vect
 
 Goal Boomerang::createLineGoal(double last_x, double last_y, double v, double accel, double theta) const {
     return lineGoal(params_, logger_, last_x, last_y, v, accel, theta);
+}
+
+// ---- constant-speed polyline family ---------------------------------------------------------------------------
+
+namespace {
+tgx_params polyParams(int type, double dt, double alt, double t_traj, const std::vector<double>& v_goals, double decel,
+                      double orientation, std::initializer_list<double> geometry) {
+    tgx_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.type = type;
+    p.dt = dt;
+    p.alt = alt;
+    p.u.poly.t_traj = t_traj;
+    p.u.poly.v_goal = v_goals.empty() ? 1.0 : v_goals[0];   // Square.cpp:48, Bounce.cpp:26, M.cpp:39
+    p.u.poly.decel = decel;
+    p.u.poly.orientation = orientation;
+    int i = 0;
+    for (double g : geometry) p.u.poly.g[i++] = g;
+    // cos / sin of the orientation from THIS host's libm, as the reference computes them (Square.cpp:37-38)
+    tgx_polyline_finalize_host(&p, 1);
+    return p;
+}
+}  // namespace
+
+Goal GpuTrajectory::polylineGoal(double x, double y, double v, double accel, double heading, double z) const {
+    double out[TGX_NCHAN];
+    tgx_params p = params_;
+    p.u.poly.g[5] = z;                           // tgx_plan_samples: z (Bounce) and the explicit heading
+    p.u.poly.g[6] = heading;
+    const int rc = tgx_sample_host(sharedEngine(), &p, v, accel, x, y, out);
+    if (rc != TGX_OK) die(logger_, "tgx_sample_host", rc);
+    return goalFromPlanes(out, 1, 0);
+}
+
+Square::Square(double alt, double side_length, double cx, double cy, double orientation, std::vector<double> v_goals,
+               double t_traj, double accel, double dt)
+    : GpuTrajectory(polyParams(TGX_SQUARE, dt, alt, t_traj, v_goals, accel, orientation, {side_length, cx, cy}),
+                    "Square", "square_logger") {}
+Goal Square::createSquareGoal(double x, double y, double v, double accel, double heading) const {
+    return polylineGoal(x, y, v, accel, heading, 0.0);
+}
+
+Rectangle::Rectangle(double alt, double side_a, double side_b, double cx, double cy, double orientation,
+                     std::vector<double> v_goals, double t_traj, double accel, double dt)
+    : GpuTrajectory(polyParams(TGX_RECTANGLE, dt, alt, t_traj, v_goals, accel, orientation, {side_a, side_b, cx, cy}),
+                    "Rectangle", "rectangle_logger") {}
+Goal Rectangle::createRectangleGoal(double x, double y, double v, double accel, double heading) const {
+    return polylineGoal(x, y, v, accel, heading, 0.0);
+}
+
+// a1 is stored by the reference class and never used (Reciprocating.cpp:13-19, :98).
+Reciprocating::Reciprocating(double alt, Eigen::Vector3d A, Eigen::Vector3d B, std::vector<double> v_goals, double a1,
+                             double a3, double t_traj, double dt)
+    : GpuTrajectory(polyParams(TGX_RECIPROCATING, dt, alt, t_traj, v_goals, a3, 0.0,
+                               {A.x(), A.y(), A.z(), B.x(), B.y(), B.z()}),
+                    "Reciprocating", "reciprocating_logger") {
+    (void)a1;
+}
+Goal Reciprocating::createReciprocatingGoal(double x, double y, double v, double accel, double heading) const {
+    return polylineGoal(x, y, v, accel, heading, 0.0);
+}
+
+Bounce::Bounce(double cx, double cy, double Az, double Bz, std::vector<double> v_goals, double t_traj,
+               double orientation, double dt)
+    : GpuTrajectory(polyParams(TGX_BOUNCE, dt, 0.0, t_traj, v_goals, 0.0, orientation, {cx, cy, Az, Bz}), "Bounce",
+                    "bounce_logger") {}
+Goal Bounce::createBounceGoal(double x, double y, double z, double vz, double heading) const {
+    return polylineGoal(x, y, vz, 0.0, heading, z);
+}
+
+M::M(double cx, double cy, double length, double width, double alt, std::vector<double> v_goals, double t_traj,
+     double orientation, double dt)
+    : GpuTrajectory(polyParams(TGX_M, dt, alt, t_traj, v_goals, 1.0, orientation, {cx, cy, length, width}), "M",
+                    "m_logger") {}
+Goal M::createMGoal(double x, double y, double v, double accel, double heading) const {
+    return polylineGoal(x, y, v, accel, heading, 0.0);
+}
+
+I::I(double cx, double cy, double length, double width, double alt, std::vector<double> v_goals, double t_traj,
+     double orientation, double dt)
+    : GpuTrajectory(polyParams(TGX_I, dt, alt, t_traj, v_goals, 1.0, orientation, {cx, cy, length, width}), "I",
+                    "i_logger") {}
+Goal I::createIGoal(double x, double y, double v, double accel, double heading) const {
+    return polylineGoal(x, y, v, accel, heading, 0.0);
+}
+
+T::T(double cx, double cy, double length, double width, double alt, std::vector<double> v_goals, double t_traj,
+     double orientation, double dt)
+    : GpuTrajectory(polyParams(TGX_T, dt, alt, t_traj, v_goals, 1.0, orientation, {cx, cy, length, width}), "T",
+                    "t_logger") {}
+Goal T::createTGoal(double x, double y, double v, double accel, double heading) const {
+    return polylineGoal(x, y, v, accel, heading, 0.0);
 }
 
 }  // namespace TGX_DROPIN_NAMESPACE

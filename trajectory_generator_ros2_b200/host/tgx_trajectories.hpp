@@ -1,4 +1,5 @@
-// tgx_trajectories.hpp — C++ host side of the drop-in: GPU-backed Circle / Line / Figure8 / Boomerang.
+// tgx_trajectories.hpp — C++ host side of the drop-in: GPU-backed Circle / Line / Figure8 / Boomerang and the
+// constant-speed polyline family Square / Rectangle / Reciprocating / Bounce / M / I / T.
 //
 // These classes keep the reference's interface — the constructor argument lists of Circle.hpp:30-31,
 // Line.hpp:30-31 and Figure8.hpp:30-31 and the three overrides of the abstract Trajectory interface
@@ -53,6 +54,9 @@ protected:
 
     // create<Shape>Goal(v, accel, theta): one setpoint from an explicit state, evaluated on the GPU.
     snapstack_msgs2::msg::Goal sampleGoal(double v, double accel, double s0, double s1) const;
+    // create<Shape>Goal(x, y, v, accel, heading) of the polyline family (createBounceGoal: v = vz, z explicit).
+    snapstack_msgs2::msg::Goal polylineGoal(double x, double y, double v, double accel, double heading,
+                                            double z) const;
 
     tgx_params params_;
     std::string shape_;       // "Circle", "Line", "Figure8": prefix of the index_msgs texts
@@ -89,6 +93,58 @@ public:
               std::vector<double> v_goals, double a1, double a3, double dt);
     snapstack_msgs2::msg::Goal createLineGoal(double last_x, double last_y,
                                               double v, double accel, double theta) const;
+};
+
+// ---- constant-speed polyline family (Square.hpp:31-32, Rectangle.hpp, Reciprocating.hpp, Bounce.hpp, M.hpp, I.hpp,
+//      T.hpp; constructed at TrajectoryGenerator.cpp:246, :258, :291-293, :318, :340, :362, :384) ----------------
+class Square : public GpuTrajectory {
+public:
+    Square(double alt, double side_length, double cx, double cy, double orientation,
+           std::vector<double> v_goals, double t_traj, double accel, double dt);
+    snapstack_msgs2::msg::Goal createSquareGoal(double x, double y, double v, double accel, double heading) const;
+};
+
+class Rectangle : public GpuTrajectory {
+public:
+    Rectangle(double alt, double side_a, double side_b, double cx, double cy, double orientation,
+              std::vector<double> v_goals, double t_traj, double accel, double dt);
+    snapstack_msgs2::msg::Goal createRectangleGoal(double x, double y, double v, double accel, double heading) const;
+};
+
+class Reciprocating : public GpuTrajectory {
+public:
+    Reciprocating(double alt, Eigen::Vector3d A, Eigen::Vector3d B,
+                  std::vector<double> v_goals, double a1, double a3, double t_traj, double dt);
+    snapstack_msgs2::msg::Goal createReciprocatingGoal(double x, double y, double v, double accel,
+                                                       double heading) const;
+};
+
+class Bounce : public GpuTrajectory {
+public:
+    Bounce(double cx, double cy, double Az, double Bz,
+           std::vector<double> v_goals, double t_traj, double orientation, double dt);
+    snapstack_msgs2::msg::Goal createBounceGoal(double x, double y, double z, double vz, double heading) const;
+};
+
+class M : public GpuTrajectory {
+public:
+    M(double cx, double cy, double length, double width, double alt,
+      std::vector<double> v_goals, double t_traj, double orientation, double dt);
+    snapstack_msgs2::msg::Goal createMGoal(double x, double y, double v, double accel, double heading) const;
+};
+
+class I : public GpuTrajectory {
+public:
+    I(double cx, double cy, double length, double width, double alt,
+      std::vector<double> v_goals, double t_traj, double orientation, double dt);
+    snapstack_msgs2::msg::Goal createIGoal(double x, double y, double v, double accel, double heading) const;
+};
+
+class T : public GpuTrajectory {
+public:
+    T(double cx, double cy, double length, double width, double alt,
+      std::vector<double> v_goals, double t_traj, double orientation, double dt);
+    snapstack_msgs2::msg::Goal createTGoal(double x, double y, double v, double accel, double heading) const;
 };
 
 // The process-wide engine the classes share (created on first use on device $TGX_DEVICE, default 0).
