@@ -258,8 +258,20 @@ def run_ours(args):
                 chunks *= 2
                 if chunks > 64:
                     raise
+    if args.records:
+        # consumer side: the samples are packed into clamped 128-byte records; planes + records of the
+        # whole batch do not fit 180 GB, so the batch runs in 8 chunks through one plane buffer and one record buffer
+        del out
+        torch.cuda.empty_cache()
+        chunks = max(chunks, 8)
+        rows = (n + chunks - 1) // chunks
+        out = torch.empty((rows, abi.TGX_NCHAN, row), dtype=torch.float64, device=dev)
+        rec = torch.empty((rows, row, 128), dtype=torch.uint8, device=dev)
+        d_counts = counts.to(torch.int32).contiguous()
+        box_lim = abi.make_limits(box=(-4.0, 4.0, -4.0, 4.0, 0.0, 2.0))
     rows = (n + chunks - 1) // chunks
     chunk_params = [d_params[c * rows: min(n, (c + 1) * rows)] for c in range(chunks)]
+    pack_pairs = []
 
     ev_pairs = []
 
@@ -286,6 +298,13 @@ def run_ours(args):
             if record:
                 b.record()
                 ev_pairs.append((a, b))
+            if args.records:
+                m = int(dp.shape[0])
+                eng.pack_goals(out[:m], d_counts[c * rows: c * rows + m], box_lim, records=rec, rec_capacity=row)
+                if record:
+                    e2 = torch.cuda.Event(enable_timing=True)
+                    e2.record()
+                    pack_pairs.append((b, e2))
 
     if feas_only:
         flags = [torch.empty(int(p.shape[0]), dtype=torch.uint8, device=dev) for p in chunk_params]
@@ -331,7 +350,7 @@ def run_ours(args):
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region) ----
     e2e = None
-    if not feas_only and not args.no_e2e:
+    if not feas_only and not args.no_e2e and not args.records:
         eng.set_host_fill(not args.e2e_all_planes)
         call_n = min(n, args.e2e_call)                       # trajectories per tgx_generate_host call
         pin_out = PinnedArray((call_n, abi.TGX_NCHAN, row))
@@ -423,6 +442,15 @@ def run_ours(args):
             cpu = {"value": s / dt, "unit": UNIT, "cores": threads, "kind": kind,
                    "sample": f"first {args.cpu_sample} trajectories of the workload ({s} samples), "
                              f"generateTraj into std::vector<Goal>, {dt:.2f} s wall"}
+        roof_extra = {}
+        if args.records:
+            pack_ms = float(np.mean([a.elapsed_time(b) for a, b in pack_pairs])) * chunks
+            pack_bytes = (BYTES_PER_SAMPLE + 128) * total_samples
+            roof_extra = {"pack_kernel": {"kernel": "tgx::pack_goals_kernel", "bound": "hbm", "ms_per_step": pack_ms,
+                                          "bytes_per_sample": BYTES_PER_SAMPLE + 128,
+                                          "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                          "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / peak,
+                                          "note": "112 B of planes read + 128 B of records written per sample"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -449,6 +477,9 @@ def run_ours(args):
                          "peak_source": peak_src + " — of measured" if "MEASURED" in peak_src else peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        line["roofline"].update(roof_extra)
+        if args.records:
+            line["config"]["step"] += " + tgx_pack_goals (clamp to the room box, pack to 128-byte records)"
         if feas_only:
             line["config"]["feasible_fraction"] = float(torch.cat(flags).float().mean())
             line["config"]["flags_allgather_ms"] = gather_ms
@@ -476,6 +507,8 @@ def main():
     ap.add_argument("--e2e-call", type=int, default=1 << 16)
     ap.add_argument("--e2e-all-planes", action="store_true", help="ship all 14 planes over PCIe in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--records", action="store_true",
+                    help="also run the consumer-side kernel: clamp + pack every sample into a 128-byte record")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

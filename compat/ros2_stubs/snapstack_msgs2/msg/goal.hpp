@@ -8,13 +8,12 @@
 #include <cstdint>
 #include <string>
 
+#include "builtin_interfaces/msg/time.hpp"
+
 namespace snapstack_msgs2 {
 namespace msg {
 
-struct GoalStamp {
-    int32_t sec = 0;
-    uint32_t nanosec = 0;
-};
+using GoalStamp = builtin_interfaces::msg::Time;   // header.stamp = this->now() (TrajectoryGenerator.cpp:606)
 
 struct GoalHeader {
     GoalStamp stamp;

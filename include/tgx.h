@@ -234,6 +234,26 @@ typedef struct tgx_polyline_legs {
     int32_t reserved;
 } tgx_polyline_legs;
 
+/* ---- consumer side ------------------------------------------------------------------
+ * What the node publishes on tick k of TRAJ_FOLLOWING: goal_ = traj_goals_[pub_index_] (TrajectoryGenerator.cpp:557)
+ * with the position saturated to the room bounds (:602-604, saturate() :773-780) — one array-of-structs record per
+ * (trajectory, sample), 128 bytes, so that a fleet of nodes can be fed straight from one engine: the host side turns a
+ * record into a snapstack_msgs2/Goal with a plain copy instead of gathering 14 strided planes. */
+typedef struct tgx_goal_record {
+    double p[3], v[3], a[3], j[3];   /* Goal.p / v / a / j */
+    double psi, dpsi;
+    int32_t traj;                    /* trajectory index in the batch */
+    int32_t k;                       /* sample index = pub_index_ of the tick that publishes it */
+    uint8_t power;                   /* Goal.power: true on every trajectory sample (Circle.cpp:127) */
+    uint8_t mode_xy, mode_z;         /* Goal.MODE_POSITION_CONTROL (0): the samplers never touch them */
+    uint8_t clamped;                 /* bit 0 / 1 / 2: p.x / p.y / p.z was saturated */
+    uint8_t last;                    /* 1 on the trajectory's last sample.  The node never publishes that one: on the tick
+                                        that loads it pub_index_ reaches size(), goal_ is overwritten by the hover goal
+                                        at the vehicle's pose and the node switches to HOVERING
+                                        (TrajectoryGenerator.cpp:561-572) */
+    uint8_t reserved[3];
+} tgx_goal_record;
+
 typedef struct tgx_engine tgx_engine;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */
@@ -326,6 +346,16 @@ int tgx_plan_samples(tgx_engine* e, const tgx_params* d_params, int64_t n, const
  * written x,y,z components) are reduced in the same pass. */
 int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_max_a, void* stream);
 
+/* ---- consumer side: clamp to the room bounds + pack to array-of-structs records ------------ */
+/* Reads the struct-of-arrays planes `planes` (as written by tgx_eval; d_counts[i] samples of trajectory i are valid),
+ * saturates p.x / p.y / p.z to limits->box if limits && limits->check_box (TrajectoryGenerator.cpp:602-604) and writes
+ * record (i, k) to d_records[(d_rec_offset ? d_rec_offset[i] : i * rec_stride) + k] for k < min(d_counts[i],
+ * rec_capacity).  One CTA per 256 samples: coalesced plane reads, a swizzled shared-memory transpose, 512-byte
+ * coalesced record writes.  Does not need (or touch) the current plan. */
+int tgx_pack_goals(tgx_engine* e, const tgx_layout* planes, const int32_t* d_counts, int64_t n,
+                   const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
+                   const int64_t* d_rec_offset, int64_t rec_capacity, void* stream);
+
 /* ---- feasibility only: no sample stores ------------------------------------------------------------ */
 /* Evaluates every sample of the current plan, reduces max |v|, max |a| per trajectory and sets
  * d_flags[i] = 1 iff max_v <= v_max && max_a <= a_max && status has no bit set (incl. OUTSIDE_BOUNDS).
@@ -353,6 +383,13 @@ int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, cons
 int tgx_generate_host_legs(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
                            double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
                            tgx_phases* h_phases, tgx_polyline_legs* h_legs);
+
+/* generateTraj for host-resident parameters straight into clamped array-of-structs records:
+ * h_records[i * rec_capacity + k] (plan, evaluate, tgx_pack_goals, D2H of the records; chunked like tgx_generate_host).
+ * limits->box, if given, is both the trajectoryInsideBounds box (status bit) and the saturation box. */
+int tgx_generate_records_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                              tgx_goal_record* h_records, int64_t rec_capacity, int32_t* h_counts,
+                              uint32_t* h_status);
 
 /* Full generateStopTraj: h_from[i*14..] is the setpoint being braked from. Same output layout. */
 int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const double* h_from,

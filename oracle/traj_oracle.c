@@ -1038,6 +1038,50 @@ int64_t orc_time_batch(const tgx_params* p, int64_t n, int64_t max_samples, int 
     return run_jobs(&j, n, nthreads, checksum);
 }
 
+/* ---- consumer side: what the node publishes while following ----------------------- */
+
+/* TrajectoryGenerator::saturate, TrajectoryGenerator.cpp:773-780. */
+static double saturate(double val, double low, double high) {
+    if (val > high)
+        val = high;
+    else if (val < low)
+        val = low;
+    return val;
+}
+
+/* goal_ = traj_goals_[pub_index_] (TrajectoryGenerator.cpp:557) then the safety bounds (:602-604), for every sample of
+ * one trajectory given as SoA planes samples[c * chan_stride + k].  box may be NULL (no saturation). */
+void orc_pack_goals(const double* samples, int64_t chan_stride, int64_t n, int32_t traj, const double* box,
+                    tgx_goal_record* out) {
+    for (int64_t k = 0; k < n; ++k) {
+        tgx_goal_record r;
+        memset(&r, 0, sizeof(r));
+        double px = samples[TGX_PX * chan_stride + k], py = samples[TGX_PY * chan_stride + k];
+        double pz = samples[TGX_PZ * chan_stride + k];
+        r.p[0] = box ? saturate(px, box[0], box[1]) : px;
+        r.p[1] = box ? saturate(py, box[2], box[3]) : py;
+        r.p[2] = box ? saturate(pz, box[4], box[5]) : pz;
+        for (int c = 0; c < 3; ++c) {
+            r.v[c] = samples[(TGX_VX + c) * chan_stride + k];
+            r.a[c] = samples[(TGX_AX + c) * chan_stride + k];
+            r.j[c] = samples[(TGX_JX + c) * chan_stride + k];
+        }
+        r.psi = samples[TGX_PSI * chan_stride + k];
+        r.dpsi = samples[TGX_DPSI * chan_stride + k];
+        r.traj = traj;
+        r.k = (int32_t)k;
+        r.power = 1;                                   /* goal.power = true, Circle.cpp:127 */
+        r.mode_xy = 0;                                 /* MODE_POSITION_CONTROL, never touched by the samplers */
+        r.mode_z = 0;
+        /* which components the saturation moved (a NaN passes through saturate() and is not "clamped") */
+        r.clamped = box ? (uint8_t)(((px > box[1] || px < box[0]) ? 1 : 0) | ((py > box[3] || py < box[2]) ? 2 : 0) |
+                                    ((pz > box[5] || pz < box[4]) ? 4 : 0))
+                        : 0;
+        r.last = (uint8_t)(k == n - 1);
+        out[k] = r;
+    }
+}
+
 /* ---- checksum ---------------------------------------------------------------------------------------- */
 
 uint64_t orc_fnv1a64(const double* x, int64_t n, uint64_t seed) {

@@ -75,6 +75,12 @@ int orc_feasibility_batch(const tgx_params* p, int64_t n, const tgx_limits* limi
  * return the total number of samples produced; *checksum gets a cheap sum so the work cannot be elided. */
 int64_t orc_time_batch(const tgx_params* p, int64_t n, int64_t max_samples, int nthreads, double* checksum);
 
+/* Consumer side: the Goal the node publishes on tick k of TRAJ_FOLLOWING, traj_goals_[k] with its
+ * position saturated to the room box (TrajectoryGenerator.cpp:557, :602-604, saturate :773-780), for every sample of
+ * one trajectory given as SoA planes samples[c * chan_stride + k].  box = xmin,xmax,ymin,ymax,zmin,zmax or NULL. */
+void orc_pack_goals(const double* samples, int64_t chan_stride, int64_t n, int32_t traj, const double* box,
+                    tgx_goal_record* out);
+
 /* FNV-1a-64 over n doubles (little-endian bytes, -0.0 canonicalised to +0.0), chained through `seed`
  * (pass 0xcbf29ce484222325 to start).  Used for golden checksums. */
 uint64_t orc_fnv1a64(const double* x, int64_t n, uint64_t seed);

@@ -63,6 +63,8 @@ class Oracle:
                                             C.POINTER(C.c_int16), _c_i64]
         L.orc_polyline_msg.restype = C.c_int
         L.orc_polyline_msg.argtypes = [C.c_int, C.c_int, _c_i64, _c_i64, C.c_char_p, C.c_int]
+        L.orc_pack_goals.restype = None
+        L.orc_pack_goals.argtypes = [_c_dp, _c_i64, _c_i64, C.c_int32, _c_dp, C.c_void_p]
         L.orc_fnv1a64.restype = C.c_uint64
         L.orc_fnv1a64.argtypes = [_c_dp, _c_i64, C.c_uint64]
 
@@ -114,6 +116,15 @@ class Oracle:
         out = np.full((abi.TGX_NCHAN, n), np.nan)
         self.lib.orc_stop(p.ctypes.data, _ptr(from14), _ptr(out), n, n, C.byref(st), ph.ctypes.data, max_samples)
         return out, int(st.value), ph[0]
+
+    def pack_goals(self, samples: np.ndarray, traj: int = 0, box=None) -> np.ndarray:
+        """samples [14, N] -> tgx_goal_record array [N]: what the node publishes while following (saturated to box)."""
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        n = samples.shape[1]
+        out = np.zeros(n, dtype=abi.RECORD_DTYPE)
+        b = np.asarray(box, dtype=np.float64) if box is not None else None
+        self.lib.orc_pack_goals(_ptr(samples), n, n, traj, _ptr(b) if b is not None else None, out.ctypes.data)
+        return out
 
     def inside_bounds(self, p: np.ndarray, box) -> bool:
         b = np.asarray(box, dtype=np.float64)

@@ -1,0 +1,199 @@
+"""GPU: the consumer side of the path and the drop-in proven with the reference's own node.
+
+  * tgx_pack_goals (clamp to the room bounds + pack to 128-byte records) against the oracle restatement of
+    TrajectoryGenerator.cpp:557 + :602-604, which tests/test_node_oracle.py pins to the unmodified node: bit-exact;
+  * tgx_generate_records_host end to end;
+  * the UNMODIFIED TrajectoryGenerator.cpp built against the GPU-backed drop-in classes (tests/cpp/bin/libnodegpu.so)
+    flown through the same scripted missions as the same node with the reference's classes (oracle/_ref/libnoderef.so):
+    the two published streams must agree tick for tick.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util
+import node_lib
+from parity import assert_samples_close
+from trajectory_generator_ros2_b200 import abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+BOX = (-1.5, 2.5, -2.0, 1.0, 0.5, 2.0)
+
+
+def oracle_rows(oracle, params, cap):
+    """Oracle samples of a batch as [n, 14, cap] (NaN padded) + counts."""
+    n = len(params)
+    out = np.full((n, abi.TGX_NCHAN, cap), np.nan)
+    counts = np.zeros(n, dtype=np.int32)
+    for i in range(n):
+        p = params[i:i + 1]
+        s = oracle.polyline_generate(p)[0] if abi.is_polyline(int(p["type"][0])) else oracle.generate(p)[0]
+        counts[i] = s.shape[1]
+        out[i, :, :min(cap, s.shape[1])] = s[:, :cap]
+    return out, counts
+
+
+@pytest.mark.parametrize("plane_major", [False, True])
+def test_pack_goals_is_bit_exact(engine, oracle, plane_major):
+    import torch
+    params = abi.concat([workloads.mixed_cfg3(40), workloads.polyline_mix(40, seed=4)])
+    cap = 1280
+    host, counts = oracle_rows(oracle, params, cap)
+    n = len(params)
+    dev = torch.device("cuda", engine.device)
+    planes = torch.from_numpy(np.ascontiguousarray(host.transpose(1, 0, 2)) if plane_major else host).to(dev)
+    d_counts = torch.from_numpy(counts).to(dev)
+    for box in (BOX, None):
+        lim = abi.make_limits(box=box) if box else None
+        rec = engine.pack_goals(planes, d_counts, lim, plane_major=plane_major)
+        torch.cuda.synchronize()
+        got = rec.cpu().numpy().view(abi.RECORD_DTYPE).reshape(n, cap)
+        for i in range(n):
+            m = min(int(counts[i]), cap)
+            want = oracle.pack_goals(host[i, :, :m], traj=i, box=box)
+            if counts[i] > cap:
+                want["last"][:] = 0                       # the trajectory's real last sample is beyond the capacity
+            assert got[i, :m].tobytes() == want.tobytes(), (i, box)
+            assert not got[i, m:].view(np.uint8).any(), "records beyond the count must not be written"
+        if box:
+            assert sum(int((got[i, :counts[i]]["clamped"] != 0).sum()) for i in range(n)) > 1000
+
+
+def test_pack_goals_packed_offsets_and_capacity(engine, oracle):
+    """Ragged batch into a densely packed record array (exclusive scan of the counts), and a record capacity below the
+    sample count."""
+    import torch
+    params = workloads.mixed_cfg3(64, seed=77)
+    host, counts = oracle_rows(oracle, params, 1536)
+    dev = torch.device("cuda", engine.device)
+    planes = torch.from_numpy(host).to(dev)
+    d_counts = torch.from_numpy(counts).to(dev)
+    offs = np.concatenate([[0], np.cumsum(counts[:-1], dtype=np.int64)])
+    total = int(counts.sum())
+    records = torch.zeros((total, 128), dtype=torch.uint8, device=dev)
+    engine.pack_goals(planes, d_counts, abi.make_limits(box=BOX), records=records, rec_capacity=1536,
+                      rec_offset=torch.from_numpy(offs).to(dev))
+    torch.cuda.synchronize()
+    got = records.cpu().numpy().view(abi.RECORD_DTYPE).reshape(total)
+    for i in range(len(params)):
+        want = oracle.pack_goals(host[i, :, :counts[i]], traj=i, box=BOX)
+        assert got[offs[i]:offs[i] + counts[i]].tobytes() == want.tobytes(), i
+    rec = engine.pack_goals(planes, d_counts, None, rec_capacity=300)
+    torch.cuda.synchronize()
+    got = rec.cpu().numpy().view(abi.RECORD_DTYPE).reshape(len(params), 300)
+    for i in (0, 5, 63):
+        m = min(300, counts[i])
+        want = oracle.pack_goals(host[i, :, :m], traj=i)
+        if counts[i] > 300:
+            want["last"][:] = 0
+        assert got[i, :m].tobytes() == want.tobytes()
+
+
+def test_generate_records_host(engine, oracle):
+    """plan + eval + pack + D2H of the records through the host-buffer call, mixed families."""
+    params = abi.concat([workloads.mixed_cfg3(30, seed=5), workloads.polyline_mix(30, seed=6)])
+    counts, _ = engine.count_host(params)
+    cap = int((counts.max() + 3) // 4 * 4)
+    lim = abi.make_limits(box=BOX)
+    rec, counts2, status = engine.generate_records_host(params, cap, lim)
+    o_counts, o_status = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts2, o_counts)
+    host, _ = oracle_rows(oracle, params, cap)
+    for i in range(len(params)):
+        m = int(counts2[i])
+        want = oracle.pack_goals(host[i, :, :m], traj=i, box=BOX)
+        got = rec[i, :m]
+        assert_samples_close(abi.records_to_channels(got), abi.records_to_channels(want), f"records[{i}]")
+        for f in ("traj", "k", "power", "mode_xy", "mode_z", "last"):
+            np.testing.assert_array_equal(got[f], want[f], err_msg=f"{i}:{f}")
+        # the clamp verdict may differ only where the reference sample sits within the tolerance of a wall
+        diff = got["clamped"] != want["clamped"]
+        if diff.any():
+            p = host[i, :3, :m]
+            walls = np.array(BOX).reshape(3, 2)
+            near = (np.abs(p[:, None, :] - walls[:, :, None]) < 1e-9).any(axis=(0, 1))
+            assert near[diff].all(), i
+
+
+# ---- the reference's own node, flown with the drop-in classes ------------------------------------------------
+
+needs_nodes = pytest.mark.skipif(not (os.path.exists(node_lib.NODE_REF_SO) and os.path.exists(node_lib.NODE_GPU_SO)),
+                                 reason="node harness libraries not built (need /root/reference at build time)")
+
+T_GO1, T_GO2, T_GO3 = 5, 700, 2600
+ALL_TYPES = ["Circle", "Line", "Boomerang", "Figure8", "Square", "Reciprocating", "Rectangle", "Bounce", "M", "I", "T"]
+
+
+def compare_streams(ref, gpu, what):
+    assert ref is not None and gpu is not None, what
+    assert ref.shape == gpu.shape, (what, ref.shape, gpu.shape)
+    np.testing.assert_array_equal(ref[:, 0], gpu[:, 0], err_msg=f"{what}: ticks")
+    np.testing.assert_array_equal(ref[:, 15:], gpu[:, 15:], err_msg=f"{what}: power / modes")
+    return assert_samples_close(gpu[:, 1:15].T, ref[:, 1:15].T, what)
+
+
+@needs_nodes
+@pytest.mark.parametrize("traj_type", ALL_TYPES)
+def test_unmodified_node_with_dropin_classes_full_mission(traj_type):
+    """take off -> go to the start -> follow -> (trajectory ends, hover) -> END: go home and land."""
+    cfg = {"traj_type": traj_type, "t_traj": 9.0, "orientation": 0.25, "center_x": 0.3, "center_y": -0.2}
+    ref_node, gpu_node = node_lib.Node(node_lib.NODE_REF_SO), node_lib.Node(node_lib.NODE_GPU_SO)
+    ev = [(T_GO1, node_lib.GO), (T_GO2, node_lib.GO), (T_GO3, node_lib.GO), (7000, node_lib.LAND)]
+    start = (0.4, -0.6, 0.0, 0.2)
+    ref = ref_node.run(cfg, ev, 10500, start)
+    gpu = gpu_node.run(cfg, ev, 10500, start)
+    e = compare_streams(ref, gpu, f"node mission {traj_type}")
+    assert ref[-1, 15] == 0, "the mission must end on the ground with the motors off"
+    assert e["pos_abs"] < 1e-9
+
+
+@needs_nodes
+@pytest.mark.parametrize("traj_type", ["Circle", "Figure8", "Line", "Boomerang", "T", "Bounce", "Reciprocating"])
+def test_unmodified_node_with_dropin_classes_end_pressed_while_following(traj_type):
+    """END while following: the node replaces its goal vector by generateStopTraj's (TrajectoryGenerator.cpp:514-517).
+    The braking count depends on the bits of the sample being braked from, which the drop-in reproduces within
+    tolerance only — so the braking lengths may differ by one step; the streams are compared up to the shorter one and
+    must agree again once both hover."""
+    cfg = {"traj_type": traj_type, "t_traj": 9.0}
+    ref_node, gpu_node = node_lib.Node(node_lib.NODE_REF_SO), node_lib.Node(node_lib.NODE_GPU_SO)
+    t_end = T_GO3 + 420
+    ev = [(T_GO1, node_lib.GO), (T_GO2, node_lib.GO), (T_GO3, node_lib.GO), (t_end, node_lib.LAND)]
+    ref = ref_node.run(cfg, ev, t_end + 900)
+    gpu = gpu_node.run(cfg, ev, t_end + 900)
+    assert ref is not None and gpu is not None
+    r_before, g_before = ref[ref[:, 0] < t_end], gpu[gpu[:, 0] < t_end]
+    compare_streams(r_before, g_before, f"{traj_type} before END")
+
+    def braking(rows):          # ticks from END until the speed reaches zero for good (the hover goal)
+        after = rows[rows[:, 0] >= t_end]
+        moving = np.nonzero(np.abs(after[:, 4:7]).sum(axis=1) > 0)[0]
+        return after, (moving[-1] + 1 if len(moving) else 0)
+
+    r_after, r_n = braking(ref)
+    g_after, g_n = braking(gpu)
+    assert abs(r_n - g_n) <= 1, (traj_type, r_n, g_n)
+    m = min(r_n, g_n)
+    assert m > 10
+    assert_samples_close(g_after[:m, 1:15].T, r_after[:m, 1:15].T, f"{traj_type} braking")
+    # both end hovering at (almost) the same place
+    assert np.abs(ref[-1, 1:4] - gpu[-1, 1:4]).max() < 1e-6 and (ref[-1, 4:13] == 0).all() and (gpu[-1, 4:13] == 0).all()
+
+
+@needs_nodes
+def test_node_refuses_the_same_configurations():
+    """readParameters() fails for the same parameter files on both builds when the shape does not fit the room
+    (trajectoryInsideBounds, TrajectoryGenerator.cpp:419-422).  (Parameter files the node rejects BEFORE it has
+    constructed traj_ — accel <= 0, an unknown traj_type — make the reference dereference a null traj_ at :71, and a Line
+    too short for its speed runs into Line.cpp:76-79's exit(1): those end the process on both builds and are not
+    flown here.)"""
+    ref_node, gpu_node = node_lib.Node(node_lib.NODE_REF_SO), node_lib.Node(node_lib.NODE_GPU_SO)
+    tight = {"x_min": -1.0, "x_max": 1.0, "y_min": -1.0, "y_max": 1.0}
+    for cfg in ({"traj_type": "Circle", **tight}, {"traj_type": "T", **tight},
+                {"traj_type": "Square", "side_length": 3.0, **tight}, {"traj_type": "Bounce", "z_max": 3.0},
+                {"traj_type": "Reciprocating", **tight}, {"traj_type": "M", "orientation": 0.7, "x_max": 2.2}):
+        assert ref_node.run(cfg, [], 3) is None, cfg
+        assert gpu_node.run(cfg, [], 3) is None, cfg
+    ok = {"traj_type": "Square", "side_length": 1.5, **tight}
+    assert ref_node.run(ok, [], 3) is not None and gpu_node.run(ok, [], 3) is not None

@@ -120,6 +120,15 @@ class PolylineLegs(C.Structure):
                 ("period", C.c_int32), ("count", C.c_int32 * TGX_POLY_MAX_LEGS), ("reserved", C.c_int32)]
 
 
+class GoalRecord(C.Structure):
+    """struct tgx_goal_record (128 bytes)."""
+    _fields_ = [("p", C.c_double * 3), ("v", C.c_double * 3), ("a", C.c_double * 3), ("j", C.c_double * 3),
+                ("psi", C.c_double), ("dpsi", C.c_double), ("traj", C.c_int32), ("k", C.c_int32),
+                ("power", C.c_uint8), ("mode_xy", C.c_uint8), ("mode_z", C.c_uint8), ("clamped", C.c_uint8),
+                ("last", C.c_uint8), ("reserved", C.c_uint8 * 3)]
+
+
+assert C.sizeof(GoalRecord) == 128, C.sizeof(GoalRecord)
 assert C.sizeof(PolylineLegs) == 64, C.sizeof(PolylineLegs)
 assert C.sizeof(Params) == 128, C.sizeof(Params)
 assert C.sizeof(Limits) == 72, C.sizeof(Limits)
@@ -141,6 +150,20 @@ PARAMS_DTYPE = np.dtype({
                 24, 32, 40, 48, 56, 64, 72],
     "itemsize": 128,
 })
+
+RECORD_DTYPE = np.dtype({
+    "names": ["p", "v", "a", "j", "psi", "dpsi", "traj", "k", "power", "mode_xy", "mode_z", "clamped", "last"],
+    "formats": [("<f8", (3,)), ("<f8", (3,)), ("<f8", (3,)), ("<f8", (3,)), "<f8", "<f8", "<i4", "<i4",
+                "u1", "u1", "u1", "u1", "u1"],
+    "offsets": [0, 24, 48, 72, 96, 104, 112, 116, 120, 121, 122, 123, 124],
+    "itemsize": 128,
+})
+
+
+def records_to_channels(rec: np.ndarray) -> np.ndarray:
+    """tgx_goal_record array [N] -> samples [14, N] in tgx_channel order."""
+    return np.concatenate([rec["p"].T, rec["v"].T, rec["a"].T, rec["j"].T, rec["psi"][None], rec["dpsi"][None]], axis=0)
+
 
 LEGS_DTYPE = np.dtype({
     "names": ["n", "n_legs", "first_special", "last_special", "period", "count"],

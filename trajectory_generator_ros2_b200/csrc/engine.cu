@@ -59,6 +59,9 @@ cudaError_t launch_plan_poly(const tgx_params* params, int64_t n, const tgx_limi
 size_t poly_rec_bytes();
 cudaError_t launch_poly_tiles(int64_t n, const int32_t* ntile, const int64_t* tile_off, int tile_shift, Tile* tiles,
                               cudaStream_t stream);
+cudaError_t launch_pack_goals(const OutView& in, const int32_t* counts, int64_t n, const tgx_limits* lim,
+                              tgx_goal_record* records, int64_t rec_stride, const int64_t* rec_offset,
+                              int64_t rec_capacity, cudaStream_t stream);
 cudaError_t launch_eval_poly(const PolyView& pv, int64_t ntiles, int tile_shift, int spt, const OutView& out,
                              bool store, double* max_v, double* max_a, cudaStream_t stream);
 
@@ -202,7 +205,7 @@ struct tgx_engine {
     cudaStream_t hs[2] = {nullptr, nullptr};
     cudaEvent_t hev[2] = {nullptr, nullptr};       // slot's D2H copies done -> its staging buffers are reusable
     cudaEvent_t hev_eval = nullptr;                // last evaluation done -> the shared plan tables are reusable
-    DevBuf h_params[2], h_out[2], h_cnt[2], h_st[2], h_ph[2], h_from[2];
+    DevBuf h_params[2], h_out[2], h_cnt[2], h_st[2], h_ph[2], h_from[2], h_rec[2];
 };
 
 namespace {
@@ -574,6 +577,7 @@ int tgx_destroy(tgx_engine* e) {
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         e->h_legs[i].release();
+        e->h_rec[i].release();
         e->h_params[i].release();
         e->h_out[i].release();
         e->h_cnt[i].release();
@@ -798,6 +802,20 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
     return TGX_OK;
 }
 
+int tgx_pack_goals(tgx_engine* e, const tgx_layout* planes, const int32_t* d_counts, int64_t n,
+                   const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
+                   const int64_t* d_rec_offset, int64_t rec_capacity, void* stream) {
+    if (!e || n < 0 || rec_capacity < 0 || (n > 0 && (!planes || !planes->d_base || !d_counts || !d_records)))
+        return TGX_ERR_INVALID;
+    if (n == 0 || rec_capacity == 0) return TGX_OK;
+    if ((reinterpret_cast<uintptr_t>(d_records) & 15u) != 0) return TGX_ERR_ALIGNMENT;
+    TGX_CUDA(cudaSetDevice(e->device));
+    TGX_CUDA(tgx::launch_pack_goals(make_view(planes), d_counts, n, limits, d_records, rec_stride, d_rec_offset,
+                                    rec_capacity, static_cast<cudaStream_t>(stream)));
+    e->launches += 1;
+    return TGX_OK;
+}
+
 int tgx_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi) {
     if (n < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return TGX_ERR_INVALID;
     // floor(rank*n/world) without overflow for n < 2^62 / world
@@ -909,8 +927,10 @@ constexpr uint32_t kVaryingChannels = 0x3fffu & ~((1u << TGX_PZ) | (1u << TGX_VZ
 // Shared body of tgx_generate_host / tgx_stop_host.
 static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_from, int64_t n,
                     const tgx_limits* limits, double* h_out, int64_t capacity, int32_t* h_counts,
-                    uint32_t* h_status, tgx_phases* h_phases, tgx_polyline_legs* h_legs) {
-    if (!e || n < 0 || (n > 0 && (!h_params || !h_out)) || capacity < 0) return TGX_ERR_INVALID;
+                    uint32_t* h_status, tgx_phases* h_phases, tgx_polyline_legs* h_legs,
+                    tgx_goal_record* h_records = nullptr) {
+    // h_records != nullptr: the samples stay on the device; what travels is one clamped 128-byte record per sample
+    if (!e || n < 0 || (n > 0 && (!h_params || (!h_out && !h_records))) || capacity < 0) return TGX_ERR_INVALID;
     if (capacity % 4 != 0) return TGX_ERR_ALIGNMENT;
     if (n == 0) return TGX_OK;
     TGX_CUDA(cudaSetDevice(e->device));
@@ -931,6 +951,9 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         if (h_phases && (rc = e->h_ph[b].reserve((size_t)chunk * sizeof(tgx_phases)))) return rc;
         if (h_from && (rc = e->h_from[b].reserve((size_t)chunk * TGX_NCHAN * sizeof(double)))) return rc;
         if (h_legs && (rc = e->h_legs[b].reserve((size_t)chunk * sizeof(tgx_polyline_legs)))) return rc;
+        if (h_records &&
+            (rc = e->h_rec[b].reserve((size_t)std::max<int64_t>(chunk * capacity, 1) * sizeof(tgx_goal_record))))
+            return rc;
     }
     // Bounce moves along z (Bounce.cpp:39-41): its z-channels are not constants
     KindMix whole;
@@ -940,7 +963,7 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
     // The z-components are literal constants in the reference (p.z = alt_, v.z = a.z = j.z = 0: Circle.cpp:109-121,
     // Line.cpp:99-108, Figure8.cpp:110-119).  They are not worth 29 % of the PCIe traffic: the device evaluates and
     // ships the 10 varying planes, and host threads write the 4 constant rows of every trajectory meanwhile.
-    const bool fill = e->host_fill_constants && capacity > 0 && !whole.bounce;
+    const bool fill = e->host_fill_constants && capacity > 0 && !whole.bounce && !h_records;
     std::vector<std::thread> fillers;
     if (fill) {
         unsigned hw = std::thread::hardware_concurrency();
@@ -1012,7 +1035,15 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
             if (rc) return rc;
             if (capacity > 0 && (rc = tgx_eval(e, &lay, nullptr, nullptr, s))) return rc;
         }
-        if (capacity > 0) {
+        if (capacity > 0 && h_records) {
+            TGX_CUDA(tgx::launch_pack_goals(make_view(&lay), e->h_cnt[b].as<int32_t>(), m,
+                                            (limits && limits->check_box) ? limits : nullptr,
+                                            e->h_rec[b].as<tgx_goal_record>(), capacity, nullptr, capacity, s));
+            e->launches += 1;
+            TGX_CUDA(cudaEventRecord(e->hev_eval, s));
+            TGX_CUDA(cudaMemcpyAsync(h_records + lo * capacity, e->h_rec[b].p,
+                                     (size_t)(m * capacity) * sizeof(tgx_goal_record), cudaMemcpyDeviceToHost, s));
+        } else if (capacity > 0) {
             TGX_CUDA(cudaEventRecord(e->hev_eval, s));
             if (fill) {
                 // the varying planes come in adjacent pairs (px,py | vx,vy | ax,ay | jx,jy | psi,dpsi): five 2-D copies,
@@ -1088,6 +1119,14 @@ int tgx_generate_host_legs(tgx_engine* e, const tgx_params* h_params, int64_t n,
                            double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
                            tgx_phases* h_phases, tgx_polyline_legs* h_legs) {
     return host_run(e, h_params, nullptr, n, limits, h_out, capacity, h_counts, h_status, h_phases, h_legs);
+}
+
+int tgx_generate_records_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                              tgx_goal_record* h_records, int64_t rec_capacity, int32_t* h_counts,
+                              uint32_t* h_status) {
+    if (n > 0 && !h_records) return TGX_ERR_INVALID;
+    return host_run(e, h_params, nullptr, n, limits, nullptr, rec_capacity, h_counts, h_status, nullptr, nullptr,
+                    h_records);
 }
 
 int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const double* h_from, double* h_out,

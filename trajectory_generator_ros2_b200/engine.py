@@ -62,6 +62,8 @@ def _load() -> C.CDLL:
     lib.tgx_plan_polyline.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64), vp]
     lib.tgx_polyline_finalize_host.argtypes = [vp, i64]
     lib.tgx_generate_host_legs.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp]
+    lib.tgx_pack_goals.argtypes = [vp, C.POINTER(abi.Layout), vp, i64, vp, vp, i64, vp, i64, vp]
+    lib.tgx_generate_records_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp]
     lib.tgx_eval.argtypes = [vp, C.POINTER(abi.Layout), vp, vp, vp]
     lib.tgx_feasibility.argtypes = [vp, C.POINTER(abi.Limits), vp, vp, vp, vp, vp]
     lib.tgx_count_host.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -323,6 +325,45 @@ class Engine:
     def eval_layout(self, lay: abi.Layout, max_v=None, max_a=None):
         self._check(self._lib.tgx_eval(self._h, C.byref(lay), max_v.data_ptr() if max_v is not None else None,
                                        max_a.data_ptr() if max_a is not None else None, self._stream()), "tgx_eval")
+
+    def pack_goals(self, planes, counts, limits: Optional[abi.Limits] = None, records=None, rec_capacity=None,
+                   rec_offset=None, plane_major: bool = False):
+        """tgx_pack_goals: SoA planes [n, 14, row] (or [14, n, row]) + counts -> tgx_goal_record tensor
+        (uint8 [n, rec_capacity, 128], or a flat [total, 128] one addressed through rec_offset)."""
+        import torch
+        assert planes.dtype == torch.float64 and planes.is_contiguous()
+        lay = abi.Layout()
+        lay.d_base = planes.data_ptr()
+        if plane_major:
+            nch, n, row = planes.shape
+            lay.traj_stride, lay.chan_stride = row, n * row
+        else:
+            n, nch, row = planes.shape
+            lay.traj_stride, lay.chan_stride = nch * row, row
+        lay.capacity = row
+        cap = row if rec_capacity is None else rec_capacity
+        if records is None:
+            records = torch.zeros((n, cap, 128), dtype=torch.uint8, device=planes.device)
+        self._check(self._lib.tgx_pack_goals(self._h, C.byref(lay), counts.data_ptr(), n, _limits_ptr(limits),
+                                             records.data_ptr(), cap,
+                                             rec_offset.data_ptr() if rec_offset is not None else None, cap,
+                                             self._stream()), "tgx_pack_goals")
+        return records
+
+    def generate_records_host(self, params: np.ndarray, rec_capacity: int, limits: Optional[abi.Limits] = None,
+                              records: Optional[np.ndarray] = None):
+        """tgx_generate_records_host -> (records [n, rec_capacity] of RECORD_DTYPE, counts, status)."""
+        params = np.ascontiguousarray(params)
+        n = len(params)
+        if records is None:
+            records = np.zeros((n, rec_capacity), dtype=abi.RECORD_DTYPE)
+        assert records.dtype == abi.RECORD_DTYPE and records.flags.c_contiguous and records.shape == (n, rec_capacity)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.tgx_generate_records_host(self._h, params.ctypes.data, n, _limits_ptr(limits),
+                                                        records.ctypes.data, rec_capacity, counts.ctypes.data,
+                                                        status.ctypes.data), "tgx_generate_records_host")
+        return records, counts, status
 
     def feasibility(self, limits: abi.Limits, n: int, flags=None, max_v=None, max_a=None, status=None):
         """tgx_feasibility on the current plan -> (flags uint8 [n], max_v, max_a, status int32)."""
