@@ -491,13 +491,73 @@ def run_ours(args):
     eng.close()
 
 
+def run_transitions(args):
+    """the node's own take-off / go-to / landing recurrences for a fleet, one thread per vehicle, one
+    128-byte record per tick.  Single GPU; rank 0 prints one JSON line (same keys, the roofline counts record bytes)."""
+    import torch
+    from trajectory_generator_ros2_b200 import abi, workloads
+    from trajectory_generator_ros2_b200.engine import Engine
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    eng = Engine(0)
+    dev = torch.device("cuda", 0)
+    n = args.n_per_gpu if args.n_per_gpu != (1 << 20) else (1 << 17)
+    t = workloads.fleet_transitions(n)
+    d_t = torch.from_numpy(t.view(np.uint8).reshape(n, 128)).to(dev)
+    lim = abi.make_limits(box=(-5.0, 5.0, -5.0, 5.0, 0.0, 5.0))
+    _, counts, status = eng.transitions(d_t, 0, lim)
+    torch.cuda.synchronize()
+    cap = int(counts.max().item())
+    cap = (cap + 3) // 4 * 4
+    total = int(counts.sum(dtype=torch.int64).item())
+    rec = torch.empty((n, cap, 128), dtype=torch.uint8, device=dev)
+    for _ in range(args.warmup):
+        eng.transitions(d_t, cap, lim, records=rec)
+    sampler = ClockSampler(0)
+    torch.cuda.synchronize()
+    sampler.mark_start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launch_count
+    a.record()
+    for _ in range(args.steps):
+        eng.transitions(d_t, cap, lim, records=rec)
+    b.record()
+    torch.cuda.synchronize()
+    sampler.mark_stop()
+    ms = a.elapsed_time(b) / args.steps
+    launches = eng.launch_count - l0
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    achieved = 128.0 * total / (ms * 1e-3) / 1e9
+    # CPU leg: the oracle restatement (pinned to the unmodified node by tests/test_node_oracle.py), one host thread
+    from oracle_lib import Oracle
+    orc = Oracle()
+    m = min(n, 512)
+    t0 = time.perf_counter()
+    ticks = sum(len(orc.transition(t[i:i + 1], box=(-5.0, 5.0, -5.0, 5.0, 0.0, 5.0))[0]) for i in range(m))
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({
+        "metric": "transition setpoints/s (take-off / go-to / landing recurrences)", "value": total / (ms * 1e-3),
+        "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"SURVEY 8(f4): {n} vehicles, one take-off / go-to / landing phase each (rng 1240), "
+                               f"{total} ticks, record rows of {cap}", "l2": "%.1f GB of records per step" % (128e-9 * total)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "tgx::transition_kernel", "bytes_per_launch": 128.0 * total,
+                     "peak_source": peak_src},
+        "cpu_baseline": {"value": ticks / cpu_s, "unit": "samples/s", "cores": 1, "kind": "port",
+                         "sample": f"first {m} vehicles ({ticks} ticks) through orc_transition incl. the Python call overhead"},
+        "e2e": None, "gpu_launches": launches, "clocks": clocks}), flush=True)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="circles_cfg2", choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--workload", default="circles_cfg2", choices=sorted(WORKLOAD_DESC) + ["transitions"])
     ap.add_argument("--n-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--plane-major", action="store_true")
     ap.add_argument("--tile-shift", type=int, default=0)
@@ -512,7 +572,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    if args.impl == "reference":
+    if args.workload == "transitions":
+        run_transitions(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -254,6 +254,34 @@ typedef struct tgx_goal_record {
     uint8_t reserved[3];
 } tgx_goal_record;
 
+/* ---- node-side transitions -------------------------------------------------------------
+ * The setpoints the node generates itself around a trajectory, one per 100 Hz tick, as recurrences on its own goal_:
+ *   TAKEOFF  goal_.p.z = saturate(goal_.p.z + vel_take*dt, 0, alt) until the vehicle is within 0.10 m of alt
+ *            (TrajectoryGenerator.cpp:531-548)
+ *   GOTO     goal_ = simpleInterpolation(goal_, dest, dest_yaw, vel, vel_yaw, dist_thresh, yaw_thresh, dt, finished)
+ *            (:549-554 towards traj_goals_[0], :574-586 back to the take-off point; simpleInterpolation :637-764)
+ *   LANDING  goal_.p.z -= (pose.z > ground + 0.4 ? vel_land_fast : vel_land_slow)*dt until goal_.p.z < 0 (:588-599)
+ * followed on every tick by the saturation of goal_.p to the room box, which feeds back into the recurrence (:602-604).
+ * The node reads the vehicle's pose in two places (the hover test of TAKEOFF, the speed choice of LANDING); the batch
+ * engine assumes PERFECT TRACKING there: the pose on tick k is the goal published on tick k-1.  One record per tick. */
+enum tgx_transition_kind { TGX_TR_TAKEOFF = 0, TGX_TR_GOTO = 1, TGX_TR_LANDING = 2 };
+
+typedef struct tgx_transition_params {          /* 128 bytes */
+    int32_t kind;                /* enum tgx_transition_kind */
+    int32_t ticks;               /* 0: run until the phase ends by itself (hover reached / finished / landed);
+                                    > 0: exactly that many ticks (a GOTO keeps holding its destination, as the node does
+                                    while it waits for the operator, :549-554) */
+    double dt;
+    double start[3];             /* goal_.p when the phase starts */
+    double start_v[2];           /* goal_.v.x, goal_.v.y (simpleInterpolation smooths the velocity reference, :662-663) */
+    double start_psi;            /* goal_.psi */
+    double dest[3];              /* GOTO: destination; TAKEOFF: dest[2] = alt_; LANDING: dest[2] = init_pos_.z */
+    double dest_yaw;             /* GOTO only (the trip home passes start_psi: :579 uses goal_.psi itself) */
+    double vel;                  /* TAKEOFF vel_take_; GOTO vel_initpos_; LANDING vel_land_fast_ */
+    double vel_yaw;              /* GOTO vel_yaw_; LANDING vel_land_slow_ */
+    double dist_thresh, yaw_thresh;   /* GOTO */
+} tgx_transition_params;
+
 typedef struct tgx_engine tgx_engine;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */
@@ -355,6 +383,20 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
 int tgx_pack_goals(tgx_engine* e, const tgx_layout* planes, const int32_t* d_counts, int64_t n,
                    const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
                    const int64_t* d_rec_offset, int64_t rec_capacity, void* stream);
+
+/* ---- node-side transitions ------------------------------------------------------------ */
+/* One thread per vehicle replays the recurrence of its tgx_transition_params with the reference's own operation
+ * order (no transcendental is involved: the results are bit-identical) and writes one tgx_goal_record per tick to
+ * d_records[i * rec_stride + k], k < rec_capacity (record.k = tick within the phase, record.last = 1 on the tick that
+ * ends it, record.power = 0 on the landing tick that cuts the motors).  d_counts[i] = number of ticks of the phase,
+ * d_status[i] = 0, TGX_ST_BAD_PARAM, TGX_ST_TOO_LONG (not finished within max_samples ticks) or TGX_ST_TRUNCATED.
+ * limits->box (if limits && limits->check_box) is the room box of :602-604. */
+int tgx_transitions(tgx_engine* e, const tgx_transition_params* d_tparams, int64_t n, const tgx_limits* limits,
+                    tgx_goal_record* d_records, int64_t rec_stride, int64_t rec_capacity, int32_t* d_counts,
+                    uint32_t* d_status, void* stream);
+/* Host-buffer variant: H2D, tgx_transitions, D2H of h_records[i * rec_capacity + k]. */
+int tgx_transitions_host(tgx_engine* e, const tgx_transition_params* h_tparams, int64_t n, const tgx_limits* limits,
+                         tgx_goal_record* h_records, int64_t rec_capacity, int32_t* h_counts, uint32_t* h_status);
 
 /* ---- feasibility only: no sample stores ------------------------------------------------------------ */
 /* Evaluates every sample of the current plan, reduces max |v|, max |a| per trajectory and sets

@@ -1082,6 +1082,129 @@ void orc_pack_goals(const double* samples, int64_t chan_stride, int64_t n, int32
     }
 }
 
+/* ---- node-side transitions ------------------------------------------------------------ */
+
+/* TrajectoryGenerator::wrap, TrajectoryGenerator.cpp:782-788. */
+static double wrap_pi(double val) {
+    if (val > M_PI) val -= 2.0 * M_PI;
+    if (val < -M_PI) val += 2.0 * M_PI;
+    return val;
+}
+
+static int transition_ok(const tgx_transition_params* t) {
+    if (!(isfinite(t->dt) && t->dt > 0.0) || t->ticks < 0) return 0;
+    for (int i = 0; i < 3; ++i)
+        if (!isfinite(t->start[i]) || !isfinite(t->dest[i])) return 0;
+    if (!isfinite(t->start_v[0]) || !isfinite(t->start_v[1]) || !isfinite(t->start_psi)) return 0;
+    if (!(isfinite(t->vel) && t->vel > 0.0)) return 0;
+    if (t->kind == TGX_TR_TAKEOFF) return 1;
+    if (t->kind == TGX_TR_LANDING) return isfinite(t->vel_yaw) && t->vel_yaw > 0.0;
+    if (t->kind == TGX_TR_GOTO)
+        return isfinite(t->dest_yaw) && isfinite(t->vel_yaw) && t->vel_yaw > 0.0 && isfinite(t->dist_thresh) &&
+               t->dist_thresh >= 0.0 && isfinite(t->yaw_thresh) && t->yaw_thresh >= 0.0;
+    return 0;
+}
+
+/* The goals pubCB publishes tick by tick in TAKING_OFF (TrajectoryGenerator.cpp:531-548), INIT_POS_TRAJ / INIT_POS
+ * (:549-554, :574-586 through simpleInterpolation :637-764) and LANDING (:588-599), each followed by the saturation of
+ * goal_.p to the room box (:602-604), under perfect tracking (pose on tick k = goal published on tick k-1).
+ * Returns the number of ticks; the first `cap` are written to out (may be NULL). */
+int64_t orc_transition(const tgx_transition_params* t, int32_t traj, const double* box, tgx_goal_record* out,
+                       int64_t cap, uint32_t* status, int64_t max_samples) {
+    uint32_t st = 0;
+    int64_t k = 0;
+    if (!transition_ok(t)) {
+        if (status) *status = TGX_ST_BAD_PARAM;
+        return 0;
+    }
+    double px = t->start[0], py = t->start[1], pz = t->start[2];
+    double vx = t->start_v[0], vy = t->start_v[1], psi = t->start_psi, dpsi = 0.0;
+    int power = 1;
+    double pose_z = pz;
+    int64_t limit = t->ticks > 0 ? t->ticks : max_samples;
+    int done = 0;
+    while (!done) {
+        if (k >= limit) {
+            if (t->ticks == 0) st |= TGX_ST_TOO_LONG;
+            break;
+        }
+        int ends = 0;
+        if (t->kind == TGX_TR_TAKEOFF) {
+            double takeoff_alt = t->dest[2];          /* :535 */
+            double eps = 0.10;
+            if (fabs(takeoff_alt - pose_z) < eps && pz >= takeoff_alt) ends = 1;   /* :540-543 */
+            else pz = saturate(pz + t->vel * t->dt, 0.0, takeoff_alt);             /* :547 */
+        } else if (t->kind == TGX_TR_GOTO) {
+            double Dx = t->dest[0] - px;              /* :642-644 */
+            double Dy = t->dest[1] - py;
+            double dist = sqrt(Dx * Dx + Dy * Dy);
+            double delta_yaw = t->dest_yaw - psi;     /* :646-647 */
+            delta_yaw = wrap_pi(delta_yaw);
+            int dist_far = dist > t->dist_thresh;     /* :649-651 */
+            int yaw_far = fabs(delta_yaw) > t->yaw_thresh;
+            ends = !dist_far && !yaw_far;
+            int accel_for_vel = 1;                    /* `bool accel_for_vel = 0.1;` (:653) */
+            double npx, npy, nvx, nvy, npsi, ndpsi;
+            if (dist_far) {                           /* :657-670 */
+                double c = Dx / dist;
+                double s = Dy / dist;
+                npx = px + c * t->vel * t->dt;
+                npy = py + s * t->vel * t->dt;
+                nvx = std_min(vx + accel_for_vel * t->dt, c * t->vel);
+                nvy = std_min(vy + accel_for_vel * t->dt, s * t->vel);
+            } else {                                  /* :671-683 */
+                npx = t->dest[0];
+                npy = t->dest[1];
+                nvx = std_max(0.0, vx - accel_for_vel * t->dt);
+                nvy = std_max(0.0, vy - accel_for_vel * t->dt);
+            }
+            if (yaw_far) {                            /* :685-693 */
+                int sgn = delta_yaw >= 0 ? 1 : -1;
+                double vel_yaw = sgn * t->vel_yaw;
+                npsi = psi + vel_yaw * t->dt;
+                ndpsi = vel_yaw;
+            } else {
+                npsi = t->dest_yaw;
+                ndpsi = 0;
+            }
+            px = npx; py = npy; pz = t->dest[2]; vx = nvx; vy = nvy; psi = npsi; dpsi = ndpsi;
+        } else {
+            double vel_land = pose_z > (t->dest[2] + 0.4) ? t->vel : t->vel_yaw;   /* :590 */
+            pz = pz - vel_land * t->dt;               /* :591 */
+            if (pz < 0) {                             /* :593-598 */
+                power = 0;
+                ends = 1;
+            }
+        }
+        int clamped = 0;
+        if (box) {                                    /* :602-604 */
+            clamped = ((px > box[1] || px < box[0]) ? 1 : 0) | ((py > box[3] || py < box[2]) ? 2 : 0) |
+                      ((pz > box[5] || pz < box[4]) ? 4 : 0);
+            px = saturate(px, box[0], box[1]);
+            py = saturate(py, box[2], box[3]);
+            pz = saturate(pz, box[4], box[5]);
+        }
+        done = ends && t->ticks == 0;
+        if (out && k < cap) {
+            tgx_goal_record r;
+            memset(&r, 0, sizeof(r));
+            r.p[0] = px; r.p[1] = py; r.p[2] = pz;
+            r.v[0] = vx; r.v[1] = vy;
+            r.psi = psi; r.dpsi = dpsi;
+            r.traj = traj; r.k = (int32_t)k;
+            r.power = (uint8_t)power;
+            r.clamped = (uint8_t)clamped;
+            r.last = (uint8_t)(done || (t->ticks > 0 && k + 1 == limit));
+            out[k] = r;
+        }
+        pose_z = pz;
+        ++k;
+    }
+    if (out && k > cap) st |= TGX_ST_TRUNCATED;
+    if (status) *status = st;
+    return k;
+}
+
 /* ---- checksum ---------------------------------------------------------------------------------------- */
 
 uint64_t orc_fnv1a64(const double* x, int64_t n, uint64_t seed) {

@@ -81,6 +81,11 @@ int64_t orc_time_batch(const tgx_params* p, int64_t n, int64_t max_samples, int 
 void orc_pack_goals(const double* samples, int64_t chan_stride, int64_t n, int32_t traj, const double* box,
                     tgx_goal_record* out);
 
+/* Node-side transitions: take-off ramp, simpleInterpolation towards a destination, landing
+ * (TrajectoryGenerator.cpp:531-599, :637-764, :602-604) under perfect tracking; see tgx_transition_params. */
+int64_t orc_transition(const tgx_transition_params* t, int32_t traj, const double* box, tgx_goal_record* out,
+                       int64_t cap, uint32_t* status, int64_t max_samples);
+
 /* FNV-1a-64 over n doubles (little-endian bytes, -0.0 canonicalised to +0.0), chained through `seed`
  * (pass 0xcbf29ce484222325 to start).  Used for golden checksums. */
 uint64_t orc_fnv1a64(const double* x, int64_t n, uint64_t seed);

@@ -65,6 +65,8 @@ class Oracle:
         L.orc_polyline_msg.argtypes = [C.c_int, C.c_int, _c_i64, _c_i64, C.c_char_p, C.c_int]
         L.orc_pack_goals.restype = None
         L.orc_pack_goals.argtypes = [_c_dp, _c_i64, _c_i64, C.c_int32, _c_dp, C.c_void_p]
+        L.orc_transition.restype = _c_i64
+        L.orc_transition.argtypes = [C.c_void_p, C.c_int32, _c_dp, C.c_void_p, _c_i64, C.POINTER(C.c_uint32), _c_i64]
         L.orc_fnv1a64.restype = C.c_uint64
         L.orc_fnv1a64.argtypes = [_c_dp, _c_i64, C.c_uint64]
 
@@ -125,6 +127,19 @@ class Oracle:
         b = np.asarray(box, dtype=np.float64) if box is not None else None
         self.lib.orc_pack_goals(_ptr(samples), n, n, traj, _ptr(b) if b is not None else None, out.ctypes.data)
         return out
+
+    def transition(self, t: np.ndarray, traj: int = 0, box=None, max_samples: int = abi.DEFAULT_MAX_SAMPLES):
+        """One tgx_transition_params record -> (records [N] of RECORD_DTYPE, status)."""
+        assert t.dtype == abi.TRANSITION_DTYPE and t.shape == (1,)
+        b = np.asarray(box, dtype=np.float64) if box is not None else None
+        st = C.c_uint32(0)
+        n = self.lib.orc_transition(t.ctypes.data, traj, _ptr(b) if b is not None else None, None, 0, C.byref(st),
+                                    max_samples)
+        out = np.zeros(n, dtype=abi.RECORD_DTYPE)
+        if n:
+            self.lib.orc_transition(t.ctypes.data, traj, _ptr(b) if b is not None else None, out.ctypes.data, n,
+                                    C.byref(st), max_samples)
+        return out, int(st.value)
 
     def inside_bounds(self, p: np.ndarray, box) -> bool:
         b = np.asarray(box, dtype=np.float64)

@@ -197,3 +197,108 @@ def test_node_refuses_the_same_configurations():
         assert gpu_node.run(cfg, [], 3) is None, cfg
     ok = {"traj_type": "Square", "side_length": 1.5, **tight}
     assert ref_node.run(ok, [], 3) is not None and gpu_node.run(ok, [], 3) is not None
+
+
+# ---- node-side transitions ------------------------------------------------------------------
+
+def random_transitions(n, seed=11):
+    rng = np.random.default_rng(seed)
+    t = np.zeros(n, dtype=abi.TRANSITION_DTYPE)
+    kind = rng.integers(0, 3, n)
+    t["kind"] = kind
+    t["dt"] = rng.choice([0.01, 0.02, 0.005], n)
+    t["start"] = rng.uniform(-4, 4, (n, 3))
+    t["start"][:, 2] = np.where(kind == abi.TR_TAKEOFF, rng.uniform(0.0, 0.3, n), rng.uniform(1.0, 2.5, n))
+    t["start_v"] = np.where(rng.random((n, 2)) < 0.5, 0.0, rng.uniform(-0.5, 0.5, (n, 2)))
+    t["start_psi"] = rng.uniform(-3.5, 3.5, n)
+    t["dest"] = rng.uniform(-4, 4, (n, 3))
+    t["dest"][:, 2] = np.where(kind == abi.TR_LANDING, rng.uniform(0.0, 0.2, n), rng.uniform(1.0, 2.5, n))
+    t["dest_yaw"] = rng.uniform(-3.5, 3.5, n)
+    t["vel"] = np.where(kind == abi.TR_GOTO, rng.uniform(0.2, 1.0, n), rng.uniform(0.2, 0.5, n))
+    t["vel_yaw"] = np.where(kind == abi.TR_LANDING, rng.uniform(0.03, 0.1, n), rng.uniform(0.1, 0.5, n))
+    t["dist_thresh"] = rng.uniform(0.05, 0.4, n)
+    t["yaw_thresh"] = rng.uniform(0.05, 0.3, n)
+    t["ticks"] = np.where((kind == abi.TR_GOTO) & (rng.random(n) < 0.3), rng.integers(1, 3000, n), 0)
+    return t
+
+
+def test_transitions_are_bit_exact(engine, oracle):
+    """tgx_transitions against the oracle restatement that tests/test_node_oracle.py pins to the unmodified node."""
+    t = random_transitions(600)
+    # some rejected records and one that cannot end within the guard
+    t["dt"][5] = 0.0
+    t["vel"][6] = -1.0
+    t["kind"][7] = 9
+    # destinations beyond the walls can never be reached: the vehicle pushes against the wall until the guard fires
+    box = (-3.5, 3.5, -3.0, 3.8, 0.0, 2.2)
+    lim = abi.make_limits(box=box)
+    guard = 6000
+    engine.set_max_samples(guard)
+    try:
+        _, counts, status = engine.transitions_host(t, 0, lim)
+        cap = int(counts.max())
+        rec, counts2, status2 = engine.transitions_host(t, cap, lim)
+    finally:
+        engine.set_max_samples(abi.DEFAULT_MAX_SAMPLES)
+    np.testing.assert_array_equal(counts, counts2)
+    assert cap == guard and (status2 & abi.ST_TOO_LONG).any()
+    kinds_seen = set()
+    for i in range(len(t)):
+        want, st = oracle.transition(t[i:i + 1], traj=i, box=box, max_samples=guard)
+        assert counts[i] == len(want) and status2[i] == st, (i, counts[i], len(want), status2[i], st)
+        assert rec[i, :len(want)].tobytes() == want.tobytes(), i
+        assert not rec[i, len(want):].view(np.uint8).any()
+        if len(want):
+            kinds_seen.add(int(t["kind"][i]))
+    assert kinds_seen == {0, 1, 2} and status2[5] == abi.ST_BAD_PARAM and status2[7] == abi.ST_BAD_PARAM
+    # capacity below the tick count: the head is written, the status says so
+    engine.set_max_samples(guard)
+    try:
+        rec, c3, s3 = engine.transitions_host(t[:50], 64, lim)
+        rec4, c4, s4 = engine.transitions_host(t[:40], cap, None)
+    finally:
+        engine.set_max_samples(abi.DEFAULT_MAX_SAMPLES)
+    for i in range(50):
+        want, st = oracle.transition(t[i:i + 1], traj=i, box=box, max_samples=guard)
+        m = min(64, len(want))
+        assert rec[i, :m].tobytes() == want[:m].tobytes()
+        assert bool(s3[i] & abi.ST_TRUNCATED) == (len(want) > 64)
+    # no box: nothing is saturated
+    for i in range(40):
+        want, st = oracle.transition(t[i:i + 1], traj=i, box=None, max_samples=guard)
+        assert rec4[i, :len(want)].tobytes() == want.tobytes() and (want["clamped"] == 0).all()
+
+
+@needs_nodes
+def test_transitions_reproduce_the_node_mission(engine, oracle):
+    """The whole mission of the unmodified node outside TRAJ_FOLLOWING, from the GPU: take-off, the trip to the start
+    of the trajectory, the trip home and the landing, bit for bit."""
+    from test_node_oracle import mission_transitions, params_for, oracle_samples, transition
+    ref_node = node_lib.Node(node_lib.NODE_REF_SO)
+    start_pose = (0.7, -1.1, 0.0, 0.4)
+    cfg = {"traj_type": "Figure8", "t_traj": 4.0, "z_min": 0.0}
+    s = oracle_samples(oracle, params_for("Figure8", cfg))
+    n = s.shape[1]
+    t_land = T_GO3 + n + 60
+    ev = [(T_GO1, node_lib.GO), (T_GO2, node_lib.GO), (T_GO3, node_lib.GO), (t_land, node_lib.LAND)]
+    rows = ref_node.run(cfg, ev, t_land + 6000, start=start_pose)
+    takeoff, goto, home, c = mission_transitions(rows, cfg, start_pose, s[:, 0], T_GO1, T_GO2, T_GO3, t_land)
+    lim = abi.make_limits(box=[c[k] for k in ("x_min", "x_max", "y_min", "y_max", "z_min", "z_max")])
+    batch = np.concatenate([takeoff, goto, home])
+    rec, counts, status = engine.transitions_host(batch, 4096, lim)
+    assert (status == 0).all()
+
+    def check(r, t0, what):
+        got = rows[(rows[:, 0] >= t0) & (rows[:, 0] < t0 + len(r))]
+        assert len(got) == len(r) and golden_util.same_bits(got[:, 1:15].T, abi.records_to_channels(r)), what
+        np.testing.assert_array_equal(got[:, 15], r["power"])
+
+    check(rec[0, :counts[0]], T_GO1, "take-off")
+    check(rec[1, :counts[1]], T_GO2, "go to start")
+    check(rec[2, :counts[2]], t_land, "go home")
+    last = rec[2, counts[2] - 1]
+    landing = transition(abi.TR_LANDING, 0.01, last["p"], last["v"][:2], last["psi"], [0, 0, start_pose[2]], 0.0,
+                         c["vel_land_fast"], c["vel_land_slow"])
+    rec2, counts2, status2 = engine.transitions_host(landing, 4096, lim)
+    check(rec2[0, :counts2[0]], t_land + counts[2], "landing")
+    assert rec2[0, counts2[0] - 1]["power"] == 0

@@ -170,3 +170,99 @@ def test_mission_phases_take_off_go_to_start_and_land(oracle):
     assert abs(step - 0.4 * 0.01) < 1e-12
     assert abs(rows[T_GO3 - 1, 1] - 3.4) < 1e-12 and abs(rows[T_GO3 - 1, 2]) < 1e-12   # arrived at traj_goals_[0]
     assert rows[-1, 15] == 0 and rows[-1, 3] <= 0.0                       # landed: motors off
+
+
+# ---- node-side transitions: orc_transition pinned to the unmodified node -------------------------
+
+def transition(kind, dt, start, start_v, start_psi, dest, dest_yaw, vel, vel_yaw, dist_thresh=0.0, yaw_thresh=0.0,
+               ticks=0):
+    t = np.zeros(1, dtype=abi.TRANSITION_DTYPE)
+    t["kind"], t["ticks"], t["dt"] = kind, ticks, dt
+    t["start"][0], t["start_v"][0], t["start_psi"] = start, start_v, start_psi
+    t["dest"][0], t["dest_yaw"], t["vel"], t["vel_yaw"] = dest, dest_yaw, vel, vel_yaw
+    t["dist_thresh"], t["yaw_thresh"] = dist_thresh, yaw_thresh
+    return t
+
+
+def mission_transitions(rows, cfg, start_pose, first_goal, t_go1, t_go2, t_go3, t_land):
+    """The four transition phases of a mission as tgx_transition_params, their start states read off the node's own
+    stream (the goal published on the tick before the phase begins), and the tick each phase starts on."""
+    c = dict(node_lib.DEFAULT_YAML)
+    c.update(cfg)
+    dt = 1.0 / c["pub_freq"]
+    row = lambda t: rows[rows[:, 0] == t][-1]
+    x0, y0, z0 = start_pose[:3]
+    psi0 = row(t_go1)[13]                      # quat2yaw(pose_.orientation) as the node computed it (:471)
+    takeoff = transition(abi.TR_TAKEOFF, dt, [x0, y0, z0], [0, 0], psi0, [0, 0, c["alt"]], 0.0, c["vel_take"], 0.0)
+    before = row(t_go2 - 1)
+    goto = transition(abi.TR_GOTO, dt, before[1:4], before[4:6], before[13], first_goal[0:3], first_goal[12],
+                      c["vel_initpos"], c["vel_yaw"], c["dist_thresh"], c["yaw_thresh"], ticks=t_go3 - t_go2)
+    before = row(t_land - 1)
+    home = transition(abi.TR_GOTO, dt, before[1:4], before[4:6], before[13], [x0, y0, c["alt"]], before[13],
+                      c["vel_initpos"], c["vel_yaw"], c["dist_thresh"], c["yaw_thresh"])
+    return takeoff, goto, home, c
+
+
+@pytest.mark.parametrize("traj_type,start_pose", [("Circle", (0.5, -0.5, 0.0, 0.3)), ("T", (-1.0, 2.0, 0.05, -2.0)),
+                                                  ("Line", (3.0, 3.0, 0.0, 3.0))])
+def test_transitions_match_the_node(oracle, traj_type, start_pose):
+    node = node_lib.Node(node_lib.NODE_REF_SO)
+    cfg = {"traj_type": traj_type, "t_traj": 4.0, "z_min": 0.0}
+    p = params_for(traj_type, cfg)
+    s = oracle_samples(oracle, p)
+    n = s.shape[1]
+    t_land = T_GO3 + n + 60
+    rows = node.run(cfg, MISSION + [(t_land, node_lib.LAND)], t_land + 6000, start=start_pose)
+    takeoff, goto, home, c = mission_transitions(rows, cfg, start_pose, s[:, 0], T_GO1, T_GO2, T_GO3, t_land)
+    box = [c[k] for k in ("x_min", "x_max", "y_min", "y_max", "z_min", "z_max")]
+
+    def check(rec, t0, what):
+        got = rows[(rows[:, 0] >= t0) & (rows[:, 0] < t0 + len(rec))]
+        assert len(got) == len(rec), what
+        assert golden_util.same_bits(got[:, 1:15].T, abi.records_to_channels(rec)), what
+        np.testing.assert_array_equal(got[:, 15], rec["power"], err_msg=what)
+
+    rec, st = oracle.transition(takeoff, box=box)
+    assert st == 0 and rec["last"][-1] == 1 and 560 < len(rec) < 620     # ~1.8 m at 0.3 m/s, 100 Hz
+    check(rec, T_GO1, "take-off")
+    assert rec["p"][-1, 2] == c["alt"]
+    rec, st = oracle.transition(goto, box=box)
+    assert st == 0 and len(rec) == T_GO3 - T_GO2
+    check(rec, T_GO2, "go to the start of the trajectory")
+    assert golden_util.same_bits(rec["p"][-1], s[0:3, 0]) and rec["psi"][-1] == s[12, 0]
+    rec, st = oracle.transition(home, box=box)
+    assert st == 0 and rec["last"][-1] == 1
+    check(rec, t_land, "go home")
+    t_landing = t_land + len(rec)
+    last = rec[-1]
+    landing = transition(abi.TR_LANDING, 1.0 / c["pub_freq"], last["p"], last["v"][:2], last["psi"],
+                         [0, 0, start_pose[2]], 0.0, c["vel_land_fast"], c["vel_land_slow"])
+    rec, st = oracle.transition(landing, box=box)
+    assert st == 0 and rec["power"][-1] == 0 and rec["power"][:-1].all()
+    check(rec, t_landing, "landing")
+    assert rec["p"][-1, 2] == 0.0 and (rec["clamped"][-1] & 4)            # z < 0 saturated at z_min = 0 (:602-604)
+    # fast above ground + 0.4 m, slow below (:590)
+    dz = -np.diff(rec["p"][:, 2])
+    assert abs(dz[5] - 0.35 * 0.01) < 1e-12 and abs(dz[-5] - 0.04 * 0.01) < 1e-12
+
+
+def test_transition_edge_cases(oracle):
+    dt = 0.01
+    # already at the destination: finished on the first tick, which still publishes the destination
+    t = transition(abi.TR_GOTO, dt, [1, 2, 1.8], [0, 0], 0.5, [1, 2, 1.8], 0.5, 0.4, 0.2, 0.3, 0.2)
+    rec, st = oracle.transition(t)
+    assert len(rec) == 1 and st == 0 and rec["last"][0] == 1
+    # yaw only, across the +-pi cut: turns the short way (wrap, :782-788)
+    t = transition(abi.TR_GOTO, dt, [0, 0, 1.8], [0, 0], 3.0, [0, 0, 1.8], -3.0, 0.4, 0.2, 0.3, 0.2)
+    rec, st = oracle.transition(t)
+    assert (rec["dpsi"][:-2] == 0.2).all() and rec["psi"][5] > 3.0 and rec["psi"][-1] == -3.0
+    # rejected parameters, and a phase that cannot end
+    bad = transition(abi.TR_TAKEOFF, 0.0, [0, 0, 0], [0, 0], 0, [0, 0, 1.8], 0, 0.3, 0)
+    assert oracle.transition(bad) [1] == abi.ST_BAD_PARAM
+    far = transition(abi.TR_GOTO, dt, [0, 0, 1.8], [0, 0], 0, [1e9, 0, 1.8], 0, 0.4, 0.2, 0.3, 0.2)
+    rec, st = oracle.transition(far, max_samples=5000)
+    assert st == abi.ST_TOO_LONG and len(rec) == 5000
+    # a box that the way home crosses: the saturated position feeds back into the recurrence
+    t = transition(abi.TR_GOTO, dt, [0, 0, 1.8], [0, 0], 0, [3, 3, 1.8], 0, 0.4, 0.2, 0.3, 0.2, ticks=1500)
+    rec, st = oracle.transition(t, box=[-5, 2, -5, 5, 0, 5])
+    assert rec["p"][:, 0].max() == 2.0 and (rec["clamped"] & 1).any() and rec["p"][-1, 1] > 2.9

@@ -128,6 +128,24 @@ class GoalRecord(C.Structure):
                 ("last", C.c_uint8), ("reserved", C.c_uint8 * 3)]
 
 
+class TransitionParams(C.Structure):
+    """struct tgx_transition_params (128 bytes)."""
+    _fields_ = [("kind", C.c_int32), ("ticks", C.c_int32), ("dt", C.c_double), ("start", C.c_double * 3),
+                ("start_v", C.c_double * 2), ("start_psi", C.c_double), ("dest", C.c_double * 3),
+                ("dest_yaw", C.c_double), ("vel", C.c_double), ("vel_yaw", C.c_double),
+                ("dist_thresh", C.c_double), ("yaw_thresh", C.c_double)]
+
+
+TR_TAKEOFF, TR_GOTO, TR_LANDING = 0, 1, 2
+assert C.sizeof(TransitionParams) == 128, C.sizeof(TransitionParams)
+TRANSITION_DTYPE = np.dtype({
+    "names": ["kind", "ticks", "dt", "start", "start_v", "start_psi", "dest", "dest_yaw", "vel", "vel_yaw",
+              "dist_thresh", "yaw_thresh"],
+    "formats": ["<i4", "<i4", "<f8", ("<f8", (3,)), ("<f8", (2,)), "<f8", ("<f8", (3,)), "<f8", "<f8", "<f8",
+                "<f8", "<f8"],
+    "offsets": [0, 4, 8, 16, 40, 56, 64, 88, 96, 104, 112, 120],
+    "itemsize": 128,
+})
 assert C.sizeof(GoalRecord) == 128, C.sizeof(GoalRecord)
 assert C.sizeof(PolylineLegs) == 64, C.sizeof(PolylineLegs)
 assert C.sizeof(Params) == 128, C.sizeof(Params)

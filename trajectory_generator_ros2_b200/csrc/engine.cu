@@ -62,6 +62,9 @@ cudaError_t launch_poly_tiles(int64_t n, const int32_t* ntile, const int64_t* ti
 cudaError_t launch_pack_goals(const OutView& in, const int32_t* counts, int64_t n, const tgx_limits* lim,
                               tgx_goal_record* records, int64_t rec_stride, const int64_t* rec_offset,
                               int64_t rec_capacity, cudaStream_t stream);
+cudaError_t launch_transitions(const tgx_transition_params* tparams, int64_t n, const tgx_limits* lim,
+                               int64_t max_samples, tgx_goal_record* records, int64_t rec_stride,
+                               int64_t rec_capacity, int32_t* counts, uint32_t* status, cudaStream_t stream);
 cudaError_t launch_eval_poly(const PolyView& pv, int64_t ntiles, int tile_shift, int spt, const OutView& out,
                              bool store, double* max_v, double* max_a, cudaStream_t stream);
 
@@ -813,6 +816,49 @@ int tgx_pack_goals(tgx_engine* e, const tgx_layout* planes, const int32_t* d_cou
     TGX_CUDA(tgx::launch_pack_goals(make_view(planes), d_counts, n, limits, d_records, rec_stride, d_rec_offset,
                                     rec_capacity, static_cast<cudaStream_t>(stream)));
     e->launches += 1;
+    return TGX_OK;
+}
+
+int tgx_transitions(tgx_engine* e, const tgx_transition_params* d_tparams, int64_t n, const tgx_limits* limits,
+                    tgx_goal_record* d_records, int64_t rec_stride, int64_t rec_capacity, int32_t* d_counts,
+                    uint32_t* d_status, void* stream) {
+    if (!e || n < 0 || rec_capacity < 0 || (n > 0 && !d_tparams)) return TGX_ERR_INVALID;
+    if (n == 0) return TGX_OK;
+    if (d_records && (reinterpret_cast<uintptr_t>(d_records) & 31u) != 0) return TGX_ERR_ALIGNMENT;
+    TGX_CUDA(cudaSetDevice(e->device));
+    TGX_CUDA(tgx::launch_transitions(d_tparams, n, limits, e->max_samples, d_records, rec_stride, rec_capacity,
+                                     d_counts, d_status, static_cast<cudaStream_t>(stream)));
+    e->launches += 1;
+    return TGX_OK;
+}
+
+static int host_streams(tgx_engine* e);
+
+int tgx_transitions_host(tgx_engine* e, const tgx_transition_params* h_tparams, int64_t n, const tgx_limits* limits,
+                         tgx_goal_record* h_records, int64_t rec_capacity, int32_t* h_counts, uint32_t* h_status) {
+    if (!e || n < 0 || rec_capacity < 0 || (n > 0 && !h_tparams)) return TGX_ERR_INVALID;
+    if (n == 0) return TGX_OK;
+    TGX_CUDA(cudaSetDevice(e->device));
+    int rc = host_streams(e);
+    if (rc) return rc;
+    cudaStream_t s = e->hs[0];
+    const bool want_rec = h_records && rec_capacity > 0;
+    if ((rc = e->h_params[0].reserve((size_t)n * sizeof(tgx_transition_params)))) return rc;
+    if ((rc = e->h_cnt[0].reserve((size_t)n * sizeof(int32_t)))) return rc;
+    if ((rc = e->h_st[0].reserve((size_t)n * sizeof(uint32_t)))) return rc;
+    if (want_rec && (rc = e->h_rec[0].reserve((size_t)(n * rec_capacity) * sizeof(tgx_goal_record)))) return rc;
+    TGX_CUDA(cudaMemcpyAsync(e->h_params[0].p, h_tparams, (size_t)n * sizeof(tgx_transition_params),
+                             cudaMemcpyHostToDevice, s));
+    rc = tgx_transitions(e, e->h_params[0].as<tgx_transition_params>(), n, limits,
+                         want_rec ? e->h_rec[0].as<tgx_goal_record>() : nullptr, rec_capacity,
+                         want_rec ? rec_capacity : 0, e->h_cnt[0].as<int32_t>(), e->h_st[0].as<uint32_t>(), s);
+    if (rc) return rc;
+    if (want_rec)
+        TGX_CUDA(cudaMemcpyAsync(h_records, e->h_rec[0].p, (size_t)(n * rec_capacity) * sizeof(tgx_goal_record),
+                                 cudaMemcpyDeviceToHost, s));
+    if (h_counts) TGX_CUDA(cudaMemcpyAsync(h_counts, e->h_cnt[0].p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (h_status) TGX_CUDA(cudaMemcpyAsync(h_status, e->h_st[0].p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    TGX_CUDA(cudaStreamSynchronize(s));
     return TGX_OK;
 }
 

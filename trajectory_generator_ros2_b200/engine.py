@@ -64,6 +64,8 @@ def _load() -> C.CDLL:
     lib.tgx_generate_host_legs.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp]
     lib.tgx_pack_goals.argtypes = [vp, C.POINTER(abi.Layout), vp, i64, vp, vp, i64, vp, i64, vp]
     lib.tgx_generate_records_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp]
+    lib.tgx_transitions.argtypes = [vp, vp, i64, vp, vp, i64, i64, vp, vp, vp]
+    lib.tgx_transitions_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp]
     lib.tgx_eval.argtypes = [vp, C.POINTER(abi.Layout), vp, vp, vp]
     lib.tgx_feasibility.argtypes = [vp, C.POINTER(abi.Limits), vp, vp, vp, vp, vp]
     lib.tgx_count_host.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -363,6 +365,34 @@ class Engine:
         self._check(self._lib.tgx_generate_records_host(self._h, params.ctypes.data, n, _limits_ptr(limits),
                                                         records.ctypes.data, rec_capacity, counts.ctypes.data,
                                                         status.ctypes.data), "tgx_generate_records_host")
+        return records, counts, status
+
+    def transitions(self, d_tparams, rec_capacity: int, limits: Optional[abi.Limits] = None, records=None):
+        """tgx_transitions on a device-resident uint8 [n, 128] tensor of tgx_transition_params ->
+        (records uint8 [n, rec_capacity, 128] or None, counts int32 [n], status int32 [n])."""
+        import torch
+        n = int(d_tparams.shape[0])
+        if records is None and rec_capacity > 0:
+            records = torch.zeros((n, rec_capacity, 128), dtype=torch.uint8, device=d_tparams.device)
+        counts = torch.empty(n, dtype=torch.int32, device=d_tparams.device)
+        status = torch.empty(n, dtype=torch.int32, device=d_tparams.device)
+        self._check(self._lib.tgx_transitions(self._h, d_tparams.data_ptr(), n, _limits_ptr(limits),
+                                              records.data_ptr() if records is not None else None, rec_capacity,
+                                              rec_capacity, counts.data_ptr(), status.data_ptr(), self._stream()),
+                    "tgx_transitions")
+        return records, counts, status
+
+    def transitions_host(self, tparams: np.ndarray, rec_capacity: int, limits: Optional[abi.Limits] = None):
+        """tgx_transitions_host -> (records [n, rec_capacity] of RECORD_DTYPE, counts, status)."""
+        tparams = np.ascontiguousarray(tparams)
+        assert tparams.dtype == abi.TRANSITION_DTYPE
+        n = len(tparams)
+        records = np.zeros((n, max(rec_capacity, 0)), dtype=abi.RECORD_DTYPE)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.tgx_transitions_host(self._h, tparams.ctypes.data, n, _limits_ptr(limits),
+                                                   records.ctypes.data if rec_capacity > 0 else None, rec_capacity,
+                                                   counts.ctypes.data, status.ctypes.data), "tgx_transitions_host")
         return records, counts, status
 
     def feasibility(self, limits: abi.Limits, n: int, flags=None, max_v=None, max_a=None, status=None):

@@ -221,3 +221,28 @@ def _fill_letters_T(rng, m):
 def letters_T(n: int, seed: int = 1239, lo: int = 0, hi: int | None = None) -> np.ndarray:
     hi = n if hi is None else hi
     return _draw(seed, lo, hi, _fill_letters_T)
+
+
+# ---- node-side transitions ------------------------------------------------------------------------
+
+def fleet_transitions(n: int, seed: int = 1240) -> np.ndarray:
+    """A fleet's worth of tgx_transition_params: per vehicle one of take-off (ground -> alt at vel_take), the trip to the
+    start of its trajectory (simpleInterpolation at vel_initpos, default.yaml:56-63 speeds and thresholds) or landing
+    from the hover altitude; a few hundred to a few thousand 100 Hz ticks each."""
+    rng = np.random.default_rng(seed)
+    t = np.zeros(n, dtype=abi.TRANSITION_DTYPE)
+    kind = rng.integers(0, 3, n)
+    t["kind"] = kind
+    t["dt"] = DT
+    alt = rng.uniform(1.0, 2.5, n)
+    t["start"][:, :2] = rng.uniform(-4.0, 4.0, (n, 2))
+    t["start"][:, 2] = np.where(kind == abi.TR_TAKEOFF, 0.0, alt)
+    t["start_psi"] = rng.uniform(-3.1, 3.1, n)
+    t["dest"][:, :2] = rng.uniform(-4.0, 4.0, (n, 2))
+    t["dest"][:, 2] = np.where(kind == abi.TR_LANDING, 0.0, alt)
+    t["dest_yaw"] = rng.uniform(-3.1, 3.1, n)
+    t["vel"] = np.where(kind == abi.TR_TAKEOFF, 0.3, np.where(kind == abi.TR_GOTO, 0.4, 0.35))
+    t["vel_yaw"] = np.where(kind == abi.TR_LANDING, 0.04, 0.2)
+    t["dist_thresh"] = 0.3
+    t["yaw_thresh"] = 0.2
+    return t
