@@ -352,8 +352,10 @@ def run_ours(args):
     e2e = None
     if not feas_only and not args.no_e2e and not args.records:
         eng.set_host_fill(not args.e2e_all_planes)
+        eng.set_host_layout(not args.e2e_traj_major)
         call_n = min(n, args.e2e_call)                       # trajectories per tgx_generate_host call
-        pin_out = PinnedArray((call_n, abi.TGX_NCHAN, row))
+        hrow = (max_count + 3) // 4 * 4                      # host rows: the caller's capacity, no padding shipped
+        pin_out = PinnedArray((call_n, abi.TGX_NCHAN, hrow) if args.e2e_traj_major else (abi.TGX_NCHAN, call_n, hrow))
         pin_params = PinnedArray((call_n,), dtype=abi.PARAMS_DTYPE)
         h_counts_total = 0
 
@@ -362,7 +364,8 @@ def run_ours(args):
             for s in range(0, n, call_n):
                 m = min(call_n, n - s)
                 pin_params.array[:m] = params[s:s + m]
-                _, c, _, _ = eng.generate_host(pin_params.array[:m], row, out=pin_out.array[:m])
+                dst = pin_out.array[:m] if args.e2e_traj_major else pin_out.array.reshape(-1)[:abi.TGX_NCHAN * m * hrow].reshape(abi.TGX_NCHAN, m, hrow)
+                _, c, _, _ = eng.generate_host(pin_params.array[:m], hrow, out=dst)
                 tot += int(c.sum())
             return tot
 
@@ -384,12 +387,15 @@ def run_ours(args):
         has_bounce = bool((params["type"] == abi.TGX_BOUNCE).any())     # Bounce moves along z: nothing is constant
         planes = 14 if (args.e2e_all_planes or has_bounce) else 10
         e2e = {"value": job_samples / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * (planes * row * 8 + 8)),
+               "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * (planes * hrow * 8 + 8)), "host_row_capacity": hrow,
                "wire_format": ("all 14 planes over PCIe" if planes == 14 else
                                "10 varying planes over PCIe; the 4 constant planes (p.z = alt, v.z = a.z = j.z = 0) "
                                "are written into the host buffer by host threads"),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
-               "call": f"tgx_generate_host, {call_n} trajectories per call into one reused pinned host buffer"}
+               "call": f"tgx_generate_host, {call_n} trajectories per call into one reused pinned host buffer, "
+                       + ("trajectory-major [n][14][row]" if args.e2e_traj_major else
+                          "plane-major [14][n][row] (tgx_set_host_layout): contiguous 1-D copies per plane")}
+        eng.set_host_layout(False)
         pin_out.free()
         pin_params.free()
     elif feas_only and not args.no_e2e:
@@ -566,6 +572,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-call", type=int, default=1 << 16)
     ap.add_argument("--e2e-all-planes", action="store_true", help="ship all 14 planes over PCIe in the e2e leg")
+    ap.add_argument("--e2e-traj-major", action="store_true",
+                    help="e2e leg with the trajectory-major host layout [n][14][row] (2-D copies) instead of plane-major")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--records", action="store_true",
                     help="also run the consumer-side kernel: clamp + pack every sample into a 128-byte record")

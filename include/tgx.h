@@ -445,6 +445,14 @@ int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const do
  * buffer holds the same values either way. */
 int tgx_set_host_fill(tgx_engine* e, int fill_constants_on_host);
 
+/* Layout of the host buffers of tgx_generate_host / tgx_generate_host_legs / tgx_stop_host.
+ *   plane_major = 0 (default): h_out[(i*14 + c)*capacity + k]   — one trajectory's 14 rows together (what the drop-in
+ *       classes repack into std::vector<Goal>);
+ *   plane_major = 1:           h_out[(c*n + i)*capacity + k]    — struct-of-arrays across the whole call: every plane of
+ *       a chunk is one contiguous run on both sides of PCIe, so the device->host copies run at the link's plain-copy
+ *       rate instead of the rate of 2-D copies with 16 KB runs (measured 52 vs 46 GB/s). */
+int tgx_set_host_layout(tgx_engine* e, int plane_major);
+
 /* One create*Goal call for host-resident arguments (see tgx_plan_samples); h_out14 receives the 14 channels. */
 int tgx_sample_host(tgx_engine* e, const tgx_params* h_params, double v, double accel, double s0, double s1,
                     double* h_out14);

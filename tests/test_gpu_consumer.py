@@ -302,3 +302,25 @@ def test_transitions_reproduce_the_node_mission(engine, oracle):
     rec2, counts2, status2 = engine.transitions_host(landing, 4096, lim)
     check(rec2[0, :counts2[0]], t_land + counts[2], "landing")
     assert rec2[0, counts2[0] - 1]["power"] == 0
+
+
+def test_plane_major_host_layout(engine, oracle):
+    """tgx_set_host_layout(1): the host buffer is [14][n][capacity]; same values as the default layout, with and
+    without the host-side fill of the constant planes, across chunk boundaries."""
+    params = abi.concat([workloads.circles_cfg2(700), workloads.mixed_cfg3(300)])
+    cap = 1536
+    ref_out, ref_counts, ref_status, _ = engine.generate_host(params, cap)
+    try:
+        for fill in (True, False):
+            engine.set_host_fill(fill)
+            engine.set_host_layout(True)
+            out, counts, status, _ = engine.generate_host(params, cap)
+            assert out.shape == (abi.TGX_NCHAN, len(params), cap)
+            np.testing.assert_array_equal(counts, ref_counts)
+            np.testing.assert_array_equal(status, ref_status)
+            for i in range(0, len(params), 37):
+                m = counts[i]
+                assert np.array_equal(out[:, i, :m], ref_out[i, :, :m]), (fill, i)
+    finally:
+        engine.set_host_fill(True)
+        engine.set_host_layout(False)

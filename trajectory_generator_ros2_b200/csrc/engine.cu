@@ -169,6 +169,7 @@ struct tgx_engine {
     int64_t max_samples = (int64_t)1 << 24;
     int tile_shift = 10;   // 1024 samples per tile
     bool host_fill_constants = true;   // host-buffer calls: ship 10 planes over PCIe, memset the 4 constant ones
+    bool host_plane_major = false;     // host-buffer calls: h_out is [14][n][capacity] instead of [n][14][capacity]
     bool exact_ramps = false;   // plan mode: replay ramps step by step (bit-identical state) or in exact-v jumps
     int spt = 4;           // samples per thread: 2 -> 128-bit stores, 4 -> 256-bit stores (measured best on B200)
     int64_t launches = 0;
@@ -636,6 +637,13 @@ int tgx_set_host_fill(tgx_engine* e, int fill_constants_on_host) {
 
 // Single-replay planning with per-trajectory slices sized from the previous plan (default on).  allow = 0 forces the
 // two-replay exact-offset path for every plan.
+// Host-buffer calls: 0 (default) = h_out[(i*14 + c)*capacity + k]; 1 = plane-major h_out[(c*n + i)*capacity + k].
+int tgx_set_host_layout(tgx_engine* e, int plane_major) {
+    if (!e) return TGX_ERR_INVALID;
+    e->host_plane_major = plane_major != 0;
+    return TGX_OK;
+}
+
 int tgx_set_slab_planning(tgx_engine* e, int allow) {
     if (!e) return TGX_ERR_INVALID;
     e->allow_slabs = allow != 0;
@@ -1010,6 +1018,10 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
     // Line.cpp:99-108, Figure8.cpp:110-119).  They are not worth 29 % of the PCIe traffic: the device evaluates and
     // ships the 10 varying planes, and host threads write the 4 constant rows of every trajectory meanwhile.
     const bool fill = e->host_fill_constants && capacity > 0 && !whole.bounce && !h_records;
+    // Plane-major host buffers ([14][n][capacity]): every plane of a chunk is ONE contiguous run on both sides of the
+    // bus, so the D2H copies are plain 1-D copies (52+ GB/s on a Gen5 x16 link) instead of 2-D copies of 16 KB runs
+    // (46 GB/s).  The device staging buffer uses the same layout per chunk.
+    const bool plane_major = e->host_plane_major && !h_records;
     std::vector<std::thread> fillers;
     if (fill) {
         unsigned hw = std::thread::hardware_concurrency();
@@ -1018,13 +1030,16 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
             const int64_t a = n * t / nthreads, z = n * (t + 1) / nthreads;
             fillers.emplace_back([=] {
                 for (int64_t i = a; i < z; ++i) {
-                    double* row = h_out + i * TGX_NCHAN * capacity;
+                    // element (i, c, k) of the host buffer
+                    const int64_t ts = plane_major ? capacity : TGX_NCHAN * capacity;
+                    const int64_t cs = plane_major ? n * capacity : capacity;
+                    double* row = h_out + i * ts;
                     const double alt = h_params[i].alt;
-                    double* pz = row + (int64_t)TGX_PZ * capacity;
+                    double* pz = row + (int64_t)TGX_PZ * cs;
                     for (int64_t k = 0; k < capacity; ++k) pz[k] = alt;
-                    std::memset(row + (int64_t)TGX_VZ * capacity, 0, (size_t)capacity * sizeof(double));
-                    std::memset(row + (int64_t)TGX_AZ * capacity, 0, (size_t)capacity * sizeof(double));
-                    std::memset(row + (int64_t)TGX_JZ * capacity, 0, (size_t)capacity * sizeof(double));
+                    std::memset(row + (int64_t)TGX_VZ * cs, 0, (size_t)capacity * sizeof(double));
+                    std::memset(row + (int64_t)TGX_AZ * cs, 0, (size_t)capacity * sizeof(double));
+                    std::memset(row + (int64_t)TGX_JZ * cs, 0, (size_t)capacity * sizeof(double));
                 }
             });
         }
@@ -1055,8 +1070,8 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         if (d_legs) TGX_CUDA(cudaMemsetAsync(d_legs, 0, (size_t)m * sizeof(tgx_polyline_legs), s));
         tgx_layout lay{};
         lay.d_base = e->h_out[b].as<double>();
-        lay.traj_stride = TGX_NCHAN * capacity;
-        lay.chan_stride = capacity;
+        lay.traj_stride = plane_major ? capacity : TGX_NCHAN * capacity;
+        lay.chan_stride = plane_major ? m * capacity : capacity;
         lay.capacity = capacity;
         lay.channel_mask = fill ? kVaryingChannels : 0;
         // planning synchronises stream s once; the other slot's D2H copies keep running meanwhile.  Braking plans take
@@ -1089,6 +1104,14 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
             TGX_CUDA(cudaEventRecord(e->hev_eval, s));
             TGX_CUDA(cudaMemcpyAsync(h_records + lo * capacity, e->h_rec[b].p,
                                      (size_t)(m * capacity) * sizeof(tgx_goal_record), cudaMemcpyDeviceToHost, s));
+        } else if (capacity > 0 && plane_major) {
+            TGX_CUDA(cudaEventRecord(e->hev_eval, s));
+            for (int c = 0; c < TGX_NCHAN; ++c) {
+                if (fill && !(kVaryingChannels & (1u << c))) continue;
+                TGX_CUDA(cudaMemcpyAsync(h_out + ((int64_t)c * n + lo) * capacity,
+                                         e->h_out[b].as<double>() + (int64_t)c * m * capacity,
+                                         (size_t)(m * capacity) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            }
         } else if (capacity > 0) {
             TGX_CUDA(cudaEventRecord(e->hev_eval, s));
             if (fill) {

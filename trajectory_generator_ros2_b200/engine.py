@@ -43,6 +43,7 @@ def _load() -> C.CDLL:
     lib.tgx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     lib.tgx_set_plan_mode.argtypes = [vp, C.c_int]
     lib.tgx_set_host_fill.argtypes = [vp, C.c_int]
+    lib.tgx_set_host_layout.argtypes = [vp, C.c_int]
     lib.tgx_set_phase_planning.argtypes = [vp, C.c_int]
     lib.tgx_phase_plan_count.restype = i64
     lib.tgx_phase_plan_count.argtypes = [vp]
@@ -195,6 +196,11 @@ class Engine:
 
     def set_host_fill(self, fill_constants_on_host: bool):
         self._check(self._lib.tgx_set_host_fill(self._h, 1 if fill_constants_on_host else 0), "tgx_set_host_fill")
+
+    def set_host_layout(self, plane_major: bool):
+        """Host buffers of generate_host / stop_host: [n, 14, cap] (default) or plane-major [14, n, cap]."""
+        self._check(self._lib.tgx_set_host_layout(self._h, 1 if plane_major else 0), "tgx_set_host_layout")
+        self._host_plane_major = bool(plane_major)
 
     def set_phase_planning(self, allow: bool):
         self._check(self._lib.tgx_set_phase_planning(self._h, 1 if allow else 0), "tgx_set_phase_planning")
@@ -445,9 +451,10 @@ class Engine:
         """tgx_generate_host -> (out [n, 14, capacity], counts, status, phases or None)."""
         params = np.ascontiguousarray(params)
         n = len(params)
+        shape = (abi.TGX_NCHAN, n, capacity) if getattr(self, "_host_plane_major", False) else (n, abi.TGX_NCHAN, capacity)
         if out is None:
-            out = np.full((n, abi.TGX_NCHAN, capacity), np.nan)
-        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (n, abi.TGX_NCHAN, capacity)
+            out = np.full(shape, np.nan)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == shape
         counts = np.zeros(n, dtype=np.int32)
         status = np.zeros(n, dtype=np.uint32)
         phases = np.zeros(n, dtype=abi.PHASES_DTYPE) if want_phases else None
