@@ -380,6 +380,13 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
  * record (i, k) to d_records[(d_rec_offset ? d_rec_offset[i] : i * rec_stride) + k] for k < min(d_counts[i],
  * rec_capacity).  One CTA per 256 samples: coalesced plane reads, a swizzled shared-memory transpose, 512-byte
  * coalesced record writes.  Does not need (or touch) the current plan. */
+/* The fused form: evaluate the current plan (either family, braking plans too) straight into clamped records,
+ * d_records[(d_rec_offset ? d_rec_offset[i] : i * rec_stride) + k], k < rec_capacity — the evaluation kernels stage
+ * each 64-byte record half through shared memory and every warp streams its own records, so a sample costs 128 bytes
+ * of HBM traffic instead of the 112 + 112 + 128 of tgx_eval followed by tgx_pack_goals.  Bit-identical to that pair. */
+int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
+                     const int64_t* d_rec_offset, int64_t rec_capacity, void* stream);
+
 int tgx_pack_goals(tgx_engine* e, const tgx_layout* planes, const int32_t* d_counts, int64_t n,
                    const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
                    const int64_t* d_rec_offset, int64_t rec_capacity, void* stream);

@@ -324,3 +324,64 @@ def test_plane_major_host_layout(engine, oracle):
     finally:
         engine.set_host_fill(True)
         engine.set_host_layout(False)
+
+
+@pytest.mark.parametrize("tuning", [(10, 4), (9, 4), (9, 2)])
+def test_eval_records_equals_eval_then_pack(engine, oracle, tuning):
+    """The fused kernel (records straight from the evaluation kernels through the swizzled shared-memory transpose) is
+    byte-identical to tgx_eval followed by tgx_pack_goals, for both families, braking plans, packed offsets and a record
+    capacity below the sample count, in every kernel shape."""
+    import torch
+    engine.set_tuning(*tuning)
+    try:
+        lim = abi.make_limits(box=BOX)
+        batches = {
+            "classic": (abi.concat([workloads.mixed_cfg3(90, seed=9), workloads.default_circle()]), engine.plan),
+            "polyline": (engine.finalize_polyline(abi.concat([workloads.polyline_mix(90, seed=10),
+                                                               workloads.default_polyline(abi.TGX_I)]).copy()),
+                         engine.plan_polyline),
+        }
+        for name, (params, planner) in batches.items():
+            d = engine.upload_params(params)
+            plan = planner(d)
+            counts = plan.counts
+            n = len(params)
+            cap = int((int(counts.max()) + 3) // 4 * 4)
+            planes = torch.full((n, abi.TGX_NCHAN, cap), float("nan"), dtype=torch.float64, device=d.device)
+            engine.eval(planes)
+            want = engine.pack_goals(planes, counts, lim)
+            got = engine.eval_records(n, cap, lim)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), (name, tuning)
+            # no box, smaller capacity
+            want = engine.pack_goals(planes, counts, None, rec_capacity=700)
+            got = engine.eval_records(n, 700, None)
+            # the truncated trajectory's `last` flag: pack sees the full count too, so both agree
+            assert torch.equal(got, want), (name, tuning, "cap 700")
+            # densely packed rows
+            c = counts.cpu().numpy()
+            offs = torch.from_numpy(np.concatenate([[0], np.cumsum(c[:-1], dtype=np.int64)])).to(d.device)
+            flat_w = torch.zeros((int(c.sum()), 128), dtype=torch.uint8, device=d.device)
+            flat_g = torch.zeros_like(flat_w)
+            engine.pack_goals(planes, counts, lim, records=flat_w, rec_capacity=cap, rec_offset=offs)
+            engine.eval_records(n, cap, lim, records=flat_g, rec_offset=offs)
+            torch.cuda.synchronize()
+            assert torch.equal(flat_g, flat_w), (name, tuning, "packed")
+        # braking plans (segment tables incl. the frozen-position records of the polyline family)
+        params = abi.concat([workloads.mixed_cfg3(40, seed=12), batches["polyline"][0][:40]])
+        froms = np.zeros((len(params), abi.TGX_NCHAN))
+        for i in range(len(params)):
+            p = params[i:i + 1]
+            smp = oracle.polyline_generate(p)[0] if abi.is_polyline(int(p["type"][0])) else oracle.generate(p)[0]
+            froms[i] = smp[:, smp.shape[1] // 2]
+        d = engine.upload_params(params)
+        plan = engine.plan_stop(d, torch.from_numpy(froms).to(d.device))
+        cap = max(4, int((int(plan.counts.max()) + 3) // 4 * 4))
+        planes = torch.full((len(params), abi.TGX_NCHAN, cap), float("nan"), dtype=torch.float64, device=d.device)
+        engine.eval(planes)
+        want = engine.pack_goals(planes, plan.counts, lim)
+        got = engine.eval_records(len(params), cap, lim)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), ("stop", tuning)
+    finally:
+        engine.set_tuning(10, 4)

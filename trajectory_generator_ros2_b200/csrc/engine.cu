@@ -65,6 +65,10 @@ cudaError_t launch_pack_goals(const OutView& in, const int32_t* counts, int64_t 
 cudaError_t launch_transitions(const tgx_transition_params* tparams, int64_t n, const tgx_limits* lim,
                                int64_t max_samples, tgx_goal_record* records, int64_t rec_stride,
                                int64_t rec_capacity, int32_t* counts, uint32_t* status, cudaStream_t stream);
+cudaError_t launch_eval_records(const TableView& tv, int64_t ntiles, int tile_shift, int spt, const RecOut& ro,
+                                cudaStream_t stream);
+cudaError_t launch_eval_poly_records(const PolyView& pv, int64_t ntiles, int tile_shift, int spt, const RecOut& ro,
+                                     cudaStream_t stream);
 cudaError_t launch_eval_poly(const PolyView& pv, int64_t ntiles, int tile_shift, int spt, const OutView& out,
                              bool store, double* max_v, double* max_a, cudaStream_t stream);
 
@@ -813,6 +817,30 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
     return TGX_OK;
 }
 
+int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
+                     const int64_t* d_rec_offset, int64_t rec_capacity, void* stream) {
+    if (!e || !d_records || rec_capacity < 0) return TGX_ERR_INVALID;
+    if (!e->has_plan) return TGX_ERR_NO_PLAN;
+    if ((reinterpret_cast<uintptr_t>(d_records) & 15u) != 0) return TGX_ERR_ALIGNMENT;
+    TGX_CUDA(cudaSetDevice(e->device));
+    if (e->plan_n == 0 || e->plan_tiles == 0 || rec_capacity == 0) return TGX_OK;
+    tgx::RecOut ro{};
+    ro.base = d_records;
+    ro.stride = rec_stride;
+    ro.offset = d_rec_offset;
+    ro.capacity = rec_capacity;
+    ro.clamp = (limits && limits->check_box) ? 1 : 0;
+    if (ro.clamp)
+        for (int i = 0; i < 6; ++i) ro.box[i] = limits->box[i];
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (e->plan_poly)
+        TGX_CUDA(tgx::launch_eval_poly_records(poly_view(e), e->plan_tiles, e->tile_shift, e->spt, ro, s));
+    else
+        TGX_CUDA(tgx::launch_eval_records(table_view(e), e->plan_tiles, e->tile_shift, e->spt, ro, s));
+    e->launches += 1;
+    return TGX_OK;
+}
+
 int tgx_pack_goals(tgx_engine* e, const tgx_layout* planes, const int32_t* d_counts, int64_t n,
                    const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
                    const int64_t* d_rec_offset, int64_t rec_capacity, void* stream) {
@@ -978,6 +1006,14 @@ int tgx_count_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const t
 // Channels that vary along a trajectory (everything but p.z, v.z, a.z, j.z).
 constexpr uint32_t kVaryingChannels = 0x3fffu & ~((1u << TGX_PZ) | (1u << TGX_VZ) | (1u << TGX_AZ) | (1u << TGX_JZ));
 
+// One chunk of a host-buffer call: struct-of-arrays planes into the staging buffer, or (records != nullptr) clamped
+// records straight from the evaluation kernel.
+static int eval_chunk(tgx_engine* e, const tgx_layout* lay, const tgx_limits* limits, tgx_goal_record* records,
+                      int64_t capacity, cudaStream_t s) {
+    if (records) return tgx_eval_records(e, limits, records, capacity, nullptr, capacity, s);
+    return tgx_eval(e, lay, nullptr, nullptr, s);
+}
+
 // Shared body of tgx_generate_host / tgx_stop_host.
 static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_from, int64_t n,
                     const tgx_limits* limits, double* h_out, int64_t capacity, int32_t* h_counts,
@@ -1087,20 +1123,20 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
                 rc = tgx_plan(e, e->h_params[b].as<tgx_params>(), m, limits, e->h_cnt[b].as<int32_t>(),
                               e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
             if (rc) return rc;
-            if (capacity > 0 && (rc = tgx_eval(e, &lay, nullptr, nullptr, s))) return rc;
+            if (capacity > 0 && (rc = eval_chunk(e, &lay, limits, h_records ? e->h_rec[b].as<tgx_goal_record>() : nullptr,
+                                                 capacity, s)))
+                return rc;
         }
         if (pass_poly) {
             if (d_ph && !pass_classic) TGX_CUDA(cudaMemsetAsync(d_ph, 0, (size_t)m * sizeof(tgx_phases), s));
             rc = plan_polyline_common(e, e->h_params[b].as<tgx_params>(), m, limits, e->h_cnt[b].as<int32_t>(),
                                       e->h_st[b].as<uint32_t>(), d_legs, nullptr, pass_classic, s);
             if (rc) return rc;
-            if (capacity > 0 && (rc = tgx_eval(e, &lay, nullptr, nullptr, s))) return rc;
+            if (capacity > 0 && (rc = eval_chunk(e, &lay, limits, h_records ? e->h_rec[b].as<tgx_goal_record>() : nullptr,
+                                                 capacity, s)))
+                return rc;
         }
         if (capacity > 0 && h_records) {
-            TGX_CUDA(tgx::launch_pack_goals(make_view(&lay), e->h_cnt[b].as<int32_t>(), m,
-                                            (limits && limits->check_box) ? limits : nullptr,
-                                            e->h_rec[b].as<tgx_goal_record>(), capacity, nullptr, capacity, s));
-            e->launches += 1;
             TGX_CUDA(cudaEventRecord(e->hev_eval, s));
             TGX_CUDA(cudaMemcpyAsync(h_records + lo * capacity, e->h_rec[b].p,
                                      (size_t)(m * capacity) * sizeof(tgx_goal_record), cudaMemcpyDeviceToHost, s));

@@ -91,10 +91,14 @@ __device__ void build_phase_segment(const tgx_params& par, const PhaseRec& phr, 
 }
 
 // MODE 0: exact-offset plan, 1: slab plan (fixed per-trajectory slices), 2: phase plan (see TableView).
-template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE>
+// RECORDS: instead of struct-of-arrays planes the kernel writes one clamped 128-byte tgx_goal_record per sample (the
+// consumer side of SURVEY.md §8 f3 fused into the evaluation: 128 B written per sample instead of 112 + 112 + 128),
+// staged through dynamic shared memory by RecStager (store.cuh).
+template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE, bool RECORDS = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 6)
-eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a) {
+eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a, RecOut ro = RecOut{}) {
     constexpr bool SLAB = MODE == 1;
+    extern __shared__ __align__(16) double2 s_dyn[];
     __shared__ __align__(16) TrajRec s_rec;
     __shared__ __align__(16) Seg s_seg[kMaxSegPerTile];
     __shared__ int s_kend[kMaxSegPerTile];          // last sample of each segment
@@ -207,11 +211,14 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     const int k0 = k_lo + SPT * (int)threadIdx.x;
     int limit = n;
     if (STORE && out.capacity < (int64_t)limit) limit = (int)out.capacity;
+    if (RECORDS && ro.capacity < (int64_t)limit) limit = (int)ro.capacity;
     const int nvalid = (REDUCE ? n : limit) - k0;   // samples this thread evaluates (may be <= 0)
 
     double best_v2 = 0.0, best_a2 = 0.0;
 
-    if (nvalid > 0) {
+    // RECORDS: every lane of a warp takes part in streaming the warp's records, so lanes beyond the trajectory's end
+    // walk through the block too (what they stage is never written)
+    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0)) {
         // ---- segment of each sample: count the segments that end before it (independent broadcast reads) ----
         int si[SPT];
         {
@@ -234,12 +241,31 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
         }
         const uint32_t mask = out.channel_mask;
         const int64_t cs = out.chan_stride;
+        RecStager<THREADS, SPT> stager;
+        tgx_goal_record* rec_row = nullptr;
+        if (RECORDS) {
+            stager.init(s_dyn, (int)threadIdx.x);
+            rec_row = ro.base + (ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride);
+        }
+        // Channels are emitted in tgx_channel order (the record stager pairs 2c with 2c+1); the record's first half
+        // leaves after channel 7 (a.y), the second after the trailing words.
 #define TGX_STORE(CH, ARR)                                                                     \
     do {                                                                                       \
-        if (STORE && nst > 0 && (mask & (1u << (CH)))) store_channel<SPT>(row + (CH) * cs, ARR, nst); \
+        if (RECORDS) {                                                                         \
+            stager.template put<(CH)>(ARR, ro);                                                \
+            if ((CH) == TGX_AY) stager.flush(0, rec_row, k_lo, limit);                         \
+            if ((CH) == TGX_DPSI) {                                                            \
+                stager.put_tail(traj, k0, n);                                                  \
+                stager.flush(1, rec_row, k_lo, limit);                                         \
+            }                                                                                  \
+        } else if (STORE && nst > 0 && (mask & (1u << (CH)))) {                                \
+            store_channel<SPT>(row + (CH) * cs, ARR, nst);                                     \
+        }                                                                                      \
     } while (0)
 
-        double o[SPT];
+        double o[SPT], zero[SPT];
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) zero[u] = 0.0;
         if (type == kRecStatic) {
             // ---- braking goals of the polyline family: createSquareGoal(last.p.x, last.p.y, v, -accel, heading) and
             //      its copies (Square.cpp:126-127, M.cpp:103-104), createBounceGoal(cx, cy, z, vz, heading)
@@ -282,10 +308,10 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
             TGX_STORE(TGX_JX, o);
             TGX_STORE(TGX_JY, o);
             TGX_STORE(TGX_JZ, o);
-            TGX_STORE(TGX_DPSI, o);
 #pragma unroll
             for (int u = 0; u < SPT; ++u) o[u] = s_rec.f[3];
             TGX_STORE(TGX_PSI, o);
+            TGX_STORE(TGX_DPSI, zero);
             if (REDUCE) {
 #pragma unroll
                 for (int u = 0; u < SPT; ++u)
@@ -326,19 +352,17 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
             }
             TGX_STORE(TGX_VX, vx);
             TGX_STORE(TGX_VY, vy);
+            TGX_STORE(TGX_VZ, zero);
             TGX_STORE(TGX_AX, ax);
             TGX_STORE(TGX_AY, ay);
-#pragma unroll
-            for (int u = 0; u < SPT; ++u) o[u] = 0.0;
-            TGX_STORE(TGX_VZ, o);
-            TGX_STORE(TGX_AZ, o);
-            TGX_STORE(TGX_JX, o);
-            TGX_STORE(TGX_JY, o);
-            TGX_STORE(TGX_JZ, o);
-            TGX_STORE(TGX_DPSI, o);
+            TGX_STORE(TGX_AZ, zero);
+            TGX_STORE(TGX_JX, zero);
+            TGX_STORE(TGX_JY, zero);
+            TGX_STORE(TGX_JZ, zero);
 #pragma unroll
             for (int u = 0; u < SPT; ++u) o[u] = theta;
             TGX_STORE(TGX_PSI, o);
+            TGX_STORE(TGX_DPSI, zero);
             if (REDUCE) {
 #pragma unroll
                 for (int u = 0; u < SPT; ++u)
@@ -388,23 +412,21 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
                 }
                 TGX_STORE(TGX_VX, vx);
                 TGX_STORE(TGX_VY, vy);
+                TGX_STORE(TGX_VZ, zero);
                 TGX_STORE(TGX_AX, ax);
                 TGX_STORE(TGX_AY, ay);
+                TGX_STORE(TGX_AZ, zero);
 #pragma unroll
                 for (int u = 0; u < SPT; ++u) o[u] = (v[u] * om[u]) * om[u] * sn[u];     // v^3/r^2 * s
                 TGX_STORE(TGX_JX, o);
 #pragma unroll
                 for (int u = 0; u < SPT; ++u) o[u] = -((v[u] * om[u]) * om[u]) * cn[u];
                 TGX_STORE(TGX_JY, o);
+                TGX_STORE(TGX_JZ, zero);
 #pragma unroll
                 for (int u = 0; u < SPT; ++u) o[u] = th[u] + kPiOver2;                   // unwrapped (:125)
                 TGX_STORE(TGX_PSI, o);
                 TGX_STORE(TGX_DPSI, om);
-#pragma unroll
-                for (int u = 0; u < SPT; ++u) o[u] = 0.0;
-                TGX_STORE(TGX_VZ, o);
-                TGX_STORE(TGX_AZ, o);
-                TGX_STORE(TGX_JZ, o);
                 if (REDUCE) {
 #pragma unroll
                     for (int u = 0; u < SPT; ++u)
@@ -435,19 +457,17 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
                 }
                 TGX_STORE(TGX_VX, vx);
                 TGX_STORE(TGX_VY, vy);
+                TGX_STORE(TGX_VZ, zero);
                 TGX_STORE(TGX_AX, ax);
                 TGX_STORE(TGX_AY, ay);
+                TGX_STORE(TGX_AZ, zero);
+                TGX_STORE(TGX_JX, zero);
+                TGX_STORE(TGX_JY, zero);
+                TGX_STORE(TGX_JZ, zero);
 #pragma unroll
                 for (int u = 0; u < SPT; ++u) o[u] = atan2(vy[u], vx[u]);               // face the velocity (:123)
                 TGX_STORE(TGX_PSI, o);
                 TGX_STORE(TGX_DPSI, om);
-#pragma unroll
-                for (int u = 0; u < SPT; ++u) o[u] = 0.0;
-                TGX_STORE(TGX_VZ, o);
-                TGX_STORE(TGX_AZ, o);
-                TGX_STORE(TGX_JX, o);
-                TGX_STORE(TGX_JY, o);
-                TGX_STORE(TGX_JZ, o);
                 if (REDUCE) {
 #pragma unroll
                     for (int u = 0; u < SPT; ++u)
@@ -527,6 +547,35 @@ cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int
         return mode == 2   ? launch_eval_t<T, S, 2>(tv, ntiles, out, store, max_v, max_a, stream)          \
                : mode == 1 ? launch_eval_t<T, S, 1>(tv, ntiles, out, store, max_v, max_a, stream)          \
                            : launch_eval_t<T, S, 0>(tv, ntiles, out, store, max_v, max_a, stream)
+    TGX_CASE(128, 4);
+    TGX_CASE(256, 2);
+    TGX_CASE(256, 4);
+#undef TGX_CASE
+    return cudaErrorInvalidConfiguration;
+}
+
+template <int THREADS, int SPT, int MODE>
+static cudaError_t launch_eval_records_t(const TableView& tv, int64_t ntiles, const RecOut& ro, cudaStream_t stream) {
+    auto kernel = eval_kernel<THREADS, SPT, false, false, MODE, true>;
+    const int smem = 4 * SPT * THREADS * (int)sizeof(double2);     // one 64-byte half of every record of the tile
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<(unsigned)ntiles, THREADS, smem, stream>>>(tv, OutView{}, nullptr, nullptr, ro);
+    return cudaGetLastError();
+}
+
+// Evaluation straight into clamped array-of-structs records (tgx_eval_records).
+cudaError_t launch_eval_records(const TableView& tv, int64_t ntiles, int tile_shift, int spt, const RecOut& ro,
+                                cudaStream_t stream) {
+    if (ntiles <= 0) return cudaSuccess;
+    if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const int threads = (1 << tile_shift) / spt;
+    const int mode = tv.phase ? 2 : (tv.tile_slab > 0 ? 1 : 0);
+#define TGX_CASE(T, S)                                                                      \
+    if (threads == (T) && spt == (S))                                                       \
+        return mode == 2   ? launch_eval_records_t<T, S, 2>(tv, ntiles, ro, stream)         \
+               : mode == 1 ? launch_eval_records_t<T, S, 1>(tv, ntiles, ro, stream)         \
+                           : launch_eval_records_t<T, S, 0>(tv, ntiles, ro, stream)
     TGX_CASE(128, 4);
     TGX_CASE(256, 2);
     TGX_CASE(256, 4);

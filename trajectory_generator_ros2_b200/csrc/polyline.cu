@@ -419,9 +419,11 @@ poly_tiles_kernel(int64_t n, const int32_t* __restrict__ ntile, const int64_t* _
 // modulo to find the position in the period, a scan over <= 10 leg lengths in shared memory, one correctly rounded
 // division and two multiply-add pairs WITHOUT contraction (the reference's `start + frac * (end - start)` is two
 // roundings per coordinate).  No transcendental on the per-sample path: heading, cos and sin are per leg.
-template <int THREADS, int SPT, bool STORE, bool REDUCE>
+template <int THREADS, int SPT, bool STORE, bool REDUCE, bool RECORDS = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 6)
-eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a) {
+eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a,
+                 RecOut ro = RecOut{}) {
+    extern __shared__ __align__(16) double2 s_dyn[];      // RECORDS: the record stager's transpose buffer (store.cuh)
     __shared__ __align__(16) int4 s_raw[4 * kPolyRecs];
     __shared__ double s_red[THREADS / 32];
 
@@ -444,10 +446,12 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
     const int k0 = k_lo + SPT * (int)threadIdx.x;
     int limit = n;
     if (STORE && out.capacity < (int64_t)limit) limit = (int)out.capacity;
+    if (RECORDS && ro.capacity < (int64_t)limit) limit = (int)ro.capacity;
     const int nvalid = (REDUCE ? n : limit) - k0;
     double best_v2 = 0.0;
 
-    if (nvalid > 0) {
+    // RECORDS: all 32 lanes of a warp with any sample to write take part in streaming the warp's records
+    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0)) {
         const int first = hd.first_special, n_legs = hd.n_legs;
         const bool bounce = hd.type == TGX_BOUNCE;
         // position of sample max(k0, first) in the period: leg l, step i
@@ -494,9 +498,24 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
         }
         const uint32_t mask = out.channel_mask;
         const int64_t cs = out.chan_stride;
+        RecStager<THREADS, SPT> stager;
+        tgx_goal_record* rec_row = nullptr;
+        if (RECORDS) {
+            stager.init(s_dyn, (int)threadIdx.x);
+            rec_row = ro.base + (ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride);
+        }
 #define TGX_STORE(CH, ARR)                                                                                \
     do {                                                                                                  \
-        if (STORE && nst > 0 && (mask & (1u << (CH)))) store_channel<SPT>(row + (CH) * cs, ARR, nst);     \
+        if (RECORDS) {                                                                                    \
+            stager.template put<(CH)>(ARR, ro);                                                           \
+            if ((CH) == TGX_AY) stager.flush(0, rec_row, k_lo, limit);                                    \
+            if ((CH) == TGX_DPSI) {                                                                       \
+                stager.put_tail(traj, k0, n);                                                             \
+                stager.flush(1, rec_row, k_lo, limit);                                                    \
+            }                                                                                             \
+        } else if (STORE && nst > 0 && (mask & (1u << (CH)))) {                                           \
+            store_channel<SPT>(row + (CH) * cs, ARR, nst);                                                \
+        }                                                                                                 \
     } while (0)
         double o[SPT], z[SPT];
 #pragma unroll
@@ -590,6 +609,28 @@ static cudaError_t launch_eval_poly_t(const PolyView& pv, int64_t ntiles, const 
     else
         eval_poly_kernel<THREADS, SPT, false, true><<<grid, THREADS, 0, stream>>>(pv, out, max_v, max_a);
     return cudaGetLastError();
+}
+
+template <int THREADS, int SPT>
+static cudaError_t launch_eval_poly_records_t(const PolyView& pv, int64_t ntiles, const RecOut& ro,
+                                              cudaStream_t stream) {
+    auto kernel = eval_poly_kernel<THREADS, SPT, false, false, true>;
+    const int smem = 4 * SPT * THREADS * (int)sizeof(double2);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<(unsigned)ntiles, THREADS, smem, stream>>>(pv, OutView{}, nullptr, nullptr, ro);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval_poly_records(const PolyView& pv, int64_t ntiles, int tile_shift, int spt, const RecOut& ro,
+                                     cudaStream_t stream) {
+    if (ntiles <= 0) return cudaSuccess;
+    if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const int threads = (1 << tile_shift) / spt;
+    if (threads == 128 && spt == 4) return launch_eval_poly_records_t<128, 4>(pv, ntiles, ro, stream);
+    if (threads == 256 && spt == 2) return launch_eval_poly_records_t<256, 2>(pv, ntiles, ro, stream);
+    if (threads == 256 && spt == 4) return launch_eval_poly_records_t<256, 4>(pv, ntiles, ro, stream);
+    return cudaErrorInvalidConfiguration;
 }
 
 cudaError_t launch_eval_poly(const PolyView& pv, int64_t ntiles, int tile_shift, int spt, const OutView& out,

@@ -183,4 +183,14 @@ struct OutView {
     uint32_t channel_mask;
 };
 
+// Where the evaluation kernels write array-of-structs records (tgx_eval_records): see RecStager in store.cuh.
+struct RecOut {
+    tgx_goal_record* base;
+    int64_t stride;            // records per trajectory (ignored when offset != nullptr)
+    const int64_t* offset;     // optional per-trajectory record offsets
+    int64_t capacity;          // records that fit per trajectory
+    double box[6];
+    int clamp;                 // saturate p to box (TrajectoryGenerator.cpp:602-604)
+};
+
 }  // namespace tgx

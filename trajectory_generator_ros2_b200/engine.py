@@ -64,6 +64,7 @@ def _load() -> C.CDLL:
     lib.tgx_polyline_finalize_host.argtypes = [vp, i64]
     lib.tgx_generate_host_legs.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp]
     lib.tgx_pack_goals.argtypes = [vp, C.POINTER(abi.Layout), vp, i64, vp, vp, i64, vp, i64, vp]
+    lib.tgx_eval_records.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.tgx_generate_records_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp]
     lib.tgx_transitions.argtypes = [vp, vp, i64, vp, vp, i64, i64, vp, vp, vp]
     lib.tgx_transitions_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp]
@@ -333,6 +334,18 @@ class Engine:
     def eval_layout(self, lay: abi.Layout, max_v=None, max_a=None):
         self._check(self._lib.tgx_eval(self._h, C.byref(lay), max_v.data_ptr() if max_v is not None else None,
                                        max_a.data_ptr() if max_a is not None else None, self._stream()), "tgx_eval")
+
+    def eval_records(self, n: int, rec_capacity: int, limits: Optional[abi.Limits] = None, records=None,
+                     rec_offset=None):
+        """tgx_eval_records: the current plan straight into clamped tgx_goal_record rows
+        (uint8 [n, rec_capacity, 128], or a flat [total, 128] tensor addressed through rec_offset)."""
+        import torch
+        if records is None:
+            records = torch.zeros((n, rec_capacity, 128), dtype=torch.uint8, device=self._torch_device())
+        self._check(self._lib.tgx_eval_records(self._h, _limits_ptr(limits), records.data_ptr(), rec_capacity,
+                                               rec_offset.data_ptr() if rec_offset is not None else None,
+                                               rec_capacity, self._stream()), "tgx_eval_records")
+        return records
 
     def pack_goals(self, planes, counts, limits: Optional[abi.Limits] = None, records=None, rec_capacity=None,
                    rec_offset=None, plane_major: bool = False):
