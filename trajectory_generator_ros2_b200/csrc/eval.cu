@@ -246,6 +246,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
         if (RECORDS) {
             stager.init(s_dyn, (int)threadIdx.x);
             rec_row = ro.base + (ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride);
+            stager.bind(rec_row, k0, limit);
         }
         // Channels are emitted in tgx_channel order (the record stager pairs 2c with 2c+1); the record's first half
         // leaves after channel 7 (a.y), the second after the trailing words.

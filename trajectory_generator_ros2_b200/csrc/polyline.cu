@@ -503,6 +503,7 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
         if (RECORDS) {
             stager.init(s_dyn, (int)threadIdx.x);
             rec_row = ro.base + (ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride);
+            stager.bind(rec_row, k0, limit);
         }
 #define TGX_STORE(CH, ARR)                                                                                \
     do {                                                                                                  \

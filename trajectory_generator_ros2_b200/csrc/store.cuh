@@ -76,6 +76,56 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double x) {
 // of one thread) each touch 8 distinct 16-byte bank groups.  Every warp then streams its OWN SPT*32 records: each store
 // instruction writes the 64-byte halves of 8 adjacent samples (full sectors), so only __syncwarp is needed.
 
+#ifdef TGX_RECORDS_DIRECT
+// Experiment: no shared-memory transpose.  Every thread writes its own samples' records as 32-byte (full-sector)
+// streaming stores, four consecutive channels at a time; a warp instruction then touches 32 different lines.
+template <int THREADS, int SPT>
+struct RecStager {
+    int t;
+    double pend[SPT][3];
+    unsigned clamped[SPT];
+    tgx_goal_record* row;
+    int k0_, limit_;
+    __device__ __forceinline__ void init(double2*, int tid) {
+        t = tid;
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) clamped[u] = 0;
+    }
+    __device__ __forceinline__ double sat(double v, double lo, double hi, unsigned bit, unsigned& flags) {
+        if (v > hi) { flags |= bit; return hi; }
+        if (v < lo) { flags |= bit; return lo; }
+        return v;
+    }
+    __device__ __forceinline__ void bind(tgx_goal_record* r, int k0, int limit) { row = r; k0_ = k0; limit_ = limit; }
+    __device__ __forceinline__ void st32(int u, int quad, double a, double b, double c, double d) {
+        if (k0_ + u < limit_) {
+            double* p = reinterpret_cast<double*>(row + k0_ + u) + 4 * quad;
+            asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+        }
+    }
+    template <int CH>
+    __device__ __forceinline__ void put(const double (&x)[SPT], const RecOut& ro) {
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            double y = x[u];
+            if (CH <= TGX_PZ && ro.clamp) y = sat(x[u], ro.box[2 * CH], ro.box[2 * CH + 1], 1u << CH, clamped[u]);
+            if ((CH & 3) != 3) pend[u][CH & 3] = y;
+            else st32(u, CH >> 2, pend[u][0], pend[u][1], pend[u][2], y);
+        }
+    }
+    __device__ __forceinline__ void put_tail(int traj, int k0, int n) {
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            const int k = k0 + u;
+            const unsigned long long w0 = (unsigned long long)(unsigned)traj | ((unsigned long long)(unsigned)k << 32);
+            const unsigned long long w1 = 1ull | ((unsigned long long)clamped[u] << 24) |
+                                          ((unsigned long long)(k == n - 1 ? 1 : 0) << 32);
+            st32(u, 3, pend[u][0], pend[u][1], __longlong_as_double((long long)w0), __longlong_as_double((long long)w1));
+        }
+    }
+    __device__ __forceinline__ void flush(int, tgx_goal_record*, int, int) {}
+};
+#else
 template <int THREADS, int SPT>
 struct RecStager {
     double2* s;                // 4 * SPT * THREADS chunks of dynamic shared memory
@@ -147,7 +197,9 @@ struct RecStager {
         }
         __syncwarp();                                       // the staging area is reused by the next half
     }
+    __device__ __forceinline__ void bind(tgx_goal_record*, int, int) {}
 };
+#endif
 
 }  // namespace
 }  // namespace tgx
