@@ -2,8 +2,10 @@
  * tgx.h — C-ABI of the B200 batched trajectory-evaluation engine (libtgx.so).
  *
  * This is the drop-in boundary for ONE path of jrached/trajectory_generator_ros2: sampling the
- * parametric trajectory classes Circle / Line / Figure8 (with their ramp-up / hold / ramp-down phases and
- * the braking trajectory) into per-time-step setpoints.  Citations are file:line in the reference tree.
+ * parametric trajectory classes (Circle / Line / Figure8 with their ramp-up / hold / ramp-down phases, Boomerang,
+ * the constant-speed polyline family Square / Rectangle / Reciprocating / Bounce / M / I / T, and every class's
+ * braking trajectory) into per-time-step setpoints, plus what the node does with them (clamp + publish) and the
+ * node's own transition setpoints around a trajectory.  Citations are file:line in the reference tree.
  *
  *   reference interface                                         replaced by
  *   ----------------------------------------------------------  ---------------------------------------------
@@ -18,6 +20,14 @@
  *     Circle/Line/Figure8 overrides   Circle.cpp:171-179, Line.cpp:154-173, Figure8.cpp:169-177
  *   index_msgs (phase announcements)  Circle.cpp:45,61-62,74,89  tgx_phases (keys + kinds; host formats text)
  *   traj_goals_[pub_index_]           TrajectoryGenerator.cpp:557  sample k of the output planes
+ *   {Square,Rectangle,Reciprocating,Bounce,M,I,T}::generateTraj                tgx_plan_polyline + tgx_eval
+ *                                     Square.cpp:21-92 ... T.cpp:19-73         (tgx_generate_host_legs)
+ *     create<Shape>Goal               Square.cpp:94-110, Bounce.cpp:54-72      tgx_plan_samples / tgx_sample_host
+ *     generateStopTraj                Square.cpp:112-137, Bounce.cpp:74-103    tgx_plan_stop + tgx_eval
+ *     per-sample index_msgs           Square.cpp:61,79,88; M.cpp:57,65         tgx_polyline_legs (host formats text)
+ *   pubCB, TRAJ_FOLLOWING + saturate  TrajectoryGenerator.cpp:556-561,602-604  tgx_eval_records / tgx_pack_goals
+ *   pubCB, TAKING_OFF / INIT_POS(_TRAJ) / LANDING + simpleInterpolation        tgx_transitions
+ *                                     TrajectoryGenerator.cpp:531-599,637-764
  *
  * Conventions
  *   - extern "C", plain pointers and sizes only.  Every function returns an int status (TGX_OK == 0) and
