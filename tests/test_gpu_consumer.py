@@ -269,6 +269,22 @@ def test_transitions_are_bit_exact(engine, oracle):
         assert rec4[i, :len(want)].tobytes() == want.tobytes() and (want["clamped"] == 0).all()
 
 
+def test_transitions_large_fleet(engine, oracle):
+    """A fleet of several thousand vehicles: every vehicle's records land in its own row, bit for bit."""
+    t = workloads.fleet_transitions(6000)
+    box = (-5.0, 5.0, -5.0, 5.0, 0.0, 5.0)
+    lim = abi.make_limits(box=box)
+    _, counts, status = engine.transitions_host(t, 0, lim)
+    cap = int((counts.max() + 3) // 4 * 4)
+    rec, counts2, status2 = engine.transitions_host(t, cap, lim)
+    np.testing.assert_array_equal(counts, counts2)
+    assert (status2 == 0).all()
+    for i in list(range(0, 6000, 61)) + [5999]:
+        want, st = oracle.transition(t[i:i + 1], traj=i, box=box)
+        assert counts2[i] == len(want) and rec[i, :len(want)].tobytes() == want.tobytes(), i
+        assert not rec[i, len(want):].view(np.uint8).any()
+
+
 @needs_nodes
 def test_transitions_reproduce_the_node_mission(engine, oracle):
     """The whole mission of the unmodified node outside TRAJ_FOLLOWING, from the GPU: take-off, the trip to the start
