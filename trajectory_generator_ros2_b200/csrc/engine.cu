@@ -681,7 +681,7 @@ int64_t tgx_scratch_bytes(const tgx_engine* e) {
     if (!e) return 0;
     const DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
                             &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats,
-                            &e->packets};
+                            &e->packets, &e->phase, &e->poly_recs, &e->poly_tiles};
     int64_t s = 0;
     for (const DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;
@@ -1035,7 +1035,7 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
 
     for (int b = 0; b < 2 && b < nchunks; ++b) {
         if ((rc = e->h_params[b].reserve((size_t)chunk * sizeof(tgx_params)))) return rc;
-        if ((rc = e->h_out[b].reserve((size_t)std::max<int64_t>(chunk * row_bytes, 32)))) return rc;
+        if (!h_records && (rc = e->h_out[b].reserve((size_t)std::max<int64_t>(chunk * row_bytes, 32)))) return rc;
         if ((rc = e->h_cnt[b].reserve((size_t)chunk * sizeof(int32_t)))) return rc;
         if ((rc = e->h_st[b].reserve((size_t)chunk * sizeof(uint32_t)))) return rc;
         if (h_phases && (rc = e->h_ph[b].reserve((size_t)chunk * sizeof(tgx_phases)))) return rc;
