@@ -75,3 +75,49 @@ def test_index_msgs_formatting():
     assert abi.format_phase(abi.TGX_FIGURE8, abi.PH_STOPPED, 0, 0) == "Figure 8 traj: stopped"
     assert abi.format_phase(abi.TGX_FIGURE8, abi.PH_STOPPED, 0, 0, stop_traj=True) == "Figure8 traj: stopped"
     assert abi.format_phase(abi.TGX_LINE, abi.PH_PRESSED_END, 0, 0) == "Line traj: pressed END, decelerating to 0 m/s"
+
+
+def test_new_record_layouts_and_host_finalize():
+    """tgx_polyline_params / tgx_polyline_legs / tgx_goal_record / tgx_transition_params, and the one host-only entry
+    point that needs no GPU: tgx_polyline_finalize_host (cos / sin of the orientation from this host's libm)."""
+    import math
+    assert C.sizeof(abi.PolylineParams) == 13 * 8 and C.sizeof(abi.PolylineLegs) == abi.LEGS_DTYPE.itemsize == 64
+    assert C.sizeof(abi.GoalRecord) == abi.RECORD_DTYPE.itemsize == 128
+    assert C.sizeof(abi.TransitionParams) == abi.TRANSITION_DTYPE.itemsize == 128
+    for name in ("p", "v", "a", "j", "psi", "dpsi", "traj", "k", "power", "mode_xy", "mode_z", "clamped", "last"):
+        assert getattr(abi.GoalRecord, name).offset == abi.RECORD_DTYPE.fields[name][1], name
+    for name in abi.TRANSITION_DTYPE.names:
+        assert getattr(abi.TransitionParams, name).offset == abi.TRANSITION_DTYPE.fields[name][1], name
+    p = abi.concat([abi.square_params(1.8, 2.0, 0.1, 0.2, 0.5, [1.5], 12.0, 0.4, 0.01),
+                    abi.letter_params(abi.TGX_T, 0.0, 0.0, 3.0, 4.0, 1.8, [], 80.0, -2.0, 0.01),
+                    abi.circle_params(1.8, 3.4, 0, 0, [1.0], 80.0, 0.4, 0.01)])
+    c = abi.Params.from_buffer_copy(p[0:1].tobytes())
+    assert (c.u.poly.t_traj, c.u.poly.v_goal, c.u.poly.decel, c.u.poly.orientation) == (12.0, 1.5, 0.4, 0.5)
+    assert list(c.u.poly.g)[:3] == [2.0, 0.1, 0.2] and c.n_vgoals == 0
+    assert p["poly_v_goal"][1] == 1.0                       # v_goals_.empty() ? 1.0 : v_goals_[0]  (T.cpp:45)
+    before = p[2:3].tobytes()
+    engine.Engine.finalize_polyline(p)
+    assert p["cos_o"][0] == math.cos(0.5) and p["sin_o"][0] == math.sin(0.5)
+    assert p["cos_o"][1] == math.cos(-2.0) and p["sin_o"][1] == math.sin(-2.0)
+    assert p["n_vgoals"][0] & abi.TGX_POLY_TRIG_GIVEN and p["n_vgoals"][1] & abi.TGX_POLY_TRIG_GIVEN
+    assert p[2:3].tobytes() == before, "records of the other families are left untouched"
+
+
+def test_polyline_message_formatting():
+    L = np.zeros(1, dtype=abi.LEGS_DTYPE)
+    L["n"], L["n_legs"], L["first_special"], L["period"] = 10, 4, 1, 8
+    L["count"][0, :4] = [2, 2, 2, 2]
+    m = abi.polyline_index_msgs(abi.TGX_SQUARE, L[0])
+    assert m[0] == "Square traj: starting at corner 0" and m[1] == m[2] == "Square traj: moving along side 0"
+    assert m[6] == "Square traj: moving along side 2" and m[7] == m[8] == "Square traj: moving along side 3"
+    assert m[9] == "Square traj: completed" and len(m) == 10
+    L["n"], L["n_legs"], L["first_special"], L["last_special"], L["period"] = 8, 4, 0, 1, 8
+    L["count"][0, :4] = [3, 1, 3, 1]
+    m = abi.polyline_index_msgs(abi.TGX_RECIPROCATING, L[0])
+    assert [m[k] for k in (0, 2, 3, 4, 6)] == ["Reciprocating: forward", "Reciprocating: forward",
+                                               "Reciprocating: yaw flip at endpoint", "Reciprocating: reverse",
+                                               "Reciprocating: reverse"]
+    assert m[7] == "Reciprocating: yaw flip at endpoint"
+    assert abi.polyline_msg(abi.TGX_M, 5, 3, 100) == "M traj: segment 1 rev"
+    assert abi.polyline_msg(abi.TGX_I, 4, 3, 100) == "I traj: segment 4 fwd"
+    assert abi.polyline_msg(abi.TGX_BOUNCE, 1, 99, 100) == "Bounce: completed"

@@ -168,6 +168,12 @@ struct WideIter {
 
 }  // namespace
 
+static_assert(sizeof(tgx_params) == 128, "tgx_params must be 128 bytes");
+static_assert(sizeof(tgx_polyline_params) == 13 * sizeof(double), "tgx_polyline_params must fill the union");
+static_assert(sizeof(tgx_polyline_legs) == 64, "tgx_polyline_legs must be 64 bytes");
+static_assert(sizeof(tgx_goal_record) == 128, "tgx_goal_record must be 128 bytes");
+static_assert(sizeof(tgx_transition_params) == 128, "tgx_transition_params must be 128 bytes");
+
 struct tgx_engine {
     int device = 0;
     int64_t max_samples = (int64_t)1 << 24;
