@@ -192,8 +192,10 @@ typedef struct tgx_limits {
  * Plane-major:       chan_stride = n*row, traj_stride = row.
  * Trajectory-major:  chan_stride = row,   traj_stride = 14*row.
  * base must be 32-byte aligned and every stride/offset a multiple of 4 doubles (vector stores).
- * Samples k >= capacity are not written (status TGX_ST_TRUNCATED). Padding k in [N_i, capacity) is never
- * written either. */
+ * Samples k >= capacity are not written (status TGX_ST_TRUNCATED).  Padding: the slots that share a 32-byte sector
+ * with the trajectory's last samples, k in [N_i, round_up(N_i, 4)), are zero-filled when they lie inside `capacity`
+ * (a partially written sector would have to be fetched from DRAM first: one read-fill per channel per trajectory in the
+ * middle of the store stream); padding k >= round_up(N_i, 4) is never written. */
 typedef struct tgx_layout {
     double* d_base;
     int64_t traj_stride;

@@ -47,7 +47,9 @@ def check_batch(engine, oracle, params, what, **kw):
         if n == 0:
             continue
         merge_errors(worst, assert_samples_close(out[i, :, :n], ref, f"{what}[{i}]"))
-        assert np.isnan(out[i, :, n:]).all(), f"{what}[{i}]: padding was written"
+        # the row's last 32-byte sector is completed with zeros, nothing else is written (tgx.h: tgx_layout)
+        n4 = min((n + 3) // 4 * 4, out.shape[2])
+        assert (out[i, :, n:n4] == 0).all() and np.isnan(out[i, :, n4:]).all(), f"{what}[{i}]: padding was written"
         if ph is not None:
             assert abi.phases_to_index_msgs(int(params["type"][i]), ph[i]) == \
                 abi.phases_to_index_msgs(int(params["type"][i]), oph), f"{what}[{i}]: index_msgs"

@@ -218,7 +218,8 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 
     // RECORDS: every lane of a warp takes part in streaming the warp's records, so lanes beyond the trajectory's end
     // walk through the block too (what they stage is never written)
-    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0)) {
+    // (SPT = 2: the thread that owns the second half of the row's last sector zero-fills it, so it enters too)
+    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0 || (STORE && k0 < ((limit + 3) & ~3)))) {
         // ---- segment of each sample: count the segments that end before it (independent broadcast reads) ----
         int si[SPT];
         {
@@ -233,11 +234,14 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
         }
 
         double* row = nullptr;
-        int nst = 0;
+        int nst = 0, nfill = 0;
         if (STORE) {
             const int64_t toff = out.traj_offset ? __ldg(out.traj_offset + traj) : (int64_t)traj * out.traj_stride;
             row = out.base + toff + k0;
             nst = limit - k0;   // <= 0: nothing to store for this thread
+            // the row's last 32-byte sector is completed with zeros when it lies inside the row's capacity
+            const int64_t lim4 = ((int64_t)limit + 3) & ~(int64_t)3;
+            nfill = (int)((lim4 <= out.capacity ? lim4 : (int64_t)limit) - k0);
         }
         const uint32_t mask = out.channel_mask;
         const int64_t cs = out.chan_stride;
@@ -259,8 +263,8 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
                 stager.put_tail(traj, k0, n);                                                  \
                 stager.flush(1, rec_row, k_lo, limit);                                         \
             }                                                                                  \
-        } else if (STORE && nst > 0 && (mask & (1u << (CH)))) {                                \
-            store_channel<SPT>(row + (CH) * cs, ARR, nst);                                     \
+        } else if (STORE && nfill > 0 && (mask & (1u << (CH)))) {                              \
+            store_channel<SPT>(row + (CH) * cs, ARR, nst, nfill);                              \
         }                                                                                      \
     } while (0)
 

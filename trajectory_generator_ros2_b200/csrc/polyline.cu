@@ -451,7 +451,7 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
     double best_v2 = 0.0;
 
     // RECORDS: all 32 lanes of a warp with any sample to write take part in streaming the warp's records
-    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0)) {
+    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0 || (STORE && k0 < ((limit + 3) & ~3)))) {
         const int first = hd.first_special, n_legs = hd.n_legs;
         const bool bounce = hd.type == TGX_BOUNCE;
         // position of sample max(k0, first) in the period: leg l, step i
@@ -490,11 +490,14 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
         }
 
         double* row = nullptr;
-        int nst = 0;
+        int nst = 0, nfill = 0;
         if (STORE) {
             const int64_t toff = out.traj_offset ? __ldg(out.traj_offset + traj) : (int64_t)traj * out.traj_stride;
             row = out.base + toff + k0;
             nst = limit - k0;
+            // the row's last 32-byte sector is completed with zeros when it lies inside the row's capacity (store.cuh)
+            const int64_t lim4 = ((int64_t)limit + 3) & ~(int64_t)3;
+            nfill = (int)((lim4 <= out.capacity ? lim4 : (int64_t)limit) - k0);
         }
         const uint32_t mask = out.channel_mask;
         const int64_t cs = out.chan_stride;
@@ -514,8 +517,8 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
                 stager.put_tail(traj, k0, n);                                                             \
                 stager.flush(1, rec_row, k_lo, limit);                                                    \
             }                                                                                             \
-        } else if (STORE && nst > 0 && (mask & (1u << (CH)))) {                                           \
-            store_channel<SPT>(row + (CH) * cs, ARR, nst);                                                \
+        } else if (STORE && nfill > 0 && (mask & (1u << (CH)))) {                                         \
+            store_channel<SPT>(row + (CH) * cs, ARR, nst, nfill);                                         \
         }                                                                                                 \
     } while (0)
         double o[SPT], z[SPT];
