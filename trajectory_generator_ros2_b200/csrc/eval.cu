@@ -248,7 +248,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     // RECORDS: every lane of a warp takes part in streaming the warp's records, so lanes beyond the trajectory's end
     // walk through the block too (what they stage is never written)
     // (SPT = 2: the thread that owns the second half of the row's last sector zero-fills it, so it enters too)
-    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0 || (STORE && k0 < ((limit + 3) & ~3)))) {
+    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0 || (STORE && k0 < ((limit + (kFillAlign - 1)) & ~(kFillAlign - 1))))) {
         // ---- segment of each sample: count the segments that end before it (independent broadcast reads) ----
         int si[SPT];
         {
@@ -269,7 +269,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
             row = out.base + toff + k0;
             nst = limit - k0;   // <= 0: nothing to store for this thread
             // the row's last 32-byte sector is completed with zeros when it lies inside the row's capacity
-            const int64_t lim4 = ((int64_t)limit + 3) & ~(int64_t)3;
+            const int64_t lim4 = ((int64_t)limit + (kFillAlign - 1)) & ~(int64_t)(kFillAlign - 1);
             nfill = (int)((lim4 <= out.capacity ? lim4 : (int64_t)limit) - k0);
         }
         const uint32_t mask = out.channel_mask;

@@ -451,7 +451,7 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
     double best_v2 = 0.0;
 
     // RECORDS: all 32 lanes of a warp with any sample to write take part in streaming the warp's records
-    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0 || (STORE && k0 < ((limit + 3) & ~3)))) {
+    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0 || (STORE && k0 < ((limit + (kFillAlign - 1)) & ~(kFillAlign - 1))))) {
         const int first = hd.first_special, n_legs = hd.n_legs;
         const bool bounce = hd.type == TGX_BOUNCE;
         // position of sample max(k0, first) in the period: leg l, step i
@@ -496,7 +496,7 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
             row = out.base + toff + k0;
             nst = limit - k0;
             // the row's last 32-byte sector is completed with zeros when it lies inside the row's capacity (store.cuh)
-            const int64_t lim4 = ((int64_t)limit + 3) & ~(int64_t)3;
+            const int64_t lim4 = ((int64_t)limit + (kFillAlign - 1)) & ~(int64_t)(kFillAlign - 1);
             nfill = (int)((lim4 <= out.capacity ? lim4 : (int64_t)limit) - k0);
         }
         const uint32_t mask = out.channel_mask;

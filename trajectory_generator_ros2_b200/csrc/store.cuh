@@ -44,6 +44,12 @@ struct VecStore<4, POLICY> {
 #define TGX_STORE_POLICY 0
 #endif
 
+// A row's tail is zero-filled up to a multiple of kFillAlign samples (see store_channel).
+#ifndef TGX_FILL_ALIGN
+#define TGX_FILL_ALIGN 4
+#endif
+constexpr int kFillAlign = TGX_FILL_ALIGN;
+
 // Store SPT adjacent samples of one channel.  nvalid = samples of this thread below the row's limit (may be <= 0),
 // nfill = samples of this thread below the limit ROUNDED UP to a 32-byte sector (4 doubles) and inside the row's
 // capacity.  A trajectory's last vector is written in full, its tail zero-filled: a partially written sector would make
