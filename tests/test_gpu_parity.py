@@ -581,10 +581,20 @@ def test_slab_planning_matches_exact_offsets_and_falls_back(engine, oracle):
     np.testing.assert_array_equal(st3, o_status)
     ref, _, _ = oracle.generate(mixed[300:301])
     assert_samples_close(out[300, :, :25001], ref, "default circle after slab fallback")
-    # ragged batch learned: the next plan of it stays on the exact-offset path (too many empty slots otherwise)
-    gpu_generate(engine, mixed, want_phases=False)
+    # ragged batch learned: the next plan of it is a single replay into fixed slices whose used tile slots are
+    # compacted into a dense work list (no CTA per empty slot); same samples as the two-replay plan
+    out2, c4, st4, _ = gpu_generate(engine, mixed, want_phases=False)
     s4, e4 = engine.plan_path_counts()
-    assert (s4 - s3, e4 - e3) == (0, 1)
+    assert (s4 - s3, e4 - e3) == (1, 0)
+    np.testing.assert_array_equal(c4, o_counts)
+    np.testing.assert_array_equal(st4, o_status)
+    m = ~np.isnan(out)
+    assert (np.isnan(out2) == np.isnan(out)).all()
+    np.testing.assert_array_equal(out2[m], out[m])
+    out3, c5, _, _ = gpu_generate(engine, mixed, want_phases=False)          # and it stays on that path
+    s5, e5 = engine.plan_path_counts()
+    assert (s5 - s4, e5 - e4) == (1, 0)
+    np.testing.assert_array_equal(out3[m], out[m])
     engine.set_phase_planning(True)
 
 

@@ -37,6 +37,9 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
                              int seg_slab, int tile_slab, TrajRec* recs, Seg* segs, Tile* tiles, int32_t* counts,
                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
                              PlanStats* stats, cudaStream_t stream);
+cudaError_t launch_count_used_tiles(int64_t n, int tile_slab, const Tile* slots, int32_t* ntile, cudaStream_t stream);
+cudaError_t launch_compact_tiles(int64_t n, int tile_slab, const Tile* slots, const int64_t* tile_off, Tile* dense,
+                                 cudaStream_t stream);
 cudaError_t launch_plan_phase(const tgx_params* params, int64_t n, const tgx_limits* lim, int64_t max_samples,
                               int tile_shift, int max_n, const void* cur_table, PhaseRec* phase, int32_t* counts,
                               uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
@@ -187,6 +190,9 @@ struct tgx_engine {
     // slab-mode planning (single replay): slice sizes learned from the previous exact-offset plan
     bool allow_slabs = true;
     bool slabs_ready = false;
+    bool ragged_ready = false;                   // slices are known but the batch is ragged: slab fill + tile compaction
+    bool plan_dense_tiles = false;               // current plan: exact-offset addressing through tiles_dense
+    int64_t ragged_plans = 0;
     int seg_slab = 0, tile_slab = 0;             // slice sizes the NEXT slab plan will use
     int seg_slab_plan = 0, tile_slab_plan = 0;   // slice sizes of the CURRENT plan (if plan_packed)
     int64_t slab_plans = 0, exact_plans = 0;
@@ -194,7 +200,7 @@ struct tgx_engine {
     // per-trajectory scratch (capacity in trajectories)
     DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals, cur_table, stats;
     // tables
-    DevBuf segs, tiles, packets, phase;
+    DevBuf segs, tiles, packets, phase, tiles_dense;
     bool plan_packed = false;                    // current plan is a slab plan
     bool plan_phase = false;                     // current plan is a phase plan
     const tgx_params* plan_params = nullptr;     // phase plans read the caller's parameter array during evaluation
@@ -228,7 +234,7 @@ tgx::TableView table_view(const tgx_engine* e) {
     tgx::TableView tv{};
     tv.recs = e->recs.as<tgx::TrajRec>();
     tv.segs = e->segs.as<tgx::Seg>();
-    tv.tiles = e->tiles.as<tgx::Tile>();
+    tv.tiles = e->plan_dense_tiles ? e->tiles_dense.as<tgx::Tile>() : e->tiles.as<tgx::Tile>();
     if (e->plan_phase) {
         tv.params = e->plan_params;
         tv.phase = e->phase.as<tgx::PhaseRec>();
@@ -295,8 +301,29 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
 
     int64_t tot_samples = 0, tot_segs = 0, tot_tiles = 0;
     bool done = false;
+    // Every fill pass measures the largest per-trajectory segment / tile counts: they size the slices of the NEXT plan
+    // and decide which single-replay path it can take (dense slices, ragged slices + tile compaction, phase records).
+    auto relearn = [&](int64_t total_tiles) {
+        // slices grow to the largest batch seen and shrink only when a batch needs less than half of them, so that
+        // alternating batches (the chunks of one large job) do not overflow each other's slices
+        int seg_slab = (h_stats->max_nseg + 4 + 3) / 4 * 4;
+        int tile_slab = std::max(h_stats->max_ntile, 1);
+        if (e->seg_slab > seg_slab && e->seg_slab <= 2 * seg_slab) seg_slab = e->seg_slab;
+        if (e->tile_slab > tile_slab && e->tile_slab <= 2 * tile_slab) tile_slab = e->tile_slab;
+        const bool dense = n * (int64_t)tile_slab <= total_tiles + total_tiles / 4 + 1;
+        const bool small = n * (int64_t)seg_slab * (int64_t)sizeof(tgx::Seg) <= ((int64_t)8 << 30) &&
+                           n * (int64_t)seg_slab <= 0x7fffffffLL && n * (int64_t)tile_slab <= 0x7fffffffLL;
+        e->slabs_ready = dense && small && total_tiles > 0;
+        e->ragged_ready = !dense && small && total_tiles > 0;
+        e->seg_slab = seg_slab;
+        e->tile_slab = tile_slab;
+        e->phase_ready = e->allow_phase && !e->exact_ramps && dense && !h_stats->has_line && h_stats->max_n > 0 &&
+                         h_stats->max_n <= tgx::kPhaseMaxSamples;
+        e->phase_tile_slab = tile_slab;
+    };
     e->plan_phase = false;
     e->plan_params = nullptr;
+    e->plan_dense_tiles = false;
 
     // ---- phase mode: batches of short orbits.  One counting replay (no angle state, no tables): the evaluation
     //      kernel derives its segments from the caller's parameter array, which must stay valid until tgx_eval ----
@@ -329,7 +356,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     }
 
     // ---- slab mode: ONE replay, no scans; falls through to the exact-offset path if a slice overflows ----------
-    if (!done && e->allow_slabs && e->slabs_ready && !d_stop_from) {
+    if (!done && e->allow_slabs && (e->slabs_ready || e->ragged_ready) && !d_stop_from) {
         const int64_t need_segs = n * (int64_t)e->seg_slab, need_tiles = n * (int64_t)e->tile_slab;
         if (need_segs <= 0x7fffffffLL && need_tiles <= 0x7fffffffLL) {
             if ((rc = e->segs.reserve((size_t)need_segs * sizeof(tgx::Seg)))) return rc;
@@ -343,7 +370,33 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
             e->launches += 1;
             TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
             TGX_CUDA(cudaStreamSynchronize(stream));
-            if (!h_stats->overflow) {
+            const bool sparse = (int64_t)h_stats->total_tiles + (int64_t)h_stats->total_tiles / 4 + 1 < need_tiles;
+            if (!h_stats->overflow && sparse) {
+                // Ragged batch: most tile slots are empty.  Keep the single replay, but hand the evaluation kernel a
+                // dense work list instead of one CTA per slot: count the used slots, scan, compact (three tiny kernels).
+                const int64_t used = (int64_t)h_stats->total_tiles;
+                if ((rc = e->tiles_dense.reserve((size_t)std::max<int64_t>(used, 1) * sizeof(tgx::Tile)))) return rc;
+                TGX_CUDA(tgx::launch_count_used_tiles(n, e->tile_slab, e->tiles.as<tgx::Tile>(), ntile, stream));
+                TGX_CUDA(cudaMemsetAsync(ntile + n, 0, sizeof(int32_t), stream));
+                WideIter tile_in{ntile};
+                size_t need = 0;
+                TGX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, tile_in, tile_off, (int)(n + 1), stream));
+                if ((rc = e->cub_tmp.reserve(need))) return rc;
+                size_t tmp_bytes = e->cub_tmp.bytes;
+                TGX_CUDA(cub::DeviceScan::ExclusiveSum(e->cub_tmp.p, tmp_bytes, tile_in, tile_off, (int)(n + 1), stream));
+                TGX_CUDA(tgx::launch_compact_tiles(n, e->tile_slab, e->tiles.as<tgx::Tile>(), tile_off,
+                                                   e->tiles_dense.as<tgx::Tile>(), stream));
+                e->launches += 2;
+                tot_samples = (int64_t)h_stats->total_samples;
+                tot_segs = need_segs;
+                tot_tiles = used;
+                done = true;
+                e->plan_packed = false;
+                e->plan_dense_tiles = true;
+                e->ragged_plans += 1;
+                e->slab_plans += 1;
+                relearn(used);
+            } else if (!h_stats->overflow) {
                 tot_samples = (int64_t)h_stats->total_samples;
                 tot_segs = need_segs;
                 tot_tiles = need_tiles;
@@ -352,16 +405,10 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                 e->seg_slab_plan = e->seg_slab;
                 e->tile_slab_plan = e->tile_slab;
                 e->slab_plans += 1;
-                // a batch with many fewer tiles than slots would launch mostly empty CTAs: go back to exact offsets
-                if ((int64_t)h_stats->total_tiles * 2 < need_tiles) e->slabs_ready = false;
-                // an all-orbit batch of short trajectories can drop the tables altogether next time
-                const int slots = (h_stats->max_n + (1 << e->tile_shift) - 1) >> e->tile_shift;
-                e->phase_ready = e->allow_phase && !e->exact_ramps && !h_stats->has_line && h_stats->max_n > 0 &&
-                                 h_stats->max_n <= tgx::kPhaseMaxSamples &&
-                                 n * (int64_t)slots <= (int64_t)h_stats->total_tiles + (int64_t)h_stats->total_tiles / 4 + 1;
-                e->phase_tile_slab = std::max(slots, 1);
+                relearn((int64_t)h_stats->total_tiles);
             } else {
                 e->slabs_ready = false;   // re-learn the slice sizes below
+                e->ragged_ready = false;
             }
         }
     }
@@ -415,18 +462,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         if (e->allow_slabs && !d_stop_from) {
             TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
             TGX_CUDA(cudaStreamSynchronize(stream));
-            // slices: the largest trajectory of this batch plus headroom; worth it only for batches without many
-            // short rows (every slot becomes a CTA) and with a moderate table footprint
-            const int seg_slab = (h_stats->max_nseg + 4 + 3) / 4 * 4;
-            const int tile_slab = std::max(h_stats->max_ntile, 1);
-            const bool dense = n * (int64_t)tile_slab <= tot_tiles + tot_tiles / 4 + 1;
-            const bool small = n * (int64_t)seg_slab * (int64_t)sizeof(tgx::Seg) <= ((int64_t)8 << 30);
-            e->slabs_ready = dense && small && tot_tiles > 0;
-            e->seg_slab = seg_slab;
-            e->tile_slab = tile_slab;
-            e->phase_ready = e->allow_phase && !e->exact_ramps && dense && !h_stats->has_line && h_stats->max_n > 0 &&
-                             h_stats->max_n <= tgx::kPhaseMaxSamples;
-            e->phase_tile_slab = tile_slab;
+            relearn(tot_tiles);
         }
     }
 
@@ -587,7 +623,7 @@ int tgx_destroy(tgx_engine* e) {
     cudaSetDevice(e->device);
     DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
                       &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats, &e->packets,
-                      &e->phase, &e->poly_recs, &e->poly_tiles};
+                      &e->phase, &e->poly_recs, &e->poly_tiles, &e->tiles_dense};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         e->h_legs[i].release();
@@ -624,6 +660,7 @@ int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt) {
     e->spt = spt;
     e->has_plan = false;   // tile size is baked into a plan
     e->slabs_ready = false;
+    e->ragged_ready = false;
     e->phase_ready = false;
     return TGX_OK;
 }
@@ -633,6 +670,7 @@ int tgx_set_plan_mode(tgx_engine* e, int exact_ramps) {
     e->exact_ramps = exact_ramps != 0;
     e->has_plan = false;
     e->slabs_ready = false;   // segment counts differ between the modes (ramp chunks)
+    e->ragged_ready = false;
     e->phase_ready = false;
     return TGX_OK;
 }
@@ -658,6 +696,7 @@ int tgx_set_slab_planning(tgx_engine* e, int allow) {
     if (!e) return TGX_ERR_INVALID;
     e->allow_slabs = allow != 0;
     e->slabs_ready = false;
+    e->ragged_ready = false;
     e->has_plan = false;
     return TGX_OK;
 }

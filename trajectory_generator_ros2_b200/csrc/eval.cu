@@ -423,7 +423,9 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
                 // the store-bound instantiations take the lighter routine (no slow path, no stack frame: 17.7 -> 17.6 ms
                 // on the 1 Mi-circle batch); the reduction-only one is FP64- / issue-bound and is 17 % faster with the
                 // library's scheduling of the same polynomials
-                if (STORE || RECORDS) sincos_orbit(th[u], &sn[u], &cn[u]);
+                // (every instantiation that reduces maxima uses the same routine, so tgx_eval's maxima equal
+                // tgx_feasibility's bit for bit)
+                if (!REDUCE) sincos_orbit(th[u], &sn[u], &cn[u]);
                 else sincos(th[u], &sn[u], &cn[u]);
 #endif
                 om[u] = v[u] * rinv;                 // omega = v / r

@@ -950,7 +950,45 @@ selftest_division_kernel(int64_t n, uint64_t seed, int per_thread, unsigned long
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// Ragged batches planned with fixed slices (one replay): most tile slots are empty, and launching one CTA per slot would
+// waste the evaluation grid.  These two kernels turn the slots into the dense work list of an exact-offset plan
+// (Tile.seg_begin already is the absolute position of the tile's segments inside the trajectory's slice).
+__global__ void __launch_bounds__(256)
+count_used_tiles_kernel(int64_t n, int tile_slab, const Tile* __restrict__ slots, int32_t* __restrict__ ntile) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = 0;
+    for (int t = 0; t < tile_slab; ++t) c += slots[i * tile_slab + t].nseg > 0 ? 1 : 0;
+    ntile[i] = c;
+}
+
+__global__ void __launch_bounds__(256)
+compact_tiles_kernel(int64_t n, int tile_slab, const Tile* __restrict__ slots, const int64_t* __restrict__ tile_off,
+                     Tile* __restrict__ dense) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t o = tile_off[i];
+    for (int t = 0; t < tile_slab; ++t) {
+        const Tile e = slots[i * tile_slab + t];
+        if (e.nseg > 0) dense[o++] = e;            // the used slots of a trajectory are its first ones, in tile order
+    }
+}
+
 // ---- host-side launchers (called from engine.cu) -------------------------------------------------------
+
+cudaError_t launch_count_used_tiles(int64_t n, int tile_slab, const Tile* slots, int32_t* ntile, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    count_used_tiles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, tile_slab, slots, ntile);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_tiles(int64_t n, int tile_slab, const Tile* slots, const int64_t* tile_off, Tile* dense,
+                                 cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    compact_tiles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, tile_slab, slots, tile_off, dense);
+    return cudaGetLastError();
+}
+
 
 cudaError_t launch_build_cur_table(const tgx_params* params, int64_t max_samples, void* table, cudaStream_t stream) {
     build_cur_table_kernel<<<1, 32, 0, stream>>>(params, max_samples, static_cast<CurTable*>(table));
