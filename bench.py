@@ -185,7 +185,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- our arm ---------------------------------------------------------------------------------------------------
@@ -505,7 +505,7 @@ def run_ours(args):
             line["config"]["flags_allgather_ms"] = gather_ms
             line["roofline"]["note"] = ("reduction-only path: writes 17 B per trajectory, FP64-pipe- and issue-bound, "
                                         "the HBM fraction is stated for information only")
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
@@ -556,7 +556,7 @@ def run_transitions(args):
     t0 = time.perf_counter()
     ticks = sum(len(orc.transition(t[i:i + 1], box=(-5.0, 5.0, -5.0, 5.0, 0.0, 5.0))[0]) for i in range(m))
     cpu_s = time.perf_counter() - t0
-    print(json.dumps({
+    emit({
         "metric": "transition setpoints/s (take-off / go-to / landing recurrences)", "value": total / (ms * 1e-3),
         "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -567,8 +567,29 @@ def run_transitions(args):
                      "peak_source": peak_src},
         "cpu_baseline": {"value": ticks / cpu_s, "unit": "samples/s", "cores": 1, "kind": "port",
                          "sample": f"first {m} vehicles ({ticks} ticks) through orc_transition incl. the Python call overhead"},
-        "e2e": None, "gpu_launches": launches, "clocks": clocks}), flush=True)
+        "e2e": None, "gpu_launches": launches, "clocks": clocks})
     eng.close()
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else a library prints there (NCCL's version banner under torchrun,
+    for instance) is sent to stderr, and the JSON line is written to the original descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -594,6 +615,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    _claim_stdout()
     if args.workload == "transitions":
         run_transitions(args)
     elif args.impl == "reference":
