@@ -32,11 +32,13 @@ constexpr double kPiOver2 = 1.57079632679489661923;
 // ~1e-16 absolute for every |x| < 1e9 checked — followed by the fdlibm minimax polynomials on [-pi/4, pi/4] (< 1 ulp).
 // No Payne-Hanek slow path, hence no stack frame.  Parity budget: |dp| <= 1e-9 m needs |d sin| <= 2e-10 at r = 5 m.
 __device__ __forceinline__ void sincos_orbit(double x, double* sn, double* cs) {
-    const double kd = rint(x * 6.36619772367581382433e-01);          // x * 2/pi
+    // k = rint(x * 2/pi) without a float->int conversion: adding 1.5 * 2^52 leaves k in the low mantissa bits
+    const double shifted = fma(x, 6.36619772367581382433e-01, 6755399441055744.0);
+    const int q = __double2loint(shifted);                           // only the two low bits matter
+    const double kd = shifted - 6755399441055744.0;
     double r = fma(kd, -1.57079632679489655800e+00, x);              // pi/2 = hi + mid + lo
     r = fma(kd, -6.12323399573676603587e-17, r);
-    r = fma(kd, 1.49738490485916983329e-33 * -1.0, r);
-    const int q = (int)__double2ll_rn(kd);                           // only the two low bits matter
+    r = fma(kd, -1.49738490485916983329e-33, r);
     const double z = r * r;
     double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
     ps = fma(z, ps, 2.75573137070700676789e-06);
