@@ -16,7 +16,8 @@ def test_cfg2_recipe_counts(oracle):
 
 
 def test_workloads_are_shard_invariant():
-    for fn in (workloads.circles_cfg2, workloads.mixed_cfg3, workloads.montecarlo_cfg4):
+    for fn in (workloads.circles_cfg2, workloads.mixed_cfg3, workloads.montecarlo_cfg4, workloads.polyline_mix,
+               workloads.letters_T):
         full = fn(200000)
         part = fn(200000, lo=65000, hi=140001)
         assert full[65000:140001].tobytes() == part.tobytes()
@@ -32,6 +33,25 @@ def test_cfg3_mix_and_line_feasibility(oracle):
         assert oracle.line_d2(lines[i:i + 1]) > 0
     counts, status = oracle.count_batch(p[:3000])
     assert (status == 0).all() and counts.min() > 50 and counts.max() < 2400
+
+
+def test_polyline_workloads(oracle):
+    """Row f2 workloads: all seven shapes present, ~1000 samples each, every record accepted; the T batch is the shape
+    default.yaml ships."""
+    p = workloads.polyline_mix(7000)
+    kinds = np.bincount(p["type"], minlength=11)
+    assert (kinds[:4] == 0).all() and (kinds[4:] > 700).all()
+    counts, status = oracle.count_batch(p)
+    assert (status == 0).all() and counts.min() >= 800 and counts.max() <= 1202
+    t = workloads.letters_T(3000)
+    counts, status = oracle.count_batch(t)
+    assert (t["type"] == abi.TGX_T).all() and (status == 0).all() and counts.min() >= 990 and counts.max() <= 1011
+    for k in abi.POLYLINE_TYPES:
+        n, st = oracle.count(workloads.default_polyline(k))
+        assert st == 0 and n in (8000, 8001)
+    tr = workloads.fleet_transitions(400)
+    lens = [len(oracle.transition(tr[i:i + 1], box=(-5, 5, -5, 5, 0, 5))[0]) for i in range(0, 400, 7)]
+    assert min(lens) > 50 and max(lens) < 2700
 
 
 def _free_port():
