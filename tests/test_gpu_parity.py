@@ -670,3 +670,71 @@ def test_hold_table_handles_mixed_dt(engine, oracle):
             for dt in (0.01, 0.02, 0.005, 0.01, 1.0 / 3.0, 0.01) for t in (0.0, 0.7, 10.0, 33.3)]
     params = abi.concat(recs)
     check_batch(engine, oracle, params, "mixed dt")
+
+
+def test_full_size_config2(engine, oracle):
+    """BASELINE.json configs[1] at FULL size: 1 Mi circles x ~1000 samples (1.05e9 samples, 117.5 GB of planes on one GPU).
+    Counts against the oracle for every trajectory; size-independent properties for every sample, checked slab by slab
+    on the device (|p - c| = r, p.z = alt, |v| = omega r, rest at the end, zero-filled tail sector, untouched padding);
+    a sum-of-sums of every plane against the same batch evaluated in 16 independent shards (what a 16-GPU job would
+    produce: sharding must not change a bit); oracle values for one trajectory in 4096."""
+    import torch
+    n = 1 << 20
+    params = workloads.circles_cfg2(n)
+    d = engine.upload_params(params)
+    torch.cuda.empty_cache()                        # blocks cached by earlier tests count as used otherwise
+    free, _ = torch.cuda.mem_get_info()
+    if free < 135 * (1 << 30):
+        pytest.skip("needs ~125 GB of free device memory")
+    engine.set_phase_planning(True)
+    engine.plan(d)                                  # whatever path this takes, it leaves the engine in steady state
+    p0 = engine.phase_plan_count
+    plan = engine.plan(d)
+    assert engine.phase_plan_count == p0 + 1, "steady state for this batch is the phase plan (what bench.py times)"
+    counts = plan.counts
+    o_counts, o_status = oracle.count_batch(params, nthreads=32)
+    np.testing.assert_array_equal(counts.cpu().numpy(), o_counts)
+    assert plan.total_samples == int(o_counts.sum()) == 1049100173
+    out = torch.full((n, 14, 1024), float("nan"), dtype=torch.float64, device=d.device)
+    engine.eval(out)
+    torch.cuda.synchronize()
+    step = 1 << 15
+    sums = torch.zeros(14, dtype=torch.float64, device=d.device)
+    k = torch.arange(1024, device=d.device)[None, :]
+    for lo in range(0, n, step):
+        sl = slice(lo, lo + step)
+        o = out[sl]
+        c = counts[sl][:, None]
+        valid = k < c
+        fill = (k >= c) & (k < (c + 3) // 4 * 4)
+        pr = lambda name: torch.from_numpy(params[name][sl].copy()).to(d.device)[:, None]
+        r, cx, cy, alt = pr("r"), pr("cx"), pr("cy"), pr("alt")
+        zero = torch.zeros((), dtype=torch.float64, device=d.device)
+        masked = lambda x: torch.where(valid, x, zero)            # the padding is NaN: mask, do not multiply
+        assert float(masked((torch.hypot(o[:, abi.PX] - cx, o[:, abi.PY] - cy) - r).abs()).max()) < 1e-12
+        assert bool(((o[:, abi.PZ] == alt) | ~valid).all())
+        speed = torch.hypot(o[:, abi.VX], o[:, abi.VY])
+        assert float(masked((speed - o[:, abi.DPSI] * r).abs()).max()) < 1e-12
+        assert float(torch.gather(speed, 1, (c - 1).long()).abs().max()) == 0.0
+        assert bool(((o[:, abi.PX] == 0) | ~fill).all()) and bool((torch.isnan(o[:, abi.PX]) | (k < (c + 3) // 4 * 4)).all())
+        sums += torch.where(valid[:, None, :], o, torch.zeros((), dtype=torch.float64, device=d.device)).sum(dim=(0, 2))
+    # the same batch as 16 independent shards
+    shard_sums = torch.zeros(14, dtype=torch.float64, device=d.device)
+    buf = torch.empty((n // 16, 14, 1024), dtype=torch.float64, device=d.device)
+    for s in range(16):
+        sl = slice(s * (n // 16), (s + 1) * (n // 16))
+        p1 = engine.phase_plan_count
+        p2 = engine.plan(d[sl])
+        assert engine.phase_plan_count == p1 + 1
+        assert torch.equal(p2.counts, counts[sl])
+        engine.eval(buf)
+        assert torch.equal(buf[:, :, :1000], out[sl][:, :, :1000]), "a shard must reproduce its slice bit for bit"
+        valid = k < p2.counts[:, None]
+        shard_sums += torch.where(valid[:, None, :], buf, torch.zeros((), dtype=torch.float64, device=d.device)).sum(dim=(0, 2))
+    # (the shards reproduce their slices bit for bit; the plane sums differ only by the order of summation)
+    assert torch.allclose(sums, shard_sums, rtol=1e-12, atol=1e-6)
+    sub = np.arange(0, n, 4096)
+    host = out[torch.from_numpy(sub).to(d.device)].cpu().numpy()
+    for j, i in enumerate(sub):
+        ref, _, _ = oracle.generate(params[i:i + 1])
+        assert_samples_close(host[j, :, :o_counts[i]], ref, f"full size[{i}]")

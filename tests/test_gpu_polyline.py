@@ -302,3 +302,54 @@ def test_python_mirror_classes(engine, oracle):
                                 -0.4 * np.sin(0.7), 0.7], rtol=1e-14)
     g = trajs[3][0].createBounceGoal(0.1, 0.2, 2.5, -1.0, 0.3)
     assert (g.p.x, g.p.y, g.p.z, g.v.x, g.v.y, g.v.z, g.psi) == (0.1, 0.2, 2.5, 0.0, 0.0, -1.0, 0.3)
+
+
+def test_full_size_T_batch(engine, oracle):
+    """Row f2 at full size: 1 Mi T trajectories (the shape default.yaml ships) x ~1000 samples, 117.5 GB of planes.
+    Counts against the oracle for every trajectory; for every sample p.z = alt, a = j = dpsi = 0, |v| = v_goal; the batch
+    evaluated as 16 independent shards reproduces its slices bit for bit; positions of one trajectory in 4096 are
+    bit-identical to the oracle's."""
+    import torch
+    n = 1 << 20
+    params = engine.finalize_polyline(workloads.letters_T(n).copy())
+    d = engine.upload_params(params)
+    torch.cuda.empty_cache()                        # blocks cached by earlier tests count as used otherwise
+    free, _ = torch.cuda.mem_get_info()
+    if free < 135 * (1 << 30):
+        pytest.skip("needs ~125 GB of free device memory")
+    plan = engine.plan_polyline(d)
+    counts = plan.counts
+    o_counts, o_status = oracle.count_batch(params, nthreads=32)
+    np.testing.assert_array_equal(counts.cpu().numpy(), o_counts)
+    np.testing.assert_array_equal(plan.status.cpu().numpy().view(np.uint32), o_status)
+    out = torch.full((n, 14, 1024), float("nan"), dtype=torch.float64, device=d.device)
+    engine.eval(out)
+    torch.cuda.synchronize()
+    k = torch.arange(1024, device=d.device)[None, :]
+    step = 1 << 15
+    zero = torch.zeros((), dtype=torch.float64, device=d.device)
+    for lo in range(0, n, step):
+        sl = slice(lo, lo + step)
+        o = out[sl]
+        valid = k < counts[sl][:, None]
+        alt = torch.from_numpy(params["alt"][sl].copy()).to(d.device)[:, None]
+        vg = torch.from_numpy(params["poly_v_goal"][sl].copy()).to(d.device)[:, None]
+        assert bool(((o[:, abi.PZ] == alt) | ~valid).all())
+        for ch in (abi.VZ, abi.AX, abi.AY, abi.AZ, abi.JX, abi.JY, abi.JZ, abi.DPSI):
+            assert bool(((o[:, ch] == 0) | ~valid).all())
+        speed = torch.hypot(o[:, abi.VX], o[:, abi.VY])
+        assert float(torch.where(valid, (speed - vg).abs() / vg, zero).max()) < 1e-15
+    buf = torch.empty((n // 16, 14, 1024), dtype=torch.float64, device=d.device)
+    for s in range(16):
+        sl = slice(s * (n // 16), (s + 1) * (n // 16))
+        p2 = engine.plan_polyline(d[sl])
+        assert torch.equal(p2.counts, counts[sl])
+        engine.eval(buf)
+        assert torch.equal(buf[:, :, :988], out[sl][:, :, :988]), "a shard must reproduce its slice bit for bit"
+    sub = np.arange(0, n, 4096)
+    host = out[torch.from_numpy(sub).to(d.device)].cpu().numpy()
+    for j, i in enumerate(sub):
+        ref = oracle.polyline_generate(params[i:i + 1])[0]
+        got = host[j, :, :o_counts[i]]
+        assert_samples_close(got, ref, f"full size T[{i}]")
+        assert np.array_equal(got[:3] + 0.0, ref[:3] + 0.0), f"full size T[{i}]: positions"
