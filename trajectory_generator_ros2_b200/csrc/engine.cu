@@ -862,6 +862,33 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
     return TGX_OK;
 }
 
+// The record buffer as TMA sees it: a 2-D fp64 tensor [records][16], one 128-byte row per record, written in boxes of
+// 32 records with the 128-byte shared-memory swizzle (RecTma in store.cuh stages in exactly that layout).  The outer
+// extent is the coordinate range, not the allocation: the kernel only issues boxes that lie inside a trajectory's row.
+// The encoder lives in libcuda; it is looked up through the runtime so libtgx.so needs no -lcuda.
+static int make_record_tmap(CUtensorMap* tmap, tgx_goal_record* d_records) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+            q != cudaDriverEntryPointSuccess)
+            return TGX_ERR_CUDA;
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    const cuuint64_t dims[2] = {16, (cuuint64_t)1 << 31};
+    const cuuint64_t strides[1] = {sizeof(tgx_goal_record)};
+    const cuuint32_t box[2] = {16, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_records, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? TGX_OK : TGX_ERR_CUDA;
+}
+
 int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
                      const int64_t* d_rec_offset, int64_t rec_capacity, void* stream) {
     if (!e || !d_records || rec_capacity < 0) return TGX_ERR_INVALID;
@@ -878,10 +905,13 @@ int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d
     if (ro.clamp)
         for (int i = 0; i < 6; ++i) ro.box[i] = limits->box[i];
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (e->plan_poly)
+    if (e->plan_poly) {
         TGX_CUDA(tgx::launch_eval_poly_records(poly_view(e), e->plan_tiles, e->tile_shift, e->spt, ro, s));
-    else
+    } else {
+        const int rc = make_record_tmap(&ro.tmap, d_records);
+        if (rc) return rc;
         TGX_CUDA(tgx::launch_eval_records(table_view(e), e->plan_tiles, e->tile_shift, e->spt, ro, s));
+    }
     e->launches += 1;
     return TGX_OK;
 }

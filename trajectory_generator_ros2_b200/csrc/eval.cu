@@ -123,12 +123,18 @@ __device__ void build_phase_segment(const tgx_params& par, const PhaseRec& phr, 
 
 // MODE 0: exact-offset plan, 1: slab plan (fixed per-trajectory slices), 2: phase plan (see TableView).
 // RECORDS: instead of struct-of-arrays planes the kernel writes one clamped 128-byte tgx_goal_record per sample (the
-// consumer side of SURVEY.md §8 f3 fused into the evaluation: 128 B written per sample instead of 112 + 112 + 128),
-// staged through dynamic shared memory by RecStager (store.cuh).
-template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE, bool RECORDS = false>
+// consumer side of SURVEY.md §8 f3 fused into the evaluation: 128 B written per sample instead of 112 + 112 + 128).
+// The tile is walked in PASSES passes of THREADS*SPT samples; in a pass a warp owns 32*SPT consecutive samples, lane l
+// the samples l, l + 32, ... of them, stages whole records in its private part of dynamic shared memory and sends them
+// with TMA (RecTma, store.cuh).
+template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE, bool RECORDS = false, int PASSES = 1>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 6)
-eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a, RecOut ro = RecOut{}) {
+eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a,
+            const __grid_constant__ RecOut ro = RecOut{}) {
+    static_assert(RECORDS || PASSES == 1, "only the record mode walks a tile in passes");
     constexpr bool SLAB = MODE == 1;
+    constexpr int TILE = THREADS * SPT * PASSES;
+    constexpr int KS = RECORDS ? 32 : 1;          // distance between a thread's samples
     extern __shared__ __align__(16) double2 s_dyn[];
     __shared__ __align__(16) TrajRec s_rec;
     __shared__ __align__(16) Seg s_seg[kMaxSegPerTile];
@@ -142,7 +148,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
         __shared__ __align__(16) tgx_params s_par;
         __shared__ __align__(16) PhaseRec s_phr;
         traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
-        k_lo = ((int)blockIdx.x - traj * tv.tile_slab) * (THREADS * SPT);
+        k_lo = ((int)blockIdx.x - traj * tv.tile_slab) * TILE;
 #ifdef TGX_EXPERIMENT_SAMEPACKET
         const int4* ppar = reinterpret_cast<const int4*>(tv.params);      // bandwidth experiment: no DRAM reads
         const int4* pphr = reinterpret_cast<const int4*>(tv.phase);
@@ -239,21 +245,40 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 
     const int type = s_rec.type & kRecTypeMask;
     const int n = s_rec.n;
-    const int k0 = k_lo + SPT * (int)threadIdx.x;
     int limit = n;
     if (STORE && out.capacity < (int64_t)limit) limit = (int)out.capacity;
     if (RECORDS && ro.capacity < (int64_t)limit) limit = (int)ro.capacity;
-    const int nvalid = (REDUCE ? n : limit) - k0;   // samples this thread evaluates (may be <= 0)
 
     double best_v2 = 0.0, best_a2 = 0.0;
 
-    // RECORDS: every lane of a warp takes part in streaming the warp's records, so lanes beyond the trajectory's end
+    RecTma<SPT> stager;
+    if (RECORDS) {
+        // the warp's private staging area: 32*SPT records, 1024-byte aligned for the 128-byte swizzle
+        const uint32_t dyn = ((uint32_t)__cvta_generic_to_shared(s_dyn) + 1023u) & ~1023u;
+        stager.init(dyn + (uint32_t)(threadIdx.x >> 5) * (uint32_t)RecTma<SPT>::kBytesPerWarp, (int)threadIdx.x & 31);
+    }
+
+#pragma unroll 1
+    for (int pass = 0; pass < PASSES; ++pass) {
+    // first sample of this warp's block of 32*SPT (RECORDS) and of this thread
+    const int wk0 = k_lo + pass * (THREADS * SPT) + ((int)threadIdx.x >> 5) * (32 * SPT);
+    const int k0 = RECORDS ? wk0 + ((int)threadIdx.x & 31) : k_lo + SPT * (int)threadIdx.x;
+    const int nvalid = (REDUCE ? n : limit) - k0;   // samples this thread evaluates (may be <= 0)
+
+    // RECORDS: every lane of a warp takes part in staging the warp's records, so lanes beyond the trajectory's end
     // walk through the block too (what they stage is never written)
     // (SPT = 2: the thread that owns the second half of the row's last sector zero-fills it, so it enters too)
-    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0 || (STORE && k0 < ((limit + (kFillAlign - 1)) & ~(kFillAlign - 1))))) {
+    if (RECORDS ? (wk0 < limit) : (nvalid > 0 || (STORE && k0 < ((limit + (kFillAlign - 1)) & ~(kFillAlign - 1))))) {
         // ---- segment of each sample: count the segments that end before it (independent broadcast reads) ----
         int si[SPT];
-        {
+        if (RECORDS) {
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) {
+                int c = 0;
+                for (int i = 0; i + 1 < nseg; ++i) c += (k0 + u * KS > s_kend[i]) ? 1 : 0;
+                si[u] = c;
+            }
+        } else {
             int c = 0;
             for (int i = 0; i + 1 < nseg; ++i) c += (k0 > s_kend[i]) ? 1 : 0;
             si[0] = c;
@@ -276,23 +301,21 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
         }
         const uint32_t mask = out.channel_mask;
         const int64_t cs = out.chan_stride;
-        RecStager<THREADS, SPT> stager;
-        tgx_goal_record* rec_row = nullptr;
+        int64_t rec_off = 0;
         if (RECORDS) {
-            stager.init(s_dyn, (int)threadIdx.x);
-            rec_row = ro.base + (ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride);
-            stager.bind(rec_row, k0, limit);
+            rec_off = ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride;
+            if (pass > 0) stager.wait_read();      // the previous pass's records have left the staging area
+            stager.begin_pass();
         }
-        // Channels are emitted in tgx_channel order (the record stager pairs 2c with 2c+1); the record's first half
-        // leaves after channel 7 (a.y), the second after the trailing words.
+        // Channels are emitted in tgx_channel order (the record stager pairs 2c with 2c+1); the warp's records leave
+        // after the trailing words.
 #define TGX_STORE(CH, ARR)                                                                     \
     do {                                                                                       \
         if (RECORDS) {                                                                         \
             stager.template put<(CH)>(ARR, ro);                                                \
-            if ((CH) == TGX_AY) stager.flush(0, rec_row, k_lo, limit);                         \
             if ((CH) == TGX_DPSI) {                                                            \
                 stager.put_tail(traj, k0, n);                                                  \
-                stager.flush(1, rec_row, k_lo, limit);                                         \
+                stager.flush(&ro.tmap, ro.base + rec_off, rec_off, wk0, limit);                \
             }                                                                                  \
         } else if (STORE && nfill > 0 && (mask & (1u << (CH)))) {                              \
             store_channel<SPT>(row + (CH) * cs, ARR, nst, nfill);                              \
@@ -311,7 +334,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 #pragma unroll
             for (int u = 0; u < SPT; ++u) {
                 const Seg& sg = s_seg[si[u]];
-                v[u] = seg_pos(sg, k0 + u).v;
+                v[u] = seg_pos(sg, k0 + u * KS).v;
                 acc[u] = sg.acc;
             }
 #pragma unroll
@@ -364,7 +387,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 #pragma unroll
             for (int u = 0; u < SPT; ++u) {
                 const Seg& sg = s_seg[si[u]];
-                const SegPos q = seg_pos(sg, k0 + u);
+                const SegPos q = seg_pos(sg, k0 + u * KS);
                 v[u] = q.v;
                 acc[u] = (q.j == 0) ? 0.0 : sg.acc;   // sample 0 is createLineGoal(A.x, A.y, 0, accel = 0, theta) (:40)
                 // S = sum of v over the segment's steps so far; p = p_base + S * (c|s) * dt   (:97-98)
@@ -414,7 +437,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 #pragma unroll
             for (int u = 0; u < SPT; ++u) {
                 const Seg& sg = s_seg[si[u]];
-                const SegPos q = seg_pos(sg, k0 + u);
+                const SegPos q = seg_pos(sg, k0 + u * KS);
                 v[u] = q.v;
                 // theta_b + sum_{m<=j} (v_m / r) * dt  =  theta_b + j*w1 + j(j+1)/2 * (dv*dt/r); a hold (dv = 0) is the
                 // reference's exact arithmetic progression; a segment's last sample carries the replayed theta.
@@ -522,6 +545,8 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
         }
 #undef TGX_STORE
     }
+    }   // pass
+    if (RECORDS) stager.wait_read();               // the TMA unit must have read the staging area before the CTA exits
 
     if (REDUCE) {
         // ---- per-trajectory max |v|, max |a|: warp shuffles -> shared -> one atomicMax per tile ------------
@@ -596,10 +621,12 @@ cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int
     return cudaErrorInvalidConfiguration;
 }
 
-template <int THREADS, int SPT, int MODE>
+// Record mode: 2 samples per thread per pass, TILE / (2 * THREADS) passes.
+template <int THREADS, int TILE, int MODE>
 static cudaError_t launch_eval_records_t(const TableView& tv, int64_t ntiles, const RecOut& ro, cudaStream_t stream) {
-    auto kernel = eval_kernel<THREADS, SPT, false, false, MODE, true>;
-    const int smem = 4 * SPT * THREADS * (int)sizeof(double2);     // one 64-byte half of every record of the tile
+    constexpr int SPP = 2;
+    auto kernel = eval_kernel<THREADS, SPP, false, false, MODE, true, TILE / (SPP * THREADS)>;
+    const int smem = (THREADS / 32) * RecTma<SPP>::kBytesPerWarp + 1024;   // whole records + alignment slack
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kernel<<<(unsigned)ntiles, THREADS, smem, stream>>>(tv, OutView{}, nullptr, nullptr, ro);
@@ -613,11 +640,11 @@ cudaError_t launch_eval_records(const TableView& tv, int64_t ntiles, int tile_sh
     if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int threads = (1 << tile_shift) / spt;
     const int mode = tv.phase ? 2 : (tv.tile_slab > 0 ? 1 : 0);
-#define TGX_CASE(T, S)                                                                      \
-    if (threads == (T) && spt == (S))                                                       \
-        return mode == 2   ? launch_eval_records_t<T, S, 2>(tv, ntiles, ro, stream)         \
-               : mode == 1 ? launch_eval_records_t<T, S, 1>(tv, ntiles, ro, stream)         \
-                           : launch_eval_records_t<T, S, 0>(tv, ntiles, ro, stream)
+#define TGX_CASE(T, S)                                                                          \
+    if (threads == (T) && spt == (S))                                                           \
+        return mode == 2   ? launch_eval_records_t<T, (T) * (S), 2>(tv, ntiles, ro, stream)     \
+               : mode == 1 ? launch_eval_records_t<T, (T) * (S), 1>(tv, ntiles, ro, stream)     \
+                           : launch_eval_records_t<T, (T) * (S), 0>(tv, ntiles, ro, stream)
     TGX_CASE(128, 4);
     TGX_CASE(256, 2);
     TGX_CASE(256, 4);

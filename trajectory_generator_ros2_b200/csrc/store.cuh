@@ -217,5 +217,108 @@ struct RecStager {
 };
 #endif
 
+// ---- record output through TMA (eval.cu) ---------------------------------------------------------------------
+// In record mode a thread does not own adjacent samples but samples 32 apart: in every pass a warp owns 32*SPT
+// CONSECUTIVE samples (lane l: wk0 + l, wk0 + 32 + l, ...), so what the warp stages is already in record order.  Each
+// lane writes its samples' 16 doubles as eight 16-byte chunks into the warp's private staging area, laid out exactly as
+// TMA's 128-byte swizzle wants it (record row ri at ri*128, chunk c at ((c ^ (ri & 7)) << 4); the area is 1024-byte
+// aligned): a quarter-warp of writers (8 consecutive lanes, one chunk index) hits 8 different 16-byte bank groups, so the
+// st.shared.v2.f64 are conflict-free.  One elected lane then hands each group of 32 records (4 KiB, contiguous in
+// global memory) to the TMA unit with cp.async.bulk.tensor: no LDS read-back and no STG — the staged bytes cross the
+// L1/shared pipe once instead of three times, which was the limiter of the LDS + STG stager above (L1TEX 87 % busy at
+// 4.7 TB/s).  Only the group that straddles the row's limit (at most one per trajectory) leaves through LDS + STG, since
+// a TMA box cannot be cut at an arbitrary record.  Everything is warp-private: __syncwarp only, no CTA barrier.
+template <int SPT>
+struct RecTma {
+    static constexpr int kBytesPerWarp = 32 * SPT * 128;
+    uint32_t sbase;            // shared-window address of this warp's staging area (1024-byte aligned)
+    int lane;
+    double pend[SPT];          // the even channel of the open pair
+    unsigned clamped[SPT];     // bit 0 / 1 / 2: p.x / p.y / p.z was saturated
+
+    __device__ __forceinline__ void init(uint32_t warp_area, int lane_) {
+        sbase = warp_area;
+        lane = lane_;
+    }
+    __device__ __forceinline__ void begin_pass() {
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) clamped[u] = 0;
+    }
+    // TrajectoryGenerator::saturate (:773-780): high is tested first, a NaN passes through.
+    __device__ __forceinline__ double sat(double v, double lo, double hi, unsigned bit, unsigned& flags) {
+        if (v > hi) { flags |= bit; return hi; }
+        if (v < lo) { flags |= bit; return lo; }
+        return v;
+    }
+    __device__ __forceinline__ void st_chunk(int u, int c, double a, double b) {
+        // row u*32 + lane: (row & 7) == (lane & 7)
+        const uint32_t addr = sbase + (uint32_t)((u * 32 + lane) * 128 + ((c ^ (lane & 7)) << 4));
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+    }
+    // Channels must arrive in tgx_channel order.
+    template <int CH>
+    __device__ __forceinline__ void put(const double (&x)[SPT], const RecOut& ro) {
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            double y = x[u];
+            if (CH <= TGX_PZ && ro.clamp) y = sat(x[u], ro.box[2 * CH], ro.box[2 * CH + 1], 1u << CH, clamped[u]);
+            if ((CH & 1) == 0) pend[u] = y;
+            else st_chunk(u, CH >> 1, pend[u], y);
+        }
+    }
+    // The two trailing words of the record (chunk 7): {traj, k}, {power, modes, clamped, last}.  k of sample u = k0 + 32u.
+    __device__ __forceinline__ void put_tail(int traj, int k0, int n) {
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            const int k = k0 + 32 * u;
+            const unsigned long long w0 = (unsigned long long)(unsigned)traj | ((unsigned long long)(unsigned)k << 32);
+            const unsigned long long w1 = 1ull | ((unsigned long long)clamped[u] << 24) |
+                                          ((unsigned long long)(k == n - 1 ? 1 : 0) << 32);
+            st_chunk(u, 7, __longlong_as_double((long long)w0), __longlong_as_double((long long)w1));
+        }
+    }
+    // Send the warp's staged records: row = the trajectory's first record, grow = its index in the record buffer,
+    // wk0 = the first sample the warp staged; samples >= limit are not written.  All 32 lanes must call it.
+    __device__ __forceinline__ void flush(const CUtensorMap* tmap, tgx_goal_record* row, int64_t grow, int wk0,
+                                          int limit) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async-proxy reads
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            const int kg = wk0 + 32 * u;                                 // warp-uniform
+            if (kg + 32 <= limit) {
+                if (lane == 0) {
+                    const int c1 = (int)(grow + kg);
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                     reinterpret_cast<uint64_t>(tmap)),
+                                 "r"(0), "r"(c1), "r"(sbase + (uint32_t)(u * 4096))
+                                 : "memory");
+                }
+            } else if (kg < limit) {
+                // the group that straddles the limit: 32 rows x 8 chunks through LDS + STG, lane = (row mod 4, chunk)
+                const int c = lane & 7;
+                double2* out = reinterpret_cast<double2*>(row);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + (lane >> 3);
+                    if (kg + r < limit) {
+                        const uint32_t addr = sbase + (uint32_t)((u * 32 + r) * 128 + ((c ^ (r & 7)) << 4));
+                        double a, b;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr) : "memory");
+                        asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(out + (int64_t)(kg + r) * 8 + c), "d"(a),
+                                     "d"(b) : "memory");
+                    }
+                }
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // The staging area may be rewritten (or the CTA may exit) once the TMA unit has READ it.
+    __device__ __forceinline__ void wait_read() {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+    }
+};
+
 }  // namespace
 }  // namespace tgx

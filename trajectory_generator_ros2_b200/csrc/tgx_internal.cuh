@@ -17,6 +17,8 @@
 
 #include <cstdint>
 
+#include <cuda.h>   // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+
 #include "../../include/tgx.h"
 
 namespace tgx {
@@ -183,8 +185,11 @@ struct OutView {
     uint32_t channel_mask;
 };
 
-// Where the evaluation kernels write array-of-structs records (tgx_eval_records): see RecStager in store.cuh.
+// Where the evaluation kernels write array-of-structs records (tgx_eval_records): see RecStager / RecTma in store.cuh.
+// tmap: the record buffer as a 2-D tensor [rows = records][16 doubles], box = 32 records, 128-byte swizzle — the
+// TMA descriptor eval_kernel's warps store their staged records through (filled by tgx_eval_records on the host).
 struct RecOut {
+    alignas(64) CUtensorMap tmap;
     tgx_goal_record* base;
     int64_t stride;            // records per trajectory (ignored when offset != nullptr)
     const int64_t* offset;     // optional per-trajectory record offsets
