@@ -905,13 +905,12 @@ int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d
     if (ro.clamp)
         for (int i = 0; i < 6; ++i) ro.box[i] = limits->box[i];
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (e->plan_poly) {
+    const int rc = make_record_tmap(&ro.tmap, d_records);
+    if (rc) return rc;
+    if (e->plan_poly)
         TGX_CUDA(tgx::launch_eval_poly_records(poly_view(e), e->plan_tiles, e->tile_shift, e->spt, ro, s));
-    } else {
-        const int rc = make_record_tmap(&ro.tmap, d_records);
-        if (rc) return rc;
+    else
         TGX_CUDA(tgx::launch_eval_records(table_view(e), e->plan_tiles, e->tile_shift, e->spt, ro, s));
-    }
     e->launches += 1;
     return TGX_OK;
 }

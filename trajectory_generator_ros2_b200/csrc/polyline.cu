@@ -419,11 +419,16 @@ poly_tiles_kernel(int64_t n, const int32_t* __restrict__ ntile, const int64_t* _
 // modulo to find the position in the period, a scan over <= 10 leg lengths in shared memory, one correctly rounded
 // division and two multiply-add pairs WITHOUT contraction (the reference's `start + frac * (end - start)` is two
 // roundings per coordinate).  No transcendental on the per-sample path: heading, cos and sin are per leg.
-template <int THREADS, int SPT, bool STORE, bool REDUCE, bool RECORDS = false>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 6)
+// RECORDS: the tile is walked in PASSES passes of THREADS*SPT samples; in a pass a warp owns 32*SPT consecutive samples
+// (lane l: l, l + 32, ...), stages whole records and sends them with TMA (RecTma, store.cuh), as eval.cu does.
+template <int THREADS, int SPT, bool STORE, bool REDUCE, bool RECORDS = false, int PASSES = 1>
+__global__ void __launch_bounds__(THREADS, 768 / THREADS)
 eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a,
-                 RecOut ro = RecOut{}) {
-    extern __shared__ __align__(16) double2 s_dyn[];      // RECORDS: the record stager's transpose buffer (store.cuh)
+                 const __grid_constant__ RecOut ro = RecOut{}) {
+    static_assert(RECORDS || PASSES == 1, "only the record mode walks a tile in passes");
+    constexpr int TILE = THREADS * SPT * PASSES;
+    constexpr int KS = RECORDS ? 32 : 1;                  // distance between a thread's samples
+    extern __shared__ __align__(16) double2 s_dyn[];      // RECORDS: the warps' record staging areas (store.cuh)
     __shared__ __align__(16) int4 s_raw[4 * kPolyRecs];
     __shared__ double s_red[THREADS / 32];
 
@@ -434,7 +439,7 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
         k_lo = tw.y;
     } else {
         traj = (int)(blockIdx.x / (unsigned)pv.tile_slab);
-        k_lo = ((int)blockIdx.x - traj * pv.tile_slab) * (THREADS * SPT);
+        k_lo = ((int)blockIdx.x - traj * pv.tile_slab) * TILE;
     }
     if (threadIdx.x < 4 * kPolyRecs) s_raw[threadIdx.x] = __ldg(pv.recs + (size_t)traj * (4 * kPolyRecs) + threadIdx.x);
     __syncthreads();
@@ -443,33 +448,52 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
     const int n = hd.n;
     if (k_lo >= n) return;                                            // an empty slot (whole CTA)
 
-    const int k0 = k_lo + SPT * (int)threadIdx.x;
     int limit = n;
     if (STORE && out.capacity < (int64_t)limit) limit = (int)out.capacity;
     if (RECORDS && ro.capacity < (int64_t)limit) limit = (int)ro.capacity;
-    const int nvalid = (REDUCE ? n : limit) - k0;
     double best_v2 = 0.0;
 
-    // RECORDS: all 32 lanes of a warp with any sample to write take part in streaming the warp's records
-    if (RECORDS ? (k_lo + ((int)threadIdx.x & ~31) * SPT < limit) : (nvalid > 0 || (STORE && k0 < ((limit + (kFillAlign - 1)) & ~(kFillAlign - 1))))) {
+    RecTma<SPT> stager;
+    if (RECORDS) {
+        if ((threadIdx.x & 31) == 0)
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ro.tmap)) : "memory");
+        // the warp's private staging area: 32*SPT records, 1024-byte aligned for the 128-byte swizzle
+        const uint32_t dyn = ((uint32_t)__cvta_generic_to_shared(s_dyn) + 1023u) & ~1023u;
+        stager.init(dyn + (uint32_t)(threadIdx.x >> 5) * (uint32_t)RecTma<SPT>::kBytesPerWarp, (int)threadIdx.x & 31);
+    }
+
+#pragma unroll 1
+    for (int pass = 0; pass < PASSES; ++pass) {
+    // first sample of this warp's block of 32*SPT (RECORDS) and of this thread
+    const int wk0 = k_lo + pass * (THREADS * SPT) + ((int)threadIdx.x >> 5) * (32 * SPT);
+    const int k0 = RECORDS ? wk0 + ((int)threadIdx.x & 31) : k_lo + SPT * (int)threadIdx.x;
+    const int nvalid = (REDUCE ? n : limit) - k0;
+
+    // RECORDS: all 32 lanes of a warp with any sample to write take part in staging the warp's records
+    if (RECORDS ? (wk0 < limit) : (nvalid > 0 || (STORE && k0 < ((limit + (kFillAlign - 1)) & ~(kFillAlign - 1))))) {
         const int first = hd.first_special, n_legs = hd.n_legs;
         const bool bounce = hd.type == TGX_BOUNCE;
-        // position of sample max(k0, first) in the period: leg l, step i
-        int m = k0 - first;
-        if (m < 0) m = 0;
-        int cyc = (int)((unsigned)m % (unsigned)hd.period);
-        int l = 0;
-        for (; l + 1 < n_legs; ++l) {
-            const int c = legs[kPolySlotLeg0 + l].steps + 1 - legs[kPolySlotLeg0 + l].i0;
-            if (cyc < c) break;
-            cyc -= c;
-        }
-        int i = legs[kPolySlotLeg0 + l].i0 + cyc;
+        // position of sample max(k, first) in the period: leg l, step i
+        int l, i;
+        auto locate = [&](int k) {
+            int m = k - first;
+            if (m < 0) m = 0;
+            int cyc = (int)((unsigned)m % (unsigned)hd.period);
+            l = 0;
+            for (; l + 1 < n_legs; ++l) {
+                const int c = legs[kPolySlotLeg0 + l].steps + 1 - legs[kPolySlotLeg0 + l].i0;
+                if (cyc < c) break;
+                cyc -= c;
+            }
+            i = legs[kPolySlotLeg0 + l].i0 + cyc;
+        };
+        locate(k0);
 
         double px[SPT], py[SPT], vx[SPT], vy[SPT], psi[SPT];
 #pragma unroll
         for (int u = 0; u < SPT; ++u) {
-            const int k = k0 + u;
+            const int k = k0 + u * KS;
+            if (RECORDS && u > 0) locate(k);                                      // the thread's samples are 32 apart
             const bool sp_first = first && k == 0;
             const bool sp_last = hd.last_special && k == n - 1;
             const int slot = sp_first ? kPolySlotFirst : (sp_last ? kPolySlotLast : kPolySlotLeg0 + l);
@@ -501,21 +525,20 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
         }
         const uint32_t mask = out.channel_mask;
         const int64_t cs = out.chan_stride;
-        RecStager<THREADS, SPT> stager;
-        tgx_goal_record* rec_row = nullptr;
+        int64_t rec_off = 0;
         if (RECORDS) {
-            stager.init(s_dyn, (int)threadIdx.x);
-            rec_row = ro.base + (ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride);
-            stager.bind(rec_row, k0, limit);
+            rec_off = ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride;
+            stager.begin_pass();
         }
 #define TGX_STORE(CH, ARR)                                                                                \
     do {                                                                                                  \
         if (RECORDS) {                                                                                    \
+            /* the previous pass's records must have left the staging area before the first write */     \
+            if ((CH) == TGX_PX && pass > 0) stager.wait_read();                                           \
             stager.template put<(CH)>(ARR, ro);                                                           \
-            if ((CH) == TGX_AY) stager.flush(0, rec_row, k_lo, limit);                                    \
             if ((CH) == TGX_DPSI) {                                                                       \
                 stager.put_tail(traj, k0, n);                                                             \
-                stager.flush(1, rec_row, k_lo, limit);                                                    \
+                stager.flush(&ro.tmap, ro.base + rec_off, rec_off, wk0, limit);                           \
             }                                                                                             \
         } else if (STORE && nfill > 0 && (mask & (1u << (CH)))) {                                         \
             store_channel<SPT>(row + (CH) * cs, ARR, nst, nfill);                                         \
@@ -562,6 +585,8 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
                 if (u < nvalid) best_v2 = fmax(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
         }
     }
+    }   // pass
+    if (RECORDS) stager.wait_read();               // the TMA unit must have read the staging area before the CTA exits
 
     if (REDUCE) {
         best_v2 = warp_max(best_v2);
@@ -615,11 +640,13 @@ static cudaError_t launch_eval_poly_t(const PolyView& pv, int64_t ntiles, const 
     return cudaGetLastError();
 }
 
-template <int THREADS, int SPT>
+// Record mode: 2 samples per thread per pass, TILE / (2 * THREADS) passes.
+template <int THREADS, int TILE>
 static cudaError_t launch_eval_poly_records_t(const PolyView& pv, int64_t ntiles, const RecOut& ro,
                                               cudaStream_t stream) {
-    auto kernel = eval_poly_kernel<THREADS, SPT, false, false, true>;
-    const int smem = 4 * SPT * THREADS * (int)sizeof(double2);
+    constexpr int SPP = 2;
+    auto kernel = eval_poly_kernel<THREADS, SPP, false, false, true, TILE / (SPP * THREADS)>;
+    const int smem = (THREADS / 32) * RecTma<SPP>::kBytesPerWarp + 1024;   // whole records + alignment slack
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kernel<<<(unsigned)ntiles, THREADS, smem, stream>>>(pv, OutView{}, nullptr, nullptr, ro);
@@ -630,10 +657,10 @@ cudaError_t launch_eval_poly_records(const PolyView& pv, int64_t ntiles, int til
                                      cudaStream_t stream) {
     if (ntiles <= 0) return cudaSuccess;
     if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    const int threads = (1 << tile_shift) / spt;
-    if (threads == 128 && spt == 4) return launch_eval_poly_records_t<128, 4>(pv, ntiles, ro, stream);
-    if (threads == 256 && spt == 2) return launch_eval_poly_records_t<256, 2>(pv, ntiles, ro, stream);
-    if (threads == 256 && spt == 4) return launch_eval_poly_records_t<256, 4>(pv, ntiles, ro, stream);
+    (void)spt;                 // record kernels: always 128 threads walking the tile in passes of 256 samples (eval.cu)
+    const int tile = 1 << tile_shift;
+    if (tile == 512) return launch_eval_poly_records_t<128, 512>(pv, ntiles, ro, stream);
+    if (tile == 1024) return launch_eval_poly_records_t<128, 1024>(pv, ntiles, ro, stream);
     return cudaErrorInvalidConfiguration;
 }
 

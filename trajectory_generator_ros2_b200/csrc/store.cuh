@@ -84,140 +84,11 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double x) {
 }
 
 // ---- record output (fused): one 128-byte tgx_goal_record per sample straight from the evaluation
-// kernels' registers.  A thread owns SPT adjacent samples and produces them channel by channel; the record layout wants
-// the 16 doubles of ONE sample together.  The transpose goes through shared memory one 64-byte record half at a time
-// (channels 0-7, then 8-13 + the two trailing words): chunk c (16 bytes = channels 2c, 2c+1) of sample u of thread t
-// is staged at 16-byte index (c*SPT + u)*THREADS + (t ^ (2c + (u & 1))).  The XOR keeps both sides conflict-free: a
-// quarter-warp of writers (8 consecutive t, fixed c, u) and a quarter-warp of readers (4 chunks x 2 adjacent samples
-// of one thread) each touch 8 distinct 16-byte bank groups.  Every warp then streams its OWN SPT*32 records: each store
-// instruction writes the 64-byte halves of 8 adjacent samples (full sectors), so only __syncwarp is needed.
-
-#ifdef TGX_RECORDS_DIRECT
-// Experiment: no shared-memory transpose.  Every thread writes its own samples' records as 32-byte (full-sector)
-// streaming stores, four consecutive channels at a time; a warp instruction then touches 32 different lines.
-template <int THREADS, int SPT>
-struct RecStager {
-    int t;
-    double pend[SPT][3];
-    unsigned clamped[SPT];
-    tgx_goal_record* row;
-    int k0_, limit_;
-    __device__ __forceinline__ void init(double2*, int tid) {
-        t = tid;
-#pragma unroll
-        for (int u = 0; u < SPT; ++u) clamped[u] = 0;
-    }
-    __device__ __forceinline__ double sat(double v, double lo, double hi, unsigned bit, unsigned& flags) {
-        if (v > hi) { flags |= bit; return hi; }
-        if (v < lo) { flags |= bit; return lo; }
-        return v;
-    }
-    __device__ __forceinline__ void bind(tgx_goal_record* r, int k0, int limit) { row = r; k0_ = k0; limit_ = limit; }
-    __device__ __forceinline__ void st32(int u, int quad, double a, double b, double c, double d) {
-        if (k0_ + u < limit_) {
-            double* p = reinterpret_cast<double*>(row + k0_ + u) + 4 * quad;
-            asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-        }
-    }
-    template <int CH>
-    __device__ __forceinline__ void put(const double (&x)[SPT], const RecOut& ro) {
-#pragma unroll
-        for (int u = 0; u < SPT; ++u) {
-            double y = x[u];
-            if (CH <= TGX_PZ && ro.clamp) y = sat(x[u], ro.box[2 * CH], ro.box[2 * CH + 1], 1u << CH, clamped[u]);
-            if ((CH & 3) != 3) pend[u][CH & 3] = y;
-            else st32(u, CH >> 2, pend[u][0], pend[u][1], pend[u][2], y);
-        }
-    }
-    __device__ __forceinline__ void put_tail(int traj, int k0, int n) {
-#pragma unroll
-        for (int u = 0; u < SPT; ++u) {
-            const int k = k0 + u;
-            const unsigned long long w0 = (unsigned long long)(unsigned)traj | ((unsigned long long)(unsigned)k << 32);
-            const unsigned long long w1 = 1ull | ((unsigned long long)clamped[u] << 24) |
-                                          ((unsigned long long)(k == n - 1 ? 1 : 0) << 32);
-            st32(u, 3, pend[u][0], pend[u][1], __longlong_as_double((long long)w0), __longlong_as_double((long long)w1));
-        }
-    }
-    __device__ __forceinline__ void flush(int, tgx_goal_record*, int, int) {}
-};
-#else
-template <int THREADS, int SPT>
-struct RecStager {
-    double2* s;                // 4 * SPT * THREADS chunks of dynamic shared memory
-    int t;
-    double pend[SPT];          // the even channel of the open pair
-    unsigned clamped[SPT];     // bit 0 / 1 / 2: p.x / p.y / p.z was saturated
-
-    __device__ __forceinline__ void init(double2* smem, int tid) {
-        s = smem;
-        t = tid;
-#pragma unroll
-        for (int u = 0; u < SPT; ++u) clamped[u] = 0;
-    }
-    // TrajectoryGenerator::saturate (:773-780): high is tested first, a NaN passes through.
-    __device__ __forceinline__ double sat(double v, double lo, double hi, unsigned bit, unsigned& flags) {
-        if (v > hi) { flags |= bit; return hi; }
-        if (v < lo) { flags |= bit; return lo; }
-        return v;
-    }
-    // Channels must arrive in tgx_channel order.
-    template <int CH>
-    __device__ __forceinline__ void put(const double (&x)[SPT], const RecOut& ro) {
-        double y[SPT];
-#pragma unroll
-        for (int u = 0; u < SPT; ++u) {
-            y[u] = x[u];
-            if (CH <= TGX_PZ && ro.clamp) y[u] = sat(x[u], ro.box[2 * CH], ro.box[2 * CH + 1], 1u << CH, clamped[u]);
-        }
-        if ((CH & 1) == 0) {
-#pragma unroll
-            for (int u = 0; u < SPT; ++u) pend[u] = y[u];
-        } else {
-            constexpr int c = (CH >> 1) & 3;
-#pragma unroll
-            for (int u = 0; u < SPT; ++u)
-                s[(c * SPT + u) * THREADS + (t ^ (2 * c + (u & 1)))] = make_double2(pend[u], y[u]);
-        }
-    }
-    // The two trailing words of the record (chunk 3 of the second half): {traj, k}, {power, modes, clamped, last}.
-    __device__ __forceinline__ void put_tail(int traj, int k0, int n) {
-#pragma unroll
-        for (int u = 0; u < SPT; ++u) {
-            const int k = k0 + u;
-            const unsigned long long w0 = (unsigned long long)(unsigned)traj | ((unsigned long long)(unsigned)k << 32);
-            const unsigned long long w1 = 1ull | ((unsigned long long)clamped[u] << 24) |
-                                          ((unsigned long long)(k == n - 1 ? 1 : 0) << 32);
-            s[(3 * SPT + u) * THREADS + (t ^ (6 + (u & 1)))] =
-                make_double2(__longlong_as_double((long long)w0), __longlong_as_double((long long)w1));
-        }
-    }
-    // Stream record half `half` (0: bytes 0-63, 1: bytes 64-127) of this warp's SPT*32 samples.  row = the trajectory's
-    // first record; k_lo = first sample of the tile; samples >= limit are not written.  All 32 lanes must call it.
-    __device__ __forceinline__ void flush(int half, tgx_goal_record* row, int k_lo, int limit) {
-        __syncwarp();
-        const int lane = t & 31, warp_base = t & ~31;
-        const int c = lane & 3;
-        double2* out = reinterpret_cast<double2*>(row);
-#pragma unroll
-        for (int it = 0; it < 4 * SPT; ++it) {
-            const int q = it * 8 + (lane >> 2);            // sample within the warp, adjacent samples are adjacent q
-            const int tl = q / SPT, u = q % SPT;
-            const int tt = warp_base + tl;
-            const int k = k_lo + SPT * tt + u;
-            if (k < limit) {
-                const double2 v = s[(c * SPT + u) * THREADS + (tt ^ (2 * c + (u & 1)))];
-                asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(out + (int64_t)k * 8 + half * 4 + c), "d"(v.x),
-                             "d"(v.y) : "memory");
-            }
-        }
-        __syncwarp();                                       // the staging area is reused by the next half
-    }
-    __device__ __forceinline__ void bind(tgx_goal_record*, int, int) {}
-};
-#endif
-
-// ---- record output through TMA (eval.cu) ---------------------------------------------------------------------
+// kernels (eval.cu, polyline.cu) -------------------------------------------------------------------------------
+// History: the first version kept 4 adjacent samples per thread and transposed 64-byte record halves through an
+// XOR-swizzled shared-memory buffer, each warp reading its records back with LDS and streaming them with 16-byte STG:
+// 28.4 ms per 1.05e9 samples, L1TEX 87 % busy.  A variant without shared memory (every thread writing
+// 32-byte pieces of its own records) took 32.3 ms.
 // In record mode a thread does not own adjacent samples but samples 32 apart: in every pass a warp owns 32*SPT
 // CONSECUTIVE samples (lane l: wk0 + l, wk0 + 32 + l, ...), so what the warp stages is already in record order.  Each
 // lane writes its samples' 16 doubles as eight 16-byte chunks into the warp's private staging area, laid out exactly as
