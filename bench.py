@@ -229,6 +229,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     eng = Engine(local_rank)
+    eng.set_store_path(args.store_path == "tma")
     if args.tile_shift or args.spt:
         eng.set_tuning(args.tile_shift or 10, args.spt or 4)
 
@@ -613,6 +614,8 @@ def main():
     ap.add_argument("--records", action="store_true",
                     help="also run the consumer-side kernel: clamp + pack every sample into a 128-byte record")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--store-path", default="tma", choices=["tma", "stg"],
+                    help="tgx_eval's planes through TMA (default) or through vector stores (tgx_set_store_path)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     _claim_stdout()

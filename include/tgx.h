@@ -329,6 +329,12 @@ int tgx_set_slab_planning(tgx_engine* e, int allow);
  * Engaged automatically after a plan has seen such a batch; anything else falls back to segment tables. */
 int tgx_set_phase_planning(tgx_engine* e, int allow);
 int64_t tgx_phase_plan_count(const tgx_engine* e);
+/* Store path of tgx_eval (default tma = 1): when the layout is regular (no per-trajectory offsets, all 14 channels,
+ * rows of at least 32 samples) and no maxima are requested, CTAs of 128 threads stage 32-sample groups of all 14
+ * channels in shared memory and hand each group to the TMA unit as one box of a [trajectory][channel][sample] tensor
+ * map over the caller's planes; only the group that holds a row's end uses vector stores.  tma = 0 always uses the
+ * vector-store kernel (one 256-bit streaming store per thread per channel).  Both write the same bytes. */
+int tgx_set_store_path(tgx_engine* e, int tma);
 /* How many plans so far took the single-replay / the two-replay path (either pointer may be NULL). */
 int tgx_plan_path_counts(const tgx_engine* e, int64_t* slab_plans, int64_t* exact_plans);
 /* Bytes of device scratch currently held by the engine (plan tables). */

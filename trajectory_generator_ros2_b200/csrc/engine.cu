@@ -45,7 +45,7 @@ cudaError_t launch_plan_phase(const tgx_params* params, int64_t n, const tgx_lim
                               uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
                               PlanStats* stats, cudaStream_t stream);
 cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int spt, const OutView& out, bool store,
-                        double* max_v, double* max_a, cudaStream_t stream);
+                        double* max_v, double* max_a, cudaStream_t stream, const RecOut* ptma = nullptr);
 cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, const double* max_v,
                                         const double* max_a, double v_max, double a_max, uint8_t* flags,
                                         uint32_t* status_out, cudaStream_t stream);
@@ -205,6 +205,7 @@ struct tgx_engine {
     bool plan_phase = false;                     // current plan is a phase plan
     const tgx_params* plan_params = nullptr;     // phase plans read the caller's parameter array during evaluation
     bool allow_phase = true;
+    bool plane_tma = true;              // tgx_eval may send the planes through TMA (tgx_set_store_path)
     bool phase_ready = false;
     int phase_tile_slab = 0;
     int64_t phase_plans = 0;
@@ -552,10 +553,46 @@ tgx::PolyView poly_view(const tgx_engine* e) {
 
 // Evaluation of the current plan, whichever family planned it.
 cudaError_t launch_current(const tgx_engine* e, const tgx::OutView& out, bool store, double* max_v, double* max_a,
-                           cudaStream_t s) {
+                           cudaStream_t s, const tgx::RecOut* ptma = nullptr) {
     if (e->plan_poly)
         return tgx::launch_eval_poly(poly_view(e), e->plan_tiles, e->tile_shift, e->spt, out, store, max_v, max_a, s);
-    return tgx::launch_eval(table_view(e), e->plan_tiles, e->tile_shift, e->spt, out, store, max_v, max_a, s);
+    return tgx::launch_eval(table_view(e), e->plan_tiles, e->tile_shift, e->spt, out, store, max_v, max_a, s, ptma);
+}
+
+// cuTensorMapEncodeTiled lives in libcuda; it is looked up through the runtime so libtgx.so needs no -lcuda.
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<tmap_encode_fn>(fn);
+    }
+    return encode;
+}
+
+// The caller's planes as TMA sees them: a 3-D fp64 tensor [trajectory][channel][sample] with the layout's strides,
+// written in boxes of {32 samples, 14 channels, 1 trajectory} (PlaneTma in store.cuh).  Returns false when the layout
+// does not qualify (per-trajectory offsets, a channel subset, rows shorter than a box, strides TMA cannot express): the
+// vector-store kernel handles those.
+bool make_plane_tmap(CUtensorMap* tmap, const tgx_layout* out, int64_t n) {
+    tmap_encode_fn encode = tmap_encoder();
+    if (!encode || out->d_traj_offset || n <= 0 || out->capacity < 32) return false;
+    if (out->channel_mask && (out->channel_mask & 0x3fffu) != 0x3fffu) return false;
+    if (out->traj_stride <= 0 || out->chan_stride <= 0) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)out->capacity, TGX_NCHAN, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)out->chan_stride * 8, (cuuint64_t)out->traj_stride * 8};
+    if (dims[0] > 0xffffffffull || dims[2] > 0x7fffffffull || strides[0] >= (1ull << 40) || strides[1] >= (1ull << 40))
+        return false;
+    const cuuint32_t box[3] = {32, TGX_NCHAN, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, out->d_base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int check_layout(const tgx_layout* out, int spt) {
@@ -714,6 +751,14 @@ int tgx_set_phase_planning(tgx_engine* e, int allow) {
 
 int64_t tgx_phase_plan_count(const tgx_engine* e) { return e ? e->phase_plans : 0; }
 
+// Store path of tgx_eval: tma = 1 (default) sends the planes of a qualifying layout through TMA, 0 always uses the
+// vector-store kernel.  Results are bit-identical.
+int tgx_set_store_path(tgx_engine* e, int tma) {
+    if (!e) return TGX_ERR_INVALID;
+    e->plane_tma = tma != 0;
+    return TGX_OK;
+}
+
 // How many plans so far took the single-replay / the two-replay path.
 int tgx_plan_path_counts(const tgx_engine* e, int64_t* slab_plans, int64_t* exact_plans) {
     if (!e) return TGX_ERR_INVALID;
@@ -827,7 +872,9 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
     if (d_max_v) TGX_CUDA(cudaMemsetAsync(d_max_v, 0, (size_t)e->plan_n * sizeof(double), s));
     if (d_max_a) TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)e->plan_n * sizeof(double), s));
     if (e->plan_tiles == 0) return TGX_OK;
-    TGX_CUDA(launch_current(e, make_view(out), true, d_max_v, d_max_a, s));
+    tgx::RecOut ptma{};
+    const bool tma = e->plane_tma && !e->plan_poly && !d_max_v && !d_max_a && make_plane_tmap(&ptma.tmap, out, e->plan_n);
+    TGX_CUDA(launch_current(e, make_view(out), true, d_max_v, d_max_a, s, tma ? &ptma : nullptr));
     e->launches += 1;
     return TGX_OK;
 }
@@ -865,20 +912,9 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
 // The record buffer as TMA sees it: a 2-D fp64 tensor [records][16], one 128-byte row per record, written in boxes of
 // 32 records with the 128-byte shared-memory swizzle (RecTma in store.cuh stages in exactly that layout).  The outer
 // extent is the coordinate range, not the allocation: the kernel only issues boxes that lie inside a trajectory's row.
-// The encoder lives in libcuda; it is looked up through the runtime so libtgx.so needs no -lcuda.
 static int make_record_tmap(CUtensorMap* tmap, tgx_goal_record* d_records) {
-    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
-            q != cudaDriverEntryPointSuccess)
-            return TGX_ERR_CUDA;
-        encode = reinterpret_cast<encode_fn>(fn);
-    }
+    tmap_encode_fn encode = tmap_encoder();
+    if (!encode) return TGX_ERR_CUDA;
     const cuuint64_t dims[2] = {16, (cuuint64_t)1 << 31};
     const cuuint64_t strides[1] = {sizeof(tgx_goal_record)};
     const cuuint32_t box[2] = {16, 32};

@@ -127,14 +127,19 @@ __device__ void build_phase_segment(const tgx_params& par, const PhaseRec& phr, 
 // The tile is walked in PASSES passes of THREADS*SPT samples; in a pass a warp owns 32*SPT consecutive samples, lane l
 // the samples l, l + 32, ... of them, stages whole records in its private part of dynamic shared memory and sends them
 // with TMA (RecTma, store.cuh).
-template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE, bool RECORDS = false, int PASSES = 1>
+// PTMA: the struct-of-arrays planes leave through TMA as well (PlaneTma, store.cuh): same passes and sample ownership as
+// the record mode, ro.tmap then describes the caller's planes as a [trajectory][channel][sample] tensor.
+template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE, bool RECORDS = false, int PASSES = 1,
+          bool PTMA = false>
 __global__ void __launch_bounds__(THREADS, 768 / THREADS)
 eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a,
             const __grid_constant__ RecOut ro = RecOut{}) {
-    static_assert(RECORDS || PASSES == 1, "only the record mode walks a tile in passes");
+    constexpr bool STAGED = RECORDS || PTMA;       // samples staged in shared memory and sent by TMA
+    static_assert(STAGED || PASSES == 1, "only the TMA modes walk a tile in passes");
+    static_assert(!PTMA || (STORE && !REDUCE && !RECORDS), "PTMA is the plain store-only evaluation");
     constexpr bool SLAB = MODE == 1;
     constexpr int TILE = THREADS * SPT * PASSES;
-    constexpr int KS = RECORDS ? 32 : 1;          // distance between a thread's samples
+    constexpr int KS = STAGED ? 32 : 1;           // distance between a thread's samples
     extern __shared__ __align__(16) double2 s_dyn[];
     __shared__ __align__(16) TrajRec s_rec;
     __shared__ __align__(16) Seg s_seg[kMaxSegPerTile];
@@ -252,28 +257,37 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     double best_v2 = 0.0, best_a2 = 0.0;
 
     RecTma<SPT> stager;
+    PlaneTma<SPT> pstager;
+    if (STAGED && (threadIdx.x & 31) == 0)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ro.tmap)) : "memory");
     if (RECORDS) {
-        if ((threadIdx.x & 31) == 0)
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ro.tmap)) : "memory");
         // the warp's private staging area: 32*SPT records, 1024-byte aligned for the 128-byte swizzle
         const uint32_t dyn = ((uint32_t)__cvta_generic_to_shared(s_dyn) + 1023u) & ~1023u;
         stager.init(dyn + (uint32_t)(threadIdx.x >> 5) * (uint32_t)RecTma<SPT>::kBytesPerWarp, (int)threadIdx.x & 31);
+    }
+    // the row's last 32-byte sector is completed with zeros when it lies inside the row's capacity
+    int fill_end = limit;
+    if (PTMA) {
+        const uint32_t dyn = ((uint32_t)__cvta_generic_to_shared(s_dyn) + 127u) & ~127u;
+        pstager.init(dyn + (uint32_t)(threadIdx.x >> 5) * (uint32_t)PlaneTma<SPT>::kBytesPerWarp, (int)threadIdx.x & 31);
+        const int64_t lim4 = ((int64_t)limit + (kFillAlign - 1)) & ~(int64_t)(kFillAlign - 1);
+        if (lim4 <= out.capacity) fill_end = (int)lim4;
     }
 
 #pragma unroll 1
     for (int pass = 0; pass < PASSES; ++pass) {
     // first sample of this warp's block of 32*SPT (RECORDS) and of this thread
     const int wk0 = k_lo + pass * (THREADS * SPT) + ((int)threadIdx.x >> 5) * (32 * SPT);
-    const int k0 = RECORDS ? wk0 + ((int)threadIdx.x & 31) : k_lo + SPT * (int)threadIdx.x;
+    const int k0 = STAGED ? wk0 + ((int)threadIdx.x & 31) : k_lo + SPT * (int)threadIdx.x;
     const int nvalid = (REDUCE ? n : limit) - k0;   // samples this thread evaluates (may be <= 0)
 
     // RECORDS: every lane of a warp takes part in staging the warp's records, so lanes beyond the trajectory's end
     // walk through the block too (what they stage is never written)
     // (SPT = 2: the thread that owns the second half of the row's last sector zero-fills it, so it enters too)
-    if (RECORDS ? (wk0 < limit) : (nvalid > 0 || (STORE && k0 < ((limit + (kFillAlign - 1)) & ~(kFillAlign - 1))))) {
+    if (STAGED ? (wk0 < (PTMA ? fill_end : limit)) : (nvalid > 0 || (STORE && k0 < ((limit + (kFillAlign - 1)) & ~(kFillAlign - 1))))) {
         // ---- segment of each sample: count the segments that end before it (independent broadcast reads) ----
         int si[SPT];
-        if (RECORDS) {
+        if (STAGED) {
 #pragma unroll
             for (int u = 0; u < SPT; ++u) {
                 int c = 0;
@@ -295,7 +309,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
         int nst = 0, nfill = 0;
         if (STORE) {
             const int64_t toff = out.traj_offset ? __ldg(out.traj_offset + traj) : (int64_t)traj * out.traj_stride;
-            row = out.base + toff + k0;
+            row = out.base + toff + (PTMA ? 0 : k0);
             nst = limit - k0;   // <= 0: nothing to store for this thread
             // the row's last 32-byte sector is completed with zeros when it lies inside the row's capacity
             const int64_t lim4 = ((int64_t)limit + (kFillAlign - 1)) & ~(int64_t)(kFillAlign - 1);
@@ -320,6 +334,10 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
                 stager.put_tail(traj, k0, n);                                                  \
                 stager.flush(&ro.tmap, ro.base + rec_off, rec_off, wk0, limit);                \
             }                                                                                  \
+        } else if (PTMA) {                                                                     \
+            if ((CH) == TGX_PX && pass > 0) pstager.wait_read();                               \
+            pstager.template put<(CH)>(ARR);                                                   \
+            if ((CH) == TGX_DPSI) pstager.flush(&ro.tmap, traj, wk0, limit, fill_end, row, cs); \
         } else if (STORE && nfill > 0 && (mask & (1u << (CH)))) {                              \
             store_channel<SPT>(row + (CH) * cs, ARR, nst, nfill);                              \
         }                                                                                      \
@@ -550,6 +568,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     }
     }   // pass
     if (RECORDS) stager.wait_read();               // the TMA unit must have read the staging area before the CTA exits
+    if (PTMA) pstager.wait_read();
 
     if (REDUCE) {
         // ---- per-trajectory max |v|, max |a|: warp shuffles -> shared -> one atomicMax per tile ------------
@@ -606,12 +625,37 @@ static cudaError_t launch_eval_t(const TableView& tv, int64_t ntiles, const OutV
 }
 
 // tile = 1 << tile_shift samples per CTA, spt samples per thread: threads per CTA = tile / spt in {128, 256}.
+// Store-only evaluation with the planes leaving through TMA: 128-thread CTAs, 2 samples per thread per pass.
+template <int TILE, int MODE>
+static cudaError_t launch_eval_ptma_t(const TableView& tv, int64_t ntiles, const OutView& out, const RecOut& ptma,
+                                      cudaStream_t stream) {
+    constexpr int THREADS = 128, SPP = 2;
+    auto kernel = eval_kernel<THREADS, SPP, true, false, MODE, false, TILE / (SPP * THREADS), true>;
+    const int smem = (THREADS / 32) * PlaneTma<SPP>::kBytesPerWarp + 128;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<(unsigned)ntiles, THREADS, smem, stream>>>(tv, out, nullptr, nullptr, ptma);
+    return cudaGetLastError();
+}
+
+// ptma != nullptr: the caller's planes qualify for the TMA store path and ptma->tmap describes them (engine.cu).
 cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int spt, const OutView& out, bool store,
-                        double* max_v, double* max_a, cudaStream_t stream) {
+                        double* max_v, double* max_a, cudaStream_t stream, const RecOut* ptma) {
     if (ntiles <= 0) return cudaSuccess;
     if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const int threads = (1 << tile_shift) / spt;
     const int mode = tv.phase ? 2 : (tv.tile_slab > 0 ? 1 : 0);
+    if (ptma && store && !max_v && !max_a) {
+        const int tile = 1 << tile_shift;
+#define TGX_PCASE(TL)                                                                           \
+    if (tile == (TL))                                                                           \
+        return mode == 2   ? launch_eval_ptma_t<TL, 2>(tv, ntiles, out, *ptma, stream)          \
+               : mode == 1 ? launch_eval_ptma_t<TL, 1>(tv, ntiles, out, *ptma, stream)          \
+                           : launch_eval_ptma_t<TL, 0>(tv, ntiles, out, *ptma, stream)
+        TGX_PCASE(512);
+        TGX_PCASE(1024);
+#undef TGX_PCASE
+    }
 #define TGX_CASE(T, S)                                                                                     \
     if (threads == (T) && spt == (S))                                                                      \
         return mode == 2   ? launch_eval_t<T, S, 2>(tv, ntiles, out, store, max_v, max_a, stream)          \

@@ -191,5 +191,67 @@ struct RecTma {
     }
 };
 
+// ---- plane output through TMA ----------------------------------------------------------------------------------
+// The same sample ownership as the record mode (a warp owns 32*SPT consecutive samples per pass, lane l the samples
+// l, l + 32, ...), staged as [group u][channel][32 samples]: consecutive lanes write consecutive doubles (conflict-free)
+// and one group is exactly the box {32 samples, 14 channels, 1 trajectory} of the 3-D tensor map tgx_eval builds over the
+// caller's planes, so a group leaves with ONE cp.async.bulk.tensor instead of 14 vector stores per thread.  The group
+// that straddles the row's end keeps the contract of store_channel (valid samples, the last 32-byte sector completed
+// with zeros, nothing beyond) by going through LDS + STG.
+template <int SPT>
+struct PlaneTma {
+    static constexpr int kBoxBytes = TGX_NCHAN * 32 * 8;        // 3584 = 28 * 128
+    static constexpr int kBytesPerWarp = SPT * kBoxBytes;
+    uint32_t sbase;            // shared-window address of this warp's staging area (128-byte aligned)
+    int lane;
+
+    __device__ __forceinline__ void init(uint32_t warp_area, int lane_) {
+        sbase = warp_area;
+        lane = lane_;
+    }
+    template <int CH>
+    __device__ __forceinline__ void put(const double (&x)[SPT]) {
+#pragma unroll
+        for (int u = 0; u < SPT; ++u)
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(sbase + (uint32_t)(u * kBoxBytes + CH * 256 + lane * 8)),
+                         "d"(x[u]) : "memory");
+    }
+    // row = channel 0, sample 0 of the trajectory; cs = channel stride; samples >= limit are not written, except zeros up
+    // to fill_end (limit rounded up to a sector when that fits the row).  All 32 lanes must call it.
+    __device__ __forceinline__ void flush(const CUtensorMap* tmap, int traj, int wk0, int limit, int fill_end,
+                                          double* row, int64_t cs) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async-proxy reads
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            const int kg = wk0 + 32 * u;                                 // warp-uniform
+            if (kg + 32 <= limit) {
+                if (lane == 0)
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                                     reinterpret_cast<uint64_t>(tmap)),
+                                 "r"(kg), "r"(0), "r"(traj), "r"(sbase + (uint32_t)(u * kBoxBytes))
+                                 : "memory");
+            } else if (kg < fill_end) {
+                // 14 channels x 8 quads of 4 samples, one (channel, quad) per lane per round
+                for (int item = lane; item < TGX_NCHAN * 8; item += 32) {
+                    const int ch = item >> 3, k = kg + 4 * (item & 7);
+                    if (k < fill_end) {
+                        const uint32_t addr = sbase + (uint32_t)(u * kBoxBytes + ch * 256 + (item & 7) * 32);
+                        double x[4];
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "r"(addr) : "memory");
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[2]), "=d"(x[3]) : "r"(addr + 16) : "memory");
+                        store_channel<4>(row + ch * cs + k, x, limit - k, fill_end - k);
+                    }
+                }
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void wait_read() {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+    }
+};
+
 }  // namespace
 }  // namespace tgx

@@ -45,6 +45,7 @@ def _load() -> C.CDLL:
     lib.tgx_set_host_fill.argtypes = [vp, C.c_int]
     lib.tgx_set_host_layout.argtypes = [vp, C.c_int]
     lib.tgx_set_phase_planning.argtypes = [vp, C.c_int]
+    lib.tgx_set_store_path.argtypes = [vp, C.c_int]
     lib.tgx_phase_plan_count.restype = i64
     lib.tgx_phase_plan_count.argtypes = [vp]
     lib.tgx_set_slab_planning.argtypes = [vp, C.c_int]
@@ -202,6 +203,10 @@ class Engine:
         """Host buffers of generate_host / stop_host: [n, 14, cap] (default) or plane-major [14, n, cap]."""
         self._check(self._lib.tgx_set_host_layout(self._h, 1 if plane_major else 0), "tgx_set_host_layout")
         self._host_plane_major = bool(plane_major)
+
+    def set_store_path(self, tma: bool):
+        """tgx_eval's planes through TMA (default) or always through vector stores; same bytes either way."""
+        self._check(self._lib.tgx_set_store_path(self._h, 1 if tma else 0), "tgx_set_store_path")
 
     def set_phase_planning(self, allow: bool):
         self._check(self._lib.tgx_set_phase_planning(self._h, 1 if allow else 0), "tgx_set_phase_planning")
