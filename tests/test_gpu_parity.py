@@ -310,6 +310,63 @@ def test_layouts_and_tunings_agree(engine, oracle):
     assert_samples_close(base[-1, :, :25001], ref, "default circle in mixed batch")
 
 
+def test_store_paths_write_the_same_bytes(engine, oracle):
+    """tgx_eval through TMA (boxes of 32 samples x 14 channels, tgx_set_store_path default) and through vector stores:
+    identical bytes incl. the zero-filled tail sector and the untouched padding, for every planning mode (phase plan,
+    fixed slices, exact offsets), both plane orders, both tile sizes, truncated rows and braking plans."""
+    import torch
+
+    def both(evaluate, shape, dev):
+        outs = []
+        for tma in (True, False):
+            engine.set_store_path(tma)
+            out = torch.full(shape, float("nan"), dtype=torch.float64, device=dev)
+            evaluate(out)
+            torch.cuda.synchronize()
+            outs.append(out.cpu().numpy())
+        engine.set_store_path(True)
+        assert np.array_equal(outs[0], outs[1], equal_nan=True)
+        return outs[0]
+
+    batches = {"circles": workloads.circles_cfg2(200), "mixed": abi.concat([workloads.mixed_cfg3(150, seed=5),
+                                                                               workloads.default_circle()])}
+    try:
+        for shift, spt in ((10, 4), (9, 4)):
+            engine.set_tuning(shift, spt)
+            for name, params in batches.items():
+                d = engine.upload_params(params)
+                for rep in range(3):          # first plan: exact offsets; later plans: fixed slices / phase plans
+                    plan = engine.plan(d, want_outputs=(rep == 0), want_phases=False)
+                    if rep == 0:
+                        counts = plan.counts.cpu().numpy()
+                    cap = int((counts.max() + 3) // 4 * 4) + 8
+                    n = len(params)
+                    got = both(lambda o: engine.eval(o), (n, abi.TGX_NCHAN, cap), d.device)
+                    for i in range(0, n, 37):
+                        n4 = (counts[i] + 3) // 4 * 4
+                        assert not np.isnan(got[i, :, :counts[i]]).any()
+                        assert (got[i, :, counts[i]:n4] == 0).all() and np.isnan(got[i, :, n4:]).all()
+                    if rep < 2:
+                        continue
+                    both(lambda o: engine.eval(o, plane_major=True), (abi.TGX_NCHAN, n, cap), d.device)
+                    for c in (32, 33, 64, 500, 997):   # rows cut by the capacity: inside a box, on a box boundary
+                        cut = both(lambda o: engine.eval(o, capacity=c), (n, abi.TGX_NCHAN, cap), d.device)
+                        assert np.isnan(cut[:, :, (c + 3) // 4 * 4:]).all()
+        # braking plans (exact-offset tables, short rows)
+        params = batches["mixed"][:80]
+        froms = np.zeros((len(params), abi.TGX_NCHAN))
+        for i in range(len(params)):
+            smp = oracle.generate(params[i:i + 1])[0]
+            froms[i] = smp[:, smp.shape[1] // 2]
+        d = engine.upload_params(params)
+        plan = engine.plan_stop(d, torch.from_numpy(froms).to(d.device))
+        cap = max(32, int((int(plan.counts.max()) + 3) // 4 * 4))
+        both(lambda o: engine.eval(o), (len(params), abi.TGX_NCHAN, cap), d.device)
+    finally:
+        engine.set_tuning(10, 4)
+        engine.set_store_path(True)
+
+
 def test_capacity_truncation_and_channel_mask(engine):
     import torch
     params = workloads.circles_cfg2(64)

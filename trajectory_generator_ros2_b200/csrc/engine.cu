@@ -873,6 +873,8 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
     if (d_max_a) TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)e->plan_n * sizeof(double), s));
     if (e->plan_tiles == 0) return TGX_OK;
     tgx::RecOut ptma{};
+    // (the polyline kernel has no per-sample transcendental and is faster with vector stores: 17.0 vs 17.7 ms per Mi
+    //  T trajectories, so its planes never take the TMA path)
     const bool tma = e->plane_tma && !e->plan_poly && !d_max_v && !d_max_a && make_plane_tmap(&ptma.tmap, out, e->plan_n);
     TGX_CUDA(launch_current(e, make_view(out), true, d_max_v, d_max_a, s, tma ? &ptma : nullptr));
     e->launches += 1;
