@@ -480,6 +480,8 @@ def run_ours(args):
                 "workload": WORKLOAD_DESC[args.workload].format(n=n),
                 "trajectories_per_gpu": n, "samples_per_gpu": total_samples, "row_stride": row,
                 "layout": "plane-major [14][n][row]" if args.plane_major else "trajectory-major [n][14][row]",
+                "store_path": ("TMA: 32-sample x 14-channel boxes staged in shared memory (polyline plans and irregular "
+                               "layouts: 256-bit vector stores)") if args.store_path == "tma" else "256-bit vector stores",
                 "chunks": chunks,
                 "step": ("tgx_plan_polyline (hold-length table + waypoints / per-leg step counts in strict IEEE "
                          "arithmetic, one thread per trajectory) + tgx_eval, parameters resident in HBM") if poly else

@@ -18,6 +18,7 @@
 #include <thread>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -36,7 +37,8 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
                              const int32_t* plan_counts, const int64_t* seg_off, const int64_t* tile_off,
                              int seg_slab, int tile_slab, TrajRec* recs, Seg* segs, Tile* tiles, int32_t* counts,
                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
-                             PlanStats* stats, cudaStream_t stream);
+                             PlanStats* stats, cudaStream_t stream, const int32_t* order = nullptr);
+cudaError_t launch_replay_keys(const tgx_params* params, int64_t n, uint8_t* key, int32_t* idx, cudaStream_t stream);
 cudaError_t launch_count_used_tiles(int64_t n, int tile_slab, const Tile* slots, int32_t* ntile, cudaStream_t stream);
 cudaError_t launch_compact_tiles(int64_t n, int tile_slab, const Tile* slots, const int64_t* tile_off, Tile* dense,
                                  cudaStream_t stream);
@@ -201,6 +203,8 @@ struct tgx_engine {
     DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals, cur_table, stats;
     // tables
     DevBuf segs, tiles, packets, phase, tiles_dense;
+    DevBuf order;                       // replay order of a mixed batch: keys in/out, indices in/out (10 bytes each)
+    bool mixed_batch = false;           // the last plan saw more than one replay class: sort the next one by class
     bool plan_packed = false;                    // current plan is a slab plan
     bool plan_phase = false;                     // current plan is a phase plan
     const tgx_params* plan_params = nullptr;     // phase plans read the caller's parameter array during evaluation
@@ -321,6 +325,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         e->phase_ready = e->allow_phase && !e->exact_ramps && dense && !h_stats->has_line && h_stats->max_n > 0 &&
                          h_stats->max_n <= tgx::kPhaseMaxSamples;
         e->phase_tile_slab = tile_slab;
+        e->mixed_batch = (h_stats->kinds & (h_stats->kinds - 1)) != 0;      // more than one replay class
     };
     e->plan_phase = false;
     e->plan_params = nullptr;
@@ -363,11 +368,33 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
             if ((rc = e->segs.reserve((size_t)need_segs * sizeof(tgx::Seg)))) return rc;
             if ((rc = e->tiles.reserve((size_t)need_tiles * sizeof(tgx::Tile)))) return rc;
             TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+            // A mixed batch is replayed in the order of its replay classes (orbits by number of speed goals, lines,
+            // boomerangs): neighbouring lanes then walk the same code instead of diverging at every branch.  One key
+            // kernel + a one-pass radix sort of (class, index) pairs; the tables are indexed by trajectory, so the
+            // plan itself does not depend on the order.
+            const int32_t* order = nullptr;
+            if (e->mixed_batch && n >= 256 && n <= 0x7fffffffLL) {
+                if ((rc = e->order.reserve((size_t)n * 10 + 64))) return rc;
+                uint8_t* key_in = e->order.as<uint8_t>();
+                uint8_t* key_out = key_in + n;
+                int32_t* idx_in = reinterpret_cast<int32_t*>(key_in + ((2 * n + 15) & ~(int64_t)15));
+                int32_t* idx_out = idx_in + n;
+                TGX_CUDA(tgx::launch_replay_keys(d_params, n, key_in, idx_in, stream));
+                size_t need = 0;
+                TGX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, idx_in, idx_out, (int)n, 0, 5,
+                                                         stream));
+                if ((rc = e->cub_tmp.reserve(need))) return rc;
+                size_t tmp_bytes = e->cub_tmp.bytes;
+                TGX_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp_bytes, key_in, key_out, idx_in, idx_out,
+                                                         (int)n, 0, 5, stream));
+                e->launches += 2;
+                order = idx_out;
+            }
             TGX_CUDA(tgx::launch_plan_fill(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
                                            tab, nullptr, nullptr, nullptr, e->seg_slab, e->tile_slab,
                                            e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(),
                                            e->tiles.as<tgx::Tile>(), d_counts, d_status, cnt, st, d_phases, d_stats,
-                                           stream));
+                                           stream, order));
             e->launches += 1;
             TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
             TGX_CUDA(cudaStreamSynchronize(stream));
@@ -660,7 +687,7 @@ int tgx_destroy(tgx_engine* e) {
     cudaSetDevice(e->device);
     DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
                       &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats, &e->packets,
-                      &e->phase, &e->poly_recs, &e->poly_tiles, &e->tiles_dense};
+                      &e->phase, &e->poly_recs, &e->poly_tiles, &e->tiles_dense, &e->order};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         e->h_legs[i].release();
@@ -771,7 +798,7 @@ int64_t tgx_scratch_bytes(const tgx_engine* e) {
     if (!e) return 0;
     const DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
                             &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats,
-                            &e->packets, &e->phase, &e->poly_recs, &e->poly_tiles};
+                            &e->packets, &e->phase, &e->poly_recs, &e->poly_tiles, &e->order};
     int64_t s = 0;
     for (const DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;

@@ -44,6 +44,12 @@ __device__ bool params_ok(const tgx_params& p) {
 
 __device__ __forceinline__ bool is_line_like(int type) { return type == TGX_LINE || type == TGX_BOOMERANG; }
 __device__ __forceinline__ bool is_orbit(int type) { return type == TGX_CIRCLE || type == TGX_FIGURE8; }
+// Trajectories of one class take the same path through the replay: orbits with the same number of speed goals
+// (1 .. TGX_MAX_VGOALS), lines, boomerangs, everything else.  < 32 classes: also a bit index in PlanStats.kinds.
+__device__ __forceinline__ int replay_class(int type, int n_vgoals) {
+    if (is_orbit(type)) return n_vgoals >= 1 && n_vgoals <= 16 ? n_vgoals : 0;
+    return type == TGX_LINE ? 17 : (type == TGX_BOOMERANG ? 18 : 19);
+}
 
 // Collects what a replay produces.  In counting mode (segs == nullptr) it only counts.
 struct Emitter {
@@ -706,9 +712,10 @@ __device__ __forceinline__ tgx_params load_params(const tgx_params* params, int6
 
 // Per-plan statistics the fill pass accumulates (one atomic per warp).
 __device__ __forceinline__ void accumulate_stats(PlanStats* stats, int n, int nseg, int ntile, bool overflow,
-                                                 bool line_like) {
+                                                 bool line_like, int kind) {
     if (!stats) return;
     const unsigned mask = __activemask();
+    const unsigned kinds = __reduce_or_sync(mask, 1u << kind);
     const unsigned tot = __reduce_add_sync(mask, (unsigned)n);
     const int mseg = __reduce_max_sync(mask, nseg);
     const int mtile = __reduce_max_sync(mask, ntile);
@@ -724,7 +731,19 @@ __device__ __forceinline__ void accumulate_stats(PlanStats* stats, int n, int ns
         atomicMax(&stats->max_n, mn);
         if (ovf) atomicOr(&stats->overflow, 1);
         if (lin) atomicOr(&stats->has_line, 1);
+        if ((*reinterpret_cast<volatile int*>(&stats->kinds) & (int)kinds) != (int)kinds) atomicOr(&stats->kinds, (int)kinds);
     }
+}
+
+// Replay order of a mixed batch: key[t] = replay class of trajectory t, idx[t] = t; a one-pass radix sort of the pairs
+// (engine.cu) then hands neighbouring lanes trajectories of the same class.
+__global__ void __launch_bounds__(256)
+replay_keys_kernel(const tgx_params* __restrict__ params, int64_t n, uint8_t* __restrict__ key, int32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 head = __ldg(reinterpret_cast<const int2*>(params + i));      // {type, n_vgoals}
+    key[i] = (uint8_t)replay_class(head.x, head.y);
+    idx[i] = (int32_t)i;
 }
 
 // Counting pass: N_i, status_i and, with SEGS, the number of segments / tiles the fill pass will emit (which
@@ -770,9 +789,14 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
                  const int64_t* __restrict__ seg_off, const int64_t* __restrict__ tile_off, int seg_slab,
                  int tile_slab, TrajRec* __restrict__ recs, Seg* __restrict__ segs, Tile* __restrict__ tiles,
                  int32_t* __restrict__ counts, uint32_t* __restrict__ status, int32_t* __restrict__ counts2,
-                 uint32_t* __restrict__ status2, tgx_phases* __restrict__ phases, PlanStats* __restrict__ stats) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                 uint32_t* __restrict__ status2, tgx_phases* __restrict__ phases, PlanStats* __restrict__ stats,
+                 const int32_t* __restrict__ order) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    // order: thread t replays trajectory order[t] (a mixed batch sorted by replay class, so that the lanes of a warp
+    // walk the same code: 4.5 of 32 lanes were active on average in config 3's unsorted replay); everything the
+    // trajectory owns is indexed by i, so the tables do not depend on the order
+    const int64_t i = order ? (int64_t)__ldg(order + t) : t;
     const tgx_params p = load_params(params, i);
     const bool slab = seg_slab > 0;
     // exact-offset mode: a trajectory the counting pass rejected owns no slice: replay it without writing tables
@@ -809,7 +833,7 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
     if (status) status[i] = r.status;
     if (counts2) counts2[i] = r.n;
     if (status2) status2[i] = r.status;
-    accumulate_stats(stats, r.n, r.nseg, r.ntile, overflow, is_line_like(p.type));
+    accumulate_stats(stats, r.n, r.nseg, r.ntile, overflow, is_line_like(p.type), replay_class(p.type, p.n_vgoals));
 }
 
 // Phase plan: counts only.  Replays the speed ramps and hold counters (no angle state: none is stored) and records
@@ -858,7 +882,7 @@ plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits l
     if (status) status[i] = r.status;
     if (counts2) counts2[i] = r.n;
     if (status2) status2[i] = r.status;
-    accumulate_stats(stats, r.n, 0, 0, overflow, line_like);
+    accumulate_stats(stats, r.n, 0, 0, overflow, line_like, replay_class(p.type, p.n_vgoals));
 }
 
 // "Per-time evaluation": a one-sample plan per trajectory from an explicit state, i.e. the public helpers
@@ -1027,7 +1051,7 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
                              const int32_t* plan_counts, const int64_t* seg_off, const int64_t* tile_off,
                              int seg_slab, int tile_slab, TrajRec* recs, Seg* segs, Tile* tiles, int32_t* counts,
                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
-                             PlanStats* stats, cudaStream_t stream) {
+                             PlanStats* stats, cudaStream_t stream, const int32_t* order) {
     if (n <= 0) return cudaSuccess;
     tgx_limits l{};
     if (lim) l = *lim;
@@ -1037,10 +1061,16 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
 #define TGX_LAUNCH_FILL(XR)                                                                                       \
     plan_fill_kernel<XR><<<(unsigned)blocks, threads, 0, stream>>>(                                               \
         params, stop_from, n, l, lim ? 1 : 0, max_samples, tile_shift, tab, plan_counts, seg_off, tile_off,       \
-        seg_slab, tile_slab, recs, segs, tiles, counts, status, counts2, status2, phases, stats)
+        seg_slab, tile_slab, recs, segs, tiles, counts, status, counts2, status2, phases, stats, order)
     if (exact_ramps) TGX_LAUNCH_FILL(true);
     else TGX_LAUNCH_FILL(false);
 #undef TGX_LAUNCH_FILL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_replay_keys(const tgx_params* params, int64_t n, uint8_t* key, int32_t* idx, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    replay_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(params, n, key, idx);
     return cudaGetLastError();
 }
 

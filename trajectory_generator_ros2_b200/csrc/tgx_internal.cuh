@@ -124,7 +124,7 @@ struct PlanStats {
     int overflow;                       // slab / phase mode: some trajectory did not fit
     int max_n;                          // largest sample count of a trajectory
     int has_line;                       // some trajectory is a Line / Boomerang
-    int pad;
+    int kinds;                          // bit mask of the replay classes seen (replay_class(): orbit x K, line, boomerang)
 };
 
 // ---- constant-speed polyline family (Square / Rectangle / Reciprocating / Bounce / M / I / T) -------------------
