@@ -131,7 +131,7 @@ __device__ void build_phase_segment(const tgx_params& par, const PhaseRec& phr, 
 // the record mode, ro.tmap then describes the caller's planes as a [trajectory][channel][sample] tensor.
 template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE, bool RECORDS = false, int PASSES = 1,
           bool PTMA = false>
-__global__ void __launch_bounds__(THREADS, 768 / THREADS)
+__global__ void __launch_bounds__(THREADS, 768 / THREADS)   // (a 7th CTA per SM at 72 registers: 16.8 vs 16.6 ms)
 eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a,
             const __grid_constant__ RecOut ro = RecOut{}) {
     constexpr bool STAGED = RECORDS || PTMA;       // samples staged in shared memory and sent by TMA
@@ -142,8 +142,10 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     constexpr int KS = STAGED ? 32 : 1;           // distance between a thread's samples
     extern __shared__ __align__(16) double2 s_dyn[];
     __shared__ __align__(16) TrajRec s_rec;
-    __shared__ __align__(16) Seg s_seg[kMaxSegPerTile];
-    __shared__ int s_kend[kMaxSegPerTile];          // last sample of each segment
+    // a phase plan has at most 2 K + 1 segments per trajectory (K <= TGX_MAX_VGOALS speed goals)
+    constexpr int NSEG = MODE == 2 ? 2 * TGX_MAX_VGOALS + 2 : kMaxSegPerTile;
+    __shared__ __align__(16) Seg s_seg[NSEG];
+    __shared__ int s_kend[NSEG];                    // last sample of each segment
     __shared__ int4 s_tile;
     __shared__ double s_red[2][THREADS / 32];
 
