@@ -20,6 +20,10 @@
 #include "tgx_internal.cuh"
 #include "store.cuh"
 
+#ifndef TGX_REDUCE_CTAS
+#define TGX_REDUCE_CTAS 4      // CTAs of 256 threads per SM the reduction-only instantiation is compiled for (64 registers)
+#endif
+
 namespace tgx {
 
 namespace {
@@ -31,26 +35,39 @@ constexpr double kPiOver2 = 1.57079632679489661923;
 // split of pi/2 — each fma rounds once, the first one to a result of magnitude <= 1, so the reduced argument is off by
 // ~1e-16 absolute for every |x| < 1e9 checked — followed by the fdlibm minimax polynomials on [-pi/4, pi/4] (< 1 ulp).
 // No Payne-Hanek slow path, hence no stack frame.  Parity budget: |dp| <= 1e-9 m needs |d sin| <= 2e-10 at r = 5 m.
+//
+// The 17 constants live in __constant__ memory: a DFMA takes a constant-bank operand directly, whereas a 64-bit
+// literal has to be materialised with two moves per use — in the reduction-only kernel (FP64- / issue-bound) those
+// moves were 60 of the ~200 instructions per sample (ncu: IMAD 16 %, UMOV 14.5 % of all executed instructions).
+__constant__ double kTrig[17] = {
+    6.36619772367581382433e-01,                                       // 0: 2/pi
+    6755399441055744.0,                                               // 1: 1.5 * 2^52
+    -1.57079632679489655800e+00, -6.12323399573676603587e-17, -1.49738490485916983329e-33,   // 2-4: -pi/2, 3 terms
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,     // 5-10: sin, S6 .. S1
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,    // 11-16: cos, C6 .. C1
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+
 __device__ __forceinline__ void sincos_orbit(double x, double* sn, double* cs) {
     // k = rint(x * 2/pi) without a float->int conversion: adding 1.5 * 2^52 leaves k in the low mantissa bits
-    const double shifted = fma(x, 6.36619772367581382433e-01, 6755399441055744.0);
+    const double shifted = fma(x, kTrig[0], kTrig[1]);
     const int q = __double2loint(shifted);                           // only the two low bits matter
-    const double kd = shifted - 6755399441055744.0;
-    double r = fma(kd, -1.57079632679489655800e+00, x);              // pi/2 = hi + mid + lo
-    r = fma(kd, -6.12323399573676603587e-17, r);
-    r = fma(kd, -1.49738490485916983329e-33, r);
+    const double kd = shifted - kTrig[1];
+    double r = fma(kd, kTrig[2], x);                                 // pi/2 = hi + mid + lo
+    r = fma(kd, kTrig[3], r);
+    r = fma(kd, kTrig[4], r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, kTrig[5], kTrig[6]);
+    ps = fma(z, ps, kTrig[7]);
+    ps = fma(z, ps, kTrig[8]);
+    ps = fma(z, ps, kTrig[9]);
+    ps = fma(z, ps, kTrig[10]);
     const double s = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, kTrig[11], kTrig[12]);
+    pc = fma(z, pc, kTrig[13]);
+    pc = fma(z, pc, kTrig[14]);
+    pc = fma(z, pc, kTrig[15]);
+    pc = fma(z, pc, kTrig[16]);
     const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
     const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;           // quadrant: (s, c), (c, -s), (-s, -c), (-c, s)
     *sn = (q & 2) ? -a : a;
@@ -131,7 +148,7 @@ __device__ void build_phase_segment(const tgx_params& par, const PhaseRec& phr, 
 // the record mode, ro.tmap then describes the caller's planes as a [trajectory][channel][sample] tensor.
 template <int THREADS, int SPT, bool STORE, bool REDUCE, int MODE, bool RECORDS = false, int PASSES = 1,
           bool PTMA = false>
-__global__ void __launch_bounds__(THREADS, 768 / THREADS)   // (a 7th CTA per SM at 72 registers: 16.8 vs 16.6 ms)
+__global__ void __launch_bounds__(THREADS, (REDUCE && !STORE) ? TGX_REDUCE_CTAS * 256 / THREADS : 768 / THREADS)   // (PTMA: a 7th CTA per SM at 72 registers: 16.8 vs 16.6 ms)
 eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a,
             const __grid_constant__ RecOut ro = RecOut{}) {
     constexpr bool STAGED = RECORDS || PTMA;       // samples staged in shared memory and sent by TMA
@@ -398,8 +415,8 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 #pragma unroll
                 for (int u = 0; u < SPT; ++u)
                     if (u < nvalid) {
-                        best_v2 = fmax(best_v2, v[u] * v[u]);                       // the direction is a unit vector
-                        best_a2 = fmax(best_a2, acc[u] * acc[u] * (dx * dx + dy * dy));
+                        best_v2 = max_nn(best_v2, v[u] * v[u]);                       // the direction is a unit vector
+                        best_a2 = max_nn(best_a2, acc[u] * acc[u] * (dx * dx + dy * dy));
                     }
             }
         } else if (type == TGX_LINE) {
@@ -449,8 +466,8 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 #pragma unroll
                 for (int u = 0; u < SPT; ++u)
                     if (u < nvalid) {
-                        best_v2 = fmax(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
-                        best_a2 = fmax(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
+                        best_v2 = max_nn(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
+                        best_a2 = max_nn(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
                     }
             }
         } else {
@@ -468,13 +485,11 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 #ifdef TGX_EXPERIMENT_NOTRIG
                 sn[u] = th[u] * 0.5; cn[u] = th[u] * 0.25;   // bandwidth experiment only: no trigonometry
 #else
-                // the store-bound instantiations take the lighter routine (no slow path, no stack frame: 17.7 -> 17.6 ms
-                // on the 1 Mi-circle batch); the reduction-only one is FP64- / issue-bound and is 17 % faster with the
-                // library's scheduling of the same polynomials
-                // (every instantiation that reduces maxima uses the same routine, so tgx_eval's maxima equal
-                // tgx_feasibility's bit for bit)
-                if (!REDUCE) sincos_orbit(th[u], &sn[u], &cn[u]);
-                else sincos(th[u], &sn[u], &cn[u]);
+                // one routine for every instantiation (so tgx_eval's maxima equal tgx_feasibility's bit for bit): no slow
+                // path, no stack frame, coefficients in constant memory.  The reduction-only kernel is issue-bound (ncu:
+                // issue slots 71 % busy, FP64 pipe 32 %) and runs as fast with it at 64 registers / 4 CTAs per SM as with
+                // the library's sincos (8.44 vs 8.45 ms per Mi config-4 circles); at 80 registers / 3 CTAs it takes 10.2 ms
+                sincos_orbit(th[u], &sn[u], &cn[u]);
 #endif
                 om[u] = v[u] * rinv;                 // omega = v / r
             }
@@ -519,8 +534,8 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 #pragma unroll
                     for (int u = 0; u < SPT; ++u)
                         if (u < nvalid) {
-                            best_v2 = fmax(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
-                            best_a2 = fmax(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
+                            best_v2 = max_nn(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
+                            best_a2 = max_nn(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
                         }
                 }
             } else {
@@ -560,8 +575,8 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 #pragma unroll
                     for (int u = 0; u < SPT; ++u)
                         if (u < nvalid) {
-                            best_v2 = fmax(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
-                            best_a2 = fmax(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
+                            best_v2 = max_nn(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
+                            best_a2 = max_nn(best_a2, fma(ax[u], ax[u], ay[u] * ay[u]));
                         }
                 }
             }

@@ -582,7 +582,7 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
         if (REDUCE) {
 #pragma unroll
             for (int u = 0; u < SPT; ++u)
-                if (u < nvalid) best_v2 = fmax(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
+                if (u < nvalid) best_v2 = max_nn(best_v2, fma(vx[u], vx[u], vy[u] * vy[u]));
         }
     }
     }   // pass

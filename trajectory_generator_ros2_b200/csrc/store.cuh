@@ -72,6 +72,11 @@ __device__ __forceinline__ void store_channel(double* p, const double (&x)[SPT],
     }
 }
 
+// Running maximum of non-negative values: a compare and two selects instead of fmax's NaN-quieting sequence (DSETP.MAX,
+// LOP3, FSEL, SEL, moves: ~8 instructions, twice per sample in the reduction kernels).  Like fmax it never lets a NaN
+// sample replace the running value.
+__device__ __forceinline__ double max_nn(double best, double x) { return x > best ? x : best; }
+
 __device__ __forceinline__ double warp_max(double x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
