@@ -77,10 +77,14 @@ __device__ __forceinline__ void store_channel(double* p, const double (&x)[SPT],
 // sample replace the running value.
 __device__ __forceinline__ double max_nn(double best, double x) { return x > best ? x : best; }
 
+// Warp maximum of non-negative (non-NaN) doubles: their bit patterns are ordered like the values, so two integer warp
+// reductions (REDUX.MAX on the high words, then on the low words of the lanes that hold the largest high word) replace
+// five rounds of 64-bit shuffles + fmax (~30 instructions per sample of a 4-sample thread in the reduction kernels).
 __device__ __forceinline__ double warp_max(double x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
+    const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
 }
 
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double x) {
