@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(THREADS, (REDUCE && !STORE) ? TGX_REDUCE_CTAS 
 eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a,
             const __grid_constant__ RecOut ro = RecOut{}) {
     constexpr bool STAGED = RECORDS || PTMA;       // samples staged in shared memory and sent by TMA
-    static_assert(STAGED || PASSES == 1, "only the TMA modes walk a tile in passes");
+    static_assert(STAGED || (REDUCE && !STORE) || PASSES == 1, "only the TMA and reduction-only modes walk a tile in passes");
     static_assert(!PTMA || (STORE && !REDUCE && !RECORDS), "PTMA is the plain store-only evaluation");
     constexpr bool SLAB = MODE == 1;
     constexpr int TILE = THREADS * SPT * PASSES;
@@ -297,7 +297,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     for (int pass = 0; pass < PASSES; ++pass) {
     // first sample of this warp's block of 32*SPT (RECORDS) and of this thread
     const int wk0 = k_lo + pass * (THREADS * SPT) + ((int)threadIdx.x >> 5) * (32 * SPT);
-    const int k0 = STAGED ? wk0 + ((int)threadIdx.x & 31) : k_lo + SPT * (int)threadIdx.x;
+    const int k0 = STAGED ? wk0 + ((int)threadIdx.x & 31) : k_lo + pass * (THREADS * SPT) + SPT * (int)threadIdx.x;
     const int nvalid = (REDUCE ? n : limit) - k0;   // samples this thread evaluates (may be <= 0)
 
     // RECORDS: every lane of a warp takes part in staging the warp's records, so lanes beyond the trajectory's end
@@ -636,6 +636,10 @@ static cudaError_t launch_eval_t(const TableView& tv, int64_t ntiles, const OutV
         eval_kernel<THREADS, SPT, true, true, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     else if (store)
         eval_kernel<THREADS, SPT, true, false, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
+    else if (THREADS == 256 && SPT == 4)
+        // reduction only: 128-thread CTAs walking the 1024-sample tile in two passes — 8 samples per thread between the
+        // prologue and the warp / CTA reduction instead of 4
+        eval_kernel<128, 4, false, true, MODE, false, 2><<<grid, 128, 0, stream>>>(tv, out, max_v, max_a);
     else
         eval_kernel<THREADS, SPT, false, true, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     return cudaGetLastError();
