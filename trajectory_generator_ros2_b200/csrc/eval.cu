@@ -21,7 +21,7 @@
 #include "store.cuh"
 
 #ifndef TGX_REDUCE_CTAS
-#define TGX_REDUCE_CTAS 4      // CTAs of 256 threads per SM the reduction-only instantiation is compiled for (64 registers)
+#define TGX_REDUCE_CTAS 4      // the reduction-only instantiation is compiled for 4 * 256 threads per SM (64 registers; 5: 48 registers, spills in the slab / phase modes, 5.72 vs 5.77 ms)
 #endif
 
 namespace tgx {
@@ -636,12 +636,11 @@ static cudaError_t launch_eval_t(const TableView& tv, int64_t ntiles, const OutV
         eval_kernel<THREADS, SPT, true, true, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     else if (store)
         eval_kernel<THREADS, SPT, true, false, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
-    else if (THREADS == 256 && SPT == 4)
-        // reduction only: 128-thread CTAs walking the 1024-sample tile in two passes — 8 samples per thread between the
-        // prologue and the warp / CTA reduction instead of 4
-        eval_kernel<128, 4, false, true, MODE, false, 2><<<grid, 128, 0, stream>>>(tv, out, max_v, max_a);
     else
-        eval_kernel<THREADS, SPT, false, true, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
+        // reduction only: 64-thread CTAs walking the tile in passes of 256 samples — 16 (8) samples per thread between
+        // the prologue and the warp / CTA reduction instead of 4, 20 small CTAs per SM.  Per Mi config-4 circles:
+        // 256 threads x 1 pass 7.76 ms, 128 x 2 6.21 ms, 64 x 4 5.72 ms
+        eval_kernel<64, 4, false, true, MODE, false, THREADS * SPT / 256><<<grid, 64, 0, stream>>>(tv, out, max_v, max_a);
     return cudaGetLastError();
 }
 
