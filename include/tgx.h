@@ -305,9 +305,10 @@ int tgx_destroy(tgx_engine* e);
 /* Guard against parameters for which the reference never terminates. Default 1<<24 samples. */
 int tgx_set_max_samples(tgx_engine* e, int64_t max_samples);
 /* Kernel shape used by tgx_eval / tgx_feasibility: one CTA evaluates a tile of (1 << tile_shift) consecutive
- * samples of one trajectory (tile_shift 9 or 10), each thread `spt` adjacent samples (2: 128-bit stores,
- * 4: 256-bit stores); (1 << tile_shift) / spt must be 128 or 256 threads.  Invalidates the current plan.
- * Default 10, 4. */
+ * samples of one trajectory (tile_shift 9 or 10); in the vector-store kernels each thread owns `spt` adjacent samples
+ * (2: 128-bit stores, 4: 256-bit stores) and (1 << tile_shift) / spt must be 128 or 256 threads.  The TMA kernels
+ * (planes, records) and the reduction-only kernel choose their own CTA width and walk the tile in passes of 256
+ * samples; only tile_shift matters to them.  Invalidates the current plan.  Default 10, 4. */
 int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt);
 /* Planning mode.  Sample counts, phase boundaries, status bits and every speed v_k are bit-identical to the
  * reference in both modes.
@@ -387,7 +388,10 @@ int tgx_plan_samples(tgx_engine* e, const tgx_params* d_params, int64_t n, const
                      int32_t* d_counts, uint32_t* d_status, void* stream);
 
 /* ---- evaluation: create*Goal for every (trajectory, k) of the current plan ------------------------- */
-/* One thread per pair of adjacent samples, fp64, SoA planes written with vector stores.
+/* One CTA per tile of the plan, fp64, struct-of-arrays planes.  Regular layouts leave through TMA (tgx_set_store_path:
+ * warps stage {32 samples x 14 channels} groups in shared memory, one cp.async.bulk.tensor per group); layouts with
+ * per-trajectory offsets, a channel subset or rows shorter than 32 samples, polyline plans and calls that ask for maxima
+ * use 256-bit streaming vector stores, one per thread per channel.  Same bytes either way.
  * If d_max_v / d_max_a are non-NULL the per-trajectory maxima of |v_k| and |a_k| (Euclidean norm of the
  * written x,y,z components) are reduced in the same pass. */
 int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_max_a, void* stream);
@@ -399,9 +403,11 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
  * rec_capacity).  One CTA per 256 samples: coalesced plane reads, a swizzled shared-memory transpose, 512-byte
  * coalesced record writes.  Does not need (or touch) the current plan. */
 /* The fused form: evaluate the current plan (either family, braking plans too) straight into clamped records,
- * d_records[(d_rec_offset ? d_rec_offset[i] : i * rec_stride) + k], k < rec_capacity — the evaluation kernels stage
- * each 64-byte record half through shared memory and every warp streams its own records, so a sample costs 128 bytes
- * of HBM traffic instead of the 112 + 112 + 128 of tgx_eval followed by tgx_pack_goals.  Bit-identical to that pair. */
+ * d_records[(d_rec_offset ? d_rec_offset[i] : i * rec_stride) + k], k < rec_capacity — every warp of the evaluation
+ * kernels stages 64 consecutive records in shared memory (128-byte TMA swizzle) and sends them as two 4 KiB TMA boxes of
+ * a [records][16 doubles] tensor map over d_records, so a sample costs 128 bytes of HBM traffic instead of the
+ * 112 + 112 + 128 of tgx_eval followed by tgx_pack_goals.  Bit-identical to that pair.  d_records must be 16-byte
+ * aligned and hold fewer than 2^31 records. */
 int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
                      const int64_t* d_rec_offset, int64_t rec_capacity, void* stream);
 

@@ -961,6 +961,8 @@ int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d
     if ((reinterpret_cast<uintptr_t>(d_records) & 15u) != 0) return TGX_ERR_ALIGNMENT;
     TGX_CUDA(cudaSetDevice(e->device));
     if (e->plan_n == 0 || e->plan_tiles == 0 || rec_capacity == 0) return TGX_OK;
+    // TMA addresses records by a 32-bit row coordinate (2^31 records = 275 GB, more than one GPU holds)
+    if (!d_rec_offset && (rec_stride < 0 || e->plan_n * rec_stride > 0x7fffffffLL)) return TGX_ERR_CAPACITY;
     tgx::RecOut ro{};
     ro.base = d_records;
     ro.stride = rec_stride;
