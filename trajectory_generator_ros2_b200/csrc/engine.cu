@@ -316,7 +316,16 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         if (e->seg_slab > seg_slab && e->seg_slab <= 2 * seg_slab) seg_slab = e->seg_slab;
         if (e->tile_slab > tile_slab && e->tile_slab <= 2 * tile_slab) tile_slab = e->tile_slab;
         const bool dense = n * (int64_t)tile_slab <= total_tiles + total_tiles / 4 + 1;
-        const bool small = n * (int64_t)seg_slab * (int64_t)sizeof(tgx::Seg) <= ((int64_t)8 << 30) &&
+        // fixed slices cost n * seg_slab segment records: up to 8 GB always, beyond that (10^7 .. 10^8-trajectory
+        // feasibility sweeps) only while they fit half of the memory that is free right now
+        const int64_t slab_bytes = n * (int64_t)seg_slab * (int64_t)sizeof(tgx::Seg);
+        int64_t budget = (int64_t)8 << 30;
+        if (slab_bytes > budget) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                budget = std::max<int64_t>(budget, (int64_t)((free_b + e->segs.bytes) / 2));
+        }
+        const bool small = slab_bytes <= budget &&
                            n * (int64_t)seg_slab <= 0x7fffffffLL && n * (int64_t)tile_slab <= 0x7fffffffLL;
         e->slabs_ready = dense && small && total_tiles > 0;
         e->ragged_ready = !dense && small && total_tiles > 0;
