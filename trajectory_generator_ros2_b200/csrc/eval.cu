@@ -474,14 +474,31 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
             const double r = s_rec.f[0], cx = s_rec.f[1], cy = s_rec.f[2], alt = s_rec.f[3];
             const double dtr = s_rec.f[4], rinv = s_rec.f[5];
             double v[SPT], th[SPT], sn[SPT], cn[SPT], om[SPT];
-#pragma unroll
-            for (int u = 0; u < SPT; ++u) {
-                const Seg& sg = s_seg[si[u]];
+            // theta_b + sum_{m<=j} (v_m / r) * dt  =  theta_b + j*w1 + j(j+1)/2 * (dv*dt/r); a hold (dv = 0) is the
+            // reference's exact arithmetic progression; a segment's last sample carries the replayed theta.
+            auto speed_and_angle = [&](const Seg& sg, int u) {
                 const SegPos q = seg_pos(sg, k0 + u * KS);
                 v[u] = q.v;
-                // theta_b + sum_{m<=j} (v_m / r) * dt  =  theta_b + j*w1 + j(j+1)/2 * (dv*dt/r); a hold (dv = 0) is the
-                // reference's exact arithmetic progression; a segment's last sample carries the replayed theta.
                 th[u] = q.last ? sg.acc : fma(q.tri, sg.dv * dtr, fma(q.fj, sg.s1, sg.s0));
+            };
+            // The reduction-only kernel is issue-bound: a thread's samples almost always lie in one segment (si is
+            // non-decreasing), so its record is read from shared memory once per thread, and speeds / angles are
+            // computed before the trigonometry (5.77 -> 5.12 ms per Mi config-4 circles).  The store kernels are
+            // latency-bound and 1.5 % slower that way (16.6 -> 16.85 ms): they keep one loop per sample.
+            constexpr bool SPLIT = REDUCE && !STORE;
+            if (SPLIT) {
+                if (si[0] == si[SPT - 1]) {
+                    const Seg sg = s_seg[si[0]];
+#pragma unroll
+                    for (int u = 0; u < SPT; ++u) speed_and_angle(sg, u);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < SPT; ++u) speed_and_angle(s_seg[si[u]], u);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) {
+                if (!SPLIT) speed_and_angle(s_seg[si[u]], u);
 #ifdef TGX_EXPERIMENT_NOTRIG
                 sn[u] = th[u] * 0.5; cn[u] = th[u] * 0.25;   // bandwidth experiment only: no trigonometry
 #else
