@@ -1,6 +1,6 @@
 // eval.cu — the evaluation kernel of libtgx: create{Circle,Line,Figure8}Goal for every (trajectory, k).
 //
-// One CTA per Tile (tile_size consecutive samples of one trajectory), one thread per SPT adjacent samples.
+// One CTA per Tile (tile_size consecutive samples of one trajectory).
 // The CTA stages its trajectory's TrajRec (64 B) and the tile's Seg records (64 B each) in shared memory,
 // every thread finds the segment its samples fall in, evaluates the closed form of the reference's
 // recurrences inside that segment
@@ -9,12 +9,21 @@
 //       theta_k = theta_b + S_k * (dt/r)          (Circle.cpp:50-51, Figure8.cpp:50-51: theta += (v/r)*dt)
 //       p_k     = p_b + S_k * (cos|sin theta) * dt            (Line.cpp:97-98: p = last + v*c*dt)
 // and then the reference's per-sample formulas (Circle.cpp:96-130, Line.cpp:91-115, Figure8.cpp:96-128) in
-// fp64.  The 14 channels go to struct-of-arrays planes with 128-bit (SPT=2) or 256-bit (SPT=4) streaming
-// vector stores: a warp writes 512 B / 1 KiB of contiguous, sector-aligned bytes per channel per instruction.
-// The kernel is store-bound: 112 B written per sample, ~0.3 B read.
+// fp64.  The kernel is store-bound: 112 B written per sample (128 B in record mode), ~0.3 B read.
 //
-// With REDUCE the per-trajectory maxima of |v_k|^2 and |a_k|^2 are reduced with warp shuffles, one shared-memory
-// hop per CTA and one atomicMax per tile (feasibility check, BASELINE.json configs 4-5).
+// One kernel template, four ways out (template flags):
+//   PTMA     struct-of-arrays planes through TMA (the default of tgx_eval for regular layouts): 128-thread CTAs walk
+//            the tile in passes of 256 samples, a warp owns 64 consecutive samples per pass (lane l: l and l + 32),
+//            stages [group][14 channels][32 samples] in its private shared memory and sends each group as one
+//            UTMASTG.3D box of a [trajectory][channel][sample] tensor map over the caller's planes (PlaneTma, store.cuh)
+//   STORE    the same planes with 128-bit (SPT=2) or 256-bit (SPT=4) streaming vector stores, one per thread per
+//            channel, a thread owning SPT adjacent samples: irregular layouts (per-trajectory offsets, channel
+//            subsets, short rows) and calls that also want the maxima
+//   RECORDS  one clamped 128-byte tgx_goal_record per sample (tgx_eval_records), staged in the 128-byte TMA swizzle and
+//            sent as 4 KiB UTMASTG.2D boxes (RecTma, store.cuh)
+//   REDUCE   per-trajectory maxima of |v_k|^2 and |a_k|^2 (feasibility check, BASELINE.json configs 4-5): integer
+//            REDUX.MAX warp reductions, one shared-memory hop per CTA and one atomicMax per tile; alone (no stores) it
+//            runs as 64-thread CTAs walking the tile in passes, 16 samples per thread per reduction
 #include <cuda_runtime.h>
 
 #include "tgx_internal.cuh"
