@@ -952,7 +952,10 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
 // extent is the coordinate range, not the allocation: the kernel only issues boxes that lie inside a trajectory's row.
 static int make_record_tmap(CUtensorMap* tmap, tgx_goal_record* d_records) {
     tmap_encode_fn encode = tmap_encoder();
-    if (!encode) return TGX_ERR_CUDA;
+    if (!encode) {
+        g_last_cuda_error = "cuTensorMapEncodeTiled is not available from this driver (tgx_eval_records needs TMA)";
+        return TGX_ERR_CUDA;
+    }
     const cuuint64_t dims[2] = {16, (cuuint64_t)1 << 31};
     const cuuint64_t strides[1] = {sizeof(tgx_goal_record)};
     const cuuint32_t box[2] = {16, 32};
@@ -960,7 +963,11 @@ static int make_record_tmap(CUtensorMap* tmap, tgx_goal_record* d_records) {
     const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_records, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? TGX_OK : TGX_ERR_CUDA;
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = "cuTensorMapEncodeTiled failed for the record buffer (CUresult " + std::to_string((int)r) + ")";
+        return TGX_ERR_CUDA;
+    }
+    return TGX_OK;
 }
 
 int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
