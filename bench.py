@@ -177,8 +177,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[args.workload].format(n=args.n_per_gpu),
-                   "step": f"generateTraj of the first {n_sample} trajectories of the workload into std::vector<Goal>, "
+        "config": {"workload": WORKLOAD_DESC[args.workload].format(n=args.n_per_gpu)},
+        "detail": {"step": f"generateTraj of the first {n_sample} trajectories of the workload into std::vector<Goal>, "
                            f"{threads} host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"first {n_sample} trajectories ({total_samples // args.steps} samples) per step"},
@@ -186,6 +186,308 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ---- extra legs of the default run: BASELINE.json configs[0], [2], [3], [4] -------------------------------------------
+# FP64 work of one circle sample on the reduction-only path, counted from csrc/eval.cu like the 112 algorithmic bytes
+# of the store path: seg_pos 4 (j(j+1)/2 and v = vb + j dv) + angle 3 + sincos_orbit 21 (1 scale-and-
+# round fma, 1 subtraction, 3 Cody-Waite fma, z = r*r, 5 + 5 polynomial fma, r*z, 2 + 2 final fma / mul) + omega 1 +
+# v^2/r 1 + v.x, v.y, a.x, a.y 4 + |v|^2, |a|^2 4 + two running-maximum compares 2 = 40 FP64-pipe instructions
+# (the quadrant selects, index arithmetic and segment bookkeeping are integer / move work on top of it).
+FP64_INSTR_PER_SAMPLE = 40
+
+
+class Ctx:
+    """What the extra legs share with the main leg."""
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def fp64_roofline(ctx, samples: int, eval_ms: float):
+    """Roofline of the reduction-only kernel against the DFMA peak measured in this run (tgx_probe_dfma)."""
+    dfma_per_s, probe_ms = ctx.eng.probe_dfma(3)
+    inst_per_s = FP64_INSTR_PER_SAMPLE * samples / (eval_ms * 1e-3)
+    return {"bound": "fp64", "achieved": 2e-12 * inst_per_s, "peak": 2e-12 * dfma_per_s, "unit": "TFLOP/s",
+            "frac": inst_per_s / dfma_per_s, "traffic": None,
+            "kernel": "tgx::eval_kernel<64, 4, STORE=false, REDUCE=true, ..., PASSES=4>",
+            "fp64_instr_per_sample": FP64_INSTR_PER_SAMPLE,
+            "convention": "every FP64-pipe instruction (DFMA / DMUL / DADD / DSETP) counted as one DFMA slot = 2 FLOP; "
+                          "achieved = 40 instr/sample x samples / kernel time (CUDA events), peak = DFMA micro-benchmark "
+                          "of this run (tgx_probe_dfma: 8 independent chains per thread, 1024 threads per SM, "
+                          "%.1f ms per launch, best of 3)" % probe_ms,
+            "peak_source": "measured in this run (no FP64 figure in MEASURED_PEAKS.json)"}
+
+
+def leg_cfg3(ctx, steps=5, warmup=2):
+    """BASELINE configs[2] as SURVEY.md 8d defines it: the mixed batch PLUS a braking trajectory (generateStopTraj from
+    k = N_i / 2, TrajectoryGenerator.cpp:514-517 -> Circle.cpp:132-169) for every tenth trajectory."""
+    import torch
+    from trajectory_generator_ros2_b200 import abi, workloads
+    eng, dev, n, rank, world = ctx.eng, ctx.dev, ctx.n, ctx.rank, ctx.world
+    params = workloads.mixed_cfg3(world * n, lo=rank * n, hi=(rank + 1) * n)
+    d_params = eng.upload_params(params)
+    counts, _ = eng.count(d_params)
+    total = int(counts.sum(dtype=torch.int64).item())
+    row = (int(counts.max().item()) + 1023) // 1024 * 1024
+    chunks = 1
+    while True:
+        try:
+            rows = (n + chunks - 1) // chunks
+            out = torch.empty((rows, abi.TGX_NCHAN, row), dtype=torch.float64, device=dev)
+            break
+        except torch.OutOfMemoryError:
+            chunks *= 2
+            if chunks > 64:
+                raise
+    rows = (n + chunks - 1) // chunks
+    chunk_params, stop_idx, stop_params, stop_k = [], [], [], []
+    for c in range(chunks):
+        dp = d_params[c * rows: min(n, (c + 1) * rows)]
+        idx = torch.arange(0, dp.shape[0], 10, device=dev)                 # every tenth trajectory brakes
+        chunk_params.append(dp)
+        stop_idx.append(idx)
+        stop_params.append(dp[idx].contiguous())
+        stop_k.append((counts[c * rows: c * rows + dp.shape[0]][idx] // 2).long())
+    # size the braking rows from an untimed pass
+    stop_cap, stop_total = 4, 0
+    for c in range(chunks):
+        eng.plan(chunk_params[c], want_outputs=False)
+        eng.eval(out[: chunk_params[c].shape[0]])
+        d_from = out[stop_idx[c], :, stop_k[c]].contiguous()
+        sp = eng.plan_stop(stop_params[c], d_from)
+        stop_cap = max(stop_cap, (int(sp.counts.max().item()) + 3) // 4 * 4)
+        stop_total += sp.total_samples
+    stop_out = torch.empty((int(stop_idx[0].shape[0]), abi.TGX_NCHAN, stop_cap), dtype=torch.float64, device=dev)
+    ev = {"eval": [], "stop": []}
+
+    def step(record):
+        for c in range(chunks):
+            dp = chunk_params[c]
+            eng.plan(dp, want_outputs=False)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            eng.eval(out[: dp.shape[0]])
+            e1.record()
+            # END pressed at k = N_i / 2: brake from that setpoint (the caller's gather of goals[pub_index] is plumbing)
+            d_from = out[stop_idx[c], :, stop_k[c]].contiguous()
+            eng.plan_stop(stop_params[c], d_from)
+            eng.eval(stop_out[: stop_idx[c].shape[0]])
+            e2.record()
+            if record:
+                ev["eval"].append((e0, e1))
+                ev["stop"].append((e1, e2))
+
+    for _ in range(warmup):
+        step(False)
+    ctx.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step(True)
+    t1.record()
+    ctx.barrier()
+    ms = ctx.allmax(t0.elapsed_time(t1) / steps)
+    eval_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev["eval"]])) * chunks)
+    stop_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev["stop"]])) * chunks)
+    job = ctx.allsum(total + stop_total)
+    peak, _ = measured_peak()
+    achieved = BYTES_PER_SAMPLE * total / (eval_ms * 1e-3) / 1e9
+    del out, stop_out
+    torch.cuda.empty_cache()
+    return {"workload": WORKLOAD_DESC["mixed_cfg3"].format(n=n) + "; every tenth trajectory additionally brakes from "
+                        "k = N_i/2 (tgx_plan_stop + tgx_eval, generateStopTraj)",
+            "value": job / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "samples_per_gpu": total, "braking_trajectories_per_gpu": int(sum(int(i.shape[0]) for i in stop_idx)),
+            "braking_samples_per_gpu": stop_total, "chunks": chunks, "row_stride": row,
+            "eval_ms_per_step": eval_ms, "braking_ms_per_step": stop_ms, "plan_ms_per_step": ms - eval_ms - stop_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "kernel": "tgx::eval_kernel (generateTraj samples only)"}}
+
+
+def leg_cfg4(ctx, steps=3, warmup=2):
+    """BASELINE configs[3]: 10^7 wide-range circles per GPU, max-|v| / max-|a| feasibility reduction only."""
+    import torch
+    from trajectory_generator_ros2_b200 import abi, workloads
+    eng, dev, rank, world = ctx.eng, ctx.dev, ctx.rank, ctx.world
+    n = ctx.args.cfg4_n
+    params = workloads.montecarlo_cfg4(world * n, lo=rank * n, hi=(rank + 1) * n)
+    d_params = eng.upload_params(params)
+    del params
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    flags = torch.empty(n, dtype=torch.uint8, device=dev)
+    mv = torch.empty(n, dtype=torch.float64, device=dev)
+    ma = torch.empty(n, dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    ev = []
+    total = 0
+
+    def step(record):
+        nonlocal total
+        total = eng.plan(d_params, limits=lim, want_outputs=False).total_samples
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.feasibility(lim, n, flags=flags, max_v=mv, max_a=ma, status=st)
+        b.record()
+        if record:
+            ev.append((a, b))
+
+    for _ in range(warmup):
+        step(False)
+    ctx.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step(True)
+    t1.record()
+    ctx.barrier()
+    ms = ctx.allmax(t0.elapsed_time(t1) / steps)
+    eval_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev])))
+    job = ctx.allsum(total)
+    res = {"workload": WORKLOAD_DESC["montecarlo_cfg4"].format(n=n), "value": job / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms, "steps": steps, "warmup": warmup, "samples_per_gpu": total,
+           "eval_ms_per_step": eval_ms, "plan_ms_per_step": ms - eval_ms,
+           "feasible_fraction": float(flags.float().mean()),
+           "step": "tgx_plan + tgx_feasibility, parameters resident in HBM",
+           "roofline": fp64_roofline(ctx, total, eval_ms)}
+    del d_params, flags, mv, ma, st
+    torch.cuda.empty_cache()
+    return res
+
+
+def leg_cfg5(ctx, steps=2, warmup=1):
+    """BASELINE configs[4]: the 10^8-trajectory sweep sharded over the GPUs of the box (strong scaling: the job is
+    fixed), every shard drawn on its own device (tgx_fill_montecarlo), then the NCCL all-gather of the 1-byte flags
+    issued through the C-ABI (tgx_gather_flags)."""
+    import torch
+    from trajectory_generator_ros2_b200 import abi, workloads
+    from trajectory_generator_ros2_b200.engine import Comm, shard_range
+    eng, dev, rank, world = ctx.eng, ctx.dev, ctx.rank, ctx.world
+    n_total = ctx.args.cfg5_total
+    lo, hi = shard_range(n_total, rank, world)
+    m = hi - lo
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_params = torch.empty((m, 128), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    a.record()
+    eng.fill_montecarlo(m, seed=1237, first_index=lo, out=d_params)
+    b.record()
+    torch.cuda.synchronize()
+    fill_ms = ctx.allmax(a.elapsed_time(b))
+    chunk = 1 << 24                                   # trajectories per plan: bounds the plan tables
+    flags = torch.empty(m, dtype=torch.uint8, device=dev)
+    full = torch.empty(n_total, dtype=torch.uint8, device=dev)
+    mv = torch.empty(min(m, chunk), dtype=torch.float64, device=dev)
+    ma = torch.empty(min(m, chunk), dtype=torch.float64, device=dev)
+    st = torch.empty(min(m, chunk), dtype=torch.int32, device=dev)
+    comm = Comm.from_torch_distributed(ctx.local_rank) if world > 1 else None
+    total = 0
+    ev_eval, ev_gather = [], []
+
+    def step(record):
+        nonlocal total
+        total = 0
+        for s in range(0, m, chunk):
+            k = min(chunk, m - s)
+            total += eng.plan(d_params[s:s + k], limits=lim, want_outputs=False).total_samples
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.feasibility(lim, k, flags=flags[s:s + k], max_v=mv[:k], max_a=ma[:k], status=st[:k])
+            e1.record()
+            if record:
+                ev_eval.append((e0, e1))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        if comm is not None:
+            comm.gather_flags(flags, n_total, out=full)
+        else:
+            full.copy_(flags)
+        g1.record()
+        if record:
+            ev_gather.append((g0, g1))
+
+    for _ in range(warmup):
+        step(False)
+    ctx.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step(True)
+    t1.record()
+    ctx.barrier()
+    ms = ctx.allmax(t0.elapsed_time(t1) / steps)
+    nchunks = (m + chunk - 1) // chunk
+    eval_ms = ctx.allmax(float(np.mean([x.elapsed_time(y) for x, y in ev_eval])) * nchunks)
+    gather_ms = ctx.allmax(float(np.mean([x.elapsed_time(y) for x, y in ev_gather])))
+    job = ctx.allsum(total)
+    ok = bool(torch.equal(full[lo:hi], flags))
+    feasible = int(full.sum(dtype=torch.int64).item())
+    # every rank must hold the same gathered vector: compare a checksum of checksums
+    chk = int((full.view(torch.int64)[: n_total // 8].sum().item()) & 0x7fffffffffff) if n_total >= 8 else feasible
+    same = ctx.allmax(float(chk)) == float(chk) and -ctx.allmax(-float(chk)) == float(chk)
+    res = {"workload": f"BASELINE configs[4]: {n_total} config-4 circles sharded over {world} GPU(s) "
+                       f"(tgx_shard_range), each shard drawn on its device (tgx_fill_montecarlo, Philox4x32-10, "
+                       f"seed 1237), feasibility only",
+           "value": job / (ms * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_step": ms, "steps": steps,
+           "warmup": warmup, "trajectories": n_total, "trajectories_per_gpu": m, "samples": job,
+           "eval_ms_per_step": eval_ms, "plan_ms_per_step": ms - eval_ms - gather_ms,
+           "flags_allgather_ms": gather_ms, "device_fill_ms": fill_ms,
+           "gather": ("tgx_gather_flags -> ncclAllGather of %d B per rank over NCCL %d, on the evaluation stream, "
+                      "inside the timed step" % (m, Comm.nccl_version())) if comm is not None else
+                     "one shard: device-to-device copy",
+           "gathered_equals_local_shard": ok, "gathered_identical_on_all_ranks": bool(same),
+           "feasible": feasible, "step": "per 2^24-trajectory chunk tgx_plan + tgx_feasibility, then the flag all-gather"}
+    if comm is not None:
+        comm.close()
+    del d_params, flags, full, mv, ma, st
+    torch.cuda.empty_cache()
+    return res
+
+
+def leg_cfg1(ctx):
+    """BASELINE configs[0] / BASELINE.md 4: ms per generateTraj of the default.yaml circle — the C++ drop-in class
+    (tests/cpp/bin/dropin_latency: count, plan, evaluate, D2H, repack into std::vector<Goal>) beside the reference class
+    on one host core (oracle/_ref; the reference's own timing hook is Circle.cpp:92).  Rank 0 only."""
+    from trajectory_generator_ros2_b200 import workloads
+    res = {"workload": "BASELINE configs[0]: Circle::generateTraj of config/default.yaml (25 001 samples), median of 20"}
+    exe = os.path.join(ROOT, "tests", "cpp", "bin", "dropin_latency")
+    if os.path.exists(exe):
+        env = dict(os.environ, TGX_DEVICE=str(ctx.local_rank))
+        r = subprocess.run([exe, "20"], capture_output=True, text=True, timeout=300, env=env)
+        try:
+            res["dropin"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            res["dropin"] = {"error": (r.stdout + r.stderr)[-300:]}
+    else:
+        res["dropin"] = {"unavailable": "tests/cpp/bin/dropin_latency not built (needs the reference headers at build time)"}
+    try:
+        from oracle_lib import Oracle, Reference
+        p = workloads.default_circle()
+        impl, kind = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
+        for _ in range(3):
+            impl.time_batch(p, 1)
+        ts = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            impl.time_batch(p, 1)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        res["cpu"] = {"kind": kind, "median_ms": float(np.median(ts)), "min_ms": float(min(ts)), "cores": 1,
+                      "call": "Circle::generateTraj into std::vector<Goal>, -O2 (the reference's flag-less build is slower)"}
+    except Exception as exc:     # the checker is optional here
+        res["cpu"] = {"error": str(exc)[:200]}
+    return res
+
+
+def run_extras(ctx):
+    extra = {}
+    t0 = time.perf_counter()
+    extra["cfg3"] = leg_cfg3(ctx)
+    extra["cfg4"] = leg_cfg4(ctx)
+    extra["cfg5"] = leg_cfg5(ctx)
+    if ctx.rank == 0:
+        extra["cfg1_latency"] = leg_cfg1(ctx)
+    extra["wall_s"] = time.perf_counter() - t0
+    return extra
 
 
 # ---- our arm ---------------------------------------------------------------------------------------------------
@@ -324,6 +626,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def allsum(x: int) -> int:
+        if world == 1:
+            return int(x)
+        t = torch.tensor([x], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t[0])
+
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -358,51 +674,73 @@ def run_ours(args):
     # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region) ----
     e2e = None
     if not feas_only and not args.no_e2e and not args.records:
-        eng.set_host_fill(not args.e2e_all_planes)
+        has_bounce = bool((params["type"] == abi.TGX_BOUNCE).any())     # Bounce moves along z: nothing is constant
+        fmt = "all" if has_bounce else args.e2e_format
+        eng.set_host_fill(fmt != "all")
         eng.set_host_layout(not args.e2e_traj_major)
         call_n = min(n, args.e2e_call)                       # trajectories per tgx_generate_host call
         hrow = (max_count + 3) // 4 * 4                      # host rows: the caller's capacity, no padding shipped
-        pin_out = PinnedArray((call_n, abi.TGX_NCHAN, hrow) if args.e2e_traj_major else (abi.TGX_NCHAN, call_n, hrow))
-        pin_params = PinnedArray((call_n,), dtype=abi.PARAMS_DTYPE)
-        h_counts_total = 0
+        hplanes = abi.TGX_NCHAN_VARYING if fmt == "compact" else abi.TGX_NCHAN
+        pin_out = PinnedArray((call_n, hplanes, hrow) if args.e2e_traj_major else (hplanes, call_n, hrow), engine=eng)
+        pin_params = PinnedArray((call_n,), dtype=abi.PARAMS_DTYPE, engine=eng)
+        gen = eng.generate_host_compact if fmt == "compact" else eng.generate_host
 
         def e2e_step():
             tot = 0
             for s in range(0, n, call_n):
                 m = min(call_n, n - s)
                 pin_params.array[:m] = params[s:s + m]
-                dst = pin_out.array[:m] if args.e2e_traj_major else pin_out.array.reshape(-1)[:abi.TGX_NCHAN * m * hrow].reshape(abi.TGX_NCHAN, m, hrow)
-                _, c, _, _ = eng.generate_host(pin_params.array[:m], hrow, out=dst)
+                dst = pin_out.array[:m] if args.e2e_traj_major else pin_out.array.reshape(-1)[:hplanes * m * hrow].reshape(hplanes, m, hrow)
+                c = gen(pin_params.array[:m], hrow, out=dst)[1]
                 tot += int(c.sum())
             return tot
 
         del out
         torch.cuda.empty_cache()
-        for _ in range(1):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+        e2e_step()                                           # warm-up (first touch of the pinned pages, plan learning)
+        step_s = []
+        h_counts_total = 0
+        for _ in range(max(3, args.e2e_steps)):
+            barrier()
+            t0 = time.perf_counter()
             h_counts_total = e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t[0])
+            barrier()
+            step_s.append(allmax(time.perf_counter() - t0))
         assert h_counts_total == total_samples
-        has_bounce = bool((params["type"] == abi.TGX_BOUNCE).any())     # Bounce moves along z: nothing is constant
-        planes = 14 if (args.e2e_all_planes or has_bounce) else 10
+        e2e_s = float(np.median(step_s))
+        planes = 14 if fmt == "all" else 10
+        d2h_bytes = int(n * (planes * hrow * 8 + 8))
+        # the ceiling of this box, measured in this run: a plain device->host copy of the same byte count into the
+        # same pinned buffer on every rank CONCURRENTLY (what PCIe and the host's memory absorb from N GPUs at once)
+        copy_bytes = min(pin_out.nbytes, call_n * planes * hrow * 8)
+        reps = max(1, int(round(n * planes * hrow * 8 / copy_bytes)))
+        barrier()
+        ceil_s = allmax(eng.probe_d2h(pin_out, copy_bytes, reps))
+        barrier()
+        ceiling_gbs = world * copy_bytes * reps / ceil_s / 1e9
+        achieved_gbs = world * d2h_bytes / e2e_s / 1e9
         e2e = {"value": job_samples / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(n * (planes * hrow * 8 + 8)), "host_row_capacity": hrow,
-               "wire_format": ("all 14 planes over PCIe" if planes == 14 else
-                               "10 varying planes over PCIe; the 4 constant planes (p.z = alt, v.z = a.z = j.z = 0) "
-                               "are written into the host buffer by host threads"),
-               "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s,
-               "call": f"tgx_generate_host, {call_n} trajectories per call into one reused pinned host buffer, "
-                       + ("trajectory-major [n][14][row]" if args.e2e_traj_major else
-                          "plane-major [14][n][row] (tgx_set_host_layout): contiguous 1-D copies per plane")}
+               "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": d2h_bytes, "host_row_capacity": hrow,
+               "wire_format": {"all": "all 14 planes over PCIe",
+                               "fill": "10 varying planes over PCIe; the 4 constant planes (p.z = alt, v.z = a.z = j.z = 0) "
+                                       "are written into the host buffer by host threads (112 B of host-memory writes "
+                                       "per sample)",
+                               "compact": "compact10 (tgx_generate_host_compact): the host buffer holds the 10 varying "
+                                          "planes; p.z = params.alt and v.z = a.z = j.z = 0 are the reference's literal "
+                                          "constants (Circle.cpp:109-121) and are not materialised (80 B of PCIe traffic "
+                                          "and of host-memory writes per sample)"}[fmt],
+               "steps": len(step_s), "ms_per_step": 1e3 * e2e_s, "ms_per_step_all": [1e3 * x for x in step_s],
+               "statistic": "median of the timed steps, each the max over ranks",
+               "achieved_gbs": achieved_gbs, "d2h_ceiling_gbs": ceiling_gbs, "frac": achieved_gbs / ceiling_gbs,
+               "ceiling": f"plain pinned D2H copy, {reps} x {copy_bytes / 1e9:.2f} GB per rank, all {world} rank(s) "
+                          f"concurrently, CUDA events, max over ranks (tgx_probe_d2h), aggregate GB/s",
+               "host": eng.host_info(),
+               "call": f"{'tgx_generate_host_compact' if fmt == 'compact' else 'tgx_generate_host'}, {call_n} "
+                       f"trajectories per call into one reused pinned host buffer, "
+                       + ("trajectory-major [n][planes][row]" if args.e2e_traj_major else
+                          "plane-major [planes][n][row] (tgx_set_host_layout): contiguous 1-D copies per plane")}
         eng.set_host_layout(False)
+        eng.set_host_fill(True)
         pin_out.free()
         pin_params.free()
     elif feas_only and not args.no_e2e:
@@ -430,20 +768,33 @@ def run_ours(args):
     gather_ms = None
     if feas_only and world > 1:
         # BASELINE configs[4]: the only exchange of the path, an all-gather of the 1-byte feasibility flags (NCCL)
-        from trajectory_generator_ros2_b200 import sharding
+        # issued by libtgx itself: tgx_gather_flags -> ncclAllGather (torch.distributed only couriers the unique id)
+        from trajectory_generator_ros2_b200.engine import Comm
+        comm = Comm.from_torch_distributed(local_rank)
         local = torch.cat(flags)
+        full = torch.empty(world * n, dtype=torch.uint8, device=dev)
         for _ in range(2):
-            sharding.gather_flags(local, world * n)
+            comm.gather_flags(local, world * n, out=full)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        full = sharding.gather_flags(local, world * n)
+        comm.gather_flags(local, world * n, out=full)
         b.record()
         barrier()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gather_ms = float(t[0])
-        assert full.numel() == world * n
+        gather_ms = allmax(a.elapsed_time(b))
+        assert torch.equal(full[rank * n:(rank + 1) * n], local)
+        comm.close()
+    extra = None
+    if args.workload == "circles_cfg2" and not args.no_extras and not args.records:
+        try:
+            del out
+        except NameError:
+            pass
+        del d_params, chunk_params
+        torch.cuda.empty_cache()
+        extra = run_extras(Ctx(eng=eng, dev=dev, n=n, rank=rank, world=world, local_rank=local_rank, args=args,
+                               barrier=barrier, allmax=allmax, allsum=allsum))
+    feas_roof = fp64_roofline(Ctx(eng=eng), total_samples, eval_ms) if (feas_only and rank == 0) else None
     if rank == 0:
         peak, peak_src = measured_peak()
         eval_bytes = BYTES_PER_SAMPLE * total_samples if not feas_only else 17 * n
@@ -456,6 +807,7 @@ def run_ours(args):
                    "sample": f"first {args.cpu_sample} trajectories of the workload ({s} samples), "
                              f"generateTraj into std::vector<Goal>, {dt:.2f} s wall"}
         roof_extra = {}
+        traffic = ncu_traffic(args.workload)
         if args.records:
             pack_ms = float(np.mean([a.elapsed_time(b) for a, b in pack_pairs])) * chunks
             pack_bytes = (BYTES_PER_SAMPLE + 128) * total_samples
@@ -476,8 +828,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD_DESC[args.workload].format(n=n),
+            "config": {"workload": WORKLOAD_DESC[args.workload].format(n=n)},
+            "detail": {
                 "trajectories_per_gpu": n, "samples_per_gpu": total_samples, "row_stride": row,
                 "layout": "plane-major [14][n][row]" if args.plane_major else "trajectory-major [n][14][row]",
                 "store_path": ("TMA: 32-sample x 14-channel boxes staged in shared memory (polyline plans and irregular "
@@ -495,19 +847,27 @@ def run_ours(args):
                 "eval_ms_per_step": eval_ms,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                         "frac": achieved / peak, "traffic": traffic,
                          "kernel": "tgx::eval_poly_kernel" if poly else "tgx::eval_kernel", "bytes_per_launch": eval_bytes / chunks,
                          "peak_source": peak_src + " — of measured" if "MEASURED" in peak_src else peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        if extra is not None:
+            line["extra"] = extra
+        if traffic is not None:
+            line["roofline"]["traffic_source"] = ("profiles/eval_traffic.json: dram__bytes_read.sum + "
+                                                  "dram__bytes_write.sum of this kernel from the committed ncu --set full "
+                                                  "capture, per sample, scaled to this launch (ncu cannot run inside a "
+                                                  "timed bench)")
         line["roofline"].update(roof_extra)
         if args.records:
-            line["config"]["step"] += " + tgx_pack_goals (clamp to the room box, pack to 128-byte records)"
+            line["detail"]["step"] += " + tgx_pack_goals (clamp to the room box, pack to 128-byte records)"
         if feas_only:
-            line["config"]["feasible_fraction"] = float(torch.cat(flags).float().mean())
-            line["config"]["flags_allgather_ms"] = gather_ms
-            line["roofline"]["note"] = ("reduction-only path: writes 17 B per trajectory, FP64-pipe- and issue-bound, "
-                                        "the HBM fraction is stated for information only")
+            line["detail"]["feasible_fraction"] = float(torch.cat(flags).float().mean())
+            line["detail"]["flags_allgather_ms"] = gather_ms
+            # reduction-only path: 17 B written per trajectory; bound by the FP64 pipe / instruction issue, not by HBM
+            feas_roof["hbm_for_information"] = {"achieved_gbs": achieved, "frac": achieved / peak}
+            line["roofline"] = feas_roof
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -607,9 +967,14 @@ def main():
     ap.add_argument("--tile-shift", type=int, default=0)
     ap.add_argument("--spt", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="trajectories timed on the CPU legs")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed end-to-end steps (at least 3; the median is reported)")
+    ap.add_argument("--e2e-format", default="compact", choices=["compact", "fill", "all"],
+                    help="host wire format of the e2e leg: compact10 (tgx_generate_host_compact, default), 10 planes + "
+                         "host-filled constants (tgx_generate_host), or all 14 planes")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg1 / cfg3 / cfg4 / cfg5 legs of the default run")
+    ap.add_argument("--cfg4-n", type=int, default=10_000_000, help="trajectories per GPU of the config-4 leg")
+    ap.add_argument("--cfg5-total", type=int, default=100_000_000, help="trajectories of the config-5 sweep (all GPUs)")
     ap.add_argument("--e2e-call", type=int, default=1 << 16)
-    ap.add_argument("--e2e-all-planes", action="store_true", help="ship all 14 planes over PCIe in the e2e leg")
     ap.add_argument("--e2e-traj-major", action="store_true",
                     help="e2e leg with the trajectory-major host layout [n][14][row] (2-D copies) instead of plane-major")
     ap.add_argument("--no-e2e", action="store_true")

@@ -175,7 +175,8 @@ enum tgx_error {
     TGX_ERR_ALIGNMENT = 3,    /* output layout not aligned for vector stores */
     TGX_ERR_NO_PLAN = 4,      /* tgx_eval / tgx_feasibility before tgx_plan */
     TGX_ERR_NOMEM = 5,        /* device or host allocation failed */
-    TGX_ERR_CAPACITY = 6      /* a caller-provided buffer is too small */
+    TGX_ERR_CAPACITY = 6,     /* a caller-provided buffer is too small */
+    TGX_ERR_COMM = 7          /* NCCL is missing or a collective failed; tgx_comm_last_error() has the text */
 };
 
 /* Room box + kinematic limits. Box follows trajectoryInsideBounds(xmin,xmax,ymin,ymax,zmin,zmax). */
@@ -449,6 +450,27 @@ int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, cons
                       double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
                       tgx_phases* h_phases);
 
+/* Compact wire format of tgx_generate_host for callers that declare it.  The z-components of every setpoint of the
+ * planar classes are literal constants in the reference (p.z = alt_, v.z = a.z = j.z = 0: Circle.cpp:109-121,
+ * Line.cpp:99-108, Figure8.cpp:110-119, Square.cpp:101-107), so the host buffer holds only the TGX_NCHAN_VARYING = 10
+ * planes that vary along a trajectory, in tgx_channel order with the four constant ones left out
+ * (TGX_COMPACT_PLANE(c): px py vx vy ax ay jx jy psi dpsi -> 0..9):
+ *     h_out10[(i*10 + q)*capacity + k]            (default)
+ *     h_out10[(q*n + i)*capacity + k]             (tgx_set_host_layout(e, 1): plane-major)
+ * and the consumer takes p.z from h_params[i].alt and v.z = a.z = j.z = 0 (the drop-in classes' repack into
+ * std::vector<Goal> does exactly that).  A sample then costs 80 bytes of PCIe traffic AND 80 bytes of host-memory
+ * writes, against 80 + 32 (constant planes written by host threads) for tgx_generate_host.  Padding (k >= N_i) is zero.
+ * h_phases / h_legs (either may be NULL) as in tgx_generate_host_legs.
+ * TGX_ERR_INVALID if the batch holds a TGX_BOUNCE trajectory (it moves along z: Bounce.cpp:39-41). */
+#define TGX_NCHAN_VARYING 10
+#define TGX_VARYING_CHANNEL_MASK 0x36dbu   /* all but TGX_PZ, TGX_VZ, TGX_AZ, TGX_JZ */
+/* plane index of channel c in the compact format, -1 for the constant channels */
+#define TGX_COMPACT_PLANE(c) \
+    (((c) % 3 == 2 && (c) < TGX_PSI) ? -1 : ((c) < TGX_PSI ? 2 * ((c) / 3) + (c) % 3 : (c) - 4))
+int tgx_generate_host_compact(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                              double* h_out10, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
+                              tgx_phases* h_phases, tgx_polyline_legs* h_legs);
+
 /* tgx_generate_host that additionally returns, for polyline-family trajectories, the leg structure their per-sample
  * index_msgs are a function of (h_legs[i].n == 0 for the other families).  A batch may mix families: every chunk is
  * routed to tgx_plan and / or tgx_plan_polyline as its trajectories require, and polyline records without
@@ -472,8 +494,10 @@ int tgx_stop_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const do
 /* Wire format of the host-buffer calls.  The z-components of every setpoint are literal constants in the reference
  * (p.z = alt_, v.z = a.z = j.z = 0: Circle.cpp:109-121, Line.cpp:99-108, Figure8.cpp:110-119).  With
  * fill_constants_on_host = 1 (default) the device evaluates and ships only the 10 varying planes over PCIe and host
- * threads write the 4 constant rows of each trajectory; with 0 all 14 planes are evaluated and shipped.  The host
- * buffer holds the same values either way. */
+ * threads write the 4 constant rows of each trajectory; with 0 all 14 planes are evaluated and shipped.  The samples
+ * (k < N_i) are the same either way.  Padding (k >= N_i, and every row of a rejected trajectory) is zero, except that
+ * with the host fill the p.z row holds alt over its whole capacity (the filling threads run before the counts are
+ * known). */
 int tgx_set_host_fill(tgx_engine* e, int fill_constants_on_host);
 
 /* Layout of the host buffers of tgx_generate_host / tgx_generate_host_legs / tgx_stop_host.
@@ -488,13 +512,77 @@ int tgx_set_host_layout(tgx_engine* e, int plane_major);
 int tgx_sample_host(tgx_engine* e, const tgx_params* h_params, double v, double accel, double s0, double s1,
                     double* h_out14);
 
-/* Page-locked host memory, so that the D2H copies of the calls above run asynchronously at full PCIe rate. */
+/* Page-locked host memory, so that the D2H copies of the calls above run asynchronously at full PCIe rate.
+ * tgx_alloc_host_for prefers pages of the NUMA node the engine's GPU is attached to (where the platform says which). */
 void* tgx_alloc_host(int64_t bytes);
+void* tgx_alloc_host_for(tgx_engine* e, int64_t bytes);
 void tgx_free_host(void* p);
 
-/* ---- sharding helper (multi-GPU: one process per GPU, contiguous block partition, no collective) ---- */
+/* How the host-buffer calls size themselves on this machine: the end-to-end rate is set by PCIe and by what the host's
+ * memory absorbs, so the threads that write the constant planes are sized to this process's share of the host — the
+ * CPUs it may run on (sched_getaffinity) divided by the processes on the node (environment LOCAL_WORLD_SIZE, or
+ * TGX_LOCAL_RANKS), half of that, at most 8 (TGX_FILLER_THREADS overrides) — and bound to the CPUs of the GPU's NUMA
+ * node when sysfs names one. */
+typedef struct tgx_host_info_t {
+    int32_t numa_node;        /* NUMA node of the GPU's PCIe slot; -1: unknown (single-node hosts, most VMs) */
+    int32_t cpus_allowed;     /* CPUs this process may run on */
+    int32_t local_ranks;      /* processes sharing the host */
+    int32_t filler_threads;   /* host threads tgx_generate_host uses for the constant planes */
+    int32_t filler_cpus;      /* CPUs they may run on */
+    int32_t reserved[3];
+} tgx_host_info_t;
+int tgx_host_info(tgx_engine* e, tgx_host_info_t* out);
+
+/* ---- multi-GPU: contiguous block partition, no data-path collective, one optional flag gather ------------ */
 /* Rank `rank` of `world` owns trajectories [*lo, *hi) of a batch of n. */
 int tgx_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+
+/* The only exchange of the path (BASELINE.json configs[4]: "NCCL gather of feasibility flags"): every GPU reduces its
+ * own shard with tgx_feasibility and the 1-byte flags are all-gathered over NVLink.  A tgx_comm wraps one NCCL
+ * communicator rank; NCCL is bound at run time (dlopen of libnccl.so.2 — a process that already carries one, e.g.
+ * torch's, shares it), and every entry point below returns TGX_ERR_COMM with tgx_comm_last_error() set if it is
+ * missing or a call fails.
+ *   one process per GPU:   rank 0 calls tgx_comm_unique_id and ships the 128 bytes to the other ranks by any means
+ *                          (bench.py: torch.distributed's store), then every rank calls tgx_comm_init_rank;
+ *   one process, all GPUs: tgx_comm_init_all(comms, ndev, devices) (ncclCommInitAll); the per-device
+ *                          tgx_gather_flags calls are then bracketed by tgx_comm_group_start / _end. */
+#define TGX_COMM_ID_BYTES 128
+typedef struct tgx_comm tgx_comm;
+const char* tgx_comm_last_error(void);
+int tgx_comm_nccl_version(int* version);                       /* e.g. 22809 */
+int tgx_comm_unique_id(char id[TGX_COMM_ID_BYTES]);
+int tgx_comm_init_rank(tgx_comm** out, int world, int rank, const char id[TGX_COMM_ID_BYTES], int device);
+int tgx_comm_init_all(tgx_comm** out /* [ndev] */, int ndev, const int* devices /* NULL: 0..ndev-1 */);
+int tgx_comm_destroy(tgx_comm* c);
+int tgx_comm_group_start(void);
+int tgx_comm_group_end(void);
+/* All-gather of per-shard flag vectors into the full vector: the calling rank holds d_local[hi - lo] for its
+ * tgx_shard_range(n_total, rank, world) and receives d_all[n_total] (both on the communicator's device), ordered on
+ * `stream`.  Equal shards: one ncclAllGather; shards that differ by one trajectory: one ncclBroadcast per shard
+ * inside a group.  c == NULL or a world of 1: a device-to-device copy. */
+int tgx_gather_flags(tgx_comm* c, const uint8_t* d_local, int64_t n_total, uint8_t* d_all, void* stream);
+
+/* ---- synthetic parameters drawn on the device (BASELINE.json configs[3]-[4]) ----------------------------- */
+/* Writes records first_index .. first_index + n - 1 of the config-4 Monte-Carlo distribution (circles, r ~ U[0.2, 5],
+ * centre ~ U[-2, 2]^2, alt ~ U[1, 2.5], v_goal ~ U[0.2, 8], accel ~ U[0.7, 2], dt = 0.01,
+ * t_traj = max(9.98 - 2 v / a, 0.5)) to d_params, record i from Philox4x32-10 with key = seed and counter = (i, draw):
+ * a shard of the 10^8-trajectory sweep needs no host->device parameter copy, and any record can be reproduced on
+ * the host (trajectory_generator_ros2_b200/workloads.py: montecarlo_philox, bit-identical). */
+int tgx_fill_montecarlo(tgx_engine* e, uint64_t seed, int64_t first_index, int64_t n, tgx_params* d_params,
+                        void* stream);
+
+/* ---- measurement probe: the FP64 roofline denominator of the reduction-only path -------------------------------- */
+/* tgx_feasibility writes 17 bytes per trajectory: it is bound by the FP64 pipe and by instruction issue, not by HBM, and
+ * MEASURED_PEAKS.json has no FP64 figure, so the peak is measured where the sweep runs: a hand-written
+ * kernel of independent DFMA chains (8 per thread, one full wave of 1024 threads per SM, ~20 ms per launch), best of
+ * `reps` launches after one warm-up, timed with CUDA events on the default stream.  *dfma_per_s = thread-level DFMA
+ * instructions per second (x 2 = FLOP/s). */
+int tgx_probe_dfma(tgx_engine* e, int reps, double* dfma_per_s, double* ms_per_launch);
+/* The ceiling of the host-buffer calls (tgx_generate_host*): `reps` plain device->host copies of `bytes` into the
+ * caller's page-locked buffer on the engine's copy stream, timed with CUDA events; *seconds = time of all reps.
+ * bench.py runs it on every rank concurrently, so the ceiling it reports is what PCIe AND the host's memory absorb
+ * from N GPUs at once. */
+int tgx_probe_d2h(tgx_engine* e, void* h_dst, int64_t bytes, int reps, double* seconds);
 
 /* ---- introspection used by bench.py ---------------------------------------------------------------- */
 /* Number of this library's own (hand-written) kernels launched on this engine since creation: plan_count,

@@ -31,3 +31,16 @@ def test_dropin_compiles_under_the_reference_names():
     r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "--no-print-directory", "-B",
                         "check-dropin-namespace"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_gather_flags_driver():
+    """tests/cpp/gather_flags.cpp: the multi-GPU split through the C-ABI alone (tgx_comm_init_all = ncclCommInitAll,
+    tgx_fill_montecarlo, tgx_plan, tgx_feasibility, tgx_gather_flags) on every visible GPU, equal and unequal shards."""
+    exe = os.path.join(ROOT, "tests", "cpp", "bin", "gather_flags")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/bin/gather_flags not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("gather_flags ok") == 2

@@ -9,6 +9,7 @@ import pytest
 
 from parity import assert_samples_close, merge_errors
 from trajectory_generator_ros2_b200 import abi, workloads
+from trajectory_generator_ros2_b200.engine import TgxError
 
 pytestmark = pytest.mark.gpu
 
@@ -496,6 +497,63 @@ def test_host_wire_formats_agree(engine):
         assert (a[i, abi.PZ, :ca[i]] == params["alt"][i]).all() and (a[i, abi.JZ, :ca[i]] == 0).all()
 
 
+def test_host_compact_wire_format(engine):
+    """tgx_generate_host_compact: the 10 varying planes, both host layouts, equal to the matching planes of
+    tgx_generate_host bit for bit; the constant planes are params['alt'] and zeros by contract."""
+    params = abi.concat([workloads.mixed_cfg3(600), workloads.default_circle(),
+                         engine.finalize_polyline(workloads.polyline_mix(64).copy())])
+    params = params[params["type"] != abi.TGX_BOUNCE]
+    cap = 25004
+    full, cf, sf, phf = engine.generate_host(params, cap, want_phases=True)
+    comp, cc, sc, phc, legs = engine.generate_host_compact(params, cap, want_phases=True, want_legs=True)
+    np.testing.assert_array_equal(cc, cf)
+    np.testing.assert_array_equal(sc, sf)
+    assert comp.shape == (len(params), abi.TGX_NCHAN_VARYING, cap)
+    for q, c in enumerate(abi.VARYING_CHANNELS):
+        for i in range(len(params)):
+            np.testing.assert_array_equal(comp[i, q, :cc[i]], full[i, c, :cc[i]])
+    for i in range(len(params)):
+        assert (full[i, abi.PZ, :cf[i]] == params["alt"][i]).all()
+        for c in (abi.VZ, abi.AZ, abi.JZ):
+            assert (full[i, c, :cf[i]] == 0).all()
+        assert (comp[i, :, cc[i]:] == 0).all(), "padding of the compact format must be zero"
+    assert (phc["n"] == phf["n"]).all()
+    # plane-major compact layout
+    engine.set_host_layout(True)
+    try:
+        pm, cp, sp, _, _ = engine.generate_host_compact(params, cap)
+    finally:
+        engine.set_host_layout(False)
+    np.testing.assert_array_equal(cp, cf)
+    np.testing.assert_array_equal(pm, comp.transpose(1, 0, 2))
+    # a Bounce trajectory moves along z: the compact format refuses it
+    with pytest.raises(TgxError):
+        engine.generate_host_compact(engine.finalize_polyline(workloads.default_polyline(abi.TGX_BOUNCE).copy()), 8004)
+    info = engine.host_info()
+    assert info["cpus_allowed"] >= 1 and 1 <= info["filler_threads"] <= 64 and info["local_ranks"] >= 1
+
+
+def test_host_padding_is_not_stale(engine):
+    """The device staging buffers are reused from call to call: the padding (k >= N_i, rows of rejected trajectories)
+    must come back as zeros, not as an earlier call's samples (p.z rows hold alt over their whole capacity)."""
+    long_p = workloads.circles_cfg2(64)
+    engine.generate_host(long_p, 1024)
+    short = abi.concat([abi.circle_params(alt=1.5, r=1.0, cx=0.0, cy=0.0, v_goals=[0.5], t_traj=0.2, accel=1.0, dt=0.01)
+                        for _ in range(63)] +
+                       [abi.circle_params(alt=1.5, r=-1.0, cx=0.0, cy=0.0, v_goals=[0.5], t_traj=0.2, accel=-1.0, dt=0.01)])
+    out, counts, status, _ = engine.generate_host(short, 1024)
+    assert status[63] & abi.ST_BAD_PARAM and counts[63] == 0
+    for i in range(64):
+        for c in range(abi.TGX_NCHAN):
+            if c == abi.PZ:
+                continue
+            assert (out[i, c, counts[i]:] == 0).all(), (i, c)
+    rec, rc, rs = engine.generate_records_host(long_p, 1024)
+    rec2, rc2, rs2 = engine.generate_records_host(short, 1024)
+    for i in range(64):
+        assert not rec2[i, rc2[i]:].tobytes().strip(b"\0"), f"stale records after sample {rc2[i]} of trajectory {i}"
+
+
 def test_generate_host_chunking(engine, oracle):
     """More rows than one 1 GiB staging chunk holds: exercises the double-buffered chunk loop."""
     params = workloads.circles_cfg2(24000)          # 24000 * 14 * 1024 * 8 B = 2.75 GB -> 3 chunks
@@ -795,3 +853,23 @@ def test_full_size_config2(engine, oracle):
     for j, i in enumerate(sub):
         ref, _, _ = oracle.generate(params[i:i + 1])
         assert_samples_close(host[j, :, :o_counts[i]], ref, f"full size[{i}]")
+
+
+def test_fill_montecarlo_matches_host_philox(engine, oracle):
+    """tgx_fill_montecarlo (csrc/params_gen.cu) draws the config-4 records on the device; workloads.montecarlo_philox
+    is the same arithmetic in numpy: byte-identical records, and the sweep over them matches the oracle."""
+    import torch
+    n, first = 70001, 123456789
+    d = engine.fill_montecarlo(n, seed=1237, first_index=first)
+    torch.cuda.synchronize()
+    host = workloads.montecarlo_philox(first + n, seed=1237, lo=first, hi=first + n)
+    assert d.cpu().numpy().tobytes() == host.tobytes()
+    # beyond 2^32 the index spills into the second counter word
+    big = engine.fill_montecarlo(64, seed=(7 << 32) | 9, first_index=(1 << 32) - 32)
+    assert big.cpu().numpy().tobytes() == workloads.montecarlo_philox((1 << 32) + 32, seed=(7 << 32) | 9,
+                                                                      lo=(1 << 32) - 32, hi=(1 << 32) + 32).tobytes()
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    engine.plan(d[:3000], limits=lim)
+    flags, mv, ma, st = engine.feasibility(lim, 3000)
+    o_flags = oracle.feasibility_batch(host[:3000], lim)[0]
+    assert (flags.cpu().numpy() != o_flags).sum() <= 1      # a maximum within 1e-8 of a limit may land on either side

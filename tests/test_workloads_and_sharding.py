@@ -24,6 +24,26 @@ def test_workloads_are_shard_invariant():
         assert fn(10, lo=3, hi=3).shape == (0,)
 
 
+def test_philox_known_answers_and_montecarlo_stream(oracle):
+    """The counter-based generator behind tgx_fill_montecarlo (config 5 draws its shards on the device): Philox4x32-10
+    against the Random123 known-answer vectors, shard invariance, and the config-4 distribution."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = workloads.philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert tuple(int(x) for x in got) == want
+    full = workloads.montecarlo_philox(100000)
+    assert full[40000:70001].tobytes() == workloads.montecarlo_philox(100000, lo=40000, hi=70001).tobytes()
+    assert workloads.montecarlo_philox(100000, seed=1238)[:100].tobytes() != full[:100].tobytes()
+    assert 0.2 <= full["r"].min() and full["r"].max() < 5.0 and abs(full["r"].mean() - 2.6) < 0.03
+    v = full["v_goals"][:, 0]
+    assert 0.2 <= v.min() and v.max() < 8.0 and abs(v.mean() - 4.1) < 0.05 and (full["t_traj"] >= 0.5).all()
+    counts, status = oracle.count_batch(full[:4000])
+    assert (status == 0).all() and 900 < counts.mean() < 1300
+
+
 def test_cfg3_mix_and_line_feasibility(oracle):
     p = workloads.mixed_cfg3(30000)
     frac = np.bincount(p["type"], minlength=3) / len(p)

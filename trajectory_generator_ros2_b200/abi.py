@@ -62,7 +62,9 @@ STATUS_NAMES = {
 }
 
 # enum tgx_error
-TGX_OK, TGX_ERR_INVALID, TGX_ERR_CUDA, TGX_ERR_ALIGNMENT, TGX_ERR_NO_PLAN, TGX_ERR_NOMEM, TGX_ERR_CAPACITY = range(7)
+(TGX_OK, TGX_ERR_INVALID, TGX_ERR_CUDA, TGX_ERR_ALIGNMENT, TGX_ERR_NO_PLAN, TGX_ERR_NOMEM, TGX_ERR_CAPACITY,
+ TGX_ERR_COMM) = range(8)
+TGX_COMM_ID_BYTES = 128
 
 # enum tgx_phase_kind
 PH_ACCEL_TO, PH_REACHED, PH_DECEL, PH_STOPPED, PH_PRESSED_END = range(5)
@@ -106,6 +108,17 @@ class Layout(C.Structure):
     _fields_ = [("d_base", C.c_void_p), ("traj_stride", C.c_int64), ("chan_stride", C.c_int64),
                 ("d_traj_offset", C.c_void_p), ("capacity", C.c_int64), ("channel_mask", C.c_uint32),
                 ("reserved", C.c_uint32)]
+
+
+TGX_NCHAN_VARYING = 10
+VARYING_CHANNELS = (0, 1, 3, 4, 6, 7, 9, 10, 12, 13)      # tgx_compact_plane: px py vx vy ax ay jx jy psi dpsi
+VARYING_CHANNEL_MASK = 0x36DB
+
+
+class HostInfo(C.Structure):
+    """struct tgx_host_info_t."""
+    _fields_ = [("numa_node", C.c_int32), ("cpus_allowed", C.c_int32), ("local_ranks", C.c_int32),
+                ("filler_threads", C.c_int32), ("filler_cpus", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Phases(C.Structure):

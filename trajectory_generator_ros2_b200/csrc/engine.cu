@@ -18,6 +18,11 @@
 #include <thread>
 #include <vector>
 
+#include <pthread.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
@@ -52,6 +57,8 @@ cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, 
                                         const double* max_a, double v_max, double a_max, uint8_t* flags,
                                         uint32_t* status_out, cudaStream_t stream);
 
+cudaError_t launch_dfma_probe(int ctas, int trips, double* sink, double* dfma_count, cudaStream_t stream);
+cudaError_t launch_fill_montecarlo(uint64_t seed, int64_t first, int64_t n, tgx_params* out, cudaStream_t stream);
 cudaError_t launch_selftest_division(int64_t n, uint64_t seed, int per_thread, unsigned long long* mismatches,
                                      cudaStream_t stream);
 cudaError_t launch_plan_samples(const tgx_params* params, const double* state, int64_t n, TrajRec* recs, Seg* segs,
@@ -230,6 +237,14 @@ struct tgx_engine {
     cudaStream_t hs[2] = {nullptr, nullptr};
     cudaEvent_t hev[2] = {nullptr, nullptr};       // slot's D2H copies done -> its staging buffers are reusable
     cudaEvent_t hev_eval = nullptr;                // last evaluation done -> the shared plan tables are reusable
+    // host topology of the host-buffer path (resolved once per engine, host_topology())
+    bool topo_ready = false;
+    int numa_node = -1;                            // NUMA node of the GPU's PCIe slot (-1: unknown / a single-node VM)
+    int cpus_allowed = 0;                          // CPUs this process may run on (sched_getaffinity)
+    int local_ranks = 1;                           // processes sharing the host (LOCAL_WORLD_SIZE)
+    int filler_threads = 1;                        // host threads that write the constant planes
+    cpu_set_t filler_cpus;                         // where they run: the allowed CPUs of the GPU's NUMA node
+    bool filler_cpus_valid = false;
     DevBuf h_params[2], h_out[2], h_cnt[2], h_st[2], h_ph[2], h_from[2], h_rec[2];
 };
 
@@ -654,6 +669,108 @@ tgx::OutView make_view(const tgx_layout* out) {
 
 }  // namespace
 
+// ---- host topology of the host-buffer path ------------------------------------------------------------------
+// The end-to-end rate of the host-buffer calls is set by PCIe and by what the host's memory absorbs, so the host side
+// is sized to the share of the machine this process owns: the CPUs it may run on (sched_getaffinity) divided by the
+// processes that share the node (LOCAL_WORLD_SIZE, one per GPU under torchrun), and — where the platform exposes it —
+// the NUMA node the GPU's PCIe slot hangs off, for the filler threads and for the pinned allocations.
+static bool parse_cpulist(const char* text, cpu_set_t* set) {
+    CPU_ZERO(set);
+    bool any = false;
+    const char* p = text;
+    while (*p) {
+        char* end = nullptr;
+        long a = std::strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        p = end;
+        if (*p == '-') {
+            b = std::strtol(p + 1, &end, 10);
+            if (end == p + 1) break;
+            p = end;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (c >= 0) { CPU_SET((int)c, set); any = true; }
+        while (*p == ',' || *p == ' ' || *p == '\n') ++p;
+    }
+    return any;
+}
+
+static bool read_small_file(const std::string& path, char* buf, size_t cap) {
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    const size_t got = std::fread(buf, 1, cap - 1, f);
+    std::fclose(f);
+    buf[got] = 0;
+    return got > 0;
+}
+
+static void host_topology(tgx_engine* e) {
+    if (e->topo_ready) return;
+    e->topo_ready = true;
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    int ncpu = 0;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) ncpu = CPU_COUNT(&allowed);
+    if (ncpu <= 0) {
+        ncpu = (int)std::max(1u, std::thread::hardware_concurrency());
+        for (int c = 0; c < ncpu && c < CPU_SETSIZE; ++c) CPU_SET(c, &allowed);
+    }
+    e->cpus_allowed = ncpu;
+    int ranks = 1;
+    for (const char* name : {"TGX_LOCAL_RANKS", "LOCAL_WORLD_SIZE"}) {
+        const char* v = std::getenv(name);
+        if (v && std::atoi(v) > 0) { ranks = std::atoi(v); break; }
+    }
+    e->local_ranks = ranks;
+    // NUMA node of the GPU (sysfs; -1 on single-node hosts and in most VMs)
+    char bus[32] = {0}, buf[4096];
+    e->numa_node = -1;
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), e->device) == cudaSuccess) {
+        for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+        if (read_small_file(std::string("/sys/bus/pci/devices/") + bus + "/numa_node", buf, sizeof(buf)))
+            e->numa_node = std::atoi(buf);
+    } else {
+        cudaGetLastError();
+    }
+    cpu_set_t local = allowed;
+    if (e->numa_node >= 0 &&
+        read_small_file("/sys/devices/system/node/node" + std::to_string(e->numa_node) + "/cpulist", buf, sizeof(buf))) {
+        cpu_set_t node;
+        if (parse_cpulist(buf, &node)) {
+            cpu_set_t both;
+            CPU_AND(&both, &node, &allowed);
+            if (CPU_COUNT(&both) > 0) local = both;
+        }
+    }
+    e->filler_cpus = local;
+    e->filler_cpus_valid = true;
+    // half of this process's share of the CPUs it may use, at most 8 (a memset stream saturates well before that)
+    const int share = std::max(1, std::min(ncpu, CPU_COUNT(&local) * std::max(1, ranks)) / std::max(1, ranks));
+    e->filler_threads = std::max(1, std::min(8, share / 2));
+    if (const char* v = std::getenv("TGX_FILLER_THREADS"))
+        if (std::atoi(v) > 0) e->filler_threads = std::min(64, std::atoi(v));
+}
+
+// MPOL_PREFERRED for the calling thread while `fn` allocates (no libnuma in the image: the raw system call)
+template <class F>
+static void with_preferred_node(int node, F fn) {
+#ifdef SYS_set_mempolicy
+    constexpr int kMpolDefault = 0, kMpolPreferred = 1;
+    bool set = false;
+    if (node >= 0 && node < 1024) {
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        set = syscall(SYS_set_mempolicy, kMpolPreferred, mask, sizeof(mask) * 8 + 1) == 0;
+    }
+    fn();
+    if (set) syscall(SYS_set_mempolicy, kMpolDefault, nullptr, 0);
+#else
+    (void)node;
+    fn();
+#endif
+}
+
 extern "C" {
 
 int tgx_version(void) { return TGX_VERSION; }
@@ -667,6 +784,7 @@ const char* tgx_strerror(int code) {
         case TGX_ERR_NO_PLAN: return "no current plan: call tgx_plan first";
         case TGX_ERR_NOMEM: return "out of memory";
         case TGX_ERR_CAPACITY: return "capacity exceeded";
+        case TGX_ERR_COMM: return "NCCL error (see tgx_comm_last_error)";
         default: return "unknown error";
     }
 }
@@ -1055,6 +1173,83 @@ int tgx_transitions_host(tgx_engine* e, const tgx_transition_params* h_tparams, 
     return TGX_OK;
 }
 
+// FP64 peak of this GPU as a DFMA micro-benchmark (probe.cu): best of `reps` timed launches after one warm-up.
+int tgx_probe_dfma(tgx_engine* e, int reps, double* dfma_per_s, double* ms_per_launch) {
+    if (!e || !dfma_per_s || reps < 1) return TGX_ERR_INVALID;
+    TGX_CUDA(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    TGX_CUDA(cudaGetDeviceProperties(&prop, e->device));
+    const int ctas = prop.multiProcessorCount * 4;          // one full wave of 4 x 256 threads per SM
+    const int trips = 4096;                                 // x 128 DFMA per thread per trip: ~20 ms on a B200
+    DevBuf sink;
+    int rc = sink.reserve((size_t)ctas * 256 * sizeof(double));
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    TGX_CUDA(cudaEventCreate(&a));
+    TGX_CUDA(cudaEventCreate(&b));
+    double best_ms = 1e30, count = 0.0;
+    cudaError_t err = cudaSuccess;
+    for (int r = 0; r <= reps && err == cudaSuccess; ++r) {
+        cudaEventRecord(a, nullptr);
+        err = tgx::launch_dfma_probe(ctas, trips, sink.as<double>(), &count, nullptr);
+        cudaEventRecord(b, nullptr);
+        if (err == cudaSuccess) err = cudaEventSynchronize(b);
+        float ms = 0.f;
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, a, b);
+        if (r > 0 && ms > 0.f && (double)ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    sink.release();
+    if (err != cudaSuccess) return cuda_fail(err, "tgx_probe_dfma");
+    e->launches += reps + 1;
+    *dfma_per_s = count / (best_ms * 1e-3);
+    if (ms_per_launch) *ms_per_launch = best_ms;
+    return TGX_OK;
+}
+
+// The end-to-end ceiling of the host-buffer calls on this machine, measured where they run: `reps` plain
+// device->host copies of `bytes` into the caller's (pinned) buffer on the engine's copy stream, CUDA events.
+int tgx_probe_d2h(tgx_engine* e, void* h_dst, int64_t bytes, int reps, double* seconds) {
+    if (!e || !h_dst || bytes <= 0 || reps < 1 || !seconds) return TGX_ERR_INVALID;
+    TGX_CUDA(cudaSetDevice(e->device));
+    int rc = host_streams(e);
+    if (rc) return rc;
+    DevBuf src;
+    if ((rc = src.reserve((size_t)bytes))) return rc;
+    cudaStream_t s = e->hs[0];
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t err = cudaMemsetAsync(src.p, 0x3c, (size_t)bytes, s);
+    if (err == cudaSuccess) err = cudaEventCreate(&a);
+    if (err == cudaSuccess) err = cudaEventCreate(&b);
+    // warm-up: the first touch of a fresh pinned buffer is slower than the steady state
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(h_dst, src.p, (size_t)std::min<int64_t>(bytes, (int64_t)256 << 20), cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaEventRecord(a, s);
+    for (int r = 0; r < reps && err == cudaSuccess; ++r)
+        err = cudaMemcpyAsync(h_dst, src.p, (size_t)bytes, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaEventRecord(b, s);
+    if (err == cudaSuccess) err = cudaEventSynchronize(b);
+    float ms = 0.f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, a, b);
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    src.release();
+    if (err != cudaSuccess) return cuda_fail(err, "tgx_probe_d2h");
+    *seconds = (double)ms * 1e-3;
+    return TGX_OK;
+}
+
+int tgx_fill_montecarlo(tgx_engine* e, uint64_t seed, int64_t first_index, int64_t n, tgx_params* d_params,
+                        void* stream) {
+    if (!e || n < 0 || first_index < 0 || (n > 0 && !d_params)) return TGX_ERR_INVALID;
+    if (n == 0) return TGX_OK;
+    TGX_CUDA(cudaSetDevice(e->device));
+    TGX_CUDA(tgx::launch_fill_montecarlo(seed, first_index, n, d_params, static_cast<cudaStream_t>(stream)));
+    e->launches += 1;
+    return TGX_OK;
+}
+
 int tgx_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi) {
     if (n < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return TGX_ERR_INVALID;
     // floor(rank*n/world) without overflow for n < 2^62 / world
@@ -1089,8 +1284,30 @@ void* tgx_alloc_host(int64_t bytes) {
     }
     return p;
 }
+// The same, with the pages preferably taken from the NUMA node the engine's GPU is attached to.
+void* tgx_alloc_host_for(tgx_engine* e, int64_t bytes) {
+    if (!e) return tgx_alloc_host(bytes);
+    if (bytes <= 0 || cudaSetDevice(e->device) != cudaSuccess) return nullptr;
+    host_topology(e);
+    void* p = nullptr;
+    with_preferred_node(e->numa_node, [&] { p = tgx_alloc_host(bytes); });
+    return p;
+}
 void tgx_free_host(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+int tgx_host_info(tgx_engine* e, tgx_host_info_t* out) {
+    if (!e || !out) return TGX_ERR_INVALID;
+    TGX_CUDA(cudaSetDevice(e->device));
+    host_topology(e);
+    out->numa_node = e->numa_node;
+    out->cpus_allowed = e->cpus_allowed;
+    out->local_ranks = e->local_ranks;
+    out->filler_threads = e->filler_threads;
+    out->filler_cpus = e->filler_cpus_valid ? CPU_COUNT(&e->filler_cpus) : 0;
+    out->reserved[0] = out->reserved[1] = out->reserved[2] = 0;
+    return TGX_OK;
 }
 
 // ---- host-buffer calls --------------------------------------------------------------------------------------
@@ -1172,10 +1389,12 @@ static int eval_chunk(tgx_engine* e, const tgx_layout* lay, const tgx_limits* li
 }
 
 // Shared body of tgx_generate_host / tgx_stop_host.
+// compact: the host buffer holds only the TGX_NCHAN_VARYING planes that vary along a trajectory (tgx.h:
+// tgx_generate_host_compact); nothing is written for the constant ones.
 static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_from, int64_t n,
                     const tgx_limits* limits, double* h_out, int64_t capacity, int32_t* h_counts,
                     uint32_t* h_status, tgx_phases* h_phases, tgx_polyline_legs* h_legs,
-                    tgx_goal_record* h_records = nullptr) {
+                    tgx_goal_record* h_records = nullptr, bool compact = false) {
     // h_records != nullptr: the samples stay on the device; what travels is one clamped 128-byte record per sample
     if (!e || n < 0 || (n > 0 && (!h_params || (!h_out && !h_records))) || capacity < 0) return TGX_ERR_INVALID;
     if (capacity % 4 != 0) return TGX_ERR_ALIGNMENT;
@@ -1210,18 +1429,26 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
     // The z-components are literal constants in the reference (p.z = alt_, v.z = a.z = j.z = 0: Circle.cpp:109-121,
     // Line.cpp:99-108, Figure8.cpp:110-119).  They are not worth 29 % of the PCIe traffic: the device evaluates and
     // ships the 10 varying planes, and host threads write the 4 constant rows of every trajectory meanwhile.
-    const bool fill = e->host_fill_constants && capacity > 0 && !whole.bounce && !h_records;
+    if (compact && (whole.bounce || h_records || h_from)) return TGX_ERR_INVALID;
+    // `fill`: the device evaluates and ships the varying planes only (always so in the compact format)
+    const bool fill = (compact || e->host_fill_constants) && capacity > 0 && !whole.bounce && !h_records;
+    const int64_t hplanes = compact ? TGX_NCHAN_VARYING : TGX_NCHAN;     // planes of the HOST buffer
     // Plane-major host buffers ([14][n][capacity]): every plane of a chunk is ONE contiguous run on both sides of the
     // bus, so the D2H copies are plain 1-D copies (52+ GB/s on a Gen5 x16 link) instead of 2-D copies of 16 KB runs
     // (46 GB/s).  The device staging buffer uses the same layout per chunk.
     const bool plane_major = e->host_plane_major && !h_records;
     std::vector<std::thread> fillers;
-    if (fill) {
-        unsigned hw = std::thread::hardware_concurrency();
-        const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(hw ? hw / 2 : 1, 8u), n));
+    if (fill && !compact) {
+        // Sized to this process's share of the host (CPUs it may use / processes on the node) and bound to the CPUs of
+        // the GPU's NUMA node: 8 ranks x 8 threads on a 32-core host only fought the DMA engines for memory bandwidth.
+        host_topology(e);
+        const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(e->filler_threads, n));
+        const bool bind = e->filler_cpus_valid && e->numa_node >= 0;
+        const cpu_set_t cpus = e->filler_cpus;
         for (int t = 0; t < nthreads; ++t) {
             const int64_t a = n * t / nthreads, z = n * (t + 1) / nthreads;
             fillers.emplace_back([=] {
+                if (bind) pthread_setaffinity_np(pthread_self(), sizeof(cpus), &cpus);
                 for (int64_t i = a; i < z; ++i) {
                     // element (i, c, k) of the host buffer
                     const int64_t ts = plane_major ? capacity : TGX_NCHAN * capacity;
@@ -1267,6 +1494,13 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         lay.chan_stride = plane_major ? m * capacity : capacity;
         lay.capacity = capacity;
         lay.channel_mask = fill ? kVaryingChannels : 0;
+        // the staging buffers are reused from call to call: clear the slot so that the padding (k >= N_i, and every
+        // row of a rejected trajectory) reaches the caller as zeros, not as an earlier call's samples or records
+        // (a device memset at HBM rate: ~0.15 ms per GiB against ~20 ms of PCIe time for the same bytes)
+        if (capacity > 0 && h_records)
+            TGX_CUDA(cudaMemsetAsync(e->h_rec[b].p, 0, (size_t)(m * capacity) * sizeof(tgx_goal_record), s));
+        else if (capacity > 0)
+            TGX_CUDA(cudaMemsetAsync(e->h_out[b].p, 0, (size_t)(m * row_bytes), s));
         // planning synchronises stream s once; the other slot's D2H copies keep running meanwhile.  Braking plans take
         // every family in one pass; generateTraj plans route each family to its own planner (a mixed chunk is planned
         // and evaluated twice, each pass writing only its own trajectories' rows).
@@ -1299,9 +1533,11 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
                                      (size_t)(m * capacity) * sizeof(tgx_goal_record), cudaMemcpyDeviceToHost, s));
         } else if (capacity > 0 && plane_major) {
             TGX_CUDA(cudaEventRecord(e->hev_eval, s));
-            for (int c = 0; c < TGX_NCHAN; ++c) {
+            for (int c = 0, q = 0; c < TGX_NCHAN; ++c) {
                 if (fill && !(kVaryingChannels & (1u << c))) continue;
-                TGX_CUDA(cudaMemcpyAsync(h_out + ((int64_t)c * n + lo) * capacity,
+                const int64_t hc = compact ? q : c;      // plane index in the host buffer
+                ++q;
+                TGX_CUDA(cudaMemcpyAsync(h_out + (hc * n + lo) * capacity,
                                          e->h_out[b].as<double>() + (int64_t)c * m * capacity,
                                          (size_t)(m * capacity) * sizeof(double), cudaMemcpyDeviceToHost, s));
             }
@@ -1311,9 +1547,11 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
                 // the varying planes come in adjacent pairs (px,py | vx,vy | ax,ay | jx,jy | psi,dpsi): five 2-D copies,
                 // each moving 2 rows of every trajectory of the chunk
                 const size_t pitch = (size_t)row_bytes, width = (size_t)(2 * capacity) * sizeof(double);
+                const size_t hpitch = (size_t)(hplanes * capacity) * sizeof(double);
                 for (int q = 0; q < 5; ++q) {
                     const size_t off = (size_t)(3 * q) * (size_t)capacity;
-                    TGX_CUDA(cudaMemcpy2DAsync(h_out + lo * TGX_NCHAN * capacity + off, pitch,
+                    const size_t hoff = (size_t)((compact ? 2 : 3) * q) * (size_t)capacity;
+                    TGX_CUDA(cudaMemcpy2DAsync(h_out + lo * hplanes * capacity + hoff, hpitch,
                                                e->h_out[b].as<double>() + off, pitch, width, (size_t)m,
                                                cudaMemcpyDeviceToHost, s));
                 }
@@ -1375,6 +1613,13 @@ int tgx_sample_host(tgx_engine* e, const tgx_params* h_params, double v, double 
 int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits, double* h_out,
                       int64_t capacity, int32_t* h_counts, uint32_t* h_status, tgx_phases* h_phases) {
     return host_run(e, h_params, nullptr, n, limits, h_out, capacity, h_counts, h_status, h_phases, nullptr);
+}
+
+int tgx_generate_host_compact(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
+                              double* h_out10, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
+                              tgx_phases* h_phases, tgx_polyline_legs* h_legs) {
+    return host_run(e, h_params, nullptr, n, limits, h_out10, capacity, h_counts, h_status, h_phases, h_legs, nullptr,
+                    true);
 }
 
 int tgx_generate_host_legs(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,

@@ -78,8 +78,22 @@ def _load() -> C.CDLL:
     lib.tgx_plan_samples.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.tgx_sample_host.argtypes = [vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp]
     lib.tgx_selftest_division.argtypes = [vp, i64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    lib.tgx_probe_dfma.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.tgx_probe_d2h.argtypes = [vp, vp, i64, C.c_int, C.POINTER(C.c_double)]
+    lib.tgx_fill_montecarlo.argtypes = [vp, C.c_uint64, i64, i64, vp, vp]
+    lib.tgx_comm_last_error.restype = C.c_char_p
+    lib.tgx_comm_nccl_version.argtypes = [C.POINTER(C.c_int)]
+    lib.tgx_comm_unique_id.argtypes = [C.c_char_p]
+    lib.tgx_comm_init_rank.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_char_p, C.c_int]
+    lib.tgx_comm_init_all.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_int)]
+    lib.tgx_comm_destroy.argtypes = [vp]
+    lib.tgx_gather_flags.argtypes = [vp, vp, i64, vp, vp]
     lib.tgx_alloc_host.restype = vp
     lib.tgx_alloc_host.argtypes = [i64]
+    lib.tgx_alloc_host_for.restype = vp
+    lib.tgx_alloc_host_for.argtypes = [vp, i64]
+    lib.tgx_host_info.argtypes = [vp, C.POINTER(abi.HostInfo)]
+    lib.tgx_generate_host_compact.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp]
     lib.tgx_free_host.argtypes = [vp]
     return lib
 
@@ -123,9 +137,12 @@ class Plan:
 class PinnedArray:
     """A numpy view over page-locked host memory obtained from tgx_alloc_host."""
 
-    def __init__(self, shape, dtype=np.float64):
+    def __init__(self, shape, dtype=np.float64, engine: "Engine" = None):
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        self.ptr = lib().tgx_alloc_host(max(self.nbytes, 1))
+        if engine is not None:      # pages preferably from the NUMA node of the engine's GPU
+            self.ptr = lib().tgx_alloc_host_for(engine._h, max(self.nbytes, 1))
+        else:
+            self.ptr = lib().tgx_alloc_host(max(self.nbytes, 1))
         if not self.ptr:
             raise MemoryError(f"tgx_alloc_host({self.nbytes}) failed")
         buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
@@ -142,6 +159,67 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+class Comm:
+    """One rank of the flag all-gather (tgx_comm: an NCCL communicator behind the C-ABI, include/tgx.h).
+
+    torch.distributed is only the courier of the 128-byte NCCL unique id; the collective itself is issued by
+    libtgx (tgx_gather_flags -> ncclAllGather) on the caller's CUDA stream.
+    """
+
+    def __init__(self, handle, world: int, rank: int, device: int):
+        self._h, self.world, self.rank, self.device = handle, world, rank, device
+
+    @staticmethod
+    def _raise(rc: int, what: str):
+        text = lib().tgx_comm_last_error().decode() if rc == abi.TGX_ERR_COMM else lib().tgx_strerror(rc).decode()
+        raise TgxError(rc, what, text)
+
+    @staticmethod
+    def nccl_version() -> int:
+        v = C.c_int(0)
+        rc = lib().tgx_comm_nccl_version(C.byref(v))
+        if rc:
+            Comm._raise(rc, "tgx_comm_nccl_version")
+        return int(v.value)
+
+    @classmethod
+    def from_torch_distributed(cls, device: int, group=None) -> "Comm":
+        """One process per GPU: rank 0 draws the NCCL unique id, torch.distributed ships it, every rank joins."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        box = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(abi.TGX_COMM_ID_BYTES)
+            rc = lib().tgx_comm_unique_id(buf)
+            if rc:
+                cls._raise(rc, "tgx_comm_unique_id")
+            box[0] = buf.raw
+        dist.broadcast_object_list(box, src=0, group=group)
+        h = C.c_void_p()
+        rc = lib().tgx_comm_init_rank(C.byref(h), world, rank, box[0], device)
+        if rc:
+            cls._raise(rc, "tgx_comm_init_rank")
+        return cls(h, world, rank, device)
+
+    def gather_flags(self, local_flags, n_total: int, out=None):
+        """tgx_gather_flags: this rank's uint8 shard -> the full [n_total] vector on every rank (current stream)."""
+        import torch
+        lo, hi = shard_range(n_total, self.rank, self.world)
+        assert local_flags.dtype == torch.uint8 and local_flags.is_contiguous() and local_flags.numel() == hi - lo
+        if out is None:
+            out = torch.empty(n_total, dtype=torch.uint8, device=local_flags.device)
+        rc = lib().tgx_gather_flags(self._h, local_flags.data_ptr(), n_total, out.data_ptr(),
+                                    int(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            self._raise(rc, "tgx_gather_flags")
+        return out
+
+    def close(self):
+        if self._h:
+            lib().tgx_comm_destroy(self._h)
+            self._h = None
 
 
 class Engine:
@@ -239,6 +317,29 @@ class Engine:
         assert params.dtype == abi.PARAMS_DTYPE
         raw = torch.from_numpy(np.ascontiguousarray(params).view(np.uint8).reshape(len(params), 128))
         return raw.to(self._torch_device(), non_blocking=False)
+
+    def probe_dfma(self, reps: int = 3):
+        """tgx_probe_dfma -> (thread-level DFMA instructions per second, ms per probe launch)."""
+        rate, ms = C.c_double(0.0), C.c_double(0.0)
+        self._check(self._lib.tgx_probe_dfma(self._h, reps, C.byref(rate), C.byref(ms)), "tgx_probe_dfma")
+        return float(rate.value), float(ms.value)
+
+    def probe_d2h(self, pinned: "PinnedArray", nbytes: int, reps: int = 1) -> float:
+        """tgx_probe_d2h: seconds for `reps` plain device->host copies of nbytes into a pinned buffer."""
+        sec = C.c_double(0.0)
+        assert nbytes <= pinned.nbytes
+        self._check(self._lib.tgx_probe_d2h(self._h, pinned.ptr, nbytes, reps, C.byref(sec)), "tgx_probe_d2h")
+        return float(sec.value)
+
+    def fill_montecarlo(self, n: int, seed: int = 1237, first_index: int = 0, out=None):
+        """tgx_fill_montecarlo: records [first_index, first_index + n) of the config-4 distribution drawn on the
+        device (Philox4x32-10; workloads.montecarlo_philox is the bit-identical host version) -> uint8 [n, 128]."""
+        import torch
+        if out is None:
+            out = torch.empty((n, 128), dtype=torch.uint8, device=self._torch_device())
+        self._check(self._lib.tgx_fill_montecarlo(self._h, seed, first_index, n, out.data_ptr(), self._stream()),
+                    "tgx_fill_montecarlo")
+        return out
 
     def count(self, d_params, limits: Optional[abi.Limits] = None):
         """tgx_count on a device-resident parameter tensor -> (counts int32 [n], status int32 [n])."""
@@ -481,6 +582,34 @@ class Engine:
                                                 phases.ctypes.data if phases is not None else None),
                     "tgx_generate_host")
         return out, counts, status, phases
+
+    def generate_host_compact(self, params: np.ndarray, capacity: int, limits: Optional[abi.Limits] = None,
+                              out: Optional[np.ndarray] = None, want_phases: bool = False, want_legs: bool = False):
+        """tgx_generate_host_compact: the 10 varying planes only -> (out [n, 10, capacity] or, plane-major,
+        [10, n, capacity]; counts; status; phases or None; legs or None).  p.z = params['alt'], v.z = a.z = j.z = 0."""
+        params = np.ascontiguousarray(params)
+        n = len(params)
+        nv = abi.TGX_NCHAN_VARYING
+        shape = (nv, n, capacity) if getattr(self, "_host_plane_major", False) else (n, nv, capacity)
+        if out is None:
+            out = np.full(shape, np.nan)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == shape
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.uint32)
+        phases = np.zeros(n, dtype=abi.PHASES_DTYPE) if want_phases else None
+        legs = np.zeros(n, dtype=abi.LEGS_DTYPE) if want_legs else None
+        self._check(self._lib.tgx_generate_host_compact(
+            self._h, params.ctypes.data, n, _limits_ptr(limits), out.ctypes.data, capacity, counts.ctypes.data,
+            status.ctypes.data, phases.ctypes.data if phases is not None else None,
+            legs.ctypes.data if legs is not None else None), "tgx_generate_host_compact")
+        return out, counts, status, phases, legs
+
+    def host_info(self) -> dict:
+        """tgx_host_info: how the host-buffer calls size themselves on this machine."""
+        info = abi.HostInfo()
+        self._check(self._lib.tgx_host_info(self._h, C.byref(info)), "tgx_host_info")
+        return {k: int(getattr(info, k)) for k in ("numa_node", "cpus_allowed", "local_ranks", "filler_threads",
+                                                   "filler_cpus")}
 
     def sample_host(self, params: np.ndarray, v: float, accel: float, s0: float, s1: float = 0.0) -> np.ndarray:
         """tgx_sample_host: one create*Goal evaluation -> the 14 channels."""

@@ -100,6 +100,21 @@ Goal goalFromPlanes(const double* row, int64_t cap, int64_t k) {
     return g;
 }
 
+// The compact wire format (tgx_generate_host_compact): the 10 planes that vary along a trajectory; the z-components
+// are the constants the reference writes literally (p.z = alt_, v.z = a.z = j.z = 0: Circle.cpp:109-121).
+Goal goalFromCompact(const double* row, int64_t cap, int64_t k, double alt) {
+    Goal g;
+    g.header.frame_id = "world";                 // Circle.cpp:106
+    g.p.x = row[0 * cap + k];  g.p.y = row[1 * cap + k];  g.p.z = alt;
+    g.v.x = row[2 * cap + k];  g.v.y = row[3 * cap + k];  g.v.z = 0.0;
+    g.a.x = row[4 * cap + k];  g.a.y = row[5 * cap + k];  g.a.z = 0.0;
+    g.j.x = row[6 * cap + k];  g.j.y = row[7 * cap + k];  g.j.z = 0.0;
+    g.psi = row[8 * cap + k];
+    g.dpsi = row[9 * cap + k];
+    g.power = true;                              // Circle.cpp:127
+    return g;
+}
+
 void goalToArray(const Goal& g, double a[TGX_NCHAN]) {
     a[TGX_PX] = g.p.x; a[TGX_PY] = g.p.y; a[TGX_PZ] = g.p.z;
     a[TGX_VX] = g.v.x; a[TGX_VY] = g.v.y; a[TGX_VZ] = g.v.z;
@@ -190,13 +205,21 @@ void GpuTrajectory::generateTraj(std::vector<Goal>& goals, std::unordered_map<in
     if (!row) die(logger_, "tgx_alloc_host", TGX_ERR_NOMEM);
     tgx_phases phases;
     tgx_polyline_legs legs;
-    rc = tgx_generate_host_legs(e, &params_, 1, nullptr, row, cap, &n, &status, &phases, &legs);
-    if (rc != TGX_OK) die(logger_, "tgx_generate_host_legs", rc);
+    // Bounce moves along z (Bounce.cpp:39-41) and ships all 14 planes; every other class uses the compact format
+    const bool compact = params_.type != TGX_BOUNCE;
+    if (compact)
+        rc = tgx_generate_host_compact(e, &params_, 1, nullptr, row, cap, &n, &status, &phases, &legs);
+    else
+        rc = tgx_generate_host_legs(e, &params_, 1, nullptr, row, cap, &n, &status, &phases, &legs);
+    if (rc != TGX_OK) die(logger_, "tgx_generate_host", rc);
     last_status_ = status;
 
     const size_t base = goals.size();            // generateTraj APPENDS (Circle.cpp:41: push_back, keys size()-1)
     goals.reserve(base + (size_t)n);
-    for (int64_t k = 0; k < n; ++k) goals.push_back(goalFromPlanes(row, cap, k));
+    if (compact)
+        for (int64_t k = 0; k < n; ++k) goals.push_back(goalFromCompact(row, cap, k, params_.alt));
+    else
+        for (int64_t k = 0; k < n; ++k) goals.push_back(goalFromPlanes(row, cap, k));
     if (TGX_IS_POLYLINE(params_.type)) {
         polylineMessages(shape_, params_.type, legs, (int)base, index_msgs);
     } else {

@@ -2,8 +2,9 @@
 
 Trajectories are independent (each is a pure function of its own parameter record, Circle.cpp:30-94), so the batch
 is sharded by index with tgx_shard_range and every rank evaluates its own shard into its own HBM.  The only
-exchange the path has is optional: an all-gather of the 1-byte feasibility flags (BASELINE.json configs[4]), done with
-torch.distributed (NCCL over NVLink on the GPUs; gloo in the CPU tests).
+exchange the path has is optional: an all-gather of the 1-byte feasibility flags (BASELINE.json configs[4]).  On the
+GPUs it is issued by libtgx itself (engine.Comm -> tgx_gather_flags -> ncclAllGather, include/tgx.h); the
+torch.distributed version below carries the same partition rule on any backend and is what the CPU tests run over gloo.
 """
 from __future__ import annotations
 

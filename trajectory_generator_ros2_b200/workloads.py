@@ -140,6 +140,64 @@ def montecarlo_cfg4(n: int, seed: int = 1236, lo: int = 0, hi: int | None = None
     return _draw(seed, lo, hi, _fill_montecarlo_cfg4)
 
 
+# ---- the same distribution from a counter-based generator (device side: csrc/params_gen.cu) -----------------------
+
+def philox4x32_10(counter: np.ndarray, key) -> np.ndarray:
+    """Philox4x32-10 (Salmon et al., SC'11) on an array of counters [m, 4] (uint32) with one key (k0, k1) -> [m, 4]."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [counter[:, i].astype(np.uint64) for i in range(4)]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(M0) * c[0]
+        p1 = np.uint64(M1) * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return np.stack(c, axis=1).astype(np.uint32)
+
+
+def _philox_uniform(x_lo: np.ndarray, x_hi: np.ndarray, a: float, b: float) -> np.ndarray:
+    bits = ((x_hi.astype(np.uint64) << np.uint64(32)) | x_lo.astype(np.uint64)) >> np.uint64(11)
+    u = bits.astype(np.float64) * 2.0 ** -53
+    return a + (b - a) * u
+
+
+def montecarlo_philox(n: int, seed: int = 1237, lo: int = 0, hi: int | None = None) -> np.ndarray:
+    """BASELINE.json configs[4]: the config-4 distribution, trajectory i drawn from Philox4x32-10 with key = seed and
+    counter = (i, draw).  Bit-identical to tgx_fill_montecarlo (csrc/params_gen.cu), which draws a shard on the device
+    so that the 10^8-trajectory sweep needs no host->device parameter copy; this host version serves the checked
+    subsets and the CPU tests."""
+    hi = n if hi is None else hi
+    idx = np.arange(lo, hi, dtype=np.uint64)
+    m = len(idx)
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    ctr = np.zeros((m, 4), dtype=np.uint32)
+    ctr[:, 0] = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ctr[:, 1] = (idx >> np.uint64(32)).astype(np.uint32)
+    draws = []
+    for d in range(3):
+        ctr[:, 2] = d
+        draws.append(philox4x32_10(ctr, key))
+    a, b, c = draws
+    p = np.zeros(m, dtype=abi.PARAMS_DTYPE)
+    p["type"] = abi.TGX_CIRCLE
+    p["n_vgoals"] = 1
+    p["dt"] = DT
+    p["r"] = _philox_uniform(a[:, 0], a[:, 1], 0.2, 5.0)
+    p["cx"] = _philox_uniform(a[:, 2], a[:, 3], -2.0, 2.0)
+    p["cy"] = _philox_uniform(b[:, 0], b[:, 1], -2.0, 2.0)
+    p["alt"] = _philox_uniform(b[:, 2], b[:, 3], 1.0, 2.5)
+    v = _philox_uniform(c[:, 0], c[:, 1], 0.2, 8.0)
+    acc = _philox_uniform(c[:, 2], c[:, 3], 0.7, 2.0)
+    p["accel"] = acc
+    p["v_goals"][:, 0] = v
+    p["t_traj"] = np.maximum(9.98 - (2.0 * v) / acc, 0.5)
+    return p
+
+
 MONTECARLO_LIMITS = dict(box=(-5.0, 5.0, -5.0, 5.0, -5.0, 5.0), v_max=5.0, a_max=6.0)
 
 
