@@ -309,26 +309,33 @@ int tgx_set_max_samples(tgx_engine* e, int64_t max_samples);
  * samples of one trajectory (tile_shift 9 or 10); in the vector-store kernels each thread owns `spt` adjacent samples
  * (2: 128-bit stores, 4: 256-bit stores) and (1 << tile_shift) / spt must be 128 or 256 threads.  The TMA kernels
  * (planes, records) and the reduction-only kernel choose their own CTA width and walk the tile in passes of 256
- * samples; only tile_shift matters to them.  Invalidates the current plan.  Default 10, 4. */
+ * samples; only tile_shift matters to them.  The tuning changes the speed only: the planner cuts a trajectory into
+ * closed-form segments by the replay alone (phase boundaries, at most 2048 steps per segment), never by the tile
+ * size, so every tuning writes the same bytes.  Invalidates the current plan.  Default 10, 4. */
 int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt);
-/* Planning mode.  Sample counts, phase boundaries, status bits and every speed v_k are bit-identical to the
- * reference in both modes.
+/* Planning mode.  Sample counts, phase boundaries (index_msgs keys), status bits and the speed at every segment base
+ * are bit-identical to the reference in both modes; inside a segment v_k = fma(j, a*dt, v_base) is rounded once where
+ * the reference rounds every step (relative difference <= j * 2^-54, observed <= 1e-13).
  *   exact_ramps = 0 (default): ramps are advanced in exact arithmetic-progression jumps of v and the angle / position
  *       state in closed form per jump; the state at segment bases then differs from the reference's running sums by
  *       those sums' own accumulated rounding (<= ~1e-12 rad, ~1e-12 m).  O(#binades) work per trajectory.
  *   exact_ramps = 1: every ramp step is replayed with the reference's operation sequence; the (v, theta | x, y) state
  *       at every segment base, and theta on every hold sample, is bit-identical to the reference.  O(N) work.
- * Braking plans (tgx_plan_stop) always use the exact replay.  Invalidates the current plan. */
+ * Braking plans (tgx_plan_stop) always use the exact replay.  Invalidates the current plan.
+ * Within one mode the samples are a function of the parameters alone: which planning path the engine takes (first
+ * plan, fixed slices, phase records, below) depends on the batches it has seen, the bytes it writes do not. */
 int tgx_set_plan_mode(tgx_engine* e, int exact_ramps);
 /* Single-replay planning (default on): once a plan has measured the largest per-trajectory segment / tile counts of
  * a batch, later plans give every trajectory a fixed slice of the tables and need no counting pass and no scans; a
  * batch that does not fit falls back to the two-replay exact-offset path automatically.  allow = 0 disables it. */
 int tgx_set_slab_planning(tgx_engine* e, int allow);
-/* Phase planning (default on): a batch of Circle / Figure8 trajectories of at most 4096 samples each is planned by a
- * counting replay only (80 bytes per trajectory: where each phase starts) and the evaluation kernel derives its
- * segments from the caller's parameter array in closed form, which removes most table reads from the store-bound
- * kernel.  d_params must then stay valid and unchanged until the last tgx_eval / tgx_feasibility of that plan.
- * Engaged automatically after a plan has seen such a batch; anything else falls back to segment tables. */
+/* Phase planning (default on): a batch of Circle / Figure8 trajectories with at most 2 goal speeds, at most 4096
+ * samples and phases of fewer than 2048 steps each is planned into ONE self-contained 160-byte record per trajectory
+ * (where each phase starts, the replayed angle there, the constants of the parameter record) instead of segment
+ * tables, and the evaluation kernel rebuilds from it exactly the segments the table path would have read — the same
+ * bytes come out, with a tenth of the table traffic in the store-bound kernel.  The plan holds a copy of everything it
+ * needs: d_params may be overwritten or freed as soon as tgx_plan returns, whichever path was taken.
+ * Engaged automatically after a plan has seen such a batch; anything else is planned with segment tables. */
 int tgx_set_phase_planning(tgx_engine* e, int allow);
 int64_t tgx_phase_plan_count(const tgx_engine* e);
 /* Store path of tgx_eval (default tma = 1): when the layout is regular (no per-trajectory offsets, all 14 channels,

@@ -300,11 +300,10 @@ def test_layouts_and_tunings_agree(engine, oracle):
             for plane_major in (False, True):
                 out, c2, s2, _ = gpu_generate(engine, params, want_phases=False, plane_major=plane_major)
                 np.testing.assert_array_equal(c2, counts)
-                # tile size changes where the exactly replayed segment bases sit, so values may differ by the closed
-                # form's drift inside a tile (<= 1024 half-ulps of theta), far below the 1e-9 m parity budget
+                # segments are cut by the replay alone (phases, kRebase steps), never by the tile size: same bytes
                 m = ~np.isnan(base)
                 assert (np.isnan(out) == np.isnan(base)).all()
-                np.testing.assert_allclose(out[m], base[m], rtol=0, atol=1e-10)
+                np.testing.assert_array_equal(out[m], base[m])
     finally:
         engine.set_tuning(10, 4)
     ref, _, _ = oracle.generate(params[-1:])
@@ -713,23 +712,30 @@ def test_slab_planning_matches_exact_offsets_and_falls_back(engine, oracle):
     engine.set_phase_planning(True)
 
 
-def test_phase_planning(engine, oracle):
-    """Batches of short orbits are planned by a counting replay only and evaluated from the parameter records."""
-    engine.set_phase_planning(True)
-    rng = np.random.default_rng(11)
+def _short_orbit_batch(rng):
+    """Circles and Figure8s with one or two goal speeds (repeated / decreasing goals, zero-length holds), one tile each."""
     recs = [workloads.circles_cfg2(3000)]
-    # Figure8s, several goal speeds (K up to 8), repeated / decreasing goals, zero-length holds, two-tile trajectories
     recs.append(workloads.circles_cfg2(500, seed=77))
     recs[-1]["type"] = abi.TGX_FIGURE8
-    for K in (2, 3, 5, 8):
-        for _ in range(6):
+    for K in (1, 2, 2, 2):
+        for _ in range(8):
             v = np.sort(rng.uniform(0.3, 2.5, K))
             if rng.random() < 0.3:
                 v = v[::-1].copy()                       # decreasing: warnings, skipped ramps
+            if rng.random() < 0.2:
+                v[:] = v[0]                              # repeated goal: a ramp with no steps
             kind = abi.TGX_CIRCLE if rng.random() < 0.5 else abi.TGX_FIGURE8
             recs.append(abi.circle_params(1.5, rng.uniform(0.5, 4), 0.3, -0.2, list(v), rng.uniform(0.0, 0.25),
                                           rng.uniform(1.0, 2.0), 0.01, kind=kind))       # N <= 1024: one tile each
-    params = abi.concat(recs)
+    return abi.concat(recs)
+
+
+def test_phase_planning(engine, oracle):
+    """Batches of short orbits are planned into one self-contained record per trajectory; the evaluation kernel rebuilds
+    the table path's segments from it, so the samples are the same BYTES whichever way the batch was planned."""
+    engine.set_phase_planning(True)
+    rng = np.random.default_rng(11)
+    params = _short_orbit_batch(rng)
     p0 = engine.phase_plan_count
     first, c1, st1, _ = gpu_generate(engine, params, want_phases=False)          # learns (segment tables)
     p1 = engine.phase_plan_count
@@ -741,7 +747,7 @@ def test_phase_planning(engine, oracle):
     np.testing.assert_array_equal(status, o_status)
     m = ~np.isnan(first)
     assert (np.isnan(out) == np.isnan(first)).all()
-    np.testing.assert_allclose(out[m], first[m], rtol=0, atol=1e-10)             # same samples as the table path
+    np.testing.assert_array_equal(out[m], first[m])                              # same bytes as the table path
     worst = {}
     for i in list(range(0, 3000, 97)) + list(range(3000, len(params))):
         ref, _, oph = oracle.generate(params[i:i + 1])
@@ -761,22 +767,90 @@ def test_phase_planning(engine, oracle):
     # trajectories of two and three tiles: every tile is its own CTA of the phase plan
     long_ones = abi.concat([abi.circle_params(1.0, rng.uniform(1, 3), 0, 0, [rng.uniform(0.8, 1.5)],
                                               rng.uniform(15.0, 25.0), 0.5, 0.01) for _ in range(40)])
-    gpu_generate(engine, long_ones, want_phases=False)
+    l1, _, _, _ = gpu_generate(engine, long_ones, want_phases=False)
     p3 = engine.phase_plan_count
     out3, c3, st3, _ = gpu_generate(engine, long_ones, want_phases=False)
     assert engine.phase_plan_count - p3 == 1 and c3.min() > 1024 and c3.max() > 2048
+    m3 = ~np.isnan(l1)
+    np.testing.assert_array_equal(out3[m3], l1[m3])
     for i in range(0, 40, 7):
         ref, _, _ = oracle.generate(long_ones[i:i + 1])
         assert_samples_close(out3[i, :, :c3[i]], ref, f"phase long[{i}]")
     p2 = engine.phase_plan_count
-    # a batch with a line, or with a long trajectory, falls back to segment tables on its own
-    mixed = abi.concat([params[:50], workloads.default_line(), workloads.default_circle()])
-    out2, c2, st2, _ = gpu_generate(engine, mixed, want_phases=False)
-    assert engine.phase_plan_count == p2, "a batch with a line and a 25-tile circle must not take the phase path"
-    o_counts, o_status = oracle.count_batch(mixed)
-    np.testing.assert_array_equal(c2, o_counts)
-    ref, _, _ = oracle.generate(mixed[50:51])
-    assert_samples_close(out2[50, :, :685], ref, "line after phase fallback")
+    # a batch with a line, a long trajectory or more than two goal speeds plans with segment tables on its own, every time
+    many = abi.concat([abi.circle_params(1.5, rng.uniform(0.5, 4), 0.3, -0.2, list(np.sort(rng.uniform(0.3, 2.5, K))),
+                                         rng.uniform(0.0, 0.25), rng.uniform(1.0, 2.0), 0.01) for K in (3, 5, 8)])
+    for what, mixed in (("line + 25-tile circle", abi.concat([params[:50], workloads.default_line(),
+                                                              workloads.default_circle()])),
+                        ("K = 3, 5, 8", abi.concat([params[:50], many]))):
+        for _ in range(3):
+            out2, c2, st2, _ = gpu_generate(engine, mixed, want_phases=False)
+        assert engine.phase_plan_count == p2, f"{what}: must not take the phase path"
+        o_counts, o_status = oracle.count_batch(mixed)
+        np.testing.assert_array_equal(c2, o_counts)
+        for i in range(max(0, len(mixed) - 3), len(mixed)):
+            ref, _, _ = oracle.generate(mixed[i:i + 1])
+            assert_samples_close(out2[i, :, :c2[i]], ref, f"{what}[{i}] after phase fallback")
+
+
+def test_results_do_not_depend_on_the_engines_history(engine, oracle):
+    """the same parameters must give the same bytes whatever the engine planned before — first plan
+    (count + scan + fill), fixed slices, phase records, ragged compaction, either tile size, either store path."""
+    rng = np.random.default_rng(5)
+    params = _short_orbit_batch(rng)
+    other = abi.concat([workloads.mixed_cfg3(400), workloads.default_circle()])
+    runs = []
+    engine.set_phase_planning(True)
+    engine.set_slab_planning(True)
+    try:
+        for step in range(4):                                   # exact offsets -> phase plan -> phase plan -> ...
+            runs.append(gpu_generate(engine, params, capacity=1024, want_phases=False)[0])
+        gpu_generate(engine, other, want_phases=False)          # a ragged mixed batch in between
+        gpu_generate(engine, other, want_phases=False)
+        runs.append(gpu_generate(engine, params, capacity=1024, want_phases=False)[0])
+        engine.set_phase_planning(False)
+        for step in range(2):                                   # fixed slices
+            runs.append(gpu_generate(engine, params, capacity=1024, want_phases=False)[0])
+        engine.set_slab_planning(False)
+        runs.append(gpu_generate(engine, params, capacity=1024, want_phases=False)[0])
+        engine.set_slab_planning(True)
+        engine.set_phase_planning(True)
+        engine.set_tuning(9, 4)
+        for step in range(2):
+            runs.append(gpu_generate(engine, params, capacity=1024, want_phases=False)[0])
+        engine.set_tuning(10, 4)
+        engine.set_store_path(False)
+        runs.append(gpu_generate(engine, params, capacity=1024, want_phases=False)[0])
+    finally:
+        engine.set_store_path(True)
+        engine.set_tuning(10, 4)
+        engine.set_phase_planning(True)
+        engine.set_slab_planning(True)
+    m = ~np.isnan(runs[0])
+    for i, r in enumerate(runs[1:]):
+        assert (np.isnan(r) == ~m).all(), f"run {i + 1}: different samples written"
+        np.testing.assert_array_equal(r[m], runs[0][m], err_msg=f"run {i + 1} differs from the first plan's bytes")
+
+
+def test_plan_does_not_reference_caller_parameters(engine, oracle):
+    """A plan is self-contained: overwriting (or freeing) d_params between tgx_plan and tgx_eval changes nothing."""
+    import torch
+    params = workloads.circles_cfg2(4000, seed=3)
+    want, counts, _, _ = gpu_generate(engine, params, capacity=1024, want_phases=False)
+    want2, _, _, _ = gpu_generate(engine, params, capacity=1024, want_phases=False)   # phase plan by now
+    for _ in range(2):
+        d_params = engine.upload_params(params)
+        engine.plan(d_params)
+        d_params.view(torch.uint8).fill_(0xff)               # garbage where the parameters were
+        torch.cuda.synchronize()
+        del d_params
+        out = torch.full((len(params), abi.TGX_NCHAN, 1024), float("nan"), dtype=torch.float64, device="cuda:0")
+        engine.eval(out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        m = ~np.isnan(want)
+        np.testing.assert_array_equal(got[m], want[m])
+        np.testing.assert_array_equal(want2[m], want[m])
 
 
 def test_hold_table_handles_mixed_dt(engine, oracle):

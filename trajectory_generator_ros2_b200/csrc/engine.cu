@@ -214,7 +214,6 @@ struct tgx_engine {
     bool mixed_batch = false;           // the last plan saw more than one replay class: sort the next one by class
     bool plan_packed = false;                    // current plan is a slab plan
     bool plan_phase = false;                     // current plan is a phase plan
-    const tgx_params* plan_params = nullptr;     // phase plans read the caller's parameter array during evaluation
     bool allow_phase = true;
     bool plane_tma = true;              // tgx_eval may send the planes through TMA (tgx_set_store_path)
     bool phase_ready = false;
@@ -256,7 +255,6 @@ tgx::TableView table_view(const tgx_engine* e) {
     tv.segs = e->segs.as<tgx::Seg>();
     tv.tiles = e->plan_dense_tiles ? e->tiles_dense.as<tgx::Tile>() : e->tiles.as<tgx::Tile>();
     if (e->plan_phase) {
-        tv.params = e->plan_params;
         tv.phase = e->phase.as<tgx::PhaseRec>();
         tv.tile_slab = e->tile_slab_plan;
     } else if (e->plan_packed) {
@@ -346,17 +344,16 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         e->ragged_ready = !dense && small && total_tiles > 0;
         e->seg_slab = seg_slab;
         e->tile_slab = tile_slab;
-        e->phase_ready = e->allow_phase && !e->exact_ramps && dense && !h_stats->has_line && h_stats->max_n > 0 &&
-                         h_stats->max_n <= tgx::kPhaseMaxSamples;
+        // phase records: every trajectory of the batch can be written as a PhaseRec (the fill pass checked)
+        e->phase_ready = e->allow_phase && !e->exact_ramps && dense && !h_stats->phase_misfit && h_stats->max_n > 0;
         e->phase_tile_slab = tile_slab;
         e->mixed_batch = (h_stats->kinds & (h_stats->kinds - 1)) != 0;      // more than one replay class
     };
     e->plan_phase = false;
-    e->plan_params = nullptr;
     e->plan_dense_tiles = false;
 
-    // ---- phase mode: batches of short orbits.  One counting replay (no angle state, no tables): the evaluation
-    //      kernel derives its segments from the caller's parameter array, which must stay valid until tgx_eval ----
+    // ---- phase mode: batches of short orbits.  One replay that writes a self-contained 160-byte record per trajectory
+    //      instead of tables; the evaluation kernel rebuilds the table path's segments from it, bit for bit ----
     if (e->allow_phase && e->phase_ready && !e->exact_ramps && !d_stop_from) {
         const int64_t need_tiles = n * (int64_t)e->phase_tile_slab;
         if (need_tiles <= 0x7fffffffLL) {
@@ -376,7 +373,6 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                 done = true;
                 e->plan_phase = true;
                 e->plan_packed = false;
-                e->plan_params = d_params;
                 e->tile_slab_plan = e->phase_tile_slab;
                 e->phase_plans += 1;
             } else {

@@ -108,43 +108,36 @@ __device__ __forceinline__ SegPos seg_pos(const Seg& sg, int k) {
 
 }  // namespace
 
-// Phase plans: build the segment of phase p of an orbit (Circle / Figure8) in closed form from the parameter record
-// and the phase start indices.  Mirrors plan.cu's fast replay: a ramp of n steps adds a*dt per step and clamps on
-// its last step (Circle.cpp:47-54, 75-82); a hold keeps v (:63-71); theta advances by (v/r)*dt per step.
-__device__ void build_phase_segment(const tgx_params& par, const PhaseRec& phr, int p, Seg& sg, int& kend) {
-    const tgx_orbit_params& o = par.u.orbit;
-    const int K = par.n_vgoals;
-    const double adt = __dmul_rn(o.accel, par.dt);          // the rounded product the reference adds every step
-    const double dtr = phr.dtr;
-    double v = 0.0, th = 0.0;
-    for (int q = 0; q <= p; ++q) {
-        const int n = phr.key(q + 1) - phr.key(q);
-        const bool hold = (q & 1) && q < 2 * K;
-        const bool up = !(q & 1) && q < 2 * K;
-        const double target = up ? o.v_goals[q >> 1] : 0.0;
-        const double dv = hold ? 0.0 : (up ? adt : -adt);
-        // state after the phase: n-1 unclamped steps plus the clamped one (ramps), or n equal steps (holds)
-        const double m = hold ? (double)n : (double)(n > 0 ? n - 1 : 0);
-        const double w1 = v * dtr;
-        const double th_m = fma(0.5 * (m * (m + 1.0)), dv * dtr, fma(m, w1, th));
-        const double v_end = (hold || n == 0) ? v : target;
-        const double th_end = (hold || n == 0) ? th_m : fma(target, dtr, th_m);
-        if (q == p) {
-            sg.kb = phr.key(q);
-            sg.n = n;
-            sg.flags = (!hold && n > 0) ? kSegClampLast : 0;
-            sg.pad = 0;
-            sg.vb = v;
-            sg.dv = dv;
-            sg.vclamp = hold ? v : target;
-            sg.s0 = th;
-            sg.s1 = w1;
-            sg.acc = th_end;       // theta of the phase's last sample
-            kend = phr.key(q + 1);
-        }
-        v = v_end;
-        th = th_end;
+// Phase plans: segment q of an orbit (Circle / Figure8) from its self-contained PhaseRec — exactly the Seg record
+// plan.cu's replay writes into the segment table for the same trajectory (ramp(), hold()): the base speed is the level
+// the preceding segments reached, the angle at both ends is the replayed one, and the per-step angle increment is
+// rounded the way the planner rounds it for that kind of segment.  A ramp of n steps adds a*dt per step and clamps on
+// its last step (Circle.cpp:47-54, 75-82); a hold keeps v (:63-71) and is one segment per binade of theta.
+__device__ void build_phase_segment(const PhaseRec& phr, int q, Seg& sg, int& kend) {
+    // speed at the start of segment q
+    double v = 0.0;
+    for (int p = 0; p < q; ++p) {
+        const int kp = (phr.kinds >> (2 * p)) & 3;
+        if (kp < kPhaseKindHold) v = phr.vg[kp];
+        else if (kp == kPhaseKindDown) v = 0.0;
     }
+    const int kind = (phr.kinds >> (2 * q)) & 3;
+    const bool hold = kind == kPhaseKindHold;
+    const bool up = kind < kPhaseKindHold;
+    const double thb = q ? phr.th[q - 1] : 0.0;
+    sg.kb = q ? phr.key[q - 1] : 0;
+    sg.n = phr.key[q] - sg.kb;
+    sg.flags = hold ? 0 : kSegClampLast;
+    sg.pad = 0;
+    sg.vb = v;
+    sg.dv = hold ? 0.0 : (up ? phr.adt : -phr.adt);
+    sg.vclamp = hold ? v : (up ? phr.vg[kind] : 0.0);
+    sg.s0 = thb;
+    // hold: the exact progression step of theta += omega*dt with omega = v/r rounded first (Circle.cpp:65-67; plan.cu:
+    // hold(), d0); ramp: v * (dt/r)  (plan.cu: ramp())
+    sg.s1 = hold ? __dsub_rn(__dadd_rn(thb, __dmul_rn(__ddiv_rn(v, phr.r), phr.dt)), thb) : __dmul_rn(v, phr.dtr);
+    sg.acc = phr.th[q];        // theta of the segment's last sample
+    kend = phr.key[q];
 }
 
 // MODE 0: exact-offset plan, 1: slab plan (fixed per-trajectory slices), 2: phase plan (see TableView).
@@ -168,8 +161,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     constexpr int KS = STAGED ? 32 : 1;           // distance between a thread's samples
     extern __shared__ __align__(16) double2 s_dyn[];
     __shared__ __align__(16) TrajRec s_rec;
-    // a phase plan has at most 2 K + 1 segments per trajectory (K <= TGX_MAX_VGOALS speed goals)
-    constexpr int NSEG = MODE == 2 ? 2 * TGX_MAX_VGOALS + 2 : kMaxSegPerTile;
+    constexpr int NSEG = MODE == 2 ? kPhaseMaxSegs : kMaxSegPerTile;
     __shared__ __align__(16) Seg s_seg[NSEG];
     __shared__ int s_kend[NSEG];                    // last sample of each segment
     __shared__ int4 s_tile;
@@ -178,47 +170,32 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     // ---- stage the tile's constants in shared memory (16-byte chunks, one per thread) -------------------
     int traj, k_lo, nseg;
     if (MODE == 2) {
-        __shared__ __align__(16) tgx_params s_par;
         __shared__ __align__(16) PhaseRec s_phr;
         traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
         k_lo = ((int)blockIdx.x - traj * tv.tile_slab) * TILE;
 #ifdef TGX_EXPERIMENT_SAMEPACKET
-        const int4* ppar = reinterpret_cast<const int4*>(tv.params);      // bandwidth experiment: no DRAM reads
-        const int4* pphr = reinterpret_cast<const int4*>(tv.phase);
+        const int4* pphr = reinterpret_cast<const int4*>(tv.phase);      // bandwidth experiment: no DRAM reads
 #else
-        const int4* ppar = reinterpret_cast<const int4*>(tv.params + traj);
         const int4* pphr = reinterpret_cast<const int4*>(tv.phase + traj);
 #endif
-        // round 1: the first 80 bytes of the parameters (everything up to v_goals[1]) and the first 48 bytes of the
-        // phase record (the phase starts for K <= 2, dt/r, 1/r)
-        {
-            const int c = threadIdx.x;
-            if (c < 5) reinterpret_cast<int4*>(&s_par)[c] = __ldg(ppar + c);
-            else if (c < 8) reinterpret_cast<int4*>(&s_phr)[c - 5] = __ldg(pphr + (c - 5));
-        }
+        // one round of independent loads: the 240-byte record holds everything the tile needs
+        if (threadIdx.x < sizeof(PhaseRec) / 16) reinterpret_cast<int4*>(&s_phr)[threadIdx.x] = __ldg(pphr + threadIdx.x);
         __syncthreads();
-        const int nent = s_phr.n;
-        if (nent <= 0) return;                     // rejected trajectory (whole CTA)
-        if (nent > 6) {                            // K > 2: fetch the rest (CTA-uniform)
-            const int c = threadIdx.x;
-            if (c < 3) reinterpret_cast<int4*>(&s_par)[5 + c] = __ldg(ppar + 5 + c);
-            else if (c < 6) reinterpret_cast<int4*>(&s_phr)[3 + (c - 3)] = __ldg(pphr + 3 + (c - 3));
-            __syncthreads();
-        }
-        const int n_total = s_phr.key(nent - 1) + 1;
+        nseg = s_phr.n;
+        if (nseg <= 0) return;                     // rejected trajectory (whole CTA)
+        const int n_total = s_phr.key[nseg - 1] + 1;
         if (k_lo >= n_total) return;               // slot beyond the trajectory's last tile (whole CTA)
-        nseg = nent - 1;
         if ((int)threadIdx.x < nseg) {
             Seg sg;
             int kend;
-            build_phase_segment(s_par, s_phr, threadIdx.x, sg, kend);
+            build_phase_segment(s_phr, threadIdx.x, sg, kend);
             s_seg[threadIdx.x] = sg;
             s_kend[threadIdx.x] = kend;
         } else if ((int)threadIdx.x == nseg) {
             TrajRec r;
-            r.type = s_par.type & kRecTypeMask;
+            r.type = s_phr.type & kRecTypeMask;
             r.n = n_total;
-            r.f[0] = s_par.u.orbit.r; r.f[1] = s_par.u.orbit.cx; r.f[2] = s_par.u.orbit.cy; r.f[3] = s_par.alt;
+            r.f[0] = s_phr.r; r.f[1] = s_phr.cx; r.f[2] = s_phr.cy; r.f[3] = s_phr.alt;
             r.f[4] = s_phr.dtr; r.f[5] = s_phr.rinv; r.f[6] = 0.0;
             s_rec = r;
         }
@@ -483,18 +460,22 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
             const double r = s_rec.f[0], cx = s_rec.f[1], cy = s_rec.f[2], alt = s_rec.f[3];
             const double dtr = s_rec.f[4], rinv = s_rec.f[5];
             double v[SPT], th[SPT], sn[SPT], cn[SPT], om[SPT];
+            constexpr bool SPLIT = REDUCE && !STORE;      // reduction only (the maxima do not see a speed of 1e-15)
             // theta_b + sum_{m<=j} (v_m / r) * dt  =  theta_b + j*w1 + j(j+1)/2 * (dv*dt/r); a hold (dv = 0) is the
             // reference's exact arithmetic progression; a segment's last sample carries the replayed theta.
             auto speed_and_angle = [&](const Seg& sg, int u) {
                 const SegPos q = seg_pos(sg, k0 + u * KS);
-                v[u] = q.v;
+                // Every sample of a ramp-down except its clamped last one has v > 0 in the reference (`while (v > 0)`,
+                // Circle.cpp:75).  With round parameters the exact value of v one step before the end is 0 and the
+                // reference's is its accumulated rounding (~1e-15); the single rounding of the closed form may land on
+                // the other side of 0 and would turn a Figure8's atan2(vy, vx) yaw (Figure8.cpp:123) by pi.
+                v[u] = (!SPLIT && sg.dv < 0.0 && !q.clamp && !(q.v > 0.0)) ? 1e-300 : q.v;
                 th[u] = q.last ? sg.acc : fma(q.tri, sg.dv * dtr, fma(q.fj, sg.s1, sg.s0));
             };
             // The reduction-only kernel is issue-bound: a thread's samples almost always lie in one segment (si is
             // non-decreasing), so its record is read from shared memory once per thread, and speeds / angles are
             // computed before the trigonometry (5.77 -> 5.12 ms per Mi config-4 circles).  The store kernels are
             // latency-bound and 1.5 % slower that way (16.6 -> 16.85 ms): they keep one loop per sample.
-            constexpr bool SPLIT = REDUCE && !STORE;
             if (SPLIT) {
                 if (si[0] == si[SPT - 1]) {
                     const Seg sg = s_seg[si[0]];

@@ -62,17 +62,24 @@ struct Emitter {
     bool orbit;           // Circle / Figure8: Seg.s1 = theta increment per step, Seg.acc = exact theta of the last sample
     int seg_cap;          // slab mode: capacity of this trajectory's slice (writes beyond it are dropped and the
     int tile_cap;         //            plan is redone with exact offsets); otherwise INT_MAX
-    int32_t* keys = nullptr;   // phase plans: where each phase starts (PhaseRec::key)
+    // phase plans (PhaseRec): where each segment ends, the replayed angle there, and what kind of segment it is
+    int32_t* keys = nullptr;
+    double* states = nullptr;
+    uint32_t kinds = 0;        // 2 bits per segment: kPhaseKind*
+    int goal = 0;              // index of the speed goal the current ramp-up heads for
+    int prev_kind = -1;
+    bool ramp_split = false;   // some ramp was cut into several segments: not expressible as a PhaseRec
 
     int nseg = 0;
     int ntile = 0;
     int nph = 0;
+    int max_tile_segs = 0;     // largest segment list of a tile (the evaluation kernel stages at most kMaxSegPerTile)
+    int max_seg_len = 0;       // longest segment
     int cur_tile = -1;
     int tile_seg_begin = 0;
     Seg cur;              // the open segment, kept in registers until closed
 
     __device__ void phase(int key, int kind, double value, double value2) {
-        if (keys && nph < 19) keys[nph] = key;
         if (ph && nph < TGX_MAX_PHASES) {
             ph->key[nph] = key;
             ph->kind[nph] = kind;
@@ -81,25 +88,36 @@ struct Emitter {
         }
         ++nph;
     }
-    __device__ void flush_tile() {
+    // The tile cur_tile is served by the segments tile_seg_begin .. seg_end - 1.
+    __device__ void flush_tile(int seg_end) {
         if (cur_tile < 0) return;
         if (tiles && ntile < tile_cap) {
             Tile t;
             t.traj = traj;
             t.k_lo = cur_tile << tile_shift;
             t.seg_begin = seg_base + tile_seg_begin;
-            t.nseg = nseg - tile_seg_begin;
+            t.nseg = seg_end - tile_seg_begin;
             tiles[ntile] = t;
         }
+        if (seg_end - tile_seg_begin > max_tile_segs) max_tile_segs = seg_end - tile_seg_begin;
         ++ntile;
     }
-    // Open a segment whose base is sample kb (its first own sample is kb+1).
+    // Open a segment whose base is sample kb (its first own sample is kb+1).  Segments are cut where the REPLAY says
+    // (phase boundaries, every kRebase / kRampChunk steps, exact-progression breaks), never at tile ends: a segment
+    // may span several tiles, and a tile lists every segment that intersects it, so the samples do not depend on the
+    // tile size.
     __device__ void open(int kb, double vb, double dv, double vclamp, double s0, double s1, double acc) {
         const int t = (kb + 1) >> tile_shift;
         if (t != cur_tile) {
-            flush_tile();
+            flush_tile(nseg);
             cur_tile = t;
             tile_seg_begin = nseg;
+        }
+        if (orbit) {
+            const int kind = dv > 0.0 ? (goal & 1) : (dv == 0.0 ? kPhaseKindHold : kPhaseKindDown);
+            if (kind != kPhaseKindHold && kind == prev_kind) ramp_split = true;
+            prev_kind = kind;
+            if (nseg < kPhaseMaxSegs) kinds |= (uint32_t)kind << (2 * nseg);
         }
         cur.kb = kb;
         cur.n = 0;
@@ -120,13 +138,25 @@ struct Emitter {
             if (orbit) cur.acc = last_state;
             segs[nseg] = cur;
         }
+        if (keys && nseg < kPhaseMaxSegs) {
+            keys[nseg] = k_last;
+            states[nseg] = last_state;
+        }
+        if (k_last - cur.kb > max_seg_len) max_seg_len = k_last - cur.kb;
+        // every further tile the segment reaches into starts its list with this segment
+        const int t_last = k_last >> tile_shift;
+        while (cur_tile < t_last) {
+            flush_tile(nseg + 1);
+            ++cur_tile;
+            tile_seg_begin = nseg;
+        }
         ++nseg;
     }
     // Optional breaks (exact-progression breaks inside a hold) are only taken while the tile has room left in the
     // evaluation kernel's shared-memory segment table; mandatory breaks (phases, tiles, ramp chunks) always fit.
     __device__ bool can_break() const { return nseg - tile_seg_begin < kMaxOptionalSegPerTile; }
     __device__ void finish() {
-        flush_tile();
+        flush_tile(nseg);
         cur_tile = -1;
         if (ph) ph->n = nph < TGX_MAX_PHASES ? nph : TGX_MAX_PHASES;
     }
@@ -185,16 +215,15 @@ __device__ __forceinline__ bool ramp(double& v, double target, double adt, doubl
             v = vn;
             step(sgn * v);
             ++k;
-            // k is the last sample of its tile (segments never straddle tiles), or the ramp chunk is full (bounds
-            // the rounding drift of the closed form against the reference's running sums)
-            if (((k + 1) & tmask) == 0 || k - E.cur.kb >= kRampChunk) {
+            // the ramp chunk is full (bounds the rounding drift of the closed form against the reference's running sums)
+            if (k - E.cur.kb >= kRampChunk) {
                 E.close(k, v == clampv, s0);
                 open = false;
             }
         } else {
             const double inc = dsub(vn, v);                      // exact
             long long J = (vn == clampv) ? 0 : regular_run(v, vn, UP ? adt : -adt);
-            J = min(J, (long long)(((k + 1) | tmask) - (k + 1)));  // stay inside the tile of sample k+1
+            J = min(J, (long long)(kRebase - (k + 1 - E.cur.kb)));  // a segment holds at most kRebase steps
             J = min(J, max_samples - 2 - (long long)k);            // the guard fires on the next real step
             if (J > 0) {
                 // none of the jumped steps may reach the clamp: vn + J*inc strictly between 0 and target
@@ -218,7 +247,7 @@ __device__ __forceinline__ bool ramp(double& v, double target, double adt, doubl
             }
             v = fma(fJ, inc, vn);                                // exact
             k += 1 + (int)J;
-            if (((k + 1) & tmask) == 0) {
+            if (k - E.cur.kb >= kRebase) {
                 E.close(k, v == clampv, s0);
                 open = false;
             }
@@ -298,20 +327,20 @@ __device__ __forceinline__ bool hold(double v, double t_hold, double dt, int& k,
         s1 = s1n;
         ++k;
         --rem;
-        if (((k + 1) & tmask) == 0 || (EXACT && d0 != seg_d && E.can_break())) {
+        if (k - E.cur.kb >= kRebase || (EXACT && d0 != seg_d && E.can_break())) {
             E.close(k, false, s0);
             open = false;
             continue;
         }
-        // ---- exact jump over the regular run, inside the tile ------------------------------------------
-        J = min(J, (long long)((k | tmask) - k));
+        // ---- exact jump over the regular run, inside the segment ---------------------------------------
+        J = min(J, (long long)(kRebase - (k - E.cur.kb)));
         if (J > 0) {
             const double fJ = (double)J;
             if (TRACK0) s0 = fma(fJ, d0, s0);                // exact: every partial sum is representable
             if (TRACK1) s1 = fma(fJ, d1, s1);
             k += (int)J;
             rem -= J;
-            if (((k + 1) & tmask) == 0) {
+            if (k - E.cur.kb >= kRebase) {
                 E.close(k, false, s0);
                 open = false;
             }
@@ -372,6 +401,7 @@ __device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E
     for (int g = 0; g < p.n_vgoals; ++g) {                   // :43
         const double vg = o.v_goals[g];
         E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                // :45
+        E.goal = g;
         if (!ramp<true, XR, STATE, false>(v, vg, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, dtr, 0.0,
                                           step)) {                                              // :47-54
             st |= TGX_ST_TOO_LONG;
@@ -380,7 +410,11 @@ __device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E
         if (fabs(dsub(v, vg)) > 0.001) st |= TGX_ST_VGOALS_NOT_INCREASING;                // :57-59
         E.phase(k, TGX_PH_REACHED, vg, o.t_traj);            // :61-62
         const double w = STATE ? dmul(div_inv(v, rdiv), dt) : 0.0;    // omega*dt_, the same on every step (:65-67)
-        if (!hold<STATE, false, STATE && XR>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0, tab)) {   // :63-71
+        // holds are cut at every binade crossing of theta in BOTH planning modes: inside a segment the reference's
+        // running sum is an exact arithmetic progression, so nothing drifts inside a hold however long it is (the hold
+        // samples are the reference's running sum from the hold's first angle: bit for bit with exact ramps, and off by
+        // the preceding ramps' closed-form rounding, ~1e-13 rad, with fast ones)
+        if (!hold<STATE, false, STATE>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0, tab)) {   // :63-71
             st |= TGX_ST_TOO_LONG;
             return -1;
         }
@@ -517,6 +551,12 @@ __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_
         else
             n = replay_orbit<STATE, XR>(p, max_samples, E, r.status, tab);
         E.finish();
+        // the evaluation kernel stages at most kMaxSegPerTile segments per tile: a trajectory that would need more
+        // (dozens of speed goals inside one tile) is rejected rather than evaluated from a truncated list
+        if (n > 0 && E.max_tile_segs > kMaxSegPerTile) {
+            r.status |= TGX_ST_TOO_LONG;
+            n = -1;
+        }
         if (lim && lim->check_box && !inside_bounds(p, lim->box)) {
             r.status |= TGX_ST_OUTSIDE_BOUNDS;
             // Line::trajectoryInsideBounds reports "not feasible" when d2 < 0 (Line.cpp:165-168)
@@ -577,14 +617,14 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
             E.phase(0, TGX_PH_PRESSED_END, 0.0, 0.0);                 // Square.cpp:123, Bounce.cpp:86
             if (p.type == TGX_BOUNCE) {
                 // Bounce::generateStopTraj, Bounce.cpp:74-103: vz *= 0.8 until |vz| <= 0.01 (then exactly 0); one
-                // one-sample segment per step, all inside the first tile
+                // one-sample segment per step, all inside the first tile (at most kMaxSegPerTile - 1 of them)
                 double vz = from[TGX_VZ];
                 t.f[0] = p.u.poly.g[0]; t.f[1] = p.u.poly.g[1]; t.f[2] = from[TGX_PZ];   // :82, :94
                 t.f[3] = from[TGX_PSI];                                                   // :83
                 t.f[4] = 0.0; t.f[5] = 0.0; t.f[6] = 1.0;
                 if (!isfinite(vz)) ok = false;
                 while (ok && fabs(vz) > 0.01) {                       // :91
-                    if (k + 1 >= kMaxOptionalSegPerTile) { ok = false; break; }
+                    if (k + 2 >= kMaxSegPerTile) { ok = false; break; }        // |vz| beyond ~1e4 m/s
                     vz = dmul(vz, 0.8);                               // :92
                     if (fabs(vz) < 0.01) vz = 0.0;                    // :93
                     E.open(k, vz, 0.0, vz, 0.0, 0.0, 0.0);
@@ -615,6 +655,10 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
                 r.n = k + 1;
             }
             E.finish();
+            if (r.n > 0 && E.max_tile_segs > kMaxSegPerTile) {
+                r.status |= TGX_ST_TOO_LONG;
+                r.n = 0;
+            }
             if (r.n > 0) {
                 r.nseg = E.nseg;
                 r.ntile = E.ntile;
@@ -651,7 +695,6 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
             step(v);
             ++k;
             bool open = true;
-            if (((k + 1) & tmask) == 0) { E.close(k, v == 0.0, 0.0); open = false; }
             while (v > 0.0) {
                 const double vn = std_max(dsub(v, adt), 0.0);
                 if (vn == v || (int64_t)k + 1 >= max_samples) { ok = false; break; }
@@ -659,7 +702,7 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
                 v = vn;
                 step(v);
                 ++k;
-                if (((k + 1) & tmask) == 0 || k - E.cur.kb >= kRampChunk) { E.close(k, v == 0.0, 0.0); open = false; }
+                if (k - E.cur.kb >= kRampChunk) { E.close(k, v == 0.0, 0.0); open = false; }
             }
             if (ok && open) E.close(k, v == 0.0, 0.0);
             t.type = TGX_LINE;
@@ -686,6 +729,10 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
             r.n = k + 1;
         }
         E.finish();
+        if (r.n > 0 && E.max_tile_segs > kMaxSegPerTile) {
+            r.status |= TGX_ST_TOO_LONG;
+            r.n = 0;
+        }
         if (r.n > 0) {
             r.nseg = E.nseg;
             r.ntile = E.ntile;
@@ -706,15 +753,26 @@ __device__ __forceinline__ tgx_params load_params(const tgx_params* params, int6
     return p;
 }
 
+// Can this trajectory's plan be written as a PhaseRec?  (A rejected one can: n = 0.)
+__device__ __forceinline__ bool phase_fits(const tgx_params& p, int n, const Emitter& E, int max_n) {
+    if (!is_orbit(p.type)) return false;
+    if (n <= 0) return true;
+    return p.n_vgoals <= kPhaseMaxGoals && E.nseg <= kPhaseMaxSegs && !E.ramp_split && n <= max_n;
+}
+
 }  // namespace
 
 // ---- kernels ------------------------------------------------------------------------------------------
 
 // Per-plan statistics the fill pass accumulates (one atomic per warp).
 __device__ __forceinline__ void accumulate_stats(PlanStats* stats, int n, int nseg, int ntile, bool overflow,
-                                                 bool line_like, int kind) {
+                                                 bool line_like, int kind, int seg_len = 0, int tile_segs = 0,
+                                                 bool phase_misfit = true) {
     if (!stats) return;
     const unsigned mask = __activemask();
+    const unsigned misfit = __reduce_or_sync(mask, phase_misfit ? 1u : 0u);
+    const int mlen = __reduce_max_sync(mask, seg_len);
+    const int mts = __reduce_max_sync(mask, tile_segs);
     const unsigned kinds = __reduce_or_sync(mask, 1u << kind);
     const unsigned tot = __reduce_add_sync(mask, (unsigned)n);
     const int mseg = __reduce_max_sync(mask, nseg);
@@ -729,7 +787,10 @@ __device__ __forceinline__ void accumulate_stats(PlanStats* stats, int n, int ns
         atomicMax(&stats->max_nseg, mseg);
         atomicMax(&stats->max_ntile, mtile);
         atomicMax(&stats->max_n, mn);
+        atomicMax(&stats->max_seg_len, mlen);
+        atomicMax(&stats->max_tile_segs, mts);
         if (ovf) atomicOr(&stats->overflow, 1);
+        if (misfit && !*reinterpret_cast<volatile int*>(&stats->phase_misfit)) atomicOr(&stats->phase_misfit, 1);
         if (lin) atomicOr(&stats->has_line, 1);
         if ((*reinterpret_cast<volatile int*>(&stats->kinds) & (int)kinds) != (int)kinds) atomicOr(&stats->kinds, (int)kinds);
     }
@@ -833,13 +894,18 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
     if (status) status[i] = r.status;
     if (counts2) counts2[i] = r.n;
     if (status2) status2[i] = r.status;
-    accumulate_stats(stats, r.n, r.nseg, r.ntile, overflow, is_line_like(p.type), replay_class(p.type, p.n_vgoals));
+    accumulate_stats(stats, r.n, r.nseg, r.ntile, overflow, is_line_like(p.type), replay_class(p.type, p.n_vgoals),
+                     r.n > 0 ? E.max_seg_len : 0, r.n > 0 ? E.max_tile_segs : 0,
+                     stop_from || !phase_fits(p, r.n, E, kPhaseMaxSamples));
 }
 
-// Phase plan: counts only.  Replays the speed ramps and hold counters (no angle state: none is stored) and records
-// where each phase starts; the evaluation kernel derives everything else from the parameter record.  Only orbits
-// of at most max_n samples qualify; anything else sets stats->overflow and the host plans with segment tables.
-// (12 CTAs of 128 threads per SM: the replay is latency-bound, more resident warps beat fewer spills: 0.90 -> 0.68 ms per Mi)
+// Phase plan: batches of short orbits (Circle / Figure8 with at most kPhaseMaxGoals speed goals, at most kPhaseMaxSegs
+// segments, at most max_n samples).  The same replay as plan_fill_kernel, but instead of TrajRec + Seg + Tile records it
+// writes ONE self-contained PhaseRec per trajectory: where each segment ends, the replayed angle there, the segment
+// kinds and the constants of the parameter record.  The evaluation CTA rebuilds the table path's Seg records from it
+// (build_phase_segment, eval.cu) — the samples are the same bits whichever way the batch was planned.  A trajectory
+// that does not qualify sets stats->overflow and the host plans the batch with segment tables.
+// (12 CTAs of 128 threads per SM: the replay is latency-bound, more resident warps beat fewer spills)
 __global__ void __launch_bounds__(128, 12)
 plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits lim, int has_lim,
                   int64_t max_samples, int tile_shift, int max_n, const CurTable* __restrict__ tab,
@@ -850,39 +916,46 @@ plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits l
     if (i >= n) return;
     const tgx_params p = load_params(params, i);
     PhaseRec rec;
-    int32_t keys[19];
     rec.n = 0;
+    rec.pad = 0;
 #pragma unroll
-    for (int q = 0; q < 19; ++q) keys[q] = 0;
+    for (int q = 0; q < kPhaseMaxSegs; ++q) {
+        rec.key[q] = 0;
+        rec.th[q] = 0.0;
+    }
     Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, phases ? phases + i : nullptr, true, 0x7fffffff,
-              0x7fffffff, keys};
-    const bool line_like = is_line_like(p.type);
+              0x7fffffff, rec.key, rec.th};
+    const bool orbit = is_orbit(p.type);
     PlanOut r{0, 0u, 0, 0};
-    bool overflow = line_like;
-    if (!line_like) {
-        r = plan_one<false, false, false>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
-        if (r.n > max_n) overflow = true;
-        if (r.n > 0) rec.n = E.nph < 19 ? E.nph : 19;
+    bool overflow = !orbit;
+    if (orbit) {
+        r = plan_one<false, true, false>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
+        overflow = !phase_fits(p, r.n, E, max_n);
+        if (r.n > 0 && !overflow) rec.n = E.nseg;
     }
     if (phases && r.n == 0) phases[i].n = 0;
+    const tgx_orbit_params& o = p.u.orbit;
+    rec.type = p.type;
+    rec.kinds = E.kinds;
+    rec.dtr = orbit ? ddiv(p.dt, o.r) : 0.0;
+    rec.rinv = orbit ? ddiv(1.0, o.r) : 0.0;
+    rec.r = o.r; rec.cx = o.cx; rec.cy = o.cy; rec.alt = p.alt;
+    rec.adt = dmul(o.accel, p.dt);
+    rec.dt = p.dt;
 #pragma unroll
-    for (int q = 0; q < 7; ++q) rec.key_lo[q] = keys[q];
-#pragma unroll
-    for (int q = 0; q < 12; ++q) rec.key_hi[q] = keys[7 + q];
-    rec.dtr = line_like ? 0.0 : ddiv(p.dt, p.u.orbit.r);
-    rec.rinv = line_like ? 0.0 : ddiv(1.0, p.u.orbit.r);
-    // 96-byte record: six 16-byte stores
+    for (int q = 0; q < kPhaseMaxGoals; ++q) rec.vg[q] = o.v_goals[q];
+    // 240-byte record: fifteen 16-byte stores
     {
         const int4* src = reinterpret_cast<const int4*>(&rec);
         int4* dst = reinterpret_cast<int4*>(phase + i);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) dst[q] = src[q];
+        for (int q = 0; q < (int)(sizeof(PhaseRec) / 16); ++q) dst[q] = src[q];
     }
     if (counts) counts[i] = r.n;
     if (status) status[i] = r.status;
     if (counts2) counts2[i] = r.n;
     if (status2) status2[i] = r.status;
-    accumulate_stats(stats, r.n, 0, 0, overflow, line_like, replay_class(p.type, p.n_vgoals));
+    accumulate_stats(stats, r.n, 0, 0, overflow, !orbit, replay_class(p.type, p.n_vgoals), 0, 0, overflow);
 }
 
 // "Per-time evaluation": a one-sample plan per trajectory from an explicit state, i.e. the public helpers

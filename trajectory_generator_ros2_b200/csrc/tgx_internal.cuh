@@ -69,11 +69,18 @@ static_assert(sizeof(Tile) == 16, "Tile must be 16 bytes");
 // A ramp is cut into chunks of at most kRampChunk steps, each starting from the exactly replayed state, which
 // bounds the closed form's rounding drift against the reference's running sums to kRampChunk half-ulps.
 constexpr int kRampChunk = 256;
+// Fast planning mode: a segment holds at most kRebase steps of one phase — the closed form inside a segment starts from
+// the replayed state at its base, so its drift against the reference's running sums is bounded by kRebase half-ulps
+// of the state (2048 x 1.1e-16 x |theta|: 2e-11 rad at theta = 100).  Segments are cut by this rule and by the phases
+// alone, never by the evaluation kernel's tile size: the samples do not depend on the tuning.
+constexpr int kRebase = 2048;
 
 // Shared-memory segment table of the evaluation kernel.  Mandatory segments in one tile: every phase of a
-// trajectory (2*K ramps/holds + ramp-down = 17) could start inside the same tile, plus ramp chunks (tile/256 <= 8).
-// Optional segments (exact-progression breaks inside holds, plan.cu) are only emitted while the tile holds fewer than
-// kMaxOptionalSegPerTile segments, so the total never exceeds kMaxSegPerTile.
+// trajectory (2*K ramps/holds + ramp-down = 17 for K = 8) could start inside the same tile, plus ramp chunks
+// (tile/256 <= 8).  Optional segments (exact-progression breaks inside holds, plan.cu) are only emitted while the tile
+// holds fewer than kMaxOptionalSegPerTile segments.  The planner ENFORCES the bound: a trajectory one of whose tiles
+// would need more than kMaxSegPerTile segments (dozens of speed goals inside 1024 samples) is rejected with
+// TGX_ST_TOO_LONG instead of being evaluated from a truncated list.
 constexpr int kMaxSegPerTile = 64;
 constexpr int kMaxOptionalSegPerTile = 36;
 
@@ -86,18 +93,29 @@ constexpr int kMaxOptionalSegPerTile = 36;
 // Keeping these reads few and dense matters more than their size suggests: every DRAM read that lands in the middle
 // of the kernel's write stream costs a write->read->write bus turnaround (tools/wbw: 1 % of read traffic costs 8 %
 // of the write bandwidth; with cache-resident tables the same kernel writes 7.27 TB/s instead of 6.5 TB/s).
-//   phase plans (phase != nullptr): batches of short orbits.  The planner writes only the sample index at which each
-//       phase starts (PhaseRec, 96 B, dense) and the CTA derives its segments from the caller's 128-byte parameter
-//       record in closed form; tile t of trajectory i is CTA i*tile_slab + t.  Reads per tile: 80 + 48 bytes.
+//   phase plans (phase != nullptr): batches of short orbits with at most kPhaseMaxGoals speed goals whose replay emits
+//       at most kPhaseMaxSegs segments (one per ramp, one per binade of theta a hold passes through).  The planner then
+//       writes one self-contained 240-byte PhaseRec per trajectory — where each segment ends, the replayed angle
+//       there, what kind of segment it is, and the constants of the parameter record — instead of TrajRec + Seg + Tile
+//       records, and the CTA rebuilds exactly the Seg records the table path would have read (build_phase_segment,
+//       eval.cu): same bits, one round of 15 independent 16-byte loads.  Tile t of trajectory i is CTA i*tile_slab + t.
+constexpr int kPhaseMaxGoals = 2;
+constexpr int kPhaseMaxSegs = 12;
+constexpr int kPhaseKindHold = 2;      // 0, 1: ramp up to speed goal 0 / 1
+constexpr int kPhaseKindDown = 3;
 struct __align__(16) PhaseRec {
-    int32_t n;            // number of phase starts = 2*K + 2 (0: rejected trajectory)
-    int32_t key_lo[7];    // key(p) = sample index at which phase p starts, key(n-1) = N - 1 (the index_msgs keys), p < 7
-    double dtr;           // dt / r and 1 / r, divided once here instead of once per CTA
-    double rinv;
-    int32_t key_hi[12];   // key(p) for p = 7 .. 18 (only read when K > 2)
-    __host__ __device__ int key(int p) const { return p < 7 ? key_lo[p] : key_hi[p - 7]; }
+    int32_t n;            // number of segments (0: rejected trajectory)
+    int32_t type;         // TGX_CIRCLE / TGX_FIGURE8
+    uint32_t kinds;       // 2 bits per segment
+    int32_t pad;
+    int32_t key[kPhaseMaxSegs];      // key[q] = last sample of segment q (segment q starts after key[q-1], or at sample 0)
+    double th[kPhaseMaxSegs];        // the replayed angle at sample key[q]
+    double r, cx, cy, alt;
+    double dtr, rinv;     // dt / r and 1 / r, divided once here instead of once per CTA
+    double adt, dt;       // the rounded product accel*dt the reference adds every step; dt
+    double vg[kPhaseMaxGoals];
 };
-static_assert(sizeof(PhaseRec) == 96, "PhaseRec must be 96 bytes");
+static_assert(sizeof(PhaseRec) == 240, "PhaseRec must be 240 bytes");
 
 struct TableView {
     const TrajRec* recs;
@@ -105,12 +123,10 @@ struct TableView {
     const Tile* tiles;
     int seg_slab;
     int tile_slab;                  // > 0: slab or phase plan
-    const tgx_params* params;       // phase plan
     const PhaseRec* phase;          // phase plan
 };
 
-// Longest trajectory a phase plan accepts: its closed forms run from the phase start, so the rounding drift against
-// the reference's running sums grows with the phase length; 4096 steps keep it below ~1e-11 rad.
+// Longest trajectory a phase plan accepts (sizes the tile slots of such a plan).
 constexpr int kPhaseMaxSamples = 4096;
 
 constexpr int kSlabSpecSegs = 4;   // segments fetched speculatively with the record in a slab plan
@@ -122,9 +138,12 @@ struct PlanStats {
     int max_nseg;                       // largest segment count of a trajectory
     int max_ntile;                      // largest tile count of a trajectory
     int overflow;                       // slab / phase mode: some trajectory did not fit
+    int phase_misfit;                   // some trajectory cannot be written as a PhaseRec (see plan_fill_kernel)
     int max_n;                          // largest sample count of a trajectory
     int has_line;                       // some trajectory is a Line / Boomerang
     int kinds;                          // bit mask of the replay classes seen (replay_class(): orbit x K, line, boomerang)
+    int max_seg_len;                    // longest segment of the plan
+    int max_tile_segs;                  // longest segment list of a tile
 };
 
 // ---- constant-speed polyline family (Square / Rectangle / Reciprocating / Bounce / M / I / T) -------------------
