@@ -258,37 +258,78 @@ def leg_cfg3(ctx, steps=5, warmup=2):
         stop_cap = max(stop_cap, (int(sp.counts.max().item()) + 3) // 4 * 4)
         stop_total += sp.total_samples
     stop_out = torch.empty((int(stop_idx[0].shape[0]), abi.TGX_NCHAN, stop_cap), dtype=torch.float64, device=dev)
+    # Braking runs on a second engine and a side stream: the setpoints are gathered on the main stream right after the
+    # chunk's samples exist (before the next chunk overwrites the buffer), and tgx_plan_stop + tgx_eval of chunk c are
+    # issued after tgx_generate of chunk c+1, so they run under its evaluation kernels.
+    eng2 = ctx.eng2
+    side = torch.cuda.Stream(device=dev)
+    pending = []
     ev = {"eval": [], "stop": []}
 
+    def brake(record):
+        while pending:
+            c, d_from, ready = pending.pop(0)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                eng2.plan_stop(stop_params[c], d_from)
+                eng2.eval(stop_out[: stop_idx[c].shape[0]])
+                b1.record()
+                d_from.record_stream(side)
+                if record:
+                    ev["stop"].append((b0, b1))
+
     def step(record):
+        main = torch.cuda.current_stream()
         for c in range(chunks):
             dp = chunk_params[c]
-            eng.plan(dp, want_outputs=False)
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-            eng.eval(out[: dp.shape[0]])
-            e1.record()
+            if pipelined:
+                eng.generate(dp, out[: dp.shape[0]])
+            else:
+                eng.plan(dp, want_outputs=False)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                eng.eval(out[: dp.shape[0]])
+                e1.record()
+                if record:
+                    ev["eval"].append((e0, e1))
+            brake(record)                     # the previous chunk's braking, under this chunk's evaluation
             # END pressed at k = N_i / 2: brake from that setpoint (the caller's gather of goals[pub_index] is plumbing)
             d_from = out[stop_idx[c], :, stop_k[c]].contiguous()
-            eng.plan_stop(stop_params[c], d_from)
-            eng.eval(stop_out[: stop_idx[c].shape[0]])
-            e2.record()
-            if record:
-                ev["eval"].append((e0, e1))
-                ev["stop"].append((e1, e2))
+            ready = torch.cuda.Event()
+            ready.record()
+            pending.append((c, d_from, ready))
+            if not pipelined:
+                brake(record)
 
+    def drain():
+        brake(True)
+        done = torch.cuda.Event()
+        done.record(side)
+        torch.cuda.current_stream().wait_event(done)
+
+    pipelined = not ctx.args.no_pipeline
     for _ in range(warmup):
         step(False)
+    drain()
     ctx.barrier()
+    eng.set_generate_profiling(pipelined)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(steps):
         step(True)
+    drain()
     t1.record()
     ctx.barrier()
     ms = ctx.allmax(t0.elapsed_time(t1) / steps)
-    eval_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev["eval"]])) * chunks)
-    stop_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev["stop"]])) * chunks)
+    if pipelined:
+        prof_ms, prof_n = eng.generate_profile()
+        eng.set_generate_profiling(False)
+        eval_ms = ctx.allmax(prof_ms / steps)
+    else:
+        eval_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev["eval"]])) * chunks)
+    stop_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev["stop"]])) * chunks) if ev["stop"] else 0.0
     job = ctx.allsum(total + stop_total)
     peak, _ = measured_peak()
     achieved = BYTES_PER_SAMPLE * total / (eval_ms * 1e-3) / 1e9
@@ -299,7 +340,13 @@ def leg_cfg3(ctx, steps=5, warmup=2):
             "value": job / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
             "samples_per_gpu": total, "braking_trajectories_per_gpu": int(sum(int(i.shape[0]) for i in stop_idx)),
             "braking_samples_per_gpu": stop_total, "chunks": chunks, "row_stride": row,
-            "eval_ms_per_step": eval_ms, "braking_ms_per_step": stop_ms, "plan_ms_per_step": ms - eval_ms - stop_ms,
+            "eval_ms_per_step": eval_ms, "braking_ms_per_step": stop_ms,
+            "not_hidden_ms_per_step": ms - eval_ms,
+            "step": ("per chunk tgx_generate (planning pipelined under the evaluation on two internal streams); braking "
+                     "(tgx_plan_stop + tgx_eval on a second engine and stream) issued after the next chunk's "
+                     "tgx_generate so that it runs under its evaluation kernels; braking_ms is its own stream time, "
+                     "not_hidden_ms what the step takes beyond the generateTraj evaluation kernels") if pipelined else
+                    "per chunk tgx_plan + tgx_eval, then tgx_plan_stop + tgx_eval, all on one stream",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "kernel": "tgx::eval_kernel (generateTraj samples only)"}}
 
@@ -321,8 +368,13 @@ def leg_cfg4(ctx, steps=3, warmup=2):
     ev = []
     total = 0
 
+    pipelined = not ctx.args.no_pipeline
+
     def step(record):
         nonlocal total
+        if pipelined:
+            total = eng.generate_feasibility(d_params, lim, flags=flags, max_v=mv, max_a=ma, status=st)[4]
+            return
         total = eng.plan(d_params, limits=lim, want_outputs=False).total_samples
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -334,6 +386,7 @@ def leg_cfg4(ctx, steps=3, warmup=2):
     for _ in range(warmup):
         step(False)
     ctx.barrier()
+    eng.set_generate_profiling(pipelined)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(steps):
@@ -341,13 +394,19 @@ def leg_cfg4(ctx, steps=3, warmup=2):
     t1.record()
     ctx.barrier()
     ms = ctx.allmax(t0.elapsed_time(t1) / steps)
-    eval_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev])))
+    if pipelined:
+        prof_ms, _ = eng.generate_profile()
+        eng.set_generate_profiling(False)
+        eval_ms = ctx.allmax(prof_ms / steps)
+    else:
+        eval_ms = ctx.allmax(float(np.mean([a.elapsed_time(b) for a, b in ev])))
     job = ctx.allsum(total)
     res = {"workload": WORKLOAD_DESC["montecarlo_cfg4"].format(n=n), "value": job / (ms * 1e-3), "unit": UNIT,
            "ms_per_step": ms, "steps": steps, "warmup": warmup, "samples_per_gpu": total,
-           "eval_ms_per_step": eval_ms, "plan_ms_per_step": ms - eval_ms,
+           "eval_ms_per_step": eval_ms, "not_hidden_ms_per_step": ms - eval_ms,
            "feasible_fraction": float(flags.float().mean()),
-           "step": "tgx_plan + tgx_feasibility, parameters resident in HBM",
+           "step": ("tgx_generate_feasibility (1 Mi-trajectory chunks, planning pipelined under the reduction kernel on "
+                    "two internal streams)" if pipelined else "tgx_plan + tgx_feasibility") + ", parameters resident in HBM",
            "roofline": fp64_roofline(ctx, total, eval_ms)}
     del d_params, flags, mv, ma, st
     torch.cuda.empty_cache()
@@ -374,7 +433,8 @@ def leg_cfg5(ctx, steps=2, warmup=1):
     b.record()
     torch.cuda.synchronize()
     fill_ms = ctx.allmax(a.elapsed_time(b))
-    chunk = 1 << 24                                   # trajectories per plan: bounds the plan tables
+    pipelined = not ctx.args.no_pipeline
+    chunk = m if pipelined else 1 << 24               # trajectories per call (tgx_generate_feasibility chunks by itself)
     flags = torch.empty(m, dtype=torch.uint8, device=dev)
     full = torch.empty(n_total, dtype=torch.uint8, device=dev)
     mv = torch.empty(min(m, chunk), dtype=torch.float64, device=dev)
@@ -389,6 +449,10 @@ def leg_cfg5(ctx, steps=2, warmup=1):
         total = 0
         for s in range(0, m, chunk):
             k = min(chunk, m - s)
+            if pipelined:
+                total += eng.generate_feasibility(d_params[s:s + k], lim, flags=flags[s:s + k], max_v=mv[:k],
+                                                  max_a=ma[:k], status=st[:k])[4]
+                continue
             total += eng.plan(d_params[s:s + k], limits=lim, want_outputs=False).total_samples
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -409,6 +473,7 @@ def leg_cfg5(ctx, steps=2, warmup=1):
     for _ in range(warmup):
         step(False)
     ctx.barrier()
+    eng.set_generate_profiling(pipelined)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(steps):
@@ -417,7 +482,12 @@ def leg_cfg5(ctx, steps=2, warmup=1):
     ctx.barrier()
     ms = ctx.allmax(t0.elapsed_time(t1) / steps)
     nchunks = (m + chunk - 1) // chunk
-    eval_ms = ctx.allmax(float(np.mean([x.elapsed_time(y) for x, y in ev_eval])) * nchunks)
+    if pipelined:
+        prof_ms, _ = eng.generate_profile()
+        eng.set_generate_profiling(False)
+        eval_ms = ctx.allmax(prof_ms / steps)
+    else:
+        eval_ms = ctx.allmax(float(np.mean([x.elapsed_time(y) for x, y in ev_eval])) * nchunks)
     gather_ms = ctx.allmax(float(np.mean([x.elapsed_time(y) for x, y in ev_gather])))
     job = ctx.allsum(total)
     ok = bool(torch.equal(full[lo:hi], flags))
@@ -430,13 +500,16 @@ def leg_cfg5(ctx, steps=2, warmup=1):
                        f"seed 1237), feasibility only",
            "value": job / (ms * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_step": ms, "steps": steps,
            "warmup": warmup, "trajectories": n_total, "trajectories_per_gpu": m, "samples": job,
-           "eval_ms_per_step": eval_ms, "plan_ms_per_step": ms - eval_ms - gather_ms,
+           "eval_ms_per_step": eval_ms, "not_hidden_ms_per_step": ms - eval_ms - gather_ms,
            "flags_allgather_ms": gather_ms, "device_fill_ms": fill_ms,
            "gather": ("tgx_gather_flags -> ncclAllGather of %d B per rank over NCCL %d, on the evaluation stream, "
                       "inside the timed step" % (m, Comm.nccl_version())) if comm is not None else
                      "one shard: device-to-device copy",
            "gathered_equals_local_shard": ok, "gathered_identical_on_all_ranks": bool(same),
-           "feasible": feasible, "step": "per 2^24-trajectory chunk tgx_plan + tgx_feasibility, then the flag all-gather"}
+           "feasible": feasible,
+           "step": ("tgx_generate_feasibility over the shard (1 Mi-trajectory chunks, planning pipelined under the "
+                    "reduction kernel)" if pipelined else "per 2^24-trajectory chunk tgx_plan + tgx_feasibility")
+                   + ", then the flag all-gather"}
     if comm is not None:
         comm.close()
     del d_params, flags, full, mv, ma, st
@@ -578,9 +651,17 @@ def run_ours(args):
 
     ev_pairs = []
 
+    pipelined = not args.no_pipeline and not poly and not args.records and not args.plane_major
+
     def step(record: bool):
         for c in range(chunks):
             dp = chunk_params[c]
+            if pipelined:
+                if feas_only:
+                    eng.generate_feasibility(dp, lim, flags=flags[c], max_v=mv[c], max_a=ma[c], status=st[c])
+                else:
+                    eng.generate(dp, out[: dp.shape[0]], chunk=args.gen_chunk)
+                continue
             if poly:
                 eng.plan_polyline(dp, want_outputs=False)
             else:
@@ -647,6 +728,7 @@ def run_ours(args):
     if sampler:
         sampler.mark_start()
     launches0 = eng.launch_count
+    eng.set_generate_profiling(pipelined)
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for _ in range(args.steps):
@@ -658,7 +740,15 @@ def run_ours(args):
     elapsed_ms = t_start.elapsed_time(t_stop)
     launches = eng.launch_count - launches0
     clocks = sampler.stop() if sampler else None
-    eval_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs])) * chunks   # per step
+    eval_launches = chunks
+    if pipelined:
+        # the library brackets every evaluation launch with an event pair on the stream it is launched on
+        prof_ms, prof_n = eng.generate_profile()
+        eng.set_generate_profiling(False)
+        eval_ms = prof_ms / args.steps
+        eval_launches = prof_n // args.steps
+    else:
+        eval_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs])) * chunks   # per step
     if world > 1:
         t = torch.tensor([elapsed_ms, eval_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -792,8 +882,10 @@ def run_ours(args):
             pass
         del d_params, chunk_params
         torch.cuda.empty_cache()
-        extra = run_extras(Ctx(eng=eng, dev=dev, n=n, rank=rank, world=world, local_rank=local_rank, args=args,
-                               barrier=barrier, allmax=allmax, allsum=allsum))
+        eng2 = Engine(local_rank)
+        extra = run_extras(Ctx(eng=eng, eng2=eng2, dev=dev, n=n, rank=rank, world=world, local_rank=local_rank,
+                               args=args, barrier=barrier, allmax=allmax, allsum=allsum))
+        eng2.close()
     feas_roof = fp64_roofline(Ctx(eng=eng), total_samples, eval_ms) if (feas_only and rank == 0) else None
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -837,10 +929,15 @@ def run_ours(args):
                 "chunks": chunks,
                 "step": ("tgx_plan_polyline (hold-length table + waypoints / per-leg step counts in strict IEEE "
                          "arithmetic, one thread per trajectory) + tgx_eval, parameters resident in HBM") if poly else
+                        (("tgx_generate_feasibility" if feas_only else "tgx_generate") + ": the batch in %d chunks, each "
+                         "planned (hold-length table + one strict-IEEE replay per trajectory) on one of two internal "
+                         "streams while the previous chunk's evaluation kernel runs on the other; parameters resident "
+                         "in HBM" % eval_launches) if pipelined else
                         "tgx_plan (hold-length table + one strict-IEEE replay per trajectory into fixed slices; the "
                         "first plan of an engine measures the slice sizes with a count + scan + fill pass) + "
                         + ("tgx_feasibility" if feas_only else "tgx_eval") + ", parameters resident in HBM",
                 "plan_paths": dict(zip(("single_replay", "two_replay"), eng.plan_path_counts())),
+                "not_hidden_ms_per_step": ms_per_step - eval_ms,
                 "l2": "each step writes %.1f GB >> 126 MB L2, no flush needed" % (eval_bytes / 1e9)
                       if not feas_only else "reduction only",
                 "parallelism": f"{world} independent shards, no data-path collective",
@@ -848,7 +945,9 @@ def run_ours(args):
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "tgx::eval_poly_kernel" if poly else "tgx::eval_kernel", "bytes_per_launch": eval_bytes / chunks,
+                         "kernel": "tgx::eval_poly_kernel" if poly else "tgx::eval_kernel",
+                         "bytes_per_launch": eval_bytes / eval_launches, "launches_per_step": eval_launches,
+                         "ms_per_launch": eval_ms / eval_launches,
                          "peak_source": peak_src + " — of measured" if "MEASURED" in peak_src else peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
@@ -981,6 +1080,10 @@ def main():
     ap.add_argument("--records", action="store_true",
                     help="also run the consumer-side kernel: clamp + pack every sample into a 128-byte record")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gen-chunk", type=int, default=0, help="trajectories per chunk of tgx_generate (0: library default)")
+    ap.add_argument("--pipeline", dest="no_pipeline", action="store_false", default=True,
+                    help="time the pipelined tgx_generate (planning of chunk c+1 under the evaluation of chunk c) instead "
+                         "of tgx_plan + tgx_eval back to back on one stream; measured: no faster (DESIGN.md 12)")
     ap.add_argument("--store-path", default="tma", choices=["tma", "stg"],
                     help="tgx_eval's planes through TMA (default) or through vector stores (tgx_set_store_path)")
     args = ap.parse_args()

@@ -404,6 +404,33 @@ int tgx_plan_samples(tgx_engine* e, const tgx_params* d_params, int64_t n, const
  * written x,y,z components) are reduced in the same pass. */
 int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_max_a, void* stream);
 
+/* ---- generateTraj for a device-resident batch in one call: tgx_plan + tgx_eval, pipelined ------------------------ */
+/* What a caller that wants the samples of a whole batch (Trajectory::generateTraj for n trajectories,
+ * Trajectory.hpp:33) should call.  Planning is a latency-bound replay, evaluation a store stream; run back to back on
+ * one stream they leave half of the machine idle in turn.  tgx_generate cuts the batch into chunks of `chunk`
+ * trajectories (0: an eighth of the batch, between 32 Ki and 1 Mi) and alternates them between the engine and a private
+ * twin on two internal streams, so that chunk c+1 is planned while chunk c is evaluated: all planning but the first
+ * chunk's hides behind the store-bound kernel.  The work starts after everything queued on `stream` so far, and
+ * `stream` waits for all of it; the host returns when the last chunk has been planned (its evaluation may still run).
+ * Writes exactly the bytes tgx_plan + tgx_eval of the whole batch write (the samples do not depend on how a batch is
+ * cut), d_counts / d_status / d_phases (each may be NULL) as tgx_plan does, and the sample total.  Circle / Line /
+ * Figure8 / Boomerang records; polyline-family records get TGX_ST_WRONG_PLANNER as in tgx_plan.  Leaves no current
+ * plan. */
+int tgx_generate(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits, const tgx_layout* out,
+                 int32_t* d_counts, uint32_t* d_status, tgx_phases* d_phases, int64_t chunk, int64_t* total_samples,
+                 void* stream);
+/* Evaluations of consecutive chunks are chained (two store streams at once are not faster than one); what overlaps an
+ * evaluation is the next chunk's planning.
+ * Profiling: with on = 1 every evaluation launch of tgx_generate / tgx_generate_feasibility is bracketed by a CUDA event
+ * pair on the stream it is launched on; tgx_generate_profile waits for them and returns the sum of their durations in
+ * milliseconds and their number since the last query (bench.py's roofline.achieved). */
+int tgx_set_generate_profiling(tgx_engine* e, int on);
+int tgx_generate_profile(tgx_engine* e, double* eval_ms, int64_t* eval_launches);
+/* The same pipeline for the feasibility reduction: tgx_plan + tgx_feasibility per chunk (any output may be NULL). */
+int tgx_generate_feasibility(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits,
+                             uint8_t* d_flags, double* d_max_v, double* d_max_a, uint32_t* d_status, int64_t chunk,
+                             int64_t* total_samples, void* stream);
+
 /* ---- consumer side: clamp to the room bounds + pack to array-of-structs records ------------ */
 /* Reads the struct-of-arrays planes `planes` (as written by tgx_eval; d_counts[i] samples of trajectory i are valid),
  * saturates p.x / p.y / p.z to limits->box if limits && limits->check_box (TrajectoryGenerator.cpp:602-604) and writes

@@ -853,6 +853,58 @@ def test_plan_does_not_reference_caller_parameters(engine, oracle):
         np.testing.assert_array_equal(want2[m], want[m])
 
 
+def test_generate_pipelined_writes_the_same_bytes(engine, oracle):
+    """tgx_generate (chunks alternating between the engine and its twin on two streams, planning of chunk c+1 under the
+    evaluation of chunk c) == tgx_plan + tgx_eval of the whole batch, byte for byte, for every chunking."""
+    import torch
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    bad = workloads.default_circle().copy()
+    bad["accel"] = -1.0
+    for what, params, cap in (("cfg2", workloads.circles_cfg2(6000, seed=9), 1024),
+                              ("cfg3 + default circle + rejected", abi.concat([workloads.mixed_cfg3(3000), bad,
+                                                                               workloads.default_circle()]), None)):
+        want, counts, status, ph = gpu_generate(engine, params, capacity=cap, want_phases=True)
+        n, _, row = want.shape
+        d_params = engine.upload_params(params)
+        for chunk in (0, 1000, n):
+            for plane_major in (False, True):
+                shape = (abi.TGX_NCHAN, n, row) if plane_major else (n, abi.TGX_NCHAN, row)
+                out = torch.full(shape, float("nan"), dtype=torch.float64, device=d_params.device)
+                plan = engine.generate(d_params, out, plane_major=plane_major, want_outputs=True, want_phases=True,
+                                       chunk=chunk)
+                torch.cuda.synchronize()
+                got = out.cpu().numpy()
+                if plane_major:
+                    got = np.ascontiguousarray(got.transpose(1, 0, 2))
+                assert plan.total_samples == int(counts.sum())
+                np.testing.assert_array_equal(plan.counts.cpu().numpy(), counts)
+                np.testing.assert_array_equal(plan.status.cpu().numpy().view(np.uint32), status)
+                ph2 = plan.phases.cpu().numpy().view(abi.PHASES_DTYPE).reshape(n)
+                for i in list(range(0, n, 211)) + [n - 2, n - 1]:
+                    t = int(params["type"][i])
+                    assert abi.phases_to_index_msgs(t, ph2[i]) == abi.phases_to_index_msgs(t, ph[i])
+                m = ~np.isnan(want)
+                assert (np.isnan(got) == ~m).all(), f"{what} chunk {chunk}: different samples written"
+                np.testing.assert_array_equal(got[m], want[m], err_msg=f"{what} chunk {chunk}")
+    # the feasibility pipeline
+    params = workloads.montecarlo_cfg4(30000)
+    d_params = engine.upload_params(params)
+    engine.plan(d_params, limits=lim)
+    f0, v0, a0, s0 = engine.feasibility(lim, len(params))
+    for chunk in (0, 7000):
+        f1, v1, a1, s1, total = engine.generate_feasibility(d_params, lim, chunk=chunk)
+        torch.cuda.synchronize()
+        assert torch.equal(f0, f1) and torch.equal(v0, v1) and torch.equal(a0, a1) and torch.equal(s0, s1)
+    o_counts, _ = oracle.count_batch(params)
+    assert total == int(o_counts.sum())
+    # profiling: one event pair per evaluation launch
+    engine.set_generate_profiling(True)
+    engine.generate_feasibility(d_params, lim, chunk=7000)
+    ms, launches = engine.generate_profile()
+    engine.set_generate_profiling(False)
+    assert launches == 5 and ms > 0.0
+
+
 def test_hold_table_handles_mixed_dt(engine, oracle):
     """The hold-length table is built for the first trajectory's dt; others must fall back to their own walk."""
     recs = [abi.circle_params(1.0, 1.5, 0, 0, [1.0], t, 0.5, dt)

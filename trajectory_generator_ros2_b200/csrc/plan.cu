@@ -912,8 +912,7 @@ plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits l
                   PhaseRec* __restrict__ phase, int32_t* __restrict__ counts, uint32_t* __restrict__ status,
                   int32_t* __restrict__ counts2, uint32_t* __restrict__ status2, tgx_phases* __restrict__ phases,
                   PlanStats* __restrict__ stats) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const tgx_params p = load_params(params, i);
     PhaseRec rec;
     rec.n = 0;
@@ -956,6 +955,7 @@ plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits l
     if (counts2) counts2[i] = r.n;
     if (status2) status2[i] = r.status;
     accumulate_stats(stats, r.n, 0, 0, overflow, !orbit, replay_class(p.type, p.n_vgoals), 0, 0, overflow);
+    }
 }
 
 // "Per-time evaluation": a one-sample plan per trajectory from an explicit state, i.e. the public helpers
@@ -1154,7 +1154,9 @@ cudaError_t launch_plan_phase(const tgx_params* params, int64_t n, const tgx_lim
     if (n <= 0) return cudaSuccess;
     tgx_limits l{};
     if (lim) l = *lim;
-    plan_phase_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(
+    const int cta = 128;
+    const int64_t grid = (n + cta - 1) / cta;
+    plan_phase_kernel<<<(unsigned)grid, cta, 0, stream>>>(
         params, n, l, lim ? 1 : 0, max_samples, tile_shift, max_n, static_cast<const CurTable*>(cur_table), phase,
         counts, status, counts2, status2, phases, stats);
     return cudaGetLastError();

@@ -70,6 +70,10 @@ def _load() -> C.CDLL:
     lib.tgx_transitions.argtypes = [vp, vp, i64, vp, vp, i64, i64, vp, vp, vp]
     lib.tgx_transitions_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp]
     lib.tgx_eval.argtypes = [vp, C.POINTER(abi.Layout), vp, vp, vp]
+    lib.tgx_set_generate_profiling.argtypes = [vp, C.c_int]
+    lib.tgx_generate_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.tgx_generate.argtypes = [vp, vp, i64, vp, C.POINTER(abi.Layout), vp, vp, vp, i64, C.POINTER(i64), vp]
+    lib.tgx_generate_feasibility.argtypes = [vp, vp, i64, C.POINTER(abi.Limits), vp, vp, vp, vp, i64, C.POINTER(i64), vp]
     lib.tgx_feasibility.argtypes = [vp, C.POINTER(abi.Limits), vp, vp, vp, vp, vp]
     lib.tgx_count_host.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.tgx_generate_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp]
@@ -436,6 +440,65 @@ class Engine:
         lay.d_traj_offset = traj_offset.data_ptr() if traj_offset is not None else None
         self._check(self._lib.tgx_eval(self._h, C.byref(lay), max_v.data_ptr() if max_v is not None else None,
                                        max_a.data_ptr() if max_a is not None else None, self._stream()), "tgx_eval")
+
+    def generate(self, d_params, out, limits: Optional[abi.Limits] = None, plane_major: bool = False,
+                 want_outputs: bool = False, want_phases: bool = False, chunk: int = 0) -> Plan:
+        """tgx_generate: plan + evaluate a device-resident batch, pipelined over two internal streams.
+
+        out: float64 [n, 14, row] (or [14, n, row] with plane_major=True).  Returns a Plan (counts / status / phases only
+        if asked for)."""
+        import torch
+        assert out.dtype == torch.float64 and out.is_contiguous()
+        n = int(d_params.shape[0])
+        lay = abi.Layout()
+        lay.d_base = out.data_ptr()
+        if plane_major:
+            nch, rows, row = out.shape
+            lay.traj_stride, lay.chan_stride = row, rows * row
+        else:
+            rows, nch, row = out.shape
+            lay.traj_stride, lay.chan_stride = nch * row, row
+        assert nch == abi.TGX_NCHAN and rows >= n
+        lay.capacity = row
+        counts = status = phases = None
+        if want_outputs:
+            counts = torch.empty(n, dtype=torch.int32, device=d_params.device)
+            status = torch.empty(n, dtype=torch.int32, device=d_params.device)
+        if want_phases:
+            phases = torch.empty((n, C.sizeof(abi.Phases)), dtype=torch.uint8, device=d_params.device)
+        total = C.c_int64(0)
+        self._check(self._lib.tgx_generate(self._h, d_params.data_ptr(), n, _limits_ptr(limits), C.byref(lay),
+                                           counts.data_ptr() if counts is not None else None,
+                                           status.data_ptr() if status is not None else None,
+                                           phases.data_ptr() if phases is not None else None,
+                                           chunk, C.byref(total), self._stream()), "tgx_generate")
+        return Plan(n, counts, status, int(total.value), phases, 0, 0)
+
+    def set_generate_profiling(self, on: bool):
+        self._check(self._lib.tgx_set_generate_profiling(self._h, 1 if on else 0), "tgx_set_generate_profiling")
+
+    def generate_profile(self):
+        """(sum of the evaluation launches' durations in ms, number of launches) since the last query."""
+        ms, cnt = C.c_double(0.0), C.c_int64(0)
+        self._check(self._lib.tgx_generate_profile(self._h, C.byref(ms), C.byref(cnt)), "tgx_generate_profile")
+        return float(ms.value), int(cnt.value)
+
+    def generate_feasibility(self, d_params, limits: abi.Limits, flags=None, max_v=None, max_a=None, status=None,
+                             chunk: int = 0):
+        """tgx_generate_feasibility -> (flags uint8 [n], max_v, max_a, status int32, total samples)."""
+        import torch
+        n = int(d_params.shape[0])
+        dev = d_params.device
+        flags = torch.empty(n, dtype=torch.uint8, device=dev) if flags is None else flags
+        max_v = torch.empty(n, dtype=torch.float64, device=dev) if max_v is None else max_v
+        max_a = torch.empty(n, dtype=torch.float64, device=dev) if max_a is None else max_a
+        status = torch.empty(n, dtype=torch.int32, device=dev) if status is None else status
+        total = C.c_int64(0)
+        self._check(self._lib.tgx_generate_feasibility(self._h, d_params.data_ptr(), n, C.byref(limits),
+                                                       flags.data_ptr(), max_v.data_ptr(), max_a.data_ptr(),
+                                                       status.data_ptr(), chunk, C.byref(total), self._stream()),
+                    "tgx_generate_feasibility")
+        return flags, max_v, max_a, status, int(total.value)
 
     def eval_layout(self, lay: abi.Layout, max_v=None, max_a=None):
         self._check(self._lib.tgx_eval(self._h, C.byref(lay), max_v.data_ptr() if max_v is not None else None,
