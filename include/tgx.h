@@ -51,7 +51,10 @@ extern "C" {
 #endif
 
 #define TGX_VERSION 100          /* 0.1.0 */
-#define TGX_MAX_VGOALS 8         /* inline capacity of v_goals per trajectory (default.yaml:42 uses 3) */
+#define TGX_MAX_VGOALS 8         /* goal speeds held by one record (default.yaml:42 uses 3); see TGX_VGOALS_MORE */
+#define TGX_MAX_VGOALS_TOTAL 64  /* goal speeds of one Circle / Figure8 over its record and its continuation records */
+/* Records a Circle / Figure8 with K goal speeds occupies in the parameter array: 1 for K <= 8, else 1 + ceil((K-8)/8). */
+#define TGX_ORBIT_RECORDS(K) ((K) <= TGX_MAX_VGOALS ? 1 : 1 + ((K) - 1) / TGX_MAX_VGOALS)
 #define TGX_NCHAN 14             /* numeric fields of one setpoint */
 #define TGX_MAX_PHASES (2 * TGX_MAX_VGOALS + 2)  /* index_msgs entries of one trajectory, upper bound */
 
@@ -69,7 +72,16 @@ enum tgx_type {
     TGX_BOUNCE = 7,        /* Bounce.cpp:19-52 */
     TGX_M = 8,             /* M.cpp:13-67 */
     TGX_I = 9,             /* I.cpp:19-75 */
-    TGX_T = 10             /* T.cpp:19-73 */
+    TGX_T = 10,            /* T.cpp:19-73 */
+    /* Continuation of the Circle / Figure8 record in front of it.  The reference loops over a std::vector of any
+     * length (Circle.cpp:43, Figure8.cpp:43); a trajectory with K > 8 goal speeds is written as TGX_ORBIT_RECORDS(K)
+     * CONSECUTIVE records: the first one carries n_vgoals = K and the goals 0..7, continuation record q = 1, 2, ...
+     * (this type) carries the goals 8q .. 8q+7 in u.orbit.v_goals (its other fields are ignored).  A continuation record
+     * is an entry of the batch like any other — count 0, status 0, no samples, its output row is never touched — so
+     * that trajectory i of the batch stays row i of every output; the tgx_phases entries of its row hold the index_msgs
+     * entries 18q .. 18q+17 of the trajectory.  A caller that cuts a batch (chunks, shards) must not separate a record
+     * from its continuations. */
+    TGX_VGOALS_MORE = 30
 };
 #define TGX_IS_POLYLINE(type) ((type) >= TGX_SQUARE && (type) <= TGX_T)
 
@@ -132,7 +144,8 @@ typedef struct tgx_polyline_params {
 /* One trajectory's parameters: exactly 128 bytes, the unit of the batch parameter array. */
 typedef struct tgx_params {
     int32_t type;                    /* enum tgx_type */
-    int32_t n_vgoals;                /* orbit: 1..TGX_MAX_VGOALS; line: ignored; polyline: flag bits (TGX_POLY_*) */
+    int32_t n_vgoals;                /* orbit: 0..TGX_MAX_VGOALS_TOTAL (0: the one-sample trajectory the reference makes of an
+                                        empty vector; > 8: see TGX_VGOALS_MORE); line: ignored; polyline: flag bits */
     double dt;                       /* Trajectory::dt_ = 1/pub_freq (TrajectoryGenerator.cpp:171-172) */
     double alt;                      /* alt_: z of every sample */
     union {
@@ -151,8 +164,10 @@ enum tgx_status_bits {
     TGX_ST_LINE_D2_NEGATIVE      = 1u << 3, /* Line.cpp:165-168: cruise segment length < 0; reported, like the reference does,
                                                by the bounds check only (set together with OUTSIDE_BOUNDS) */
     TGX_ST_OUTSIDE_BOUNDS        = 1u << 4, /* trajectoryInsideBounds() == false (only if a box was given) */
-    TGX_ST_BAD_PARAM             = 1u << 5, /* v<=0, accel<=0 (TrajectoryGenerator.cpp:184-195,268-277), dt<=0, r<=0,
-                                               n_vgoals out of range, unknown type, non-finite input: no samples */
+    TGX_ST_BAD_PARAM             = 1u << 5, /* v<=0, accel<=0 (TrajectoryGenerator.cpp:184-195,268-277), dt<=0, r==0
+                                               (a negative radius flies the mirrored circle, as in the reference),
+                                               n_vgoals out of range or continuation records missing, unknown type,
+                                               non-finite input: no samples */
     TGX_ST_VMAX_EXCEEDED         = 1u << 6, /* max_k |v_k| > limits.v_max  (tgx_feasibility only) */
     TGX_ST_AMAX_EXCEEDED         = 1u << 7, /* max_k |a_k| > limits.a_max  (tgx_feasibility only) */
     TGX_ST_TOO_LONG              = 1u << 8, /* sample count would exceed the engine's max_samples guard (the reference

@@ -46,11 +46,15 @@ bool params_ok(const tgx_params& p) {
     if (!finite_pos(p.dt) || !std::isfinite(p.alt)) return false;
     if (p.type == TGX_CIRCLE || p.type == TGX_FIGURE8) {
         const tgx_orbit_params& o = p.u.orbit;
-        if (p.n_vgoals < 1 || p.n_vgoals > TGX_MAX_VGOALS) return false;
-        if (!finite_pos(o.r) || !finite_pos(o.accel)) return false;
+        // goal speeds beyond the eighth live in the continuation records that follow p (tgx.h: TGX_VGOALS_MORE); the
+        // caller guarantees they are there
+        if (p.n_vgoals < 0 || p.n_vgoals > TGX_MAX_VGOALS_TOTAL) return false;
+        if (!std::isfinite(o.r) || o.r == 0.0 || !finite_pos(o.accel)) return false;
         if (!std::isfinite(o.cx) || !std::isfinite(o.cy) || !std::isfinite(o.t_traj)) return false;
+        for (int q = 1; q < TGX_ORBIT_RECORDS(p.n_vgoals); ++q)
+            if ((&p)[q].type != TGX_VGOALS_MORE) return false;
         for (int i = 0; i < p.n_vgoals; ++i)
-            if (!finite_pos(o.v_goals[i])) return false;
+            if (!finite_pos(i < TGX_MAX_VGOALS ? o.v_goals[i] : (&p)[i >> 3].u.orbit.v_goals[i & 7])) return false;
         return true;
     }
     if (p.type == TGX_LINE || p.type == TGX_BOOMERANG) {
@@ -115,7 +119,9 @@ std::unique_ptr<tg::Trajectory> make_traj(const tgx_params& p) {
                                           Eigen::Vector3d(l.B[0], l.B[1], l.B[2]), vg, l.a1, l.a3, p.dt);
     }
     const tgx_orbit_params& o = p.u.orbit;
-    std::vector<double> vg(o.v_goals, o.v_goals + p.n_vgoals);
+    std::vector<double> vg;
+    for (int i = 0; i < p.n_vgoals; ++i)
+        vg.push_back(i < TGX_MAX_VGOALS ? o.v_goals[i] : (&p)[i >> 3].u.orbit.v_goals[i & 7]);
     if (p.type == TGX_FIGURE8)
         return std::make_unique<tg::Figure8>(p.alt, o.r, o.cx, o.cy, vg, o.t_traj, o.accel, p.dt);
     return std::make_unique<tg::Circle>(p.alt, o.r, o.cx, o.cy, vg, o.t_traj, o.accel, p.dt);

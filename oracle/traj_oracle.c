@@ -40,13 +40,33 @@ static void sink_push(sink_t* s, const double g[TGX_NCHAN]) {
     s->n += 1;
 }
 
+/* index_msgs entry: a trajectory with more than 8 goal speeds owns the tgx_phases rows of its continuation records too
+ * (tgx.h: TGX_VGOALS_MORE); entry e goes to slot e % 18 of row e / 18.  g_ph_rows is set by the entry points. */
+static __thread int g_ph_rows = 1;
+/* records available from the one an entry point was handed (the batch drivers know; single calls trust the caller) */
+static __thread int64_t g_navail = INT64_MAX;
+
 static void phase_add(tgx_phases* ph, int64_t key, int kind, double value, double value2) {
-    if (!ph || ph->n >= TGX_MAX_PHASES) return;
+    if (!ph) return;
+    int b = 0;
+    while (ph[b].n >= TGX_MAX_PHASES && b + 1 < g_ph_rows) ++b;
+    ph += b;
+    if (ph->n >= TGX_MAX_PHASES) return;
     ph->key[ph->n] = (int32_t)key;
     ph->kind[ph->n] = kind;
     ph->value[ph->n] = value;
     ph->value2[ph->n] = value2;
     ph->n += 1;
+}
+
+static void phases_clear(tgx_phases* ph) {
+    if (!ph) return;
+    for (int b = 0; b < g_ph_rows; ++b) ph[b].n = 0;
+}
+
+/* Goal speed g of an orbit record: beyond the eighth they live in the continuation records that follow it. */
+static double orbit_goal_speed(const tgx_params* p, int g) {
+    return g < TGX_MAX_VGOALS ? p->u.orbit.v_goals[g] : p[g >> 3].u.orbit.v_goals[g & 7];
 }
 
 /* std::min(a, b) / std::max(a, b) exactly as libstdc++ defines them. */
@@ -138,11 +158,16 @@ static int params_ok(const tgx_params* p) {
     if (!finite_pos(p->dt) || !isfinite(p->alt)) return 0;
     if (p->type == TGX_CIRCLE || p->type == TGX_FIGURE8) {
         const tgx_orbit_params* o = &p->u.orbit;
-        if (p->n_vgoals < 1 || p->n_vgoals > TGX_MAX_VGOALS) return 0;
-        if (!finite_pos(o->r) || !finite_pos(o->accel)) return 0;
+        /* the reference takes a vector of any length (an empty one gives the start sample alone) and any non-zero
+         * radius; the caller guarantees that the continuation records of n_vgoals > 8 follow p in memory */
+        if (p->n_vgoals < 0 || p->n_vgoals > TGX_MAX_VGOALS_TOTAL) return 0;
+        if (!isfinite(o->r) || o->r == 0.0 || !finite_pos(o->accel)) return 0;
         if (!isfinite(o->cx) || !isfinite(o->cy) || !isfinite(o->t_traj)) return 0;
+        if (TGX_ORBIT_RECORDS(p->n_vgoals) > g_navail) return 0;
+        for (int q = 1; q < TGX_ORBIT_RECORDS(p->n_vgoals); ++q)
+            if (p[q].type != TGX_VGOALS_MORE) return 0;
         for (int i = 0; i < p->n_vgoals; ++i)
-            if (!finite_pos(o->v_goals[i])) return 0;
+            if (!finite_pos(orbit_goal_speed(p, i))) return 0;
         return 1;
     }
     if (p->type == TGX_LINE || p->type == TGX_BOOMERANG) {
@@ -202,7 +227,7 @@ static int64_t orbit_generate(const tgx_params* p, sink_t* sk, uint32_t* status,
     orbit_goal(p, v, theta, g);                       /* :41 */
     sink_push(sk, g);
     for (int i = 0; i < p->n_vgoals; ++i) {           /* :43 */
-        double v_goal = o->v_goals[i];
+        double v_goal = orbit_goal_speed(p, i);
         phase_add(ph, sk->n - 1, TGX_PH_ACCEL_TO, v_goal, 0.0);   /* :45 */
         while (v < v_goal) {                          /* :47 */
             double v_new = std_min(v + o->accel * p->dt, v_goal);
@@ -788,7 +813,11 @@ int64_t orc_generate(const tgx_params* p, double* out, int64_t chan_stride, int6
     uint32_t st = 0;
     int64_t n;
     sink_t sk = {out, chan_stride, cap, 0, {0}};
-    if (ph) ph->n = 0;
+    g_ph_rows = 1;
+    if ((p->type == TGX_CIRCLE || p->type == TGX_FIGURE8) && p->n_vgoals > TGX_MAX_VGOALS &&
+        p->n_vgoals <= TGX_MAX_VGOALS_TOTAL && TGX_ORBIT_RECORDS(p->n_vgoals) <= g_navail)
+        g_ph_rows = TGX_ORBIT_RECORDS(p->n_vgoals);
+    phases_clear(ph);
     if (!params_ok(p)) {
         st |= TGX_ST_BAD_PARAM;
         n = -1;
@@ -801,7 +830,8 @@ int64_t orc_generate(const tgx_params* p, double* out, int64_t chan_stride, int6
     } else {
         n = orbit_generate(p, &sk, &st, ph, max_samples);
     }
-    if (n < 0 && ph) ph->n = 0;
+    if (n < 0) phases_clear(ph);
+    g_ph_rows = 1;
     if (n > cap && out) st |= TGX_ST_TRUNCATED;
     if (status) *status = st;
     return n;
@@ -814,6 +844,7 @@ int64_t orc_stop(const tgx_params* p, const double* from, double* out, int64_t c
     uint32_t st = 0;
     sink_t sk = {out, chan_stride, cap, 0, {0}};
     double g[TGX_NCHAN];
+    g_ph_rows = 1;
     if (ph) ph->n = 0;
     if (!params_ok(p)) {
         if (status) *status = TGX_ST_BAD_PARAM;
@@ -905,6 +936,7 @@ int orc_inside_bounds(const tgx_params* p, const double box[6]) {
 typedef struct {
     int mode;                 /* 0 generate, 1 feasibility, 2 timing */
     const tgx_params* p;
+    int64_t n_total;
     int64_t lo, hi;
     double* out;
     int64_t traj_stride, chan_stride, cap;
@@ -942,6 +974,23 @@ static void* job_run(void* arg) {
     for (int64_t i = j->lo; i < j->hi; ++i) {
         uint32_t st = 0;
         int64_t n;
+        g_navail = j->n_total - i;
+        if (j->p[i].type == TGX_VGOALS_MORE) {
+            /* a continuation record (tgx.h): an entry without a trajectory; an orphan is a bad record */
+            int owned = 0;
+            for (int q = 1; q < TGX_MAX_VGOALS_TOTAL / TGX_MAX_VGOALS && i - q >= 0; ++q) {
+                const tgx_params* h = &j->p[i - q];
+                if (h->type == TGX_VGOALS_MORE) continue;
+                owned = (h->type == TGX_CIRCLE || h->type == TGX_FIGURE8) && TGX_ORBIT_RECORDS(h->n_vgoals) > q;
+                break;
+            }
+            if (j->counts) j->counts[i] = 0;
+            if (j->status) j->status[i] = owned ? 0u : (uint32_t)TGX_ST_BAD_PARAM;
+            if (j->max_v) j->max_v[i] = 0.0;
+            if (j->max_a) j->max_a[i] = 0.0;
+            if (j->flags) j->flags[i] = owned ? 1 : 0;
+            continue;
+        }
         if (j->mode == 0) {
             double* dst = j->out ? j->out + i * j->traj_stride : NULL;
             n = orc_generate(&j->p[i], dst, j->chan_stride, j->cap, &st, NULL, j->max_samples);
@@ -963,8 +1012,11 @@ static void* job_run(void* arg) {
             if (j->mode == 1) {
                 double mv = 0.0, ma = 0.0;
                 if (n > 0) reduce_norms(scratch, scratch_cap, n, &mv, &ma);
-                if (j->limits && j->limits->check_box && !(st & TGX_ST_BAD_PARAM) &&
-                    !orc_inside_bounds(&j->p[i], j->limits->box)) {
+                /* trajectoryInsideBounds tests the geometry alone (Circle.cpp:171-179, Line.cpp:154-173): it is
+                 * reported for records the samplers reject too (polyline records: only accepted ones) */
+                if (j->limits && j->limits->check_box &&
+                    (!(st & TGX_ST_BAD_PARAM) || !TGX_IS_POLYLINE(j->p[i].type)) && j->p[i].type >= TGX_CIRCLE &&
+                    j->p[i].type <= TGX_T && !orc_inside_bounds(&j->p[i], j->limits->box)) {
                     st |= TGX_ST_OUTSIDE_BOUNDS;
                     /* Line::trajectoryInsideBounds reports "not feasible" when d2 < 0 (Line.cpp:165-168) */
                     if ((j->p[i].type == TGX_LINE || j->p[i].type == TGX_BOOMERANG) && orc_line_d2(&j->p[i]) < 0)
@@ -984,6 +1036,7 @@ static void* job_run(void* arg) {
         if (n > 0) j->total += n;
     }
     free(scratch);
+    g_navail = INT64_MAX;
     return NULL;
 }
 
@@ -996,6 +1049,7 @@ static int64_t run_jobs(job_t* proto, int64_t n, int nthreads, double* checksum)
     if (!jobs || !th) { free(jobs); free(th); return -1; }
     for (int t = 0; t < nthreads; ++t) {
         jobs[t] = *proto;
+        jobs[t].n_total = n;
         jobs[t].lo = n * t / nthreads;
         jobs[t].hi = n * (t + 1) / nthreads;
     }

@@ -219,6 +219,25 @@ int main() {
             }
         }
     }
+    {   // v_goals of any length (Circle.cpp:43 loops over a std::vector): 12 and 17 goal speeds go through continuation
+        // records (tgx.h: TGX_VGOALS_MORE); an empty vector is the start sample alone; a negative radius is the
+        // mirrored circle.  The node checks vel > 0 and accel > 0 only (TrajectoryGenerator.cpp:184-195).
+        std::vector<double> v12, v17;
+        for (int i = 0; i < 12; ++i) v12.push_back(0.3 + 0.2 * i);
+        for (int i = 0; i < 17; ++i) v17.push_back(0.25 + 0.15 * i);
+        ref::Circle r12(1.5, 2.0, 0.3, -0.2, v12, 0.7, 1.0, dt);
+        gpu::Circle g12(1.5, 2.0, 0.3, -0.2, v12, 0.7, 1.0, dt);
+        runPair("12-goal Circle", r12, g12, 700);
+        ref::Figure8 r17(1.2, 1.5, 0.0, 0.5, v17, 0.4, 1.5, dt);
+        gpu::Figure8 g17(1.2, 1.5, 0.0, 0.5, v17, 0.4, 1.5, dt);
+        runPair("17-goal Figure8", r17, g17, 900);
+        ref::Circle r0(1.5, 2.0, 0.3, -0.2, {}, 0.7, 1.0, dt);
+        gpu::Circle g0(1.5, 2.0, 0.3, -0.2, {}, 0.7, 1.0, dt);
+        runPair("empty-v_goals Circle", r0, g0, 0);
+        ref::Circle rn(1.5, -2.0, 0.3, -0.2, {1.0, 2.0}, 0.7, 1.0, dt);
+        gpu::Circle gn(1.5, -2.0, 0.3, -0.2, {1.0, 2.0}, 0.7, 1.0, dt);
+        runPair("negative-radius Circle", rn, gn, 200);
+    }
     // random parameters
     std::mt19937_64 rng(20261018);
     std::uniform_real_distribution<double> U(0.0, 1.0);

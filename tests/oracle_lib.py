@@ -71,7 +71,18 @@ class Oracle:
         L.orc_fnv1a64.argtypes = [_c_dp, _c_i64, C.c_uint64]
 
     # -- single trajectory ---------------------------------------------------------------------------
+    @staticmethod
+    def _rows(p: np.ndarray) -> int:
+        """Records the trajectory p[0] occupies; the C side trusts that they are all there."""
+        p = np.ascontiguousarray(p)
+        k = int(p["n_vgoals"][0])
+        rows = abi.orbit_records(k) if int(p["type"][0]) in (abi.TGX_CIRCLE, abi.TGX_FIGURE8) and \
+            0 <= k <= abi.TGX_MAX_VGOALS_TOTAL else 1
+        assert len(p) >= rows and p.flags.c_contiguous, "pass the continuation records together with the first one"
+        return rows
+
     def count(self, p: np.ndarray, max_samples: int = abi.DEFAULT_MAX_SAMPLES):
+        self._rows(p)
         st = C.c_uint32(0)
         n = self.lib.orc_generate(p.ctypes.data, None, 0, 0, C.byref(st), None, max_samples)
         return int(n), int(st.value)
@@ -79,14 +90,15 @@ class Oracle:
     def generate(self, p: np.ndarray, max_samples: int = abi.DEFAULT_MAX_SAMPLES):
         """-> (samples[14, N], status, phases-record)."""
         n, st = self.count(p, max_samples)
-        ph = np.zeros(1, dtype=abi.PHASES_DTYPE)
+        rows = self._rows(p)
+        ph = np.zeros(rows, dtype=abi.PHASES_DTYPE)
         if n <= 0:
             return np.zeros((abi.TGX_NCHAN, 0)), st, ph[0]
         out = np.full((abi.TGX_NCHAN, n), np.nan)
         st2 = C.c_uint32(0)
         n2 = self.lib.orc_generate(p.ctypes.data, _ptr(out), n, n, C.byref(st2), ph.ctypes.data, max_samples)
         assert n2 == n
-        return out, int(st2.value), ph[0]
+        return out, int(st2.value), (ph[0] if rows == 1 else ph)
 
     def polyline_generate(self, p: np.ndarray, max_samples: int = abi.DEFAULT_MAX_SAMPLES):
         """Polyline family -> (samples[14, N], status, leg_of[N] int16, index_msgs dict)."""

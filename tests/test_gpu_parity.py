@@ -177,12 +177,59 @@ def test_vgoals_edge_cases(mode_engine, oracle):
     check_batch(engine, oracle, params, "v_goals edge cases")
 
 
+def test_vgoals_of_any_length(mode_engine, oracle):
+    """The reference loops over a std::vector of any length (Circle.cpp:43): more than 8 goal speeds travel in
+    continuation records (TGX_VGOALS_MORE), an empty vector is the start sample alone, a negative radius the mirrored
+    circle.  Continuation records are entries of the batch without samples; their tgx_phases rows hold the trajectory's
+    further index_msgs entries."""
+    engine = mode_engine
+    rng = np.random.default_rng(3)
+    trajs = []
+    for K in (0, 9, 12, 16, 17, 30, 3, 0, 64):
+        v = list(np.sort(rng.uniform(0.3, 2.8, K)))
+        kind = abi.TGX_FIGURE8 if K % 2 else abi.TGX_CIRCLE
+        t_hold = 0.5 if K == 64 else rng.uniform(0.05, 0.6)     # 64 goals: ~19 per 1024-sample tile, < 64 segments
+        trajs.append(abi.circle_params(1.5, rng.uniform(0.8, 3.0), 0.3, -0.2, v, t_hold, 1.3, 0.01, kind=kind))
+    trajs.append(abi.circle_params(1.5, -2.0, 0.3, -0.2, [1.0, 2.0], 0.7, 1.0, 0.01))                # r < 0
+    trajs.append(abi.circle_params(1.5, -1.1, 0.0, 0.0, [0.8], 3.0, 0.9, 0.01, kind=abi.TGX_FIGURE8))
+    orphan = abi.circle_params(1.5, 2.0, 0, 0, list(np.linspace(0.5, 2, 12)), 0.3, 1.0, 0.01)[1:]     # a continuation alone
+    short = abi.circle_params(1.5, 2.0, 0, 0, list(np.linspace(0.5, 2, 20)), 0.3, 1.0, 0.01)[:2]      # one record missing
+    params = abi.concat(trajs + [orphan, workloads.circles_cfg2(5), short])
+    starts = np.cumsum([0] + [len(t) for t in trajs])[:-1]
+    out, counts, status, ph = gpu_generate(engine, params)
+    o_counts, o_status = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts, o_counts)
+    np.testing.assert_array_equal(status, o_status)
+    base = int(starts[-1] + len(trajs[-1]))
+    assert status[base] == abi.ST_BAD_PARAM and counts[base] == 0, "an orphan continuation record is a bad record"
+    assert status[-2] == abi.ST_BAD_PARAM and status[-1] == 0 and counts[-2] == 0, "missing continuation record"
+    for t, i in zip(trajs, starts):
+        rows = len(t)
+        ref, st, oph = oracle.generate(params[i:i + rows])
+        n = counts[i]
+        assert ref.shape[1] == n and (n > 0)
+        assert (counts[i + 1:i + rows] == 0).all() and (status[i + 1:i + rows] == 0).all()
+        assert_samples_close(out[i, :, :n], ref, f"K = {int(t['n_vgoals'][0])}, r = {float(t['r'][0]):.2f}")
+        assert np.isnan(out[i + 1:i + rows]).all(), "continuation rows must stay untouched"
+        kind = int(t["type"][0])
+        assert abi.phases_to_index_msgs(kind, ph[i:i + rows] if rows > 1 else ph[i]) == \
+            abi.phases_to_index_msgs(kind, oph)
+    assert counts[starts[0]] == 1                      # empty vector: the start sample alone
+    # the same through the host-buffer call, whose chunks must not separate a record from its continuations
+    cap = int(counts.max() + 3) // 4 * 4
+    h_out, h_counts, h_status, _ = engine.generate_host(params, cap)
+    np.testing.assert_array_equal(h_counts, counts)
+    np.testing.assert_array_equal(h_status, status)
+    for i in starts:
+        np.testing.assert_array_equal(h_out[i, :, :counts[i]], out[i, :, :counts[i]])
+
+
 def test_bad_params_are_rejected(mode_engine, oracle):
     engine = mode_engine
     good = abi.circle_params(1.8, 3.4, 0, 0, [1.0], 2.0, 0.4, 0.01)
     bad = []
     for field, val in (("accel", 0.0), ("accel", -1.0), ("r", 0.0), ("dt", 0.0), ("dt", float("nan")),
-                       ("t_traj", float("inf")), ("n_vgoals", 0), ("n_vgoals", 9), ("type", 99)):
+                       ("t_traj", float("inf")), ("n_vgoals", -1), ("n_vgoals", 9), ("n_vgoals", 65), ("type", 99)):
         q = good.copy()
         q[field] = val
         bad.append(q)

@@ -102,10 +102,22 @@ def test_survey_count_traps(oracle):
 
 def test_oracle_rejects_bad_parameters(oracle):
     good = workloads.default_circle()
-    for field, val in (("accel", 0.0), ("r", -1.0), ("dt", 0.0), ("n_vgoals", 0), ("n_vgoals", 9), ("type", 5)):
+    for field, val in (("accel", 0.0), ("r", 0.0), ("dt", 0.0), ("n_vgoals", -1), ("n_vgoals", 65), ("type", 5)):
         q = good.copy()
         q[field] = val
         n, st = oracle.count(q)
         assert n == -1 and st == abi.ST_BAD_PARAM
+    # nine goal speeds need a continuation record (tgx.h: TGX_VGOALS_MORE): without one the record is rejected
+    q = abi.concat([good, good])
+    q["n_vgoals"][0] = 9
+    counts, status = oracle.count_batch(q)
+    assert counts[0] == 0 and status[0] == abi.ST_BAD_PARAM and counts[1] > 0
+    # what the reference accepts although it is unusual: an empty vector (the start sample alone), a negative radius
+    q = good.copy()
+    q["n_vgoals"] = 0
+    assert oracle.count(q) == (1, 0)
+    q = good.copy()
+    q["r"] = -3.4
+    assert oracle.count(q) == oracle.count(good)
     n, st = oracle.count(abi.circle_params(1, 1, 0, 0, [1.0], 1e9, 1.0, 0.01), max_samples=10000)
     assert n == -1 and st == abi.ST_TOO_LONG

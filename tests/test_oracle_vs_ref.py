@@ -39,6 +39,31 @@ def test_index_msgs_and_stop_bit_exact(oracle, reference):
         assert abi.phases_to_index_msgs(t, soph, stop_traj=True) == srmsgs
 
 
+def test_vgoals_of_any_length_bit_exact(oracle, reference):
+    """The reference loops over a std::vector of any length (Circle.cpp:43, Figure8.cpp:43) and accepts any non-zero
+    radius: more than 8 goal speeds (continuation records, tgx.h TGX_VGOALS_MORE), none at all, r < 0."""
+    rng = np.random.default_rng(5)
+    for K in (0, 1, 8, 9, 12, 16, 17, 30, 64):
+        for kind in (abi.TGX_CIRCLE, abi.TGX_FIGURE8):
+            v = list(np.sort(rng.uniform(0.3, 2.8, K)))
+            if K == 12:
+                v[5] = v[4] * 0.5                           # a goal below the current speed: warning, skipped ramp
+            r = rng.uniform(0.8, 3.0) * (-1.0 if K in (1, 12) else 1.0)
+            p = abi.circle_params(1.5, r, 0.3, -0.2, v, rng.uniform(0.05, 0.6), 1.3, 0.01, kind=kind)
+            assert len(p) == abi.orbit_records(K)
+            o, ost, oph = oracle.generate(p)
+            rr, rst, rmsgs = reference.generate(p)
+            assert ost == rst and o.shape == rr.shape and o.shape[1] >= 1
+            assert ((o + 0.0).view(np.uint64) == (rr + 0.0).view(np.uint64)).all()
+            assert abi.phases_to_index_msgs(kind, oph) == rmsgs
+            assert len(rmsgs) == (2 * K + 2 if K else 1) - (1 if K == 12 else 0)     # a skipped ramp shares its key
+            k = o.shape[1] // 2
+            so, _, soph = oracle.stop(p, o[:, k])
+            sr, _, srmsgs = reference.stop(p, rr[:, k])
+            assert so.shape == sr.shape and ((so + 0.0).view(np.uint64) == (sr + 0.0).view(np.uint64)).all()
+            assert abi.phases_to_index_msgs(kind, soph, stop_traj=True) == srmsgs
+
+
 def test_bounds_and_feasibility_match(oracle, reference):
     params = abi.concat([workloads.montecarlo_cfg4(500), workloads.mixed_cfg3(300)])
     lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)

@@ -12,6 +12,14 @@ import ctypes as C
 import numpy as np
 
 TGX_MAX_VGOALS = 8
+TGX_MAX_VGOALS_TOTAL = 64
+TGX_VGOALS_MORE = 30          # type of a continuation record (tgx.h)
+
+
+def orbit_records(k: int) -> int:
+    """TGX_ORBIT_RECORDS: parameter records a Circle / Figure8 with k goal speeds occupies."""
+    return 1 if k <= TGX_MAX_VGOALS else 1 + (k - 1) // TGX_MAX_VGOALS
+
 TGX_NCHAN = 14
 TGX_MAX_PHASES = 2 * TGX_MAX_VGOALS + 2
 
@@ -239,14 +247,20 @@ def make_limits(box=None, v_max=float("inf"), a_max=float("inf")) -> Limits:
 
 
 def circle_params(alt, r, cx, cy, v_goals, t_traj, accel, dt, kind=TGX_CIRCLE) -> np.ndarray:
-    """One Circle (or Figure8) record from the reference constructor arguments (Circle.hpp:30-31)."""
-    p = np.zeros(1, dtype=PARAMS_DTYPE)
+    """One Circle (or Figure8) from the reference constructor arguments (Circle.hpp:30-31): one record, plus the
+    continuation records (TGX_VGOALS_MORE) that hold the goal speeds beyond the eighth."""
     v_goals = list(v_goals)
-    p["type"] = kind
-    p["n_vgoals"] = len(v_goals)
+    p = np.zeros(orbit_records(len(v_goals)), dtype=PARAMS_DTYPE)
+    p["type"] = TGX_VGOALS_MORE
+    p["type"][0] = kind
+    p["n_vgoals"][0] = len(v_goals)
     p["dt"], p["alt"] = dt, alt
-    p["r"], p["cx"], p["cy"], p["t_traj"], p["accel"] = r, cx, cy, t_traj, accel
-    p["v_goals"][0, :min(len(v_goals), TGX_MAX_VGOALS)] = v_goals[:TGX_MAX_VGOALS]
+    p["r"][0], p["cx"][0], p["cy"][0], p["t_traj"][0], p["accel"][0] = r, cx, cy, t_traj, accel
+    for q in range(len(p)):
+        part = v_goals[q * TGX_MAX_VGOALS:(q + 1) * TGX_MAX_VGOALS]
+        p["v_goals"][q, :len(part)] = part
+        if q:
+            p["n_vgoals"][q] = len(part)
     return p
 
 
@@ -400,9 +414,11 @@ def format_phase(type_id: int, kind: int, value: float, value2: float, stop_traj
 
 
 def phases_to_index_msgs(type_id: int, ph, stop_traj: bool = False) -> dict:
-    """tgx_phases record -> {sample index: message}; later entries overwrite earlier ones at the same key."""
+    """tgx_phases record -> {sample index: message}; later entries overwrite earlier ones at the same key.  `ph` may
+    also be the ROWS of a trajectory with more than 8 goal speeds (its own and its continuation records')."""
     out = {}
-    for i in range(int(ph["n"])):
-        out[int(ph["key"][i])] = format_phase(type_id, int(ph["kind"][i]), float(ph["value"][i]),
-                                              float(ph["value2"][i]), stop_traj)
+    for row in (ph if isinstance(ph, np.ndarray) and ph.ndim == 1 else [ph]):
+        for i in range(int(row["n"])):
+            out[int(row["key"][i])] = format_phase(type_id, int(row["kind"][i]), float(row["value"][i]),
+                                                   float(row["value2"][i]), stop_traj)
     return out

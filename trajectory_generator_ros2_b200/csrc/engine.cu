@@ -1635,18 +1635,21 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
     const int64_t row_bytes = (int64_t)TGX_NCHAN * capacity * (int64_t)sizeof(double);
     int64_t chunk = row_bytes > 0 ? std::max<int64_t>(1, ((int64_t)1 << 30) / row_bytes) : n;
     chunk = std::min(chunk, n);
-    const int64_t nchunks = (n + chunk - 1) / chunk;
+    // a chunk never ends between an orbit record and its continuation records (tgx.h: TGX_VGOALS_MORE): it may grow
+    // by up to 7 records
+    constexpr int64_t kMoreMax = TGX_MAX_VGOALS_TOTAL / TGX_MAX_VGOALS - 1;
+    const int64_t chunk_cap = std::min(n, chunk + kMoreMax);
 
-    for (int b = 0; b < 2 && b < nchunks; ++b) {
-        if ((rc = e->h_params[b].reserve((size_t)chunk * sizeof(tgx_params)))) return rc;
-        if (!h_records && (rc = e->h_out[b].reserve((size_t)std::max<int64_t>(chunk * row_bytes, 32)))) return rc;
-        if ((rc = e->h_cnt[b].reserve((size_t)chunk * sizeof(int32_t)))) return rc;
-        if ((rc = e->h_st[b].reserve((size_t)chunk * sizeof(uint32_t)))) return rc;
-        if (h_phases && (rc = e->h_ph[b].reserve((size_t)chunk * sizeof(tgx_phases)))) return rc;
-        if (h_from && (rc = e->h_from[b].reserve((size_t)chunk * TGX_NCHAN * sizeof(double)))) return rc;
-        if (h_legs && (rc = e->h_legs[b].reserve((size_t)chunk * sizeof(tgx_polyline_legs)))) return rc;
+    for (int b = 0; b < 2 && (b == 0 || chunk < n); ++b) {
+        if ((rc = e->h_params[b].reserve((size_t)chunk_cap * sizeof(tgx_params)))) return rc;
+        if (!h_records && (rc = e->h_out[b].reserve((size_t)std::max<int64_t>(chunk_cap * row_bytes, 32)))) return rc;
+        if ((rc = e->h_cnt[b].reserve((size_t)chunk_cap * sizeof(int32_t)))) return rc;
+        if ((rc = e->h_st[b].reserve((size_t)chunk_cap * sizeof(uint32_t)))) return rc;
+        if (h_phases && (rc = e->h_ph[b].reserve((size_t)chunk_cap * sizeof(tgx_phases)))) return rc;
+        if (h_from && (rc = e->h_from[b].reserve((size_t)chunk_cap * TGX_NCHAN * sizeof(double)))) return rc;
+        if (h_legs && (rc = e->h_legs[b].reserve((size_t)chunk_cap * sizeof(tgx_polyline_legs)))) return rc;
         if (h_records &&
-            (rc = e->h_rec[b].reserve((size_t)std::max<int64_t>(chunk * capacity, 1) * sizeof(tgx_goal_record))))
+            (rc = e->h_rec[b].reserve((size_t)std::max<int64_t>(chunk_cap * capacity, 1) * sizeof(tgx_goal_record))))
             return rc;
     }
     // Bounce moves along z (Bounce.cpp:39-41): its z-channels are not constants
@@ -1697,10 +1700,11 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
     } joiner{fillers};
 
-    for (int64_t ci = 0; ci < nchunks; ++ci) {
+    for (int64_t ci = 0, lo = 0, m = 0; lo < n; ++ci, lo += m) {
         const int b = (int)(ci & 1);
         cudaStream_t s = e->hs[b];
-        const int64_t lo = ci * chunk, m = std::min(chunk, n - lo);
+        m = std::min(chunk, n - lo);
+        while (lo + m < n && m < chunk_cap && h_params[lo + m].type == TGX_VGOALS_MORE) ++m;
         // the staging buffers of slot b are free once the copies issued two chunks ago have completed
         if (ci >= 2) TGX_CUDA(cudaEventSynchronize(e->hev[b]));
         // the plan tables are shared by both slots: do not re-plan before the previous chunk's evaluation is done

@@ -20,17 +20,36 @@ namespace tgx {
 
 namespace {
 
+// Where a trajectory's parameter record sits in the batch: goal speeds beyond the eighth live in the continuation
+// records that follow it (tgx.h: TGX_VGOALS_MORE).
+struct Src {
+    const tgx_params* params;
+    int64_t i, n;
+};
+
+__device__ __forceinline__ double orbit_goal(const tgx_params& p, const Src& src, int g) {
+    if (g < TGX_MAX_VGOALS) return p.u.orbit.v_goals[g];
+    return __ldg(&src.params[src.i + (g >> 3)].u.orbit.v_goals[g & 7]);
+}
+
 // Same acceptance rule as the node-side validation (TrajectoryGenerator.cpp:184-195, 268-277) plus the
-// conditions under which the reference's loops cannot terminate (dt <= 0, r <= 0, non-finite input).
-__device__ bool params_ok(const tgx_params& p) {
+// conditions under which the reference's loops cannot terminate (dt <= 0, r == 0, non-finite input).
+// check_goals = false: the per-time evaluation helpers (create*Goal) do not involve the goal speeds.
+__device__ bool params_ok(const tgx_params& p, const Src& src, bool check_goals = true) {
     if (!finite_pos(p.dt) || !isfinite(p.alt)) return false;
     if (p.type == TGX_CIRCLE || p.type == TGX_FIGURE8) {
         const tgx_orbit_params& o = p.u.orbit;
-        if (p.n_vgoals < 1 || p.n_vgoals > TGX_MAX_VGOALS) return false;
-        if (!finite_pos(o.r) || !finite_pos(o.accel)) return false;
+        if (p.n_vgoals < 0 || p.n_vgoals > TGX_MAX_VGOALS_TOTAL) return false;
+        // a negative radius is legal in the reference (omega = v / r_ < 0: the mirrored circle)
+        if (!isfinite(o.r) || o.r == 0.0 || !finite_pos(o.accel)) return false;
         if (!isfinite(o.cx) || !isfinite(o.cy) || !isfinite(o.t_traj)) return false;
-        for (int i = 0; i < p.n_vgoals; ++i)
-            if (!finite_pos(o.v_goals[i])) return false;
+        if (!check_goals) return true;
+        const int more = TGX_ORBIT_RECORDS(p.n_vgoals) - 1;
+        if (src.i + more >= src.n) return false;
+        for (int q = 1; q <= more; ++q)
+            if (__ldg(&src.params[src.i + q].type) != TGX_VGOALS_MORE) return false;
+        for (int g = 0; g < p.n_vgoals; ++g)
+            if (!finite_pos(orbit_goal(p, src, g))) return false;
         return true;
     }
     if (p.type == TGX_LINE || p.type == TGX_BOOMERANG) {
@@ -38,6 +57,16 @@ __device__ bool params_ok(const tgx_params& p) {
         for (int i = 0; i < 3; ++i)
             if (!isfinite(l.A[i]) || !isfinite(l.B[i])) return false;
         return finite_pos(l.v_goal) && finite_pos(l.a1) && finite_pos(l.a3);
+    }
+    return false;
+}
+
+// A continuation record is valid when it belongs to an orbit record with enough goal speeds to reach it.
+__device__ bool continuation_has_owner(const Src& src) {
+    for (int q = 1; q < TGX_MAX_VGOALS_TOTAL / TGX_MAX_VGOALS && src.i - q >= 0; ++q) {
+        const int2 head = __ldg(reinterpret_cast<const int2*>(src.params + (src.i - q)));      // {type, n_vgoals}
+        if (head.x == TGX_VGOALS_MORE) continue;
+        return (head.x == TGX_CIRCLE || head.x == TGX_FIGURE8) && TGX_ORBIT_RECORDS(head.y) > q;
     }
     return false;
 }
@@ -79,14 +108,24 @@ struct Emitter {
     int tile_seg_begin = 0;
     Seg cur;              // the open segment, kept in registers until closed
 
+    int ph_blocks = 1;         // tgx_phases rows this trajectory owns (its own and its continuation records')
+    // entry nph goes to slot nph % 18 of row nph / 18 (tgx.h: TGX_VGOALS_MORE)
     __device__ void phase(int key, int kind, double value, double value2) {
-        if (ph && nph < TGX_MAX_PHASES) {
-            ph->key[nph] = key;
-            ph->kind[nph] = kind;
-            ph->value[nph] = value;
-            ph->value2[nph] = value2;
+        const int b = nph / TGX_MAX_PHASES, q = nph - b * TGX_MAX_PHASES;
+        if (ph && b < ph_blocks) {
+            ph[b].key[q] = key;
+            ph[b].kind[q] = kind;
+            ph[b].value[q] = value;
+            ph[b].value2[q] = value2;
         }
         ++nph;
+    }
+    __device__ void set_phase_counts(int total) {
+        if (!ph) return;
+        for (int b = 0; b < ph_blocks; ++b) {
+            const int left = total - b * TGX_MAX_PHASES;
+            ph[b].n = left < 0 ? 0 : (left < TGX_MAX_PHASES ? left : TGX_MAX_PHASES);
+        }
     }
     // The tile cur_tile is served by the segments tile_seg_begin .. seg_end - 1.
     __device__ void flush_tile(int seg_end) {
@@ -158,7 +197,7 @@ struct Emitter {
     __device__ void finish() {
         flush_tile(nseg);
         cur_tile = -1;
-        if (ph) ph->n = nph < TGX_MAX_PHASES ? nph : TGX_MAX_PHASES;
+        set_phase_counts(nph);
     }
 };
 
@@ -385,7 +424,7 @@ __device__ __forceinline__ double div_inv(double a, const InvDiv& d) {
 // Circle::generateTraj (Circle.cpp:30-94) == Figure8::generateTraj (Figure8.cpp:30-94).
 // STATE = false skips the theta recurrence (counts and status do not depend on it); XR selects exact ramps.
 template <bool STATE, bool XR>
-__device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E, uint32_t& st,
+__device__ int replay_orbit(const tgx_params& p, const Src& src, int64_t max_samples, Emitter& E, uint32_t& st,
                             const CurTable* __restrict__ tab) {
     const tgx_orbit_params& o = p.u.orbit;
     const double r = o.r, dt = p.dt;
@@ -399,7 +438,7 @@ __device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E
         if (STATE) th = dadd(th, dmul(div_inv(vnew, rdiv), dt));
     };
     for (int g = 0; g < p.n_vgoals; ++g) {                   // :43
-        const double vg = o.v_goals[g];
+        const double vg = orbit_goal(p, src, g);
         E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                // :45
         E.goal = g;
         if (!ramp<true, XR, STATE, false>(v, vg, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, dtr, 0.0,
@@ -427,6 +466,12 @@ __device__ int replay_orbit(const tgx_params& p, int64_t max_samples, Emitter& E
     }
     if (fabs(v) > 0.001) st |= TGX_ST_FINAL_V_NONZERO;       // :85-88
     E.phase(k, TGX_PH_STOPPED, 0.0, 0.0);                    // :89
+    if (k == 0) {
+        // no step at all (an empty v_goals vector): the trajectory is the start sample alone (:41), which needs a
+        // segment of its own
+        E.open(0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0);
+        E.close(0, false, 0.0);
+    }
     return k + 1;
 }
 
@@ -536,20 +581,29 @@ struct PlanOut {
 // generateTraj plan of one trajectory.  FILL = false: count only; STATE = false: skip the theta replay (then the
 // segment count is not meaningful: exact-progression breaks depend on theta).
 template <bool FILL, bool STATE, bool XR>
-__device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_limits* lim, Emitter& E,
+__device__ PlanOut plan_one(const tgx_params& p, const Src& src, int64_t max_samples, const tgx_limits* lim, Emitter& E,
                             TrajRec* rec, const CurTable* __restrict__ tab) {
     PlanOut r{0, 0u, 0, 0};
+    if (is_orbit(p.type) && p.n_vgoals > TGX_MAX_VGOALS && p.n_vgoals <= TGX_MAX_VGOALS_TOTAL)
+        E.ph_blocks = (int)min((int64_t)TGX_ORBIT_RECORDS(p.n_vgoals), src.n - src.i);
     if (TGX_IS_POLYLINE(p.type)) {
         r.status = TGX_ST_WRONG_PLANNER;   // planned by tgx_plan_polyline (polyline.cu)
-    } else if (!params_ok(p)) {
+    } else if (p.type == TGX_VGOALS_MORE) {
+        // a continuation record: no trajectory of its own; its tgx_phases row belongs to the record it continues
+        if (continuation_has_owner(src)) E.ph = nullptr;
+        else r.status = TGX_ST_BAD_PARAM;
+    } else if (!params_ok(p, src)) {
         r.status = TGX_ST_BAD_PARAM;
+        // trajectoryInsideBounds tests the geometry alone (Circle.cpp:171-179): report it for rejected records too
+        if (lim && lim->check_box && (is_orbit(p.type) || is_line_like(p.type)) && !inside_bounds(p, lim->box))
+            r.status |= TGX_ST_OUTSIDE_BOUNDS;
     } else {
         int n;
         double theta = 0.0, c = 1.0, s = 0.0;
         if (is_line_like(p.type))
             n = replay_line<XR>(p, max_samples, E, r.status, theta, c, s, tab, p.type == TGX_BOOMERANG);
         else
-            n = replay_orbit<STATE, XR>(p, max_samples, E, r.status, tab);
+            n = replay_orbit<STATE, XR>(p, src, max_samples, E, r.status, tab);
         E.finish();
         // the evaluation kernel stages at most kMaxSegPerTile segments per tile: a trajectory that would need more
         // (dozens of speed goals inside one tile) is rejected rather than evaluated from a truncated list
@@ -590,14 +644,14 @@ __device__ PlanOut plan_one(const tgx_params& p, int64_t max_samples, const tgx_
         for (int i = 0; i < 7; ++i) t.f[i] = 0.0;
         *rec = t;
     }
-    if (FILL && E.ph && r.n == 0) E.ph->n = 0;
+    if (FILL && r.n == 0) E.set_phase_counts(0);
     return r;
 }
 
 // generateStopTraj plan of one trajectory (Circle.cpp:132-169, Line.cpp:117-152, Figure8.cpp:130-167).
 // Samples of a braking plan are numbered from 0 = first braking step, so the segment base is sample -1.
 template <bool FILL>
-__device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max_samples, Emitter& E,
+__device__ PlanOut stop_one(const tgx_params& p, const Src& src, const double* from, int64_t max_samples, Emitter& E,
                             TrajRec* rec) {
     PlanOut r{0, 0u, 0, 0};
     TrajRec t;
@@ -668,7 +722,9 @@ __device__ PlanOut stop_one(const tgx_params& p, const double* from, int64_t max
         if (FILL && rec) *rec = t;
         return r;
     }
-    if (!params_ok(p)) {
+    if (p.type == TGX_VGOALS_MORE && continuation_has_owner(src)) {
+        E.ph = nullptr;                    // a continuation record: nothing to brake
+    } else if (!params_ok(p, src)) {
         r.status = TGX_ST_BAD_PARAM;
     } else {
         const int tmask = (1 << E.tile_shift) - 1;
@@ -819,15 +875,16 @@ plan_count_kernel(const tgx_params* __restrict__ params, const double* __restric
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const tgx_params p = load_params(params, i);
+    const Src src{params, i, n};
     Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, nullptr, is_orbit(p.type), 0x7fffffff, 0x7fffffff};
     PlanOut r;
     if (stop_from) {
         double from[TGX_NCHAN];
 #pragma unroll
         for (int c = 0; c < TGX_NCHAN; ++c) from[c] = stop_from[i * TGX_NCHAN + c];
-        r = stop_one<false>(p, from, max_samples, E, nullptr);
+        r = stop_one<false>(p, src, from, max_samples, E, nullptr);
     } else {
-        r = plan_one<false, SEGS, XR>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
+        r = plan_one<false, SEGS, XR>(p, src, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
     }
     if (counts) counts[i] = r.n;
     if (status) status[i] = r.status;
@@ -859,6 +916,7 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
     // trajectory owns is indexed by i, so the tables do not depend on the order
     const int64_t i = order ? (int64_t)__ldg(order + t) : t;
     const tgx_params p = load_params(params, i);
+    const Src src{params, i, n};
     const bool slab = seg_slab > 0;
     // exact-offset mode: a trajectory the counting pass rejected owns no slice: replay it without writing tables
     const bool keep = slab || plan_counts[i] > 0;
@@ -874,10 +932,10 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
         double from[TGX_NCHAN];
 #pragma unroll
         for (int c = 0; c < TGX_NCHAN; ++c) from[c] = stop_from[i * TGX_NCHAN + c];
-        r = stop_one<true>(p, from, max_samples, E, rec_out);
-        if (phases && r.status) phases[i].n = 0;
+        r = stop_one<true>(p, src, from, max_samples, E, rec_out);
+        if (E.ph && r.status) E.ph->n = 0;
     } else {
-        r = plan_one<true, true, XR>(p, max_samples, has_lim ? &lim : nullptr, E, rec_out, tab);
+        r = plan_one<true, true, XR>(p, src, max_samples, has_lim ? &lim : nullptr, E, rec_out, tab);
     }
     bool overflow = false;
     if (slab) {
@@ -928,7 +986,7 @@ plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits l
     PlanOut r{0, 0u, 0, 0};
     bool overflow = !orbit;
     if (orbit) {
-        r = plan_one<false, true, false>(p, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
+        r = plan_one<false, true, false>(p, Src{params, i, n}, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
         overflow = !phase_fits(p, r.n, E, max_n);
         if (r.n > 0 && !overflow) rec.n = E.nseg;
     }
@@ -976,7 +1034,7 @@ plan_samples_kernel(const tgx_params* __restrict__ params, const double* __restr
     g.vb = v; g.dv = 0.0; g.vclamp = v;
     t.n = 1;
     for (int q = 0; q < 7; ++q) t.f[q] = 0.0;
-    const bool ok = TGX_IS_POLYLINE(p.type) ? poly_params_ok(p) : params_ok(p);
+    const bool ok = TGX_IS_POLYLINE(p.type) ? poly_params_ok(p) : params_ok(p, Src{params, i, n}, false);
     if (TGX_IS_POLYLINE(p.type)) {
         // createSquareGoal(x, y, v, accel, heading) and its copies (Square.cpp:94-110); createBounceGoal(x, y, z, vz,
         // heading) (Bounce.cpp:54-72).  state = {v | vz, accel, x, y}; z = g[5] (Bounce), heading = g[6].

@@ -141,14 +141,18 @@ Staging& staging() {
     return s;
 }
 
-tgx_params orbitParams(int type, double alt, double r, double cx, double cy, const std::vector<double>& v_goals,
-                       double t_traj, double accel, double dt) {
-    if (v_goals.size() > TGX_MAX_VGOALS)
-        throw std::invalid_argument("tgx: at most " + std::to_string(TGX_MAX_VGOALS) + " v_goals are supported");
-    tgx_params p;
-    std::memset(&p, 0, sizeof(p));
+// The reference takes a std::vector of any length (Circle.cpp:43): goal speeds beyond the eighth go into continuation
+// records (tgx.h: TGX_VGOALS_MORE).  More than TGX_MAX_VGOALS_TOTAL of them is reported by the engine as
+// TGX_ST_BAD_PARAM when the trajectory is generated (RCLCPP_ERROR + exit(1), like the reference's own fatal paths).
+std::vector<tgx_params> orbitParams(int type, double alt, double r, double cx, double cy,
+                                    const std::vector<double>& v_goals, double t_traj, double accel, double dt) {
+    const size_t k = v_goals.size();
+    const size_t rows = k <= TGX_MAX_VGOALS_TOTAL ? (size_t)TGX_ORBIT_RECORDS((int)k) : 1;
+    std::vector<tgx_params> recs(rows);
+    std::memset(recs.data(), 0, rows * sizeof(tgx_params));
+    tgx_params& p = recs[0];
     p.type = type;
-    p.n_vgoals = (int32_t)v_goals.size();
+    p.n_vgoals = (int32_t)std::min<size_t>(k, 0x7fffffff);
     p.dt = dt;
     p.alt = alt;
     p.u.orbit.r = r;
@@ -156,8 +160,18 @@ tgx_params orbitParams(int type, double alt, double r, double cx, double cy, con
     p.u.orbit.cy = cy;
     p.u.orbit.t_traj = t_traj;
     p.u.orbit.accel = accel;
-    for (size_t i = 0; i < v_goals.size(); ++i) p.u.orbit.v_goals[i] = v_goals[i];
-    return p;
+    for (size_t q = 0; q < rows; ++q) {
+        tgx_params& rec = recs[q];
+        if (q) {
+            rec.type = TGX_VGOALS_MORE;
+            rec.dt = dt;
+            rec.alt = alt;
+        }
+        int cnt = 0;
+        for (size_t g = q * TGX_MAX_VGOALS; g < k && g < (q + 1) * TGX_MAX_VGOALS; ++g) rec.u.orbit.v_goals[cnt++] = v_goals[g];
+        if (q) rec.n_vgoals = cnt;
+    }
+    return recs;
 }
 
 }  // namespace
@@ -178,7 +192,11 @@ tgx_engine* sharedEngine() {
 }
 
 GpuTrajectory::GpuTrajectory(const tgx_params& params, const char* shape, const char* logger_name)
-    : ::trajectory_generator::Trajectory(params.dt), params_(params), shape_(shape),
+    : ::trajectory_generator::Trajectory(params.dt), params_(params), records_(1, params), shape_(shape),
+      logger_(rclcpp::get_logger(logger_name)) {}
+
+GpuTrajectory::GpuTrajectory(const std::vector<tgx_params>& records, const char* shape, const char* logger_name)
+    : ::trajectory_generator::Trajectory(records.at(0).dt), params_(records.at(0)), records_(records), shape_(shape),
       logger_(rclcpp::get_logger(logger_name)) {}
 
 GpuTrajectory::~GpuTrajectory() {}
@@ -189,10 +207,15 @@ void GpuTrajectory::generateTraj(std::vector<Goal>& goals, std::unordered_map<in
     tgx_engine* e = sharedEngine();
 
     // pass 1: the exact sample count (replays the reference's loops on the GPU)
-    int32_t n = 0;
-    uint32_t status = 0;
-    int rc = tgx_count_host(e, &params_, 1, nullptr, &n, &status);
+    // (a Circle / Figure8 with more than 8 goal speeds is R > 1 records: the trajectory is row 0, the continuation rows
+    //  carry no samples, only further index_msgs entries)
+    const int64_t R = (int64_t)records_.size();
+    std::vector<int32_t> counts((size_t)R, 0);
+    std::vector<uint32_t> stats((size_t)R, 0u);
+    int rc = tgx_count_host(e, records_.data(), R, nullptr, counts.data(), stats.data());
     if (rc != TGX_OK) die(logger_, "tgx_count_host", rc);
+    int32_t n = counts[0];
+    uint32_t status = stats[0];
     last_status_ = status;
     if (status & (TGX_ST_BAD_PARAM | TGX_ST_TOO_LONG)) {
         RCLCPP_ERROR(logger_, "Error: %s trajectory parameters rejected (status 0x%x)", shape_.c_str(), status);
@@ -201,17 +224,22 @@ void GpuTrajectory::generateTraj(std::vector<Goal>& goals, std::unordered_map<in
 
     // pass 2: all samples into a page-locked SoA row, then repack to the reference's AoS messages
     const int64_t cap = std::max<int64_t>(4, ((int64_t)n + 3) / 4 * 4);
-    double* row = staging().reserve((int64_t)TGX_NCHAN * cap);
+    double* row = staging().reserve(R * (int64_t)TGX_NCHAN * cap);
     if (!row) die(logger_, "tgx_alloc_host", TGX_ERR_NOMEM);
-    tgx_phases phases;
-    tgx_polyline_legs legs;
+    std::vector<tgx_phases> phase_rows((size_t)R);
+    std::vector<tgx_polyline_legs> leg_rows((size_t)R);
     // Bounce moves along z (Bounce.cpp:39-41) and ships all 14 planes; every other class uses the compact format
     const bool compact = params_.type != TGX_BOUNCE;
     if (compact)
-        rc = tgx_generate_host_compact(e, &params_, 1, nullptr, row, cap, &n, &status, &phases, &legs);
+        rc = tgx_generate_host_compact(e, records_.data(), R, nullptr, row, cap, counts.data(), stats.data(),
+                                       phase_rows.data(), leg_rows.data());
     else
-        rc = tgx_generate_host_legs(e, &params_, 1, nullptr, row, cap, &n, &status, &phases, &legs);
+        rc = tgx_generate_host_legs(e, records_.data(), R, nullptr, row, cap, counts.data(), stats.data(),
+                                    phase_rows.data(), leg_rows.data());
     if (rc != TGX_OK) die(logger_, "tgx_generate_host", rc);
+    n = counts[0];
+    status = stats[0];
+    const tgx_polyline_legs& legs = leg_rows[0];
     last_status_ = status;
 
     const size_t base = goals.size();            // generateTraj APPENDS (Circle.cpp:41: push_back, keys size()-1)
@@ -223,9 +251,10 @@ void GpuTrajectory::generateTraj(std::vector<Goal>& goals, std::unordered_map<in
     if (TGX_IS_POLYLINE(params_.type)) {
         polylineMessages(shape_, params_.type, legs, (int)base, index_msgs);
     } else {
-        for (int i = 0; i < phases.n; ++i)
-            index_msgs[(int)base + phases.key[i]] =
-                phaseText(shape_, params_.type, phases.kind[i], phases.value[i], phases.value2[i], false);
+        for (const tgx_phases& phases : phase_rows)
+            for (int i = 0; i < phases.n; ++i)
+                index_msgs[(int)base + phases.key[i]] =
+                    phaseText(shape_, params_.type, phases.kind[i], phases.value[i], phases.value2[i], false);
     }
 
     if (status & TGX_ST_VGOALS_NOT_INCREASING)   // Circle.cpp:57-59, Figure8.cpp:57-59
@@ -251,17 +280,24 @@ void GpuTrajectory::generateStopTraj(std::vector<Goal>& goals, std::unordered_ma
     goalToArray(goals[pub_index], from);         // the setpoint being braked from (Circle.cpp:140-143)
 
     // a braking ramp never has more samples than v / (a*dt) + 2; size the row from a count-only call
-    int32_t n = 0;
-    uint32_t status = 0;
+    const int64_t R = (int64_t)records_.size();        // continuation records brake nothing (rows 1.. stay empty)
+    std::vector<int32_t> counts((size_t)R, 0);
+    std::vector<uint32_t> stats((size_t)R, 0u);
+    std::vector<double> from_rows((size_t)(R * TGX_NCHAN), 0.0);
+    std::copy(from, from + TGX_NCHAN, from_rows.begin());
     double dummy[4 * TGX_NCHAN];
-    int rc = tgx_stop_host(e, &params_, 1, from, dummy, 0, &n, &status, nullptr);
+    int rc = tgx_stop_host(e, records_.data(), R, from_rows.data(), dummy, 0, counts.data(), stats.data(), nullptr);
     if (rc != TGX_OK) die(logger_, "tgx_stop_host", rc);
+    int32_t n = counts[0];
     const int64_t cap = ((int64_t)n + 3) / 4 * 4;
-    double* row = staging().reserve((int64_t)TGX_NCHAN * (cap > 0 ? cap : 4));
+    double* row = staging().reserve(R * (int64_t)TGX_NCHAN * (cap > 0 ? cap : 4));
     if (!row) die(logger_, "tgx_alloc_host", TGX_ERR_NOMEM);
-    tgx_phases phases;
-    rc = tgx_stop_host(e, &params_, 1, from, row, cap, &n, &status, &phases);
+    std::vector<tgx_phases> phase_rows((size_t)R);
+    rc = tgx_stop_host(e, records_.data(), R, from_rows.data(), row, cap, counts.data(), stats.data(), phase_rows.data());
     if (rc != TGX_OK) die(logger_, "tgx_stop_host", rc);
+    n = counts[0];
+    const uint32_t status = stats[0];
+    const tgx_phases& phases = phase_rows[0];
     last_status_ = status & ~(uint32_t)TGX_ST_TRUNCATED;
 
     std::vector<Goal> goals_tmp;
@@ -286,13 +322,17 @@ bool GpuTrajectory::trajectoryInsideBounds(double xmin, double xmax, double ymin
     std::memset(&lim, 0, sizeof(lim));
     lim.box[0] = xmin; lim.box[1] = xmax; lim.box[2] = ymin; lim.box[3] = ymax; lim.box[4] = zmin; lim.box[5] = zmax;
     lim.check_box = 1;
-    int32_t n = 0;
-    uint32_t status = 0;
-    const int rc = tgx_count_host(sharedEngine(), &params_, 1, &lim, &n, &status);
+    const int64_t R = (int64_t)records_.size();
+    std::vector<int32_t> counts((size_t)R, 0);
+    std::vector<uint32_t> stats((size_t)R, 0u);
+    const int rc = tgx_count_host(sharedEngine(), records_.data(), R, &lim, counts.data(), stats.data());
     if (rc != TGX_OK) die(logger_, "tgx_count_host", rc);
+    const uint32_t status = stats[0];
     if (status & TGX_ST_LINE_D2_NEGATIVE)        // Line.cpp:165-168
         RCLCPP_ERROR(logger_, "Line trajectory not feasible. Please increase accel, decrease v, or increase line length.");
-    return (status & (TGX_ST_OUTSIDE_BOUNDS | TGX_ST_BAD_PARAM)) == 0;
+    // the reference tests the geometry alone (Circle.cpp:171-179): parameters its samplers would choke on do not make
+    // the box test fail, and the engine reports the box test for rejected records too
+    return (status & TGX_ST_OUTSIDE_BOUNDS) == 0;
 }
 
 Goal GpuTrajectory::sampleGoal(double v, double accel, double s0, double s1) const {

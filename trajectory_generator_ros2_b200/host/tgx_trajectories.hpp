@@ -28,7 +28,8 @@
 
 namespace TGX_DROPIN_NAMESPACE {
 
-// Common implementation of the three overrides; one tgx_params record per object.
+// Common implementation of the three overrides; one tgx_params record per object (plus continuation records for
+// a Circle / Figure8 with more than 8 goal speeds).
 class GpuTrajectory : public ::trajectory_generator::Trajectory {
 public:
     ~GpuTrajectory() override;
@@ -51,6 +52,9 @@ public:
 
 protected:
     GpuTrajectory(const tgx_params& params, const char* shape, const char* logger_name);
+    // Circle / Figure8 with more than 8 goal speeds: `records` = the record and its continuation records (tgx.h:
+    // TGX_VGOALS_MORE), exactly as they are handed to the engine
+    GpuTrajectory(const std::vector<tgx_params>& records, const char* shape, const char* logger_name);
 
     // create<Shape>Goal(v, accel, theta): one setpoint from an explicit state, evaluated on the GPU.
     snapstack_msgs2::msg::Goal sampleGoal(double v, double accel, double s0, double s1) const;
@@ -59,6 +63,7 @@ protected:
                                             double z) const;
 
     tgx_params params_;
+    std::vector<tgx_params> records_;   // params_ followed by its continuation records (one entry for most classes)
     std::string shape_;       // "Circle", "Line", "Figure8": prefix of the index_msgs texts
     rclcpp::Logger logger_;
     uint32_t last_status_ = 0;
