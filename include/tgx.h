@@ -457,7 +457,10 @@ int tgx_generate_feasibility(tgx_engine* e, const tgx_params* d_params, int64_t 
  * kernels stages 64 consecutive records in shared memory (128-byte TMA swizzle) and sends them as two 4 KiB TMA boxes of
  * a [records][16 doubles] tensor map over d_records, so a sample costs 128 bytes of HBM traffic instead of the
  * 112 + 112 + 128 of tgx_eval followed by tgx_pack_goals.  Bit-identical to that pair.  d_records must be 16-byte
- * aligned and hold fewer than 2^31 records. */
+ * aligned and hold fewer than 2^31 records.  The call must know where the buffer ends: without offsets it holds
+ * n * rec_stride records; WITH d_rec_offset, rec_stride is the total number of records d_records holds (> 0).  That
+ * count is the extent of the tensor map, and a trajectory whose offset lies outside [0, total) writes nothing, one whose
+ * row runs past the end is cut there. */
 int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d_records, int64_t rec_stride,
                      const int64_t* d_rec_offset, int64_t rec_capacity, void* stream);
 

@@ -383,6 +383,29 @@ def test_eval_records_equals_eval_then_pack(engine, oracle, tuning):
             engine.eval_records(n, cap, lim, records=flat_g, rec_offset=offs)
             torch.cuda.synchronize()
             assert torch.equal(flat_g, flat_w), (name, tuning, "packed")
+            # offsets that point outside the buffer (negative, beyond the end, 2^32 + a valid row: the TMA row coordinate
+            # is 32 bits and must not wrap into the buffer) write nothing; a row that runs past the end is cut there
+            total = int(c.sum())
+            guard = 4096
+            big = torch.full((total + guard, 128), 0xab, dtype=torch.uint8, device=d.device)
+            bad = offs.clone()
+            bad[1] = -5
+            bad[2] = total + 7
+            bad[3] = (1 << 32) + int(offs[3])
+            bad[4] = total - 10                                   # the last 10 records of the buffer, then the end
+            bad[n - 1] = -1                                       # (so that nothing else writes those 10 records)
+            big[:total] = 0
+            engine.eval_records(n, cap, lim, records=big[:total], rec_offset=bad)
+            torch.cuda.synchronize()
+            assert bool((big[total:] == 0xab).all()), (name, tuning, "wrote past the end of the record buffer")
+            # every other trajectory wrote its usual rows, the five displaced ones left theirs untouched
+            keep = torch.ones(total, dtype=torch.bool, device=d.device)
+            for i in (1, 2, 3, 4, n - 1):
+                keep[int(offs[i]):int(offs[i]) + int(c[i])] = False
+                assert bool((big[int(offs[i]):min(int(offs[i]) + int(c[i]), total - 10)] == 0).all()), (name, tuning, i)
+            assert torch.equal(big[:total][keep], flat_w[keep]), (name, tuning, "bad offsets disturbed other rows")
+            assert int(c[4]) > 10 and int(c[n - 1]) > 10
+            assert torch.equal(big[total - 10:total], flat_w[int(offs[4]):int(offs[4]) + 10]), (name, tuning, "cut row")
         # braking plans (segment tables incl. the frozen-position records of the polyline family)
         params = abi.concat([workloads.mixed_cfg3(40, seed=12), batches["polyline"][0][:40]])
         froms = np.zeros((len(params), abi.TGX_NCHAN))

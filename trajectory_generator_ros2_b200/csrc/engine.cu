@@ -1295,14 +1295,15 @@ int tgx_generate_profile(tgx_engine* e, double* eval_ms, int64_t* eval_launches)
 
 // The record buffer as TMA sees it: a 2-D fp64 tensor [records][16], one 128-byte row per record, written in boxes of
 // 32 records with the 128-byte shared-memory swizzle (RecTma in store.cuh stages in exactly that layout).  The outer
-// extent is the coordinate range, not the allocation: the kernel only issues boxes that lie inside a trajectory's row.
-static int make_record_tmap(CUtensorMap* tmap, tgx_goal_record* d_records) {
+// extent is the number of records the buffer holds: TMA clips whatever a box would write beyond it, and the kernels never
+// form a row coordinate outside [0, total).
+static int make_record_tmap(CUtensorMap* tmap, tgx_goal_record* d_records, int64_t total) {
     tmap_encode_fn encode = tmap_encoder();
     if (!encode) {
         g_last_cuda_error = "cuTensorMapEncodeTiled is not available from this driver (tgx_eval_records needs TMA)";
         return TGX_ERR_CUDA;
     }
-    const cuuint64_t dims[2] = {16, (cuuint64_t)1 << 31};
+    const cuuint64_t dims[2] = {16, (cuuint64_t)total};
     const cuuint64_t strides[1] = {sizeof(tgx_goal_record)};
     const cuuint32_t box[2] = {16, 32};
     const cuuint32_t estr[2] = {1, 1};
@@ -1323,9 +1324,13 @@ int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d
     if ((reinterpret_cast<uintptr_t>(d_records) & 15u) != 0) return TGX_ERR_ALIGNMENT;
     TGX_CUDA(cudaSetDevice(e->device));
     if (e->plan_n == 0 || e->plan_tiles == 0 || rec_capacity == 0) return TGX_OK;
-    // TMA addresses records by a 32-bit row coordinate (2^31 records = 275 GB, more than one GPU holds)
-    if (!d_rec_offset && (rec_stride < 0 || e->plan_n * rec_stride > 0x7fffffffLL)) return TGX_ERR_CAPACITY;
+    // TMA addresses records by a 32-bit row coordinate (2^31 records = 275 GB, more than one GPU holds).  The buffer's
+    // extent: n * rec_stride records, or — with per-trajectory offsets — rec_stride records in all
+    if (rec_stride <= 0) return TGX_ERR_INVALID;
+    const int64_t total = d_rec_offset ? rec_stride : e->plan_n * rec_stride;
+    if (total > 0x7fffffffLL || (!d_rec_offset && rec_stride > 0x7fffffffLL)) return TGX_ERR_CAPACITY;
     tgx::RecOut ro{};
+    ro.total = total;
     ro.base = d_records;
     ro.stride = rec_stride;
     ro.offset = d_rec_offset;
@@ -1334,7 +1339,7 @@ int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d
     if (ro.clamp)
         for (int i = 0; i < 6; ++i) ro.box[i] = limits->box[i];
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int rc = make_record_tmap(&ro.tmap, d_records);
+    const int rc = make_record_tmap(&ro.tmap, d_records, total);
     if (rc) return rc;
     if (e->plan_poly)
         TGX_CUDA(tgx::launch_eval_poly_records(poly_view(e), e->plan_tiles, e->tile_shift, e->spt, ro, s));

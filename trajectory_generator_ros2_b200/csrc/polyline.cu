@@ -450,7 +450,15 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
 
     int limit = n;
     if (STORE && out.capacity < (int64_t)limit) limit = (int)out.capacity;
-    if (RECORDS && ro.capacity < (int64_t)limit) limit = (int)ro.capacity;
+    // a trajectory's records start at its offset and end where its row capacity, or the record buffer, ends: offsets that
+    // point outside the buffer write nothing (the TMA row coordinate is 32 bits: it must never wrap into the buffer)
+    int64_t rec_off = 0;
+    if (RECORDS) {
+        if (ro.capacity < (int64_t)limit) limit = (int)ro.capacity;
+        rec_off = ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride;
+        if (rec_off < 0 || rec_off >= ro.total) limit = 0;
+        else if (rec_off + (int64_t)limit > ro.total) limit = (int)(ro.total - rec_off);
+    }
     double best_v2 = 0.0;
 
     RecTma<SPT> stager;
@@ -525,11 +533,7 @@ eval_poly_kernel(PolyView pv, OutView out, double* __restrict__ max_v, double* _
         }
         const uint32_t mask = out.channel_mask;
         const int64_t cs = out.chan_stride;
-        int64_t rec_off = 0;
-        if (RECORDS) {
-            rec_off = ro.offset ? __ldg(ro.offset + traj) : (int64_t)traj * ro.stride;
-            stager.begin_pass();
-        }
+        if (RECORDS) stager.begin_pass();
 #define TGX_STORE(CH, ARR)                                                                                \
     do {                                                                                                  \
         if (RECORDS) {                                                                                    \

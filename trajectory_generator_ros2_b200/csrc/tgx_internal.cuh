@@ -213,6 +213,7 @@ struct RecOut {
     int64_t stride;            // records per trajectory (ignored when offset != nullptr)
     const int64_t* offset;     // optional per-trajectory record offsets
     int64_t capacity;          // records that fit per trajectory
+    int64_t total;             // records the buffer holds (= the tensor map's outer extent): nothing is written beyond
     double box[6];
     int clamp;                 // saturate p to box (TrajectoryGenerator.cpp:602-604)
 };

@@ -511,7 +511,9 @@ class Engine:
         import torch
         if records is None:
             records = torch.zeros((n, rec_capacity, 128), dtype=torch.uint8, device=self._torch_device())
-        self._check(self._lib.tgx_eval_records(self._h, _limits_ptr(limits), records.data_ptr(), rec_capacity,
+        # with offsets the call takes the buffer's total record count in place of the per-trajectory stride
+        stride = rec_capacity if rec_offset is None else int(records.numel() // 128)
+        self._check(self._lib.tgx_eval_records(self._h, _limits_ptr(limits), records.data_ptr(), stride,
                                                rec_offset.data_ptr() if rec_offset is not None else None,
                                                rec_capacity, self._stream()), "tgx_eval_records")
         return records
