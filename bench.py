@@ -189,12 +189,13 @@ def run_reference_arm(args):
 
 
 # ---- extra legs of the default run: BASELINE.json configs[0], [2], [3], [4] -------------------------------------------
-# FP64 work of one circle sample on the reduction-only path, counted from csrc/eval.cu like the 112 algorithmic bytes
-# of the store path: seg_pos 4 (j(j+1)/2 and v = vb + j dv) + angle 3 + sincos_orbit 21 (1 scale-and-
-# round fma, 1 subtraction, 3 Cody-Waite fma, z = r*r, 5 + 5 polynomial fma, r*z, 2 + 2 final fma / mul) + omega 1 +
-# v^2/r 1 + v.x, v.y, a.x, a.y 4 + |v|^2, |a|^2 4 + two running-maximum compares 2 = 40 FP64-pipe instructions
-# (the quadrant selects, index arithmetic and segment bookkeeping are integer / move work on top of it).
-FP64_INSTR_PER_SAMPLE = 40
+# FP64 work of one circle sample on the reduction-only path (csrc/eval.cu: reduce_kernel), counted from the source like
+# the 112 algorithmic bytes of the store path: speed 1 (v = vb + j dv) + j(j+1)/2 2 + angle 2 +
+# sincos_orbit 21 (1 scale-and-round fma, 1 subtraction, 3 Cody-Waite fma, z = r*r, 5 + 5 polynomial fma, r*z, 2 + 2
+# final fma / mul) + omega 1 + v^2/r 1 + v.x, v.y, a.x, a.y 4 + |v|^2, |a|^2 4 + two running-maximum compares 2 = 38
+# FP64-pipe instructions (ncu, thread level: 38.3 per sample; the quadrant selects, index arithmetic and segment
+# bookkeeping are ~35 integer / move instructions on top of it).
+FP64_INSTR_PER_SAMPLE = 38
 
 
 class Ctx:
@@ -209,10 +210,10 @@ def fp64_roofline(ctx, samples: int, eval_ms: float):
     inst_per_s = FP64_INSTR_PER_SAMPLE * samples / (eval_ms * 1e-3)
     return {"bound": "fp64", "achieved": 2e-12 * inst_per_s, "peak": 2e-12 * dfma_per_s, "unit": "TFLOP/s",
             "frac": inst_per_s / dfma_per_s, "traffic": None,
-            "kernel": "tgx::eval_kernel<64, 4, STORE=false, REDUCE=true, ..., PASSES=4>",
+            "kernel": "tgx::reduce_kernel<MODE, 1024>",
             "fp64_instr_per_sample": FP64_INSTR_PER_SAMPLE,
             "convention": "every FP64-pipe instruction (DFMA / DMUL / DADD / DSETP) counted as one DFMA slot = 2 FLOP; "
-                          "achieved = 40 instr/sample x samples / kernel time (CUDA events), peak = DFMA micro-benchmark "
+                          "achieved = %d instr/sample x samples / kernel time (CUDA events), peak = DFMA micro-benchmark " % FP64_INSTR_PER_SAMPLE +
                           "of this run (tgx_probe_dfma: 8 independent chains per thread, 1024 threads per SM, "
                           "%.1f ms per launch, best of 3)" % probe_ms,
             "peak_source": "measured in this run (no FP64 figure in MEASURED_PEAKS.json)"}

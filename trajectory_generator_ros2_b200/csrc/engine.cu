@@ -346,8 +346,9 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         // fixed slices cost n * seg_slab segment records: up to 8 GB always, beyond that (10^7 .. 10^8-trajectory
         // feasibility sweeps) only while they fit half of the memory that is free right now
         const int64_t slab_bytes = n * (int64_t)seg_slab * (int64_t)sizeof(tgx::Seg);
-        int64_t budget = (int64_t)8 << 30;
+        int64_t budget = std::max<int64_t>((int64_t)8 << 30, (int64_t)e->segs.bytes);   // what is held already is affordable
         if (slab_bytes > budget) {
+            // (asked only when the table would have to grow: cudaMemGetInfo costs milliseconds on a busy context)
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
                 budget = std::max<int64_t>(budget, (int64_t)((free_b + e->segs.bytes) / 2));

@@ -29,6 +29,9 @@
 #include "tgx_internal.cuh"
 #include "store.cuh"
 
+#ifndef TGX_REDUCE_LEGACY
+#define TGX_REDUCE_LEGACY 0
+#endif
 #ifndef TGX_REDUCE_CTAS
 #define TGX_REDUCE_CTAS 4      // the reduction-only instantiation is compiled for 4 * 256 threads per SM (64 registers; 5: 48 registers, spills in the slab / phase modes, 5.72 vs 5.77 ms)
 #endif
@@ -621,6 +624,252 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     }
 }
 
+// ---- reduction-only evaluation (tgx_feasibility; BASELINE.json configs 4-5) ----------------------------------------------
+// Per-trajectory maxima of |v_k| and |a_k| over the reference's own samples, nothing stored.  The arithmetic of every
+// sample is the store kernels' (same closed forms, same sincos_orbit, same products: tgx_eval's maxima and
+// tgx_feasibility's are the same bits); what differs is everything around it, because this kernel is bound by
+// instruction issue and the FP64 pipe, not by HBM:
+//   * a thread owns a run of CONSECUTIVE samples of the tile (ceil(samples in the tile / 64) of them), so it finds its
+//     segment once, keeps the segment record in registers and only moves on where a segment ends — instead of a
+//     search, a 64-byte shared-memory read and a "last sample of the segment?" select per sample;
+//   * inside a segment the samples run through a branch-free body, four at a time for instruction-level parallelism
+//     (one sample's sincos is a dependent chain of ~15 DFMA); a segment's last sample (clamped speed, replayed angle)
+//     is the only special case and is handled apart;
+//   * |v|^2 and |a|^2 are sums of squares, so the SIGNS the quadrant logic of sin / cos would fix do not matter: only the
+//     swap of the two polynomials for odd quadrants is kept (4 selects instead of 12 per sample).
+// 40 FP64 instructions per circle sample remain, plus ~15 others (was ~90).
+struct RedSample {
+    double v, th;
+};
+
+// sin / cos up to sign (see above): the magnitudes sincos_orbit returns, without its two sign selects.
+__device__ __forceinline__ void sincos_orbit_unsigned(double x, double* sn, double* cs) {
+    const double shifted = fma(x, kTrig[0], kTrig[1]);
+    const int q = __double2loint(shifted);
+    const double kd = shifted - kTrig[1];
+    double r = fma(kd, kTrig[2], x);
+    r = fma(kd, kTrig[3], r);
+    r = fma(kd, kTrig[4], r);
+    const double z = r * r;
+    double ps = fma(z, kTrig[5], kTrig[6]);
+    ps = fma(z, ps, kTrig[7]);
+    ps = fma(z, ps, kTrig[8]);
+    ps = fma(z, ps, kTrig[9]);
+    ps = fma(z, ps, kTrig[10]);
+    const double s = fma(r * z, ps, r);
+    double pc = fma(z, kTrig[11], kTrig[12]);
+    pc = fma(z, pc, kTrig[13]);
+    pc = fma(z, pc, kTrig[14]);
+    pc = fma(z, pc, kTrig[15]);
+    pc = fma(z, pc, kTrig[16]);
+    const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+    *sn = (q & 1) ? c : s;
+    *cs = (q & 1) ? s : c;
+}
+
+// |v|^2 and |a|^2 of one sample with the products of the store kernels' formulas (eval_kernel above).
+template <int TYPE>
+__device__ __forceinline__ void red_norms(const TrajRec& rec, double v, double th, double acc, double& v2, double& a2) {
+    if (TYPE == TGX_LINE) {
+        const double c = rec.f[0], s = rec.f[1];
+        const double vx = v * c, vy = v * s, ax = acc * c, ay = acc * s;
+        v2 = fma(vx, vx, vy * vy);
+        a2 = fma(ax, ax, ay * ay);
+    } else if (TYPE == kRecStatic) {
+        const double dx = rec.f[4], dy = rec.f[5];
+        v2 = v * v;
+        a2 = acc * acc * (dx * dx + dy * dy);
+    } else {
+        double sn, cn;
+        sincos_orbit_unsigned(th, &sn, &cn);
+        const double om = v * rec.f[5];                  // omega = v / r
+        if (TYPE == TGX_CIRCLE) {
+            const double v2r = v * om;
+            const double vx = v * sn, vy = v * cn, ax = v2r * cn, ay = v2r * sn;
+            v2 = fma(vx, vx, vy * vy);
+            a2 = fma(ax, ax, ay * ay);
+        } else {
+            const double r = rec.f[0];
+            const double rw = r * om;
+            const double vx = rw * cn, vy = rw * (cn * cn - sn * sn);
+            const double ax = rw * om * sn, ay = (-4.0 * r) * om * om * (sn * cn);
+            v2 = fma(vx, vx, vy * vy);
+            a2 = fma(ax, ax, ay * ay);
+        }
+    }
+}
+
+// The samples [k, k_end) of one trajectory type, walking the tile's segment list forward from segment si.  Only the
+// segment INDEX lives in a register and moves on (a two-instruction divergent loop) where a sample lies beyond the
+// segment's end; the record's fields are read from shared memory where they are used and everything else is
+// branch-free, so the lanes of a warp stay together through the long FP64 chains whatever segments they are in.
+// (Two earlier shapes were slower than the generic kernel's 50 ms per 10^7 config-4 circles: peeling the segments' last
+// samples into a path of their own, 57 ms — every warp serialised through the one-sample paths of the few lanes that met
+// a segment end; and a register-resident copy of the record, 53 ms — 176 bytes of spills per thread, LSU pipe 40 % busy.)
+#ifndef TGX_RED_U
+#define TGX_RED_U 4            // samples a thread evaluates side by side
+#endif
+template <int TYPE>
+__device__ __forceinline__ void red_run(const TrajRec& rec, const Seg* __restrict__ segs, const int* __restrict__ kends,
+                                        int nseg, int si, int k, int k_end, double& best_v2, double& best_a2) {
+    constexpr bool ORBIT = TYPE == TGX_CIRCLE || TYPE == TGX_FIGURE8;
+    const double dtr = rec.f[4];
+    // speed, angle and the `accel` argument of sample kk (seg_pos, and eval_kernel's speed_and_angle)
+    auto state = [&](int kk, double& v, double& th, double& acc) {
+        while (si + 1 < nseg && kk > kends[si]) ++si;
+        const Seg& sg = segs[si];
+        const SegPos q = seg_pos(sg, kk);
+        v = q.v;
+        th = 0.0;
+        acc = sg.acc;
+        if (ORBIT) th = q.last ? sg.acc : fma(q.tri, sg.dv * dtr, fma(q.fj, sg.s1, sg.s0));
+        if (TYPE == TGX_LINE && q.j == 0) acc = 0.0;     // sample 0 is createLineGoal(A.x, A.y, 0, accel = 0, theta)
+    };
+    constexpr int U = TGX_RED_U;
+    for (; k + U <= k_end; k += U) {
+        double v[U], th[U], acc[U], v2[U], a2[U];
+        while (si + 1 < nseg && k > kends[si]) ++si;
+        const int k_last = (si + 1 < nseg) ? kends[si] : 0x7fffffff;
+        if (k + U - 1 <= k_last) {
+            // the common case: one segment serves the whole group; its record is read once (four 16-byte LDS) and only
+            // the group's last sample can be the segment's last one (clamped speed, replayed angle)
+            const Seg sg = segs[si];
+            const double ddth = sg.dv * dtr;
+            const int j0 = k - sg.kb;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double fj = (double)(j0 + u);
+                v[u] = fma(fj, sg.dv, sg.vb);
+                th[u] = 0.0;
+                // j(j+1)/2 is an exact integer below 2^53 however it is formed: fma(j, j, j)/2 == seg_pos's 0.5*(j*(j+1))
+                if (ORBIT) th[u] = fma(0.5 * fma(fj, fj, fj), ddth, fma(fj, sg.s1, sg.s0));
+                acc[u] = sg.acc;
+            }
+            if (k + U - 1 == k_last) {
+                v[U - 1] = seg_pos(sg, k + U - 1).v;
+                if (ORBIT) th[U - 1] = sg.acc;
+            }
+            if (TYPE == TGX_LINE && j0 == 0) acc[0] = 0.0;
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) state(k + u, v[u], th[u], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) red_norms<TYPE>(rec, v[u], th[u], acc[u], v2[u], a2[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            best_v2 = max_nn(best_v2, v2[u]);
+            best_a2 = max_nn(best_a2, a2[u]);
+        }
+    }
+    for (; k < k_end; ++k) {
+        double v, th, acc, v2, a2;
+        state(k, v, th, acc);
+        red_norms<TYPE>(rec, v, th, acc, v2, a2);
+        best_v2 = max_nn(best_v2, v2);
+        best_a2 = max_nn(best_a2, a2);
+    }
+}
+
+template <int MODE, int TILE>
+__global__ void __launch_bounds__(64, TGX_REDUCE_CTAS * 4)
+reduce_kernel(TableView tv, double* __restrict__ max_v, double* __restrict__ max_a) {
+    constexpr int THREADS = 64;
+    __shared__ __align__(16) TrajRec s_rec;
+    constexpr int NSEG = MODE == 2 ? kPhaseMaxSegs : kMaxSegPerTile;
+    __shared__ __align__(16) Seg s_seg[NSEG];
+    __shared__ int s_kend[NSEG];
+    __shared__ int4 s_tile;
+    __shared__ double s_red[2][THREADS / 32];
+
+    // ---- stage the tile's constants (as eval_kernel does) -----------------------------------------------------------------
+    int traj, k_lo, nseg;
+    if (MODE == 2) {
+        __shared__ __align__(16) PhaseRec s_phr;
+        traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
+        k_lo = ((int)blockIdx.x - traj * tv.tile_slab) * TILE;
+        const int4* pphr = reinterpret_cast<const int4*>(tv.phase + traj);
+        if (threadIdx.x < sizeof(PhaseRec) / 16) reinterpret_cast<int4*>(&s_phr)[threadIdx.x] = __ldg(pphr + threadIdx.x);
+        __syncthreads();
+        nseg = s_phr.n;
+        if (nseg <= 0) return;
+        const int n_total = s_phr.key[nseg - 1] + 1;
+        if (k_lo >= n_total) return;
+        if ((int)threadIdx.x < nseg) {
+            Seg sg;
+            int kend;
+            build_phase_segment(s_phr, threadIdx.x, sg, kend);
+            s_seg[threadIdx.x] = sg;
+            s_kend[threadIdx.x] = kend;
+        } else if ((int)threadIdx.x == nseg) {
+            TrajRec r;
+            r.type = s_phr.type & kRecTypeMask;
+            r.n = n_total;
+            r.f[0] = s_phr.r; r.f[1] = s_phr.cx; r.f[2] = s_phr.cy; r.f[3] = s_phr.alt;
+            r.f[4] = s_phr.dtr; r.f[5] = s_phr.rinv; r.f[6] = 0.0;
+            s_rec = r;
+        }
+        __syncthreads();
+    } else {
+        int4 tw;
+        if (MODE == 1) {
+            traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
+            if (threadIdx.x == 0) s_tile = __ldg(reinterpret_cast<const int4*>(tv.tiles) + blockIdx.x);
+            __syncthreads();
+            tw = s_tile;
+        } else {
+            tw = __ldg(reinterpret_cast<const int4*>(tv.tiles) + blockIdx.x);   // {traj, k_lo, seg_begin, nseg}
+            traj = tw.x;
+        }
+        if (tw.w <= 0) return;
+        k_lo = tw.y;
+        nseg = tw.w < kMaxSegPerTile ? tw.w : kMaxSegPerTile;
+        const int4* src = reinterpret_cast<const int4*>(tv.segs + tw.z);
+        for (int t = threadIdx.x; t < 4 + 4 * nseg; t += THREADS) {
+            if (t < 4) {
+                reinterpret_cast<int4*>(&s_rec)[t] = __ldg(reinterpret_cast<const int4*>(tv.recs + traj) + t);
+            } else {
+                const int4 w = __ldg(src + (t - 4));
+                reinterpret_cast<int4*>(s_seg)[t - 4] = w;
+                if (((t - 4) & 3) == 0) s_kend[(t - 4) >> 2] = w.x + w.y;
+            }
+        }
+        __syncthreads();
+    }
+
+    const int type = s_rec.type & kRecTypeMask;
+    const int n = s_rec.n;
+    // the tile's samples in runs of `per` consecutive ones, one run per thread
+    const int in_tile = min(n - k_lo, TILE);
+    int per = (in_tile + THREADS - 1) / THREADS;
+    if (per > 2) per = (per + TGX_RED_U - 1) / TGX_RED_U * TGX_RED_U;      // whole groups (the unrolled body)
+    const int k = k_lo + (int)threadIdx.x * per;
+    const int k_end = min(k + per, k_lo + in_tile);
+    double best_v2 = 0.0, best_a2 = 0.0;
+    if (k < k_end) {
+        int si = 0;
+        for (int i = 0; i + 1 < nseg; ++i) si += (k > s_kend[i]) ? 1 : 0;
+        if (type == TGX_CIRCLE) red_run<TGX_CIRCLE>(s_rec, s_seg, s_kend, nseg, si, k, k_end, best_v2, best_a2);
+        else if (type == TGX_FIGURE8) red_run<TGX_FIGURE8>(s_rec, s_seg, s_kend, nseg, si, k, k_end, best_v2, best_a2);
+        else if (type == TGX_LINE) red_run<TGX_LINE>(s_rec, s_seg, s_kend, nseg, si, k, k_end, best_v2, best_a2);
+        else red_run<kRecStatic>(s_rec, s_seg, s_kend, nseg, si, k, k_end, best_v2, best_a2);
+    }
+
+    best_v2 = warp_max(best_v2);
+    best_a2 = warp_max(best_a2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_red[0][warp] = best_v2;
+        s_red[1][warp] = best_a2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double a = max_nn(s_red[0][0], s_red[0][1]), b = max_nn(s_red[1][0], s_red[1][1]);
+        if (max_v) atomic_max_nonneg(max_v + traj, sqrt(a));
+        if (max_a) atomic_max_nonneg(max_a + traj, sqrt(b));
+    }
+}
+
 // Feasibility verdict per trajectory (BASELINE.json config 4): flag = max_v <= v_max && max_a <= a_max &&
 // no status bit set (the plan's status already carries OUTSIDE_BOUNDS when a box was given).
 __global__ void __launch_bounds__(256)
@@ -647,11 +896,12 @@ static cudaError_t launch_eval_t(const TableView& tv, int64_t ntiles, const OutV
         eval_kernel<THREADS, SPT, true, true, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
     else if (store)
         eval_kernel<THREADS, SPT, true, false, MODE><<<grid, THREADS, 0, stream>>>(tv, out, max_v, max_a);
-    else
-        // reduction only: 64-thread CTAs walking the tile in passes of 256 samples — 16 (8) samples per thread between
-        // the prologue and the warp / CTA reduction instead of 4, 20 small CTAs per SM.  Per Mi config-4 circles:
-        // 256 threads x 1 pass 7.76 ms, 128 x 2 6.21 ms, 64 x 4 5.72 ms
+    else if (TGX_REDUCE_LEGACY)
+        // (the generic kernel's reduction-only instantiation, kept for A/B runs: 64-thread CTAs walking the tile in
+        //  passes of 256 samples; per Mi config-4 circles 256 threads x 1 pass 7.76 ms, 128 x 2 6.21 ms, 64 x 4 5.72 ms)
         eval_kernel<64, 4, false, true, MODE, false, THREADS * SPT / 256><<<grid, 64, 0, stream>>>(tv, out, max_v, max_a);
+    else
+        reduce_kernel<MODE, THREADS * SPT><<<grid, 64, 0, stream>>>(tv, max_v, max_a);
     return cudaGetLastError();
 }
 
