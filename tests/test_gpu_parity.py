@@ -478,17 +478,30 @@ def test_stop_trajectories(engine, oracle):
 # ---- feasibility -------------------------------------------------------------------------------------------
 
 def test_feasibility_matches_oracle(engine, oracle):
-    params = abi.concat([workloads.montecarlo_cfg4(2000), workloads.mixed_cfg3(500)])
+    # ramps whose clamped last step is the last sample of a tile (1023 / 511 steps), the first sample of the next one
+    # (1024 / 512), and neighbours: the segment that ends there is the last one of its tile's list
+    edges = [abi.circle_params(1.5, 3.0, 0, 0, [v], 0.5, 1.0, 0.01, kind=kind)
+             for v in (10.225, 10.235, 10.215, 5.105, 5.115, 5.125, 20.465, 20.475)
+             for kind in (abi.TGX_CIRCLE, abi.TGX_FIGURE8)]
+    params = abi.concat([workloads.montecarlo_cfg4(2000), workloads.mixed_cfg3(500)] + edges)
     lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
     d = engine.upload_params(params)
+    o_flags, o_mv, o_ma, o_counts, o_status = oracle.feasibility_batch(params, lim)
+    try:
+        for tuning in ((9, 4), (10, 4)):                    # 512- and 1024-sample tiles; twice: both planning paths
+            engine.set_tuning(*tuning)
+            for _ in range(2):
+                plan = engine.plan(d, limits=lim)
+                flags, mv, ma, status = engine.feasibility(lim, len(params))
+                np.testing.assert_array_equal(plan.counts.cpu().numpy(), o_counts)
+                np.testing.assert_allclose(mv.cpu().numpy(), o_mv, rtol=1e-8, atol=1e-14, err_msg=str(tuning))
+                np.testing.assert_allclose(ma.cpu().numpy(), o_ma, rtol=1e-8, atol=1e-14, err_msg=str(tuning))
+    finally:
+        engine.set_tuning(10, 4)             # (invalidates the plan)
     plan = engine.plan(d, limits=lim)
     flags, mv, ma, status = engine.feasibility(lim, len(params))
     flags, mv, ma = flags.cpu().numpy(), mv.cpu().numpy(), ma.cpu().numpy()
     status = status.cpu().numpy().view(np.uint32)
-    o_flags, o_mv, o_ma, o_counts, o_status = oracle.feasibility_batch(params, lim)
-    np.testing.assert_array_equal(plan.counts.cpu().numpy(), o_counts)
-    np.testing.assert_allclose(mv, o_mv, rtol=1e-8, atol=1e-14)
-    np.testing.assert_allclose(ma, o_ma, rtol=1e-8, atol=1e-14)
     # a verdict may only differ where a maximum sits within tolerance of its limit
     near = (np.abs(o_mv - lim.v_max) <= 1e-8 * lim.v_max) | (np.abs(o_ma - lim.a_max) <= 1e-8 * lim.a_max)
     np.testing.assert_array_equal(flags[~near], o_flags[~near])
@@ -607,6 +620,8 @@ def test_tolerance_concessions_are_quantified(engine, oracle, capsys):
     with capsys.disabled():
         print("TOLERANCE CONCESSIONS (verdicts) " + json.dumps(report["feasibility sweep (config 4), 100 000 trajectories"]))
     assert differ <= near, report
+    v = report["feasibility sweep (config 4), 100 000 trajectories"]
+    assert v["worst_rel_max_v"] < 1e-12 and v["worst_rel_max_a"] < 1e-12, v
 
 
 # ---- host-buffer C-ABI calls ------------------------------------------------------------------------------

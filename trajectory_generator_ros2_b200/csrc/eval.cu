@@ -729,7 +729,7 @@ __device__ __forceinline__ void red_run(const TrajRec& rec, const Seg* __restric
     for (; k + U <= k_end; k += U) {
         double v[U], th[U], acc[U], v2[U], a2[U];
         while (si + 1 < nseg && k > kends[si]) ++si;
-        const int k_last = (si + 1 < nseg) ? kends[si] : 0x7fffffff;
+        const int k_last = kends[si];               // (also of the list's last segment: its last sample is special too)
         if (k + U - 1 <= k_last) {
             // the common case: one segment serves the whole group; its record is read once (four 16-byte LDS) and only
             // the group's last sample can be the segment's last one (clamped speed, replayed angle)

@@ -34,8 +34,19 @@ __device__ __forceinline__ long long regular_run(double x0, double x1, double a)
     const double inc = dsub(x1, x0);                      // exact
     if (inc == 0.0) return 1LL << 40;                     // |a| < u/2: x does not move while it stays in this binade
     const double lo = __longlong_as_double(i1 & 0x7ff0000000000000LL);   // 2^E
-    const double r = fabs(a) / dmul(lo, 0x1p-53);         // |a| in units of u/2 (exact scaling)
-    if (r < 0x1p53 && r == rint(r) && (((long long)r) & 1LL)) return 0;  // tie: increments alternate
+    // tie: |a| is an odd multiple of u/2 = 2^(E-53), the increments alternate.  In integers: |a| = ma * 2^(ea-1075) with
+    // the 53-bit significand ma, so |a| / (u/2) = ma * 2^(ea-e+1); for ea >= e that is an even number (or >= 2^53: no tie
+    // by definition), a subnormal |a| is below u/2, and otherwise it is ma >> s with s = e - ea - 1: an odd integer exactly
+    // when ma has s trailing zeros.  (The same test used to be  r = |a| / (lo * 2^-53); r < 2^53 && r == rint(r) && odd(r):
+    // a division, a rint and a 64-bit conversion, 17 % of the replay kernels' executed instructions.)
+    {
+        const unsigned long long ab = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffULL;
+        const int ea = (int)(ab >> 52);
+        if (ea > 0 && ea < e) {
+            const unsigned long long ma = (ab & 0x000fffffffffffffULL) | 0x0010000000000000ULL;
+            if (__ffsll((long long)ma) - 1 == e - ea - 1) return 0;
+        }
+    }
     const double ax = fabs(x1), ai = fabs(inc);
     const bool growing = (inc > 0.0) == (x1 > 0.0);
     const double room = growing ? dsub(dmul(2.0, lo), ax) : dsub(ax, lo);   // exact distance to the binade edge
