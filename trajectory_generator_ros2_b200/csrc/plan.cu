@@ -224,6 +224,9 @@ __device__ __forceinline__ bool ramp(double& v, double target, double adt, doubl
                                      const double* force_xy = nullptr) {
     bool open = false;
     const double clampv = UP ? target : 0.0;
+    // one division per ramp instead of two per run: the run-length estimates below multiply by 1 / (a*dt) and are then
+    // settled by exact checks (see regular_run)
+    const double inv_adt = XR ? 0.0 : ddiv(1.0, adt);
     while (UP ? (v < target) : (v > 0.0)) {
         const double vn = UP ? std_min(dadd(v, adt), target) : std_max(dsub(v, adt), 0.0);
         if (vn == v || (int64_t)k + 1 >= max_samples) return false;
@@ -261,13 +264,13 @@ __device__ __forceinline__ bool ramp(double& v, double target, double adt, doubl
             }
         } else {
             const double inc = dsub(vn, v);                      // exact
-            long long J = (vn == clampv) ? 0 : regular_run(v, vn, UP ? adt : -adt);
+            long long J = (vn == clampv) ? 0 : regular_run(v, vn, UP ? adt : -adt, inv_adt);
             J = min(J, (long long)(kRebase - (k + 1 - E.cur.kb)));  // a segment holds at most kRebase steps
             J = min(J, max_samples - 2 - (long long)k);            // the guard fires on the next real step
             if (J > 0) {
                 // none of the jumped steps may reach the clamp: vn + J*inc strictly between 0 and target
                 const double room = UP ? dsub(target, vn) : vn;
-                const double q = ceil(ddiv(room, fabs(inc))) - 1.0;
+                const double q = ceil(dmul(room, inv_adt)) - 1.0;        // an estimate: the loop below is the exact test
                 const long long Jc = q < 1.0 ? 0 : (q > 1e15 ? (1LL << 40) : (long long)q);
                 J = min(J, Jc);
                 while (J > 0) {
@@ -346,6 +349,9 @@ __device__ __forceinline__ bool hold(double v, double t_hold, double dt, int& k,
     if (rem < 0) return false;
     bool open = false;
     double seg_d = 0.0;
+    // reciprocals of the per-step addends for regular_run's run-length estimates (0: not usable, divide)
+    const double inv0 = (TRACK0 && rem > 1 && fabs(a0) > 0x1p-500 && fabs(a0) < 0x1p500) ? ddiv(1.0, fabs(a0)) : 0.0;
+    const double inv1 = (TRACK1 && rem > 1 && fabs(a1) > 0x1p-500 && fabs(a1) < 0x1p500) ? ddiv(1.0, fabs(a1)) : 0.0;
     while (rem > 0) {
         // ---- one real step ----------------------------------------------------------------------------
         const double s0n = TRACK0 ? dadd(s0, a0) : s0;
@@ -360,8 +366,8 @@ __device__ __forceinline__ bool hold(double v, double t_hold, double dt, int& k,
             open = true;
         }
         long long J = rem - 1;
-        if (TRACK0) J = min(J, regular_run(s0, s0n, a0));
-        if (TRACK1) J = min(J, regular_run(s1, s1n, a1));
+        if (TRACK0) J = min(J, regular_run(s0, s0n, a0, inv0));
+        if (TRACK1) J = min(J, regular_run(s1, s1n, a1, inv1));
         s0 = s0n;
         s1 = s1n;
         ++k;

@@ -26,7 +26,11 @@ __device__ __forceinline__ bool finite_pos(double x) { return isfinite(x) && x >
 // adds exactly the same inc = fl(x + a) - x and the reference's running sum is an exact arithmetic progression.
 // Given one real step x0 -> x1 this returns how many FURTHER steps are guaranteed to add exactly x1 - x0
 // (0 when the step crossed a binade, hit a tie, or the values are zero / subnormal-ish).
-__device__ __forceinline__ long long regular_run(double x0, double x1, double a) {
+// inv_a (optional): an approximation of 1 / |a| hoisted out of the caller's loop.  It only replaces the division in the
+// ESTIMATE of the run length — the effective increment differs from a by less than half an ulp of x, so the estimate is
+// off by at most one step — and the exact check below settles the result either way: an estimate that is too long is
+// shortened, one that is a step short makes the caller take one more (equally exact) run.
+__device__ __forceinline__ long long regular_run(double x0, double x1, double a, double inv_a = 0.0) {
     const long long i0 = __double_as_longlong(x0), i1 = __double_as_longlong(x1);
     if (((i0 ^ i1) >> 52) != 0) return 0;                 // sign or exponent changed: an irregular (crossing) step
     const int e = (int)((i1 >> 52) & 0x7ff);
@@ -50,7 +54,7 @@ __device__ __forceinline__ long long regular_run(double x0, double x1, double a)
     const double ax = fabs(x1), ai = fabs(inc);
     const bool growing = (inc > 0.0) == (x1 > 0.0);
     const double room = growing ? dsub(dmul(2.0, lo), ax) : dsub(ax, lo);   // exact distance to the binade edge
-    const double q = floor(ddiv(room, ai));
+    const double q = floor(inv_a > 0.0 ? dmul(room, inv_a) : ddiv(room, ai));
     long long J = q > 1e15 ? (1LL << 40) : (long long)q;
     // exact check: after J further steps the value must still lie in [2^E, 2^(E+1)]
     while (J > 0) {
