@@ -108,6 +108,15 @@ struct Emitter {
     int tile_seg_begin = 0;
     Seg cur;              // the open segment, kept in registers until closed
 
+    // Lanes of a warp that replay trajectories of the same class (same type, same number of speed goals) meet at a warp
+    // barrier after every phase.  Without it a lane that leaves a ramp loop early runs ahead into the next phase on its own
+    // — the compiler reconverges such loops (several exits) only at the end of the replay — and the warp executes every
+    // phase once per straggler: ncu showed 9 of 32 lanes active per executed instruction.  `grp` is formed where the
+    // lanes enter the replay (plan_one); every lane of it passes the same barriers, failed ones included.
+    unsigned grp = 0;
+    __device__ __forceinline__ void converge() const {
+        if (grp) __syncwarp(grp);
+    }
     int ph_blocks = 1;         // tgx_phases rows this trajectory owns (its own and its continuation records')
     // entry nph goes to slot nph % 18 of row nph / 18 (tgx.h: TGX_VGOALS_MORE)
     __device__ void phase(int key, int kind, double value, double value2) {
@@ -443,30 +452,37 @@ __device__ int replay_orbit(const tgx_params& p, const Src& src, int64_t max_sam
     auto step = [&](double vnew) {                           // omega = v/r_; theta += omega*dt_  (:50-51, :79)
         if (STATE) th = dadd(th, dmul(div_inv(vnew, rdiv), dt));
     };
+    // (a phase that fails — the sample guard, a speed that does not move — ends the replay, but the lane still walks
+    //  through the remaining barriers so that its group stays in step)
+    bool ok = true;
     for (int g = 0; g < p.n_vgoals; ++g) {                   // :43
         const double vg = orbit_goal(p, src, g);
-        E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                // :45
-        E.goal = g;
-        if (!ramp<true, XR, STATE, false>(v, vg, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, dtr, 0.0,
-                                          step)) {                                              // :47-54
-            st |= TGX_ST_TOO_LONG;
-            return -1;
+        if (ok) {
+            E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);            // :45
+            E.goal = g;
+            ok = ramp<true, XR, STATE, false>(v, vg, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, dtr, 0.0,
+                                              step);                                            // :47-54
         }
-        if (fabs(dsub(v, vg)) > 0.001) st |= TGX_ST_VGOALS_NOT_INCREASING;                // :57-59
-        E.phase(k, TGX_PH_REACHED, vg, o.t_traj);            // :61-62
-        const double w = STATE ? dmul(div_inv(v, rdiv), dt) : 0.0;    // omega*dt_, the same on every step (:65-67)
-        // holds are cut at every binade crossing of theta in BOTH planning modes: inside a segment the reference's
-        // running sum is an exact arithmetic progression, so nothing drifts inside a hold however long it is (the hold
-        // samples are the reference's running sum from the hold's first angle: bit for bit with exact ramps, and off by
-        // the preceding ramps' closed-form rounding, ~1e-13 rad, with fast ones)
-        if (!hold<STATE, false, STATE>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0, tab)) {   // :63-71
-            st |= TGX_ST_TOO_LONG;
-            return -1;
+        E.converge();
+        if (ok) {
+            if (fabs(dsub(v, vg)) > 0.001) st |= TGX_ST_VGOALS_NOT_INCREASING;            // :57-59
+            E.phase(k, TGX_PH_REACHED, vg, o.t_traj);        // :61-62
+            const double w = STATE ? dmul(div_inv(v, rdiv), dt) : 0.0;    // omega*dt_, the same on every step (:65-67)
+            // holds are cut at every binade crossing of theta in BOTH planning modes: inside a segment the reference's
+            // running sum is an exact arithmetic progression, so nothing drifts inside a hold however long it is (the
+            // hold samples are the reference's running sum from the hold's first angle: bit for bit with exact ramps,
+            // and off by the preceding ramps' closed-form rounding, ~1e-13 rad, with fast ones)
+            ok = hold<STATE, false, STATE>(v, o.t_traj, dt, k, max_samples, tmask, E, th, unused, w, 0.0, tab);   // :63-71
         }
+        E.converge();
     }
-    E.phase(k, TGX_PH_DECEL, 0.0, 0.0);                      // :74
-    if (!ramp<false, XR, STATE, false>(v, 0.0, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, dtr, 0.0,
-                                       step)) {                                                 // :75-82
+    if (ok) {
+        E.phase(k, TGX_PH_DECEL, 0.0, 0.0);                  // :74
+        ok = ramp<false, XR, STATE, false>(v, 0.0, adt, dtr, k, max_samples, tmask, E, 0.0, th, unused, dtr, 0.0,
+                                           step);                                               // :75-82
+    }
+    E.converge();
+    if (!ok) {
         st |= TGX_ST_TOO_LONG;
         return -1;
     }
@@ -513,45 +529,52 @@ __device__ int replay_line(const tgx_params& p, int64_t max_samples, Emitter& E,
         y = dadd(y, dmul(dmul(vnew, ss), dt));
     };
     int k = 0;
+    bool ok = true;                                              // (see replay_orbit: failed lanes keep to the barriers)
     for (int leg = 0; leg < (boomerang ? 2 : 1); ++leg) {
         const double sgn = leg == 0 ? 1.0 : -1.0;
         const double* from = leg == 0 ? l.A : l.B;
         const double* to = leg == 0 ? l.B : l.A;
         double v = 0.0;
-        // the leg's first sample: createLineGoal(from.x, from.y, +-0, 0, theta)  (:40, Boomerang.cpp:90)
-        x = dadd(from[0], dmul(dmul(sgn * v, cc), dt));
-        y = dadd(from[1], dmul(dmul(sgn * v, ss), dt));
-        if (leg == 1) {
-            // sample 0 of the plan is served by the first ramp segment (j = 0); the return leg's first sample needs
-            // a segment of its own, one step of speed -0 from B
-            if ((int64_t)k + 1 >= max_samples) {
-                st |= TGX_ST_TOO_LONG;
-                return -1;
+        if (ok) {
+            // the leg's first sample: createLineGoal(from.x, from.y, +-0, 0, theta)  (:40, Boomerang.cpp:90)
+            x = dadd(from[0], dmul(dmul(sgn * v, cc), dt));
+            y = dadd(from[1], dmul(dmul(sgn * v, ss), dt));
+            if (leg == 1) {
+                // sample 0 of the plan is served by the first ramp segment (j = 0); the return leg's first sample
+                // needs a segment of its own, one step of speed -0 from B
+                if ((int64_t)k + 1 >= max_samples) {
+                    ok = false;
+                } else {
+                    E.open(k, sgn * v, 0.0, sgn * v, from[0], from[1], 0.0);
+                    ++k;
+                    E.close(k, false, 0.0);
+                }
             }
-            E.open(k, sgn * v, 0.0, sgn * v, from[0], from[1], 0.0);
-            ++k;
-            E.close(k, false, 0.0);
         }
-        E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                    // :44
-        if (!ramp<true, XR, true, true>(v, vg, dmul(l.a1, dt), 0.0, k, max_samples, tmask, E, sgn * l.a1, x, y,
-                                        sgn * cdt, sgn * sdt, step, sgn)) {                    // :46-50
-            st |= TGX_ST_TOO_LONG;
-            return -1;
+        if (ok) {
+            E.phase(k, TGX_PH_ACCEL_TO, vg, 0.0);                // :44
+            ok = ramp<true, XR, true, true>(v, vg, dmul(l.a1, dt), 0.0, k, max_samples, tmask, E, sgn * l.a1, x, y,
+                                            sgn * cdt, sgn * sdt, step, sgn);                  // :46-50
         }
-        E.phase(k, TGX_PH_REACHED, vg, t2);                      // :55-56
-        if (!hold<true, true, false>(sgn * v, t2, dt, k, max_samples, tmask, E, x, y, dmul(dmul(sgn * v, cc), dt),
-                                     dmul(dmul(sgn * v, ss), dt), tab)) {                    // :57-62
-            st |= TGX_ST_TOO_LONG;
-            return -1;
+        E.converge();
+        if (ok) {
+            E.phase(k, TGX_PH_REACHED, vg, t2);                  // :55-56
+            ok = hold<true, true, false>(sgn * v, t2, dt, k, max_samples, tmask, E, x, y, dmul(dmul(sgn * v, cc), dt),
+                                         dmul(dmul(sgn * v, ss), dt), tab);                  // :57-62
         }
-        E.phase(k, TGX_PH_DECEL, 0.0, 0.0);                      // :64
-        if (!ramp<false, XR, true, true>(v, 0.0, dmul(l.a3, dt), 0.0, k, max_samples, tmask, E, -sgn * l.a3, x, y,
-                                         sgn * cdt, sgn * sdt, step, sgn, to)) {               // :65-68, forced :81-82
-            st |= TGX_ST_TOO_LONG;
-            return -1;
+        E.converge();
+        if (ok) {
+            E.phase(k, TGX_PH_DECEL, 0.0, 0.0);                  // :64
+            ok = ramp<false, XR, true, true>(v, 0.0, dmul(l.a3, dt), 0.0, k, max_samples, tmask, E, -sgn * l.a3, x, y,
+                                             sgn * cdt, sgn * sdt, step, sgn, to);             // :65-68, forced :81-82
         }
+        E.converge();
         // :71-79 / Boomerang.cpp:126-129 (exit(1) in the reference), checked on the replayed, not the forced, position
-        if (fabs(dsub(to[0], x)) > 0.05 || fabs(dsub(to[1], y)) > 0.05) st |= TGX_ST_LINE_END_NOT_B;
+        if (ok && (fabs(dsub(to[0], x)) > 0.05 || fabs(dsub(to[1], y)) > 0.05)) st |= TGX_ST_LINE_END_NOT_B;
+    }
+    if (!ok) {
+        st |= TGX_ST_TOO_LONG;
+        return -1;
     }
     E.phase(k, TGX_PH_STOPPED, 0.0, 0.0);                        // :84, Boomerang.cpp:134
     return k + 1;
@@ -606,6 +629,8 @@ __device__ PlanOut plan_one(const tgx_params& p, const Src& src, int64_t max_sam
     } else {
         int n;
         double theta = 0.0, c = 1.0, s = 0.0;
+        // the lanes that arrive here together and replay the same class of trajectory (replay_orbit / replay_line)
+        E.grp = __match_any_sync(__activemask(), (p.type << 8) | (is_orbit(p.type) ? p.n_vgoals : 0));
         if (is_line_like(p.type))
             n = replay_line<XR>(p, max_samples, E, r.status, theta, c, s, tab, p.type == TGX_BOOMERANG);
         else

@@ -22,10 +22,10 @@ __device__ __forceinline__ bool finite_pos(double x) { return isfinite(x) && x >
 
 // ---- skip-ahead for x <- fl(x + a) with a constant addend -------------------------------------------------
 // While x stays inside one binade [2^E, 2^(E+1)] (same sign), every exact sum x + a is rounded to the same grid
-// of spacing u = 2^(E-52), so unless a is an odd multiple of u/2 (a tie, where round-half-even alternates) each step
-// adds exactly the same inc = fl(x + a) - x and the reference's running sum is an exact arithmetic progression.
+// of spacing u = 2^(E-52), so each step adds exactly the same inc = fl(x + a) - x and the reference's running sum is
+// an exact arithmetic progression — also when a is an odd multiple of u/2 (a tie), once x has an even significand.
 // Given one real step x0 -> x1 this returns how many FURTHER steps are guaranteed to add exactly x1 - x0
-// (0 when the step crossed a binade, hit a tie, or the values are zero / subnormal-ish).
+// (0 when the step crossed a binade, started a tie run from an odd significand, or the values are zero / subnormal-ish).
 // inv_a (optional): an approximation of 1 / |a| hoisted out of the caller's loop.  It only replaces the division in the
 // ESTIMATE of the run length — the effective increment differs from a by less than half an ulp of x, so the estimate is
 // off by at most one step — and the exact check below settles the result either way: an estimate that is too long is
@@ -48,7 +48,12 @@ __device__ __forceinline__ long long regular_run(double x0, double x1, double a,
         const int ea = (int)(ab >> 52);
         if (ea > 0 && ea < e) {
             const unsigned long long ma = (ab & 0x000fffffffffffffULL) | 0x0010000000000000ULL;
-            if (__ffsll((long long)ma) - 1 == e - ea - 1) return 0;
+            // Round-half-even sends a tie to the neighbour with the even significand and an even x stays even (its
+            // increment is then an even number of ulps), so from an EVEN x0 on the run is as regular as any other; only
+            // the one step that starts from an odd x0 is irregular.  (Returning 0 for every step of a tie binade made
+            // one lane in a few replay its ramp step by step — 64 or 128 single steps — while the rest of its warp
+            // waited: 9 of 32 lanes active per executed instruction.)
+            if (__ffsll((long long)ma) - 1 == e - ea - 1 && (i0 & 1LL)) return 0;
         }
     }
     const double ax = fabs(x1), ai = fabs(inc);
