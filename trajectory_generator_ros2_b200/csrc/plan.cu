@@ -115,7 +115,9 @@ struct Emitter {
     // lanes enter the replay (plan_one); every lane of it passes the same barriers, failed ones included.
     unsigned grp = 0;
     __device__ __forceinline__ void converge() const {
+#ifndef TGX_NO_REPLAY_BARRIERS
         if (grp) __syncwarp(grp);
+#endif
     }
     int ph_blocks = 1;         // tgx_phases rows this trajectory owns (its own and its continuation records')
     // entry nph goes to slot nph % 18 of row nph / 18 (tgx.h: TGX_VGOALS_MORE)
