@@ -88,3 +88,36 @@ if traffic:
                    "_how": f"dram__bytes_read.sum + dram__bytes_write.sum of tgx::eval_kernel from profiles/{tag}_kernels_ncu.txt "
                            f"(ncu --set full at 65 536 trajectories) divided by that launch's algorithmic bytes = "
                            f"{traffic['ratio']:.4f}, times the bench launch's algorithmic bytes ({bench_bytes})"}, f, indent=1)
+
+# ---- the other captures of tools/refresh_profiles.sh: records (f3), reduction-only (configs 4-5), plan_fill ----------------
+extra = [("prof_rec_tma.ncu-rep", "ncu --set full -k regex:eval_kernel -s 3 -c 1 of `python bench.py --records --steps 1 --warmup 1 "
+          "--no-cpu --no-e2e`: the RECORDS instantiation through TMA (tgx_eval_records) on one chunk of 131 072 circles; "
+          "algorithmic bytes 128 B/sample"),
+         ("prof_feas.ncu-rep", "ncu --set full -k regex:reduce_kernel -s 3 -c 1 of `python bench.py --workload montecarlo_cfg4 "
+          "--steps 2 --warmup 3 --no-cpu --no-e2e --n-per-gpu 2000000`: tgx_feasibility's kernel on 2 000 000 config-4 circles "
+          "= 2.157e9 samples; writes 17 B per trajectory, FP64- / issue-bound"),
+         ("prof_plan_fill.ncu-rep", "ncu --set full -k regex:plan_fill_kernel -s 3 -c 1 of `python bench.py --workload "
+          "montecarlo_cfg4 --steps 2 --warmup 3 --no-cpu --no-e2e --n-per-gpu 1000000`: the replay that writes the segment "
+          "tables, 1 000 000 config-4 circles")]
+want2 = want + ["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+                "smsp__warps_eligible.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
+                "sass__inst_executed_local_loads", "sass__inst_executed_local_stores"]
+with open(os.path.join(dst, f"{tag}_f3_cfg4_plan_kernels_ncu.txt"), "w") as f:
+    for name, title in extra:
+        rep = os.path.join(src, name)
+        if not os.path.exists(rep):
+            continue
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        if len(rows) < 3:
+            continue
+        h, u = rows[0], rows[1]
+        f.write("# " + title + "\n")
+        for r in rows[2:]:
+            for i, nm in enumerate(h):
+                if nm in want2:
+                    f.write(f"{nm:90s} {u[i]:16s} {r[i][:110]}\n")
+            f.write("\n")
+print(open(os.path.join(dst, f"{tag}_f3_cfg4_plan_kernels_ncu.txt")).read()[:3000])
