@@ -206,6 +206,13 @@ struct tgx_engine {
     int seg_slab_plan = 0, tile_slab_plan = 0;   // slice sizes of the CURRENT plan (if plan_packed)
     int64_t slab_plans = 0, exact_plans = 0;
 
+    // the same for braking plans (tgx_plan_stop), whose segment / tile counts have nothing to do with generateTraj's:
+    // swapped in for the duration of such a plan (LearnSwap in plan_common)
+    struct Learned {
+        bool slabs_ready = false, ragged_ready = false, mixed_batch = false, phase_ready = false;
+        int seg_slab = 0, tile_slab = 0, phase_tile_slab = 0;
+    } stop_learn;
+
     // per-trajectory scratch (capacity in trajectories)
     DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals, cur_table, stats;
     // tables
@@ -313,6 +320,24 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     int rc = ensure_traj_scratch(e, n);
     if (rc) return rc;
 
+    // braking plans learn and use their own slice sizes
+    struct LearnSwap {
+        tgx_engine* e;
+        bool on;
+        void swap() {
+            auto& L = e->stop_learn;
+            std::swap(e->slabs_ready, L.slabs_ready);
+            std::swap(e->ragged_ready, L.ragged_ready);
+            std::swap(e->mixed_batch, L.mixed_batch);
+            std::swap(e->phase_ready, L.phase_ready);
+            std::swap(e->seg_slab, L.seg_slab);
+            std::swap(e->tile_slab, L.tile_slab);
+            std::swap(e->phase_tile_slab, L.phase_tile_slab);
+        }
+        LearnSwap(tgx_engine* e_, bool on_) : e(e_), on(on_) { if (on) swap(); }
+        ~LearnSwap() { if (on) swap(); }
+    } learn_swap(e, d_stop_from != nullptr);
+
     int32_t* cnt = e->cnt.as<int32_t>();
     int32_t* nseg = e->nseg.as<int32_t>();
     int32_t* ntile = e->ntile.as<int32_t>();
@@ -397,7 +422,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     }
 
     // ---- slab mode: ONE replay, no scans; falls through to the exact-offset path if a slice overflows ----------
-    if (!done && e->allow_slabs && (e->slabs_ready || e->ragged_ready) && !d_stop_from) {
+    if (!done && e->allow_slabs && (e->slabs_ready || e->ragged_ready)) {
         const int64_t need_segs = n * (int64_t)e->seg_slab, need_tiles = n * (int64_t)e->tile_slab;
         if (need_segs <= 0x7fffffffLL && need_tiles <= 0x7fffffffLL) {
             if ((rc = e->segs.reserve((size_t)need_segs * sizeof(tgx::Seg)))) return rc;
@@ -425,7 +450,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                 e->launches += 2;
                 order = idx_out;
             }
-            TGX_CUDA(tgx::launch_plan_fill(d_params, nullptr, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
+            TGX_CUDA(tgx::launch_plan_fill(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
                                            tab, nullptr, nullptr, nullptr, e->seg_slab, e->tile_slab,
                                            e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(),
                                            e->tiles.as<tgx::Tile>(), d_counts, d_status, cnt, st, d_phases, d_stats,
@@ -522,7 +547,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                                        nullptr, d_phases, d_stats, stream));
         e->launches += 1;
         e->exact_plans += 1;
-        if (e->allow_slabs && !d_stop_from) {
+        if (e->allow_slabs) {
             TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
             TGX_CUDA(cudaStreamSynchronize(stream));
             relearn(tot_tiles);
@@ -878,6 +903,7 @@ int tgx_set_tuning(tgx_engine* e, int tile_shift, int spt) {
     e->slabs_ready = false;
     e->ragged_ready = false;
     e->phase_ready = false;
+    e->stop_learn = tgx_engine::Learned();
     return TGX_OK;
 }
 
@@ -888,6 +914,7 @@ int tgx_set_plan_mode(tgx_engine* e, int exact_ramps) {
     e->slabs_ready = false;   // segment counts differ between the modes (ramp chunks)
     e->ragged_ready = false;
     e->phase_ready = false;
+    e->stop_learn = tgx_engine::Learned();
     return TGX_OK;
 }
 
@@ -914,6 +941,7 @@ int tgx_set_slab_planning(tgx_engine* e, int allow) {
     e->slabs_ready = false;
     e->ragged_ready = false;
     e->has_plan = false;
+    e->stop_learn = tgx_engine::Learned();
     return TGX_OK;
 }
 
