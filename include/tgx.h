@@ -428,7 +428,8 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
  * chunk's hides behind the store-bound kernel.  The work starts after everything queued on `stream` so far, and
  * `stream` waits for all of it; the host returns when the last chunk has been planned (its evaluation may still run).
  * Writes exactly the bytes tgx_plan + tgx_eval of the whole batch write (the samples do not depend on how a batch is
- * cut), d_counts / d_status / d_phases (each may be NULL) as tgx_plan does, and the sample total.  Circle / Line /
+ * cut; a chunk never ends between a record and its continuation records), d_counts / d_status / d_phases (each may be
+ * NULL) as tgx_plan does, and the sample total.  Circle / Line /
  * Figure8 / Boomerang records; polyline-family records get TGX_ST_WRONG_PLANNER as in tgx_plan.  Leaves no current
  * plan. */
 int tgx_generate(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx_limits* limits, const tgx_layout* out,

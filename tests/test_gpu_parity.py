@@ -215,6 +215,19 @@ def test_vgoals_of_any_length(mode_engine, oracle):
         assert abi.phases_to_index_msgs(kind, ph[i:i + rows] if rows > 1 else ph[i]) == \
             abi.phases_to_index_msgs(kind, oph)
     assert counts[starts[0]] == 1                      # empty vector: the start sample alone
+    # tgx_generate cuts the batch into chunks itself: no chunk may end between a record and its continuations
+    import torch
+    d_params = engine.upload_params(params)
+    for chunk in (1, 2, 5, 7):
+        o2 = torch.full(out.shape, float("nan"), dtype=torch.float64, device=d_params.device)
+        plan = engine.generate(d_params, o2, want_outputs=True, chunk=chunk)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(plan.counts.cpu().numpy(), counts, err_msg=f"chunk {chunk}")
+        np.testing.assert_array_equal(plan.status.cpu().numpy().view(np.uint32), status, err_msg=f"chunk {chunk}")
+        got = o2.cpu().numpy()
+        m = ~np.isnan(out)
+        assert (np.isnan(got) == ~m).all()
+        np.testing.assert_array_equal(got[m], out[m], err_msg=f"chunk {chunk}")
     # the same through the host-buffer call, whose chunks must not separate a record from its continuations
     cap = int(counts.max() + 3) // 4 * 4
     h_out, h_counts, h_status, _ = engine.generate_host(params, cap)

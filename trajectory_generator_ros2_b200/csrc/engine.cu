@@ -43,6 +43,8 @@ cudaError_t launch_plan_fill(const tgx_params* params, const double* stop_from, 
                              int seg_slab, int tile_slab, TrajRec* recs, Seg* segs, Tile* tiles, int32_t* counts,
                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
                              PlanStats* stats, cudaStream_t stream, const int32_t* order = nullptr);
+cudaError_t launch_chunk_bounds(const tgx_params* params, int64_t n, int64_t chunk, int nb, int64_t* bounds,
+                                cudaStream_t stream);
 cudaError_t launch_replay_keys(const tgx_params* params, int64_t n, uint8_t* key, int32_t* idx, cudaStream_t stream);
 cudaError_t launch_count_used_tiles(int64_t n, int tile_slab, const Tile* slots, int32_t* ntile, cudaStream_t stream);
 cudaError_t launch_compact_tiles(int64_t n, int tile_slab, const Tile* slots, const int64_t* tile_off, Tile* dense,
@@ -1210,6 +1212,28 @@ static int generate_after_eval(tgx_engine* e, int64_t ci, cudaEvent_t prof_end) 
     return TGX_OK;
 }
 
+// Where the chunks of a pipelined call end: multiples of `chunk`, moved forward past continuation records so that no
+// trajectory is separated from its goal speeds (one tiny kernel and one 8-byte-per-boundary read-back on the caller's
+// stream, before anything else is queued).
+static int generate_bounds(tgx_engine* e, const tgx_params* d_params, int64_t n, int64_t chunk, cudaStream_t caller,
+                           std::vector<int64_t>& ends) {
+    ends.clear();
+    const int64_t nb = (n + chunk - 1) / chunk - 1;          // interior boundaries
+    if (nb > 0) {
+        if (nb > (1 << 20)) return TGX_ERR_INVALID;
+        int rc = e->totals.reserve((size_t)std::max<int64_t>(nb, 4) * sizeof(int64_t));
+        if (rc) return rc;
+        std::vector<int64_t> h((size_t)nb);
+        TGX_CUDA(tgx::launch_chunk_bounds(d_params, n, chunk, (int)nb, e->totals.as<int64_t>(), caller));
+        TGX_CUDA(cudaMemcpyAsync(h.data(), e->totals.p, (size_t)nb * sizeof(int64_t), cudaMemcpyDeviceToHost, caller));
+        TGX_CUDA(cudaStreamSynchronize(caller));
+        for (int64_t v : h)
+            if (v < n && (ends.empty() || v > ends.back())) ends.push_back(v);
+    }
+    ends.push_back(n);
+    return TGX_OK;
+}
+
 static int64_t generate_chunk(int64_t n, int64_t chunk) {
     if (chunk <= 0) {
         // eight chunks hide 7/8 of the planning; at least 32 Ki trajectories (a few hundred CTAs per SM) per chunk so
@@ -1231,12 +1255,14 @@ int tgx_generate(tgx_engine* e, const tgx_params* d_params, int64_t n, const tgx
     if (n == 0) return TGX_OK;
     TGX_CUDA(cudaSetDevice(e->device));
     cudaStream_t caller = static_cast<cudaStream_t>(stream);
-    if ((rc = generate_setup(e, caller))) return rc;
     chunk = generate_chunk(n, chunk);
+    std::vector<int64_t> ends;
+    if ((rc = generate_bounds(e, d_params, n, chunk, caller, ends))) return rc;
+    if ((rc = generate_setup(e, caller))) return rc;
     int64_t total = 0;
     int64_t ci = 0;
-    for (int64_t lo = 0; lo < n; lo += chunk, ++ci) {
-        const int64_t m = std::min(chunk, n - lo);
+    for (int64_t lo = 0; ci < (int64_t)ends.size(); lo = ends[ci], ++ci) {
+        const int64_t m = ends[ci] - lo;
         tgx_engine* eng = (ci & 1) ? e->twin : e;
         cudaStream_t ps;
         if ((rc = generate_before_plan(e, ci, &ps))) break;
@@ -1268,13 +1294,15 @@ int tgx_generate_feasibility(tgx_engine* e, const tgx_params* d_params, int64_t 
     if (n == 0) return TGX_OK;
     TGX_CUDA(cudaSetDevice(e->device));
     cudaStream_t caller = static_cast<cudaStream_t>(stream);
-    int rc = generate_setup(e, caller);
-    if (rc) return rc;
     chunk = generate_chunk(n, chunk);
+    std::vector<int64_t> ends;
+    int rc = generate_bounds(e, d_params, n, chunk, caller, ends);
+    if (rc) return rc;
+    if ((rc = generate_setup(e, caller))) return rc;
     int64_t total = 0;
     int64_t ci = 0;
-    for (int64_t lo = 0; lo < n; lo += chunk, ++ci) {
-        const int64_t m = std::min(chunk, n - lo);
+    for (int64_t lo = 0; ci < (int64_t)ends.size(); lo = ends[ci], ++ci) {
+        const int64_t m = ends[ci] - lo;
         tgx_engine* eng = (ci & 1) ? e->twin : e;
         cudaStream_t ps;
         if ((rc = generate_before_plan(e, ci, &ps))) break;

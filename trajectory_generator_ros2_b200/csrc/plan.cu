@@ -1163,6 +1163,24 @@ compact_tiles_kernel(int64_t n, int tile_slab, const Tile* __restrict__ slots, c
     }
 }
 
+// Chunk boundaries of tgx_generate: boundary b would fall at (b + 1) * chunk; it moves forward past continuation records
+// (tgx.h: TGX_VGOALS_MORE), so that a Circle / Figure8 with more than 8 goal speeds is never cut from its goals.
+__global__ void chunk_bounds_kernel(const tgx_params* __restrict__ params, int64_t n, int64_t chunk, int nb,
+                                    int64_t* __restrict__ bounds) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    int64_t lo = (int64_t)(b + 1) * chunk;
+    while (lo < n && __ldg(&params[lo].type) == TGX_VGOALS_MORE) ++lo;
+    bounds[b] = lo < n ? lo : n;
+}
+
+cudaError_t launch_chunk_bounds(const tgx_params* params, int64_t n, int64_t chunk, int nb, int64_t* bounds,
+                                cudaStream_t stream) {
+    if (nb <= 0) return cudaSuccess;
+    chunk_bounds_kernel<<<(nb + 63) / 64, 64, 0, stream>>>(params, n, chunk, nb, bounds);
+    return cudaGetLastError();
+}
+
 // ---- host-side launchers (called from engine.cu) -------------------------------------------------------
 
 cudaError_t launch_count_used_tiles(int64_t n, int tile_slab, const Tile* slots, int32_t* ntile, cudaStream_t stream) {
