@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -90,6 +91,54 @@ cudaError_t launch_eval_poly(const PolyView& pv, int64_t ntiles, int tile_shift,
 
 namespace {
 
+// Zero-fill on the SMs.  cudaMemsetAsync of a staging buffer this size is executed by a copy engine — the one the
+// other slot's device-to-host copies are queued on — so the memset of chunk c+1, and with it that chunk's planning and
+// evaluation, waited for ALL of chunk c's copies: no overlap at all, 0.46 ms of idle link per 14 ms chunk (events around
+// the copy blocks showed it).  A kernel does not queue behind the copies.
+__global__ void __launch_bounds__(256) zero_fill_kernel(int4* __restrict__ p, size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_int4(0, 0, 0, 0);
+}
+
+// A few dozen bytes from device memory to PINNED host memory, written by an SM instead of a copy engine.  The
+// device-to-host copy engine works through its copies in submission order, so a cudaMemcpyAsync of a plan's 64 bytes of
+// statistics queued behind the 0.8 GB of sample planes the other staging slot was shipping: tgx_plan's host
+// synchronisation then lasted as long as those copies, and the chunks of a host-buffer call never overlapped (events
+// around the copy blocks: every chunk's evaluation finished 0.46 ms AFTER the previous chunk's last copy).
+__global__ void peek_kernel(const unsigned* __restrict__ src, volatile unsigned* __restrict__ host_dst, int words) {
+    for (int i = threadIdx.x; i < words; i += blockDim.x) host_dst[i] = src[i];
+    __threadfence_system();
+}
+
+cudaError_t peek_to_host(const void* d_src, void* h_dst_pinned, size_t bytes, cudaStream_t s) {
+    void* mapped = nullptr;
+    if ((bytes & 3u) || cudaHostGetDevicePointer(&mapped, h_dst_pinned, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return cudaMemcpyAsync(h_dst_pinned, d_src, bytes, cudaMemcpyDeviceToHost, s);
+    }
+    peek_kernel<<<1, 32, 0, s>>>(static_cast<const unsigned*>(d_src), static_cast<volatile unsigned*>(mapped),
+                                 (int)(bytes / 4));
+    return cudaGetLastError();
+}
+
+__global__ void zero_words_kernel(unsigned* __restrict__ p, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+
+cudaError_t zero_fill(void* p, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return cudaSuccess;
+    if ((reinterpret_cast<uintptr_t>(p) & 3u) || (bytes & 3u)) return cudaMemsetAsync(p, 0, bytes, s);
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) || (bytes & 15u)) {
+        const size_t n4 = bytes / 4;
+        zero_words_kernel<<<(unsigned)std::min<size_t>((n4 + 255) / 256, 148 * 8), 256, 0, s>>>(static_cast<unsigned*>(p), n4);
+        return cudaGetLastError();
+    }
+    const size_t n16 = bytes / 16;
+    const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 148 * 16);
+    zero_fill_kernel<<<grid, 256, 0, s>>>(static_cast<int4*>(p), n16);
+    return cudaGetLastError();
+}
+
 thread_local std::string g_last_cuda_error;
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -145,7 +194,7 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         bytes = 0;
-        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
             cudaGetLastError();
             g_last_cuda_error = "cudaHostAlloc(" + std::to_string(want) + " bytes) failed";
             return TGX_ERR_NOMEM;
@@ -268,6 +317,9 @@ struct tgx_engine {
     cpu_set_t filler_cpus;                         // where they run: the allowed CPUs of the GPU's NUMA node
     bool filler_cpus_valid = false;
     DevBuf h_params[2], h_out[2], h_cnt[2], h_st[2], h_ph[2], h_from[2], h_rec[2];
+    DevBuf h_params_all, h_from_all;               // a whole call's parameters, uploaded before the first D2H copy is queued
+    PinBuf p_small;                                // pinned landing area of a call's counts / status / phases / legs
+    cudaEvent_t hev_up = nullptr;
 };
 
 namespace {
@@ -401,12 +453,12 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         if (need_tiles <= 0x7fffffffLL) {
             if ((rc = e->phase.reserve((size_t)n * sizeof(tgx::PhaseRec)))) return rc;
             const int max_n = std::min<int64_t>((int64_t)e->phase_tile_slab << e->tile_shift, tgx::kPhaseMaxSamples);
-            TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+            TGX_CUDA(zero_fill(d_stats, sizeof(tgx::PlanStats), stream));
             TGX_CUDA(tgx::launch_plan_phase(d_params, n, limits, e->max_samples, e->tile_shift, max_n, tab,
                                             e->phase.as<tgx::PhaseRec>(), d_counts, d_status, cnt, st, d_phases,
                                             d_stats, stream));
             e->launches += 1;
-            TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
+            TGX_CUDA(peek_to_host(d_stats, h_stats, sizeof(tgx::PlanStats), stream));
             TGX_CUDA(cudaStreamSynchronize(stream));
             if (!h_stats->overflow) {
                 tot_samples = (int64_t)h_stats->total_samples;
@@ -429,7 +481,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         if (need_segs <= 0x7fffffffLL && need_tiles <= 0x7fffffffLL) {
             if ((rc = e->segs.reserve((size_t)need_segs * sizeof(tgx::Seg)))) return rc;
             if ((rc = e->tiles.reserve((size_t)need_tiles * sizeof(tgx::Tile)))) return rc;
-            TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+            TGX_CUDA(zero_fill(d_stats, sizeof(tgx::PlanStats), stream));
             // A mixed batch is replayed in the order of its replay classes (orbits by number of speed goals, lines,
             // boomerangs): neighbouring lanes then walk the same code instead of diverging at every branch.  One key
             // kernel + a one-pass radix sort of (class, index) pairs; the tables are indexed by trajectory, so the
@@ -458,7 +510,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                                            e->tiles.as<tgx::Tile>(), d_counts, d_status, cnt, st, d_phases, d_stats,
                                            stream, order));
             e->launches += 1;
-            TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
+            TGX_CUDA(peek_to_host(d_stats, h_stats, sizeof(tgx::PlanStats), stream));
             TGX_CUDA(cudaStreamSynchronize(stream));
             const bool sparse = (int64_t)h_stats->total_tiles + (int64_t)h_stats->total_tiles / 4 + 1 < need_tiles;
             if (!h_stats->overflow && sparse) {
@@ -467,7 +519,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                 const int64_t used = (int64_t)h_stats->total_tiles;
                 if ((rc = e->tiles_dense.reserve((size_t)std::max<int64_t>(used, 1) * sizeof(tgx::Tile)))) return rc;
                 TGX_CUDA(tgx::launch_count_used_tiles(n, e->tile_slab, e->tiles.as<tgx::Tile>(), ntile, stream));
-                TGX_CUDA(cudaMemsetAsync(ntile + n, 0, sizeof(int32_t), stream));
+                TGX_CUDA(zero_fill(ntile + n, sizeof(int32_t), stream));
                 WideIter tile_in{ntile};
                 size_t need = 0;
                 TGX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, tile_in, tile_off, (int)(n + 1), stream));
@@ -510,8 +562,8 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
                                         e->exact_ramps, tab, cnt, st, nseg, ntile, stream));
         e->launches += 1;
         // trailing zero so that an exclusive scan over n+1 items leaves the grand total in element n
-        TGX_CUDA(cudaMemsetAsync(nseg + n, 0, sizeof(int32_t), stream));
-        TGX_CUDA(cudaMemsetAsync(ntile + n, 0, sizeof(int32_t), stream));
+        TGX_CUDA(zero_fill(nseg + n, sizeof(int32_t), stream));
+        TGX_CUDA(zero_fill(ntile + n, sizeof(int32_t), stream));
 
         // pass 2: exclusive scans (segment and tile offsets) and the sample total
         WideIter seg_in{nseg}, tile_in{ntile}, cnt_in{cnt};
@@ -529,9 +581,9 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         // (the cub scan / reduce launches are library plumbing and are not counted in tgx_launch_count)
 
         int64_t* h = static_cast<int64_t*>(e->h_totals.p);
-        TGX_CUDA(cudaMemcpyAsync(h + 0, totals, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-        TGX_CUDA(cudaMemcpyAsync(h + 1, seg_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-        TGX_CUDA(cudaMemcpyAsync(h + 2, tile_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        TGX_CUDA(peek_to_host(totals, h + 0, sizeof(int64_t), stream));
+        TGX_CUDA(peek_to_host(seg_off + n, h + 1, sizeof(int64_t), stream));
+        TGX_CUDA(peek_to_host(tile_off + n, h + 2, sizeof(int64_t), stream));
         TGX_CUDA(cudaStreamSynchronize(stream));
         tot_samples = h[0];
         tot_segs = h[1];
@@ -542,7 +594,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         if ((rc = e->tiles.reserve((size_t)std::max<int64_t>(tot_tiles, 1) * sizeof(tgx::Tile)))) return rc;
 
         // pass 3: fill (also measures the per-trajectory maxima that size the slabs of the next plan)
-        TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+        TGX_CUDA(zero_fill(d_stats, sizeof(tgx::PlanStats), stream));
         TGX_CUDA(tgx::launch_plan_fill(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
                                        tab, cnt, seg_off, tile_off, 0, 0, e->recs.as<tgx::TrajRec>(),
                                        e->segs.as<tgx::Seg>(), e->tiles.as<tgx::Tile>(), d_counts, d_status, nullptr,
@@ -550,7 +602,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         e->launches += 1;
         e->exact_plans += 1;
         if (e->allow_slabs) {
-            TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
+            TGX_CUDA(peek_to_host(d_stats, h_stats, sizeof(tgx::PlanStats), stream));
             TGX_CUDA(cudaStreamSynchronize(stream));
             relearn(tot_tiles);
         }
@@ -592,11 +644,11 @@ int plan_polyline_common(tgx_engine* e, const tgx_params* d_params, int64_t n, c
     tgx::PlanStats* h_stats = reinterpret_cast<tgx::PlanStats*>(static_cast<int64_t*>(e->h_totals.p) + 4);
 
     TGX_CUDA(tgx::launch_build_cur_table(d_params, e->max_samples, e->cur_table.p, stream));
-    TGX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(tgx::PlanStats), stream));
+    TGX_CUDA(zero_fill(d_stats, sizeof(tgx::PlanStats), stream));
     TGX_CUDA(tgx::launch_plan_poly(d_params, n, limits, e->max_samples, e->tile_shift, e->cur_table.p, e->poly_recs.p,
                                    d_counts, d_status, cnt, st, d_legs, ntile, d_stats, skip_foreign, stream));
     e->launches += 2;
-    TGX_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(tgx::PlanStats), cudaMemcpyDeviceToHost, stream));
+    TGX_CUDA(peek_to_host(d_stats, h_stats, sizeof(tgx::PlanStats), stream));
     TGX_CUDA(cudaStreamSynchronize(stream));
     const int64_t tot_tiles = (int64_t)h_stats->total_tiles;
     const int64_t slab_tiles = n * (int64_t)h_stats->max_ntile;
@@ -608,7 +660,7 @@ int plan_polyline_common(tgx_engine* e, const tgx_params* d_params, int64_t n, c
     } else {
         if (tot_tiles > 0x7fffffffLL) return TGX_ERR_CAPACITY;
         int64_t* tile_off = e->tile_off.as<int64_t>();
-        TGX_CUDA(cudaMemsetAsync(ntile + n, 0, sizeof(int32_t), stream));
+        TGX_CUDA(zero_fill(ntile + n, sizeof(int32_t), stream));
         WideIter tile_in{ntile};
         size_t need = 0;
         TGX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, tile_in, tile_off, (int)(n + 1), stream));
@@ -881,6 +933,10 @@ int tgx_destroy(tgx_engine* e) {
         if (e->hev[i]) cudaEventDestroy(e->hev[i]);
     }
     if (e->hev_eval) cudaEventDestroy(e->hev_eval);
+    if (e->hev_up) cudaEventDestroy(e->hev_up);
+    e->h_params_all.release();
+    e->h_from_all.release();
+    e->p_small.release();
     e->h_totals.release();
     delete e;
     return TGX_OK;
@@ -1078,8 +1134,8 @@ int tgx_eval(tgx_engine* e, const tgx_layout* out, double* d_max_v, double* d_ma
     TGX_CUDA(cudaSetDevice(e->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (e->plan_n == 0) return TGX_OK;
-    if (d_max_v) TGX_CUDA(cudaMemsetAsync(d_max_v, 0, (size_t)e->plan_n * sizeof(double), s));
-    if (d_max_a) TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)e->plan_n * sizeof(double), s));
+    if (d_max_v) TGX_CUDA(zero_fill(d_max_v, (size_t)e->plan_n * sizeof(double), s));
+    if (d_max_a) TGX_CUDA(zero_fill(d_max_a, (size_t)e->plan_n * sizeof(double), s));
     if (e->plan_tiles == 0) return TGX_OK;
     tgx::RecOut ptma{};
     // (the polyline kernel has no per-sample transcendental and is faster with vector stores: 17.0 vs 17.7 ms per Mi
@@ -1107,8 +1163,8 @@ int tgx_feasibility(tgx_engine* e, const tgx_limits* limits, uint8_t* d_flags, d
         if ((rc = e->maxa.reserve((size_t)n * sizeof(double)))) return rc;
         d_max_a = e->maxa.as<double>();
     }
-    TGX_CUDA(cudaMemsetAsync(d_max_v, 0, (size_t)n * sizeof(double), s));
-    TGX_CUDA(cudaMemsetAsync(d_max_a, 0, (size_t)n * sizeof(double), s));
+    TGX_CUDA(zero_fill(d_max_v, (size_t)n * sizeof(double), s));
+    TGX_CUDA(zero_fill(d_max_a, (size_t)n * sizeof(double), s));
     if (e->plan_tiles > 0) {
         tgx::OutView none{};
         TGX_CUDA(launch_current(e, none, false, d_max_v, d_max_a, s));
@@ -1608,6 +1664,7 @@ static int host_streams(tgx_engine* e) {
         if (!e->hev[i]) TGX_CUDA(cudaEventCreateWithFlags(&e->hev[i], cudaEventDisableTiming));
     }
     if (!e->hev_eval) TGX_CUDA(cudaEventCreateWithFlags(&e->hev_eval, cudaEventDisableTiming));
+    if (!e->hev_up) TGX_CUDA(cudaEventCreateWithFlags(&e->hev_up, cudaEventDisableTiming));
     return TGX_OK;
 }
 
@@ -1762,6 +1819,50 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
     } joiner{fillers};
 
+    // The parameters of the whole call go up FIRST, in one copy.  On these boxes a host-to-device copy queued while
+    // device-to-host copies are in flight waits for them (events around the copy blocks: every chunk's H2D, and with it
+    // its planning and evaluation, started when the previous chunk's last D2H copy had finished — 0.47 ms of idle link
+    // per 14 ms chunk), so per-chunk uploads defeat the double buffering.  Up to 1 GiB of records (8 Mi trajectories);
+    // larger calls keep the per-chunk uploads.
+    const bool upfront = (size_t)n * sizeof(tgx_params) <= ((size_t)1 << 30);
+    std::vector<tgx_params> staged_all;
+    if (upfront) {
+        if ((rc = e->h_params_all.reserve((size_t)n * sizeof(tgx_params)))) return rc;
+        const tgx_params* src_all = stage_params(h_params, n, staged_all, nullptr);
+        TGX_CUDA(cudaMemcpyAsync(e->h_params_all.p, src_all, (size_t)n * sizeof(tgx_params), cudaMemcpyHostToDevice, e->hs[0]));
+        if (h_from) {
+            if ((rc = e->h_from_all.reserve((size_t)n * TGX_NCHAN * sizeof(double)))) return rc;
+            TGX_CUDA(cudaMemcpyAsync(e->h_from_all.p, h_from, (size_t)n * TGX_NCHAN * sizeof(double), cudaMemcpyHostToDevice,
+                                     e->hs[0]));
+        }
+        TGX_CUDA(cudaEventRecord(e->hev_up, e->hs[0]));
+        TGX_CUDA(cudaStreamWaitEvent(e->hs[1], e->hev_up, 0));
+        if (!staged_all.empty()) TGX_CUDA(cudaEventSynchronize(e->hev_up));      // (the staged copy is a local)
+    }
+    // The per-trajectory results (counts, status, index_msgs, legs) land in PINNED memory of the engine and are handed to
+    // the caller's arrays after the last chunk.  The caller's arrays are ordinary pageable memory, and a
+    // cudaMemcpyAsync into pageable memory does not return before everything queued on its stream has finished: with
+    // those four small copies queued behind a chunk's sample planes the host sat out every chunk's copies (14 ms)
+    // before it could queue the next chunk, and the two staging slots never overlapped.
+    const size_t small_bytes = (size_t)n * (sizeof(int32_t) + sizeof(uint32_t) + (h_phases ? sizeof(tgx_phases) : 0) +
+                                            (h_legs ? sizeof(tgx_polyline_legs) : 0));
+    if ((rc = e->p_small.reserve(small_bytes + 64))) return rc;
+    // (8-byte alignment of every part: phases and legs first)
+    char* sp = static_cast<char*>(e->p_small.p);
+    tgx_phases* p_ph = reinterpret_cast<tgx_phases*>(sp);
+    sp += h_phases ? (size_t)n * sizeof(tgx_phases) : 0;
+    tgx_polyline_legs* p_legs = reinterpret_cast<tgx_polyline_legs*>(sp);
+    sp += h_legs ? (size_t)n * sizeof(tgx_polyline_legs) : 0;
+    int32_t* p_cnt = reinterpret_cast<int32_t*>(sp);
+    sp += (size_t)n * sizeof(int32_t);
+    uint32_t* p_st = reinterpret_cast<uint32_t*>(sp);
+    static const bool trace = std::getenv("TGX_TRACE_D2H") != nullptr;
+    std::vector<cudaEvent_t> tr_a, tr_b;
+    std::vector<double> tr_host;
+    const auto tr_t0 = std::chrono::steady_clock::now();
+    auto tr_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr_t0).count(); };
+    cudaEvent_t tr_0 = nullptr;
+    if (trace) { cudaEventCreate(&tr_0); cudaEventRecord(tr_0, e->hs[0]); }
     for (int64_t ci = 0, lo = 0, m = 0; lo < n; ++ci, lo += m) {
         const int b = (int)(ci & 1);
         cudaStream_t s = e->hs[b];
@@ -1774,14 +1875,26 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         if (ci >= 1) TGX_CUDA(cudaStreamWaitEvent(s, e->hev_eval, 0));
         KindMix mix;
         std::vector<tgx_params> staged;
-        const tgx_params* src = stage_params(h_params + lo, m, staged, &mix);
-        TGX_CUDA(cudaMemcpyAsync(e->h_params[b].p, src, (size_t)m * sizeof(tgx_params), cudaMemcpyHostToDevice, s));
-        if (h_from)
-            TGX_CUDA(cudaMemcpyAsync(e->h_from[b].p, h_from + lo * TGX_NCHAN, (size_t)m * TGX_NCHAN * sizeof(double),
-                                     cudaMemcpyHostToDevice, s));
+        const tgx_params* d_par = e->h_params[b].as<tgx_params>();
+        const double* d_from = h_from ? e->h_from[b].as<double>() : nullptr;
+        if (upfront) {
+            for (int64_t q = lo; q < lo + m; ++q) {
+                const int ty = h_params[q].type;
+                if (TGX_IS_POLYLINE(ty)) { mix.poly = true; if (ty == TGX_BOUNCE) mix.bounce = true; }
+                else mix.classic = true;
+            }
+            d_par = e->h_params_all.as<tgx_params>() + lo;
+            if (h_from) d_from = e->h_from_all.as<double>() + lo * TGX_NCHAN;
+        } else {
+            const tgx_params* src = stage_params(h_params + lo, m, staged, &mix);
+            TGX_CUDA(cudaMemcpyAsync(e->h_params[b].p, src, (size_t)m * sizeof(tgx_params), cudaMemcpyHostToDevice, s));
+            if (h_from)
+                TGX_CUDA(cudaMemcpyAsync(e->h_from[b].p, h_from + lo * TGX_NCHAN, (size_t)m * TGX_NCHAN * sizeof(double),
+                                         cudaMemcpyHostToDevice, s));
+        }
         tgx_phases* d_ph = h_phases ? e->h_ph[b].as<tgx_phases>() : nullptr;
         tgx_polyline_legs* d_legs = h_legs ? e->h_legs[b].as<tgx_polyline_legs>() : nullptr;
-        if (d_legs) TGX_CUDA(cudaMemsetAsync(d_legs, 0, (size_t)m * sizeof(tgx_polyline_legs), s));
+        if (d_legs) TGX_CUDA(zero_fill(d_legs, (size_t)m * sizeof(tgx_polyline_legs), s));
         tgx_layout lay{};
         lay.d_base = e->h_out[b].as<double>();
         lay.traj_stride = plane_major ? capacity : TGX_NCHAN * capacity;
@@ -1790,11 +1903,12 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         lay.channel_mask = fill ? kVaryingChannels : 0;
         // the staging buffers are reused from call to call: clear the slot so that the padding (k >= N_i, and every
         // row of a rejected trajectory) reaches the caller as zeros, not as an earlier call's samples or records
-        // (a device memset at HBM rate: ~0.15 ms per GiB against ~20 ms of PCIe time for the same bytes)
+        // (a zero-fill KERNEL at HBM rate, ~0.2 ms per GiB against ~20 ms of PCIe time for the same bytes — not
+        //  cudaMemsetAsync, which a copy engine executes behind the other slot's device-to-host copies: zero_fill above)
         if (capacity > 0 && h_records)
-            TGX_CUDA(cudaMemsetAsync(e->h_rec[b].p, 0, (size_t)(m * capacity) * sizeof(tgx_goal_record), s));
+            TGX_CUDA(zero_fill(e->h_rec[b].p, (size_t)(m * capacity) * sizeof(tgx_goal_record), s));
         else if (capacity > 0)
-            TGX_CUDA(cudaMemsetAsync(e->h_out[b].p, 0, (size_t)(m * row_bytes), s));
+            TGX_CUDA(zero_fill(e->h_out[b].p, (size_t)(m * row_bytes), s));
         // planning synchronises stream s once; the other slot's D2H copies keep running meanwhile.  Braking plans take
         // every family in one pass; generateTraj plans route each family to its own planner (a mixed chunk is planned
         // and evaluated twice, each pass writing only its own trajectories' rows).
@@ -1802,25 +1916,25 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
         const bool pass_poly = !h_from && mix.poly;
         if (pass_classic) {
             if (h_from)
-                rc = tgx_plan_stop(e, e->h_params[b].as<tgx_params>(), m, e->h_from[b].as<double>(),
-                                   e->h_cnt[b].as<int32_t>(), e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
+                rc = tgx_plan_stop(e, d_par, m, d_from, e->h_cnt[b].as<int32_t>(), e->h_st[b].as<uint32_t>(), d_ph,
+                                   nullptr, s);
             else
-                rc = tgx_plan(e, e->h_params[b].as<tgx_params>(), m, limits, e->h_cnt[b].as<int32_t>(),
-                              e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
+                rc = tgx_plan(e, d_par, m, limits, e->h_cnt[b].as<int32_t>(), e->h_st[b].as<uint32_t>(), d_ph, nullptr, s);
             if (rc) return rc;
             if (capacity > 0 && (rc = eval_chunk(e, &lay, limits, h_records ? e->h_rec[b].as<tgx_goal_record>() : nullptr,
                                                  capacity, s)))
                 return rc;
         }
         if (pass_poly) {
-            if (d_ph && !pass_classic) TGX_CUDA(cudaMemsetAsync(d_ph, 0, (size_t)m * sizeof(tgx_phases), s));
-            rc = plan_polyline_common(e, e->h_params[b].as<tgx_params>(), m, limits, e->h_cnt[b].as<int32_t>(),
-                                      e->h_st[b].as<uint32_t>(), d_legs, nullptr, pass_classic, s);
+            if (d_ph && !pass_classic) TGX_CUDA(zero_fill(d_ph, (size_t)m * sizeof(tgx_phases), s));
+            rc = plan_polyline_common(e, d_par, m, limits, e->h_cnt[b].as<int32_t>(), e->h_st[b].as<uint32_t>(), d_legs,
+                                      nullptr, pass_classic, s);
             if (rc) return rc;
             if (capacity > 0 && (rc = eval_chunk(e, &lay, limits, h_records ? e->h_rec[b].as<tgx_goal_record>() : nullptr,
                                                  capacity, s)))
                 return rc;
         }
+        if (trace) { cudaEvent_t a; cudaEventCreate(&a); cudaEventRecord(a, s); tr_a.push_back(a); tr_host.push_back(tr_now()); }
         if (capacity > 0 && h_records) {
             TGX_CUDA(cudaEventRecord(e->hev_eval, s));
             TGX_CUDA(cudaMemcpyAsync(h_records + lo * capacity, e->h_rec[b].p,
@@ -1854,24 +1968,39 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
                                          cudaMemcpyDeviceToHost, s));
             }
         }
-        if (h_counts)
-            TGX_CUDA(cudaMemcpyAsync(h_counts + lo, e->h_cnt[b].p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        if (h_status)
-            TGX_CUDA(cudaMemcpyAsync(h_status + lo, e->h_st[b].p, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TGX_CUDA(cudaMemcpyAsync(p_cnt + lo, e->h_cnt[b].p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        TGX_CUDA(cudaMemcpyAsync(p_st + lo, e->h_st[b].p, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (h_phases)
-            TGX_CUDA(cudaMemcpyAsync(h_phases + lo, e->h_ph[b].p, (size_t)m * sizeof(tgx_phases), cudaMemcpyDeviceToHost, s));
+            TGX_CUDA(cudaMemcpyAsync(p_ph + lo, e->h_ph[b].p, (size_t)m * sizeof(tgx_phases), cudaMemcpyDeviceToHost, s));
         if (h_legs)
-            TGX_CUDA(cudaMemcpyAsync(h_legs + lo, e->h_legs[b].p, (size_t)m * sizeof(tgx_polyline_legs),
+            TGX_CUDA(cudaMemcpyAsync(p_legs + lo, e->h_legs[b].p, (size_t)m * sizeof(tgx_polyline_legs),
                                      cudaMemcpyDeviceToHost, s));
         TGX_CUDA(cudaEventRecord(e->hev[b], s));
+        if (trace) { cudaEvent_t z; cudaEventCreate(&z); cudaEventRecord(z, s); tr_b.push_back(z); tr_host.push_back(tr_now()); }
     }
     TGX_CUDA(cudaStreamSynchronize(e->hs[0]));
     TGX_CUDA(cudaStreamSynchronize(e->hs[1]));
+    if (trace) {
+        float t_prev_end = 0.f;
+        for (size_t q = 0; q < tr_a.size(); ++q) {
+            float ta = 0.f, tb = 0.f;
+            cudaEventElapsedTime(&ta, tr_0, tr_a[q]);
+            cudaEventElapsedTime(&tb, tr_0, tr_b[q]);
+            std::fprintf(stderr, "[tgx d2h] chunk %zu: eval done %.3f ms, copies done %.3f ms (%.3f ms after the previous chunk's); host: eval queued %.3f, copies queued %.3f\n",
+                         q, ta, tb, tb - t_prev_end, tr_host[2 * q], tr_host[2 * q + 1]);
+            t_prev_end = tb;
+            cudaEventDestroy(tr_a[q]);
+            cudaEventDestroy(tr_b[q]);
+        }
+        cudaEventDestroy(tr_0);
+    }
     for (auto& x : fillers) x.join();
-    // TRUNCATED is a property of the caller's capacity, known only here
-    if (h_status && h_counts)
-        for (int64_t i = 0; i < n; ++i)
-            if ((int64_t)h_counts[i] > capacity) h_status[i] |= TGX_ST_TRUNCATED;
+    // hand the per-trajectory results over; TRUNCATED is a property of the caller's capacity, known only here
+    if (h_status)
+        for (int64_t i = 0; i < n; ++i) h_status[i] = p_st[i] | ((int64_t)p_cnt[i] > capacity ? (uint32_t)TGX_ST_TRUNCATED : 0u);
+    if (h_counts) std::memcpy(h_counts, p_cnt, (size_t)n * sizeof(int32_t));
+    if (h_phases) std::memcpy(h_phases, p_ph, (size_t)n * sizeof(tgx_phases));
+    if (h_legs) std::memcpy(h_legs, p_legs, (size_t)n * sizeof(tgx_polyline_legs));
     return TGX_OK;
 }
 
