@@ -1743,6 +1743,7 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
                     uint32_t* h_status, tgx_phases* h_phases, tgx_polyline_legs* h_legs,
                     tgx_goal_record* h_records = nullptr, bool compact = false) {
     // h_records != nullptr: the samples stay on the device; what travels is one clamped 128-byte record per sample
+    const auto t_entry = std::chrono::steady_clock::now();
     if (!e || n < 0 || (n > 0 && (!h_params || (!h_out && !h_records))) || capacity < 0) return TGX_ERR_INVALID;
     if (capacity % 4 != 0) return TGX_ERR_ALIGNMENT;
     if (n == 0) return TGX_OK;
@@ -2001,6 +2002,17 @@ static int host_run(tgx_engine* e, const tgx_params* h_params, const double* h_f
     if (h_counts) std::memcpy(h_counts, p_cnt, (size_t)n * sizeof(int32_t));
     if (h_phases) std::memcpy(h_phases, p_ph, (size_t)n * sizeof(tgx_phases));
     if (h_legs) std::memcpy(h_legs, p_legs, (size_t)n * sizeof(tgx_polyline_legs));
+    if (trace) {
+        static std::chrono::steady_clock::time_point last_return;
+        static bool have_last = false;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[tgx d2h] call: %.3f ms inside (tracing starts %.3f ms after entry), %.3f ms since the previous call returned\n",
+                     std::chrono::duration<double, std::milli>(now - t_entry).count(),
+                     std::chrono::duration<double, std::milli>(tr_t0 - t_entry).count(),
+                     have_last ? std::chrono::duration<double, std::milli>(t_entry - last_return).count() : 0.0);
+        last_return = now;
+        have_last = true;
+    }
     return TGX_OK;
 }
 
