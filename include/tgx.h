@@ -497,8 +497,12 @@ int tgx_count_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const t
 
 /* Full generateTraj for host-resident parameters into a host buffer with the layout
  * h_out[(i*14 + c)*capacity + k] (trajectory-major rows of `capacity` doubles).  Runs in chunks of
- * trajectories so that device staging stays bounded, overlapping D2H copies with evaluation.
- * h_phases may be NULL. */
+ * trajectories through two device staging slots: while one slot's planes travel to the host, the next chunk is
+ * planned and evaluated into the other.  h_out is best page-locked (tgx_alloc_host_for); h_params, h_counts, h_status,
+ * h_phases may be ordinary memory — the parameters go up in one copy at the start of the call and the per-trajectory
+ * results are handed over from a pinned area of the engine at its end, so nothing pageable sits between two chunks'
+ * copies (it would serialise them).  TGX_TRACE_D2H=1 in the environment prints, per call, when every chunk's
+ * evaluation and copies finished and when the host queued them.  h_phases may be NULL. */
 int tgx_generate_host(tgx_engine* e, const tgx_params* h_params, int64_t n, const tgx_limits* limits,
                       double* h_out, int64_t capacity, int32_t* h_counts, uint32_t* h_status,
                       tgx_phases* h_phases);
