@@ -942,7 +942,7 @@ def test_phase_planning(engine, oracle):
     o_flags, o_mv, o_ma, _, o_st = oracle.feasibility_batch(params, lim)
     np.testing.assert_allclose(mv.cpu().numpy(), o_mv, rtol=1e-8, atol=1e-14)
     np.testing.assert_allclose(ma.cpu().numpy(), o_ma, rtol=1e-8, atol=1e-14)
-    # trajectories of two and three tiles: every tile is its own CTA of the phase plan
+    # trajectories of two and three tiles: the trajectory's CTA walks all of them
     long_ones = abi.concat([abi.circle_params(1.0, rng.uniform(1, 3), 0, 0, [rng.uniform(0.8, 1.5)],
                                               rng.uniform(15.0, 25.0), 0.5, 0.01) for _ in range(40)])
     l1, _, _, _ = gpu_generate(engine, long_ones, want_phases=False)
@@ -969,6 +969,88 @@ def test_phase_planning(engine, oracle):
         for i in range(max(0, len(mixed) - 3), len(mixed)):
             ref, _, _ = oracle.generate(mixed[i:i + 1])
             assert_samples_close(out2[i, :, :c2[i]], ref, f"{what}[{i}] after phase fallback")
+
+
+def test_phase_planning_of_lines_and_ragged_mixed_batches(engine, oracle):
+    """Plain lines have a phase-record form too (ramp, cruise, ramp, forced end point), and a phase plan has no tile slots:
+    BASELINE.json config 3's mix of lines, circles and figure-eights of 600 .. 3000 samples is planned that way, and the
+    samples, maxima and goal records are the same BYTES as the segment-table path's."""
+    import torch
+    rng = np.random.default_rng(23)
+    edge = [
+        workloads.default_line(),
+        abi.line_params(1.0, [0, 0, 1], [0.3, 0.1, 1], [2.0], 1.0, 1.0, 0.01),        # d2 < 0: no cruise, ends short of B
+        abi.line_params(1.0, [0, 0, 1], [3, 4, 1], [1.0], 200.0, 1.0, 0.01),          # the ramp-up is one clamped step
+        abi.line_params(1.0, [0, 0, 1], [3, 4, 1], [1.0], 1.0, 200.0, 0.01),          # the ramp-down is the forced step alone
+        abi.line_params(1.0, [1, 1, 1], [-20, 1, 1], [1.0], 0.7, 0.9, 0.01),          # cruise > kRebase steps: two hold segments
+        abi.line_params(1.0, [0, 0, 1], [1, 1, 1], [1.0], 0.0, 1.0, 0.01),            # rejected (a1 = 0)
+        abi.line_params(0.5, [2, -1, 0.5], [2, -1, 0.5], [1.0], 1.0, 1.0, 0.01),      # A == B
+    ]
+    for _ in range(20):
+        A = rng.uniform(-4, 4, 3)
+        B = A + rng.uniform(-6, 6, 3)
+        edge.append(abi.line_params(rng.uniform(0.5, 2), A, B, [rng.uniform(0.3, 2.5)], rng.uniform(0.3, 3),
+                                    rng.uniform(0.3, 3), 0.01))
+    params = abi.concat([workloads.mixed_cfg3(600)] + edge + [_short_orbit_batch(rng)[:300]])
+    n = len(params)
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+
+    def run(phase):
+        engine.set_phase_planning(phase)
+        for _ in range(2):                                       # the second plan takes the learned path
+            before = engine.phase_plan_count
+            out, counts, status, ph = gpu_generate(engine, params, want_phases=True)
+        took_phase = engine.phase_plan_count - before == 1
+        d = engine.upload_params(params)
+        engine.plan(d, limits=lim)
+        _, mv, ma, fst = engine.feasibility(lim, n)
+        recs = engine.eval_records(n, 1100, limits=lim)                 # (rows shorter than the longest trajectories)
+        torch.cuda.synchronize()
+        return took_phase, out, counts, status, ph, mv.cpu().numpy(), ma.cpu().numpy(), fst.cpu().numpy(), recs.cpu().numpy()
+
+    try:
+        t_phase, t_out, t_counts, t_status, t_ph, t_mv, t_ma, t_fst, t_recs = run(False)
+        assert not t_phase
+        p_phase, out, counts, status, ph, mv, ma, fst, recs = run(True)
+        assert p_phase, "a batch of plain lines and short orbits should be planned as phase records"
+    finally:
+        engine.set_phase_planning(True)
+    assert counts.min() == 0 and counts.max() > 2048 and np.ptp(counts[counts > 0]) > 1500      # rejected, long, ragged
+    o_counts, o_status = oracle.count_batch(params)
+    np.testing.assert_array_equal(counts, o_counts)
+    np.testing.assert_array_equal(status, o_status)
+    np.testing.assert_array_equal(t_counts, counts)
+    np.testing.assert_array_equal(t_status, status)
+    m = ~np.isnan(t_out)
+    assert (np.isnan(out) == ~m).all()
+    np.testing.assert_array_equal(out[m], t_out[m])                               # same bytes as the table path
+    np.testing.assert_array_equal(mv, t_mv)
+    np.testing.assert_array_equal(ma, t_ma)
+    np.testing.assert_array_equal(fst, t_fst)
+    for i in range(n):
+        np.testing.assert_array_equal(recs[i, :min(counts[i], 1100)], t_recs[i, :min(counts[i], 1100)])
+    np.testing.assert_array_equal(ph["n"], t_ph["n"])
+    for i in range(n):                                                            # (slots beyond n are not written)
+        for f in ("key", "kind", "value", "value2"):
+            np.testing.assert_array_equal(ph[f][i, :ph["n"][i]], t_ph[f][i, :ph["n"][i]])
+    worst = {}
+    for i in list(range(0, 600, 17)) + list(range(600, 600 + len(edge))):
+        ref, _, oph = oracle.generate(params[i:i + 1])
+        assert ref.shape[1] == counts[i]
+        if counts[i] == 0:
+            continue
+        merge_errors(worst, assert_samples_close(out[i, :, :counts[i]], ref, f"phase mixed[{i}]"))
+        t = int(params["type"][i])
+        assert abi.phases_to_index_msgs(t, ph[i]) == abi.phases_to_index_msgs(t, oph)
+    assert worst["pos_abs"] < 1e-10, worst
+    # a boomerang has no phase-record form: such a batch keeps to segment tables, every time
+    p0 = engine.phase_plan_count
+    withb = abi.concat([params[:200], abi.boomerang_params(1.0, [0, 0, 1], [3, 4, 1], [1.0], 1.0, 1.0, 0.01)])
+    for _ in range(3):
+        out2, c2, _, _ = gpu_generate(engine, withb, want_phases=False)
+    assert engine.phase_plan_count == p0
+    ref, _, _ = oracle.generate(withb[-1:])
+    assert_samples_close(out2[-1, :, :c2[-1]], ref, "boomerang after phase fallback")
 
 
 def test_results_do_not_depend_on_the_engines_history(engine, oracle):

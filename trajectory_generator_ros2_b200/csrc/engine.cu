@@ -51,9 +51,9 @@ cudaError_t launch_count_used_tiles(int64_t n, int tile_slab, const Tile* slots,
 cudaError_t launch_compact_tiles(int64_t n, int tile_slab, const Tile* slots, const int64_t* tile_off, Tile* dense,
                                  cudaStream_t stream);
 cudaError_t launch_plan_phase(const tgx_params* params, int64_t n, const tgx_limits* lim, int64_t max_samples,
-                              int tile_shift, int max_n, const void* cur_table, PhaseRec* phase, int32_t* counts,
-                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
-                              PlanStats* stats, cudaStream_t stream);
+                              int tile_shift, int max_n, const void* cur_table, PhaseRec* phase, PhaseExt* phase_ext,
+                              int32_t* counts, uint32_t* status, int32_t* counts2, uint32_t* status2,
+                              tgx_phases* phases, PlanStats* stats, cudaStream_t stream, const int32_t* order);
 cudaError_t launch_eval(const TableView& tv, int64_t ntiles, int tile_shift, int spt, const OutView& out, bool store,
                         double* max_v, double* max_a, cudaStream_t stream, const RecOut* ptma = nullptr);
 cudaError_t launch_feasibility_finalize(int64_t n, const uint32_t* plan_status, const double* max_v,
@@ -261,13 +261,13 @@ struct tgx_engine {
     // swapped in for the duration of such a plan (LearnSwap in plan_common)
     struct Learned {
         bool slabs_ready = false, ragged_ready = false, mixed_batch = false, phase_ready = false;
-        int seg_slab = 0, tile_slab = 0, phase_tile_slab = 0;
+        int seg_slab = 0, tile_slab = 0;
     } stop_learn;
 
     // per-trajectory scratch (capacity in trajectories)
     DevBuf cnt, nseg, ntile, status, seg_off, tile_off, recs, maxv, maxa, cub_tmp, totals, cur_table, stats;
     // tables
-    DevBuf segs, tiles, packets, phase, tiles_dense;
+    DevBuf segs, tiles, packets, phase, phase_ext, tiles_dense;
     DevBuf order;                       // replay order of a mixed batch: keys in/out, indices in/out (10 bytes each)
     bool mixed_batch = false;           // the last plan saw more than one replay class: sort the next one by class
     bool plan_packed = false;                    // current plan is a slab plan
@@ -275,7 +275,12 @@ struct tgx_engine {
     bool allow_phase = true;
     bool plane_tma = true;              // tgx_eval may send the planes through TMA (tgx_set_store_path)
     bool phase_ready = false;
-    int phase_tile_slab = 0;
+    // Which kernels consumed the current plan.  A plan that only fed the reduction kernel (feasibility sweeps) makes the
+    // next plan prefer segment tables over phase records: that kernel is issue-bound, and rebuilding the segments from
+    // a phase record costs it 2 % more instructions than copying them from a table (ncu, 10^6 config-4 circles: 3.32 vs
+    // 3.22 G warp instructions, 4.17 vs 4.08 ms), more than the phase plan saves in planning time.  The store kernels
+    // are HBM-bound and gain from the record's single round of loads.  Speed only: the samples do not depend on it.
+    bool plan_stored = false, plan_reduced = false, reduce_only = false;
     int64_t phase_plans = 0;
     PinBuf h_totals;
 
@@ -331,6 +336,7 @@ tgx::TableView table_view(const tgx_engine* e) {
     tv.tiles = e->plan_dense_tiles ? e->tiles_dense.as<tgx::Tile>() : e->tiles.as<tgx::Tile>();
     if (e->plan_phase) {
         tv.phase = e->phase.as<tgx::PhaseRec>();
+        tv.phase_ext = e->phase_ext.as<tgx::PhaseExt>();
         tv.tile_slab = e->tile_slab_plan;
     } else if (e->plan_packed) {
         tv.seg_slab = e->seg_slab_plan;
@@ -363,6 +369,8 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
     if (!e || n < 0 || (n > 0 && !d_params)) return TGX_ERR_INVALID;
     if (n > 0x7fffffffLL) return TGX_ERR_INVALID;
     TGX_CUDA(cudaSetDevice(e->device));
+    if (e->plan_stored || e->plan_reduced) e->reduce_only = !e->plan_stored;
+    e->plan_stored = e->plan_reduced = false;
     e->has_plan = false;
     e->plan_poly = false;
     e->plan_n = e->plan_tiles = e->plan_segs = e->plan_samples = 0;
@@ -386,7 +394,6 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
             std::swap(e->phase_ready, L.phase_ready);
             std::swap(e->seg_slab, L.seg_slab);
             std::swap(e->tile_slab, L.tile_slab);
-            std::swap(e->phase_tile_slab, L.phase_tile_slab);
         }
         LearnSwap(tgx_engine* e_, bool on_) : e(e_), on(on_) { if (on) swap(); }
         ~LearnSwap() { if (on) swap(); }
@@ -439,39 +446,70 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         e->seg_slab = seg_slab;
         e->tile_slab = tile_slab;
         // phase records: every trajectory of the batch can be written as a PhaseRec (the fill pass checked)
-        e->phase_ready = e->allow_phase && !e->exact_ramps && dense && !h_stats->phase_misfit && h_stats->max_n > 0;
-        e->phase_tile_slab = tile_slab;
+        // (dense or ragged: a phase plan has no tile slots, one CTA walks a whole trajectory).  Records that spill into
+        // PhaseExt rows cost their CTAs a second round of loads and a longer rebuild: worth it against the two dependent
+        // rounds of a ragged batch's work list, not against fixed slices (10^7 config-4 circles of up to 18 segments: slices
+        // 46.3 ms per step, phase records 47.2 ms — the reduction kernel is issue-bound and pays for the rebuild)
+        const bool spills = h_stats->max_nseg > tgx::kPhaseBaseSegs;
+        e->phase_ready = e->allow_phase && !e->exact_ramps && !h_stats->phase_misfit && h_stats->max_n > 0 &&
+                         !(spills && e->slabs_ready);
         e->mixed_batch = (h_stats->kinds & (h_stats->kinds - 1)) != 0;      // more than one replay class
     };
     e->plan_phase = false;
     e->plan_dense_tiles = false;
 
-    // ---- phase mode: batches of short orbits.  One replay that writes a self-contained 160-byte record per trajectory
-    //      instead of tables; the evaluation kernel rebuilds the table path's segments from it, bit for bit ----
-    if (e->allow_phase && e->phase_ready && !e->exact_ramps && !d_stop_from) {
-        const int64_t need_tiles = n * (int64_t)e->phase_tile_slab;
-        if (need_tiles <= 0x7fffffffLL) {
-            if ((rc = e->phase.reserve((size_t)n * sizeof(tgx::PhaseRec)))) return rc;
-            const int max_n = std::min<int64_t>((int64_t)e->phase_tile_slab << e->tile_shift, tgx::kPhaseMaxSamples);
-            TGX_CUDA(zero_fill(d_stats, sizeof(tgx::PlanStats), stream));
-            TGX_CUDA(tgx::launch_plan_phase(d_params, n, limits, e->max_samples, e->tile_shift, max_n, tab,
-                                            e->phase.as<tgx::PhaseRec>(), d_counts, d_status, cnt, st, d_phases,
-                                            d_stats, stream));
-            e->launches += 1;
-            TGX_CUDA(peek_to_host(d_stats, h_stats, sizeof(tgx::PlanStats), stream));
-            TGX_CUDA(cudaStreamSynchronize(stream));
-            if (!h_stats->overflow) {
-                tot_samples = (int64_t)h_stats->total_samples;
-                tot_segs = 0;
-                tot_tiles = need_tiles;
-                done = true;
-                e->plan_phase = true;
-                e->plan_packed = false;
-                e->tile_slab_plan = e->phase_tile_slab;
-                e->phase_plans += 1;
-            } else {
-                e->phase_ready = false;   // lines, long or rejected-by-size trajectories: plan with segment tables
-            }
+    // A mixed batch is replayed in the order of its replay classes (orbits by number of speed goals, lines,
+    // boomerangs): neighbouring lanes then walk the same code instead of diverging at every branch.  One key
+    // kernel + a one-pass radix sort of (class, index) pairs; the tables are indexed by trajectory, so the
+    // plan itself does not depend on the order.
+    const int32_t* order = nullptr;
+    auto replay_order = [&]() -> int {
+        if (order || !e->mixed_batch || n < 256) return TGX_OK;
+        int rc2;
+        if ((rc2 = e->order.reserve((size_t)n * 10 + 64))) return rc2;
+        uint8_t* key_in = e->order.as<uint8_t>();
+        uint8_t* key_out = key_in + n;
+        int32_t* idx_in = reinterpret_cast<int32_t*>(key_in + ((2 * n + 15) & ~(int64_t)15));
+        int32_t* idx_out = idx_in + n;
+        TGX_CUDA(tgx::launch_replay_keys(d_params, n, key_in, idx_in, stream));
+        size_t need = 0;
+        TGX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, idx_in, idx_out, (int)n, 0, 5, stream));
+        if ((rc2 = e->cub_tmp.reserve(need))) return rc2;
+        size_t tmp_bytes = e->cub_tmp.bytes;
+        TGX_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp_bytes, key_in, key_out, idx_in, idx_out, (int)n, 0, 5,
+                                                 stream));
+        e->launches += 2;
+        order = idx_out;
+        return TGX_OK;
+    };
+
+    // ---- phase mode: batches of short orbits and plain lines.  One replay that writes a self-contained 240-byte record
+    //      per trajectory instead of tables; the evaluation kernel rebuilds the table path's segments from it, bit for
+    //      bit, one CTA per trajectory ----
+    if (e->allow_phase && e->phase_ready && !e->exact_ramps && !d_stop_from &&
+        !(e->reduce_only && (e->slabs_ready || e->ragged_ready))) {
+        if ((rc = e->phase.reserve((size_t)n * sizeof(tgx::PhaseRec)))) return rc;
+        if ((rc = e->phase_ext.reserve((size_t)n * sizeof(tgx::PhaseExt)))) return rc;
+        if ((rc = replay_order())) return rc;
+        TGX_CUDA(zero_fill(d_stats, sizeof(tgx::PlanStats), stream));
+        TGX_CUDA(tgx::launch_plan_phase(d_params, n, limits, e->max_samples, e->tile_shift, tgx::kPhaseMaxSamples, tab,
+                                        e->phase.as<tgx::PhaseRec>(), e->phase_ext.as<tgx::PhaseExt>(), d_counts,
+                                        d_status, cnt, st, d_phases, d_stats, stream, order));
+        e->launches += 1;
+        TGX_CUDA(peek_to_host(d_stats, h_stats, sizeof(tgx::PlanStats), stream));
+        TGX_CUDA(cudaStreamSynchronize(stream));
+        if (!h_stats->overflow) {
+            tot_samples = (int64_t)h_stats->total_samples;
+            tot_segs = 0;
+            tot_tiles = n;                // one CTA per trajectory
+            done = true;
+            e->plan_phase = true;
+            e->plan_packed = false;
+            e->tile_slab_plan = 0;
+            e->phase_plans += 1;
+            e->mixed_batch = (h_stats->kinds & (h_stats->kinds - 1)) != 0;
+        } else {
+            e->phase_ready = false;   // boomerangs, many speed goals, long trajectories: plan with segment tables
         }
     }
 
@@ -482,28 +520,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
             if ((rc = e->segs.reserve((size_t)need_segs * sizeof(tgx::Seg)))) return rc;
             if ((rc = e->tiles.reserve((size_t)need_tiles * sizeof(tgx::Tile)))) return rc;
             TGX_CUDA(zero_fill(d_stats, sizeof(tgx::PlanStats), stream));
-            // A mixed batch is replayed in the order of its replay classes (orbits by number of speed goals, lines,
-            // boomerangs): neighbouring lanes then walk the same code instead of diverging at every branch.  One key
-            // kernel + a one-pass radix sort of (class, index) pairs; the tables are indexed by trajectory, so the
-            // plan itself does not depend on the order.
-            const int32_t* order = nullptr;
-            if (e->mixed_batch && n >= 256 && n <= 0x7fffffffLL) {
-                if ((rc = e->order.reserve((size_t)n * 10 + 64))) return rc;
-                uint8_t* key_in = e->order.as<uint8_t>();
-                uint8_t* key_out = key_in + n;
-                int32_t* idx_in = reinterpret_cast<int32_t*>(key_in + ((2 * n + 15) & ~(int64_t)15));
-                int32_t* idx_out = idx_in + n;
-                TGX_CUDA(tgx::launch_replay_keys(d_params, n, key_in, idx_in, stream));
-                size_t need = 0;
-                TGX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, idx_in, idx_out, (int)n, 0, 5,
-                                                         stream));
-                if ((rc = e->cub_tmp.reserve(need))) return rc;
-                size_t tmp_bytes = e->cub_tmp.bytes;
-                TGX_CUDA(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp_bytes, key_in, key_out, idx_in, idx_out,
-                                                         (int)n, 0, 5, stream));
-                e->launches += 2;
-                order = idx_out;
-            }
+            if ((rc = replay_order())) return rc;
             TGX_CUDA(tgx::launch_plan_fill(d_params, d_stop_from, n, limits, e->max_samples, e->tile_shift, e->exact_ramps,
                                            tab, nullptr, nullptr, nullptr, e->seg_slab, e->tile_slab,
                                            e->recs.as<tgx::TrajRec>(), e->segs.as<tgx::Seg>(),
@@ -693,8 +710,9 @@ tgx::PolyView poly_view(const tgx_engine* e) {
 }
 
 // Evaluation of the current plan, whichever family planned it.
-cudaError_t launch_current(const tgx_engine* e, const tgx::OutView& out, bool store, double* max_v, double* max_a,
+cudaError_t launch_current(tgx_engine* e, const tgx::OutView& out, bool store, double* max_v, double* max_a,
                            cudaStream_t s, const tgx::RecOut* ptma = nullptr) {
+    (store ? e->plan_stored : e->plan_reduced) = true;         // what the plan is used for steers how the next one is made
     if (e->plan_poly)
         return tgx::launch_eval_poly(poly_view(e), e->plan_tiles, e->tile_shift, e->spt, out, store, max_v, max_a, s);
     return tgx::launch_eval(table_view(e), e->plan_tiles, e->tile_shift, e->spt, out, store, max_v, max_a, s, ptma);
@@ -918,7 +936,7 @@ int tgx_destroy(tgx_engine* e) {
     e->prof_ev.clear();
     DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
                       &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats, &e->packets,
-                      &e->phase, &e->poly_recs, &e->poly_tiles, &e->tiles_dense, &e->order};
+                      &e->phase, &e->phase_ext, &e->poly_recs, &e->poly_tiles, &e->tiles_dense, &e->order};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         e->h_legs[i].release();
@@ -1036,7 +1054,7 @@ int64_t tgx_scratch_bytes(const tgx_engine* e) {
     if (!e) return 0;
     const DevBuf* bufs[] = {&e->cnt, &e->nseg, &e->ntile, &e->status, &e->seg_off, &e->tile_off, &e->recs, &e->maxv,
                             &e->maxa, &e->cub_tmp, &e->totals, &e->segs, &e->tiles, &e->cur_table, &e->stats,
-                            &e->packets, &e->phase, &e->poly_recs, &e->poly_tiles, &e->order};
+                            &e->packets, &e->phase, &e->phase_ext, &e->poly_recs, &e->poly_tiles, &e->tiles_dense, &e->order};
     int64_t s = 0;
     for (const DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;
@@ -1454,6 +1472,7 @@ int tgx_eval_records(tgx_engine* e, const tgx_limits* limits, tgx_goal_record* d
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int rc = make_record_tmap(&ro.tmap, d_records, total);
     if (rc) return rc;
+    e->plan_stored = true;
     if (e->plan_poly)
         TGX_CUDA(tgx::launch_eval_poly_records(poly_view(e), e->plan_tiles, e->tile_shift, e->spt, ro, s));
     else

@@ -111,36 +111,121 @@ __device__ __forceinline__ SegPos seg_pos(const Seg& sg, int k) {
 
 }  // namespace
 
-// Phase plans: segment q of an orbit (Circle / Figure8) from its self-contained PhaseRec — exactly the Seg record
-// plan.cu's replay writes into the segment table for the same trajectory (ramp(), hold()): the base speed is the level
-// the preceding segments reached, the angle at both ends is the replayed one, and the per-step angle increment is
-// rounded the way the planner rounds it for that kind of segment.  A ramp of n steps adds a*dt per step and clamps on
-// its last step (Circle.cpp:47-54, 75-82); a hold keeps v (:63-71) and is one segment per binade of theta.
-__device__ void build_phase_segment(const PhaseRec& phr, int q, Seg& sg, int& kend) {
-    // speed at the start of segment q
-    double v = 0.0;
-    for (int p = 0; p < q; ++p) {
-        const int kp = (phr.kinds >> (2 * p)) & 3;
-        if (kp < kPhaseKindHold) v = phr.vg[kp];
-        else if (kp == kPhaseKindDown) v = 0.0;
+// The TrajRec of a phase plan's trajectory (what plan_one writes for the table path).
+__device__ __forceinline__ TrajRec build_phase_rec(const PhasePlan& P, int n_total) {
+    TrajRec r;
+    r.type = P.type & kRecTypeMask;
+    r.n = n_total;
+    // both variants keep TrajRec.f[0..3] first; f[4] (dt / r | dt) and f[5] (1 / r | unused) follow
+    r.f[0] = P.c.r; r.f[1] = P.c.cx; r.f[2] = P.c.cy; r.f[3] = P.c.alt;
+    r.f[4] = P.c.dtr;
+    r.f[5] = r.type == TGX_LINE ? 0.0 : P.c.rinv;
+    r.f[6] = 0.0;
+    return r;
+}
+
+// Phase plans: segment q of a trajectory from its self-contained record — exactly the Seg record plan.cu's replay
+// writes into the segment table for the same trajectory (ramp(), hold()).
+// Orbits (Circle / Figure8): the base speed is the level the preceding segments reached, the angle at both ends is the
+// replayed one, and the per-step angle increment is rounded the way the planner rounds it for that kind of segment.  A
+// ramp of n steps adds a*dt per step and clamps on its last step (Circle.cpp:47-54, 75-82); a hold keeps v (:63-71) and
+// is one segment per binade of theta.
+// Lines: ramp up from 0 to v_goal, clamped on its last step (Line.cpp:46-50); cruise (:57-62); ramp down, whose last step
+// — the one the std::max clamp turns into 0 — is a one-sample segment of its own with the position forced to B
+// (:65-68, :81-82).  The position at each segment's base is the replayed one.
+// The lanes of a warp rebuild different segments of one trajectory: everything below is selects, no divergent branch
+// (the trajectory type is the same for the whole CTA).
+__device__ __forceinline__ void build_phase_segment(const PhasePlan& P, int q, Seg& sg, int& kend) {
+    const int qp = q > 0 ? q - 1 : 0;
+    kend = P.key[q];
+    sg.kb = q ? P.key[qp] : 0;
+    sg.n = kend - sg.kb;
+    sg.pad = 0;
+    const uint64_t kinds = (uint64_t)P.kinds[0] | ((uint64_t)P.kinds[1] << 32);
+    if ((P.type & kRecTypeMask) == TGX_LINE) {
+        const int kind = (int)(kinds >> (3 * q)) & 7;
+        const double vg = P.c.lvg;
+        sg.flags = kind == kPhaseLineUp ? kSegClampLast : (kind == kPhaseLineForced ? kSegForcePos : 0);
+        sg.vb = (kind == kPhaseLineUp || kind == kPhaseLineForced) ? 0.0 : vg;
+        sg.dv = kind == kPhaseLineUp ? P.c.ladt1 : (kind == kPhaseLineDown ? -P.c.ladt3 : 0.0);
+        sg.vclamp = (kind == kPhaseLineUp || kind == kPhaseLineHold) ? vg : 0.0;
+        sg.s0 = P.xy[q][0];
+        sg.s1 = P.xy[q][1];
+        sg.acc = kind == kPhaseLineUp ? P.c.la1 : (kind == kPhaseLineHold ? 0.0 : -P.c.la3);
+        return;
     }
-    const int kind = (phr.kinds >> (2 * q)) & 3;
+    // The speed at the start of segment q is the level the last ramp before it reached (holds, kind 0b10, keep it): the
+    // highest two-bit field below q that is not a hold.  A ramp-down (0b11, v = 0) is put below segment 0 so that there
+    // always is one.
+    const uint64_t k2 = (kinds << 2) | 3ull;
+    const uint64_t mask = (4ull << (2 * q)) - 1ull;              // the virtual field and segments 0 .. q-1
+    const uint64_t below = k2 & mask;
+    const uint64_t ramps = ((~below >> 1) | below) & 0x5555555555555555ull & mask;
+    const int level = (int)(k2 >> (63 - __clzll((long long)ramps))) & 3;
+    const bool moving = level != kPhaseKindDown;
+    const double v = moving ? P.c.vg[level & 1] : 0.0;
+    const double w = moving ? P.c.w[level & 1] : 0.0;
+    const int kind = (int)(kinds >> (2 * q)) & 3;
     const bool hold = kind == kPhaseKindHold;
     const bool up = kind < kPhaseKindHold;
-    const double thb = q ? phr.th[q - 1] : 0.0;
-    sg.kb = q ? phr.key[q - 1] : 0;
-    sg.n = phr.key[q] - sg.kb;
+    const double thp = P.th[qp];
+    const double thb = q ? thp : 0.0;
     sg.flags = hold ? 0 : kSegClampLast;
-    sg.pad = 0;
     sg.vb = v;
-    sg.dv = hold ? 0.0 : (up ? phr.adt : -phr.adt);
-    sg.vclamp = hold ? v : (up ? phr.vg[kind] : 0.0);
+    sg.dv = hold ? 0.0 : (up ? P.c.adt : -P.c.adt);
+    const double vup = P.c.vg[kind & 1];
+    sg.vclamp = hold ? v : (up ? vup : 0.0);
     sg.s0 = thb;
     // hold: the exact progression step of theta += omega*dt with omega = v/r rounded first (Circle.cpp:65-67; plan.cu:
     // hold(), d0); ramp: v * (dt/r)  (plan.cu: ramp())
-    sg.s1 = hold ? __dsub_rn(__dadd_rn(thb, __dmul_rn(__ddiv_rn(v, phr.r), phr.dt)), thb) : __dmul_rn(v, phr.dtr);
-    sg.acc = phr.th[q];        // theta of the segment's last sample
-    kend = phr.key[q];
+    const double s1h = __dsub_rn(__dadd_rn(thb, w), thb), s1r = __dmul_rn(v, P.c.dtr);
+    sg.s1 = hold ? s1h : s1r;
+    sg.acc = P.th[q];          // theta of the segment's last sample
+}
+
+// Stage a phase plan's trajectory: its PhaseRec (one round of loads), the PhaseExt row if it has one, then the Seg records
+// and the TrajRec of the table path.  Returns the number of segments (0: rejected trajectory, whole CTA).
+template <int NSEG>
+__device__ __forceinline__ int stage_phase_plan(const TableView& tv, int traj, PhasePlan& P, Seg (&s_seg)[NSEG],
+                                                int (&s_kend)[NSEG], TrajRec& s_rec) {
+    // where the 16-byte chunks of the two records land in the shared-memory image (see PhasePlan)
+    constexpr int kRecChunks = sizeof(PhaseRec) / 16, kExtChunks = sizeof(PhaseExt) / 16;
+    constexpr int kThRec = offsetof(PhaseRec, th) / 16, kThPlan = offsetof(PhasePlan, th) / 16;
+    constexpr int kKeyExtTo = offsetof(PhasePlan, key) / 16 + kPhaseBaseSegs * 4 / 16;
+    constexpr int kThExt = offsetof(PhaseExt, th) / 16, kThExtTo = kThPlan + kPhaseBaseSegs * 8 / 16;
+    static_assert(offsetof(PhaseRec, key) == offsetof(PhasePlan, key), "the head of the record is copied as it is");
+    int4* dst = reinterpret_cast<int4*>(&P);
+#ifdef TGX_EXPERIMENT_SAMEPACKET
+    const int4* pphr = reinterpret_cast<const int4*>(tv.phase);      // bandwidth experiment: no DRAM reads
+#else
+    const int4* pphr = reinterpret_cast<const int4*>(tv.phase + traj);
+#endif
+    if (threadIdx.x < kRecChunks) {
+        const int c = threadIdx.x;
+        dst[c + (c >= kThRec ? kThPlan - kThRec : 0)] = __ldg(pphr + c);
+    }
+    __syncthreads();
+    const int nseg = P.n;
+    if (nseg <= 0) return 0;
+    if (nseg > kPhaseBaseSegs) {                   // CTA-uniform, rare
+        if (threadIdx.x < kExtChunks) {
+            const int x = threadIdx.x;
+            dst[x < kThExt ? kKeyExtTo + x : kThExtTo + (x - kThExt)] =
+                __ldg(reinterpret_cast<const int4*>(tv.phase_ext + traj) + x);
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < nseg) {
+        Seg sg;
+        int kend;
+        build_phase_segment(P, threadIdx.x, sg, kend);
+        s_seg[threadIdx.x] = sg;
+        s_kend[threadIdx.x] = kend;
+    } else if (threadIdx.x == 32) {                // (the second warp: the segments keep the first one busy)
+        s_rec = build_phase_rec(P, P.key[nseg - 1] + 1);      // the trajectory's last sample ends its last segment
+    }
+    __syncthreads();
+    return nseg;
 }
 
 // MODE 0: exact-offset plan, 1: slab plan (fixed per-trajectory slices), 2: phase plan (see TableView).
@@ -157,7 +242,8 @@ __global__ void __launch_bounds__(THREADS, (REDUCE && !STORE) ? TGX_REDUCE_CTAS 
 eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __restrict__ max_a,
             const __grid_constant__ RecOut ro = RecOut{}) {
     constexpr bool STAGED = RECORDS || PTMA;       // samples staged in shared memory and sent by TMA
-    static_assert(STAGED || (REDUCE && !STORE) || PASSES == 1, "only the TMA and reduction-only modes walk a tile in passes");
+    static_assert(STAGED || (REDUCE && !STORE) || PASSES == 1 || MODE == 2,
+                  "only the TMA and reduction-only modes walk a tile in passes (phase plans: the whole trajectory, always)");
     static_assert(!PTMA || (STORE && !REDUCE && !RECORDS), "PTMA is the plain store-only evaluation");
     constexpr bool SLAB = MODE == 1;
     constexpr int TILE = THREADS * SPT * PASSES;
@@ -172,37 +258,14 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
 
     // ---- stage the tile's constants in shared memory (16-byte chunks, one per thread) -------------------
     int traj, k_lo, nseg;
+    int npass = PASSES;
     if (MODE == 2) {
-        __shared__ __align__(16) PhaseRec s_phr;
-        traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
-        k_lo = ((int)blockIdx.x - traj * tv.tile_slab) * TILE;
-#ifdef TGX_EXPERIMENT_SAMEPACKET
-        const int4* pphr = reinterpret_cast<const int4*>(tv.phase);      // bandwidth experiment: no DRAM reads
-#else
-        const int4* pphr = reinterpret_cast<const int4*>(tv.phase + traj);
-#endif
-        // one round of independent loads: the 240-byte record holds everything the tile needs
-        if (threadIdx.x < sizeof(PhaseRec) / 16) reinterpret_cast<int4*>(&s_phr)[threadIdx.x] = __ldg(pphr + threadIdx.x);
-        __syncthreads();
-        nseg = s_phr.n;
+        __shared__ __align__(16) PhasePlan s_plan;
+        traj = (int)blockIdx.x;                    // one CTA per trajectory, which it walks in passes
+        k_lo = 0;
+        nseg = stage_phase_plan(tv, traj, s_plan, s_seg, s_kend, s_rec);
         if (nseg <= 0) return;                     // rejected trajectory (whole CTA)
-        const int n_total = s_phr.key[nseg - 1] + 1;
-        if (k_lo >= n_total) return;               // slot beyond the trajectory's last tile (whole CTA)
-        if ((int)threadIdx.x < nseg) {
-            Seg sg;
-            int kend;
-            build_phase_segment(s_phr, threadIdx.x, sg, kend);
-            s_seg[threadIdx.x] = sg;
-            s_kend[threadIdx.x] = kend;
-        } else if ((int)threadIdx.x == nseg) {
-            TrajRec r;
-            r.type = s_phr.type & kRecTypeMask;
-            r.n = n_total;
-            r.f[0] = s_phr.r; r.f[1] = s_phr.cx; r.f[2] = s_phr.cy; r.f[3] = s_phr.alt;
-            r.f[4] = s_phr.dtr; r.f[5] = s_phr.rinv; r.f[6] = 0.0;
-            s_rec = r;
-        }
-        __syncthreads();
+        npass = (s_rec.n + THREADS * SPT - 1) / (THREADS * SPT);
     } else if (SLAB) {
         traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
         const int t = (int)blockIdx.x - traj * tv.tile_slab;
@@ -291,7 +354,7 @@ eval_kernel(TableView tv, OutView out, double* __restrict__ max_v, double* __res
     }
 
 #pragma unroll 1
-    for (int pass = 0; pass < PASSES; ++pass) {
+    for (int pass = 0; pass < (MODE == 2 ? npass : PASSES); ++pass) {
     // first sample of this warp's block of 32*SPT (RECORDS) and of this thread
     const int wk0 = k_lo + pass * (THREADS * SPT) + ((int)threadIdx.x >> 5) * (32 * SPT);
     const int k0 = STAGED ? wk0 + ((int)threadIdx.x & 31) : k_lo + pass * (THREADS * SPT) + SPT * (int)threadIdx.x;
@@ -785,31 +848,11 @@ reduce_kernel(TableView tv, double* __restrict__ max_v, double* __restrict__ max
     // ---- stage the tile's constants (as eval_kernel does) -----------------------------------------------------------------
     int traj, k_lo, nseg;
     if (MODE == 2) {
-        __shared__ __align__(16) PhaseRec s_phr;
-        traj = (int)(blockIdx.x / (unsigned)tv.tile_slab);
-        k_lo = ((int)blockIdx.x - traj * tv.tile_slab) * TILE;
-        const int4* pphr = reinterpret_cast<const int4*>(tv.phase + traj);
-        if (threadIdx.x < sizeof(PhaseRec) / 16) reinterpret_cast<int4*>(&s_phr)[threadIdx.x] = __ldg(pphr + threadIdx.x);
-        __syncthreads();
-        nseg = s_phr.n;
+        __shared__ __align__(16) PhasePlan s_plan;
+        traj = (int)blockIdx.x;                    // one CTA per trajectory
+        k_lo = 0;
+        nseg = stage_phase_plan(tv, traj, s_plan, s_seg, s_kend, s_rec);
         if (nseg <= 0) return;
-        const int n_total = s_phr.key[nseg - 1] + 1;
-        if (k_lo >= n_total) return;
-        if ((int)threadIdx.x < nseg) {
-            Seg sg;
-            int kend;
-            build_phase_segment(s_phr, threadIdx.x, sg, kend);
-            s_seg[threadIdx.x] = sg;
-            s_kend[threadIdx.x] = kend;
-        } else if ((int)threadIdx.x == nseg) {
-            TrajRec r;
-            r.type = s_phr.type & kRecTypeMask;
-            r.n = n_total;
-            r.f[0] = s_phr.r; r.f[1] = s_phr.cx; r.f[2] = s_phr.cy; r.f[3] = s_phr.alt;
-            r.f[4] = s_phr.dtr; r.f[5] = s_phr.rinv; r.f[6] = 0.0;
-            s_rec = r;
-        }
-        __syncthreads();
     } else {
         int4 tw;
         if (MODE == 1) {
@@ -840,7 +883,7 @@ reduce_kernel(TableView tv, double* __restrict__ max_v, double* __restrict__ max
     const int type = s_rec.type & kRecTypeMask;
     const int n = s_rec.n;
     // the tile's samples in runs of `per` consecutive ones, one run per thread
-    const int in_tile = min(n - k_lo, TILE);
+    const int in_tile = MODE == 2 ? n : min(n - k_lo, TILE);      // (phase plan: the whole trajectory)
     int per = (in_tile + THREADS - 1) / THREADS;
     if (per > 2) per = (per + TGX_RED_U - 1) / TGX_RED_U * TGX_RED_U;      // whole groups (the unrolled body)
     const int k = k_lo + (int)threadIdx.x * per;

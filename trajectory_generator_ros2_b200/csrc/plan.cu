@@ -91,10 +91,11 @@ struct Emitter {
     bool orbit;           // Circle / Figure8: Seg.s1 = theta increment per step, Seg.acc = exact theta of the last sample
     int seg_cap;          // slab mode: capacity of this trajectory's slice (writes beyond it are dropped and the
     int tile_cap;         //            plan is redone with exact offsets); otherwise INT_MAX
-    // phase plans (PhaseRec): where each segment ends, the replayed angle there, and what kind of segment it is
+    // phase plans (PhaseRec): where each segment ends, the replayed state (orbit: the angle at the segment's end; line:
+    // the position at its base), and what kind of segment it is
     int32_t* keys = nullptr;
     double* states = nullptr;
-    uint32_t kinds = 0;        // 2 bits per segment: kPhaseKind*
+    uint64_t kinds = 0;        // orbit: 2 bits per segment, kPhaseKind*; line: 3 bits, kPhaseLine*
     int goal = 0;              // index of the speed goal the current ramp-up heads for
     int prev_kind = -1;
     bool ramp_split = false;   // some ramp was cut into several segments: not expressible as a PhaseRec
@@ -167,7 +168,18 @@ struct Emitter {
             const int kind = dv > 0.0 ? (goal & 1) : (dv == 0.0 ? kPhaseKindHold : kPhaseKindDown);
             if (kind != kPhaseKindHold && kind == prev_kind) ramp_split = true;
             prev_kind = kind;
-            if (nseg < kPhaseMaxSegs) kinds |= (uint32_t)kind << (2 * nseg);
+            if (nseg < kPhaseMaxSegs) kinds |= (uint64_t)kind << (2 * nseg);
+        } else {
+            const int kind = dv > 0.0 ? kPhaseLineUp : (dv == 0.0 ? kPhaseLineHold : kPhaseLineDown);
+            if (kind != kPhaseLineHold && kind == prev_kind) ramp_split = true;
+            prev_kind = kind;
+            if (nseg < kPhaseLineMaxSegs) {
+                kinds |= (uint64_t)kind << (3 * nseg);
+                if (states) {
+                    states[2 * nseg] = s0;
+                    states[2 * nseg + 1] = s1;
+                }
+            }
         }
         cur.kb = kb;
         cur.n = 0;
@@ -190,8 +202,10 @@ struct Emitter {
         }
         if (keys && nseg < kPhaseMaxSegs) {
             keys[nseg] = k_last;
-            states[nseg] = last_state;
+            if (orbit) states[nseg] = last_state;
         }
+        // (a forced end point was opened as a hold, dv = 0: kPhaseLineHold | 2 == kPhaseLineForced)
+        if (!orbit && (extra_flags & kSegForcePos) && nseg < kPhaseLineMaxSegs) kinds |= (uint64_t)2 << (3 * nseg);
         if (k_last - cur.kb > max_seg_len) max_seg_len = k_last - cur.kb;
         // every further tile the segment reaches into starts its list with this segment
         const int t_last = k_last >> tile_shift;
@@ -844,9 +858,11 @@ __device__ __forceinline__ tgx_params load_params(const tgx_params* params, int6
 
 // Can this trajectory's plan be written as a PhaseRec?  (A rejected one can: n = 0.)
 __device__ __forceinline__ bool phase_fits(const tgx_params& p, int n, const Emitter& E, int max_n) {
-    if (!is_orbit(p.type)) return false;
+    if (!is_orbit(p.type) && p.type != TGX_LINE) return false;
     if (n <= 0) return true;
-    return p.n_vgoals <= kPhaseMaxGoals && E.nseg <= kPhaseMaxSegs && !E.ramp_split && n <= max_n;
+    if (E.ramp_split || n > max_n) return false;
+    if (p.type == TGX_LINE) return E.nseg <= kPhaseLineMaxSegs;
+    return p.n_vgoals <= kPhaseMaxGoals && E.nseg <= kPhaseMaxSegs;
 }
 
 }  // namespace
@@ -991,50 +1007,88 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
 }
 
 // Phase plan: batches of short orbits (Circle / Figure8 with at most kPhaseMaxGoals speed goals, at most kPhaseMaxSegs
-// segments, at most max_n samples).  The same replay as plan_fill_kernel, but instead of TrajRec + Seg + Tile records it
-// writes ONE self-contained PhaseRec per trajectory: where each segment ends, the replayed angle there, the segment
-// kinds and the constants of the parameter record.  The evaluation CTA rebuilds the table path's Seg records from it
-// (build_phase_segment, eval.cu) — the samples are the same bits whichever way the batch was planned.  A trajectory
-// that does not qualify sets stats->overflow and the host plans the batch with segment tables.
+// segments) and plain lines (at most kPhaseLineMaxSegs segments), at most max_n samples each.  The same replay as
+// plan_fill_kernel, but instead of TrajRec + Seg + Tile records it writes ONE self-contained PhaseRec per trajectory:
+// where each segment ends, the replayed state there, the segment kinds and the constants of the parameter record.  The
+// evaluation CTA rebuilds the table path's Seg records from it (build_phase_segment, eval.cu) — the samples are the same
+// bits whichever way the batch was planned.  A trajectory that does not qualify sets stats->overflow and the host plans
+// the batch with segment tables.  `order`: see plan_fill_kernel.
 // (12 CTAs of 128 threads per SM: the replay is latency-bound, more resident warps beat fewer spills)
 __global__ void __launch_bounds__(128, 12)
 plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits lim, int has_lim,
                   int64_t max_samples, int tile_shift, int max_n, const CurTable* __restrict__ tab,
-                  PhaseRec* __restrict__ phase, int32_t* __restrict__ counts, uint32_t* __restrict__ status,
-                  int32_t* __restrict__ counts2, uint32_t* __restrict__ status2, tgx_phases* __restrict__ phases,
-                  PlanStats* __restrict__ stats) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+                  PhaseRec* __restrict__ phase, PhaseExt* __restrict__ phase_ext, int32_t* __restrict__ counts,
+                  uint32_t* __restrict__ status, int32_t* __restrict__ counts2, uint32_t* __restrict__ status2,
+                  tgx_phases* __restrict__ phases, PlanStats* __restrict__ stats, const int32_t* __restrict__ order) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = order ? (int64_t)__ldg(order + t) : t;
     const tgx_params p = load_params(params, i);
     PhaseRec rec;
     rec.n = 0;
-    rec.pad = 0;
+    int32_t key[kPhaseMaxSegs];
+    double th[kPhaseMaxSegs];
 #pragma unroll
     for (int q = 0; q < kPhaseMaxSegs; ++q) {
-        rec.key[q] = 0;
-        rec.th[q] = 0.0;
+        key[q] = 0;
+        th[q] = 0.0;
     }
-    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, phases ? phases + i : nullptr, true, 0x7fffffff,
-              0x7fffffff, rec.key, rec.th};
     const bool orbit = is_orbit(p.type);
+    Emitter E{tile_shift, (int32_t)i, nullptr, nullptr, 0, phases ? phases + i : nullptr, orbit, 0x7fffffff,
+              0x7fffffff, key, th};
     PlanOut r{0, 0u, 0, 0};
-    bool overflow = !orbit;
-    if (orbit) {
-        r = plan_one<false, true, false>(p, Src{params, i, n}, max_samples, has_lim ? &lim : nullptr, E, nullptr, tab);
+    TrajRec tr;
+    bool overflow = !orbit && p.type != TGX_LINE;
+    if (!overflow) {
+        r = plan_one<true, true, false>(p, Src{params, i, n}, max_samples, has_lim ? &lim : nullptr, E, &tr, tab);
         overflow = !phase_fits(p, r.n, E, max_n);
         if (r.n > 0 && !overflow) rec.n = E.nseg;
+    } else if (phases) {
+        phases[i].n = 0;
     }
-    if (phases && r.n == 0) phases[i].n = 0;
-    const tgx_orbit_params& o = p.u.orbit;
     rec.type = p.type;
-    rec.kinds = E.kinds;
-    rec.dtr = orbit ? ddiv(p.dt, o.r) : 0.0;
-    rec.rinv = orbit ? ddiv(1.0, o.r) : 0.0;
-    rec.r = o.r; rec.cx = o.cx; rec.cy = o.cy; rec.alt = p.alt;
-    rec.adt = dmul(o.accel, p.dt);
-    rec.dt = p.dt;
+    rec.kinds[0] = (uint32_t)E.kinds;
+    rec.kinds[1] = (uint32_t)(E.kinds >> 32);
 #pragma unroll
-    for (int q = 0; q < kPhaseMaxGoals; ++q) rec.vg[q] = o.v_goals[q];
-    // 240-byte record: fifteen 16-byte stores
+    for (int q = 0; q < kPhaseBaseSegs; ++q) {
+        rec.key[q] = key[q];
+        rec.th[q] = th[q];
+    }
+    if (rec.n > kPhaseBaseSegs) {
+        PhaseExt x;
+#pragma unroll
+        for (int q = 0; q < kPhaseMaxSegs - kPhaseBaseSegs; ++q) {
+            x.key[q] = key[kPhaseBaseSegs + q];
+            x.th[q] = th[kPhaseBaseSegs + q];
+        }
+        const int4* src = reinterpret_cast<const int4*>(&x);
+        int4* dst = reinterpret_cast<int4*>(phase_ext + i);
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(PhaseExt) / 16); ++q) dst[q] = src[q];
+    }
+    if (p.type == TGX_LINE) {
+        const tgx_line_params& l = p.u.line;
+        rec.c.lcos = tr.f[0]; rec.c.lsin = tr.f[1]; rec.c.ltheta = tr.f[2]; rec.c.lalt = tr.f[3]; rec.c.ldt = tr.f[4];
+        rec.c.lvg = l.v_goal;
+        rec.c.ladt1 = dmul(l.a1, p.dt);
+        rec.c.ladt3 = dmul(l.a3, p.dt);
+        rec.c.la1 = l.a1;
+        rec.c.la3 = l.a3;
+        rec.c.lspare[0] = rec.c.lspare[1] = 0.0;
+    } else {
+        const tgx_orbit_params& o = p.u.orbit;
+        rec.c.dtr = orbit ? ddiv(p.dt, o.r) : 0.0;
+        rec.c.rinv = orbit ? ddiv(1.0, o.r) : 0.0;
+        rec.c.r = o.r; rec.c.cx = o.cx; rec.c.cy = o.cy; rec.c.alt = p.alt;
+        rec.c.adt = dmul(o.accel, p.dt);
+        rec.c.spare = 0.0;
+#pragma unroll
+        for (int q = 0; q < kPhaseMaxGoals; ++q) {
+            rec.c.vg[q] = o.v_goals[q];
+            // omega = v / r_; theta += omega * dt_ (Circle.cpp:65-67), as replay_orbit's hold passes it on
+            rec.c.w[q] = orbit ? dmul(ddiv(o.v_goals[q], o.r), p.dt) : 0.0;
+        }
+    }
+    // 256-byte record: sixteen 16-byte stores
     {
         const int4* src = reinterpret_cast<const int4*>(&rec);
         int4* dst = reinterpret_cast<int4*>(phase + i);
@@ -1045,7 +1099,7 @@ plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits l
     if (status) status[i] = r.status;
     if (counts2) counts2[i] = r.n;
     if (status2) status2[i] = r.status;
-    accumulate_stats(stats, r.n, 0, 0, overflow, !orbit, replay_class(p.type, p.n_vgoals), 0, 0, overflow);
+    accumulate_stats(stats, r.n, 0, 0, overflow, is_line_like(p.type), replay_class(p.type, p.n_vgoals), 0, 0, overflow);
     }
 }
 
@@ -1257,9 +1311,9 @@ cudaError_t launch_replay_keys(const tgx_params* params, int64_t n, uint8_t* key
 }
 
 cudaError_t launch_plan_phase(const tgx_params* params, int64_t n, const tgx_limits* lim, int64_t max_samples,
-                              int tile_shift, int max_n, const void* cur_table, PhaseRec* phase, int32_t* counts,
-                              uint32_t* status, int32_t* counts2, uint32_t* status2, tgx_phases* phases,
-                              PlanStats* stats, cudaStream_t stream) {
+                              int tile_shift, int max_n, const void* cur_table, PhaseRec* phase, PhaseExt* phase_ext,
+                              int32_t* counts, uint32_t* status, int32_t* counts2, uint32_t* status2,
+                              tgx_phases* phases, PlanStats* stats, cudaStream_t stream, const int32_t* order) {
     if (n <= 0) return cudaSuccess;
     tgx_limits l{};
     if (lim) l = *lim;
@@ -1267,7 +1321,7 @@ cudaError_t launch_plan_phase(const tgx_params* params, int64_t n, const tgx_lim
     const int64_t grid = (n + cta - 1) / cta;
     plan_phase_kernel<<<(unsigned)grid, cta, 0, stream>>>(
         params, n, l, lim ? 1 : 0, max_samples, tile_shift, max_n, static_cast<const CurTable*>(cur_table), phase,
-        counts, status, counts2, status2, phases, stats);
+        phase_ext, counts, status, counts2, status2, phases, stats, order);
     return cudaGetLastError();
 }
 

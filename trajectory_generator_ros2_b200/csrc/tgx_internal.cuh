@@ -15,6 +15,7 @@
 // (eval.cu) consumes one Tile per CTA.
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 
 #include <cuda.h>   // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
@@ -94,39 +95,88 @@ constexpr int kMaxOptionalSegPerTile = 36;
 // of the kernel's write stream costs a write->read->write bus turnaround (tools/wbw: 1 % of read traffic costs 8 %
 // of the write bandwidth; with cache-resident tables the same kernel writes 7.27 TB/s instead of 6.5 TB/s).
 //   phase plans (phase != nullptr): batches of short orbits with at most kPhaseMaxGoals speed goals whose replay emits
-//       at most kPhaseMaxSegs segments (one per ramp, one per binade of theta a hold passes through).  The planner then
-//       writes one self-contained 240-byte PhaseRec per trajectory — where each segment ends, the replayed angle
-//       there, what kind of segment it is, and the constants of the parameter record — instead of TrajRec + Seg + Tile
-//       records, and the CTA rebuilds exactly the Seg records the table path would have read (build_phase_segment,
-//       eval.cu): same bits, one round of 15 independent 16-byte loads.  Tile t of trajectory i is CTA i*tile_slab + t.
+//       at most kPhaseMaxSegs segments (one per ramp, one per binade of theta a hold passes through) and of plain lines
+//       (at most kPhaseLineMaxSegs segments: ramp, cruise, ramp, forced end point).  The planner then writes one
+//       self-contained 256-byte PhaseRec per trajectory — where each segment ends, the replayed state there, what kind
+//       of segment it is, and the constants of the parameter record — instead of TrajRec + Seg + Tile records, and the
+//       CTA rebuilds exactly the Seg records the table path would have read (build_phase_segment, eval.cu): same bits,
+//       one round of 16 independent 16-byte loads.  The rare orbit with more than kPhaseBaseSegs segments (a slow first
+//       goal speed: the hold starts at a tiny angle and passes through ten binades) keeps the rest in a PhaseExt row,
+//       a second round of loads for that CTA alone.  There is no tile directory: CTA i serves trajectory i and walks
+//       its samples (at most kPhaseMaxSamples) in passes, so a ragged batch costs no empty CTAs and no work list.
 constexpr int kPhaseMaxGoals = 2;
-constexpr int kPhaseMaxSegs = 12;
-constexpr int kPhaseKindHold = 2;      // 0, 1: ramp up to speed goal 0 / 1
+constexpr int kPhaseBaseSegs = 12;     // segments held by the PhaseRec itself
+constexpr int kPhaseMaxSegs = 20;      // ... and with the trajectory's PhaseExt row
+constexpr int kPhaseKindHold = 2;      // orbits, 2 bits per segment: 0, 1 = ramp up to speed goal 0 / 1
 constexpr int kPhaseKindDown = 3;
+constexpr int kPhaseLineMaxSegs = 6;
+constexpr int kPhaseLineUp = 0;        // lines, 3 bits per segment
+constexpr int kPhaseLineHold = 1;
+constexpr int kPhaseLineDown = 2;
+constexpr int kPhaseLineForced = 3;    // the leg's last sample, position forced to B (Line.cpp:81-82)
+// The constants of a phase plan's trajectory (12 doubles), shared by the record in HBM and its image in shared memory.
+union PhaseConsts {
+    struct {
+        double r, cx, cy, alt;
+        double dtr, rinv;     // dt / r and 1 / r, divided once by the planner instead of once per CTA
+        double adt;           // the rounded product accel*dt the reference adds every step
+        double vg[kPhaseMaxGoals];
+        double w[kPhaseMaxGoals];     // (vg / r) * dt as the reference rounds it: what a hold adds to theta per step
+        double spare;
+    };
+    struct {
+        double lcos, lsin, ltheta, lalt, ldt;       // TrajRec.f[0..4] of a line
+        double lvg;                                 // v_goal
+        double ladt1, ladt3;                        // the rounded products a1*dt, a3*dt (Line.cpp:48, :67)
+        double la1, la3;
+        double lspare[2];
+    };
+};
 struct __align__(16) PhaseRec {
     int32_t n;            // number of segments (0: rejected trajectory)
-    int32_t type;         // TGX_CIRCLE / TGX_FIGURE8
-    uint32_t kinds;       // 2 bits per segment
-    int32_t pad;
-    int32_t key[kPhaseMaxSegs];      // key[q] = last sample of segment q (segment q starts after key[q-1], or at sample 0)
-    double th[kPhaseMaxSegs];        // the replayed angle at sample key[q]
-    double r, cx, cy, alt;
-    double dtr, rinv;     // dt / r and 1 / r, divided once here instead of once per CTA
-    double adt, dt;       // the rounded product accel*dt the reference adds every step; dt
-    double vg[kPhaseMaxGoals];
+    int32_t type;         // TGX_CIRCLE / TGX_FIGURE8 / TGX_LINE
+    uint32_t kinds[2];    // 2 (orbit) or 3 (line) bits per segment, 64 bits in all
+    PhaseConsts c;
+    int32_t key[kPhaseBaseSegs];     // key[q] = last sample of segment q (segment q starts after key[q-1], or at sample 0)
+    union {
+        double th[kPhaseBaseSegs];           // orbit: the replayed angle at sample key[q]
+        double xy[kPhaseLineMaxSegs][2];     // line: the replayed position at the BASE sample of segment q (Seg.s0, Seg.s1)
+    };
 };
-static_assert(sizeof(PhaseRec) == 240, "PhaseRec must be 240 bytes");
+static_assert(sizeof(PhaseRec) == 256, "PhaseRec must be 256 bytes (two 128-byte lines)");
+// Segments kPhaseBaseSegs .. kPhaseMaxSegs - 1 of trajectory i (written and read only when PhaseRec.n > kPhaseBaseSegs).
+struct __align__(16) PhaseExt {
+    int32_t key[kPhaseMaxSegs - kPhaseBaseSegs];
+    double th[kPhaseMaxSegs - kPhaseBaseSegs];
+};
+static_assert(sizeof(PhaseExt) == 96, "PhaseExt must be 96 bytes");
+// What the evaluation CTA keeps of both in shared memory: the 16-byte chunks of the two records land so that key[] and
+// th[] each run on from the record into the extension row (stage_phase_plan, eval.cu).
+struct __align__(16) PhasePlan {
+    int32_t n, type;
+    uint32_t kinds[2];
+    PhaseConsts c;
+    int32_t key[kPhaseMaxSegs];
+    union {
+        double th[kPhaseMaxSegs];
+        double xy[kPhaseLineMaxSegs][2];
+    };
+};
+static_assert(sizeof(PhasePlan) == sizeof(PhaseRec) + sizeof(PhaseExt), "PhasePlan is PhaseRec + PhaseExt");
+static_assert(offsetof(PhaseRec, key) % 16 == 0 && offsetof(PhaseRec, th) % 16 == 0 && offsetof(PhasePlan, th) % 16 == 0 &&
+              offsetof(PhaseExt, th) % 16 == 0, "the chunks of key[] / th[] must not straddle");
 
 struct TableView {
     const TrajRec* recs;
     const Seg* segs;
     const Tile* tiles;
     int seg_slab;
-    int tile_slab;                  // > 0: slab or phase plan
+    int tile_slab;                  // > 0: slab plan
     const PhaseRec* phase;          // phase plan
+    const PhaseExt* phase_ext;
 };
 
-// Longest trajectory a phase plan accepts (sizes the tile slots of such a plan).
+// Longest trajectory a phase plan accepts (one CTA walks all of it).
 constexpr int kPhaseMaxSamples = 4096;
 
 constexpr int kSlabSpecSegs = 4;   // segments fetched speculatively with the record in a slab plan
