@@ -344,13 +344,18 @@ int tgx_set_plan_mode(tgx_engine* e, int exact_ramps);
  * a batch, later plans give every trajectory a fixed slice of the tables and need no counting pass and no scans; a
  * batch that does not fit falls back to the two-replay exact-offset path automatically.  allow = 0 disables it. */
 int tgx_set_slab_planning(tgx_engine* e, int allow);
-/* Phase planning (default on): a batch of Circle / Figure8 trajectories with at most 2 goal speeds, at most 4096
- * samples and phases of fewer than 2048 steps each is planned into ONE self-contained 160-byte record per trajectory
- * (where each phase starts, the replayed angle there, the constants of the parameter record) instead of segment
- * tables, and the evaluation kernel rebuilds from it exactly the segments the table path would have read — the same
- * bytes come out, with a tenth of the table traffic in the store-bound kernel.  The plan holds a copy of everything it
- * needs: d_params may be overwritten or freed as soon as tgx_plan returns, whichever path was taken.
- * Engaged automatically after a plan has seen such a batch; anything else is planned with segment tables. */
+/* Phase planning (default on): a batch of Circle / Figure8 trajectories with at most 2 goal speeds and at most 20
+ * segments and of plain Line trajectories, none longer than 4096 samples, is planned into ONE self-contained 256-byte
+ * record per trajectory (where each segment ends, the replayed state there, the constants of the parameter record;
+ * orbits of more than 12 segments keep the rest in a 96-byte extension row) instead of segment tables.  One CTA
+ * evaluates one trajectory: it rebuilds from the record exactly the segments the table path would have read — the same
+ * bytes come out, with a tenth of the table traffic in the store-bound kernel and no tile directory, however ragged the
+ * batch is.  The plan holds a copy of everything it needs: d_params may be overwritten or freed as soon as tgx_plan
+ * returns, whichever path was taken.
+ * Engaged automatically after a plan has seen such a batch; anything else (Boomerangs, more goal speeds, long
+ * trajectories) is planned with segment tables, and so are batches whose previous plan only fed tgx_feasibility: the
+ * reduction kernel is bound by instruction issue, not by HBM, and copying segments is cheaper for it than rebuilding
+ * them. */
 int tgx_set_phase_planning(tgx_engine* e, int allow);
 int64_t tgx_phase_plan_count(const tgx_engine* e);
 /* Store path of tgx_eval (default tma = 1): when the layout is regular (no per-trajectory offsets, all 14 channels,

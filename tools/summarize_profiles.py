@@ -98,7 +98,11 @@ extra = [("prof_rec_tma.ncu-rep", "ncu --set full -k regex:eval_kernel -s 3 -c 1
           "= 2.157e9 samples; writes 17 B per trajectory, FP64- / issue-bound"),
          ("prof_plan_fill.ncu-rep", "ncu --set full -k regex:plan_fill_kernel -s 3 -c 1 of `python bench.py --workload "
           "montecarlo_cfg4 --steps 2 --warmup 3 --no-cpu --no-e2e --n-per-gpu 1000000`: the replay that writes the segment "
-          "tables, 1 000 000 config-4 circles")]
+          "tables, 1 000 000 config-4 circles"),
+         ("prof_cfg3.ncu-rep", "ncu --set full --kernel-name-base demangled -k regex:tgx::eval_kernel|tgx::plan_phase_kernel -s 2 -c 2 "
+          "of `python bench.py --workload mixed_cfg3 --steps 1 --warmup 2 --no-cpu --no-e2e --no-extras --n-per-gpu 262144`: "
+          "config 3's mixed circle / line / figure-eight batch as phase records, one CTA per trajectory (97 .. 1889 samples), "
+          "and the phase planner on the class-sorted batch; algorithmic bytes 112 B/sample")]
 want2 = want + ["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
                 "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
                 "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
