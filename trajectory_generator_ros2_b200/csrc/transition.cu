@@ -10,6 +10,8 @@
 // in the reference's order (this file is compiled with -fmad=false; sqrt and division are correctly rounded; there is
 // no transcendental), which makes every record bit-identical to what the node publishes under perfect tracking.
 // Each tick's 128-byte record leaves the thread as four 32-byte (full-sector) streaming stores into the vehicle's row.
+// That store pattern — one line per vehicle per tick, as many row streams as vehicles — is what bounds the kernel: the
+// same stores with no arithmetic at all take 0.87 of its time (tools/wbw/streams.cu).
 #include <cuda_runtime.h>
 
 #include "tgx_internal.cuh"
@@ -96,13 +98,17 @@ transition_kernel(const tgx_transition_params* __restrict__ tparams, int64_t n, 
         for (int q = 0; q < 8; ++q) dst[q] = __ldg(src + q);
     }
     uint32_t st = 0;
-    int64_t k = 0;
+    // (32-bit tick counters: with 64-bit ones the compiler kept one of them in local memory and every tick reloaded it
+    //  behind the store traffic — the LDL and the compare that waits for it were half of ncu's stall samples)
+    int k = 0;
+    const int cap = rec_capacity > 0x7fffffffLL ? 0x7fffffff : (int)rec_capacity;
+    const int guard = max_samples > 0x7fffffffLL ? 0x7fffffff : (int)max_samples;
     if (!transition_ok(t)) {
         st = TGX_ST_BAD_PARAM;
     } else {
         GoalState g{t.start[0], t.start[1], t.start[2], t.start_v[0], t.start_v[1], t.start_psi, 0.0, true};
         tgx_goal_record* row = records ? records + i * rec_stride : nullptr;
-        const int64_t limit = t.ticks > 0 ? (int64_t)t.ticks : max_samples;
+        const int limit = t.ticks > 0 ? t.ticks : guard;
         double pose_z = g.pz;                       // perfect tracking: the pose is the previously published goal
         bool done = false;
         while (!done) {
@@ -169,13 +175,13 @@ transition_kernel(const tgx_transition_params* __restrict__ tparams, int64_t n, 
             }
             done = ends && t.ticks == 0;
             const bool last = done || (t.ticks > 0 && k + 1 == limit);
-            if (row && k < rec_capacity) store_record(row + k, g, (int)i, (int)k, clamped, last);
+            if (row && k < cap) store_record(row + k, g, (int)i, k, clamped, last);
             pose_z = g.pz;
             ++k;
         }
-        if (k > rec_capacity && records) st |= TGX_ST_TRUNCATED;
+        if (k > cap && records) st |= TGX_ST_TRUNCATED;
     }
-    if (counts) counts[i] = (int32_t)k;
+    if (counts) counts[i] = k;
     if (status) status[i] = st;
 }
 
