@@ -1053,6 +1053,39 @@ def test_phase_planning_of_lines_and_ragged_mixed_batches(engine, oracle):
     assert_samples_close(out2[-1, :, :c2[-1]], ref, "boomerang after phase fallback")
 
 
+def test_plans_that_only_feed_the_reduction_keep_to_segment_tables(engine, oracle):
+    """The consumer steers the kind of plan (speed only): after a plan that only fed tgx_feasibility the next plan is made
+    of segment tables — the reduction kernel is issue-bound and copies segments faster than it rebuilds them — and after
+    a plan whose samples were stored it is made of phase records again.  The maxima are the same bytes either way."""
+    params = workloads.montecarlo_cfg4(3000)
+    n = len(params)
+    lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
+    d = engine.upload_params(params)
+    engine.set_phase_planning(True)
+    for _ in range(3):
+        gpu_generate(engine, params, want_phases=False)            # learns; the samples are stored
+    seen = []
+
+    def sweep():
+        before = engine.phase_plan_count
+        engine.plan(d, limits=lim)
+        flags, mv, ma, st = engine.feasibility(lim, n)
+        seen.append((flags.cpu().numpy(), mv.cpu().numpy(), ma.cpu().numpy(), st.cpu().numpy()))
+        return engine.phase_plan_count - before
+
+    assert sweep() == 1                                            # the previous plan was stored: phase records
+    assert sweep() == 0 and sweep() == 0                           # the previous plans only fed the reduction: tables
+    gpu_generate(engine, params, want_phases=False)                # (still planned with tables; its samples are stored)
+    assert sweep() == 1
+    for other in seen[1:]:
+        for a, b in zip(seen[0], other):
+            np.testing.assert_array_equal(a, b)
+    o_flags, o_mv, o_ma, _, o_st = oracle.feasibility_batch(params, lim)
+    np.testing.assert_array_equal(seen[0][0], o_flags)
+    np.testing.assert_allclose(seen[0][1], o_mv, rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(seen[0][2], o_ma, rtol=1e-8, atol=1e-14)
+
+
 def test_results_do_not_depend_on_the_engines_history(engine, oracle):
     """the same parameters must give the same bytes whatever the engine planned before — first plan
     (count + scan + fill), fixed slices, phase records, ragged compaction, either tile size, either store path."""

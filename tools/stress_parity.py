@@ -4,8 +4,9 @@
     python tools/stress_parity.py [first_seed] [n_seeds]
 
 For every seed: a mixed circle / line / figure-eight batch and a polyline batch are planned three times (exact offsets,
-then fixed slices with the class-sorted replay), evaluated through the TMA and the vector-store path, packed into records
-by both record paths, and compared with the CPU oracle (counts exact, samples within the parity tolerances)."""
+fixed slices with the class-sorted replay, then — the mixed batch — phase records, one CTA per trajectory), evaluated through
+the TMA and the vector-store path, packed into records by both record paths, and compared with the CPU oracle (counts
+exact, samples within the parity tolerances); the three plans must write the same bytes."""
 import os
 import sys
 
@@ -57,6 +58,9 @@ for seed in range(first, first + count):
             got = eng.eval_records(n, cap, lim)
             torch.cuda.synchronize()
             assert torch.equal(got, want), (seed, family, rep, "record paths differ")
+        for rep in (1, 2):
+            assert torch.equal(torch.nan_to_num(outs[2 * rep], nan=-7.0), torch.nan_to_num(outs[0], nan=-7.0)), \
+                (seed, family, rep, "the planning path changed the samples")
         host = outs[-2].cpu().numpy()
         for i in rng.choice(n, size=40, replace=False):
             ref = (orc.generate(params[i:i + 1])[0] if family == "classic" else orc.polyline_generate(params[i:i + 1])[0])
@@ -65,5 +69,5 @@ for seed in range(first, first + count):
             assert (host[i, :, counts[i]:n4] == 0).all() and np.isnan(host[i, :, n4:]).all()
             checked += 1
         del outs
-    print(f"seed {seed}: n = {n} ok", flush=True)
+    print(f"seed {seed}: n = {n} ok (phase plans so far: {eng.phase_plan_count})", flush=True)
 print(f"stress parity ok: {count} seeds, {checked} trajectories compared with the oracle sample by sample")

@@ -446,13 +446,8 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         e->seg_slab = seg_slab;
         e->tile_slab = tile_slab;
         // phase records: every trajectory of the batch can be written as a PhaseRec (the fill pass checked)
-        // (dense or ragged: a phase plan has no tile slots, one CTA walks a whole trajectory).  Records that spill into
-        // PhaseExt rows cost their CTAs a second round of loads and a longer rebuild: worth it against the two dependent
-        // rounds of a ragged batch's work list, not against fixed slices (10^7 config-4 circles of up to 18 segments: slices
-        // 46.3 ms per step, phase records 47.2 ms — the reduction kernel is issue-bound and pays for the rebuild)
-        const bool spills = h_stats->max_nseg > tgx::kPhaseBaseSegs;
-        e->phase_ready = e->allow_phase && !e->exact_ramps && !h_stats->phase_misfit && h_stats->max_n > 0 &&
-                         !(spills && e->slabs_ready);
+        // (dense or ragged: a phase plan has no tile slots, one CTA walks a whole trajectory)
+        e->phase_ready = e->allow_phase && !e->exact_ramps && !h_stats->phase_misfit && h_stats->max_n > 0;
         e->mixed_batch = (h_stats->kinds & (h_stats->kinds - 1)) != 0;      // more than one replay class
     };
     e->plan_phase = false;
@@ -483,7 +478,7 @@ int plan_common(tgx_engine* e, const tgx_params* d_params, const double* d_stop_
         return TGX_OK;
     };
 
-    // ---- phase mode: batches of short orbits and plain lines.  One replay that writes a self-contained 240-byte record
+    // ---- phase mode: batches of short orbits and plain lines.  One replay that writes a self-contained 256-byte record
     //      per trajectory instead of tables; the evaluation kernel rebuilds the table path's segments from it, bit for
     //      bit, one CTA per trajectory ----
     if (e->allow_phase && e->phase_ready && !e->exact_ramps && !d_stop_from &&
