@@ -948,8 +948,14 @@ plan_count_kernel(const tgx_params* __restrict__ params, const double* __restric
 //       counting pass, no scans.  A trajectory that needs more than its slice sets stats->overflow (its extra
 //       records are dropped) and the host redoes the plan in exact-offset mode.  Unused tile slots are written as
 //       empty tiles (nseg = 0), which the evaluation kernel skips.
+// (CTAs of 128 threads per SM the replay is compiled for.  Round 1 found 8 — 64 registers, 1.4 KB of spill code — better
+//  than fewer spills; with the replay barriers and the reciprocal-based run lengths of round 2 the balance moved: config 4's
+//  plan, 10^7 circles: 8 CTAs 5.70 ms, 6: 5.57, 5 (96 registers, 0.2 KB of spills): 5.50, 4 (126 registers, none): 5.66)
+#ifndef TGX_FILL_CTAS
+#define TGX_FILL_CTAS 5
+#endif
 template <bool XR>
-__global__ void __launch_bounds__(128, 8)      // latency-bound replay: occupancy over spills (5.6 -> 5.0 ms, config 3)
+__global__ void __launch_bounds__(128, TGX_FILL_CTAS)
 plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict__ stop_from, int64_t n,
                  tgx_limits lim, int has_lim, int64_t max_samples, int tile_shift,
                  const CurTable* __restrict__ tab, const int32_t* __restrict__ plan_counts,
@@ -1013,8 +1019,12 @@ plan_fill_kernel(const tgx_params* __restrict__ params, const double* __restrict
 // evaluation CTA rebuilds the table path's Seg records from it (build_phase_segment, eval.cu) — the samples are the same
 // bits whichever way the batch was planned.  A trajectory that does not qualify sets stats->overflow and the host plans
 // the batch with segment tables.  `order`: see plan_fill_kernel.
-// (12 CTAs of 128 threads per SM: the replay is latency-bound, more resident warps beat fewer spills)
-__global__ void __launch_bounds__(128, 12)
+// (CTAs of 128 threads per SM, plan time per Mi trajectories of config 2 / config 3: 12 CTAs (40 registers, 2 KB of spill
+//  code) 0.68 / 1.12 ms, 8: 0.62 / 0.99, 6: 0.58 / 0.96, 5 (96 registers): 0.56 / 0.96, 4 (112 registers, no spills): 0.60)
+#ifndef TGX_PHASE_CTAS
+#define TGX_PHASE_CTAS 5
+#endif
+__global__ void __launch_bounds__(128, TGX_PHASE_CTAS)
 plan_phase_kernel(const tgx_params* __restrict__ params, int64_t n, tgx_limits lim, int has_lim,
                   int64_t max_samples, int tile_shift, int max_n, const CurTable* __restrict__ tab,
                   PhaseRec* __restrict__ phase, PhaseExt* __restrict__ phase_ext, int32_t* __restrict__ counts,
