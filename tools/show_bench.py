@@ -5,7 +5,8 @@ for path in sys.argv[1:]:
     d = json.load(open(path))
     print(path)
     print("  value %.2f G/s  ms/step %.3f  eval_ms %.3f  not_hidden %.3f  roofline.frac %.4f  launches %s" % (
-        d["value"] / 1e9, d["ms_per_step"], d["detail"].get("eval_ms_per_step", 0), d["detail"].get("not_hidden_ms_per_step", 0),
+        d["value"] / 1e9, d["ms_per_step"], d.get("detail", {}).get("eval_ms_per_step", 0),
+        d.get("detail", {}).get("not_hidden_ms_per_step", 0),
         d["roofline"].get("frac", 0), d.get("gpu_launches")))
     e = d.get("e2e")
     if e:
