@@ -1005,7 +1005,16 @@ def test_phase_planning_of_lines_and_ragged_mixed_batches(engine, oracle):
         engine.plan(d, limits=lim)
         _, mv, ma, fst = engine.feasibility(lim, n)
         recs = engine.eval_records(n, 1100, limits=lim)                 # (rows shorter than the longest trajectories)
+        # the fused store + reduce kernel (vector stores, the trajectory walked in passes) on the same plan
+        fused = torch.full(out.shape, float("nan"), dtype=torch.float64, device=d.device)
+        mv2, ma2 = torch.empty_like(mv), torch.empty_like(ma)
+        engine.eval(fused, max_v=mv2, max_a=ma2)
         torch.cuda.synchronize()
+        fused = fused.cpu().numpy()
+        assert (np.isnan(fused) == np.isnan(out)).all()
+        np.testing.assert_array_equal(fused[~np.isnan(out)], out[~np.isnan(out)])
+        np.testing.assert_array_equal(mv2.cpu().numpy(), mv.cpu().numpy())
+        np.testing.assert_array_equal(ma2.cpu().numpy(), ma.cpu().numpy())
         return took_phase, out, counts, status, ph, mv.cpu().numpy(), ma.cpu().numpy(), fst.cpu().numpy(), recs.cpu().numpy()
 
     try:
