@@ -1,6 +1,7 @@
 // eval.cu — the evaluation kernel of libtgx: create{Circle,Line,Figure8}Goal for every (trajectory, k).
 //
-// One CTA per Tile (tile_size consecutive samples of one trajectory).
+// One CTA per Tile (tile_size consecutive samples of one trajectory); phase plans (tgx_internal.cuh): one CTA per
+// trajectory, which it walks in passes, its Seg records rebuilt from the trajectory's 256-byte PhaseRec.
 // The CTA stages its trajectory's TrajRec (64 B) and the tile's Seg records (64 B each) in shared memory,
 // every thread finds the segment its samples fall in, evaluates the closed form of the reference's
 // recurrences inside that segment
