@@ -64,6 +64,32 @@ def test_vgoals_of_any_length_bit_exact(oracle, reference):
             assert abi.phases_to_index_msgs(kind, soph, stop_traj=True) == srmsgs
 
 
+def test_line_edge_cases_bit_exact(oracle, reference):
+    """The Line shapes the phase-record planner has special segments for (tests/test_gpu_parity.py holds the GPU to the
+    oracle on the same ones): no cruise at all (d2 < 0: the trajectory ends short of B and the node would exit, status
+    LINE_END_NOT_B), a ramp-up or a ramp-down of a single clamped step, a cruise longer than one rebase interval, A == B."""
+    cases = [
+        abi.line_params(1.0, [0, 0, 1], [0.3, 0.1, 1], [2.0], 1.0, 1.0, 0.01),
+        abi.line_params(1.0, [0, 0, 1], [3, 4, 1], [1.0], 200.0, 1.0, 0.01),
+        abi.line_params(1.0, [0, 0, 1], [3, 4, 1], [1.0], 1.0, 200.0, 0.01),
+        abi.line_params(1.0, [1, 1, 1], [-20, 1, 1], [1.0], 0.7, 0.9, 0.01),
+        abi.line_params(0.5, [2, -1, 0.5], [2, -1, 0.5], [1.0], 1.0, 1.0, 0.01),
+    ]
+    for p in cases:
+        o, ost, oph = oracle.generate(p)
+        r, rst, rmsgs = reference.generate(p)
+        assert ost == rst
+        assert o.shape == r.shape and o.shape[1] >= 2
+        if ost & abi.ST_FATAL_MASK:
+            # the reference exit(1)s at Line.cpp:71-79, before it would overwrite the last sample with B (:81-82): there is
+            # no published trajectory to compare; every sample before the last one still is the reference's
+            assert ost & abi.ST_LINE_END_NOT_B
+            assert ((o[:, :-1] + 0.0).view(np.uint64) == (r[:, :-1] + 0.0).view(np.uint64)).all()
+            continue
+        assert ((o + 0.0).view(np.uint64) == (r + 0.0).view(np.uint64)).all()
+        assert abi.phases_to_index_msgs(abi.TGX_LINE, oph) == rmsgs
+
+
 def test_bounds_and_feasibility_match(oracle, reference):
     params = abi.concat([workloads.montecarlo_cfg4(500), workloads.mixed_cfg3(300)])
     lim = abi.make_limits(**workloads.MONTECARLO_LIMITS)
