@@ -75,6 +75,12 @@ def test_line_edge_cases_bit_exact(oracle, reference):
         abi.line_params(1.0, [1, 1, 1], [-20, 1, 1], [1.0], 0.7, 0.9, 0.01),
         abi.line_params(0.5, [2, -1, 0.5], [2, -1, 0.5], [1.0], 1.0, 1.0, 0.01),
     ]
+    rng = np.random.default_rng(23)
+    for _ in range(40):                                  # any direction, length, speed and pair of accelerations
+        A = rng.uniform(-4, 4, 3)
+        B = A + rng.uniform(-6, 6, 3)
+        cases.append(abi.line_params(rng.uniform(0.5, 2), A, B, [rng.uniform(0.3, 2.5)], rng.uniform(0.3, 3),
+                                     rng.uniform(0.3, 3), 0.01))
     for p in cases:
         o, ost, oph = oracle.generate(p)
         r, rst, rmsgs = reference.generate(p)
